@@ -1,0 +1,528 @@
+// sbk_capi.cu -- implementation of the C ABI in include/sbk.h (host side, CUDA runtime).
+//
+// Host responsibilities: topology compilation (topology.cpp), the structure-of-arrays batched
+// State in HBM, stage bookkeeping that mirrors the reference's Stage checks, and kernel
+// launches on the batch's stream.  There is no CPU compute path: without a usable CUDA device
+// every compute entry point returns SBK_ERR_CUDA.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+
+#include "sbk.h"
+#include "topology.h"
+#include "sbk_kernels.cuh"
+
+using namespace sbkd;
+
+namespace {
+thread_local std::string g_lastError;
+int fail(int code, const std::string& msg) { g_lastError = msg; return code; }
+#define CUDA_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) \
+    return fail(SBK_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); } while (0)
+
+enum Stage { ST_EMPTY = 0, ST_POSITION = 1, ST_VELOCITY = 2, ST_ACCELERATION = 3 };
+} // namespace
+
+struct sbk_batch {
+    const sbk_topology* topo = nullptr;
+    int N = 0, device = 0, plan = 1;
+    cudaStream_t stream = nullptr; bool ownStream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    KArgs a;                      // device pointers + constants
+    unsigned char* dTables = nullptr;
+    double *dOpA = nullptr, *dOpB = nullptr, *dOpF = nullptr, *dOpOut = nullptr, *dScratch = nullptr;
+    size_t scratchDoubles = 0;
+    int stage = ST_EMPTY; bool abiValid = false, accelValid = false;
+    int64_t launches = 0, stepsTaken = 0, realizations = 0;
+    double lastKernelMs = 0;
+    long long recTotal = 0;
+};
+
+namespace {
+
+int useDevice(const sbk_batch* b) {
+    cudaError_t e = cudaSetDevice(b->device);
+    if (e != cudaSuccess) return fail(SBK_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    return SBK_OK;
+}
+int launch(sbk_batch* b, KernelOp op) {
+    CUDA_TRY(launchTpi(op, b->a, b->stream));
+    b->launches++;
+    return SBK_OK;
+}
+int ensureScratch(sbk_batch* b, size_t doubles) {
+    if (doubles <= b->scratchDoubles) return SBK_OK;
+    if (b->dScratch) cudaFree(b->dScratch);
+    b->dScratch = nullptr; b->scratchDoubles = 0;
+    CUDA_TRY(cudaMalloc(&b->dScratch, doubles*sizeof(double)));
+    b->scratchDoubles = doubles;
+    return SBK_OK;
+}
+// host SoA [rows][N] -> device
+int h2d(sbk_batch* b, double* dst, const double* src, size_t rows) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, rows*b->N*sizeof(double), cudaMemcpyHostToDevice, b->stream));
+    return SBK_OK;
+}
+int d2h(sbk_batch* b, double* dst, const double* src, size_t rows) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, rows*b->N*sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return SBK_OK;
+}
+int needStage(const sbk_batch* b, int st, const char* who) {
+    if (b->stage < st) {
+        static const char* names[] = {"Empty", "Position", "Velocity", "Acceleration"};
+        return fail(SBK_ERR_STAGE, std::string(who) + ": state must be realized to Stage::" + names[st] +
+                                   " (current: " + names[b->stage] + ")");
+    }
+    return SBK_OK;
+}
+} // namespace
+
+extern "C" {
+
+int sbk_version(void) { return SBK_VERSION; }
+const char* sbk_last_error(void) { return g_lastError.c_str(); }
+
+int sbk_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
+    }
+    return ok;
+}
+
+// ---- topology -----------------------------------------------------------------------------
+sbk_topology* sbk_topology_create(const sbk_body_desc* bodies, int nb, const sbk_force_desc* forces, int nf) {
+    if (!bodies || nb < 1 || nf < 0 || (nf > 0 && !forces)) { fail(SBK_ERR_ARG, "sbk_topology_create: bad arguments"); return nullptr; }
+    try {
+        sbk::ModelSpec spec; spec.name = "user";
+        spec.bodies.assign(bodies, bodies + nb);
+        if (nf) spec.forces.assign(forces, forces + nf);
+        sbk_topology* t = new sbk_topology();
+        try { sbk::compileTopology(spec, *t); } catch (...) { delete t; throw; }
+        return t;
+    } catch (const std::exception& e) { fail(SBK_ERR_TOPOLOGY, e.what()); return nullptr; }
+}
+sbk_topology* sbk_topology_from_text(const char* text) {
+    if (!text) { fail(SBK_ERR_ARG, "sbk_topology_from_text: null text"); return nullptr; }
+    try {
+        sbk::ModelSpec spec = sbk::fromText(text);
+        sbk_topology* t = new sbk_topology();
+        try { sbk::compileTopology(spec, *t); } catch (...) { delete t; throw; }
+        return t;
+    } catch (const std::exception& e) { fail(SBK_ERR_TOPOLOGY, e.what()); return nullptr; }
+}
+void sbk_topology_destroy(sbk_topology* t) { delete t; }
+int sbk_topology_counts(const sbk_topology* t, int* nb, int* nq, int* nu, int* nquat, int* nlevels) {
+    if (!t) return fail(SBK_ERR_ARG, "sbk_topology_counts: null topology");
+    if (nb) *nb = t->nb; if (nq) *nq = t->nq; if (nu) *nu = t->nu; if (nquat) *nquat = t->nquat; if (nlevels) *nlevels = t->nlevels;
+    return SBK_OK;
+}
+int sbk_topology_slots(const sbk_topology* t, int* q0, int* nq, int* u0, int* nu, int* level) {
+    if (!t) return fail(SBK_ERR_ARG, "sbk_topology_slots: null topology");
+    for (int b = 0; b < t->nb; ++b) {
+        if (q0) q0[b] = t->q0[b]; if (nq) nq[b] = t->nqOf[b]; if (u0) u0[b] = t->u0[b]; if (nu) nu[b] = t->nuOf[b];
+        if (level) level[b] = t->level[b];
+    }
+    return SBK_OK;
+}
+int sbk_model_text(const char* name, int n, char* buf, int cap) {
+    if (!name) { fail(SBK_ERR_ARG, "sbk_model_text: null name"); return -1; }
+    try {
+        const std::string s = sbk::toText(sbk::makeNamedModel(name, n));
+        if (buf && (int)s.size() + 1 <= cap) std::memcpy(buf, s.c_str(), s.size() + 1);
+        return (int)s.size() + 1;
+    } catch (const std::exception& e) { fail(SBK_ERR_ARG, e.what()); return -1; }
+}
+
+// ---- batch --------------------------------------------------------------------------------
+sbk_batch* sbk_batch_create(const sbk_topology* t, int n, int device, void* stream) {
+    if (!t || n < 1) { fail(SBK_ERR_ARG, "sbk_batch_create: bad arguments"); return nullptr; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        fail(SBK_ERR_CUDA, "sbk_batch_create: no usable CUDA device " + std::to_string(device) +
+                           " (this library has no CPU fallback)");
+        return nullptr;
+    }
+    sbk_batch* b = new sbk_batch();
+    b->topo = t; b->N = n; b->device = device;
+    auto bail = [&](const std::string& m) { fail(SBK_ERR_CUDA, m); sbk_batch_destroy(b); return (sbk_batch*)nullptr; };
+    if (cudaSetDevice(device) != cudaSuccess) return bail("cudaSetDevice failed");
+    if (stream) b->stream = (cudaStream_t)stream;
+    else { if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate failed"); b->ownStream = true; }
+    cudaEventCreate(&b->ev0); cudaEventCreate(&b->ev1);
+
+    // tables blob: bodies | children | forces, cache bases for the thread-per-instance plan
+    std::vector<BodyConst> bodies = t->bodies;
+    long long off = 0;
+    for (int i = 0; i < t->nb; ++i) { bodies[i].cacheBase = off*n; off += (i == 0) ? F_H : cacheRecordSize(t->nuOf[i]); }
+    for (int i = 0; i < t->nb; ++i) bodies[i].parentCacheBase = bodies[bodies[i].parent].cacheBase;
+    b->recTotal = off;
+    auto pad16 = [](size_t x) { return (x + 15)/16*16; };
+    const size_t bodiesBytes = pad16(bodies.size()*sizeof(BodyConst));
+    const size_t childBytes  = pad16(t->children.size()*sizeof(int));
+    const size_t forceBytes  = pad16(t->forces.size()*sizeof(ForceConst));
+    std::vector<unsigned char> blob(bodiesBytes + childBytes + forceBytes, 0);
+    std::memcpy(blob.data(), bodies.data(), bodies.size()*sizeof(BodyConst));
+    std::memcpy(blob.data() + bodiesBytes, t->children.data(), t->children.size()*sizeof(int));
+    std::memcpy(blob.data() + bodiesBytes + childBytes, t->forces.data(), t->forces.size()*sizeof(ForceConst));
+
+    KArgs& a = b->a; std::memset(&a, 0, sizeof a);
+    a.tableBytes = (uint32_t)blob.size(); a.childrenOff = (uint32_t)bodiesBytes; a.forcesOff = (uint32_t)(bodiesBytes + childBytes);
+    a.stageInSmem = blob.size() <= 96*1024 ? 1u : 0u;
+    a.nb = t->nb; a.nq = t->nq; a.nu = t->nu; a.nquat = t->nquat;
+    a.gx = t->grav[0]; a.gy = t->grav[1]; a.gz = t->grav[2];
+    a.N = n;
+    const size_t ny = (size_t)t->nq + t->nu, N = (size_t)n;
+    bool ok = true;
+    auto dalloc = [&](double** p, size_t doubles) { if (ok && cudaMalloc(p, std::max<size_t>(doubles, 1)*sizeof(double)) != cudaSuccess) ok = false;
+                                                    if (ok) cudaMemsetAsync(*p, 0, std::max<size_t>(doubles, 1)*sizeof(double), b->stream); };
+    if (cudaMalloc(&b->dTables, blob.size()) != cudaSuccess) return bail("cudaMalloc(tables) failed");
+    cudaMemcpyAsync(b->dTables, blob.data(), blob.size(), cudaMemcpyHostToDevice, b->stream);
+    cudaStreamSynchronize(b->stream);
+    a.tables = b->dTables;
+    dalloc(&a.cache, (size_t)off*N);
+    dalloc(&a.y, ny*N); dalloc(&a.ydot, ny*N); dalloc(&a.qdotdot, (size_t)t->nq*N); dalloc(&a.qerr, (size_t)std::max(t->nquat, 1)*N);
+    dalloc(&a.y0, ny*N); dalloc(&a.f0, ny*N); dalloc(&a.fa, ny*N); dalloc(&a.fb, ny*N); dalloc(&a.ys, ny*N);
+    dalloc(&a.tcur, N); dalloc(&a.errNorm, N);
+    dalloc(&b->dOpA, (size_t)t->nu*N); dalloc(&b->dOpB, (size_t)t->nu*N); dalloc(&b->dOpOut, (size_t)t->nu*N); dalloc(&b->dOpF, (size_t)t->nb*6*N);
+    if (ok && cudaMalloc(&a.status, N*sizeof(int)) != cudaSuccess) ok = false;
+    if (ok && cudaMalloc(&a.projCount, N*sizeof(int)) != cudaSuccess) ok = false;
+    if (!ok) return bail(std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
+    cudaMemsetAsync(a.status, 0, N*sizeof(int), b->stream);
+    cudaMemsetAsync(a.projCount, 0, N*sizeof(int), b->stream);
+    // default state: q = 0 except quaternions (1,0,0,0), like the reference's default State
+    if (t->nquat) {
+        std::vector<double> q0((size_t)t->nq*N, 0.0);
+        for (int i = 0; i < t->nb; ++i) if (t->quatIndex[i] >= 0) for (size_t k = 0; k < N; ++k) q0[(size_t)t->q0[i]*N + k] = 1.0;
+        cudaMemcpyAsync(a.y, q0.data(), q0.size()*sizeof(double), cudaMemcpyHostToDevice, b->stream);
+        cudaStreamSynchronize(b->stream);
+    }
+    if (launchInitGround(a.cache, n, b->stream) != cudaSuccess) return bail("init kernel launch failed");
+    b->launches++;
+    if (cudaStreamSynchronize(b->stream) != cudaSuccess) return bail(std::string("batch init failed: ") + cudaGetErrorString(cudaGetLastError()));
+    sbk_rkm_opts o; sbk_rkm_default_opts(&o);
+    a.accuracy = o.accuracy; a.consTol = o.constraint_tol;
+    return b;
+}
+void sbk_batch_destroy(sbk_batch* b) {
+    if (!b) return;
+    cudaSetDevice(b->device);
+    KArgs& a = b->a;
+    void* ptrs[] = {b->dTables, a.cache, a.y, a.ydot, a.qdotdot, a.qerr, a.y0, a.f0, a.fa, a.fb, a.ys, a.tcur, a.errNorm,
+                    b->dOpA, b->dOpB, b->dOpOut, b->dOpF, a.status, a.projCount, b->dScratch};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (b->ev0) cudaEventDestroy(b->ev0); if (b->ev1) cudaEventDestroy(b->ev1);
+    if (b->ownStream && b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+}
+int sbk_batch_size(const sbk_batch* b) { return b ? b->N : 0; }
+int sbk_batch_set_plan(sbk_batch* b, int plan) {
+    if (!b) return fail(SBK_ERR_ARG, "null batch");
+    if (plan != 0 && plan != 1) return fail(SBK_ERR_ARG, "sbk_batch_set_plan: only plan 0 (auto) and 1 (thread-per-instance) are available in this build");
+    b->plan = 1; return SBK_OK;
+}
+int sbk_batch_get_plan(const sbk_batch* b) { return b ? b->plan : 0; }
+int sbk_synchronize(sbk_batch* b) {
+    if (!b) return fail(SBK_ERR_ARG, "null batch");
+    if (int rc = useDevice(b)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return SBK_OK;
+}
+
+// ---- state ----------------------------------------------------------------------------------
+static void invalidate(sbk_batch* b) { b->stage = ST_EMPTY; b->abiValid = false; b->accelValid = false; }
+
+int sbk_set_state(sbk_batch* b, const double* q, const double* u, const double* t) {
+    if (!b) return fail(SBK_ERR_ARG, "null batch");
+    if (int rc = useDevice(b)) return rc;
+    const sbk_topology* T = b->topo;
+    if (q) if (int rc = h2d(b, b->a.y, q, T->nq)) return rc;
+    if (u) if (int rc = h2d(b, b->a.y + (size_t)T->nq*b->N, u, T->nu)) return rc;
+    if (t) CUDA_TRY(cudaMemcpyAsync(b->a.tcur, t, (size_t)b->N*sizeof(double), cudaMemcpyHostToDevice, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));   // the host buffers may be reused by the caller
+    invalidate(b);
+    return SBK_OK;
+}
+int sbk_get_state(sbk_batch* b, double* q, double* u, double* t) {
+    if (!b) return fail(SBK_ERR_ARG, "null batch");
+    if (int rc = useDevice(b)) return rc;
+    const sbk_topology* T = b->topo;
+    if (q) CUDA_TRY(cudaMemcpyAsync(q, b->a.y, (size_t)T->nq*b->N*sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    if (u) CUDA_TRY(cudaMemcpyAsync(u, b->a.y + (size_t)T->nq*b->N, (size_t)T->nu*b->N*sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    if (t) CUDA_TRY(cudaMemcpyAsync(t, b->a.tcur, (size_t)b->N*sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return SBK_OK;
+}
+int sbk_set_state_aos(sbk_batch* b, const double* q, const double* u) {
+    if (!b) return fail(SBK_ERR_ARG, "null batch");
+    if (int rc = useDevice(b)) return rc;
+    const sbk_topology* T = b->topo; const int N = b->N;
+    if (int rc = ensureScratch(b, (size_t)std::max(T->nq, T->nu)*N)) return rc;
+    if (q) {
+        CUDA_TRY(cudaMemcpyAsync(b->dScratch, q, (size_t)T->nq*N*sizeof(double), cudaMemcpyHostToDevice, b->stream));
+        CUDA_TRY(launchTranspose(b->dScratch, b->a.y, N, T->nq, b->stream)); b->launches++;
+    }
+    if (u) {
+        CUDA_TRY(cudaMemcpyAsync(b->dScratch, u, (size_t)T->nu*N*sizeof(double), cudaMemcpyHostToDevice, b->stream));
+        CUDA_TRY(launchTranspose(b->dScratch, b->a.y + (size_t)T->nq*N, N, T->nu, b->stream)); b->launches++;
+    }
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    invalidate(b);
+    return SBK_OK;
+}
+int sbk_get_state_aos(sbk_batch* b, double* q, double* u) {
+    if (!b) return fail(SBK_ERR_ARG, "null batch");
+    if (int rc = useDevice(b)) return rc;
+    const sbk_topology* T = b->topo; const int N = b->N;
+    if (int rc = ensureScratch(b, (size_t)std::max(T->nq, T->nu)*N)) return rc;
+    if (q) {
+        CUDA_TRY(launchTranspose(b->a.y, b->dScratch, T->nq, N, b->stream)); b->launches++;
+        CUDA_TRY(cudaMemcpyAsync(q, b->dScratch, (size_t)T->nq*N*sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+        CUDA_TRY(cudaStreamSynchronize(b->stream));
+    }
+    if (u) {
+        CUDA_TRY(launchTranspose(b->a.y + (size_t)T->nq*N, b->dScratch, T->nu, N, b->stream)); b->launches++;
+        CUDA_TRY(cudaMemcpyAsync(u, b->dScratch, (size_t)T->nu*N*sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+        CUDA_TRY(cudaStreamSynchronize(b->stream));
+    }
+    return SBK_OK;
+}
+int sbk_state_device_ptrs(sbk_batch* b, double** q, double** u, double** t) {
+    if (!b) return fail(SBK_ERR_ARG, "null batch");
+    if (q) *q = b->a.y; if (u) *u = b->a.y + (size_t)b->topo->nq*b->N; if (t) *t = b->a.tcur;
+    return SBK_OK;
+}
+int sbk_state_touched(sbk_batch* b) { if (!b) return fail(SBK_ERR_ARG, "null batch"); invalidate(b); return SBK_OK; }
+
+// ---- realize ----------------------------------------------------------------------------------
+static int realizeKin(sbk_batch* b, int toStage) {
+    if (int rc = useDevice(b)) return rc;
+    if (b->stage < ST_POSITION) {
+        if (int rc = launch(b, OP_KIN)) return rc;
+        b->abiValid = false; b->accelValid = false;
+    }
+    if (b->stage < toStage) b->stage = toStage;
+    return SBK_OK;
+}
+int sbk_realize_position(sbk_batch* b) { if (!b) return fail(SBK_ERR_ARG, "null batch"); return realizeKin(b, ST_POSITION); }
+int sbk_realize_velocity(sbk_batch* b) { if (!b) return fail(SBK_ERR_ARG, "null batch"); return realizeKin(b, ST_VELOCITY); }
+int sbk_realize_articulated_body_inertias(sbk_batch* b) {
+    if (!b) return fail(SBK_ERR_ARG, "null batch");
+    if (int rc = realizeKin(b, ST_POSITION)) return rc;
+    if (!b->abiValid) { if (int rc = launch(b, OP_ABI)) return rc; b->abiValid = true; }
+    return SBK_OK;
+}
+int sbk_realize_acceleration(sbk_batch* b) {
+    if (!b) return fail(SBK_ERR_ARG, "null batch");
+    if (int rc = useDevice(b)) return rc;
+    if (b->stage == ST_ACCELERATION && b->accelValid) return SBK_OK;
+    // one fused launch: kinematics + forces + ABI + both acceleration sweeps
+    b->a.fmobOut = b->dOpA; b->a.FbodyOut = b->dOpF;
+    CUDA_TRY(cudaMemsetAsync(b->dOpF, 0, (size_t)6*b->N*sizeof(double), b->stream));   // Ground row
+    int rc = launch(b, OP_EVAL);
+    b->a.fmobOut = nullptr; b->a.FbodyOut = nullptr;
+    if (rc) return rc;
+    b->stage = ST_ACCELERATION; b->abiValid = true; b->accelValid = true; b->realizations++;
+    return SBK_OK;
+}
+
+// ---- getters ----------------------------------------------------------------------------------
+int sbk_get_udot(sbk_batch* b, double* udot) {
+    if (!b || !udot) return fail(SBK_ERR_ARG, "sbk_get_udot: null argument");
+    if (int rc = useDevice(b)) return rc;
+    if (int rc = needStage(b, ST_ACCELERATION, "sbk_get_udot")) return rc;
+    return d2h(b, udot, b->a.ydot + (size_t)b->topo->nq*b->N, b->topo->nu);
+}
+int sbk_get_qdot(sbk_batch* b, double* qdot) {
+    if (!b || !qdot) return fail(SBK_ERR_ARG, "sbk_get_qdot: null argument");
+    if (int rc = useDevice(b)) return rc;
+    if (int rc = needStage(b, ST_VELOCITY, "sbk_get_qdot")) return rc;
+    return d2h(b, qdot, b->a.ydot, b->topo->nq);
+}
+int sbk_get_qdotdot(sbk_batch* b, double* qdd) {
+    if (!b || !qdd) return fail(SBK_ERR_ARG, "sbk_get_qdotdot: null argument");
+    if (int rc = useDevice(b)) return rc;
+    if (int rc = needStage(b, ST_ACCELERATION, "sbk_get_qdotdot")) return rc;
+    return d2h(b, qdd, b->a.qdotdot, b->topo->nq);
+}
+int sbk_get_qerr(sbk_batch* b, double* qerr) {
+    if (!b || !qerr) return fail(SBK_ERR_ARG, "sbk_get_qerr: null argument");
+    if (int rc = useDevice(b)) return rc;
+    if (int rc = needStage(b, ST_POSITION, "sbk_get_qerr")) return rc;
+    if (b->topo->nquat == 0) return SBK_OK;
+    return d2h(b, qerr, b->a.qerr, b->topo->nquat);
+}
+static int getBodyField(sbk_batch* b, int field, int width, double* out, int st, const char* who) {
+    if (!b || !out) return fail(SBK_ERR_ARG, std::string(who) + ": null argument");
+    if (int rc = useDevice(b)) return rc;
+    if (int rc = needStage(b, st, who)) return rc;
+    const size_t rows = (size_t)b->topo->nb*width;
+    if (int rc = ensureScratch(b, rows*b->N)) return rc;
+    CUDA_TRY(launchGatherBodyField(b->a, field, width, b->dScratch, b->stream)); b->launches++;
+    return d2h(b, out, b->dScratch, rows);
+}
+int sbk_get_body_transforms(sbk_batch* b, double* X)  { return getBodyField(b, F_XGB, 12, X, ST_POSITION, "sbk_get_body_transforms"); }
+int sbk_get_body_velocities(sbk_batch* b, double* V)  { return getBodyField(b, F_VGB, 6, V, ST_VELOCITY, "sbk_get_body_velocities"); }
+int sbk_get_body_accelerations(sbk_batch* b, double* A) {
+    if (b && !b->accelValid) return fail(SBK_ERR_STAGE, "sbk_get_body_accelerations: accelerations are not realized");
+    return getBodyField(b, F_AGB, 6, A, ST_ACCELERATION, "sbk_get_body_accelerations");
+}
+int sbk_get_applied_forces(sbk_batch* b, double* fmob, double* Fbody) {
+    if (!b) return fail(SBK_ERR_ARG, "null batch");
+    if (int rc = useDevice(b)) return rc;
+    if (int rc = needStage(b, ST_ACCELERATION, "sbk_get_applied_forces")) return rc;
+    if (!b->accelValid) return fail(SBK_ERR_STAGE, "sbk_get_applied_forces: forces were overwritten by an operator call; realize again");
+    if (fmob)  if (int rc = d2h(b, fmob, b->dOpA, b->topo->nu)) return rc;
+    if (Fbody) if (int rc = d2h(b, Fbody, b->dOpF, (size_t)b->topo->nb*6)) return rc;
+    return SBK_OK;
+}
+
+// ---- operators --------------------------------------------------------------------------------
+int sbk_calc_acceleration(sbk_batch* b, const double* fmob, const double* Fbody, double* udot, double* A_GB) {
+    if (!b) return fail(SBK_ERR_ARG, "null batch");
+    if (int rc = useDevice(b)) return rc;
+    if (int rc = needStage(b, ST_VELOCITY, "sbk_calc_acceleration")) return rc;
+    if (!b->abiValid) { if (int rc = launch(b, OP_ABI)) return rc; b->abiValid = true; }
+    b->accelValid = false;
+    if (fmob)  if (int rc = h2d(b, b->dOpB, fmob, b->topo->nu)) return rc;
+    if (Fbody) if (int rc = h2d(b, b->dOpF, Fbody, (size_t)b->topo->nb*6)) return rc;
+    b->a.fmobIn = fmob ? b->dOpB : nullptr; b->a.FbodyIn = Fbody ? b->dOpF : nullptr; b->a.vecOut = b->dOpOut;
+    int rc = launch(b, OP_CALCACC);
+    b->a.fmobIn = nullptr; b->a.FbodyIn = nullptr; b->a.vecOut = nullptr;
+    if (rc) return rc;
+    if (udot) if (int rc2 = d2h(b, udot, b->dOpOut, b->topo->nu)) return rc2;
+    if (A_GB) {
+        const size_t rows = (size_t)b->topo->nb*6;
+        if (int rc2 = ensureScratch(b, rows*b->N)) return rc2;
+        CUDA_TRY(launchGatherBodyField(b->a, F_AGB, 6, b->dScratch, b->stream)); b->launches++;
+        if (int rc2 = d2h(b, A_GB, b->dScratch, rows)) return rc2;
+    }
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return SBK_OK;
+}
+int sbk_multiply_by_M(sbk_batch* b, const double* v, double* Mv) {
+    if (!b || !v || !Mv) return fail(SBK_ERR_ARG, "sbk_multiply_by_M: null argument");
+    if (int rc = useDevice(b)) return rc;
+    if (int rc = needStage(b, ST_POSITION, "sbk_multiply_by_M")) return rc;
+    b->accelValid = false;
+    if (int rc = h2d(b, b->dOpB, v, b->topo->nu)) return rc;
+    b->a.vecIn = b->dOpB; b->a.vecOut = b->dOpOut;
+    int rc = launch(b, OP_MULM);
+    b->a.vecIn = nullptr; b->a.vecOut = nullptr;
+    if (rc) return rc;
+    return d2h(b, Mv, b->dOpOut, b->topo->nu);
+}
+int sbk_multiply_by_MInv(sbk_batch* b, const double* v, double* MinvV) {
+    if (!b || !v || !MinvV) return fail(SBK_ERR_ARG, "sbk_multiply_by_MInv: null argument");
+    if (int rc = useDevice(b)) return rc;
+    if (int rc = needStage(b, ST_POSITION, "sbk_multiply_by_MInv")) return rc;
+    if (!b->abiValid) { if (int rc = launch(b, OP_ABI)) return rc; b->abiValid = true; }   // lazy, like the reference
+    b->accelValid = false;
+    if (int rc = h2d(b, b->dOpB, v, b->topo->nu)) return rc;
+    b->a.vecIn = b->dOpB; b->a.vecOut = b->dOpOut;
+    int rc = launch(b, OP_MULMINV);
+    b->a.vecIn = nullptr; b->a.vecOut = nullptr;
+    if (rc) return rc;
+    return d2h(b, MinvV, b->dOpOut, b->topo->nu);
+}
+int sbk_calc_residual_force(sbk_batch* b, const double* fmob, const double* Fbody, const double* knownUdot, double* residual) {
+    if (!b || !residual) return fail(SBK_ERR_ARG, "sbk_calc_residual_force: null argument");
+    if (int rc = useDevice(b)) return rc;
+    if (int rc = needStage(b, ST_VELOCITY, "sbk_calc_residual_force")) return rc;
+    b->accelValid = false;
+    if (fmob)      if (int rc = h2d(b, b->dOpA, fmob, b->topo->nu)) return rc;
+    if (knownUdot) if (int rc = h2d(b, b->dOpB, knownUdot, b->topo->nu)) return rc;
+    if (Fbody)     if (int rc = h2d(b, b->dOpF, Fbody, (size_t)b->topo->nb*6)) return rc;
+    b->a.fmobIn = fmob ? b->dOpA : nullptr; b->a.FbodyIn = Fbody ? b->dOpF : nullptr;
+    b->a.vecIn = knownUdot ? b->dOpB : nullptr; b->a.vecOut = b->dOpOut;
+    int rc = launch(b, OP_RESID);
+    b->a.fmobIn = nullptr; b->a.FbodyIn = nullptr; b->a.vecIn = nullptr; b->a.vecOut = nullptr;
+    if (rc) return rc;
+    return d2h(b, residual, b->dOpOut, b->topo->nu);
+}
+
+// ---- integrator -------------------------------------------------------------------------------
+void sbk_rkm_default_opts(sbk_rkm_opts* o) {
+    if (!o) return;
+    o->accuracy = 1e-3; o->constraint_tol = 1e-4; o->use_infinity_norm = 0; o->project_every_step = 0;
+}
+int sbk_rkm_step(sbk_batch* b, double h, int nsteps, const sbk_rkm_opts* opts, double* errNorm) {
+    if (!b) return fail(SBK_ERR_ARG, "null batch");
+    if (!(h > 0) || nsteps < 0) return fail(SBK_ERR_ARG, "sbk_rkm_step: need h > 0 and nsteps >= 0");
+    if (int rc = useDevice(b)) return rc;
+    sbk_rkm_opts o; sbk_rkm_default_opts(&o);
+    if (opts) { o = *opts; if (!(o.accuracy > 0)) o.accuracy = 1e-3; if (!(o.constraint_tol > 0)) o.constraint_tol = o.accuracy/10; }
+    KArgs& a = b->a;
+    a.h = h; a.nsteps = nsteps; a.accuracy = o.accuracy; a.consTol = o.constraint_tol;
+    a.useInfNorm = o.use_infinity_norm; a.projectEveryStep = o.project_every_step;
+    if (nsteps > 0) {
+        CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
+        if (int rc = launch(b, OP_RKM)) return rc;
+        CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
+        invalidate(b);
+        b->stepsTaken += (int64_t)nsteps*b->N; b->realizations += (int64_t)5*nsteps*b->N;
+    }
+    if (errNorm) {
+        CUDA_TRY(cudaMemcpyAsync(errNorm, a.errNorm, (size_t)b->N*sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+        CUDA_TRY(cudaStreamSynchronize(b->stream));
+    }
+    return SBK_OK;
+}
+int sbk_rkm_stats(sbk_batch* b, int64_t* steps, int64_t* realizations, int64_t* qproj) {
+    if (!b) return fail(SBK_ERR_ARG, "null batch");
+    if (int rc = useDevice(b)) return rc;
+    if (steps) *steps = b->stepsTaken; if (realizations) *realizations = b->realizations;
+    if (qproj) {
+        std::vector<int> h(b->N);
+        CUDA_TRY(cudaMemcpyAsync(h.data(), b->a.projCount, (size_t)b->N*sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+        CUDA_TRY(cudaStreamSynchronize(b->stream));
+        int64_t s = 0; for (int v : h) s += v; *qproj = s;
+    }
+    return SBK_OK;
+}
+int sbk_get_status(sbk_batch* b, int32_t* status, int64_t* nbad) {
+    if (!b) return fail(SBK_ERR_ARG, "null batch");
+    if (int rc = useDevice(b)) return rc;
+    std::vector<int> h(b->N);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), b->a.status, (size_t)b->N*sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    int64_t bad = 0; for (int k = 0; k < b->N; ++k) { if (h[k]) ++bad; if (status) status[k] = h[k]; }
+    if (nbad) *nbad = bad;
+    return SBK_OK;
+}
+int64_t sbk_launch_count(const sbk_batch* b) { return b ? b->launches : 0; }
+double sbk_last_kernel_ms(const sbk_batch* b) {
+    if (!b || !b->ev0 || !b->ev1) return 0;
+    cudaSetDevice(b->device);
+    if (cudaEventSynchronize(b->ev1) != cudaSuccess) { cudaGetLastError(); return 0; }
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, b->ev0, b->ev1) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return ms;
+}
+
+// FP64 roofline probe (bench only): executes blocks*threads*iters*8 DFMAs on the batch's device.
+int sbk_dfma_probe(int device, int blocks, int threads, int iters, double* ms_out) {
+    if (cudaSetDevice(device) != cudaSuccess) return fail(SBK_ERR_CUDA, "cudaSetDevice failed");
+    double* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, (size_t)blocks*threads*sizeof(double)));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    launchDfmaProbe(d, 16, blocks, threads, 0);            // warm-up
+    cudaEventRecord(e0, 0);
+    cudaError_t le = launchDfmaProbe(d, iters, blocks, threads, 0);
+    cudaEventRecord(e1, 0);
+    cudaError_t se = cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    if (le != cudaSuccess || se != cudaSuccess) return fail(SBK_ERR_CUDA, "dfma probe failed");
+    if (ms_out) *ms_out = ms;
+    return SBK_OK;
+}
+
+} // extern "C"

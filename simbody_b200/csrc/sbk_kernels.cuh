@@ -1,0 +1,56 @@
+// sbk_kernels.cuh -- kernel argument block and launch wrappers (implemented in sbk_kernels.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "sbk_rkm.cuh"
+
+namespace sbkd {
+
+// Batch-shared tables live in ONE contiguous device blob so that a CTA stages them into shared
+// memory with a single TMA bulk copy (cp.async.bulk + mbarrier):
+//   [ BodyConst[nb] | int children[...] (16B padded) | ForceConst forces[...] (16B padded) ]
+struct KArgs {
+    const unsigned char* tables;     // device blob
+    uint32_t tableBytes, childrenOff, forcesOff, stageInSmem;
+    int nb, nq, nu, nquat;
+    double gx, gy, gz;
+    int N;
+    double* cache;
+    double* y;          // state [nq+nu][N]
+    double* ydot;       // [nq+nu][N] (qdot, udot)
+    double* qdotdot;    // [nq][N]
+    double* qerr;       // [nquat][N]
+    const double* fmobIn; const double* FbodyIn;
+    double* fmobOut; double* FbodyOut;
+    const double* vecIn; double* vecOut;
+    int* status;
+    // RKM
+    double* y0; double* f0; double* fa; double* fb; double* ys;
+    double* tcur;       // [N] time
+    double h; int nsteps;
+    double accuracy, consTol; int useInfNorm, projectEveryStep;
+    double* errNorm;    // [N]
+    int* projCount;     // [N] accumulated
+};
+
+enum KernelOp {
+    OP_KIN = 0,        // sweeps A+B
+    OP_ABI,            // sweep C (+ZB)
+    OP_EVAL,           // full realize(Acceleration)
+    OP_CALCACC,        // sweeps D+E with caller forces
+    OP_MULM, OP_MULMINV, OP_RESID,
+    OP_RKM
+};
+
+// Launch one operation for the thread-per-instance plan on `stream`.
+cudaError_t launchTpi(KernelOp op, const KArgs& a, cudaStream_t stream);
+// Ground record (identity transform, zero velocity/acceleration) for every instance.
+cudaError_t launchInitGround(double* cache, int N, cudaStream_t stream);
+// dst[k*len + i] <-> src[i*N + k]
+cudaError_t launchTranspose(const double* src, double* dst, int rows, int cols, cudaStream_t stream);
+// Gather one per-body cache field (width doubles at field offset) into out[(b*width+i)*N + k].
+cudaError_t launchGatherBodyField(const KArgs& a, int fieldOffset, int width, double* out, cudaStream_t stream);
+// FP64 FMA throughput probe: returns flops executed; used by bench.py to measure the FP64 roofline.
+cudaError_t launchDfmaProbe(double* out, int iters, int blocks, int threads, cudaStream_t stream);
+
+} // namespace sbkd

@@ -1,0 +1,36 @@
+// topology.h -- host-side topology compiler: ModelSpec -> flat body table.
+//
+// Replaces the parts of SimbodyMatterSubsystemRep::endConstruction
+// (Simbody/src/SimbodyMatterSubsystemRep.cpp:256-330) that the hot path needs:
+//   * q/u slot assignment in MobilizedBodyIndex order using max-nq per mobilizer
+//     (RigidBodyNodeSpec.h:81-87, SimbodyMatterSubsystemRep.cpp:270-293,537-571);
+//   * level of each body and level-ordered body lists (rbNodeLevels,
+//     SimbodyMatterSubsystemRep.h:1366);
+//   * children lists in creation order (RigidBodyNode::children);
+//   * X_MB = ~X_BM precomputed once (RigidBodyNode.h:1012);
+//   * per-body lists of mobility force elements in force-index order.
+#pragma once
+#include <string>
+#include <vector>
+#include "sbk.h"
+#include "sbk_sweeps.cuh"
+#include "../host/model_spec.h"
+
+struct sbk_topology {
+    sbk::ModelSpec spec;
+    int nb = 0, nq = 0, nu = 0, nquat = 0, nlevels = 0;
+    std::vector<int> q0, nqOf, u0, nuOf, level, quatIndex;
+    std::vector<sbkd::BodyConst>  bodies;     // cacheBase fields filled per batch/plan
+    std::vector<int>              children;   // concatenated child lists
+    std::vector<sbkd::ForceConst> forces;     // concatenated per-body mobility force lists
+    std::vector<int>              levelOrder; // body indices sorted by level (stable)
+    std::vector<int>              levelStart; // nlevels+1 offsets into levelOrder
+    double grav[3] = {0, 0, 0};
+    int maxLevelWidth = 0;
+    bool isChain = false;                      // every body's parent is the previous body
+};
+
+namespace sbk {
+// Throws std::runtime_error with a message on invalid input.
+void compileTopology(const ModelSpec& spec, sbk_topology& out);
+}

@@ -1,0 +1,139 @@
+// lower_simbody.h -- lower a realized SimTK::MultibodySystem into a sbk::ModelSpec
+// (the flat body table + force list that sbk_topology_create consumes).
+//
+// This is the piece a Simbody user adds to switch the hot path to the B200 engine: build
+// the system exactly as before, call system.realizeTopology(), then
+//     sbk::ModelSpec spec = sbk::lowerSimbodySystem(system, matter, forces);
+//     sbk_topology* topo = sbk_topology_create(spec.bodies.data(), spec.bodies.size(), ...);
+// Only the PUBLIC Simbody API is used:
+//   SimbodyMatterSubsystem::getNumBodies / getMobilizedBody
+//   MobilizedBody::getParentMobilizedBody (MobilizedBody.h:1627), getDefaultInboardFrame /
+//   getDefaultOutboardFrame (:1605,:1609), getDefaultMassProperties (:1556),
+//   MobilizedBody::Pin::isInstanceOf etc. (SimTKcommon PrivateImplementation.h:348),
+//   Force::Gravity::getDefaultDownDirection / getDefaultMagnitude (Force_Gravity.h:276-278),
+//   Force::MobilityLinearSpring::getDefaultStiffness / getDefaultQZero
+//   (Force_MobilityLinearSpring.h:109,113), Force::MobilityLinearDamper::getDefaultDamping
+//   (Force_MobilityLinearDamper.h:87).
+// The spring/damper classes do not expose WHICH mobility they act on, so it is recovered by
+// probing Force::calcForceContribution (Force.h:130) at a state where every q-q0 (resp. u)
+// is non-zero: exactly one mobility force entry is non-zero.
+//
+// Requires the Simbody headers; it is compiled only into programs that link Simbody
+// (oracle/ref_driver.cpp here, the user's program in production).  Unsupported features
+// (other mobilizers, reversed mobilizers, constraints, other force types, Euler-angle mode)
+// raise std::runtime_error rather than being silently dropped.
+#pragma once
+#include <string>
+#include "Simbody.h"
+#include "simbody_b200/host/model_spec.h"
+
+namespace sbk {
+
+inline void lowerTransform(const SimTK::Transform& X, double out[12]) {
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) out[3*i+j] = X.R()[i][j];
+    for (int i = 0; i < 3; ++i) out[9+i] = X.p()[i];
+}
+
+inline ModelSpec lowerSimbodySystem(const SimTK::MultibodySystem&        system,
+                                    const SimTK::SimbodyMatterSubsystem& matter,
+                                    const SimTK::GeneralForceSubsystem*  forces,
+                                    const std::string& name = "lowered")
+{
+    using namespace SimTK;
+    if (!system.systemTopologyHasBeenRealized())
+        throw std::runtime_error("lowerSimbodySystem: call system.realizeTopology() first");
+    if (matter.getNumConstraints() != 0)
+        throw std::runtime_error("lowerSimbodySystem: constraints are out of scope (tree topologies only)");
+    if (matter.getNumParticles() != 0)
+        throw std::runtime_error("lowerSimbodySystem: particles are not supported");
+
+    ModelSpec spec; spec.name = name;
+    const int nb = matter.getNumBodies();
+    State state = system.getDefaultState();
+    if (matter.getUseEulerAngles(state))
+        throw std::runtime_error("lowerSimbodySystem: Euler-angle mode is not supported (quaternions only)");
+
+    std::vector<int> uFirst(nb, 0), uCount(nb, 0);
+    for (MobilizedBodyIndex mbx(0); mbx < nb; ++mbx) {
+        const MobilizedBody& mobod = matter.getMobilizedBody(mbx);
+        sbk_body_desc b = groundBody();
+        if (mbx == 0) { spec.bodies.push_back(b); continue; }
+        b.parent = (int)mobod.getParentMobilizedBody().getMobilizedBodyIndex();
+        if      (MobilizedBody::Pin::isInstanceOf(mobod))       b.joint_type = SBK_JOINT_PIN;
+        else if (MobilizedBody::Slider::isInstanceOf(mobod))    b.joint_type = SBK_JOINT_SLIDER;
+        else if (MobilizedBody::Universal::isInstanceOf(mobod)) b.joint_type = SBK_JOINT_UNIVERSAL;
+        else if (MobilizedBody::Ball::isInstanceOf(mobod))      b.joint_type = SBK_JOINT_BALL;
+        else if (MobilizedBody::Free::isInstanceOf(mobod))      b.joint_type = SBK_JOINT_FREE;
+        else throw std::runtime_error("lowerSimbodySystem: body " + std::to_string((int)mbx) +
+                                      " uses a mobilizer outside {Pin,Slider,Universal,Ball,Free}");
+        // NOTE: the public API has no getter for MobilizedBody::Direction; reversed mobilizers
+        // are out of scope and must not be used with this lowering.
+        const MassProperties& mp = mobod.getDefaultMassProperties();
+        b.mass = mp.getMass();
+        for (int k = 0; k < 3; ++k) b.com_B[k] = mp.getMassCenter()[k];
+        const Vec3& mom = mp.getUnitInertia().getMoments();
+        const Vec3& prd = mp.getUnitInertia().getProducts();   // xy, xz, yz
+        for (int k = 0; k < 3; ++k) { b.unit_inertia_OB_B[k] = mom[k]; b.unit_inertia_OB_B[3+k] = prd[k]; }
+        lowerTransform(mobod.getDefaultInboardFrame(),  b.X_PF);
+        lowerTransform(mobod.getDefaultOutboardFrame(), b.X_BM);
+        uFirst[mbx] = (int)mobod.getFirstUIndex(state); uCount[mbx] = mobod.getNumU(state);
+        if (mobod.getNumQ(state) != jointNQ(b.joint_type) || uCount[mbx] != jointNU(b.joint_type))
+            throw std::runtime_error("lowerSimbodySystem: unexpected nq/nu for body " + std::to_string((int)mbx));
+        spec.bodies.push_back(b);
+    }
+
+    if (forces) {
+        auto slotToBodyCoord = [&](int uslot, int& body, int& coord) {
+            for (int b = 1; b < nb; ++b)
+                if (uslot >= uFirst[b] && uslot < uFirst[b] + uCount[b]) { body = b; coord = uslot - uFirst[b]; return; }
+            throw std::runtime_error("lowerSimbodySystem: mobility slot not found");
+        };
+        for (ForceIndex fx(0); fx < forces->getNumForces(); ++fx) {
+            const Force& f = forces->getForce(fx);
+            if (forces->isForceDisabled(state, fx)) continue;
+            if (Force::Gravity::isInstanceOf(f)) {
+                const Force::Gravity& g = Force::Gravity::downcast(f);
+                for (MobilizedBodyIndex mbx(1); mbx < nb; ++mbx)
+                    if (g.getDefaultBodyIsExcluded(mbx))
+                        throw std::runtime_error("lowerSimbodySystem: per-body gravity exclusion is not supported");
+                const UnitVec3& d = g.getDefaultDownDirection();
+                spec.forces.push_back(gravityForce(g.getDefaultMagnitude(), d[0], d[1], d[2]));
+            } else if (Force::MobilityLinearSpring::isInstanceOf(f)) {
+                const Force::MobilityLinearSpring& s = Force::MobilityLinearSpring::downcast(f);
+                const Real k = s.getDefaultStiffness(), q0 = s.getDefaultQZero();
+                State probe = system.getDefaultState();
+                probe.updQ() = q0 + 1; probe.updU() = 0;
+                system.realize(probe, Stage::Velocity);
+                Vector_<SpatialVec> bf; Vector_<Vec3> pf; Vector mf;
+                f.calcForceContribution(probe, bf, pf, mf);
+                int hit = -1, nhit = 0;
+                for (int i = 0; i < mf.size(); ++i) if (mf[i] != 0) { hit = i; ++nhit; }
+                if (nhit != 1) throw std::runtime_error("lowerSimbodySystem: could not locate spring mobility");
+                int body, coord; slotToBodyCoord(hit, body, coord);
+                const int jt = spec.bodies[body].joint_type;
+                if (jt == SBK_JOINT_BALL || jt == SBK_JOINT_FREE)
+                    throw std::runtime_error("lowerSimbodySystem: MobilityLinearSpring on a quaternion mobilizer "
+                                             "is not supported (reference mixes q and u indices, Force.cpp:348)");
+                spec.forces.push_back(springForce(body, coord, k, q0));
+            } else if (Force::MobilityLinearDamper::isInstanceOf(f)) {
+                const Force::MobilityLinearDamper& d = Force::MobilityLinearDamper::downcast(f);
+                State probe = system.getDefaultState();
+                probe.updU() = 1;
+                system.realize(probe, Stage::Velocity);
+                Vector_<SpatialVec> bf; Vector_<Vec3> pf; Vector mf;
+                f.calcForceContribution(probe, bf, pf, mf);
+                int hit = -1, nhit = 0;
+                for (int i = 0; i < mf.size(); ++i) if (mf[i] != 0) { hit = i; ++nhit; }
+                if (nhit != 1) throw std::runtime_error("lowerSimbodySystem: could not locate damper mobility");
+                int body, coord; slotToBodyCoord(hit, body, coord);
+                spec.forces.push_back(damperForce(body, coord, d.getDefaultDamping()));
+            } else {
+                throw std::runtime_error("lowerSimbodySystem: force element " + std::to_string((int)fx) +
+                                         " is outside {Gravity, MobilityLinearSpring, MobilityLinearDamper}");
+            }
+        }
+    }
+    return spec;
+}
+
+} // namespace sbk

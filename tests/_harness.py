@@ -1,0 +1,204 @@
+"""Shared test plumbing: model texts, the reference driver (oracle/_ref) and I/O layouts.
+
+Nothing here is product code.  `RefDriver` executes oracle/_ref/ref_driver, the harness linked
+against the UNMODIFIED reference (simbody 3.9.0) compiled by oracle/Makefile.
+"""
+import ctypes
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+REF_DRIVER = os.path.join(REF_DIR, "ref_driver")
+
+JOINT_NQ = {"PIN": 1, "SLIDER": 1, "UNIVERSAL": 2, "BALL": 4, "FREE": 7}
+JOINT_NU = {"PIN": 1, "SLIDER": 1, "UNIVERSAL": 2, "BALL": 3, "FREE": 6}
+
+
+def have_ref():
+    return os.path.exists(REF_DRIVER) and os.path.exists(os.path.join(REF_DIR, "libsimbody_ref.so"))
+
+
+class ModelInfo:
+    """Parsed view of a model text (format of simbody_b200/host/model_spec.h)."""
+
+    def __init__(self, text):
+        self.text = text
+        self.joints, self.parents = [], []
+        for line in text.splitlines():
+            tok = line.split()
+            if tok and tok[0] == "body":
+                self.parents.append(int(tok[2]))
+                self.joints.append(tok[3])
+        self.nb = len(self.joints)
+        self.q0, self.u0 = [], []
+        nq = nu = 0
+        for j in self.joints:
+            self.q0.append(nq)
+            self.u0.append(nu)
+            nq += JOINT_NQ.get(j, 0)
+            nu += JOINT_NU.get(j, 0)
+        self.nq, self.nu = nq, nu
+        self.nquat = sum(1 for j in self.joints if j in ("BALL", "FREE"))
+        self.quat_q0 = [self.q0[i] for i, j in enumerate(self.joints) if j in ("BALL", "FREE")]
+
+    # ---- layouts of `ref_driver eval` (oracle/ref_driver.cpp) --------------------------------
+    @property
+    def eval_in_stride(self):
+        return self.nq + 5 * self.nu + 6 * self.nb
+
+    def eval_out_fields(self):
+        nb, nq, nu, nquat = self.nb, self.nq, self.nu, self.nquat
+        return [("qdot", nq), ("udot", nu), ("qdotdot", nq), ("qerr", nquat), ("X_GB", nb * 12),
+                ("V_GB", nb * 6), ("A_GB", nb * 6), ("fmob_sys", nu), ("Fbody_sys", nb * 6),
+                ("Ma", nu), ("MInvv", nu), ("resid", nu), ("resid0", nu), ("udot_op", nu),
+                ("A_GB_op", nb * 6)]
+
+    @property
+    def eval_out_stride(self):
+        return sum(n for _, n in self.eval_out_fields())
+
+    def split_eval_out(self, out):
+        out = np.asarray(out).reshape(-1, self.eval_out_stride)
+        res, o = {}, 0
+        for name, n in self.eval_out_fields():
+            res[name] = out[:, o:o + n]
+            o += n
+        return res
+
+    def random_states(self, n, seed, q_scale=1.0, u_scale=1.0):
+        """Seeded q,u with unit quaternions; returns (q [n,nq], u [n,nu])."""
+        rng = np.random.default_rng(seed)
+        q = rng.uniform(-1, 1, size=(n, self.nq)) * q_scale
+        u = rng.uniform(-1, 1, size=(n, self.nu)) * u_scale
+        for s in self.quat_q0:
+            quat = rng.normal(size=(n, 4))
+            q[:, s:s + 4] = quat / np.linalg.norm(quat, axis=1, keepdims=True)
+        return q, u
+
+    def random_eval_input(self, n, seed, **kw):
+        q, u = self.random_states(n, seed, **kw)
+        rng = np.random.default_rng(seed + 7919)
+        rest = rng.uniform(-1, 1, size=(n, 4 * self.nu + 6 * self.nb))
+        return np.ascontiguousarray(np.concatenate([q, u, rest], axis=1))
+
+
+class RefDriver:
+    def __init__(self):
+        if not have_ref():
+            raise RuntimeError("oracle/_ref/ref_driver missing: run `make -C oracle` where /root/reference exists")
+        self.env = dict(os.environ)
+        self.env["LD_LIBRARY_PATH"] = REF_DIR + ":" + self.env.get("LD_LIBRARY_PATH", "")
+
+    def _run(self, args, **kw):
+        r = subprocess.run([REF_DRIVER] + [str(a) for a in args], env=self.env, capture_output=True, text=True, **kw)
+        if r.returncode != 0:
+            raise RuntimeError("ref_driver %s failed (%d): %s" % (args[0], r.returncode, r.stderr[-2000:]))
+        return r.stdout
+
+    def _with_model(self, text, fn):
+        with tempfile.TemporaryDirectory() as d:
+            mp = os.path.join(d, "model.txt")
+            with open(mp, "w") as f:
+                f.write(text)
+            return fn(d, mp)
+
+    def lower(self, text):
+        return self._with_model(text, lambda d, mp: self._run(["lower", mp]))
+
+    def slots(self, text):
+        return self._with_model(text, lambda d, mp: self._run(["slots", mp]))
+
+    def eval(self, info, inp):
+        inp = np.ascontiguousarray(inp, dtype=np.float64)
+        n = inp.shape[0]
+
+        def go(d, mp):
+            ip, op = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
+            inp.tofile(ip)
+            self._run(["eval", mp, ip, op, n])
+            return np.fromfile(op, dtype=np.float64).reshape(n, info.eval_out_stride)
+        return self._with_model(info.text, go)
+
+    def step(self, info, y, h, nsteps, accuracy=-1):
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        n = y.shape[0]
+
+        def go(d, mp):
+            ip, op = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
+            y.tofile(ip)
+            self._run(["step", mp, ip, op, n, repr(float(h)), nsteps, repr(float(accuracy))])
+            return np.fromfile(op, dtype=np.float64).reshape(n, info.nq + info.nu + 3)
+        return self._with_model(info.text, go)
+
+    def adaptive(self, info, y, t_final, accuracy=-1):
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        n = y.shape[0]
+
+        def go(d, mp):
+            ip, op = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
+            y.tofile(ip)
+            self._run(["adaptive", mp, ip, op, n, repr(float(t_final)), repr(float(accuracy))])
+            return np.fromfile(op, dtype=np.float64).reshape(n, info.nq + info.nu + 4)
+        return self._with_model(info.text, go)
+
+    def bench(self, info, y, h, nsteps, threads):
+        import json
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        n = y.shape[0]
+
+        def go(d, mp):
+            ip = os.path.join(d, "in.bin")
+            y.tofile(ip)
+            return json.loads(self._run(["bench", mp, ip, n, repr(float(h)), nsteps, threads]))
+        return self._with_model(info.text, go)
+
+
+class HostEmu:
+    """ctypes view of build/libsbk_hostemu.so (tests/hostemu/hostemu.cpp) -- test-only."""
+
+    def __init__(self):
+        path = os.path.join(ROOT, "build", "libsbk_hostemu.so")
+        self.lib = ctypes.CDLL(path)
+        dp = ctypes.POINTER(ctypes.c_double)
+        self.lib.emu_eval.argtypes = [ctypes.c_char_p, ctypes.c_int, dp, dp]
+        self.lib.emu_step.argtypes = [ctypes.c_char_p, ctypes.c_int, dp, dp, ctypes.c_double, ctypes.c_int,
+                                      ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int]
+        self.lib.emu_model_text.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
+
+    def model_text(self, name, n=0):
+        need = self.lib.emu_model_text(name.encode(), n, None, 0)
+        assert need > 0
+        buf = ctypes.create_string_buffer(need)
+        self.lib.emu_model_text(name.encode(), n, buf, need)
+        return buf.value.decode()
+
+    def eval(self, info, inp):
+        inp = np.ascontiguousarray(inp, dtype=np.float64)
+        n = inp.shape[0]
+        out = np.zeros((n, info.eval_out_stride))
+        dp = ctypes.POINTER(ctypes.c_double)
+        rc = self.lib.emu_eval(info.text.encode(), n, inp.ctypes.data_as(dp), out.ctypes.data_as(dp))
+        assert rc == 0, rc
+        return out
+
+    def step(self, info, y, h, nsteps, accuracy=1e-3, cons_tol=None, inf_norm=0, project_every=0):
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        n = y.shape[0]
+        out = np.zeros((n, info.nq + info.nu + 2))
+        dp = ctypes.POINTER(ctypes.c_double)
+        rc = self.lib.emu_step(info.text.encode(), n, y.ctypes.data_as(dp), out.ctypes.data_as(dp), h, nsteps,
+                               accuracy, accuracy / 10 if cons_tol is None else cons_tol, inf_norm, project_every)
+        assert rc == 0, rc
+        return out
+
+
+def rel_err(a, b):
+    """max |a-b| / max(1, max|b|) -- the relative measure used for the 1e-10 parity bar."""
+    a, b = np.asarray(a), np.asarray(b)
+    if a.size == 0:
+        return 0.0
+    return float(np.max(np.abs(a - b)) / max(1.0, float(np.max(np.abs(b)))))

@@ -1,0 +1,165 @@
+// hostemu.cpp -- TEST-ONLY host build of the kernels' per-body device functions.
+//
+// The sweeps in simbody_b200/csrc/sbk_sweeps.cuh / sbk_rkm.cuh are __host__ __device__
+// templates.  This file compiles them for the CPU and drives them with the same
+// thread-per-instance loop structure the CUDA kernels use, so that the kernel *math* can be
+// differential-tested against the reference in a container without a GPU.  It is NOT part of
+// libsbk.so and is never a fallback: the product library has no CPU path.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../simbody_b200/csrc/topology.h"
+#include "../../simbody_b200/csrc/sbk_rkm.cuh"
+
+using namespace sbkd;
+
+namespace {
+struct Emu {
+    sbk_topology topo;
+    int N = 0;
+    long long recTotal = 0;
+    std::vector<BodyConst> bodies;
+    std::vector<double> cache, y, ydot, qdd, qerr, fmob, Fbody, vin, vout, vin2, Fin;
+    std::vector<double> y0, f0, fa, fb, ys;
+    std::vector<int> status;
+};
+void setup(Emu& e, const char* text, int N) {
+    sbk::compileTopology(sbk::fromText(text), e.topo);
+    e.N = N; e.bodies = e.topo.bodies;
+    long long off = 0;
+    for (int b = 0; b < e.topo.nb; ++b) {
+        e.bodies[b].cacheBase = off*N;
+        off += (b == 0) ? F_H : cacheRecordSize(e.topo.nuOf[b]);
+    }
+    for (int b = 0; b < e.topo.nb; ++b) e.bodies[b].parentCacheBase = e.bodies[e.bodies[b].parent].cacheBase;
+    e.recTotal = off;
+    const sbk_topology& t = e.topo;
+    e.cache.assign((size_t)off*N, 0.0);
+    for (int k = 0; k < N; ++k) { e.cache[(F_XGB+0)*(size_t)N+k] = 1; e.cache[(F_XGB+4)*(size_t)N+k] = 1; e.cache[(F_XGB+8)*(size_t)N+k] = 1; }
+    const size_t ny = t.nq + t.nu;
+    e.y.assign(ny*N, 0); e.ydot.assign(ny*N, 0); e.qdd.assign((size_t)t.nq*N, 0); e.qerr.assign((size_t)std::max(1, t.nquat)*N, 0);
+    e.fmob.assign((size_t)t.nu*N, 0); e.Fbody.assign((size_t)t.nb*6*N, 0);
+    e.vin.assign((size_t)t.nu*N, 0); e.vin2.assign((size_t)t.nu*N, 0); e.vout.assign((size_t)t.nu*N, 0); e.Fin.assign((size_t)t.nb*6*N, 0);
+    e.y0.assign(ny*N, 0); e.f0.assign(ny*N, 0); e.fa.assign(ny*N, 0); e.fb.assign(ny*N, 0); e.ys.assign(ny*N, 0);
+    e.status.assign(N, 0);
+}
+Ctx makeCtx(Emu& e, int inst) {
+    const sbk_topology& t = e.topo; const int N = e.N;
+    Ctx c; std::memset(&c, 0, sizeof c);
+    c.bodies = e.bodies.data(); c.children = t.children.data(); c.forces = t.forces.data();
+    c.nb = t.nb; c.nq = t.nq; c.nu = t.nu; c.nquat = t.nquat;
+    c.gx = t.grav[0]; c.gy = t.grav[1]; c.gz = t.grav[2];
+    c.cache = e.cache.data(); c.cStride = N; c.cOff = inst;
+    c.sStride = N; c.sOff = inst;
+    c.q = e.y.data(); c.u = e.y.data() + (size_t)t.nq*N;
+    c.qdot = e.ydot.data(); c.udot = e.ydot.data() + (size_t)t.nq*N;
+    c.qdotdot = e.qdd.data(); c.qerr = e.qerr.data();
+    c.status = &e.status[inst];
+    return c;
+}
+} // namespace
+
+extern "C" {
+
+int emu_counts(const char* text, int* nb, int* nq, int* nu, int* nquat) {
+    try { sbk_topology t; sbk::compileTopology(sbk::fromText(text), t); *nb = t.nb; *nq = t.nq; *nu = t.nu; *nquat = t.nquat; return 0; }
+    catch (const std::exception& ex) { std::fprintf(stderr, "emu: %s\n", ex.what()); return 1; }
+}
+
+// Same binary layout as `ref_driver eval` (oracle/ref_driver.cpp): instance-major in/out.
+int emu_eval(const char* text, int N, const double* in, double* out) {
+    try {
+        Emu e; setup(e, text, N);
+        const sbk_topology& t = e.topo; const int nb = t.nb, nq = t.nq, nu = t.nu, nquat = t.nquat;
+        const int inStride = nq + 5*nu + 6*nb;
+        const int outStride = nq + nu + nq + nquat + nb*12 + nb*6 + nb*6 + nu + nb*6 + 4*nu + nu + nb*6;
+        for (int k = 0; k < N; ++k) {
+            const double* p = in + (size_t)k*inStride;
+            for (int i = 0; i < nq + nu; ++i) e.y[(size_t)i*N + k] = p[i];
+        }
+        for (int k = 0; k < N; ++k) {
+            const double* p = in + (size_t)k*inStride; double* o = out + (size_t)k*outStride;
+            Ctx c = makeCtx(e, k);
+            c.fmobOut = e.fmob.data(); c.FbodyOut = e.Fbody.data();
+            tpiEvalDerivatives(c);
+            for (int i = 0; i < nq; ++i) *o++ = e.ydot[(size_t)i*N + k];
+            for (int i = 0; i < nu; ++i) *o++ = e.ydot[(size_t)(nq+i)*N + k];
+            for (int i = 0; i < nq; ++i) *o++ = e.qdd[(size_t)i*N + k];
+            for (int i = 0; i < nquat; ++i) *o++ = e.qerr[(size_t)i*N + k];
+            auto rec = [&](int b, int f) { return e.cache[(size_t)(e.bodies[b].cacheBase) + (size_t)f*N + k]; };
+            for (int b = 0; b < nb; ++b) for (int i = 0; i < 12; ++i) *o++ = rec(b, F_XGB + i);
+            for (int b = 0; b < nb; ++b) for (int i = 0; i < 6; ++i)  *o++ = rec(b, F_VGB + i);
+            for (int b = 0; b < nb; ++b) for (int i = 0; i < 6; ++i)  *o++ = rec(b, F_AGB + i);
+            for (int i = 0; i < nu; ++i) *o++ = e.fmob[(size_t)i*N + k];
+            for (int i = 0; i < nb*6; ++i) *o++ = e.Fbody[(size_t)i*N + k];
+            // operators
+            const double* pa = p + nq + nu; const double* pv = pa + nu; const double* pud = pv + nu;
+            const double* pf = pud + nu;    const double* pF = pf + nu;
+            c.fmobOut = nullptr; c.FbodyOut = nullptr; c.vecOut = e.vout.data();
+            // M*a
+            for (int i = 0; i < nu; ++i) e.vin[(size_t)i*N + k] = pa[i];
+            c.vecIn = e.vin.data();
+            for (int b = 1; b < nb; ++b) idOutDispatch<false>(c, b);
+            for (int b = nb-1; b >= 1; --b) idInDispatch<false>(c, b);
+            for (int i = 0; i < nu; ++i) *o++ = e.vout[(size_t)i*N + k];
+            // M^-1 v
+            for (int i = 0; i < nu; ++i) e.vin[(size_t)i*N + k] = pv[i];
+            c.fmobIn = e.vin.data(); c.FbodyIn = nullptr;
+            tpiInward<IN_Z>(c);
+            tpiOutward<false>(c, e.vout.data(), nullptr);
+            for (int i = 0; i < nu; ++i) *o++ = e.vout[(size_t)i*N + k];
+            // residual(f, F, udot)
+            for (int i = 0; i < nu; ++i) { e.vin[(size_t)i*N + k] = pud[i]; e.vin2[(size_t)i*N + k] = pf[i]; }
+            for (int i = 0; i < nb*6; ++i) e.Fin[(size_t)i*N + k] = pF[i];
+            c.vecIn = e.vin.data(); c.fmobIn = e.vin2.data(); c.FbodyIn = e.Fin.data();
+            for (int b = 1; b < nb; ++b) idOutDispatch<true>(c, b);
+            for (int b = nb-1; b >= 1; --b) idInDispatch<true>(c, b);
+            for (int i = 0; i < nu; ++i) *o++ = e.vout[(size_t)i*N + k];
+            // residual with all-zero arguments
+            c.vecIn = nullptr; c.fmobIn = nullptr; c.FbodyIn = nullptr;
+            for (int b = 1; b < nb; ++b) idOutDispatch<true>(c, b);
+            for (int b = nb-1; b >= 1; --b) idInDispatch<true>(c, b);
+            for (int i = 0; i < nu; ++i) *o++ = e.vout[(size_t)i*N + k];
+            // calcAcceleration(f, F)
+            c.fmobIn = e.vin2.data(); c.FbodyIn = e.Fin.data();
+            tpiInward<IN_Z | IN_BIAS>(c);
+            tpiOutward<true>(c, e.vout.data(), nullptr);
+            for (int i = 0; i < nu; ++i) *o++ = e.vout[(size_t)i*N + k];
+            for (int b = 0; b < nb; ++b) for (int i = 0; i < 6; ++i) *o++ = rec(b, F_AGB + i);
+            if (o - (out + (size_t)k*outStride) != outStride) return 3;
+        }
+        return 0;
+    } catch (const std::exception& ex) { std::fprintf(stderr, "emu: %s\n", ex.what()); return 1; }
+}
+
+// in: [N][nq+nu]; out: [N][nq+nu+2] (q, u, errNorm of last step, number of projections)
+int emu_step(const char* text, int N, const double* in, double* out, double h, int nsteps,
+             double accuracy, double consTol, int useInfNorm, int projectEveryStep) {
+    try {
+        Emu e; setup(e, text, N);
+        const sbk_topology& t = e.topo; const int ny = t.nq + t.nu;
+        for (int k = 0; k < N; ++k) for (int i = 0; i < ny; ++i) e.y[(size_t)i*N + k] = in[(size_t)k*ny + i];
+        RkmWork w; w.y = e.y.data(); w.y0 = e.y0.data(); w.f0 = e.f0.data(); w.fa = e.fa.data(); w.fb = e.fb.data(); w.ys = e.ys.data();
+        w.accuracy = accuracy; w.consTol = consTol; w.useInfNorm = useInfNorm; w.projectEveryStep = projectEveryStep;
+        for (int k = 0; k < N; ++k) {
+            Ctx c = makeCtx(e, k);
+            RkmStepResult r; r.errNorm = 0; r.projected = 0; int nproj = 0;
+            for (int s = 0; s < nsteps; ++s) { r = tpiRkmStep(c, w, h); nproj += r.projected; }
+            double* o = out + (size_t)k*(ny+2);
+            for (int i = 0; i < ny; ++i) o[i] = e.y[(size_t)i*N + k];
+            o[ny] = r.errNorm; o[ny+1] = nproj;
+        }
+        return 0;
+    } catch (const std::exception& ex) { std::fprintf(stderr, "emu: %s\n", ex.what()); return 1; }
+}
+
+int emu_model_text(const char* name, int n, char* buf, int cap) {
+    try {
+        const std::string s = sbk::toText(sbk::makeNamedModel(name, n));
+        if ((int)s.size() + 1 <= cap) std::memcpy(buf, s.c_str(), s.size() + 1);
+        return (int)s.size() + 1;
+    } catch (const std::exception& ex) { std::fprintf(stderr, "emu: %s\n", ex.what()); return -1; }
+}
+
+} // extern "C"

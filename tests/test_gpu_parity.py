@@ -1,0 +1,147 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the reference.
+
+Two sources of truth:
+  * tests/golden/*.npz -- outputs of the UNMODIFIED reference recorded by
+    tests/golden/make_golden.py (always available);
+  * oracle/_ref/ref_driver -- the compiled reference itself, run live on fresh seeded inputs
+    when the prebuilt binary travelled with the snapshot.
+Tolerance: north_star asks for 1e-10 relative in double precision; measured agreement is
+~1e-15, the tests gate at 1e-11 (accelerations / single step) so that regressions are caught
+long before the contract is at risk.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import simbody_b200 as sb
+from _harness import ModelInfo, RefDriver, have_ref, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-11
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MODELS = ["double_pendulum", "pin_chain", "mixed7", "humanoid30", "branched_tree"]
+
+
+def soa(a):
+    return np.ascontiguousarray(np.asarray(a).T)
+
+
+def run_eval(info, ein):
+    """Run every operator of the C ABI on the inputs of `ref_driver eval`; returns dict like split_eval_out."""
+    n = ein.shape[0]
+    nq, nu, nb = info.nq, info.nu, info.nb
+    topo = sb.Topology(text=info.text)
+    assert (topo.nb, topo.nq, topo.nu, topo.nquat) == (nb, nq, nu, info.nquat)
+    bm = sb.BatchedMatter(topo, n)
+    o = nq
+    q, u = ein[:, :nq], ein[:, nq:nq + nu]
+    o = nq + nu
+    a, v, ud, f = (ein[:, o + i * nu:o + (i + 1) * nu] for i in range(4))
+    F = ein[:, o + 4 * nu:]
+    bm.setState(soa(q), soa(u))
+    bm.realizeAcceleration()
+    res = {"qdot": bm.getQDot().T, "udot": bm.getUDot().T, "qdotdot": bm.getQDotDot().T, "qerr": bm.getQErr().T,
+           "X_GB": bm.getBodyTransforms().reshape(nb * 12, n).T, "V_GB": bm.getBodyVelocities().reshape(nb * 6, n).T,
+           "A_GB": bm.getBodyAccelerations().reshape(nb * 6, n).T}
+    fm, Fb = bm.getAppliedForces()
+    res["fmob_sys"], res["Fbody_sys"] = fm.T, Fb.reshape(nb * 6, n).T
+    res["Ma"] = bm.multiplyByM(soa(a)).T
+    res["MInvv"] = bm.multiplyByMInv(soa(v)).T
+    res["resid"] = bm.calcResidualForceIgnoringConstraints(soa(f), soa(F), soa(ud)).T
+    res["resid0"] = bm.calcResidualForceIgnoringConstraints().T
+    udot_op, A_op = bm.calcAcceleration(soa(f), soa(F))
+    res["udot_op"], res["A_GB_op"] = udot_op.T, A_op.reshape(nb * 6, n).T
+    st, nbad = bm.status()
+    assert nbad == 0
+    bm.close(); topo.close()
+    return res
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_eval_matches_golden(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    info = ModelInfo(str(g["text"]))
+    ref = info.split_eval_out(g["eval_out"])
+    got = run_eval(info, g["eval_in"])
+    for k in ref:
+        assert rel_err(got[k], ref[k]) < TOL, (name, k, rel_err(got[k], ref[k]))
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_rkm_step_matches_golden(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    info = ModelInfo(str(g["text"]))
+    y0, yref = g["step_in"], g["step_out"]
+    n, ny = y0.shape[0], info.nq + info.nu
+    topo = sb.Topology(text=info.text); bm = sb.BatchedMatter(topo, n)
+    bm.setState(soa(y0[:, :info.nq]), soa(y0[:, info.nq:]), t=0.0)
+    err = bm.stepBy(float(g["h"]), int(g["nsteps"]), want_err_norm=True)
+    q, u, t = bm.getState()
+    assert np.all(np.isfinite(err))
+    assert np.allclose(t, float(g["h"]) * int(g["nsteps"]), rtol=1e-12)
+    got = np.concatenate([q.T, u.T], axis=1)
+    assert rel_err(got, yref[:, :ny]) < 1e-10, (name, rel_err(got, yref[:, :ny]))
+    s = bm.stats()
+    assert s["steps_taken"] == n * int(g["nsteps"]) and s["realizations"] == 5 * n * int(g["nsteps"])
+    bm.close(); topo.close()
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("name,n,count", [("double_pendulum", 0, 512), ("pin_chain", 50, 96), ("mixed7", 0, 256),
+                                          ("humanoid30", 0, 128), ("branched_tree", 60, 64)])
+def test_eval_matches_live_reference(name, n, count):
+    info = ModelInfo(sb.model_text(name, n))
+    ein = info.random_eval_input(count, 4242, q_scale=2.0 if name == "double_pendulum" else 0.7)
+    ref = info.split_eval_out(RefDriver().eval(info, ein))
+    got = run_eval(info, ein)
+    for k in ref:
+        assert rel_err(got[k], ref[k]) < TOL, (name, k, rel_err(got[k], ref[k]))
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("name,n,count,h,nsteps", [("double_pendulum", 0, 256, 1e-3, 100), ("pin_chain", 50, 32, 1e-3, 10),
+                                                   ("mixed7", 0, 64, 2e-3, 50), ("humanoid30", 0, 64, 1e-3, 20)])
+def test_rkm_matches_live_reference(name, n, count, h, nsteps):
+    info = ModelInfo(sb.model_text(name, n))
+    q, u = info.random_states(count, 99, q_scale=0.5)
+    y0 = np.concatenate([q, u], axis=1)
+    yref = RefDriver().step(info, y0, h, nsteps)[:, :info.nq + info.nu]
+    topo = sb.Topology(text=info.text); bm = sb.BatchedMatter(topo, count)
+    bm.setStateAoS(q, u)
+    bm.stepBy(h, nsteps)
+    qg, ug = bm.getStateAoS()
+    assert rel_err(np.concatenate([qg, ug], axis=1), yref) < 1e-10
+    bm.close(); topo.close()
+
+
+def test_mass_matrix_invariants_large_batch():
+    """Size-independent properties at a large batch (reference TestMassMatrix.cpp:670-787):
+    M^-1 (M v) = v, and inverse dynamics o forward dynamics = identity."""
+    info = ModelInfo(sb.model_text("humanoid30"))
+    n = 4096
+    q, u = info.random_states(n, 7, q_scale=0.5)
+    topo = sb.Topology(text=info.text); bm = sb.BatchedMatter(topo, n)
+    bm.setState(soa(q), soa(u))
+    bm.realizeVelocityKinematics()
+    rng = np.random.default_rng(3)
+    v = rng.uniform(-1, 1, size=(info.nu, n))
+    back = bm.multiplyByMInv(bm.multiplyByM(v))
+    assert rel_err(back, v) < 1e-9
+    f = rng.uniform(-1, 1, size=(info.nu, n)); F = rng.uniform(-1, 1, size=(info.nb * 6, n))
+    udot, _ = bm.calcAcceleration(f, F)
+    resid = bm.calcResidualForceIgnoringConstraints(f, F, udot)
+    assert float(np.max(np.abs(resid))) < 1e-8
+    bm.close(); topo.close()
+
+
+def test_stage_and_argument_errors():
+    info = ModelInfo(sb.model_text("double_pendulum"))
+    topo = sb.Topology(text=info.text); bm = sb.BatchedMatter(topo, 8)
+    with pytest.raises(sb.SbkError) as e:      # operator before realize: SimTK_STAGECHECK analogue
+        bm.multiplyByM(np.zeros((2, 8)))
+    assert e.value.code == 2
+    with pytest.raises(sb.SbkError) as e:      # wrong length: SimTK_APIARGCHECK analogue
+        bm.realizePositionKinematics(); bm.multiplyByM(np.zeros((3, 8)))
+    assert e.value.code == 1
+    bm.close(); topo.close()
