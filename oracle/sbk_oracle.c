@@ -1,0 +1,415 @@
+/* sbk_oracle.c -- TEST INFRASTRUCTURE ONLY.  CPU restatement, in plain C, of the reference's
+ * algorithm for the hot path (simbody/simbody 3.9.0): one derivative evaluation of a
+ * tree-topology system (sweeps A-E + gravity/spring/damper forces), the matter operators, and
+ * the fixed-step Runge-Kutta-Merson step.  One instance at a time, array-of-structures, no
+ * vectorisation: clarity over speed.  It is the checker for the CUDA path; nothing in the
+ * product links, imports or executes it (only tests/, __graft_entry__.smoke() and bench.py's
+ * CPU-baseline leg may).
+ *
+ * PARITY PINNING: this restatement is pinned against the UNMODIFIED reference itself
+ * (oracle/_ref, compiled from /root/reference by oracle/Makefile) through the golden vectors
+ * in tests/golden/*.npz and live differential runs (tests/test_oracle.py); SURVEY.md section 8c
+ * golden values (udot of the README double pendulum and the mixed 7-body fixture) are checked
+ * too.  The only third-party arithmetic on the path is LAPACK dgetrf/dgetri for the 6x6 D^-1 of
+ * Free mobilizers (SmallMatrixMixed.h:859-893; any LAPACK >= 3.6, OpenBLAS 0.3.15 in
+ * oracle/_ref); it is restated here as LU with partial pivoting, the published algorithm of
+ * dgetrf + dgetri.
+ *
+ * Reference lines followed (paths relative to the reference root):
+ *   slot rules            Simbody/src/RigidBodyNodeSpec.h:81-87
+ *   X_FM, H_FM, HDot_FM   Simbody/src/RigidBodyNodeSpec_{Pin,Slider,Universal,Ball,Free}.h
+ *   sweep A               Simbody/src/RigidBodyNodeSpec.h:229-288,554-569; RigidBodyNodeSpec.cpp:44-74;
+ *                         RigidBodyNode.cpp:54-84
+ *   sweep B               RigidBodyNodeSpec.h:305-333; RigidBodyNodeSpec.cpp:82-129; RigidBodyNode.cpp:97-174
+ *   sweep C               RigidBodyNodeSpec.cpp:249-325; MassProperties.cpp:76-127
+ *   bias                  RigidBodyNode.cpp:201-213
+ *   forces                Force_Gravity.cpp:514-569; Force.cpp:339-351,434-443
+ *   sweeps D, E           RigidBodyNodeSpec.cpp:355-446
+ *   operators             RigidBodyNodeSpec.cpp:483-695
+ *   RKM step              SimTKmath/Integrators/src/RungeKuttaMersonIntegrator.cpp:86-140,
+ *                         AbstractIntegratorRep.cpp:137-208, IntegratorRep.h:454-513,644-655,
+ *                         SimbodyMatterSubsystemRep.cpp:4096-4184,4448-4476
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+enum { PIN = 1, SLIDER = 2, UNIVERSAL = 3, BALL = 4, FREE = 5 };
+enum { F_GRAVITY = 1, F_SPRING = 2, F_DAMPER = 3 };
+#define MAXD 6
+
+typedef struct {
+    int nb, nf;
+    const int *parent, *joint;
+    const double *mass, *com, *uinertia, *X_PF, *X_BM;   /* [nb], [nb*3], [nb*6], [nb*12], [nb*12] */
+    const int *fkind, *fbody, *fcoord; const double *fa, *fb, *fdir;   /* [nf], ..., [nf*3] */
+} Model;
+
+typedef struct {   /* per-body cache, dense */
+    double R[9], p[3];          /* X_GB */
+    double V[6], A[6];          /* V_GB, A_GB (angular, linear) */
+    double H[MAXD][6];          /* columns of H_PB_G */
+    double l[3];                /* Phi */
+    double m, c[3], G[9];       /* Mk_G: mass, com in G, unit inertia in G (full 3x3) */
+    double a[6], b[6];          /* mobilizer coriolis acceleration, gyroscopic force */
+    double P[36], PP[36];       /* articulated inertia and P+ as dense 6x6: [J F; F^T M] */
+    double DI[MAXD*MAXD], Gm[MAXD][6];
+    double zb[6], z[6], zP[6], eps[MAXD], Fapp[6];
+    int q0, u0, nq, nu;
+} Body;
+
+static int NQ(int j) { return j == PIN || j == SLIDER ? 1 : j == UNIVERSAL ? 2 : j == BALL ? 4 : j == FREE ? 7 : 0; }
+static int NU(int j) { return j == PIN || j == SLIDER ? 1 : j == UNIVERSAL ? 2 : j == BALL ? 3 : j == FREE ? 6 : 0; }
+
+static void matvec3(const double* R, const double* v, double* o) { for (int i = 0; i < 3; ++i) o[i] = R[3*i]*v[0] + R[3*i+1]*v[1] + R[3*i+2]*v[2]; }
+static void matmul3(const double* A, const double* B, double* C) {
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) C[3*i+j] = A[3*i]*B[j] + A[3*i+1]*B[3+j] + A[3*i+2]*B[6+j];
+}
+static void cross(const double* a, const double* b, double* o) {
+    double x = a[1]*b[2] - a[2]*b[1], y = a[2]*b[0] - a[0]*b[2], z = a[0]*b[1] - a[1]*b[0]; o[0] = x; o[1] = y; o[2] = z;
+}
+static void crossMat(const double* v, double* M) { M[0]=0; M[1]=-v[2]; M[2]=v[1]; M[3]=v[2]; M[4]=0; M[5]=-v[0]; M[6]=-v[1]; M[7]=v[0]; M[8]=0; }
+/* ~Phi(l)*V and Phi(l)*F (SpatialAlgebra.h:729-762) */
+static void phiT(const double* l, const double* V, double* o) { double t[3]; cross(V, l, t); for (int i = 0; i < 3; ++i) { o[i] = V[i]; o[3+i] = V[3+i] + t[i]; } }
+static void phiF(const double* l, const double* F, double* o) { double t[3]; cross(l, F+3, t); for (int i = 0; i < 3; ++i) { o[i] = F[i] + t[i]; o[3+i] = F[3+i]; } }
+static void mat6vec(const double* P, const double* v, double* o) { for (int i = 0; i < 6; ++i) { double s = 0; for (int j = 0; j < 6; ++j) s += P[6*i+j]*v[j]; o[i] = s; } }
+/* SpatialInertia * V (MassProperties.h:1071-1072) */
+static void mkTimes(const Body* B, const double* V, double* o) {
+    double Gw[3], pv[3], pw[3]; matvec3(B->G, V, Gw); cross(B->c, V+3, pv); cross(B->c, V, pw);
+    for (int i = 0; i < 3; ++i) { o[i] = B->m*(Gw[i] + pv[i]); o[3+i] = B->m*(V[3+i] - pw[i]); }
+}
+
+/* General inverse by LU with partial pivoting (dgetrf + dgetri); n <= 6. Closed forms for n <= 3
+ * as in SmallMatrixMixed.h:841-1006. */
+static int invertD(int n, const double* D, double* DI) {
+    if (n == 1) { DI[0] = 1.0/D[0]; return D[0] != 0; }
+    if (n == 2) { double det = D[0]*D[3] - D[1]*D[2], ood = 1.0/det; DI[0] = ood*D[3]; DI[1] = -ood*D[1]; DI[2] = -ood*D[2]; DI[3] = ood*D[0]; return det != 0; }
+    if (n == 3) {
+        #define m(i,j) D[3*(i)+(j)]
+        double d00 = m(1,1)*m(2,2)-m(1,2)*m(2,1), nd01 = m(1,2)*m(2,0)-m(1,0)*m(2,2), d02 = m(1,0)*m(2,1)-m(1,1)*m(2,0);
+        double det = m(0,0)*d00 + m(0,1)*nd01 + m(0,2)*d02, ood = 1.0/det;
+        double nd10 = m(0,2)*m(2,1)-m(0,1)*m(2,2), d11 = m(0,0)*m(2,2)-m(0,2)*m(2,0), nd12 = m(0,1)*m(2,0)-m(0,0)*m(2,1),
+               d20 = m(0,1)*m(1,2)-m(0,2)*m(1,1), nd21 = m(0,2)*m(1,0)-m(0,0)*m(1,2), d22 = m(0,0)*m(1,1)-m(0,1)*m(1,0);
+        #undef m
+        DI[0] = ood*d00; DI[1] = ood*nd10; DI[2] = ood*d20; DI[3] = ood*nd01; DI[4] = ood*d11; DI[5] = ood*nd21; DI[6] = ood*d02; DI[7] = ood*nd12; DI[8] = ood*d22;
+        return det != 0;
+    }
+    double A[MAXD*MAXD]; int piv[MAXD];
+    memcpy(A, D, sizeof(double)*n*n);
+    for (int k = 0; k < n; ++k) {
+        int p = k; double best = fabs(A[n*k+k]);
+        for (int i = k+1; i < n; ++i) if (fabs(A[n*i+k]) > best) { best = fabs(A[n*i+k]); p = i; }
+        piv[k] = p; if (best == 0) return 0;
+        if (p != k) for (int j = 0; j < n; ++j) { double t = A[n*k+j]; A[n*k+j] = A[n*p+j]; A[n*p+j] = t; }
+        for (int i = k+1; i < n; ++i) { A[n*i+k] /= A[n*k+k]; for (int j = k+1; j < n; ++j) A[n*i+j] -= A[n*i+k]*A[n*k+j]; }
+    }
+    for (int c = 0; c < n; ++c) {            /* solve A x = P e_c */
+        double x[MAXD]; for (int i = 0; i < n; ++i) x[i] = (i == c);
+        for (int k = 0; k < n; ++k) if (piv[k] != k) { double t = x[k]; x[k] = x[piv[k]]; x[piv[k]] = t; }
+        for (int i = 0; i < n; ++i) for (int j = 0; j < i; ++j) x[i] -= A[n*i+j]*x[j];
+        for (int i = n-1; i >= 0; --i) { for (int j = i+1; j < n; ++j) x[i] -= A[n*i+j]*x[j]; x[i] /= A[n*i+i]; }
+        for (int i = 0; i < n; ++i) DI[n*i+c] = x[i];
+    }
+    return 1;
+}
+
+static void quatN(const double* q, const double* w, double* o) {   /* Rotation.h:712-720 */
+    double e0 = q[0]/2, e1 = q[1]/2, e2 = q[2]/2, e3 = q[3]/2;
+    o[0] = -e1*w[0] + -e2*w[1] + -e3*w[2]; o[1] = e0*w[0] + e3*w[1] + -e2*w[2];
+    o[2] = -e3*w[0] + e0*w[1] + e1*w[2];   o[3] = e2*w[0] + -e1*w[1] + e0*w[2];
+}
+static void quatNInv(const double* q, const double* qd, double* o) {   /* Rotation.h:742-748 */
+    double e0 = 2*q[0], e1 = 2*q[1], e2 = 2*q[2], e3 = 2*q[3];
+    o[0] = -e1*qd[0] + e0*qd[1] + -e3*qd[2] + e2*qd[3];
+    o[1] = -e2*qd[0] + e3*qd[1] + e0*qd[2] + -e1*qd[3];
+    o[2] = -e3*qd[0] + -e2*qd[1] + e1*qd[2] + e0*qd[3];
+}
+
+static Body* setupBodies(const Model* M, int* nqOut, int* nuOut, int* nquatOut) {
+    Body* B = (Body*)calloc((size_t)M->nb, sizeof(Body));
+    int q = 0, u = 0, nquat = 0;
+    for (int b = 1; b < M->nb; ++b) {
+        B[b].q0 = q; B[b].u0 = u; B[b].nq = NQ(M->joint[b]); B[b].nu = NU(M->joint[b]); q += B[b].nq; u += B[b].nu;
+        if (M->joint[b] == BALL || M->joint[b] == FREE) ++nquat;
+    }
+    B[0].R[0] = B[0].R[4] = B[0].R[8] = 1;
+    *nqOut = q; *nuOut = u; *nquatOut = nquat;
+    return B;
+}
+
+/* Sweeps A + B for all bodies, base to tip (body index order is a valid order). */
+static void kinematics(const Model* M, Body* B, const double* q, const double* u, double* qdot, double* qerr) {
+    int iq = 0;
+    for (int b = 1; b < M->nb; ++b) {
+        Body* me = &B[b]; const Body* pa = &B[M->parent[b]];
+        const int jt = M->joint[b], d = me->nu; const double* qb = q + me->q0; const double* ub = u + me->u0;
+        double Rfm[9] = {1,0,0, 0,1,0, 0,0,1}, pfm[3] = {0,0,0};
+        double Hw[MAXD][3], Hv[MAXD][3], HDw[MAXD][3];
+        memset(Hw, 0, sizeof Hw); memset(Hv, 0, sizeof Hv); memset(HDw, 0, sizeof HDw);
+        if (jt == PIN) { double c = cos(qb[0]), s = sin(qb[0]); Rfm[0] = c; Rfm[1] = -s; Rfm[3] = s; Rfm[4] = c; Hw[0][2] = 1; }
+        else if (jt == SLIDER) { pfm[0] = qb[0]; Hv[0][0] = 1; }
+        else if (jt == UNIVERSAL) {   /* body-fixed X then Y (Rotation.cpp:241-264) */
+            double c1 = cos(qb[0]), s1 = sin(qb[0]), c2 = cos(qb[1]), s2 = sin(qb[1]);
+            Rfm[0] = c2; Rfm[1] = 0; Rfm[2] = s2; Rfm[3] = s2*s1; Rfm[4] = c1; Rfm[5] = -s1*c2; Rfm[6] = -s2*c1; Rfm[7] = s1; Rfm[8] = c1*c2;
+            Hw[0][0] = 1; Hw[1][0] = Rfm[1]; Hw[1][1] = Rfm[4]; Hw[1][2] = Rfm[7];
+        } else {                      /* Ball / Free, quaternion (Rotation.cpp:600-611) */
+            double n = sqrt(qb[0]*qb[0] + qb[1]*qb[1] + qb[2]*qb[2] + qb[3]*qb[3]);
+            if (qerr) qerr[iq] = n - 1.0; ++iq;
+            double oo = 1.0/n, a0 = qb[0]*oo, a1 = qb[1]*oo, a2 = qb[2]*oo, a3 = qb[3]*oo;
+            double q00=a0*a0, q11=a1*a1, q22=a2*a2, q33=a3*a3, q01=a0*a1, q02=a0*a2, q03=a0*a3, q12=a1*a2, q13=a1*a3, q23=a2*a3;
+            double q00mq11 = q00-q11, q22mq33 = q22-q33;
+            Rfm[0] = q00+q11-q22-q33; Rfm[1] = 2*(q12-q03); Rfm[2] = 2*(q13+q02);
+            Rfm[3] = 2*(q12+q03); Rfm[4] = q00mq11+q22mq33; Rfm[5] = 2*(q23-q01);
+            Rfm[6] = 2*(q13-q02); Rfm[7] = 2*(q23+q01); Rfm[8] = q00mq11-q22mq33;
+            Hw[0][0] = Hw[1][1] = Hw[2][2] = 1;
+            if (jt == FREE) { pfm[0] = qb[4]; pfm[1] = qb[5]; pfm[2] = qb[6]; Hv[3][0] = Hv[4][1] = Hv[5][2] = 1; }
+        }
+        /* X_MB = ~X_BM */
+        const double* XBM = M->X_BM + 12*b; const double* XPF = M->X_PF + 12*b;
+        double Rmb[9], pmb[3];
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Rmb[3*i+j] = XBM[3*j+i];
+        for (int i = 0; i < 3; ++i) pmb[i] = -(Rmb[3*i]*XBM[9] + Rmb[3*i+1]*XBM[10] + Rmb[3*i+2]*XBM[11]);
+        /* X_FB = X_FM X_MB; X_PB = X_PF X_FB; X_GB = X_GP X_PB */
+        double r[3], Rfb[9], pfb[3], Rpb[9], ppb[3], t[3];
+        matvec3(Rfm, pmb, r); matmul3(Rfm, Rmb, Rfb); for (int i = 0; i < 3; ++i) pfb[i] = pfm[i] + r[i];
+        matmul3(XPF, Rfb, Rpb); matvec3(XPF, pfb, t); for (int i = 0; i < 3; ++i) ppb[i] = XPF[9+i] + t[i];
+        matmul3(pa->R, Rpb, me->R); matvec3(pa->R, ppb, me->l); for (int i = 0; i < 3; ++i) me->p[i] = pa->p[i] + me->l[i];
+        /* H = R_GF (H_FM + H_MB_F) */
+        double Rgf[9]; matmul3(pa->R, XPF, Rgf);
+        for (int j = 0; j < d; ++j) {
+            double hv[3], cx[3]; cross(Hw[j], r, cx); for (int i = 0; i < 3; ++i) hv[i] = Hv[j][i] + cx[i];
+            matvec3(Rgf, Hw[j], me->H[j]); matvec3(Rgf, hv, me->H[j]+3);
+        }
+        /* mass properties in G: G_G = R G_B R^T (dense; the reference uses the 57-flop form) */
+        const double* ui = M->uinertia + 6*b;
+        double Gb[9] = {ui[0], ui[3], ui[4], ui[3], ui[1], ui[5], ui[4], ui[5], ui[2]}, RG[9], Rt[9];
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Rt[3*i+j] = me->R[3*j+i];
+        matmul3(me->R, Gb, RG); matmul3(RG, Rt, me->G);
+        me->m = M->mass[b]; matvec3(me->R, M->com + 3*b, me->c);
+        /* velocity */
+        double wfm[3] = {0,0,0}, Vpb[6] = {0,0,0,0,0,0};
+        for (int j = 0; j < d; ++j) { for (int i = 0; i < 3; ++i) wfm[i] += Hw[j][i]*ub[j]; for (int i = 0; i < 6; ++i) Vpb[i] += me->H[j][i]*ub[j]; }
+        if (jt == UNIVERSAL) { double y[3] = {Rfm[1], Rfm[4], Rfm[7]}; cross(wfm, y, HDw[1]); }
+        double wxr[3]; cross(wfm, r, wxr);
+        double VD[6] = {0,0,0,0,0,0};
+        for (int j = 0; j < d; ++j) {
+            double HD[6], t1[3], t2[3], t3[3], s[3];
+            matvec3(Rgf, HDw[j], t1); cross(pa->V, me->H[j], t2); for (int i = 0; i < 3; ++i) HD[i] = t1[i] + t2[i];
+            cross(HDw[j], r, t1); cross(Hw[j], wxr, t2); for (int i = 0; i < 3; ++i) s[i] = t1[i] + t2[i];
+            matvec3(Rgf, s, t3); cross(pa->V, me->H[j]+3, t2); for (int i = 0; i < 3; ++i) HD[3+i] = t3[i] + t2[i];
+            for (int i = 0; i < 6; ++i) VD[i] += HD[i]*ub[j];
+        }
+        double Vs[6]; phiT(me->l, pa->V, Vs); for (int i = 0; i < 6; ++i) me->V[i] = Vs[i] + Vpb[i];
+        double Gw[3], wGw[3], wc[3], wwc[3], dv[3], wdv[3];
+        matvec3(me->G, me->V, Gw); cross(me->V, Gw, wGw); cross(me->V, me->c, wc); cross(me->V, wc, wwc);
+        for (int i = 0; i < 3; ++i) { me->b[i] = me->m*wGw[i]; me->b[3+i] = me->m*wwc[i]; }
+        for (int i = 0; i < 3; ++i) dv[i] = me->V[3+i] - pa->V[3+i];
+        cross(pa->V, dv, wdv);
+        for (int i = 0; i < 3; ++i) { me->a[i] = VD[i]; me->a[3+i] = VD[3+i] + wdv[i]; }
+        /* qdot */
+        if (qdot) {
+            if (jt == BALL || jt == FREE) { quatN(qb, ub, qdot + me->q0); if (jt == FREE) for (int i = 0; i < 3; ++i) qdot[me->q0+4+i] = ub[3+i]; }
+            else for (int i = 0; i < d; ++i) qdot[me->q0+i] = ub[i];
+        }
+    }
+}
+
+/* Sweep C: dense 6x6 articulated inertias, tip to base. */
+static int articulatedInertias(const Model* M, Body* B) {
+    int ok = 1;
+    for (int b = M->nb-1; b >= 1; --b) {
+        Body* me = &B[b]; const int d = me->nu;
+        double mc[3] = {me->m*me->c[0], me->m*me->c[1], me->m*me->c[2]}, F[9]; crossMat(mc, F);
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+            me->P[6*i+j] = me->m*me->G[3*i+j]; me->P[6*i+3+j] = F[3*i+j]; me->P[6*(3+i)+j] = F[3*j+i]; me->P[6*(3+i)+3+j] = (i == j) ? me->m : 0.0;
+        }
+        for (int c = b+1; c < M->nb; ++c) if (M->parent[c] == b) {   /* P += Phi(l) P+ ~Phi(l), dense */
+            double Phi[36] = {0}, T[36], S[36], lx[9]; crossMat(B[c].l, lx);
+            for (int i = 0; i < 6; ++i) Phi[7*i] = 1;
+            for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Phi[6*i+3+j] = lx[3*i+j];
+            for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) { double s = 0; for (int k = 0; k < 6; ++k) s += Phi[6*i+k]*B[c].PP[6*k+j]; T[6*i+j] = s; }
+            for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) { double s = 0; for (int k = 0; k < 6; ++k) s += T[6*i+k]*Phi[6*j+k]; S[6*i+j] = s; }
+            for (int i = 0; i < 36; ++i) me->P[i] += S[i];
+        }
+        double PH[MAXD][6], D[MAXD*MAXD];
+        for (int j = 0; j < d; ++j) mat6vec(me->P, me->H[j], PH[j]);
+        for (int i = 0; i < d; ++i) for (int j = 0; j < d; ++j) { double s = 0; for (int k = 0; k < 6; ++k) s += me->H[i][k]*PH[j][k]; D[d*i+j] = s; }
+        if (!invertD(d, D, me->DI)) ok = 0;
+        for (int j = 0; j < d; ++j) for (int k = 0; k < 6; ++k) { double s = 0; for (int i = 0; i < d; ++i) s += PH[i][k]*me->DI[d*i+j]; me->Gm[j][k] = s; }
+        for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) { double s = 0; for (int k = 0; k < d; ++k) s += me->Gm[k][i]*PH[k][j]; me->PP[6*i+j] = me->P[6*i+j] - s; }
+        for (int i = 0; i < 6; ++i) for (int j = i+1; j < 6; ++j) { double s = 0.5*(me->PP[6*i+j] + me->PP[6*j+i]); me->PP[6*i+j] = me->PP[6*j+i] = s; }
+        double Pa[6]; mat6vec(me->P, me->a, Pa); for (int i = 0; i < 6; ++i) me->zb[i] = Pa[i] + me->b[i];
+    }
+    return ok;
+}
+
+static void systemForces(const Model* M, Body* B, const double* q, const double* u, double* fmob) {
+    int nu = 0; for (int b = 1; b < M->nb; ++b) nu += B[b].nu;
+    for (int i = 0; i < nu; ++i) fmob[i] = 0;
+    for (int b = 0; b < M->nb; ++b) memset(B[b].Fapp, 0, sizeof B[b].Fapp);
+    for (int k = 0; k < M->nf; ++k) {
+        if (M->fkind[k] == F_GRAVITY) {
+            const double g[3] = {M->fa[k]*M->fdir[3*k], M->fa[k]*M->fdir[3*k+1], M->fa[k]*M->fdir[3*k+2]};
+            for (int b = 1; b < M->nb; ++b) { double F[3] = {B[b].m*g[0], B[b].m*g[1], B[b].m*g[2]}, t[3]; cross(B[b].c, F, t);
+                for (int i = 0; i < 3; ++i) { B[b].Fapp[i] += t[i]; B[b].Fapp[3+i] += F[i]; } }
+        } else if (M->fkind[k] == F_SPRING) { const Body* me = &B[M->fbody[k]]; fmob[me->u0 + M->fcoord[k]] += -M->fa[k]*(q[me->q0 + M->fcoord[k]] - M->fb[k]); }
+        else if (M->fkind[k] == F_DAMPER) { const Body* me = &B[M->fbody[k]]; fmob[me->u0 + M->fcoord[k]] += -M->fa[k]*u[me->u0 + M->fcoord[k]]; }
+    }
+}
+
+/* Sweeps D and E. withBias: z starts from P a + b - F (forward dynamics) or 0 (M^-1). */
+static void accelerations(const Model* M, Body* B, const double* fmob, int withBias, double* udot) {
+    for (int b = M->nb-1; b >= 1; --b) {
+        Body* me = &B[b]; const int d = me->nu;
+        for (int i = 0; i < 6; ++i) me->z[i] = withBias ? me->zb[i] - me->Fapp[i] : 0.0;
+        for (int c = b+1; c < M->nb; ++c) if (M->parent[c] == b) { double t[6]; phiF(B[c].l, B[c].zP, t); for (int i = 0; i < 6; ++i) me->z[i] += t[i]; }
+        for (int j = 0; j < d; ++j) { double s = 0; for (int k = 0; k < 6; ++k) s += me->H[j][k]*me->z[k]; me->eps[j] = fmob[me->u0+j] - s; }
+        for (int i = 0; i < 6; ++i) { double s = 0; for (int j = 0; j < d; ++j) s += me->Gm[j][i]*me->eps[j]; me->zP[i] = me->z[i] + s; }
+    }
+    memset(B[0].A, 0, sizeof B[0].A);
+    for (int b = 1; b < M->nb; ++b) {
+        Body* me = &B[b]; const int d = me->nu; double Ap[6];
+        phiT(me->l, B[M->parent[b]].A, Ap);
+        for (int i = 0; i < d; ++i) { double s = 0, g = 0; for (int j = 0; j < d; ++j) s += me->DI[d*i+j]*me->eps[j]; for (int k = 0; k < 6; ++k) g += me->Gm[i][k]*Ap[k]; udot[me->u0+i] = s - g; }
+        for (int k = 0; k < 6; ++k) { double s = 0; for (int j = 0; j < d; ++j) s += me->H[j][k]*udot[me->u0+j]; me->A[k] = Ap[k] + s + (withBias ? me->a[k] : 0.0); }
+    }
+}
+
+static void qdotdot(const Model* M, const Body* B, const double* q, const double* u, const double* udot, double* qdd) {
+    for (int b = 1; b < M->nb; ++b) {
+        const Body* me = &B[b]; const int jt = M->joint[b];
+        if (jt == BALL || jt == FREE) {
+            const double* w = u + me->u0; double Nb[4]; quatN(q + me->q0, udot + me->u0, Nb);
+            double k = -0.25*(w[0]*w[0] + w[1]*w[1] + w[2]*w[2]);
+            for (int i = 0; i < 4; ++i) qdd[me->q0+i] = Nb[i] + k*q[me->q0+i];
+            if (jt == FREE) for (int i = 0; i < 3; ++i) qdd[me->q0+4+i] = udot[me->u0+3+i];
+        } else for (int i = 0; i < me->nu; ++i) qdd[me->q0+i] = udot[me->u0+i];
+    }
+}
+
+/* M*v (withVel=0) or inverse dynamics residual (withVel=1). */
+static void inverseDynamics(const Model* M, Body* B, const double* udotIn, const double* fmob, const double* Fbody, int withVel, double* tau) {
+    memset(B[0].A, 0, sizeof B[0].A);
+    for (int b = 1; b < M->nb; ++b) {
+        Body* me = &B[b]; double Ap[6]; phiT(me->l, B[M->parent[b]].A, Ap);
+        for (int k = 0; k < 6; ++k) { double s = 0; for (int j = 0; j < me->nu; ++j) s += me->H[j][k]*(udotIn ? udotIn[me->u0+j] : 0.0); me->A[k] = Ap[k] + s + (withVel ? me->a[k] : 0.0); }
+    }
+    for (int b = M->nb-1; b >= 1; --b) {
+        Body* me = &B[b]; double F[6]; mkTimes(me, me->A, F);
+        if (withVel) for (int k = 0; k < 6; ++k) F[k] = F[k] + me->b[k] - (Fbody ? Fbody[6*b+k] : 0.0);
+        for (int c = b+1; c < M->nb; ++c) if (M->parent[c] == b) { double t[6]; phiF(B[c].l, B[c].zP, t); for (int k = 0; k < 6; ++k) F[k] += t[k]; }
+        memcpy(me->zP, F, sizeof F);
+        for (int j = 0; j < me->nu; ++j) { double s = 0; for (int k = 0; k < 6; ++k) s += me->H[j][k]*F[k]; tau[me->u0+j] = s - ((withVel && fmob) ? fmob[me->u0+j] : 0.0); }
+    }
+}
+
+static void derivs(const Model* M, Body* B, int nq, int nu, const double* y, double* ydot, double* qdd, double* qerr, double* fmobOut) {
+    double* fm = (double*)malloc(sizeof(double)*(size_t)(nu > 0 ? nu : 1));
+    kinematics(M, B, y, y+nq, ydot, qerr);
+    systemForces(M, B, y, y+nq, fm);
+    articulatedInertias(M, B);
+    accelerations(M, B, fm, 1, ydot+nq);
+    if (qdd) qdotdot(M, B, y, y+nq, ydot+nq, qdd);
+    if (fmobOut) memcpy(fmobOut, fm, sizeof(double)*(size_t)nu);
+    free(fm);
+}
+
+static Model mkModel(int nb, const int* parent, const int* joint, const double* mass, const double* com, const double* ui,
+                     const double* XPF, const double* XBM, int nf, const int* fkind, const int* fbody, const int* fcoord,
+                     const double* fa, const double* fb, const double* fdir) {
+    Model M; M.nb = nb; M.nf = nf; M.parent = parent; M.joint = joint; M.mass = mass; M.com = com; M.uinertia = ui; M.X_PF = XPF; M.X_BM = XBM;
+    M.fkind = fkind; M.fbody = fbody; M.fcoord = fcoord; M.fa = fa; M.fb = fb; M.fdir = fdir; return M;
+}
+
+/* Same instance-major binary layout as `ref_driver eval` (oracle/ref_driver.cpp). */
+int oracle_eval(int nb, const int* parent, const int* joint, const double* mass, const double* com, const double* ui,
+                const double* XPF, const double* XBM, int nf, const int* fkind, const int* fbody, const int* fcoord,
+                const double* fa, const double* fb, const double* fdir, int N, const double* in, double* out) {
+    Model M = mkModel(nb, parent, joint, mass, com, ui, XPF, XBM, nf, fkind, fbody, fcoord, fa, fb, fdir);
+    int nq, nu, nquat; Body* B = setupBodies(&M, &nq, &nu, &nquat);
+    const int inStride = nq + 5*nu + 6*nb;
+    double* ydot = (double*)malloc(sizeof(double)*(size_t)(nq+nu+1)); double* tmp = (double*)malloc(sizeof(double)*(size_t)(nu+1));
+    for (int k = 0; k < N; ++k) {
+        const double* p = in + (size_t)k*inStride; double* o = out;
+        const int outStride = nq + nu + nq + nquat + nb*12 + nb*6 + nb*6 + nu + nb*6 + 4*nu + nu + nb*6;
+        o = out + (size_t)k*outStride;
+        double* qdd = o + nq + nu; double* qerr = qdd + nq; double* X = qerr + nquat; double* V = X + nb*12; double* A = V + nb*6;
+        double* fsys = A + nb*6; double* Fsys = fsys + nu; double* Ma = Fsys + nb*6; double* MInv = Ma + nu; double* res = MInv + nu;
+        double* res0 = res + nu; double* udop = res0 + nu; double* Aop = udop + nu;
+        derivs(&M, B, nq, nu, p, ydot, qdd, qerr, fsys);
+        memcpy(o, ydot, sizeof(double)*(size_t)(nq+nu));
+        for (int b = 0; b < nb; ++b) { memcpy(X + 12*b, B[b].R, 9*sizeof(double)); memcpy(X + 12*b + 9, B[b].p, 3*sizeof(double));
+                                       memcpy(V + 6*b, B[b].V, 6*sizeof(double)); memcpy(A + 6*b, B[b].A, 6*sizeof(double)); memcpy(Fsys + 6*b, B[b].Fapp, 6*sizeof(double)); }
+        const double* pa = p + nq + nu; const double* pv = pa + nu; const double* pud = pv + nu; const double* pf = pud + nu; const double* pF = pf + nu;
+        inverseDynamics(&M, B, pa, NULL, NULL, 0, Ma);
+        accelerations(&M, B, pv, 0, MInv);
+        inverseDynamics(&M, B, pud, pf, pF, 1, res);
+        inverseDynamics(&M, B, NULL, NULL, NULL, 1, res0);
+        for (int b = 0; b < nb; ++b) memcpy(B[b].Fapp, pF + 6*b, 6*sizeof(double));
+        accelerations(&M, B, pf, 1, udop);
+        for (int b = 0; b < nb; ++b) memcpy(Aop + 6*b, B[b].A, 6*sizeof(double));
+        (void)tmp;
+    }
+    free(ydot); free(tmp); free(B);
+    return 0;
+}
+
+static double errNorm(const Model* M, const Body* B, int nq, int nu, const double* y1, const double* y0, const double* err, int infNorm) {
+    double qa = 0, ua = 0;
+    for (int i = 0; i < nu; ++i) { double a = fabs(y0[nq+i]), sc = a > 1.0 ? 1.0/a : 1.0, v = sc*err[nq+i]; if (infNorm) { if (fabs(v) > ua) ua = fabs(v); } else ua += v*v; }
+    for (int b = 1; b < M->nb; ++b) {
+        const Body* me = &B[b]; int first = 0;
+        if (M->joint[b] == BALL || M->joint[b] == FREE) { double du[3], o[4]; quatNInv(y1+me->q0, err+me->q0, du); quatN(y1+me->q0, du, o);
+            for (int i = 0; i < 4; ++i) { if (infNorm) { if (fabs(o[i]) > qa) qa = fabs(o[i]); } else qa += o[i]*o[i]; } first = 4; }
+        for (int i = first; i < me->nq; ++i) { double v = err[me->q0+i]; if (infNorm) { if (fabs(v) > qa) qa = fabs(v); } else qa += v*v; }
+    }
+    double qn = infNorm ? qa : (nq ? sqrt(qa/nq) : 0), un = infNorm ? ua : (nu ? sqrt(ua/nu) : 0);
+    return qn >= un ? qn : un;
+}
+
+/* in [N][ny]; out [N][ny+2]: y after nsteps, error norm of the last step, number of projections */
+int oracle_step(int nb, const int* parent, const int* joint, const double* mass, const double* com, const double* ui,
+                const double* XPF, const double* XBM, int nf, const int* fkind, const int* fbody, const int* fcoord,
+                const double* fa, const double* fb, const double* fdir, int N, const double* in, double* out,
+                double h, int nsteps, double accuracy, double consTol, int infNorm, int projectEveryStep) {
+    Model M = mkModel(nb, parent, joint, mass, com, ui, XPF, XBM, nf, fkind, fbody, fcoord, fa, fb, fdir);
+    int nq, nu, nquat; Body* B = setupBodies(&M, &nq, &nu, &nquat);
+    const int ny = nq + nu;
+    double* w = (double*)malloc(sizeof(double)*(size_t)ny*7);
+    double *y = w, *y0 = w+ny, *f0 = w+2*ny, *fa_ = w+3*ny, *fb_ = w+4*ny, *ys = w+5*ny, *er = w+6*ny;
+    for (int k = 0; k < N; ++k) {
+        memcpy(y, in + (size_t)k*ny, sizeof(double)*(size_t)ny);
+        double en = 0; int nproj = 0;
+        for (int s = 0; s < nsteps; ++s) {
+            derivs(&M, B, nq, nu, y, f0, NULL, NULL, NULL);
+            memcpy(y0, y, sizeof(double)*(size_t)ny);
+            for (int i = 0; i < ny; ++i) y[i] = y0[i] + (h/3)*f0[i];
+            derivs(&M, B, nq, nu, y, fa_, NULL, NULL, NULL);
+            for (int i = 0; i < ny; ++i) y[i] = y0[i] + (h/6)*(f0[i] + fa_[i]);
+            derivs(&M, B, nq, nu, y, fa_, NULL, NULL, NULL);
+            for (int i = 0; i < ny; ++i) y[i] = y0[i] + (h/8)*(f0[i] + 3*fa_[i]);
+            derivs(&M, B, nq, nu, y, fb_, NULL, NULL, NULL);
+            for (int i = 0; i < ny; ++i) { ys[i] = y0[i] + (h/2)*(f0[i] - 3*fa_[i] + 4*fb_[i]); y[i] = ys[i]; }
+            derivs(&M, B, nq, nu, y, fa_, NULL, NULL, NULL);
+            for (int i = 0; i < ny; ++i) { y[i] = y0[i] + (h/6)*(f0[i] + 4*fb_[i] + fa_[i]); er[i] = 0.2*fabs(y[i] - ys[i]); }
+            en = errNorm(&M, B, nq, nu, y, y0, er, infNorm);
+            if (nquat > 0 && !(en > 16.0*accuracy)) {
+                double acc = 0;
+                for (int b = 1; b < nb; ++b) if (joint[b] == BALL || joint[b] == FREE) { const double* qq = y + B[b].q0;
+                    double e = sqrt(qq[0]*qq[0] + qq[1]*qq[1] + qq[2]*qq[2] + qq[3]*qq[3]) - 1.0; if (infNorm) { if (fabs(e) > acc) acc = fabs(e); } else acc += e*e; }
+                double qn = infNorm ? acc : sqrt(acc/nquat);
+                if (qn > consTol || projectEveryStep) {
+                    for (int b = 1; b < nb; ++b) if (joint[b] == BALL || joint[b] == FREE) { double* qq = y + B[b].q0; double* ee = er + B[b].q0;
+                        double n = sqrt(qq[0]*qq[0] + qq[1]*qq[1] + qq[2]*qq[2] + qq[3]*qq[3]), dt = 0;
+                        for (int i = 0; i < 4; ++i) { qq[i] = qq[i]/n; dt += ee[i]*qq[i]; }
+                        for (int i = 0; i < 4; ++i) ee[i] -= dt*qq[i]; }
+                    ++nproj; en = errNorm(&M, B, nq, nu, y, y0, er, infNorm);
+                }
+            }
+        }
+        memcpy(out + (size_t)k*(ny+2), y, sizeof(double)*(size_t)ny);
+        out[(size_t)k*(ny+2)+ny] = en; out[(size_t)k*(ny+2)+ny+1] = nproj;
+    }
+    free(w); free(B);
+    return 0;
+}

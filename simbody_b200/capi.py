@@ -83,7 +83,8 @@ SYMBOLS = {
 
 
 def library_path():
-    return os.path.join(_HERE, "libsbk.so")
+    # SBK_LIB lets experiments load an alternative build of the same ABI (kernel tuning variants)
+    return os.environ.get("SBK_LIB") or os.path.join(_HERE, "libsbk.so")
 
 
 def load_library():

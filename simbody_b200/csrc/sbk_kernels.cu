@@ -13,7 +13,13 @@ namespace sbkd {
 
 namespace {
 
-constexpr int TPI_THREADS = 128;
+#ifndef SBK_TPI_THREADS
+#define SBK_TPI_THREADS 128
+#endif
+#ifndef SBK_TPI_MINBLOCKS
+#define SBK_TPI_MINBLOCKS 2
+#endif
+constexpr int TPI_THREADS = SBK_TPI_THREADS;
 
 __device__ __forceinline__ uint32_t smemAddr(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -60,7 +66,7 @@ __device__ __forceinline__ Ctx makeCtx(const KArgs& a, const unsigned char* tabl
 }
 
 template <int OP, bool STAGE>
-__global__ void __launch_bounds__(TPI_THREADS) tpiKernel(const KArgs a) {
+__global__ void __launch_bounds__(TPI_THREADS, SBK_TPI_MINBLOCKS) tpiKernel(const KArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t mbar;
     const unsigned char* tables = a.tables;

@@ -202,3 +202,66 @@ def rel_err(a, b):
     if a.size == 0:
         return 0.0
     return float(np.max(np.abs(a - b)) / max(1.0, float(np.max(np.abs(b)))))
+
+
+class COracle:
+    """ctypes view of build/libsbk_oracle.so (oracle/sbk_oracle.c, the plain-C restatement)."""
+
+    def __init__(self):
+        self.lib = ctypes.CDLL(os.path.join(ROOT, "build", "libsbk_oracle.so"))
+
+    @staticmethod
+    def _arrays(text):
+        jt = {"GROUND": 0, "PIN": 1, "SLIDER": 2, "UNIVERSAL": 3, "BALL": 4, "FREE": 5}
+        parent, joint, mass, com, ui, xpf, xbm = [], [], [], [], [], [], []
+        fk, fb, fc, fa, fbb, fd = [], [], [], [], [], []
+        for line in text.splitlines():
+            t = line.split()
+            if not t:
+                continue
+            if t[0] == "body":
+                v = [float(x) for x in t[4:]]
+                parent.append(int(t[2])); joint.append(jt[t[3]]); mass.append(v[0]); com += v[1:4]; ui += v[4:10]
+                xpf += v[10:22]; xbm += v[22:34]
+            elif t[0] == "gravity":
+                fk.append(1); fb.append(-1); fc.append(0); fa.append(float(t[1])); fbb.append(0.0); fd += [float(x) for x in t[2:5]]
+            elif t[0] == "spring":
+                fk.append(2); fb.append(int(t[1])); fc.append(int(t[2])); fa.append(float(t[3])); fbb.append(float(t[4])); fd += [0.0] * 3
+            elif t[0] == "damper":
+                fk.append(3); fb.append(int(t[1])); fc.append(int(t[2])); fa.append(float(t[3])); fbb.append(0.0); fd += [0.0] * 3
+        i32 = lambda a: np.ascontiguousarray(a if len(a) else [0], dtype=np.int32)
+        f64 = lambda a: np.ascontiguousarray(a if len(a) else [0.0], dtype=np.float64)
+        return (len(parent), i32(parent), i32(joint), f64(mass), f64(com), f64(ui), f64(xpf), f64(xbm),
+                len(fk), i32(fk), i32(fb), i32(fc), f64(fa), f64(fbb), f64(fd))
+
+    @staticmethod
+    def _cargs(arrs):
+        out = []
+        for a in arrs:
+            if isinstance(a, np.ndarray):
+                out.append(a.ctypes.data_as(ctypes.c_void_p))
+            else:
+                out.append(ctypes.c_int(a))
+        return out
+
+    def eval(self, info, inp):
+        inp = np.ascontiguousarray(inp, dtype=np.float64)
+        n = inp.shape[0]
+        out = np.zeros((n, info.eval_out_stride))
+        arrs = self._arrays(info.text)
+        rc = self.lib.oracle_eval(*self._cargs(arrs), ctypes.c_int(n), inp.ctypes.data_as(ctypes.c_void_p),
+                                  out.ctypes.data_as(ctypes.c_void_p))
+        assert rc == 0
+        return out
+
+    def step(self, info, y, h, nsteps, accuracy=1e-3, cons_tol=None, inf_norm=0, project_every=0):
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        n = y.shape[0]
+        out = np.zeros((n, info.nq + info.nu + 2))
+        arrs = self._arrays(info.text)
+        rc = self.lib.oracle_step(*self._cargs(arrs), ctypes.c_int(n), y.ctypes.data_as(ctypes.c_void_p),
+                                  out.ctypes.data_as(ctypes.c_void_p), ctypes.c_double(h), ctypes.c_int(nsteps),
+                                  ctypes.c_double(accuracy), ctypes.c_double(accuracy / 10 if cons_tol is None else cons_tol),
+                                  ctypes.c_int(inf_norm), ctypes.c_int(project_every))
+        assert rc == 0
+        return out

@@ -1,0 +1,134 @@
+"""CPU tests (no GPU): the oracle and the host logic.
+
+  * oracle/sbk_oracle.c (plain-C restatement) against the reference's recorded outputs
+    (tests/golden, produced by the UNMODIFIED reference) and against SURVEY.md section 8c values;
+  * the kernels' per-body math compiled for the host (tests/hostemu, test-only) against the same;
+  * when oracle/_ref is present, live differential runs against the compiled reference and the
+    lowering round trip (model -> Simbody system -> lowered model).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from _harness import COracle, HostEmu, ModelInfo, RefDriver, have_ref, rel_err, ROOT
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+MODELS = ["double_pendulum", "pin_chain", "mixed7", "humanoid30", "branched_tree"]
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+    if not (os.path.exists(os.path.join(ROOT, "build", "libsbk_oracle.so")) and os.path.exists(os.path.join(ROOT, "build", "libsbk_hostemu.so"))):
+        g.build()
+    return True
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_c_oracle_matches_reference_golden(built, name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    info = ModelInfo(str(g["text"]))
+    ref = info.split_eval_out(g["eval_out"])
+    got = info.split_eval_out(COracle().eval(info, g["eval_in"]))
+    for k in ref:
+        assert rel_err(got[k], ref[k]) < 1e-10, (name, k, rel_err(got[k], ref[k]))
+    ny = info.nq + info.nu
+    ys = COracle().step(info, g["step_in"], float(g["h"]), int(g["nsteps"]))
+    assert rel_err(ys[:, :ny], g["step_out"][:, :ny]) < 1e-10
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_kernel_math_on_host_matches_reference_golden(built, name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    info = ModelInfo(str(g["text"]))
+    ref = info.split_eval_out(g["eval_out"])
+    got = info.split_eval_out(HostEmu().eval(info, g["eval_in"]))
+    for k in ref:
+        assert rel_err(got[k], ref[k]) < 1e-11, (name, k, rel_err(got[k], ref[k]))
+    ny = info.nq + info.nu
+    ys = HostEmu().step(info, g["step_in"], float(g["h"]), int(g["nsteps"]))
+    assert rel_err(ys[:, :ny], g["step_out"][:, :ny]) < 1e-10
+
+
+def test_survey_golden_double_pendulum(built):
+    """README double pendulum at q=(0.3,-0.7), u=(1.1,-0.4)."""
+    info = ModelInfo(HostEmu().model_text("double_pendulum"))
+    inp = np.zeros((1, info.eval_in_stride))
+    inp[0, :4] = [0.3, -0.7, 1.1, -0.4]
+    inp[0, 4:6] = [0.25, -1.5]      # a for M*a
+    inp[0, 6:8] = [0.25, -1.5]      # v for M^-1 v
+    inp[0, 8:10] = [0.25, -1.5]     # known udot for the residual
+    for impl in (COracle(), HostEmu()):
+        o = info.split_eval_out(impl.eval(info, inp))
+        assert np.allclose(o["udot"][0], [-2.9050308120918449, 6.3138774504076149], rtol=1e-13)
+        assert np.allclose(o["Ma"][0], [-2.5148421872844886, -2.308789453178878], rtol=1e-13)
+        assert np.allclose(o["MInvv"][0], [0.85821776207819422, -1.9364183372353365], rtol=1e-13)
+        assert np.allclose(o["resid"][0], [-2.978678922095626, -3.0882928547364843], rtol=1e-13)
+
+
+def test_survey_golden_mixed_fixture(built):
+    """mixed Free/Ball/Universal/Pin/Slider tree, xorshift64 state."""
+    info = ModelInfo(HostEmu().model_text("mixed7"))
+    assert (info.nb, info.nq, info.nu) == (7, 16, 14)
+    z = 88172645463325252
+    vals = []
+    for _ in range(30):
+        z ^= (z << 13) & 0xFFFFFFFFFFFFFFFF; z ^= z >> 7; z ^= (z << 17) & 0xFFFFFFFFFFFFFFFF
+        vals.append((z >> 11) / 2.0**53 * 2 - 1)
+    q, u = np.array(vals[:16]), np.array(vals[16:])
+    q[0:4] /= np.linalg.norm(q[0:4]); q[7:11] /= np.linalg.norm(q[7:11])
+    assert abs(q[0] - (-0.042694314853977691)) < 1e-15 and abs(u[0] - (-0.99110031744089322)) < 1e-15
+    udot_ref = [0.17422288626456839, -0.069420612369921753, -0.26318985600444844, -1.7890383082053554, -10.348226139581147,
+                -0.016958149641840503, 0.29386900582164843, -1.5669639987250292, -0.22674220709203174, 2.4868968324497542,
+                -0.64761928335628627, -1.2002467096587237, -1.1624387427364304, -0.50966663220061525]
+    inp = np.zeros((1, info.eval_in_stride)); inp[0, :16] = q; inp[0, 16:30] = u
+    for impl in (COracle(), HostEmu()):
+        o = info.split_eval_out(impl.eval(info, inp))
+        assert rel_err(o["udot"][0], np.array(udot_ref)) < 1e-12
+
+
+def test_quaternion_projection_rule(built):
+    """Quaternions are normalised only when RMS(|q|-1) > consTol or when forced
+    (SimbodyMatterSubsystemRep.cpp:4160); both restatements must agree on when."""
+    info = ModelInfo(HostEmu().model_text("mixed7"))
+    q, u = info.random_states(4, 11, q_scale=0.3)
+    y = np.concatenate([q, u], axis=1)
+    ny = info.nq + info.nu
+    for kw in (dict(), dict(project_every=1), dict(cons_tol=1e-14)):
+        a = HostEmu().step(info, y, 5e-3, 20, **kw); b = COracle().step(info, y, 5e-3, 20, **kw)
+        assert rel_err(a[:, :ny], b[:, :ny]) < 1e-10
+        assert np.array_equal(a[:, ny + 1], b[:, ny + 1])
+    forced = HostEmu().step(info, y, 5e-3, 20, project_every=1)
+    assert np.all(forced[:, ny + 1] == 20)
+    qn = np.linalg.norm(forced[:, 0:4], axis=1)
+    assert np.allclose(qn, 1.0, atol=1e-15)
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("name,n", [("double_pendulum", 0), ("pin_chain", 12), ("mixed7", 0), ("humanoid30", 0), ("branched_tree", 33)])
+def test_live_reference_differential(built, name, n):
+    emu, ref, co = HostEmu(), RefDriver(), COracle()
+    text = emu.model_text(name, n)
+    info = ModelInfo(text)
+    assert ref.lower(text) == text        # lowering a realized Simbody system reproduces the spec bit for bit
+    inp = info.random_eval_input(12, 321, q_scale=0.6)
+    r = info.split_eval_out(ref.eval(info, inp))
+    for impl, tol in ((emu, 1e-11), (co, 1e-10)):
+        g = info.split_eval_out(impl.eval(info, inp))
+        for k in r:
+            assert rel_err(g[k], r[k]) < tol, (name, k)
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
+def test_slot_rules_match_reference(built):
+    """q/u slots follow MobilizedBodyIndex order with max-nq (RigidBodyNodeSpec.h:81-87)."""
+    text = HostEmu().model_text("mixed7")
+    info = ModelInfo(text)
+    lines = RefDriver().slots(text).splitlines()
+    assert lines[0].split() == ["nb", "7", "nq", "16", "nu", "14", "nquat", "2"]
+    for b, line in enumerate(lines[1:]):
+        t = line.split()
+        if b == 0:
+            continue
+        assert int(t[3]) == info.q0[b] and int(t[7]) == info.u0[b]
