@@ -141,6 +141,11 @@ int sbk_model_text(const char* name, int n, char* buf, int cap) {
 }
 
 // ---- batch --------------------------------------------------------------------------------
+static bool fusedOk(const sbk_batch* b) {
+    std::vector<int> joints(b->topo->nb);
+    for (int i = 0; i < b->topo->nb; ++i) joints[i] = b->topo->bodies[i].joint;
+    return b->topo->isChain && fusedPlanSupports(b->topo->nb, joints.data());
+}
 sbk_batch* sbk_batch_create(const sbk_topology* t, int n, int device, void* stream) {
     if (!t || n < 1) { fail(SBK_ERR_ARG, "sbk_batch_create: bad arguments"); return nullptr; }
     int ndev = 0;
@@ -209,6 +214,7 @@ sbk_batch* sbk_batch_create(const sbk_topology* t, int n, int device, void* stre
     if (cudaStreamSynchronize(b->stream) != cudaSuccess) return bail(std::string("batch init failed: ") + cudaGetErrorString(cudaGetLastError()));
     sbk_rkm_opts o; sbk_rkm_default_opts(&o);
     a.accuracy = o.accuracy; a.consTol = o.constraint_tol;
+    b->plan = fusedOk(b) ? 2 : 1;
     return b;
 }
 void sbk_batch_destroy(sbk_batch* b) {
@@ -225,8 +231,13 @@ void sbk_batch_destroy(sbk_batch* b) {
 int sbk_batch_size(const sbk_batch* b) { return b ? b->N : 0; }
 int sbk_batch_set_plan(sbk_batch* b, int plan) {
     if (!b) return fail(SBK_ERR_ARG, "null batch");
-    if (plan != 0 && plan != 1) return fail(SBK_ERR_ARG, "sbk_batch_set_plan: only plan 0 (auto) and 1 (thread-per-instance) are available in this build");
-    b->plan = 1; return SBK_OK;
+    if (plan == 0) { b->plan = fusedOk(b) ? 2 : 1; return SBK_OK; }
+    if (plan == 1) { b->plan = 1; return SBK_OK; }
+    if (plan == 2) {
+        if (!fusedOk(b)) return fail(SBK_ERR_ARG, "sbk_batch_set_plan: the register-resident fused plan needs a serial chain of 1-2 Pin/Slider mobilizers");
+        b->plan = 2; return SBK_OK;
+    }
+    return fail(SBK_ERR_ARG, "sbk_batch_set_plan: plan 3 (level-parallel) is not available in this build");
 }
 int sbk_batch_get_plan(const sbk_batch* b) { return b ? b->plan : 0; }
 int sbk_synchronize(sbk_batch* b) {
@@ -464,7 +475,11 @@ int sbk_rkm_step(sbk_batch* b, double h, int nsteps, const sbk_rkm_opts* opts, d
     a.useInfNorm = o.use_infinity_norm; a.projectEveryStep = o.project_every_step;
     if (nsteps > 0) {
         CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
-        if (int rc = launch(b, OP_RKM)) return rc;
+        if (b->plan == 2) {
+            std::vector<int> joints(b->topo->nb);
+            for (int i = 0; i < b->topo->nb; ++i) joints[i] = b->topo->bodies[i].joint;
+            CUDA_TRY(launchFusedRkm(a, joints.data(), b->stream)); b->launches++;
+        } else if (int rc = launch(b, OP_RKM)) return rc;
         CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
         invalidate(b);
         b->stepsTaken += (int64_t)nsteps*b->N; b->realizations += (int64_t)5*nsteps*b->N;

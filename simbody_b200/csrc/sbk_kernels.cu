@@ -8,6 +8,7 @@
 // broadcasts.  FP64 throughout; no tensor cores (6x6 spatial operators are not a dense
 // contraction).
 #include "sbk_kernels.cuh"
+#include "sbk_fused.cuh"
 
 namespace sbkd {
 
@@ -17,7 +18,7 @@ namespace {
 #define SBK_TPI_THREADS 128
 #endif
 #ifndef SBK_TPI_MINBLOCKS
-#define SBK_TPI_MINBLOCKS 2
+#define SBK_TPI_MINBLOCKS 4
 #endif
 constexpr int TPI_THREADS = SBK_TPI_THREADS;
 
@@ -74,23 +75,24 @@ __global__ void __launch_bounds__(TPI_THREADS, SBK_TPI_MINBLOCKS) tpiKernel(cons
     const int inst = blockIdx.x*blockDim.x + threadIdx.x;
     if (inst >= a.N) return;
     Ctx c = makeCtx(a, tables, inst);
+    Carry cy; resetCarry(cy);
 
     if constexpr (OP == OP_KIN) {
-        tpiKinematics(c);
+        tpiKinematics<false>(c, cy);
     } else if constexpr (OP == OP_ABI) {
-        tpiInward<IN_ABI>(c);
+        tpiInward<IN_ABI, false>(c, cy);
     } else if constexpr (OP == OP_EVAL) {
-        tpiEvalDerivatives(c);
+        tpiEvalDerivatives<false>(c, cy);
     } else if constexpr (OP == OP_CALCACC) {
-        tpiInward<IN_Z | IN_BIAS>(c);
-        tpiOutward<true>(c, c.vecOut, nullptr);
+        tpiInward<IN_Z | IN_BIAS, false>(c, cy);
+        tpiOutward<true, false>(c, cy, c.vecOut, nullptr);
     } else if constexpr (OP == OP_MULM) {
         for (int b = 1; b < c.nb; ++b) idOutDispatch<false>(c, b);
         for (int b = c.nb - 1; b >= 1; --b) idInDispatch<false>(c, b);
     } else if constexpr (OP == OP_MULMINV) {
         c.fmobIn = a.vecIn; c.FbodyIn = nullptr;
-        tpiInward<IN_Z>(c);
-        tpiOutward<false>(c, c.vecOut, nullptr);
+        tpiInward<IN_Z, false>(c, cy);
+        tpiOutward<false, false>(c, cy, c.vecOut, nullptr);
     } else if constexpr (OP == OP_RESID) {
         for (int b = 1; b < c.nb; ++b) idOutDispatch<true>(c, b);
         for (int b = c.nb - 1; b >= 1; --b) idInDispatch<true>(c, b);
@@ -100,12 +102,43 @@ __global__ void __launch_bounds__(TPI_THREADS, SBK_TPI_MINBLOCKS) tpiKernel(cons
         w.accuracy = a.accuracy; w.consTol = a.consTol; w.useInfNorm = a.useInfNorm; w.projectEveryStep = a.projectEveryStep;
         RkmStepResult r; r.errNorm = 0; r.projected = 0;
         int nproj = 0; double t = a.tcur[inst];
-        for (int s = 0; s < a.nsteps; ++s) { r = tpiRkmStep(c, w, a.h); nproj += r.projected; t += a.h; }
+        for (int s = 0; s < a.nsteps; ++s) { r = tpiRkmStep<true>(c, w, a.h, cy); nproj += r.projected; t += a.h; }
         a.tcur[inst] = t;
         a.errNorm[inst] = r.errNorm;
         a.projCount[inst] += nproj;
         if (c.status && !(r.errNorm == r.errNorm)) *c.status |= 1;   // NaN error norm
     }
+}
+
+// Register-resident fused plan: the whole multi-step RKM loop of one instance in one thread.
+template <class E>
+__global__ void __launch_bounds__(128) fusedRkmKernel(const KArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ __align__(8) uint64_t mbar;
+    tmaStage(smem, a.tables, a.tableBytes, &mbar);
+    const int inst = blockIdx.x*blockDim.x + threadIdx.x;
+    if (inst >= a.N) return;
+    const BodyConst* bodies = reinterpret_cast<const BodyConst*>(smem);
+    E e; e.b0 = &bodies[1]; e.b1 = &bodies[E::NB - 1];
+    e.forces = reinterpret_cast<const ForceConst*>(smem + a.forcesOff);
+    e.gx = a.gx; e.gy = a.gy; e.gz = a.gz;
+    double y[E::NY];
+#pragma unroll
+    for (int i = 0; i < E::NY; ++i) y[i] = a.y[(long long)i*a.N + inst];
+    double err = 0;
+    for (int s = 0; s < a.nsteps; ++s) err = fusedRkmStep(e, y, a.h, a.useInfNorm);
+#pragma unroll
+    for (int i = 0; i < E::NY; ++i) a.y[(long long)i*a.N + inst] = y[i];
+    a.tcur[inst] += a.nsteps*a.h;
+    a.errNorm[inst] = err;
+    if (a.status && !(err == err)) a.status[inst] |= 1;
+}
+template <class E>
+cudaError_t launchFusedT(const KArgs& a, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(fusedRkmKernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.tableBytes);
+    if (e != cudaSuccess) return e;
+    fusedRkmKernel<E><<<(a.N + 127)/128, 128, a.tableBytes, stream>>>(a);
+    return cudaGetLastError();
 }
 
 template <int OP>
@@ -170,6 +203,30 @@ cudaError_t launchTpi(KernelOp op, const KArgs& a, cudaStream_t stream) {
         case OP_MULMINV: return launchOp<OP_MULMINV>(a, stream);
         case OP_RESID:   return launchOp<OP_RESID>(a, stream);
         case OP_RKM:     return launchOp<OP_RKM>(a, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+bool fusedPlanSupports(int nb, const int* joints) {
+    auto simple = [](int j) { return j == JT_PIN || j == JT_SLIDER; };
+    if (nb == 2) return simple(joints[1]) || joints[1] == JT_UNIVERSAL;
+    if (nb == 3) return simple(joints[1]) && simple(joints[2]);
+    return false;
+}
+cudaError_t launchFusedRkm(const KArgs& a, const int* joints, cudaStream_t stream) {
+    if (a.nb == 2) {
+        switch (joints[1]) {
+            case JT_PIN:       return launchFusedT<Chain1<JT_PIN>>(a, stream);
+            case JT_SLIDER:    return launchFusedT<Chain1<JT_SLIDER>>(a, stream);
+            case JT_UNIVERSAL: return launchFusedT<Chain1<JT_UNIVERSAL>>(a, stream);
+        }
+    } else if (a.nb == 3) {
+        const int k = joints[1]*10 + joints[2];
+        switch (k) {
+            case JT_PIN*10 + JT_PIN:       return launchFusedT<Chain2<JT_PIN, JT_PIN>>(a, stream);
+            case JT_PIN*10 + JT_SLIDER:    return launchFusedT<Chain2<JT_PIN, JT_SLIDER>>(a, stream);
+            case JT_SLIDER*10 + JT_PIN:    return launchFusedT<Chain2<JT_SLIDER, JT_PIN>>(a, stream);
+            case JT_SLIDER*10 + JT_SLIDER: return launchFusedT<Chain2<JT_SLIDER, JT_SLIDER>>(a, stream);
+        }
     }
     return cudaErrorInvalidValue;
 }

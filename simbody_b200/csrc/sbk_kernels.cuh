@@ -44,6 +44,9 @@ enum KernelOp {
 
 // Launch one operation for the thread-per-instance plan on `stream`.
 cudaError_t launchTpi(KernelOp op, const KArgs& a, cudaStream_t stream);
+// Register-resident fused plan (serial chains of 1-2 Pin/Slider[/Universal] mobilizers).
+bool fusedPlanSupports(int nb, const int* joints /*[nb]*/);
+cudaError_t launchFusedRkm(const KArgs& a, const int* joints, cudaStream_t stream);
 // Ground record (identity transform, zero velocity/acceleration) for every instance.
 cudaError_t launchInitGround(double* cache, int N, cudaStream_t stream);
 // dst[k*len + i] <-> src[i*N + k]

@@ -29,6 +29,7 @@ SBK_HD double rkmErrorNorm(const Ctx& c, const RkmWork& w) {
     const int nq = c.nq, nu = c.nu;
     double qAcc = 0, uAcc = 0;
     // u part: uScale_i = |u0_i| > 1 ? 1/|u0_i| : 1   (calcRelativeScaling, frozen at step start)
+#pragma unroll 8
     for (int i = 0; i < nu; ++i) {
         const double u0 = fabs(ldS(c, w.y0, nq + i));
         const double sc = (u0*1.0 > 1.0) ? 1.0/u0 : 1.0;
@@ -60,31 +61,37 @@ SBK_HD double rkmErrorNorm(const Ctx& c, const RkmWork& w) {
     return qNorm >= uNorm ? qNorm : uNorm;
 }
 
-SBK_HD RkmStepResult tpiRkmStep(Ctx c, const RkmWork& w, const double h) {
+template <bool LEAN>
+SBK_HD RkmStepResult tpiRkmStep(Ctx c, const RkmWork& w, const double h, Carry& cy) {
     const int nq = c.nq, ny = c.nq + c.nu;
     const long long uoff = (long long)nq*c.sStride;
     c.q = w.y; c.u = w.y + uoff; c.qdotdot = nullptr; c.qerr = nullptr;
     c.fmobOut = nullptr; c.FbodyOut = nullptr;
 
     // f0 = f(y0): AbstractIntegratorRep.cpp:393 realizeStateDerivatives at the start of the step
-    c.qdot = w.f0; c.udot = w.f0 + uoff; tpiEvalDerivatives(c);
+    c.qdot = w.f0; c.udot = w.f0 + uoff; tpiEvalDerivatives<LEAN>(c, cy);
+#pragma unroll 8
     for (int i = 0; i < ny; ++i) {
         const double y0 = ldS(c, w.y, i);
         stS(c, w.y0, i, y0);
         stS(c, w.y, i, y0 + (h/3)*ldS(c, w.f0, i));
     }
-    c.qdot = w.fa; c.udot = w.fa + uoff; tpiEvalDerivatives(c);                     // f1
+    c.qdot = w.fa; c.udot = w.fa + uoff; tpiEvalDerivatives<LEAN>(c, cy);                     // f1
+#pragma unroll 8
     for (int i = 0; i < ny; ++i)
         stS(c, w.y, i, ldS(c, w.y0, i) + (h/6)*(ldS(c, w.f0, i) + ldS(c, w.fa, i)));
-    tpiEvalDerivatives(c);                                                          // f2 -> fa
+    tpiEvalDerivatives<LEAN>(c, cy);                                                          // f2 -> fa
+#pragma unroll 8
     for (int i = 0; i < ny; ++i)
         stS(c, w.y, i, ldS(c, w.y0, i) + (h/8)*(ldS(c, w.f0, i) + 3*ldS(c, w.fa, i)));
-    c.qdot = w.fb; c.udot = w.fb + uoff; tpiEvalDerivatives(c);                     // f3 -> fb
+    c.qdot = w.fb; c.udot = w.fb + uoff; tpiEvalDerivatives<LEAN>(c, cy);                     // f3 -> fb
+#pragma unroll 8
     for (int i = 0; i < ny; ++i) {
         const double ys = ldS(c, w.y0, i) + (h/2)*(ldS(c, w.f0, i) - 3*ldS(c, w.fa, i) + 4*ldS(c, w.fb, i));
         stS(c, w.ys, i, ys); stS(c, w.y, i, ys);
     }
-    c.qdot = w.fa; c.udot = w.fa + uoff; tpiEvalDerivatives(c);                     // f4 -> fa
+    c.qdot = w.fa; c.udot = w.fa + uoff; tpiEvalDerivatives<LEAN>(c, cy);                     // f4 -> fa
+#pragma unroll 8
     for (int i = 0; i < ny; ++i) {
         const double y1 = ldS(c, w.y0, i) + (h/6)*(ldS(c, w.f0, i) + 4*ldS(c, w.fb, i) + ldS(c, w.fa, i));
         stS(c, w.y, i, y1);

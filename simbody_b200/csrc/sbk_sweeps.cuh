@@ -1,20 +1,23 @@
-// sbk_sweeps.cuh -- per-body steps of the O(n) sweeps and the per-instance drivers.
+// sbk_sweeps.cuh -- per-body steps of the O(n) sweeps.
 //
-// One *work item* runs these functions for one (instance, body) pair.  The functions are
-// written once and used by every execution plan (thread-per-instance, register-resident
-// fused, level-parallel); plans differ only in the Cache/State accessor types they pass in
-// and in who loops over bodies.
+// Structure
+//   *Core functions*  pure register arithmetic for ONE body of ONE instance (no memory
+//                     traffic): kinCore (sweeps A+B), abiCore (sweep C + bias), zCore (sweep D),
+//                     accCore (sweep E), qddCore, forceCore.
+//   *Body wrappers*   move a body's data between the cores and the per-body cache records in
+//                     HBM (thread-per-instance and level-parallel plans), optionally in LEAN
+//                     mode: parent->child and child->parent links ride in a per-thread carry
+//                     (registers / L1-resident stack) and only what a later sweep needs is stored.
+//   The register-resident fused plan (sbk_fused.cuh) calls the cores directly.
 //
-// Sweeps (reference file:line each one replaces)
-//   kinBody      sweeps A+B, base->tip   RigidBodyNodeSpec.h:229-333, RigidBodyNodeSpec.cpp:44-129,
-//                                        RigidBodyNode.cpp:54-174, RigidBodyNodeSpec_{Pin,Slider,
-//                                        Universal,Ball,Free}.h
-//   inwardBody   sweeps C(+bias)+D, tip->base
-//                                        RigidBodyNodeSpec.cpp:249-325 (ABI), RigidBodyNode.cpp:201-213
-//                                        (P*a+b), :355-400 (z, eps, zPlus), :483-515 (M^-1 pass 1),
-//                                        Force_Gravity.cpp:514-569, Force.cpp:339-351,434-443
-//   outwardBody  sweep E, base->tip      RigidBodyNodeSpec.cpp:408-446, :521-552, calcQDotDot
-//   mulMOut/In, residOut/In              RigidBodyNodeSpec.cpp:566-695
+// Reference file:line each core replaces
+//   kinCore   RigidBodyNodeSpec.h:229-333,554-569; RigidBodyNodeSpec.cpp:44-129;
+//             RigidBodyNode.cpp:54-174; RigidBodyNodeSpec_{Pin,Slider,Universal,Ball,Free}.h
+//   abiCore   RigidBodyNodeSpec.cpp:249-325 (ABI), RigidBodyNode.cpp:201-213 (P*a+b)
+//   zCore     RigidBodyNodeSpec.cpp:355-400 (forward dynamics), :483-515 (M^-1 pass 1)
+//   accCore   RigidBodyNodeSpec.cpp:408-446, :521-552
+//   forces    Force_Gravity.cpp:514-569, Force.cpp:339-351,434-443
+//   idOut/idIn (M*v, inverse dynamics) RigidBodyNodeSpec.cpp:566-695
 //
 // Per-body cache record (doubles), dof = d:
 //   XGB 12 | VGB 6 | L 3 | MK 9 (c_G, G_G) | ACOR 6 | GYRO 6 | ZB 6 | PPLUS 21 | ZPLUS 6 | AGB 6 |
@@ -43,6 +46,10 @@ SBK_HD constexpr int fEPS(int d) { return F_H + 12*d + d*d; }
 SBK_HD constexpr int cacheRecordSize(int d) { return F_H + 13*d + d*d; }
 enum { CACHE_RECORD_MAX = F_H + 13*6 + 36 };   // 195
 
+// body flags
+enum { BF_PARENT_PREV = 1,   // parent is the body processed just before (index - 1): links ride in the carry
+       BF_STORE_LINK  = 2 }; // some child is NOT index + 1: links must also be stored in the cache
+
 // Per-body constants (batch-shared; staged into shared memory by the kernels).
 struct BodyConst {
     double X_PF[12];        // R_PF row-major, p_PF
@@ -54,7 +61,7 @@ struct BodyConst {
     long long parentCacheBase;
     int joint, parent, q0, u0;
     int nchild, childStart, quat, nforce;
-    int forceStart, level, pad0, pad1;
+    int forceStart, level, flags, pad1;
 };
 struct ForceConst { int kind; int coord; double a; double b; };
 
@@ -77,6 +84,14 @@ struct Ctx {
     double* fmobOut; double* FbodyOut;              // force-subsystem results (getter)
     const double* vecIn; double* vecOut;            // generic nu-vectors for M, M^-1, residual
     int* status;                                    // per-instance status word
+};
+
+// Links between consecutive bodies of one instance, kept by the thread that walks the tree.
+struct Carry {
+    M3 R; V3 p; SV V;        // X_GB, V_GB of the last body visited by an outward sweep
+    SV A;                    // A_GB of the last body visited by sweep E
+    ABI PP; SV zP; V3 l;     // P+, z+ and Phi.l of the last body visited by an inward sweep
+    int outBody, inBody;
 };
 
 struct CacheRef {     // accessor for one body's record
@@ -126,25 +141,26 @@ SBK_HD V3 quatNInvTimes(const double* q, const double* qd) {
 }
 
 //==============================================================================================
-// Sweeps A+B for one body (base->tip).  Needs the parent's XGB/VGB already in the cache.
+//                                        CORES
 //==============================================================================================
+template <int d> struct KinOut {     // results of sweeps A+B for one body
+    M3 R; V3 p; SV V;                // X_GB, V_GB
+    SV H[d]; V3 l; V3 c; S3 G;       // H_PB_G columns, Phi.l, com in G, unit inertia in G
+    SV acor, gyro;                   // mobilizer coriolis acceleration a, gyroscopic force b
+};
+
 template <int JT>
-SBK_HDN void kinBody(const Ctx& c, const BodyConst& bc) {
-    constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
-    const CacheRef me = cacheOf(c, bc.cacheBase), pa = cacheOf(c, bc.parentCacheBase);
-
-    double q[NQ], u[d];
-#pragma unroll
-    for (int i = 0; i < NQ; ++i) q[i] = ldS(c, c.q, bc.q0 + i);
-#pragma unroll
-    for (int i = 0; i < d; ++i)  u[i] = ldS(c, c.u, bc.u0 + i);
-
+SBK_HD void kinCore(const BodyConst& bc, const double* q, const double* u,
+                    const M3& R_GP, const V3 p_GP, const SV V_GP,
+                    KinOut<JointDims<JT>::nu>& o, double* qdot, double& qerr) {
+    constexpr int d = JointDims<JT>::nu;
     // ---- mobilizer-specific: X_FM, H_FM, HDot_FM (all expressed in F) ----------------------
     M3 R_FM; V3 p_FM = zero3();
     V3 Hw[d], Hv[d];          // H_FM columns (angular, linear)
     V3 HDw[d];                // HDot_FM angular part (linear part is zero for all five mobilizers)
 #pragma unroll
     for (int j = 0; j < d; ++j) { Hw[j] = zero3(); Hv[j] = zero3(); HDw[j] = zero3(); }
+    qerr = 0;
 
     if constexpr (JT == JT_PIN) {                 // RigidBodyNodeSpec_Pin.h:103-140
         double s, co; sincos(q[0], &s, &co);
@@ -164,7 +180,7 @@ SBK_HDN void kinBody(const Ctx& c, const BodyConst& bc) {
         Hw[1] = col(R_FM, 1);
     } else {                                      // Ball / Free: RigidBodyNodeSpec_Ball.h:113-180, _Free.h:142-222
         const double quatLen = sqrt(q[0]*q[0] + q[1]*q[1] + q[2]*q[2] + q[3]*q[3]);
-        if (c.qerr) stS(c, c.qerr, bc.quat, quatLen - 1.0);
+        qerr = quatLen - 1.0;
         const double oon = 1.0/quatLen;
         R_FM = rotFromQuat(q[0]*oon, q[1]*oon, q[2]*oon, q[3]*oon);
         Hw[0] = mk(1, 0, 0); Hw[1] = mk(0, 1, 0); Hw[2] = mk(0, 0, 1);
@@ -177,37 +193,31 @@ SBK_HDN void kinBody(const Ctx& c, const BodyConst& bc) {
     // ---- calcBodyTransforms (RigidBodyNodeSpec.h:554-569) ------------------------------------
     const M3 R_PF = loadR(bc.X_PF), R_MB = loadR(bc.X_MB);
     const V3 p_PF = loadP(bc.X_PF), p_MB = loadP(bc.X_MB);
-    const M3 R_GP = pa.ldM3(F_XGB); const V3 p_GP = pa.ld3(F_XGB + 9);
-    const SV V_GP = pa.ldSV(F_VGB);
 
     const V3 r     = mul(R_FM, p_MB);                 // r_MB_F = R_FM * p_MB
     const M3 R_FB  = mul(R_FM, R_MB);  const V3 p_FB = p_FM + r;
     const M3 R_PB  = mul(R_PF, R_FB);  const V3 p_PB = p_PF + mul(R_PF, p_FB);
-    const M3 R_GB  = mul(R_GP, R_PB);
-    const V3 l     = mul(R_GP, p_PB);                 // Phi: p_PB_G (RigidBodyNode.cpp:61)
-    const V3 p_GB  = p_GP + l;
-    me.stM3(F_XGB, R_GB); me.st3(F_XGB + 9, p_GB); me.st3(F_L, l);
+    o.R = mul(R_GP, R_PB);
+    o.l = mul(R_GP, p_PB);                            // Phi: p_PB_G (RigidBodyNode.cpp:61)
+    o.p = p_GP + o.l;
 
     // ---- H = R_GF (H_FM + H_MB_F)  (RigidBodyNodeSpec.cpp:44-74) -----------------------------
     const M3 R_GF = mul(R_GP, R_PF);
-    SV H[d];
 #pragma unroll
     for (int j = 0; j < d; ++j) {
-        H[j].w = mul(R_GF, Hw[j]);
-        H[j].v = mul(R_GF, Hv[j] + cross(Hw[j], r));  // H_MB_F[1] = -r x H_FM[0]
-        me.stSV(F_H + 6*j, H[j]);
+        o.H[j].w = mul(R_GF, Hw[j]);
+        o.H[j].v = mul(R_GF, Hv[j] + cross(Hw[j], r));  // H_MB_F[1] = -r x H_FM[0]
     }
 
     // ---- mass properties in Ground (RigidBodyNode.cpp:54-84) ---------------------------------
     S3 G_B; G_B.xx = bc.G_B[0]; G_B.yy = bc.G_B[1]; G_B.zz = bc.G_B[2]; G_B.xy = bc.G_B[3]; G_B.xz = bc.G_B[4]; G_B.yz = bc.G_B[5];
-    const S3 G_G = reexpressSym(R_GB, G_B);
-    const V3 c_G = mul(R_GB, mk(bc.com_B[0], bc.com_B[1], bc.com_B[2]));
-    me.st3(F_MK, c_G); me.stS3(F_MK + 3, G_G);
+    o.G = reexpressSym(o.R, G_B);
+    o.c = mul(o.R, mk(bc.com_B[0], bc.com_B[1], bc.com_B[2]));
 
     // ---- velocity (RigidBodyNodeSpec.h:305-333) ------------------------------------------------
     V3 w_FM = zero3(); SV V_PB = zeroSV();
 #pragma unroll
-    for (int j = 0; j < d; ++j) { w_FM = w_FM + u[j]*Hw[j]; V_PB = V_PB + u[j]*H[j]; }
+    for (int j = 0; j < d; ++j) { w_FM = w_FM + u[j]*Hw[j]; V_PB = V_PB + u[j]*o.H[j]; }
     if constexpr (JT == JT_UNIVERSAL) HDw[1] = cross(w_FM, col(R_FM, 1));   // _Universal.h:176-190
 
     // HDot (RigidBodyNodeSpec.cpp:82-129) and VD = HDot*u
@@ -217,138 +227,239 @@ SBK_HDN void kinBody(const Ctx& c, const BodyConst& bc) {
 #pragma unroll
     for (int j = 0; j < d; ++j) {
         SV HD;
-        HD.w = mul(R_GF, HDw[j]) + cross(w_GP, H[j].w);
-        HD.v = mul(R_GF, cross(HDw[j], r) + cross(Hw[j], wxr)) + cross(w_GP, H[j].v);
+        HD.w = mul(R_GF, HDw[j]) + cross(w_GP, o.H[j].w);
+        HD.v = mul(R_GF, cross(HDw[j], r) + cross(Hw[j], wxr)) + cross(w_GP, o.H[j].v);
         VD = VD + u[j]*HD;
     }
 
     // ---- joint-independent velocity kinematics (RigidBodyNode.cpp:97-174) ----------------------
-    const SV V_GB = phiT(l, V_GP) + V_PB;
-    me.stSV(F_VGB, V_GB);
-    const V3 w = V_GB.w;
-    SV gyro; gyro.w = bc.mass*cross(w, mul(G_G, w)); gyro.v = bc.mass*cross(w, cross(w, c_G));
-    me.stSV(F_GYRO, gyro);
-    SV acor; acor.w = VD.w; acor.v = VD.v + cross(w_GP, V_GB.v - v_GP);
-    me.stSV(F_ACOR, acor);
+    o.V = phiT(o.l, V_GP) + V_PB;
+    const V3 w = o.V.w;
+    o.gyro.w = bc.mass*cross(w, mul(o.G, w)); o.gyro.v = bc.mass*cross(w, cross(w, o.c));
+    o.acor.w = VD.w; o.acor.v = VD.v + cross(w_GP, o.V.v - v_GP);
 
     // ---- qdot = N(q) u  ------------------------------------------------------------------------
-    if (c.qdot) {
-        if constexpr (JT == JT_BALL || JT == JT_FREE) {
-            double qd[4]; quatNTimes(q, mk(u[0], u[1], u[2]), qd);
+    if constexpr (JT == JT_BALL || JT == JT_FREE) {
+        quatNTimes(q, mk(u[0], u[1], u[2]), qdot);
+        if constexpr (JT == JT_FREE) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) stS(c, c.qdot, bc.q0 + i, qd[i]);
-            if constexpr (JT == JT_FREE) {
+            for (int i = 0; i < 3; ++i) qdot[4+i] = u[3+i];
+        }
+    } else {
 #pragma unroll
-                for (int i = 0; i < 3; ++i) stS(c, c.qdot, bc.q0 + 4 + i, u[3+i]);
+        for (int i = 0; i < d; ++i) qdot[i] = u[i];
+    }
+}
+
+template <int d> struct AbiOut { SV G[d]; double DI[d*d]; ABI PP; SV zb; bool ok; };
+
+// Sweep C for one body, given P = Mk + sum of shifted children P+ (RigidBodyNodeSpec.cpp:249-325).
+template <int d>
+SBK_HD void abiCore(const ABI& P, const SV* H, const SV acor, const SV gyro, AbiOut<d>& o) {
+    SV PH[d];
+#pragma unroll
+    for (int j = 0; j < d; ++j) PH[j] = mul(P, H[j]);
+    double D[d*d];
+#pragma unroll
+    for (int i = 0; i < d; ++i)
+#pragma unroll
+        for (int j = 0; j < d; ++j) D[d*i+j] = dot(H[i].w, PH[j].w) + dot(H[i].v, PH[j].v);
+    o.ok = Inv<d>::run(D, o.DI);
+#pragma unroll
+    for (int j = 0; j < d; ++j) {
+        SV g = zeroSV();
+#pragma unroll
+        for (int k = 0; k < d; ++k) g = g + o.DI[d*k+j]*PH[k];
+        o.G[j] = g;
+    }
+    // PPlus = P - G*~PH, symmetrised (RigidBodyNodeSpec.cpp:309-324)
+    double mm[9], ms[9], in[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { mm[i] = 0; ms[i] = 0; in[i] = 0; }
+#pragma unroll
+    for (int k = 0; k < d; ++k) {
+        const double gw[3] = {o.G[k].w.x, o.G[k].w.y, o.G[k].w.z}, gv[3] = {o.G[k].v.x, o.G[k].v.y, o.G[k].v.z};
+        const double pw[3] = {PH[k].w.x, PH[k].w.y, PH[k].w.z}, pv[3] = {PH[k].v.x, PH[k].v.y, PH[k].v.z};
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                mm[3*i+j] += gw[i]*pv[j];    // massMoment = G.row(0)*~PH.row(1)
+                ms[3*i+j] += gv[i]*pv[j];    // mass       = G.row(1)*~PH.row(1)
+                in[3*i+j] += gw[i]*pw[j];    // inertia    = G.row(0)*~PH.row(0)
             }
-        } else {
+    }
+    o.PP.M.xx = P.M.xx - ms[0]; o.PP.M.yy = P.M.yy - ms[4]; o.PP.M.zz = P.M.zz - ms[8];
+    o.PP.M.xy = P.M.xy - (ms[3]+ms[1])/2; o.PP.M.xz = P.M.xz - (ms[6]+ms[2])/2; o.PP.M.yz = P.M.yz - (ms[7]+ms[5])/2;
+    o.PP.J.xx = P.J.xx - in[0]; o.PP.J.yy = P.J.yy - in[4]; o.PP.J.zz = P.J.zz - in[8];
+    o.PP.J.xy = P.J.xy - (in[3]+in[1])/2; o.PP.J.xz = P.J.xz - (in[6]+in[2])/2; o.PP.J.yz = P.J.yz - (in[7]+in[5])/2;
 #pragma unroll
-            for (int i = 0; i < d; ++i) stS(c, c.qdot, bc.q0 + i, u[i]);
+    for (int i = 0; i < 9; ++i) o.PP.F.a[i] = P.F.a[i] - mm[i];
+    // realizeArticulatedBodyVelocityCache (RigidBodyNode.cpp:201-213): P*a + b
+    o.zb = mul(P, acor) + gyro;
+}
+
+// Sweep D for one body: z already holds (P a + b - F) + sum Phi*z+ of the children.
+template <int d>
+SBK_HD void zCore(const SV* H, const SV* G, const SV z, const double* f, double* eps, SV& zPlus) {
+#pragma unroll
+    for (int j = 0; j < d; ++j) eps[j] = f[j] - (dot(H[j].w, z.w) + dot(H[j].v, z.v));
+    SV Ge = zeroSV();
+#pragma unroll
+    for (int j = 0; j < d; ++j) Ge = Ge + eps[j]*G[j];
+    zPlus = z + Ge;
+}
+
+// Sweep E for one body.
+template <int d, bool WITH_COR>
+SBK_HD void accCore(const SV* H, const SV* G, const double* DI, const double* eps, const V3 l, const SV A_GP,
+                    const SV acor, double* udot, SV& A) {
+    const SV APlus = phiT(l, A_GP);
+    SV Hu = zeroSV();
+#pragma unroll
+    for (int i = 0; i < d; ++i) {
+        double s = 0;
+#pragma unroll
+        for (int j = 0; j < d; ++j) s += DI[d*i+j]*eps[j];
+        udot[i] = s - (dot(G[i].w, APlus.w) + dot(G[i].v, APlus.v));
+        Hu = Hu + udot[i]*H[i];
+    }
+    A = APlus + Hu;
+    if constexpr (WITH_COR) A = A + acor;
+}
+
+// calcQDotDot (RigidBodyNodeSpec_Ball.h:355-390, _Free.h:418-455)
+template <int JT>
+SBK_HD void qddCore(const double* q, const double* u, const double* udot, double* qdd) {
+    constexpr int d = JointDims<JT>::nu;
+    if constexpr (JT == JT_BALL || JT == JT_FREE) {
+        const V3 w = mk(u[0], u[1], u[2]);
+        double Nb[4]; quatNTimes(q, mk(udot[0], udot[1], udot[2]), Nb);
+        const double k = -0.25*dot(w, w);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) qdd[i] = Nb[i] + k*q[i];
+        if constexpr (JT == JT_FREE) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) qdd[4+i] = udot[3+i];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < d; ++i) qdd[i] = udot[i];
+    }
+}
+
+// Force::Gravity on one body (Force_Gravity.cpp:538-556): F = (p_CB_G x m g, m g)
+SBK_HD SV gravityForce(const double mass, const V3 c_G, const double gx, const double gy, const double gz) {
+    const V3 Fc = mass*mk(gx, gy, gz);
+    SV F; F.w = cross(c_G, Fc); F.v = Fc; return F;
+}
+// MobilityLinearSpring / Damper of one body in force-index order (Force.cpp:339-351,434-443);
+// q, u are the body's own coordinates.
+template <int d>
+SBK_HD void mobilityForces(const BodyConst& bc, const ForceConst* forces, const double* q, const double* u, double* f) {
+#pragma unroll
+    for (int j = 0; j < d; ++j) f[j] = 0;
+    for (int k = 0; k < bc.nforce; ++k) {
+        const ForceConst fc = forces[bc.forceStart + k];
+#pragma unroll
+        for (int j = 0; j < d; ++j) if (j == fc.coord) {
+            const double frc = (fc.kind == FK_SPRING) ? -fc.a*(q[j] - fc.b) : -fc.a*u[j];
+            f[j] += frc;
         }
     }
 }
 
 //==============================================================================================
-// Inward body step.  MODE bits select what is done:
+//                     BODY WRAPPERS (cache records in HBM + per-thread carry)
+//==============================================================================================
+// LEAN = false: every field is stored (API realize path: getters and operators need them).
+// LEAN = true : integrator path; links ride in the carry when the tree order allows.
+
+template <int JT, bool LEAN>
+SBK_HDN void kinBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, Carry& cy) {
+    constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
+    const CacheRef me = cacheOf(c, bc.cacheBase);
+    double q[NQ], u[d], qdot[NQ], qerr;
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) q[i] = ldS(c, c.q, bc.q0 + i);
+#pragma unroll
+    for (int i = 0; i < d; ++i)  u[i] = ldS(c, c.u, bc.u0 + i);
+
+    M3 R_GP; V3 p_GP; SV V_GP;
+    if (LEAN && (bc.flags & BF_PARENT_PREV) && cy.outBody == bc.parent) { R_GP = cy.R; p_GP = cy.p; V_GP = cy.V; }
+    else { const CacheRef pa = cacheOf(c, bc.parentCacheBase); R_GP = pa.ldM3(F_XGB); p_GP = pa.ld3(F_XGB + 9); V_GP = pa.ldSV(F_VGB); }
+
+    KinOut<d> o;
+    kinCore<JT>(bc, q, u, R_GP, p_GP, V_GP, o, qdot, qerr);
+
+    if (!LEAN || (bc.flags & BF_STORE_LINK)) { me.stM3(F_XGB, o.R); me.st3(F_XGB + 9, o.p); me.stSV(F_VGB, o.V); }
+    cy.R = o.R; cy.p = o.p; cy.V = o.V; cy.outBody = bodyIndex;
+    me.st3(F_L, o.l); me.st3(F_MK, o.c); me.stS3(F_MK + 3, o.G);
+    me.stSV(F_ACOR, o.acor); me.stSV(F_GYRO, o.gyro);
+#pragma unroll
+    for (int j = 0; j < d; ++j) me.stSV(F_H + 6*j, o.H[j]);
+    if (c.qdot) {
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) stS(c, c.qdot, bc.q0 + i, qdot[i]);
+    }
+    if constexpr (JT == JT_BALL || JT == JT_FREE) { if (c.qerr) stS(c, c.qerr, bc.quat, qerr); }
+}
+
+// Inward body step.  MODE bits:
 //   IN_ABI    articulated-body inertia: P, D, DI, G, PPlus (+ ZB = P*a + b)
 //   IN_Z      residual pass: z, eps, zPlus
-//   IN_BIAS   z starts from ZB (forward dynamics); otherwise from 0 (M^-1)
+//   IN_BIAS   z starts from ZB - F (forward dynamics); otherwise from 0 (M^-1)
 //   IN_FORCES applied forces come from the lowered force elements (gravity/spring/damper)
 //             rather than from c.fmobIn / c.FbodyIn
-//==============================================================================================
 enum { IN_ABI = 1, IN_Z = 2, IN_BIAS = 4, IN_FORCES = 8 };
 
-template <int JT, int MODE>
-SBK_HDN void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex) {
-    constexpr int d = JointDims<JT>::nu;
+template <int JT, int MODE, bool LEAN>
+SBK_HDN void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, Carry& cy) {
+    constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
     const CacheRef me = cacheOf(c, bc.cacheBase);
-
     SV H[d];
 #pragma unroll
     for (int j = 0; j < d; ++j) H[j] = me.ldSV(F_H + 6*j);
-    SV G[d]; SV zb = zeroSV();
     const V3 c_G = me.ld3(F_MK);
+    const bool linkToCache = !LEAN || !(bc.flags & BF_PARENT_PREV);
 
+    AbiOut<d> ao; ao.zb = zeroSV();
     if constexpr ((MODE & IN_ABI) != 0) {
-        // ---- realizeArticulatedBodyInertiasInward (RigidBodyNodeSpec.cpp:249-325) -------------
         const S3 G_G = me.ldS3(F_MK + 3);
         ABI P = abiFromRigid(bc.mass, c_G, G_G);
         for (int k = 0; k < bc.nchild; ++k) {
-            const BodyConst& cb = c.bodies[c.children[bc.childStart + k]];
-            const CacheRef ch = cacheOf(c, cb.cacheBase);
-            addInto(P, shiftABI(ch.ldABI(F_PPLUS), ch.ld3(F_L)));
+            const int ci = c.children[bc.childStart + k];
+            if (LEAN && ci == cy.inBody) addInto(P, shiftABI(cy.PP, cy.l));
+            else { const CacheRef ch = cacheOf(c, c.bodies[ci].cacheBase); addInto(P, shiftABI(ch.ldABI(F_PPLUS), ch.ld3(F_L))); }
         }
-        SV PH[d];
+        abiCore<d>(P, H, me.ldSV(F_ACOR), me.ldSV(F_GYRO), ao);
+        if (!ao.ok && c.status) *c.status |= 2;
 #pragma unroll
-        for (int j = 0; j < d; ++j) PH[j] = mul(P, H[j]);
-        double D[d*d], DI[d*d];
+        for (int j = 0; j < d; ++j) me.stSV(fG(d) + 6*j, ao.G[j]);
 #pragma unroll
-        for (int i = 0; i < d; ++i)
-#pragma unroll
-            for (int j = 0; j < d; ++j) D[d*i+j] = dot(H[i].w, PH[j].w) + dot(H[i].v, PH[j].v);
-        const bool ok = Inv<d>::run(D, DI);
-        if (!ok && c.status) *c.status |= 2;
-#pragma unroll
-        for (int j = 0; j < d; ++j) {
-            SV g = zeroSV();
-#pragma unroll
-            for (int k = 0; k < d; ++k) g = g + DI[d*k+j]*PH[k];
-            G[j] = g; me.stSV(fG(d) + 6*j, g);
-        }
-#pragma unroll
-        for (int i = 0; i < d*d; ++i) me.st(fDI(d) + i, DI[i]);
-        // PPlus = P - G*~PH, symmetrised (RigidBodyNodeSpec.cpp:309-324)
-        double mm[9], ms[9], in[9];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) { mm[i] = 0; ms[i] = 0; in[i] = 0; }
-#pragma unroll
-        for (int k = 0; k < d; ++k) {
-            const double gw[3] = {G[k].w.x, G[k].w.y, G[k].w.z}, gv[3] = {G[k].v.x, G[k].v.y, G[k].v.z};
-            const double pw[3] = {PH[k].w.x, PH[k].w.y, PH[k].w.z}, pv[3] = {PH[k].v.x, PH[k].v.y, PH[k].v.z};
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    mm[3*i+j] += gw[i]*pv[j];    // massMoment = G.row(0)*~PH.row(1)
-                    ms[3*i+j] += gv[i]*pv[j];    // mass       = G.row(1)*~PH.row(1)
-                    in[3*i+j] += gw[i]*pw[j];    // inertia    = G.row(0)*~PH.row(0)
-                }
-        }
-        ABI PP;
-        PP.M.xx = P.M.xx - ms[0]; PP.M.yy = P.M.yy - ms[4]; PP.M.zz = P.M.zz - ms[8];
-        PP.M.xy = P.M.xy - (ms[3]+ms[1])/2; PP.M.xz = P.M.xz - (ms[6]+ms[2])/2; PP.M.yz = P.M.yz - (ms[7]+ms[5])/2;
-        PP.J.xx = P.J.xx - in[0]; PP.J.yy = P.J.yy - in[4]; PP.J.zz = P.J.zz - in[8];
-        PP.J.xy = P.J.xy - (in[3]+in[1])/2; PP.J.xz = P.J.xz - (in[6]+in[2])/2; PP.J.yz = P.J.yz - (in[7]+in[5])/2;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) PP.F.a[i] = P.F.a[i] - mm[i];
-        me.stABI(F_PPLUS, PP);
-        // realizeArticulatedBodyVelocityCache (RigidBodyNode.cpp:201-213): P*a + b
-        zb = mul(P, me.ldSV(F_ACOR)) + me.ldSV(F_GYRO);
-        me.stSV(F_ZB, zb);
+        for (int i = 0; i < d*d; ++i) me.st(fDI(d) + i, ao.DI[i]);
+        if (linkToCache) me.stABI(F_PPLUS, ao.PP);
+        if (!LEAN) me.stSV(F_ZB, ao.zb);
     } else {
 #pragma unroll
-        for (int j = 0; j < d; ++j) G[j] = me.ldSV(fG(d) + 6*j);
-        if constexpr ((MODE & IN_BIAS) != 0) zb = me.ldSV(F_ZB);
+        for (int j = 0; j < d; ++j) ao.G[j] = me.ldSV(fG(d) + 6*j);
+        if constexpr ((MODE & IN_BIAS) != 0) ao.zb = me.ldSV(F_ZB);
     }
 
+    SV zPlus = zeroSV();
     if constexpr ((MODE & IN_Z) != 0) {
         // ---- applied forces -------------------------------------------------------------------
         SV F = zeroSV(); double f[d];
-#pragma unroll
-        for (int j = 0; j < d; ++j) f[j] = 0;
         if constexpr ((MODE & IN_FORCES) != 0) {
-            // Force::Gravity (Force_Gravity.cpp:538-556): F = (p_CB_G x m g, m g)
-            const V3 Fc = bc.mass*mk(c.gx, c.gy, c.gz);
-            F.w = cross(c_G, Fc); F.v = Fc;
-            // MobilityLinearSpring / Damper in force-index order (Force.cpp:339-351,434-443)
-            for (int k = 0; k < bc.nforce; ++k) {
-                const ForceConst fc = c.forces[bc.forceStart + k];
-                double frc;
-                if (fc.kind == FK_SPRING) frc = -fc.a*(ldS(c, c.q, bc.q0 + fc.coord) - fc.b);
-                else                      frc = -fc.a*ldS(c, c.u, bc.u0 + fc.coord);
+            F = gravityForce(bc.mass, c_G, c.gx, c.gy, c.gz);
+            double q[NQ], u[d];
+            if (bc.nforce > 0) {
 #pragma unroll
-                for (int j = 0; j < d; ++j) if (j == fc.coord) f[j] += frc;
+                for (int i = 0; i < NQ; ++i) q[i] = ldS(c, c.q, bc.q0 + i);
+#pragma unroll
+                for (int i = 0; i < d; ++i)  u[i] = ldS(c, c.u, bc.u0 + i);
             }
+            mobilityForces<d>(bc, c.forces, q, u, f);
             if (c.fmobOut) {
 #pragma unroll
                 for (int j = 0; j < d; ++j) stS(c, c.fmobOut, bc.u0 + j, f[j]);
@@ -358,10 +469,8 @@ SBK_HDN void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex) 
                 stS(c, c.FbodyOut, 6*bodyIndex+3, F.v.x); stS(c, c.FbodyOut, 6*bodyIndex+4, F.v.y); stS(c, c.FbodyOut, 6*bodyIndex+5, F.v.z);
             }
         } else {
-            if (c.fmobIn) {
 #pragma unroll
-                for (int j = 0; j < d; ++j) f[j] = ldS(c, c.fmobIn, bc.u0 + j);
-            }
+            for (int j = 0; j < d; ++j) f[j] = c.fmobIn ? ldS(c, c.fmobIn, bc.u0 + j) : 0.0;
             if (c.FbodyIn) {
                 F.w = mk(ldS(c, c.FbodyIn, 6*bodyIndex+0), ldS(c, c.FbodyIn, 6*bodyIndex+1), ldS(c, c.FbodyIn, 6*bodyIndex+2));
                 F.v = mk(ldS(c, c.FbodyIn, 6*bodyIndex+3), ldS(c, c.FbodyIn, 6*bodyIndex+4), ldS(c, c.FbodyIn, 6*bodyIndex+5));
@@ -369,81 +478,61 @@ SBK_HDN void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex) 
         }
         // ---- calcUDotPass1Inward (RigidBodyNodeSpec.cpp:355-400) / M^-1 pass 1 (:483-515) ------
         SV z;
-        if constexpr ((MODE & IN_BIAS) != 0) z = zb - F; else z = zeroSV();
+        if constexpr ((MODE & IN_BIAS) != 0) z = ao.zb - F; else z = zeroSV();
         for (int k = 0; k < bc.nchild; ++k) {
-            const BodyConst& cb = c.bodies[c.children[bc.childStart + k]];
-            const CacheRef ch = cacheOf(c, cb.cacheBase);
-            z = z + phi(ch.ld3(F_L), ch.ldSV(F_ZPLUS));
+            const int ci = c.children[bc.childStart + k];
+            if (LEAN && ci == cy.inBody) z = z + phi(cy.l, cy.zP);
+            else { const CacheRef ch = cacheOf(c, c.bodies[ci].cacheBase); z = z + phi(ch.ld3(F_L), ch.ldSV(F_ZPLUS)); }
         }
-        SV zPlus = z;
+        double eps[d];
+        zCore<d>(H, ao.G, z, f, eps, zPlus);
 #pragma unroll
-        for (int j = 0; j < d; ++j) {
-            const double eps = f[j] - (dot(H[j].w, z.w) + dot(H[j].v, z.v));
-            me.st(fEPS(d) + j, eps);
-            f[j] = eps;
-        }
-        SV Ge = zeroSV();
-#pragma unroll
-        for (int j = 0; j < d; ++j) Ge = Ge + f[j]*G[j];
-        zPlus = zPlus + Ge;
-        me.stSV(F_ZPLUS, zPlus);
+        for (int j = 0; j < d; ++j) me.st(fEPS(d) + j, eps[j]);
+        if (linkToCache) me.stSV(F_ZPLUS, zPlus);
     }
+    if (LEAN) { cy.PP = ao.PP; cy.zP = zPlus; cy.l = me.ld3(F_L); cy.inBody = bodyIndex; }
 }
 
-//==============================================================================================
 // Sweep E for one body (base->tip): udot, A_GB, qdotdot.
-//   WITH_COR: add the mobilizer coriolis acceleration (forward dynamics) or not (M^-1).
-//==============================================================================================
-template <int JT, bool WITH_COR>
-SBK_HDN void outwardBody(const Ctx& c, const BodyConst& bc, double* udotDst, double* qdotdotDst) {
-    constexpr int d = JointDims<JT>::nu;
-    const CacheRef me = cacheOf(c, bc.cacheBase), pa = cacheOf(c, bc.parentCacheBase);
-    const SV APlus = phiT(me.ld3(F_L), pa.ldSV(F_AGB));
-    double eps[d], udot[d];
+template <int JT, bool WITH_COR, bool LEAN>
+SBK_HDN void outwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, Carry& cy, double* udotDst, double* qdotdotDst) {
+    constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
+    const CacheRef me = cacheOf(c, bc.cacheBase);
+    SV A_GP;
+    if (LEAN && (bc.flags & BF_PARENT_PREV) && cy.outBody == bc.parent) A_GP = cy.A;
+    else A_GP = cacheOf(c, bc.parentCacheBase).ldSV(F_AGB);
+    SV H[d], G[d]; double DI[d*d], eps[d], udot[d];
 #pragma unroll
-    for (int j = 0; j < d; ++j) eps[j] = me.ld(fEPS(d) + j);
-    SV A = APlus;
-    SV Hu = zeroSV();
+    for (int j = 0; j < d; ++j) { H[j] = me.ldSV(F_H + 6*j); G[j] = me.ldSV(fG(d) + 6*j); eps[j] = me.ld(fEPS(d) + j); }
 #pragma unroll
-    for (int i = 0; i < d; ++i) {
-        double s = 0;
+    for (int i = 0; i < d*d; ++i) DI[i] = me.ld(fDI(d) + i);
+    SV acor = zeroSV();
+    if constexpr (WITH_COR) acor = me.ldSV(F_ACOR);
+    SV A;
+    accCore<d, WITH_COR>(H, G, DI, eps, me.ld3(F_L), A_GP, acor, udot, A);
+    if (!LEAN || (bc.flags & BF_STORE_LINK)) me.stSV(F_AGB, A);
+    cy.A = A; cy.outBody = bodyIndex;
+    if (udotDst) {
 #pragma unroll
-        for (int j = 0; j < d; ++j) s += me.ld(fDI(d) + d*i + j)*eps[j];
-        const SV Gi = me.ldSV(fG(d) + 6*i);
-        udot[i] = s - (dot(Gi.w, APlus.w) + dot(Gi.v, APlus.v));
-        Hu = Hu + udot[i]*me.ldSV(F_H + 6*i);
-        if (udotDst) stS(c, udotDst, bc.u0 + i, udot[i]);
+        for (int i = 0; i < d; ++i) stS(c, udotDst, bc.u0 + i, udot[i]);
     }
-    A = A + Hu;
-    if constexpr (WITH_COR) A = A + me.ldSV(F_ACOR);
-    me.stSV(F_AGB, A);
-
-    if (qdotdotDst) {   // calcQDotDot (RigidBodyNodeSpec_Ball.h:355-390, _Free.h:418-455)
+    if (qdotdotDst) {
+        double q[NQ], u[d], qdd[NQ];
         if constexpr (JT == JT_BALL || JT == JT_FREE) {
-            double q[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) q[i] = ldS(c, c.q, bc.q0 + i);
-            const V3 w = mk(ldS(c, c.u, bc.u0), ldS(c, c.u, bc.u0 + 1), ldS(c, c.u, bc.u0 + 2));
-            double Nb[4]; quatNTimes(q, mk(udot[0], udot[1], udot[2]), Nb);
-            const double k = -0.25*dot(w, w);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) stS(c, qdotdotDst, bc.q0 + i, Nb[i] + k*q[i]);
-            if constexpr (JT == JT_FREE) {
-#pragma unroll
-                for (int i = 0; i < 3; ++i) stS(c, qdotdotDst, bc.q0 + 4 + i, udot[3+i]);
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < d; ++i) stS(c, qdotdotDst, bc.q0 + i, udot[i]);
+            for (int i = 0; i < 3; ++i) u[i] = ldS(c, c.u, bc.u0 + i);
         }
+        qddCore<JT>(q, u, udot, qdd);
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) stS(c, qdotdotDst, bc.q0 + i, qdd[i]);
     }
 }
 
-//==============================================================================================
 // multiplyByM / inverse dynamics passes (RigidBodyNodeSpec.cpp:566-695).
 //   WITH_VEL: residual form (adds coriolis a, gyroscopic b, applied forces).
 // The outward pass stores A in AGB; the inward pass stores F in ZPLUS.
-//==============================================================================================
 template <int JT, bool WITH_VEL>
 SBK_HDN void idOutBody(const Ctx& c, const BodyConst& bc) {
     constexpr int d = JointDims<JT>::nu;
@@ -503,17 +592,17 @@ SBK_HDN void idInBody(const Ctx& c, const BodyConst& bc, const int bodyIndex) {
         default: break;                                                             \
     }
 
-SBK_HD void kinDispatch(const Ctx& c, int b) {
+template <bool LEAN> SBK_HD void kinDispatch(const Ctx& c, int b, Carry& cy) {
     const BodyConst& bc = c.bodies[b];
-    SBK_DISPATCH_JOINT(bc.joint, (kinBody<JT>(c, bc)));
+    SBK_DISPATCH_JOINT(bc.joint, (kinBody<JT, LEAN>(c, bc, b, cy)));
 }
-template <int MODE> SBK_HD void inwardDispatch(const Ctx& c, int b) {
+template <int MODE, bool LEAN> SBK_HD void inwardDispatch(const Ctx& c, int b, Carry& cy) {
     const BodyConst& bc = c.bodies[b];
-    SBK_DISPATCH_JOINT(bc.joint, (inwardBody<JT, MODE>(c, bc, b)));
+    SBK_DISPATCH_JOINT(bc.joint, (inwardBody<JT, MODE, LEAN>(c, bc, b, cy)));
 }
-template <bool WITH_COR> SBK_HD void outwardDispatch(const Ctx& c, int b, double* udotDst, double* qddDst) {
+template <bool WITH_COR, bool LEAN> SBK_HD void outwardDispatch(const Ctx& c, int b, Carry& cy, double* udotDst, double* qddDst) {
     const BodyConst& bc = c.bodies[b];
-    SBK_DISPATCH_JOINT(bc.joint, (outwardBody<JT, WITH_COR>(c, bc, udotDst, qddDst)));
+    SBK_DISPATCH_JOINT(bc.joint, (outwardBody<JT, WITH_COR, LEAN>(c, bc, b, cy, udotDst, qddDst)));
 }
 template <bool WITH_VEL> SBK_HD void idOutDispatch(const Ctx& c, int b) {
     const BodyConst& bc = c.bodies[b];
@@ -528,16 +617,24 @@ template <bool WITH_VEL> SBK_HD void idInDispatch(const Ctx& c, int b) {
 // Per-instance drivers for the thread-per-instance plan: body index order is a valid
 // base->tip order because a parent's MobilizedBodyIndex is always smaller than its child's.
 //==============================================================================================
-SBK_HD void tpiKinematics(const Ctx& c) { for (int b = 1; b < c.nb; ++b) kinDispatch(c, b); }
-template <int MODE> SBK_HD void tpiInward(const Ctx& c) { for (int b = c.nb - 1; b >= 1; --b) inwardDispatch<MODE>(c, b); }
-template <bool WITH_COR> SBK_HD void tpiOutward(const Ctx& c, double* udotDst, double* qddDst) {
-    for (int b = 1; b < c.nb; ++b) outwardDispatch<WITH_COR>(c, b, udotDst, qddDst);
+SBK_HD void resetCarry(Carry& cy) { cy.outBody = -1; cy.inBody = -1; }
+template <bool LEAN> SBK_HD void tpiKinematics(const Ctx& c, Carry& cy) {
+    cy.outBody = -1;
+    for (int b = 1; b < c.nb; ++b) kinDispatch<LEAN>(c, b, cy);
+}
+template <int MODE, bool LEAN> SBK_HD void tpiInward(const Ctx& c, Carry& cy) {
+    cy.inBody = -1;
+    for (int b = c.nb - 1; b >= 1; --b) inwardDispatch<MODE, LEAN>(c, b, cy);
+}
+template <bool WITH_COR, bool LEAN> SBK_HD void tpiOutward(const Ctx& c, Carry& cy, double* udotDst, double* qddDst) {
+    cy.outBody = -1;
+    for (int b = 1; b < c.nb; ++b) outwardDispatch<WITH_COR, LEAN>(c, b, cy, udotDst, qddDst);
 }
 // One full derivative evaluation = System::realize(Acceleration) for the lowered system.
-SBK_HD void tpiEvalDerivatives(const Ctx& c) {
-    tpiKinematics(c);
-    tpiInward<IN_ABI | IN_Z | IN_BIAS | IN_FORCES>(c);
-    tpiOutward<true>(c, c.udot, c.qdotdot);
+template <bool LEAN> SBK_HD void tpiEvalDerivatives(const Ctx& c, Carry& cy) {
+    tpiKinematics<LEAN>(c, cy);
+    tpiInward<IN_ABI | IN_Z | IN_BIAS | IN_FORCES, LEAN>(c, cy);
+    tpiOutward<true, LEAN>(c, cy, c.udot, c.qdotdot);
 }
 
 } // namespace sbkd

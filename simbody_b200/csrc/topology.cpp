@@ -79,6 +79,9 @@ void compileTopology(const ModelSpec& spec, sbk_topology& t) {
         for (int i = 0; i < 6; ++i) bc.G_B[i] = d.unit_inertia_OB_B[i];
         bc.joint = d.joint_type; bc.parent = d.parent < 0 ? 0 : d.parent;
         bc.q0 = t.q0[b]; bc.u0 = t.u0[b]; bc.quat = t.quatIndex[b]; bc.level = t.level[b];
+        bc.flags = 0;
+        if (b >= 1 && d.parent == b - 1) bc.flags |= sbkd::BF_PARENT_PREV;
+        for (int k : kids[b]) if (k != b + 1) bc.flags |= sbkd::BF_STORE_LINK;
         bc.nchild = (int)kids[b].size(); bc.childStart = (int)t.children.size();
         for (int k : kids[b]) t.children.push_back(k);
         bc.nforce = (int)perBody[b].size(); bc.forceStart = (int)t.forces.size();

@@ -124,6 +124,13 @@ class BatchedMatter:
         self._chk(self.lib.sbk_state_device_ptrs(self.handle, *[ctypes.byref(x) for x in p]))
         return [x.value for x in p]
 
+    def setPlan(self, plan):
+        """0 auto, 1 thread-per-instance (per-body cache in HBM), 2 register-resident fused (tiny chains)."""
+        self._chk(self.lib.sbk_batch_set_plan(self.handle, int(plan)))
+
+    def getPlan(self):
+        return int(self.lib.sbk_batch_get_plan(self.handle))
+
     def synchronize(self):
         self._chk(self.lib.sbk_synchronize(self.handle))
 

@@ -166,7 +166,7 @@ class HostEmu:
         dp = ctypes.POINTER(ctypes.c_double)
         self.lib.emu_eval.argtypes = [ctypes.c_char_p, ctypes.c_int, dp, dp]
         self.lib.emu_step.argtypes = [ctypes.c_char_p, ctypes.c_int, dp, dp, ctypes.c_double, ctypes.c_int,
-                                      ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int]
+                                      ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         self.lib.emu_model_text.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
 
     def model_text(self, name, n=0):
@@ -185,13 +185,14 @@ class HostEmu:
         assert rc == 0, rc
         return out
 
-    def step(self, info, y, h, nsteps, accuracy=1e-3, cons_tol=None, inf_norm=0, project_every=0):
+    def step(self, info, y, h, nsteps, accuracy=1e-3, cons_tol=None, inf_norm=0, project_every=0, lean=1):
+        """lean=1 runs the integrator's LEAN body wrappers (carry links), lean=0 the full-record ones."""
         y = np.ascontiguousarray(y, dtype=np.float64)
         n = y.shape[0]
         out = np.zeros((n, info.nq + info.nu + 2))
         dp = ctypes.POINTER(ctypes.c_double)
         rc = self.lib.emu_step(info.text.encode(), n, y.ctypes.data_as(dp), out.ctypes.data_as(dp), h, nsteps,
-                               accuracy, accuracy / 10 if cons_tol is None else cons_tol, inf_norm, project_every)
+                               accuracy, accuracy / 10 if cons_tol is None else cons_tol, inf_norm, project_every, lean)
         assert rc == 0, rc
         return out
 

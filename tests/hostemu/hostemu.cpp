@@ -10,7 +10,7 @@
 #include <string>
 #include <vector>
 #include "../../simbody_b200/csrc/topology.h"
-#include "../../simbody_b200/csrc/sbk_rkm.cuh"
+#include "../../simbody_b200/csrc/sbk_fused.cuh"
 
 using namespace sbkd;
 
@@ -81,8 +81,9 @@ int emu_eval(const char* text, int N, const double* in, double* out) {
         for (int k = 0; k < N; ++k) {
             const double* p = in + (size_t)k*inStride; double* o = out + (size_t)k*outStride;
             Ctx c = makeCtx(e, k);
+            Carry cy; resetCarry(cy);
             c.fmobOut = e.fmob.data(); c.FbodyOut = e.Fbody.data();
-            tpiEvalDerivatives(c);
+            tpiEvalDerivatives<false>(c, cy);
             for (int i = 0; i < nq; ++i) *o++ = e.ydot[(size_t)i*N + k];
             for (int i = 0; i < nu; ++i) *o++ = e.ydot[(size_t)(nq+i)*N + k];
             for (int i = 0; i < nq; ++i) *o++ = e.qdd[(size_t)i*N + k];
@@ -106,8 +107,8 @@ int emu_eval(const char* text, int N, const double* in, double* out) {
             // M^-1 v
             for (int i = 0; i < nu; ++i) e.vin[(size_t)i*N + k] = pv[i];
             c.fmobIn = e.vin.data(); c.FbodyIn = nullptr;
-            tpiInward<IN_Z>(c);
-            tpiOutward<false>(c, e.vout.data(), nullptr);
+            tpiInward<IN_Z, false>(c, cy);
+            tpiOutward<false, false>(c, cy, e.vout.data(), nullptr);
             for (int i = 0; i < nu; ++i) *o++ = e.vout[(size_t)i*N + k];
             // residual(f, F, udot)
             for (int i = 0; i < nu; ++i) { e.vin[(size_t)i*N + k] = pud[i]; e.vin2[(size_t)i*N + k] = pf[i]; }
@@ -123,8 +124,8 @@ int emu_eval(const char* text, int N, const double* in, double* out) {
             for (int i = 0; i < nu; ++i) *o++ = e.vout[(size_t)i*N + k];
             // calcAcceleration(f, F)
             c.fmobIn = e.vin2.data(); c.FbodyIn = e.Fin.data();
-            tpiInward<IN_Z | IN_BIAS>(c);
-            tpiOutward<true>(c, e.vout.data(), nullptr);
+            tpiInward<IN_Z | IN_BIAS, false>(c, cy);
+            tpiOutward<true, false>(c, cy, e.vout.data(), nullptr);
             for (int i = 0; i < nu; ++i) *o++ = e.vout[(size_t)i*N + k];
             for (int b = 0; b < nb; ++b) for (int i = 0; i < 6; ++i) *o++ = rec(b, F_AGB + i);
             if (o - (out + (size_t)k*outStride) != outStride) return 3;
@@ -135,17 +136,42 @@ int emu_eval(const char* text, int N, const double* in, double* out) {
 
 // in: [N][nq+nu]; out: [N][nq+nu+2] (q, u, errNorm of last step, number of projections)
 int emu_step(const char* text, int N, const double* in, double* out, double h, int nsteps,
-             double accuracy, double consTol, int useInfNorm, int projectEveryStep) {
+             double accuracy, double consTol, int useInfNorm, int projectEveryStep, int lean) {
     try {
         Emu e; setup(e, text, N);
         const sbk_topology& t = e.topo; const int ny = t.nq + t.nu;
         for (int k = 0; k < N; ++k) for (int i = 0; i < ny; ++i) e.y[(size_t)i*N + k] = in[(size_t)k*ny + i];
         RkmWork w; w.y = e.y.data(); w.y0 = e.y0.data(); w.f0 = e.f0.data(); w.fa = e.fa.data(); w.fb = e.fb.data(); w.ys = e.ys.data();
         w.accuracy = accuracy; w.consTol = consTol; w.useInfNorm = useInfNorm; w.projectEveryStep = projectEveryStep;
+        if (lean == 2) {   // register-resident fused plan (2-body Pin/Slider chains only in this emulation)
+            if (t.nb != 3) return 4;
+            const int j1 = t.bodies[1].joint, j2 = t.bodies[2].joint;
+            for (int k = 0; k < N; ++k) {
+                double y[8]; for (int i = 0; i < ny; ++i) y[i] = e.y[(size_t)i*N + k];
+                double err = 0;
+                auto run = [&](auto ch) {
+                    ch.b0 = &e.bodies[1]; ch.b1 = &e.bodies[2]; ch.forces = t.forces.data();
+                    ch.gx = t.grav[0]; ch.gy = t.grav[1]; ch.gz = t.grav[2];
+                    for (int s = 0; s < nsteps; ++s) err = fusedRkmStep(ch, y, h, useInfNorm);
+                };
+                if (j1 == JT_PIN && j2 == JT_PIN) run(Chain2<JT_PIN, JT_PIN>());
+                else if (j1 == JT_SLIDER && j2 == JT_PIN) run(Chain2<JT_SLIDER, JT_PIN>());
+                else if (j1 == JT_PIN && j2 == JT_SLIDER) run(Chain2<JT_PIN, JT_SLIDER>());
+                else return 4;
+                double* o = out + (size_t)k*(ny+2);
+                for (int i = 0; i < ny; ++i) o[i] = y[i];
+                o[ny] = err; o[ny+1] = 0;
+            }
+            return 0;
+        }
         for (int k = 0; k < N; ++k) {
             Ctx c = makeCtx(e, k);
+            Carry cy; resetCarry(cy);
             RkmStepResult r; r.errNorm = 0; r.projected = 0; int nproj = 0;
-            for (int s = 0; s < nsteps; ++s) { r = tpiRkmStep(c, w, h); nproj += r.projected; }
+            for (int s = 0; s < nsteps; ++s) {
+                r = lean ? tpiRkmStep<true>(c, w, h, cy) : tpiRkmStep<false>(c, w, h, cy);
+                nproj += r.projected;
+            }
             double* o = out + (size_t)k*(ny+2);
             for (int i = 0; i < ny; ++i) o[i] = e.y[(size_t)i*N + k];
             o[ny] = r.errNorm; o[ny+1] = nproj;

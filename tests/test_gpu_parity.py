@@ -145,3 +145,31 @@ def test_stage_and_argument_errors():
         bm.realizePositionKinematics(); bm.multiplyByM(np.zeros((3, 8)))
     assert e.value.code == 1
     bm.close(); topo.close()
+
+
+def test_fused_plan_matches_generic_plan():
+    """The register-resident fused plan calls the same cores in the same order as the
+    thread-per-instance plan (bit-identical in the host build, tests/test_oracle.py); on the GPU
+    nvcc contracts FMAs differently in the two inlining contexts, so agreement is to rounding."""
+    g = np.load(os.path.join(GOLDEN, "double_pendulum.npz"))
+    info = ModelInfo(str(g["text"]))
+    n = 4096
+    q, u = info.random_states(n, 17, q_scale=3.0)
+    out = {}
+    for plan in (1, 2):
+        topo = sb.Topology(text=info.text); bm = sb.BatchedMatter(topo, n)
+        bm.setPlan(plan); assert bm.getPlan() == plan
+        bm.setState(soa(q), soa(u), t=0.0)
+        err = bm.stepBy(1e-3, 40, want_err_norm=True)
+        qq, uu, t = bm.getState()
+        out[plan] = (qq, uu, err, t)
+        bm.close(); topo.close()
+    for a, b in zip(out[1][:2], out[2][:2]):
+        assert rel_err(a, b) < 1e-11
+    assert np.array_equal(out[1][3], out[2][3])
+    assert np.allclose(out[1][2], out[2][2], rtol=1e-3, atol=1e-18)
+    topo = sb.Topology(text=sb.model_text("humanoid30")); bm = sb.BatchedMatter(topo, 8)
+    assert bm.getPlan() == 1
+    with pytest.raises(sb.SbkError):
+        bm.setPlan(2)
+    bm.close(); topo.close()
