@@ -4,6 +4,7 @@
 // State in HBM, stage bookkeeping that mirrors the reference's Stage checks, and kernel
 // launches on the batch's stream.  There is no CPU compute path: without a usable CUDA device
 // every compute entry point returns SBK_ERR_CUDA.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -48,7 +49,7 @@ int useDevice(const sbk_batch* b) {
     return SBK_OK;
 }
 int launch(sbk_batch* b, KernelOp op) {
-    CUDA_TRY(launchTpi(op, b->a, b->stream));
+    CUDA_TRY(b->plan == 3 ? launchLp(op, b->a, b->stream) : launchTpi(op, b->a, b->stream));
     b->launches++;
     return SBK_OK;
 }
@@ -146,6 +147,67 @@ static bool fusedOk(const sbk_batch* b) {
     for (int i = 0; i < b->topo->nb; ++i) joints[i] = b->topo->bodies[i].joint;
     return b->topo->isChain && fusedPlanSupports(b->topo->nb, joints.data());
 }
+static int autoPlan(const sbk_batch* b) {
+    if (fusedOk(b)) return 2;
+    // wide tree + batch too small to fill 148 SMs with one thread per instance
+    if (b->N < 16384 && b->topo->nb >= 128 && b->topo->maxLevelWidth >= 32) return 3;
+    return 1;
+}
+// (Re)build the batch-shared tables and the per-body cache for an execution plan.
+//   plans 1/2: record (body b, field k, instance i) at cache[(base_b + k)*N + i]
+//   plan 3   : cache[i*(KMAX*nb) + k*nb + pos_b], pos_b = position in (level, joint) order, so
+//              that the threads of a CTA (bodies of one level) touch adjacent addresses.
+static int configurePlan(sbk_batch* b, int plan) {
+    const sbk_topology* t = b->topo; const int n = b->N; KArgs& a = b->a;
+    std::vector<BodyConst> bodies = t->bodies;
+    std::vector<int> order = t->levelOrder;
+    long long cacheDoubles = 0;
+    if (plan == 3) {
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+            if (t->level[x] != t->level[y]) return t->level[x] < t->level[y];
+            return t->bodies[x].joint < t->bodies[y].joint; });
+        std::vector<int> pos(t->nb);
+        for (int i = 0; i < t->nb; ++i) pos[order[i]] = i;
+        for (int i = 0; i < t->nb; ++i) bodies[i].cacheBase = pos[i];
+        a.cStride = t->nb; a.cInstStride = (long long)CACHE_RECORD_MAX*t->nb;
+        cacheDoubles = a.cInstStride*n;
+    } else {
+        long long off = 0;
+        for (int i = 0; i < t->nb; ++i) { bodies[i].cacheBase = off*n; off += (i == 0) ? F_H : cacheRecordSize(t->nuOf[i]); }
+        a.cStride = n; a.cInstStride = 1; cacheDoubles = off*n; b->recTotal = off;
+    }
+    for (int i = 0; i < t->nb; ++i) bodies[i].parentCacheBase = bodies[bodies[i].parent].cacheBase;
+    auto pad16 = [](size_t x) { return (x + 15)/16*16; };
+    const size_t bodiesBytes = pad16(bodies.size()*sizeof(BodyConst));
+    const size_t childBytes  = pad16(t->children.size()*sizeof(int));
+    const size_t forceBytes  = pad16(t->forces.size()*sizeof(ForceConst));
+    const size_t orderBytes  = pad16(order.size()*sizeof(int));
+    const size_t startBytes  = pad16(t->levelStart.size()*sizeof(int));
+    std::vector<unsigned char> blob(bodiesBytes + childBytes + forceBytes + orderBytes + startBytes, 0);
+    std::memcpy(blob.data(), bodies.data(), bodies.size()*sizeof(BodyConst));
+    std::memcpy(blob.data() + bodiesBytes, t->children.data(), t->children.size()*sizeof(int));
+    std::memcpy(blob.data() + bodiesBytes + childBytes, t->forces.data(), t->forces.size()*sizeof(ForceConst));
+    std::memcpy(blob.data() + bodiesBytes + childBytes + forceBytes, order.data(), order.size()*sizeof(int));
+    std::memcpy(blob.data() + bodiesBytes + childBytes + forceBytes + orderBytes, t->levelStart.data(), t->levelStart.size()*sizeof(int));
+    a.tableBytes = (uint32_t)blob.size(); a.childrenOff = (uint32_t)bodiesBytes; a.forcesOff = (uint32_t)(bodiesBytes + childBytes);
+    a.levelOrderOff = (uint32_t)(bodiesBytes + childBytes + forceBytes); a.levelStartOff = a.levelOrderOff + (uint32_t)orderBytes;
+    a.nlevels = t->nlevels; a.plan = plan;
+    a.stageInSmem = (plan != 3 && blob.size() <= 96*1024) ? 1u : 0u;
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    if (b->dTables) cudaFree(b->dTables);
+    if (a.cache) cudaFree(a.cache);
+    b->dTables = nullptr; a.cache = nullptr;
+    CUDA_TRY(cudaMalloc(&b->dTables, blob.size()));
+    CUDA_TRY(cudaMemcpyAsync(b->dTables, blob.data(), blob.size(), cudaMemcpyHostToDevice, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    a.tables = b->dTables;
+    CUDA_TRY(cudaMalloc(&a.cache, (size_t)cacheDoubles*sizeof(double)));
+    CUDA_TRY(cudaMemsetAsync(a.cache, 0, (size_t)cacheDoubles*sizeof(double), b->stream));
+    CUDA_TRY(launchInitGround(a, b->stream)); b->launches++;
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    b->plan = plan; b->stage = ST_EMPTY; b->abiValid = false; b->accelValid = false;
+    return SBK_OK;
+}
 sbk_batch* sbk_batch_create(const sbk_topology* t, int n, int device, void* stream) {
     if (!t || n < 1) { fail(SBK_ERR_ARG, "sbk_batch_create: bad arguments"); return nullptr; }
     int ndev = 0;
@@ -163,24 +225,7 @@ sbk_batch* sbk_batch_create(const sbk_topology* t, int n, int device, void* stre
     else { if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate failed"); b->ownStream = true; }
     cudaEventCreate(&b->ev0); cudaEventCreate(&b->ev1);
 
-    // tables blob: bodies | children | forces, cache bases for the thread-per-instance plan
-    std::vector<BodyConst> bodies = t->bodies;
-    long long off = 0;
-    for (int i = 0; i < t->nb; ++i) { bodies[i].cacheBase = off*n; off += (i == 0) ? F_H : cacheRecordSize(t->nuOf[i]); }
-    for (int i = 0; i < t->nb; ++i) bodies[i].parentCacheBase = bodies[bodies[i].parent].cacheBase;
-    b->recTotal = off;
-    auto pad16 = [](size_t x) { return (x + 15)/16*16; };
-    const size_t bodiesBytes = pad16(bodies.size()*sizeof(BodyConst));
-    const size_t childBytes  = pad16(t->children.size()*sizeof(int));
-    const size_t forceBytes  = pad16(t->forces.size()*sizeof(ForceConst));
-    std::vector<unsigned char> blob(bodiesBytes + childBytes + forceBytes, 0);
-    std::memcpy(blob.data(), bodies.data(), bodies.size()*sizeof(BodyConst));
-    std::memcpy(blob.data() + bodiesBytes, t->children.data(), t->children.size()*sizeof(int));
-    std::memcpy(blob.data() + bodiesBytes + childBytes, t->forces.data(), t->forces.size()*sizeof(ForceConst));
-
     KArgs& a = b->a; std::memset(&a, 0, sizeof a);
-    a.tableBytes = (uint32_t)blob.size(); a.childrenOff = (uint32_t)bodiesBytes; a.forcesOff = (uint32_t)(bodiesBytes + childBytes);
-    a.stageInSmem = blob.size() <= 96*1024 ? 1u : 0u;
     a.nb = t->nb; a.nq = t->nq; a.nu = t->nu; a.nquat = t->nquat;
     a.gx = t->grav[0]; a.gy = t->grav[1]; a.gz = t->grav[2];
     a.N = n;
@@ -188,11 +233,6 @@ sbk_batch* sbk_batch_create(const sbk_topology* t, int n, int device, void* stre
     bool ok = true;
     auto dalloc = [&](double** p, size_t doubles) { if (ok && cudaMalloc(p, std::max<size_t>(doubles, 1)*sizeof(double)) != cudaSuccess) ok = false;
                                                     if (ok) cudaMemsetAsync(*p, 0, std::max<size_t>(doubles, 1)*sizeof(double), b->stream); };
-    if (cudaMalloc(&b->dTables, blob.size()) != cudaSuccess) return bail("cudaMalloc(tables) failed");
-    cudaMemcpyAsync(b->dTables, blob.data(), blob.size(), cudaMemcpyHostToDevice, b->stream);
-    cudaStreamSynchronize(b->stream);
-    a.tables = b->dTables;
-    dalloc(&a.cache, (size_t)off*N);
     dalloc(&a.y, ny*N); dalloc(&a.ydot, ny*N); dalloc(&a.qdotdot, (size_t)t->nq*N); dalloc(&a.qerr, (size_t)std::max(t->nquat, 1)*N);
     dalloc(&a.y0, ny*N); dalloc(&a.f0, ny*N); dalloc(&a.fa, ny*N); dalloc(&a.fb, ny*N); dalloc(&a.ys, ny*N);
     dalloc(&a.tcur, N); dalloc(&a.errNorm, N);
@@ -209,12 +249,9 @@ sbk_batch* sbk_batch_create(const sbk_topology* t, int n, int device, void* stre
         cudaMemcpyAsync(a.y, q0.data(), q0.size()*sizeof(double), cudaMemcpyHostToDevice, b->stream);
         cudaStreamSynchronize(b->stream);
     }
-    if (launchInitGround(a.cache, n, b->stream) != cudaSuccess) return bail("init kernel launch failed");
-    b->launches++;
-    if (cudaStreamSynchronize(b->stream) != cudaSuccess) return bail(std::string("batch init failed: ") + cudaGetErrorString(cudaGetLastError()));
     sbk_rkm_opts o; sbk_rkm_default_opts(&o);
     a.accuracy = o.accuracy; a.consTol = o.constraint_tol;
-    b->plan = fusedOk(b) ? 2 : 1;
+    if (configurePlan(b, autoPlan(b)) != SBK_OK) { const std::string m = g_lastError; sbk_batch_destroy(b); g_lastError = m; return nullptr; }
     return b;
 }
 void sbk_batch_destroy(sbk_batch* b) {
@@ -231,13 +268,13 @@ void sbk_batch_destroy(sbk_batch* b) {
 int sbk_batch_size(const sbk_batch* b) { return b ? b->N : 0; }
 int sbk_batch_set_plan(sbk_batch* b, int plan) {
     if (!b) return fail(SBK_ERR_ARG, "null batch");
-    if (plan == 0) { b->plan = fusedOk(b) ? 2 : 1; return SBK_OK; }
-    if (plan == 1) { b->plan = 1; return SBK_OK; }
-    if (plan == 2) {
-        if (!fusedOk(b)) return fail(SBK_ERR_ARG, "sbk_batch_set_plan: the register-resident fused plan needs a serial chain of 1-2 Pin/Slider mobilizers");
-        b->plan = 2; return SBK_OK;
-    }
-    return fail(SBK_ERR_ARG, "sbk_batch_set_plan: plan 3 (level-parallel) is not available in this build");
+    if (int rc = useDevice(b)) return rc;
+    if (plan == 0) plan = autoPlan(b);
+    if (plan < 1 || plan > 3) return fail(SBK_ERR_ARG, "sbk_batch_set_plan: plan must be 0..3");
+    if (plan == 2 && !fusedOk(b))
+        return fail(SBK_ERR_ARG, "sbk_batch_set_plan: the register-resident fused plan needs a serial chain of 1-2 Pin/Slider mobilizers");
+    if (plan == b->plan) return SBK_OK;
+    return configurePlan(b, plan);
 }
 int sbk_batch_get_plan(const sbk_batch* b) { return b ? b->plan : 0; }
 int sbk_synchronize(sbk_batch* b) {

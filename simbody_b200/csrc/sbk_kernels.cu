@@ -55,7 +55,7 @@ __device__ __forceinline__ Ctx makeCtx(const KArgs& a, const unsigned char* tabl
     c.forces   = reinterpret_cast<const ForceConst*>(tables + a.forcesOff);
     c.nb = a.nb; c.nq = a.nq; c.nu = a.nu; c.nquat = a.nquat;
     c.gx = a.gx; c.gy = a.gy; c.gz = a.gz;
-    c.cache = a.cache; c.cStride = a.N; c.cOff = inst;
+    c.cache = a.cache; c.cStride = a.cStride; c.cOff = (long long)inst*a.cInstStride;
     c.sStride = a.N; c.sOff = inst;
     c.q = a.y; c.u = a.y + (long long)a.nq*a.N;
     c.qdot = a.ydot; c.udot = a.ydot ? a.ydot + (long long)a.nq*a.N : nullptr;
@@ -154,10 +154,169 @@ cudaError_t launchOp(const KArgs& a, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-__global__ void initGroundKernel(double* cache, int N) {
+//==============================================================================================
+// Level-parallel plan: CTA = instance, threads = bodies of one tree level.
+//==============================================================================================
+constexpr int LP_THREADS = 256;
+
+__device__ __forceinline__ double blockReduce(double v, bool isMax, double* red) {
+    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, v, o); v = isMax ? fmax(v, t) : v + t; }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = isMax ? 0.0 : 0.0;
+    for (int w = 0; w < LP_THREADS/32; ++w) r = isMax ? fmax(r, red[w]) : r + red[w];
+    return r;
+}
+
+struct LpLevels { const int* order; const int* start; int nlevels; };
+
+template <class F> __device__ __forceinline__ void lpOutward(const LpLevels& L, F f) {
+    for (int l = 1; l < L.nlevels; ++l) {
+        for (int i = L.start[l] + threadIdx.x; i < L.start[l+1]; i += LP_THREADS) f(L.order[i]);
+        __syncthreads();
+    }
+}
+template <class F> __device__ __forceinline__ void lpInward(const LpLevels& L, F f) {
+    for (int l = L.nlevels - 1; l >= 1; --l) {
+        for (int i = L.start[l] + threadIdx.x; i < L.start[l+1]; i += LP_THREADS) f(L.order[i]);
+        __syncthreads();
+    }
+}
+__device__ __forceinline__ void lpEval(const Ctx& c, const LpLevels& L, Carry& cy) {
+    lpOutward(L, [&](int b) { kinDispatch<false>(c, b, cy); });
+    lpInward(L,  [&](int b) { inwardDispatch<IN_ABI | IN_Z | IN_BIAS | IN_FORCES, false>(c, b, cy); });
+    lpOutward(L, [&](int b) { outwardDispatch<true, false>(c, b, cy, c.udot, c.qdotdot); });
+}
+
+// Error norm of IntegratorRep::calcErrorNorm, threads over slots / bodies (cf. rkmErrorNorm).
+__device__ double lpErrorNorm(const Ctx& c, const KArgs& a, double* red) {
+    const int nq = c.nq, nu = c.nu; const bool inf = a.useInfNorm != 0;
+    double uAcc = 0, qAcc = 0;
+    for (int i = threadIdx.x; i < nu; i += LP_THREADS) {
+        const double u0 = fabs(ldS(c, a.y0, nq + i));
+        const double sc = (u0*1.0 > 1.0) ? 1.0/u0 : 1.0;
+        const double v = sc*ldS(c, a.ys, nq + i);
+        if (inf) uAcc = fmax(uAcc, fabs(v)); else uAcc += v*v;
+    }
+    for (int b = 1 + threadIdx.x; b < c.nb; b += LP_THREADS) {
+        const BodyConst& bc = c.bodies[b];
+        int first = 0;
+        if (bc.joint == JT_BALL || bc.joint == JT_FREE) {
+            double q[4], e[4], o[4];
+            for (int i = 0; i < 4; ++i) { q[i] = ldS(c, a.y, bc.q0 + i); e[i] = ldS(c, a.ys, bc.q0 + i); }
+            const V3 du = quatNInvTimes(q, e);
+            quatNTimes(q, du, o);
+            for (int i = 0; i < 4; ++i) { if (inf) qAcc = fmax(qAcc, fabs(o[i])); else qAcc += o[i]*o[i]; }
+            first = 4;
+        }
+        const int nqb = bc.joint == JT_FREE ? 7 : bc.joint == JT_BALL ? 4 : bc.joint == JT_UNIVERSAL ? 2 : 1;
+        for (int i = first; i < nqb; ++i) { const double v = ldS(c, a.ys, bc.q0 + i); if (inf) qAcc = fmax(qAcc, fabs(v)); else qAcc += v*v; }
+    }
+    uAcc = blockReduce(uAcc, inf, red); qAcc = blockReduce(qAcc, inf, red);
+    const double qNorm = inf ? qAcc : (nq ? sqrt(qAcc/nq) : 0.0), uNorm = inf ? uAcc : (nu ? sqrt(uAcc/nu) : 0.0);
+    return qNorm >= uNorm ? qNorm : uNorm;
+}
+
+template <int OP>
+__global__ void __launch_bounds__(LP_THREADS, 2) lpKernel(const KArgs a) {
+    __shared__ double red[LP_THREADS/32];
+    const int inst = blockIdx.x;
+    Ctx c = makeCtx(a, a.tables, inst);
+    Carry cy; resetCarry(cy);
+    LpLevels L; L.order = reinterpret_cast<const int*>(a.tables + a.levelOrderOff);
+    L.start = reinterpret_cast<const int*>(a.tables + a.levelStartOff); L.nlevels = a.nlevels;
+
+    if constexpr (OP == OP_KIN) {
+        lpOutward(L, [&](int b) { kinDispatch<false>(c, b, cy); });
+    } else if constexpr (OP == OP_ABI) {
+        lpInward(L, [&](int b) { inwardDispatch<IN_ABI, false>(c, b, cy); });
+    } else if constexpr (OP == OP_EVAL) {
+        lpEval(c, L, cy);
+    } else if constexpr (OP == OP_CALCACC) {
+        lpInward(L,  [&](int b) { inwardDispatch<IN_Z | IN_BIAS, false>(c, b, cy); });
+        lpOutward(L, [&](int b) { outwardDispatch<true, false>(c, b, cy, c.vecOut, nullptr); });
+    } else if constexpr (OP == OP_MULM) {
+        lpOutward(L, [&](int b) { idOutDispatch<false>(c, b); });
+        lpInward(L,  [&](int b) { idInDispatch<false>(c, b); });
+    } else if constexpr (OP == OP_MULMINV) {
+        c.fmobIn = a.vecIn; c.FbodyIn = nullptr;
+        lpInward(L,  [&](int b) { inwardDispatch<IN_Z, false>(c, b, cy); });
+        lpOutward(L, [&](int b) { outwardDispatch<false, false>(c, b, cy, c.vecOut, nullptr); });
+    } else if constexpr (OP == OP_RESID) {
+        lpOutward(L, [&](int b) { idOutDispatch<true>(c, b); });
+        lpInward(L,  [&](int b) { idInDispatch<true>(c, b); });
+    } else if constexpr (OP == OP_RKM) {
+        const int nq = c.nq, ny = c.nq + c.nu; const long long uoff = (long long)nq*c.sStride;
+        c.q = a.y; c.u = a.y + uoff; c.qdotdot = nullptr; c.qerr = nullptr; c.fmobOut = nullptr; c.FbodyOut = nullptr;
+        const double h = a.h; double err = 0; int nproj = 0;
+        for (int s = 0; s < a.nsteps; ++s) {
+            c.qdot = a.f0; c.udot = a.f0 + uoff; lpEval(c, L, cy);
+            for (int i = threadIdx.x; i < ny; i += LP_THREADS) { const double y0 = ldS(c, a.y, i); stS(c, a.y0, i, y0); stS(c, a.y, i, y0 + (h/3)*ldS(c, a.f0, i)); }
+            __syncthreads();
+            c.qdot = a.fa; c.udot = a.fa + uoff; lpEval(c, L, cy);
+            for (int i = threadIdx.x; i < ny; i += LP_THREADS) stS(c, a.y, i, ldS(c, a.y0, i) + (h/6)*(ldS(c, a.f0, i) + ldS(c, a.fa, i)));
+            __syncthreads();
+            lpEval(c, L, cy);
+            for (int i = threadIdx.x; i < ny; i += LP_THREADS) stS(c, a.y, i, ldS(c, a.y0, i) + (h/8)*(ldS(c, a.f0, i) + 3*ldS(c, a.fa, i)));
+            __syncthreads();
+            c.qdot = a.fb; c.udot = a.fb + uoff; lpEval(c, L, cy);
+            for (int i = threadIdx.x; i < ny; i += LP_THREADS) {
+                const double ys = ldS(c, a.y0, i) + (h/2)*(ldS(c, a.f0, i) - 3*ldS(c, a.fa, i) + 4*ldS(c, a.fb, i));
+                stS(c, a.ys, i, ys); stS(c, a.y, i, ys);
+            }
+            __syncthreads();
+            c.qdot = a.fa; c.udot = a.fa + uoff; lpEval(c, L, cy);
+            for (int i = threadIdx.x; i < ny; i += LP_THREADS) {
+                const double y1 = ldS(c, a.y0, i) + (h/6)*(ldS(c, a.f0, i) + 4*ldS(c, a.fb, i) + ldS(c, a.fa, i));
+                stS(c, a.y, i, y1); stS(c, a.ys, i, 0.2*fabs(y1 - ldS(c, a.ys, i)));
+            }
+            __syncthreads();
+            err = lpErrorNorm(c, a, red);
+            if (c.nquat > 0 && !(err > 16.0*a.accuracy)) {       // uniform across the CTA
+                double acc = 0; const bool inf = a.useInfNorm != 0;
+                for (int b = 1 + threadIdx.x; b < c.nb; b += LP_THREADS) {
+                    const BodyConst& bc = c.bodies[b];
+                    if (bc.joint != JT_BALL && bc.joint != JT_FREE) continue;
+                    double n2 = 0; for (int i = 0; i < 4; ++i) { const double qi = ldS(c, a.y, bc.q0 + i); n2 += qi*qi; }
+                    const double e = sqrt(n2) - 1.0;
+                    if (inf) acc = fmax(acc, fabs(e)); else acc += e*e;
+                }
+                acc = blockReduce(acc, inf, red);
+                const double quatNorm = inf ? acc : sqrt(acc/c.nquat);
+                if (quatNorm > a.consTol || a.projectEveryStep) {
+                    for (int b = 1 + threadIdx.x; b < c.nb; b += LP_THREADS) {
+                        const BodyConst& bc = c.bodies[b];
+                        if (bc.joint != JT_BALL && bc.joint != JT_FREE) continue;
+                        double q[4], e[4], n2 = 0;
+                        for (int i = 0; i < 4; ++i) { q[i] = ldS(c, a.y, bc.q0 + i); e[i] = ldS(c, a.ys, bc.q0 + i); n2 += q[i]*q[i]; }
+                        const double n = sqrt(n2); double dt = 0;
+                        for (int i = 0; i < 4; ++i) { q[i] = q[i]/n; dt += e[i]*q[i]; }
+                        for (int i = 0; i < 4; ++i) { stS(c, a.y, bc.q0 + i, q[i]); stS(c, a.ys, bc.q0 + i, e[i] - dt*q[i]); }
+                    }
+                    __syncthreads();
+                    ++nproj;
+                    err = lpErrorNorm(c, a, red);
+                }
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            a.tcur[inst] += a.nsteps*a.h; a.errNorm[inst] = err; a.projCount[inst] += nproj;
+            if (a.status && !(err == err)) a.status[inst] |= 1;
+        }
+    }
+}
+template <int OP> cudaError_t launchLpOp(const KArgs& a, cudaStream_t stream) {
+    lpKernel<OP><<<a.N, LP_THREADS, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+__global__ void initGroundKernel(const KArgs a) {
     const int k = blockIdx.x*blockDim.x + threadIdx.x;
-    if (k >= N) return;
-    for (int f = 0; f < F_H; ++f) cache[(long long)f*N + k] = (f == F_XGB || f == F_XGB+4 || f == F_XGB+8) ? 1.0 : 0.0;
+    if (k >= a.N) return;
+    double* rec = a.cache + (long long)k*a.cInstStride;     // Ground is record base 0 in every plan
+    for (int f = 0; f < F_H; ++f) rec[(long long)f*a.cStride] = (f == F_XGB || f == F_XGB+4 || f == F_XGB+8) ? 1.0 : 0.0;
 }
 
 // 32x32 tiled transpose: src is [rows][cols] row-major -> dst [cols][rows]
@@ -175,8 +334,8 @@ __global__ void gatherBodyFieldKernel(const KArgs a, int fieldOffset, int width,
     if (k >= a.N) return;
     const BodyConst* bodies = reinterpret_cast<const BodyConst*>(a.tables);
     for (int b = 0; b < a.nb; ++b) {
-        const double* rec = a.cache + bodies[b].cacheBase + k;
-        for (int i = 0; i < width; ++i) out[((long long)b*width + i)*a.N + k] = rec[(long long)(fieldOffset + i)*a.N];
+        const double* rec = a.cache + bodies[b].cacheBase + (long long)k*a.cInstStride;
+        for (int i = 0; i < width; ++i) out[((long long)b*width + i)*a.N + k] = rec[(long long)(fieldOffset + i)*a.cStride];
     }
 }
 
@@ -206,6 +365,19 @@ cudaError_t launchTpi(KernelOp op, const KArgs& a, cudaStream_t stream) {
     }
     return cudaErrorInvalidValue;
 }
+cudaError_t launchLp(KernelOp op, const KArgs& a, cudaStream_t stream) {
+    switch (op) {
+        case OP_KIN:     return launchLpOp<OP_KIN>(a, stream);
+        case OP_ABI:     return launchLpOp<OP_ABI>(a, stream);
+        case OP_EVAL:    return launchLpOp<OP_EVAL>(a, stream);
+        case OP_CALCACC: return launchLpOp<OP_CALCACC>(a, stream);
+        case OP_MULM:    return launchLpOp<OP_MULM>(a, stream);
+        case OP_MULMINV: return launchLpOp<OP_MULMINV>(a, stream);
+        case OP_RESID:   return launchLpOp<OP_RESID>(a, stream);
+        case OP_RKM:     return launchLpOp<OP_RKM>(a, stream);
+    }
+    return cudaErrorInvalidValue;
+}
 bool fusedPlanSupports(int nb, const int* joints) {
     auto simple = [](int j) { return j == JT_PIN || j == JT_SLIDER; };
     if (nb == 2) return simple(joints[1]) || joints[1] == JT_UNIVERSAL;
@@ -230,8 +402,8 @@ cudaError_t launchFusedRkm(const KArgs& a, const int* joints, cudaStream_t strea
     }
     return cudaErrorInvalidValue;
 }
-cudaError_t launchInitGround(double* cache, int N, cudaStream_t stream) {
-    initGroundKernel<<<(N + 255)/256, 256, 0, stream>>>(cache, N);
+cudaError_t launchInitGround(const KArgs& a, cudaStream_t stream) {
+    initGroundKernel<<<(a.N + 255)/256, 256, 0, stream>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launchTranspose(const double* src, double* dst, int rows, int cols, cudaStream_t stream) {

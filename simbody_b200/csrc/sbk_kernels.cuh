@@ -12,6 +12,8 @@ namespace sbkd {
 struct KArgs {
     const unsigned char* tables;     // device blob
     uint32_t tableBytes, childrenOff, forcesOff, stageInSmem;
+    uint32_t levelOrderOff, levelStartOff; int nlevels, plan;
+    long long cStride, cInstStride;  // cache addressing: base_b + field*cStride + inst*cInstStride
     int nb, nq, nu, nquat;
     double gx, gy, gz;
     int N;
@@ -47,8 +49,11 @@ cudaError_t launchTpi(KernelOp op, const KArgs& a, cudaStream_t stream);
 // Register-resident fused plan (serial chains of 1-2 Pin/Slider[/Universal] mobilizers).
 bool fusedPlanSupports(int nb, const int* joints /*[nb]*/);
 cudaError_t launchFusedRkm(const KArgs& a, const int* joints, cudaStream_t stream);
+// Level-parallel plan (wide trees, small batches): one CTA per instance, threads over the bodies
+// of a tree level, __syncthreads between levels.
+cudaError_t launchLp(KernelOp op, const KArgs& a, cudaStream_t stream);
 // Ground record (identity transform, zero velocity/acceleration) for every instance.
-cudaError_t launchInitGround(double* cache, int N, cudaStream_t stream);
+cudaError_t launchInitGround(const KArgs& a, cudaStream_t stream);
 // dst[k*len + i] <-> src[i*N + k]
 cudaError_t launchTranspose(const double* src, double* dst, int rows, int cols, cudaStream_t stream);
 // Gather one per-body cache field (width doubles at field offset) into out[(b*width+i)*N + k].

@@ -433,7 +433,13 @@ SBK_HDN void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, 
             else { const CacheRef ch = cacheOf(c, c.bodies[ci].cacheBase); addInto(P, shiftABI(ch.ldABI(F_PPLUS), ch.ld3(F_L))); }
         }
         abiCore<d>(P, H, me.ldSV(F_ACOR), me.ldSV(F_GYRO), ao);
-        if (!ao.ok && c.status) *c.status |= 2;
+        if (!ao.ok && c.status) {
+#if defined(__CUDA_ARCH__)
+            atomicOr(c.status, 2);
+#else
+            *c.status |= 2;
+#endif
+        }
 #pragma unroll
         for (int j = 0; j < d; ++j) me.stSV(fG(d) + 6*j, ao.G[j]);
 #pragma unroll

@@ -1,0 +1,53 @@
+// facade_smoke.cpp -- exercises the C++ host facade (simbody_b200/host/BatchedMatter.h) end to end:
+// built-in model -> Topology -> BatchedMatter -> operators -> fixed-step RKM.  Needs a GPU.
+// Checks the reference's own invariants (Simbody/tests/TestMassMatrix.cpp:670-787):
+// M^-1 (M v) = v and inverse dynamics of the forward-dynamics accelerations reproduces the forces.
+#include <cmath>
+#include <cstdio>
+#include "simbody_b200/host/BatchedMatter.h"
+
+int main() {
+    try {
+        const int N = 512;
+        sbk::Topology topo(sbk::makeNamedModel("humanoid30", 0));
+        sbk::BatchedMatter matter(topo, N);
+        const int nq = topo.getNQ(), nu = topo.getNU(), nb = topo.getNumBodies();
+        std::vector<double> q((size_t)nq*N, 0.0), u((size_t)nu*N, 0.0);
+        sbk::XorShift64 rng(42);
+        for (auto& x : q) x = 0.3*rng.next();
+        for (auto& x : u) x = rng.next();
+        // unit quaternions: pelvis Free (slots 0-3) and every Ball
+        sbk::ModelSpec spec = sbk::makeNamedModel("humanoid30", 0);
+        int slot = 0;
+        for (int b = 1; b < nb; ++b) {
+            const int jt = spec.bodies[b].joint_type;
+            if (jt == SBK_JOINT_BALL || jt == SBK_JOINT_FREE)
+                for (int k = 0; k < N; ++k) {
+                    double n2 = 0; for (int i = 0; i < 4; ++i) n2 += q[(size_t)(slot+i)*N + k]*q[(size_t)(slot+i)*N + k];
+                    q[(size_t)slot*N + k] += 1.0; n2 = 0;
+                    for (int i = 0; i < 4; ++i) n2 += q[(size_t)(slot+i)*N + k]*q[(size_t)(slot+i)*N + k];
+                    for (int i = 0; i < 4; ++i) q[(size_t)(slot+i)*N + k] /= std::sqrt(n2);
+                }
+            slot += sbk::jointNQ(jt);
+        }
+        matter.setState(q, u);
+        bool threw = false;
+        try { std::vector<double> t; matter.multiplyByM(u, t); } catch (const std::logic_error&) { threw = true; }   // stage check
+        if (!threw) { std::printf("FAIL: stage violation not reported\n"); return 1; }
+        matter.realizeVelocityKinematics();
+        std::vector<double> v((size_t)nu*N), Mv, back, f((size_t)nu*N), F((size_t)6*nb*N), udot, A, resid;
+        for (auto& x : v) x = rng.next(); for (auto& x : f) x = rng.next(); for (auto& x : F) x = rng.next();
+        matter.multiplyByM(v, Mv); matter.multiplyByMInv(Mv, back);
+        double e1 = 0; for (size_t i = 0; i < v.size(); ++i) e1 = std::fmax(e1, std::fabs(back[i] - v[i]));
+        matter.calcAcceleration(f, F, udot, A);
+        matter.calcResidualForceIgnoringConstraints(f, F, udot, resid);
+        double e2 = 0; for (double r : resid) e2 = std::fmax(e2, std::fabs(r));
+        sbk::BatchedRungeKuttaMerson integ(matter);
+        integ.setFixedStepSize(1e-3); integ.stepBy(10);
+        std::printf("facade_smoke: |Minv(M v)-v|=%.3e  |ID(FD)|=%.3e  steps=%lld realizations=%lld\n", e1, e2,
+                    integ.getNumStepsTaken(), integ.getNumRealizations());
+        if (!(e1 < 1e-9 && e2 < 1e-8 && integ.getNumStepsTaken() == 10LL*N && integ.getNumRealizations() == 50LL*N)) { std::printf("FAIL\n"); return 1; }
+        std::printf("OK\n");
+        return 0;
+    } catch (const std::exception& e) { std::printf("FAIL: %s\n", e.what()); return 1; }
+}
