@@ -21,7 +21,7 @@ struct Chain2 {
            NQ = NQ0 + NQ1, NU = D0 + D1, NY = NQ + NU, NB = 3 };
     const BodyConst* b0; const BodyConst* b1; const ForceConst* forces; double gx, gy, gz;
 
-    SBK_HD void eval(const double* y, double* ydot) const {
+    SBK_HDN void eval(const double* y, double* ydot) const {
         const double* q0 = y; const double* q1 = y + NQ0; const double* u0 = y + NQ; const double* u1 = y + NQ + D0;
         double qe;
         KinOut<D0> k0; KinOut<D1> k1;
@@ -51,7 +51,7 @@ struct Chain1 {
     enum { NQ = JointDims<J0>::nq, NU = JointDims<J0>::nu, NY = NQ + NU, NB = 2 };
     const BodyConst* b0; const BodyConst* b1; const ForceConst* forces; double gx, gy, gz;
 
-    SBK_HD void eval(const double* y, double* ydot) const {
+    SBK_HDN void eval(const double* y, double* ydot) const {
         const double* q0 = y; const double* u0 = y + NQ;
         double qe; KinOut<NU> k0;
         kinCore<J0>(*b0, q0, u0, identity3(), zero3(), zeroSV(), k0, ydot, qe);

@@ -48,7 +48,9 @@ enum { CACHE_RECORD_MAX = F_H + 13*6 + 36 };   // 195
 
 // body flags
 enum { BF_PARENT_PREV = 1,   // parent is the body processed just before (index - 1): links ride in the carry
-       BF_STORE_LINK  = 2 }; // some child is NOT index + 1: links must also be stored in the cache
+       BF_STORE_LINK  = 2,   // some child is NOT index + 1: links must also be stored in the cache
+       BF_NO_R_PF     = 4,   // R_PF is exactly the identity (the reference's noR_PF template flag,
+       BF_NO_R_MB     = 8 }; // RigidBodyNodeSpec_Derived.cpp:50-64); likewise R_MB: skip the products
 
 // Per-body constants (batch-shared; staged into shared memory by the kernels).
 struct BodyConst {
@@ -94,10 +96,27 @@ struct Carry {
     int outBody, inBody;
 };
 
+// Streaming global accesses bypass L1 (ld.global.cg / st.global.cg): the per-body records and the
+// state vectors are touched once per sweep, while L1 is needed for the per-thread stack (carry
+// links, Ctx, spills), which the streaming traffic would otherwise evict.
+SBK_HD double gld(const double* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+SBK_HD void gst(double* p, double v) {
+#if defined(__CUDA_ARCH__)
+    __stcg(p, v);
+#else
+    *p = v;
+#endif
+}
 struct CacheRef {     // accessor for one body's record
     double* p; long long stride;
-    SBK_HD double ld(int k) const { return p[(long long)k*stride]; }
-    SBK_HD void   st(int k, double v) const { p[(long long)k*stride] = v; }
+    SBK_HD double ld(int k) const { return gld(p + (long long)k*stride); }
+    SBK_HD void   st(int k, double v) const { gst(p + (long long)k*stride, v); }
     SBK_HD V3 ld3(int k) const { return mk(ld(k), ld(k+1), ld(k+2)); }
     SBK_HD void st3(int k, V3 v) const { st(k, v.x); st(k+1, v.y); st(k+2, v.z); }
     SBK_HD SV ldSV(int k) const { SV r; r.w = ld3(k); r.v = ld3(k+3); return r; }
@@ -114,8 +133,8 @@ struct CacheRef {     // accessor for one body's record
     SBK_HD void stABI(int k, const ABI& P) const { stS3(k, P.M); stS3(k+6, P.J); stM3(k+12, P.F); }
 };
 SBK_HD CacheRef cacheOf(const Ctx& c, long long base) { CacheRef r; r.p = c.cache + base + c.cOff; r.stride = c.cStride; return r; }
-SBK_HD double ldS(const Ctx& c, const double* a, int slot) { return a[(long long)slot*c.sStride + c.sOff]; }
-SBK_HD void   stS(const Ctx& c, double* a, int slot, double v) { a[(long long)slot*c.sStride + c.sOff] = v; }
+SBK_HD double ldS(const Ctx& c, const double* a, int slot) { return gld(a + (long long)slot*c.sStride + c.sOff); }
+SBK_HD void   stS(const Ctx& c, double* a, int slot, double v) { gst(a + (long long)slot*c.sStride + c.sOff, v); }
 
 SBK_HD M3 loadR(const double* X) { M3 R;
 #pragma unroll
@@ -194,15 +213,18 @@ SBK_HD void kinCore(const BodyConst& bc, const double* q, const double* u,
     const M3 R_PF = loadR(bc.X_PF), R_MB = loadR(bc.X_MB);
     const V3 p_PF = loadP(bc.X_PF), p_MB = loadP(bc.X_MB);
 
+    // Multiplying by an exact identity is skipped (same values up to the sign of zeros), as the
+    // reference does through its noR_PF / noX_MB template flags.
+    const bool noRPF = (bc.flags & BF_NO_R_PF) != 0, noRMB = (bc.flags & BF_NO_R_MB) != 0;
     const V3 r     = mul(R_FM, p_MB);                 // r_MB_F = R_FM * p_MB
-    const M3 R_FB  = mul(R_FM, R_MB);  const V3 p_FB = p_FM + r;
-    const M3 R_PB  = mul(R_PF, R_FB);  const V3 p_PB = p_PF + mul(R_PF, p_FB);
+    const M3 R_FB  = noRMB ? R_FM : mul(R_FM, R_MB);  const V3 p_FB = p_FM + r;
+    const M3 R_PB  = noRPF ? R_FB : mul(R_PF, R_FB);  const V3 p_PB = p_PF + (noRPF ? p_FB : mul(R_PF, p_FB));
     o.R = mul(R_GP, R_PB);
     o.l = mul(R_GP, p_PB);                            // Phi: p_PB_G (RigidBodyNode.cpp:61)
     o.p = p_GP + o.l;
 
     // ---- H = R_GF (H_FM + H_MB_F)  (RigidBodyNodeSpec.cpp:44-74) -----------------------------
-    const M3 R_GF = mul(R_GP, R_PF);
+    const M3 R_GF = noRPF ? R_GP : mul(R_GP, R_PF);
 #pragma unroll
     for (int j = 0; j < d; ++j) {
         o.H[j].w = mul(R_GF, Hw[j]);

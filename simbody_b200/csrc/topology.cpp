@@ -80,6 +80,10 @@ void compileTopology(const ModelSpec& spec, sbk_topology& t) {
         bc.joint = d.joint_type; bc.parent = d.parent < 0 ? 0 : d.parent;
         bc.q0 = t.q0[b]; bc.u0 = t.u0[b]; bc.quat = t.quatIndex[b]; bc.level = t.level[b];
         bc.flags = 0;
+        auto isIdentityR = [](const double* X) { return X[0] == 1 && X[4] == 1 && X[8] == 1 && X[1] == 0 && X[2] == 0 &&
+                                                        X[3] == 0 && X[5] == 0 && X[6] == 0 && X[7] == 0; };
+        if (isIdentityR(bc.X_PF)) bc.flags |= sbkd::BF_NO_R_PF;
+        if (isIdentityR(bc.X_MB)) bc.flags |= sbkd::BF_NO_R_MB;
         if (b >= 1 && d.parent == b - 1) bc.flags |= sbkd::BF_PARENT_PREV;
         for (int k : kids[b]) if (k != b + 1) bc.flags |= sbkd::BF_STORE_LINK;
         bc.nchild = (int)kids[b].size(); bc.childStart = (int)t.children.size();
