@@ -34,6 +34,9 @@ WORKLOADS = {
     "humanoid30_64k":     dict(model="humanoid30", n=0, batch=65536, h=1e-3, q_scale=0.5),
     "branched_tree1000_256": dict(model="branched_tree", n=1000, batch=256, h=5e-4, q_scale=0.5),
 }
+# measured DRAM bytes per instance-step (ncu --set full, profiles/r1_prof_*.txt): launch traffic / (N * steps)
+NCU_TRAFFIC_PER_INSTANCE_STEP = {"double_pendulum_1M": 5.588e7 / (1048576 * 20), "humanoid30_64k": 1.746e10 / 65536,
+                                 "pin_chain50_64k": 1.429e10 / 65536}
 F_EVAL = {"PIN": 1180.0, "SLIDER": 1130.0, "UNIVERSAL": 1710.0, "BALL": 2060.0, "FREE": 3800.0}
 
 
@@ -202,7 +205,8 @@ def main():
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         ms_max, e2e_ms_max = float(tmax[0]), float(tmax[1])
         flop, byts = algorithmic_work(info)
-        res = {"name": name, "info": info, "N": N, "spl": spl, "ms_per_step": ms_max / steps,
+        plan = bm.getPlan()
+        res = {"name": name, "info": info, "N": N, "spl": spl, "ms_per_step": ms_max / steps, "plan": plan,
                "value": world * N * spl * steps / (ms_max * 1e-3),
                "e2e": world * N * spl * e2e_steps / (e2e_ms_max * 1e-3),
                "h2d": 8 * ny * N, "d2h": 8 * ny * N, "launches": launches, "kernel_ms_last": kern_ms[-1],
@@ -227,11 +231,15 @@ def main():
     per_gpu_rate = r["value"] / world
     achieved_tflops = per_gpu_rate * r["flop_per_inst_step"] / 1e12
     roofline = {"bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
-                "frac": achieved_tflops / fp64_peak_tflops, "traffic": None,
+                "frac": achieved_tflops / fp64_peak_tflops,
                 "peak_source": "measured live: sbk_dfma_probe DFMA kernel on this GPU (MEASURED_PEAKS.json has no FP64 entry)",
                 "hbm_algorithmic_GBs": per_gpu_rate * r["bytes_per_inst_step"] / 1e9,
                 "hbm_peak_GBs": peaks.get("hbm_gbs"),
-                "kernel": "tpiKernel<OP_RKM>", "kernel_ms_last_launch": r["kernel_ms_last"]}
+                "kernel": {1: "tpiKernel<OP_RKM> (thread-per-instance, LEAN records)", 2: "fusedRkmKernel (register-resident)",
+                           3: "lpKernel<OP_RKM> (level-parallel)"}[r["plan"]],
+                "kernel_ms_last_launch": r["kernel_ms_last"],
+                # dram__bytes_read+write per launch from the committed ncu captures (profiles/), scaled to this launch
+                "traffic": NCU_TRAFFIC_PER_INSTANCE_STEP.get(args.workload, 0) * r["N"] * r["spl"] or None}
 
     line = {"metric": "instance_steps_per_s", "value": r["value"], "unit": "instance-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,

@@ -192,6 +192,8 @@ static int configurePlan(sbk_batch* b, int plan) {
     a.tableBytes = (uint32_t)blob.size(); a.childrenOff = (uint32_t)bodiesBytes; a.forcesOff = (uint32_t)(bodiesBytes + childBytes);
     a.levelOrderOff = (uint32_t)(bodiesBytes + childBytes + forceBytes); a.levelStartOff = a.levelOrderOff + (uint32_t)orderBytes;
     a.nlevels = t->nlevels; a.plan = plan;
+    a.lightJoints = 1;
+    for (int i = 1; i < t->nb; ++i) if (t->nuOf[i] > 2) a.lightJoints = 0;
     a.stageInSmem = (plan != 3 && blob.size() <= 96*1024) ? 1u : 0u;
     CUDA_TRY(cudaStreamSynchronize(b->stream));
     if (b->dTables) cudaFree(b->dTables);
@@ -474,9 +476,9 @@ int sbk_multiply_by_MInv(sbk_batch* b, const double* v, double* MinvV) {
     if (!b->abiValid) { if (int rc = launch(b, OP_ABI)) return rc; b->abiValid = true; }   // lazy, like the reference
     b->accelValid = false;
     if (int rc = h2d(b, b->dOpB, v, b->topo->nu)) return rc;
-    b->a.vecIn = b->dOpB; b->a.vecOut = b->dOpOut;
+    b->a.fmobIn = b->dOpB; b->a.FbodyIn = nullptr; b->a.vecOut = b->dOpOut;   // M^-1: f = v, no body forces
     int rc = launch(b, OP_MULMINV);
-    b->a.vecIn = nullptr; b->a.vecOut = nullptr;
+    b->a.fmobIn = nullptr; b->a.vecOut = nullptr;
     if (rc) return rc;
     return d2h(b, MinvV, b->dOpOut, b->topo->nu);
 }

@@ -21,6 +21,7 @@ namespace {
 #define SBK_TPI_MINBLOCKS 4
 #endif
 constexpr int TPI_THREADS = SBK_TPI_THREADS;
+constexpr int SBK_CARRY_STRIDE_DEVICE = 128;
 
 __device__ __forceinline__ uint32_t smemAddr(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -48,65 +49,71 @@ __device__ __forceinline__ void tmaStage(void* dst, const void* src, uint32_t by
     }
 }
 
-__device__ __forceinline__ Ctx makeCtx(const KArgs& a, const unsigned char* tables, int inst) {
-    Ctx c;
+__device__ __forceinline__ void fillCtx(Ctx& c, const KArgs& a, const unsigned char* tables, bool integrator) {
     c.bodies   = reinterpret_cast<const BodyConst*>(tables);
     c.children = reinterpret_cast<const int*>(tables + a.childrenOff);
     c.forces   = reinterpret_cast<const ForceConst*>(tables + a.forcesOff);
     c.nb = a.nb; c.nq = a.nq; c.nu = a.nu; c.nquat = a.nquat;
     c.gx = a.gx; c.gy = a.gy; c.gz = a.gz;
-    c.cache = a.cache; c.cStride = a.cStride; c.cOff = (long long)inst*a.cInstStride;
-    c.sStride = a.N; c.sOff = inst;
+    c.cache = a.cache; c.cStride = a.cStride; c.cInstStride = a.cInstStride;
+    c.sStride = a.N; c.sInstStride = 1;
     c.q = a.y; c.u = a.y + (long long)a.nq*a.N;
     c.qdot = a.ydot; c.udot = a.ydot ? a.ydot + (long long)a.nq*a.N : nullptr;
     c.qdotdot = a.qdotdot; c.qerr = a.qerr;
     c.fmobIn = a.fmobIn; c.FbodyIn = a.FbodyIn; c.fmobOut = a.fmobOut; c.FbodyOut = a.FbodyOut;
     c.vecIn = a.vecIn; c.vecOut = a.vecOut;
-    c.status = a.status ? a.status + inst : nullptr;
-    return c;
+    c.status = a.status;
+    if (integrator) { c.qdotdot = nullptr; c.qerr = nullptr; c.fmobOut = nullptr; c.FbodyOut = nullptr; }
 }
 
-template <int OP, bool STAGE>
-__global__ void __launch_bounds__(TPI_THREADS, SBK_TPI_MINBLOCKS) tpiKernel(const KArgs a) {
+// MINB = resident CTAs per SM the register allocation is sized for: 4 (128 registers) suits
+// models made of 1-2 dof mobilizers, 2 (255 registers) models with Ball/Free bodies, whose 3x3 /
+// 6x6 articulated-inertia algebra would otherwise spill (measured: +46% on the humanoid).
+template <int OP, bool STAGE, int MINB>
+__global__ void __launch_bounds__(TPI_THREADS, MINB) tpiKernel(const KArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t mbar;
+    __shared__ Ctx sctx;                      // ONE context per CTA, read with LDS by every body step
     const unsigned char* tables = a.tables;
     if constexpr (STAGE) { tmaStage(smem, a.tables, a.tableBytes, &mbar); tables = smem; }
+    if (threadIdx.x == 0) fillCtx(sctx, a, tables, OP == OP_RKM);
+    __syncthreads();
     const int inst = blockIdx.x*blockDim.x + threadIdx.x;
     if (inst >= a.N) return;
-    Ctx c = makeCtx(a, tables, inst);
-    Carry cy; resetCarry(cy);
+    const Ctx& c = sctx;
+    // LEAN carry: a [CARRY_ROWS][128] block of shared memory behind the staged tables
+    double* cy = nullptr;
+    if constexpr (OP == OP_RKM) cy = reinterpret_cast<double*>(smem + (STAGE ? a.tableBytes : 0)) + threadIdx.x;
 
     if constexpr (OP == OP_KIN) {
-        tpiKinematics<false>(c, cy);
+        tpiKinematics<false>(c, inst, cy, c.qdot);
     } else if constexpr (OP == OP_ABI) {
-        tpiInward<IN_ABI, false>(c, cy);
+        tpiInward<IN_ABI, false>(c, inst, cy);
     } else if constexpr (OP == OP_EVAL) {
-        tpiEvalDerivatives<false>(c, cy);
+        tpiEvalDerivatives<false>(c, inst, cy, c.qdot, c.udot, c.qdotdot);
     } else if constexpr (OP == OP_CALCACC) {
-        tpiInward<IN_Z | IN_BIAS, false>(c, cy);
-        tpiOutward<true, false>(c, cy, c.vecOut, nullptr);
+        tpiInward<IN_Z | IN_BIAS, false>(c, inst, cy);
+        tpiOutward<true, false>(c, inst, cy, c.vecOut, nullptr);
     } else if constexpr (OP == OP_MULM) {
-        for (int b = 1; b < c.nb; ++b) idOutDispatch<false>(c, b);
-        for (int b = c.nb - 1; b >= 1; --b) idInDispatch<false>(c, b);
+        for (int b = 1; b < c.nb; ++b) idOutDispatch<false>(c, b, inst);
+        for (int b = c.nb - 1; b >= 1; --b) idInDispatch<false>(c, b, inst);
     } else if constexpr (OP == OP_MULMINV) {
-        c.fmobIn = a.vecIn; c.FbodyIn = nullptr;
-        tpiInward<IN_Z, false>(c, cy);
-        tpiOutward<false, false>(c, cy, c.vecOut, nullptr);
+        tpiInward<IN_Z, false>(c, inst, cy);             // c.fmobIn == a.vecIn, c.FbodyIn == null (set by the host)
+        tpiOutward<false, false>(c, inst, cy, c.vecOut, nullptr);
     } else if constexpr (OP == OP_RESID) {
-        for (int b = 1; b < c.nb; ++b) idOutDispatch<true>(c, b);
-        for (int b = c.nb - 1; b >= 1; --b) idInDispatch<true>(c, b);
+        for (int b = 1; b < c.nb; ++b) idOutDispatch<true>(c, b, inst);
+        for (int b = c.nb - 1; b >= 1; --b) idInDispatch<true>(c, b, inst);
     } else if constexpr (OP == OP_RKM) {
         RkmWork w;
         w.y = a.y; w.y0 = a.y0; w.f0 = a.f0; w.fa = a.fa; w.fb = a.fb; w.ys = a.ys;
         w.accuracy = a.accuracy; w.consTol = a.consTol; w.useInfNorm = a.useInfNorm; w.projectEveryStep = a.projectEveryStep;
         RkmStepResult r; r.errNorm = 0; r.projected = 0;
         int nproj = 0; double t = a.tcur[inst];
-        for (int s = 0; s < a.nsteps; ++s) { r = tpiRkmStep<true>(c, w, a.h, cy); nproj += r.projected; t += a.h; }
+        for (int s = 0; s < a.nsteps; ++s) { r = tpiRkmStep<true>(c, inst, w, a.h, cy); nproj += r.projected; t += a.h; }
         a.tcur[inst] = t;
         a.errNorm[inst] = r.errNorm;
         a.projCount[inst] += nproj;
-        if (c.status && !(r.errNorm == r.errNorm)) *c.status |= 1;   // NaN error norm
+        if (a.status && !(r.errNorm == r.errNorm)) atomicOr(a.status + inst, 1);   // NaN error norm
     }
 }
 
@@ -143,15 +150,20 @@ cudaError_t launchFusedT(const KArgs& a, cudaStream_t stream) {
 
 template <int OP>
 cudaError_t launchOp(const KArgs& a, cudaStream_t stream) {
+    static_assert(TPI_THREADS == SBK_CARRY_STRIDE_DEVICE, "carry columns are laid out for 128-thread CTAs");
     const int grid = (a.N + TPI_THREADS - 1)/TPI_THREADS;
-    if (a.stageInSmem) {
-        cudaError_t e = cudaFuncSetAttribute(tpiKernel<OP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.tableBytes);
+    const size_t carryBytes = (OP == OP_RKM) ? (size_t)CARRY_ROWS*TPI_THREADS*sizeof(double) : 0;
+    const size_t smemBytes = (a.stageInSmem ? a.tableBytes : 0) + carryBytes;
+    auto go = [&](auto kernel) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
         if (e != cudaSuccess) return e;
-        tpiKernel<OP, true><<<grid, TPI_THREADS, a.tableBytes, stream>>>(a);
-    } else {
-        tpiKernel<OP, false><<<grid, TPI_THREADS, 0, stream>>>(a);
+        kernel<<<grid, TPI_THREADS, smemBytes, stream>>>(a);
+        return cudaGetLastError();
+    };
+    if constexpr (OP == OP_RKM) {
+        if (a.lightJoints) return a.stageInSmem ? go(tpiKernel<OP, true, 4>) : go(tpiKernel<OP, false, 4>);
     }
-    return cudaGetLastError();
+    return a.stageInSmem ? go(tpiKernel<OP, true, 2>) : go(tpiKernel<OP, false, 2>);
 }
 
 //==============================================================================================
@@ -183,20 +195,20 @@ template <class F> __device__ __forceinline__ void lpInward(const LpLevels& L, F
         __syncthreads();
     }
 }
-__device__ __forceinline__ void lpEval(const Ctx& c, const LpLevels& L, Carry& cy) {
-    lpOutward(L, [&](int b) { kinDispatch<false>(c, b, cy); });
-    lpInward(L,  [&](int b) { inwardDispatch<IN_ABI | IN_Z | IN_BIAS | IN_FORCES, false>(c, b, cy); });
-    lpOutward(L, [&](int b) { outwardDispatch<true, false>(c, b, cy, c.udot, c.qdotdot); });
+__device__ __forceinline__ void lpEval(const Ctx& c, const int inst, const LpLevels& L, double* qdotDst, double* udotDst, double* qddDst) {
+    lpOutward(L, [&](int b) { kinDispatch<false>(c, b, inst, nullptr, qdotDst); });
+    lpInward(L,  [&](int b) { inwardDispatch<IN_ABI | IN_Z | IN_BIAS | IN_FORCES, false>(c, b, inst, nullptr); });
+    lpOutward(L, [&](int b) { outwardDispatch<true, false>(c, b, inst, nullptr, udotDst, qddDst); });
 }
 
 // Error norm of IntegratorRep::calcErrorNorm, threads over slots / bodies (cf. rkmErrorNorm).
-__device__ double lpErrorNorm(const Ctx& c, const KArgs& a, double* red) {
+__device__ double lpErrorNorm(const Ctx& c, const int inst, const KArgs& a, double* red) {
     const int nq = c.nq, nu = c.nu; const bool inf = a.useInfNorm != 0;
     double uAcc = 0, qAcc = 0;
     for (int i = threadIdx.x; i < nu; i += LP_THREADS) {
-        const double u0 = fabs(ldS(c, a.y0, nq + i));
+        const double u0 = fabs(ldS(c, inst, a.y0, nq + i));
         const double sc = (u0*1.0 > 1.0) ? 1.0/u0 : 1.0;
-        const double v = sc*ldS(c, a.ys, nq + i);
+        const double v = sc*ldS(c, inst, a.ys, nq + i);
         if (inf) uAcc = fmax(uAcc, fabs(v)); else uAcc += v*v;
     }
     for (int b = 1 + threadIdx.x; b < c.nb; b += LP_THREADS) {
@@ -204,14 +216,14 @@ __device__ double lpErrorNorm(const Ctx& c, const KArgs& a, double* red) {
         int first = 0;
         if (bc.joint == JT_BALL || bc.joint == JT_FREE) {
             double q[4], e[4], o[4];
-            for (int i = 0; i < 4; ++i) { q[i] = ldS(c, a.y, bc.q0 + i); e[i] = ldS(c, a.ys, bc.q0 + i); }
+            for (int i = 0; i < 4; ++i) { q[i] = ldS(c, inst, a.y, bc.q0 + i); e[i] = ldS(c, inst, a.ys, bc.q0 + i); }
             const V3 du = quatNInvTimes(q, e);
             quatNTimes(q, du, o);
             for (int i = 0; i < 4; ++i) { if (inf) qAcc = fmax(qAcc, fabs(o[i])); else qAcc += o[i]*o[i]; }
             first = 4;
         }
         const int nqb = bc.joint == JT_FREE ? 7 : bc.joint == JT_BALL ? 4 : bc.joint == JT_UNIVERSAL ? 2 : 1;
-        for (int i = first; i < nqb; ++i) { const double v = ldS(c, a.ys, bc.q0 + i); if (inf) qAcc = fmax(qAcc, fabs(v)); else qAcc += v*v; }
+        for (int i = first; i < nqb; ++i) { const double v = ldS(c, inst, a.ys, bc.q0 + i); if (inf) qAcc = fmax(qAcc, fabs(v)); else qAcc += v*v; }
     }
     uAcc = blockReduce(uAcc, inf, red); qAcc = blockReduce(qAcc, inf, red);
     const double qNorm = inf ? qAcc : (nq ? sqrt(qAcc/nq) : 0.0), uNorm = inf ? uAcc : (nu ? sqrt(uAcc/nu) : 0.0);
@@ -221,64 +233,64 @@ __device__ double lpErrorNorm(const Ctx& c, const KArgs& a, double* red) {
 template <int OP>
 __global__ void __launch_bounds__(LP_THREADS, 2) lpKernel(const KArgs a) {
     __shared__ double red[LP_THREADS/32];
+    __shared__ Ctx sctx;
     const int inst = blockIdx.x;
-    Ctx c = makeCtx(a, a.tables, inst);
-    Carry cy; resetCarry(cy);
+    if (threadIdx.x == 0) fillCtx(sctx, a, a.tables, OP == OP_RKM);
+    __syncthreads();
+    const Ctx& c = sctx;
     LpLevels L; L.order = reinterpret_cast<const int*>(a.tables + a.levelOrderOff);
     L.start = reinterpret_cast<const int*>(a.tables + a.levelStartOff); L.nlevels = a.nlevels;
 
     if constexpr (OP == OP_KIN) {
-        lpOutward(L, [&](int b) { kinDispatch<false>(c, b, cy); });
+        lpOutward(L, [&](int b) { kinDispatch<false>(c, b, inst, nullptr, c.qdot); });
     } else if constexpr (OP == OP_ABI) {
-        lpInward(L, [&](int b) { inwardDispatch<IN_ABI, false>(c, b, cy); });
+        lpInward(L, [&](int b) { inwardDispatch<IN_ABI, false>(c, b, inst, nullptr); });
     } else if constexpr (OP == OP_EVAL) {
-        lpEval(c, L, cy);
+        lpEval(c, inst, L, c.qdot, c.udot, c.qdotdot);
     } else if constexpr (OP == OP_CALCACC) {
-        lpInward(L,  [&](int b) { inwardDispatch<IN_Z | IN_BIAS, false>(c, b, cy); });
-        lpOutward(L, [&](int b) { outwardDispatch<true, false>(c, b, cy, c.vecOut, nullptr); });
+        lpInward(L,  [&](int b) { inwardDispatch<IN_Z | IN_BIAS, false>(c, b, inst, nullptr); });
+        lpOutward(L, [&](int b) { outwardDispatch<true, false>(c, b, inst, nullptr, c.vecOut, nullptr); });
     } else if constexpr (OP == OP_MULM) {
-        lpOutward(L, [&](int b) { idOutDispatch<false>(c, b); });
-        lpInward(L,  [&](int b) { idInDispatch<false>(c, b); });
+        lpOutward(L, [&](int b) { idOutDispatch<false>(c, b, inst); });
+        lpInward(L,  [&](int b) { idInDispatch<false>(c, b, inst); });
     } else if constexpr (OP == OP_MULMINV) {
-        c.fmobIn = a.vecIn; c.FbodyIn = nullptr;
-        lpInward(L,  [&](int b) { inwardDispatch<IN_Z, false>(c, b, cy); });
-        lpOutward(L, [&](int b) { outwardDispatch<false, false>(c, b, cy, c.vecOut, nullptr); });
+        lpInward(L,  [&](int b) { inwardDispatch<IN_Z, false>(c, b, inst, nullptr); });
+        lpOutward(L, [&](int b) { outwardDispatch<false, false>(c, b, inst, nullptr, c.vecOut, nullptr); });
     } else if constexpr (OP == OP_RESID) {
-        lpOutward(L, [&](int b) { idOutDispatch<true>(c, b); });
-        lpInward(L,  [&](int b) { idInDispatch<true>(c, b); });
+        lpOutward(L, [&](int b) { idOutDispatch<true>(c, b, inst); });
+        lpInward(L,  [&](int b) { idInDispatch<true>(c, b, inst); });
     } else if constexpr (OP == OP_RKM) {
         const int nq = c.nq, ny = c.nq + c.nu; const long long uoff = (long long)nq*c.sStride;
-        c.q = a.y; c.u = a.y + uoff; c.qdotdot = nullptr; c.qerr = nullptr; c.fmobOut = nullptr; c.FbodyOut = nullptr;
         const double h = a.h; double err = 0; int nproj = 0;
         for (int s = 0; s < a.nsteps; ++s) {
-            c.qdot = a.f0; c.udot = a.f0 + uoff; lpEval(c, L, cy);
-            for (int i = threadIdx.x; i < ny; i += LP_THREADS) { const double y0 = ldS(c, a.y, i); stS(c, a.y0, i, y0); stS(c, a.y, i, y0 + (h/3)*ldS(c, a.f0, i)); }
+            lpEval(c, inst, L, a.f0, a.f0 + uoff, nullptr);
+            for (int i = threadIdx.x; i < ny; i += LP_THREADS) { const double y0 = ldS(c, inst, a.y, i); stS(c, inst, a.y0, i, y0); stS(c, inst, a.y, i, y0 + (h/3)*ldS(c, inst, a.f0, i)); }
             __syncthreads();
-            c.qdot = a.fa; c.udot = a.fa + uoff; lpEval(c, L, cy);
-            for (int i = threadIdx.x; i < ny; i += LP_THREADS) stS(c, a.y, i, ldS(c, a.y0, i) + (h/6)*(ldS(c, a.f0, i) + ldS(c, a.fa, i)));
+            lpEval(c, inst, L, a.fa, a.fa + uoff, nullptr);
+            for (int i = threadIdx.x; i < ny; i += LP_THREADS) stS(c, inst, a.y, i, ldS(c, inst, a.y0, i) + (h/6)*(ldS(c, inst, a.f0, i) + ldS(c, inst, a.fa, i)));
             __syncthreads();
-            lpEval(c, L, cy);
-            for (int i = threadIdx.x; i < ny; i += LP_THREADS) stS(c, a.y, i, ldS(c, a.y0, i) + (h/8)*(ldS(c, a.f0, i) + 3*ldS(c, a.fa, i)));
+            lpEval(c, inst, L, a.fa, a.fa + uoff, nullptr);
+            for (int i = threadIdx.x; i < ny; i += LP_THREADS) stS(c, inst, a.y, i, ldS(c, inst, a.y0, i) + (h/8)*(ldS(c, inst, a.f0, i) + 3*ldS(c, inst, a.fa, i)));
             __syncthreads();
-            c.qdot = a.fb; c.udot = a.fb + uoff; lpEval(c, L, cy);
+            lpEval(c, inst, L, a.fb, a.fb + uoff, nullptr);
             for (int i = threadIdx.x; i < ny; i += LP_THREADS) {
-                const double ys = ldS(c, a.y0, i) + (h/2)*(ldS(c, a.f0, i) - 3*ldS(c, a.fa, i) + 4*ldS(c, a.fb, i));
-                stS(c, a.ys, i, ys); stS(c, a.y, i, ys);
+                const double ys = ldS(c, inst, a.y0, i) + (h/2)*(ldS(c, inst, a.f0, i) - 3*ldS(c, inst, a.fa, i) + 4*ldS(c, inst, a.fb, i));
+                stS(c, inst, a.ys, i, ys); stS(c, inst, a.y, i, ys);
             }
             __syncthreads();
-            c.qdot = a.fa; c.udot = a.fa + uoff; lpEval(c, L, cy);
+            lpEval(c, inst, L, a.fa, a.fa + uoff, nullptr);
             for (int i = threadIdx.x; i < ny; i += LP_THREADS) {
-                const double y1 = ldS(c, a.y0, i) + (h/6)*(ldS(c, a.f0, i) + 4*ldS(c, a.fb, i) + ldS(c, a.fa, i));
-                stS(c, a.y, i, y1); stS(c, a.ys, i, 0.2*fabs(y1 - ldS(c, a.ys, i)));
+                const double y1 = ldS(c, inst, a.y0, i) + (h/6)*(ldS(c, inst, a.f0, i) + 4*ldS(c, inst, a.fb, i) + ldS(c, inst, a.fa, i));
+                stS(c, inst, a.y, i, y1); stS(c, inst, a.ys, i, 0.2*fabs(y1 - ldS(c, inst, a.ys, i)));
             }
             __syncthreads();
-            err = lpErrorNorm(c, a, red);
+            err = lpErrorNorm(c, inst, a, red);
             if (c.nquat > 0 && !(err > 16.0*a.accuracy)) {       // uniform across the CTA
                 double acc = 0; const bool inf = a.useInfNorm != 0;
                 for (int b = 1 + threadIdx.x; b < c.nb; b += LP_THREADS) {
                     const BodyConst& bc = c.bodies[b];
                     if (bc.joint != JT_BALL && bc.joint != JT_FREE) continue;
-                    double n2 = 0; for (int i = 0; i < 4; ++i) { const double qi = ldS(c, a.y, bc.q0 + i); n2 += qi*qi; }
+                    double n2 = 0; for (int i = 0; i < 4; ++i) { const double qi = ldS(c, inst, a.y, bc.q0 + i); n2 += qi*qi; }
                     const double e = sqrt(n2) - 1.0;
                     if (inf) acc = fmax(acc, fabs(e)); else acc += e*e;
                 }
@@ -289,14 +301,14 @@ __global__ void __launch_bounds__(LP_THREADS, 2) lpKernel(const KArgs a) {
                         const BodyConst& bc = c.bodies[b];
                         if (bc.joint != JT_BALL && bc.joint != JT_FREE) continue;
                         double q[4], e[4], n2 = 0;
-                        for (int i = 0; i < 4; ++i) { q[i] = ldS(c, a.y, bc.q0 + i); e[i] = ldS(c, a.ys, bc.q0 + i); n2 += q[i]*q[i]; }
+                        for (int i = 0; i < 4; ++i) { q[i] = ldS(c, inst, a.y, bc.q0 + i); e[i] = ldS(c, inst, a.ys, bc.q0 + i); n2 += q[i]*q[i]; }
                         const double n = sqrt(n2); double dt = 0;
                         for (int i = 0; i < 4; ++i) { q[i] = q[i]/n; dt += e[i]*q[i]; }
-                        for (int i = 0; i < 4; ++i) { stS(c, a.y, bc.q0 + i, q[i]); stS(c, a.ys, bc.q0 + i, e[i] - dt*q[i]); }
+                        for (int i = 0; i < 4; ++i) { stS(c, inst, a.y, bc.q0 + i, q[i]); stS(c, inst, a.ys, bc.q0 + i, e[i] - dt*q[i]); }
                     }
                     __syncthreads();
                     ++nproj;
-                    err = lpErrorNorm(c, a, red);
+                    err = lpErrorNorm(c, inst, a, red);
                 }
             }
             __syncthreads();

@@ -13,6 +13,7 @@ struct KArgs {
     const unsigned char* tables;     // device blob
     uint32_t tableBytes, childrenOff, forcesOff, stageInSmem;
     uint32_t levelOrderOff, levelStartOff; int nlevels, plan;
+    int lightJoints, pad0_;           // 1 if every mobilizer has dof <= 2 (128-register kernel variant)
     long long cStride, cInstStride;  // cache addressing: base_b + field*cStride + inst*cInstStride
     int nb, nq, nu, nquat;
     double gx, gy, gz;

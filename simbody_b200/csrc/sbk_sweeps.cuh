@@ -25,6 +25,21 @@
 #pragma once
 #include "sbk_math.cuh"
 
+// Where the function-call boundaries sit.  An ABI call makes the callee save and restore every
+// callee-saved register it touches (~100 registers = ~800 bytes of local-memory traffic per call
+// for these FP64-heavy bodies, measured with ncu), so the integrator calls ONE non-inlined
+// function per derivative evaluation and inlines the per-body steps into it.
+#ifndef SBK_INLINE_BODIES
+#define SBK_INLINE_BODIES 1
+#endif
+#if SBK_INLINE_BODIES
+#define SBK_BODY SBK_HD
+#define SBK_EVAL SBK_HDN
+#else
+#define SBK_BODY SBK_HDN
+#define SBK_EVAL SBK_HD
+#endif
+
 namespace sbkd {
 
 enum { JT_GROUND = 0, JT_PIN = 1, JT_SLIDER = 2, JT_UNIVERSAL = 3, JT_BALL = 4, JT_FREE = 5 };
@@ -67,34 +82,79 @@ struct BodyConst {
 };
 struct ForceConst { int kind; int coord; double a; double b; };
 
-// What one work item sees.  q/u/qdot/... are SoA arrays addressed [slot*sStride + sOff].
+// Context shared by every work item of a CTA (the device keeps ONE copy in shared memory, read
+// with LDS: nothing per-thread lives in local memory).  SoA arrays are addressed
+//   state : a[slot*sStride + inst*sInstStride]          cache : cache[base_b + k*cStride + inst*cInstStride]
 struct Ctx {
     const BodyConst*  bodies;
     const int*        children;
     const ForceConst* forces;
     int nb, nq, nu, nquat;
     double gx, gy, gz;              // gravity vector g*d (Force_Gravity.cpp:532), 0 if none
-    // cache addressing: element (body record base B, field k) at cache[B + k*cStride + cOff]
     double*   cache;
-    long long cStride, cOff;
-    // state addressing
-    long long sStride, sOff;
+    long long cStride, cInstStride;
+    long long sStride, sInstStride;
     const double* q; const double* u;
-    double* qdot; double* udot; double* qdotdot; double* qerr;
+    double* qdot; double* udot; double* qdotdot; double* qerr;   // realize-path destinations (nullable)
     // operator inputs / outputs (nullable)
     const double* fmobIn;  const double* FbodyIn;   // applied forces for operator forms
     double* fmobOut; double* FbodyOut;              // force-subsystem results (getter)
     const double* vecIn; double* vecOut;            // generic nu-vectors for M, M^-1, residual
-    int* status;                                    // per-instance status word
+    int* status;                                    // per-instance status words [N]
 };
 
-// Links between consecutive bodies of one instance, kept by the thread that walks the tree.
-struct Carry {
-    M3 R; V3 p; SV V;        // X_GB, V_GB of the last body visited by an outward sweep
-    SV A;                    // A_GB of the last body visited by sweep E
-    ABI PP; SV zP; V3 l;     // P+, z+ and Phi.l of the last body visited by an inward sweep
-    int outBody, inBody;
-};
+// Links between consecutive bodies of one instance in LEAN mode: a column of CARRY_ROWS doubles
+// per work item in SHARED memory ([row][thread], conflict-free), reused by the three sweeps:
+//   sweeps A+B : X_GB (12) + V_GB (6) of the previous body      rows 0..17
+//   sweep  C/D : P+ (21) + z+ (6) + Phi.l (3) of the next body  rows 0..29
+//   sweep  E   : A_GB (6) of the previous body                  rows 0..5
+// Body b-1 is always the previous body of an outward sweep and b+1 of an inward one, so no
+// bookkeeping is needed: BF_PARENT_PREV says whether the parent is b-1.
+enum { CARRY_ROWS = 30 };
+#if defined(__CUDA_ARCH__)
+#define SBK_CARRY_STRIDE 128
+#else
+#define SBK_CARRY_STRIDE 1
+#endif
+SBK_HD void cyStoreOut(double* cy, const M3& R, const V3 p, const SV V) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) cy[i*SBK_CARRY_STRIDE] = R.a[i];
+    cy[9*SBK_CARRY_STRIDE] = p.x; cy[10*SBK_CARRY_STRIDE] = p.y; cy[11*SBK_CARRY_STRIDE] = p.z;
+    cy[12*SBK_CARRY_STRIDE] = V.w.x; cy[13*SBK_CARRY_STRIDE] = V.w.y; cy[14*SBK_CARRY_STRIDE] = V.w.z;
+    cy[15*SBK_CARRY_STRIDE] = V.v.x; cy[16*SBK_CARRY_STRIDE] = V.v.y; cy[17*SBK_CARRY_STRIDE] = V.v.z;
+}
+SBK_HD void cyLoadOut(const double* cy, M3& R, V3& p, SV& V) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R.a[i] = cy[i*SBK_CARRY_STRIDE];
+    p = mk(cy[9*SBK_CARRY_STRIDE], cy[10*SBK_CARRY_STRIDE], cy[11*SBK_CARRY_STRIDE]);
+    V.w = mk(cy[12*SBK_CARRY_STRIDE], cy[13*SBK_CARRY_STRIDE], cy[14*SBK_CARRY_STRIDE]);
+    V.v = mk(cy[15*SBK_CARRY_STRIDE], cy[16*SBK_CARRY_STRIDE], cy[17*SBK_CARRY_STRIDE]);
+}
+SBK_HD void cyStoreA(double* cy, const SV A) {
+    cy[0] = A.w.x; cy[1*SBK_CARRY_STRIDE] = A.w.y; cy[2*SBK_CARRY_STRIDE] = A.w.z;
+    cy[3*SBK_CARRY_STRIDE] = A.v.x; cy[4*SBK_CARRY_STRIDE] = A.v.y; cy[5*SBK_CARRY_STRIDE] = A.v.z;
+}
+SBK_HD SV cyLoadA(const double* cy) {
+    SV A; A.w = mk(cy[0], cy[1*SBK_CARRY_STRIDE], cy[2*SBK_CARRY_STRIDE]);
+    A.v = mk(cy[3*SBK_CARRY_STRIDE], cy[4*SBK_CARRY_STRIDE], cy[5*SBK_CARRY_STRIDE]); return A;
+}
+SBK_HD void cyStoreIn(double* cy, const ABI& P, const SV z, const V3 l) {
+    const double v[30] = {P.M.xx, P.M.yy, P.M.zz, P.M.xy, P.M.xz, P.M.yz, P.J.xx, P.J.yy, P.J.zz, P.J.xy, P.J.xz, P.J.yz,
+                          P.F.a[0], P.F.a[1], P.F.a[2], P.F.a[3], P.F.a[4], P.F.a[5], P.F.a[6], P.F.a[7], P.F.a[8],
+                          z.w.x, z.w.y, z.w.z, z.v.x, z.v.y, z.v.z, l.x, l.y, l.z};
+#pragma unroll
+    for (int i = 0; i < 30; ++i) cy[i*SBK_CARRY_STRIDE] = v[i];
+}
+SBK_HD void cyLoadIn(const double* cy, ABI& P, SV& z, V3& l) {
+    double v[30];
+#pragma unroll
+    for (int i = 0; i < 30; ++i) v[i] = cy[i*SBK_CARRY_STRIDE];
+    P.M.xx = v[0]; P.M.yy = v[1]; P.M.zz = v[2]; P.M.xy = v[3]; P.M.xz = v[4]; P.M.yz = v[5];
+    P.J.xx = v[6]; P.J.yy = v[7]; P.J.zz = v[8]; P.J.xy = v[9]; P.J.xz = v[10]; P.J.yz = v[11];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) P.F.a[i] = v[12+i];
+    z.w = mk(v[21], v[22], v[23]); z.v = mk(v[24], v[25], v[26]); l = mk(v[27], v[28], v[29]);
+}
 
 // Streaming global accesses bypass L1 (ld.global.cg / st.global.cg): the per-body records and the
 // state vectors are touched once per sweep, while L1 is needed for the per-thread stack (carry
@@ -132,9 +192,9 @@ struct CacheRef {     // accessor for one body's record
     SBK_HD ABI ldABI(int k) const { ABI P; P.M = ldS3(k); P.J = ldS3(k+6); P.F = ldM3(k+12); return P; }
     SBK_HD void stABI(int k, const ABI& P) const { stS3(k, P.M); stS3(k+6, P.J); stM3(k+12, P.F); }
 };
-SBK_HD CacheRef cacheOf(const Ctx& c, long long base) { CacheRef r; r.p = c.cache + base + c.cOff; r.stride = c.cStride; return r; }
-SBK_HD double ldS(const Ctx& c, const double* a, int slot) { return gld(a + (long long)slot*c.sStride + c.sOff); }
-SBK_HD void   stS(const Ctx& c, double* a, int slot, double v) { gst(a + (long long)slot*c.sStride + c.sOff, v); }
+SBK_HD CacheRef cacheOf(const Ctx& c, int inst, long long base) { CacheRef r; r.p = c.cache + base + (long long)inst*c.cInstStride; r.stride = c.cStride; return r; }
+SBK_HD double ldS(const Ctx& c, int inst, const double* a, int slot) { return gld(a + (long long)slot*c.sStride + (long long)inst*c.sInstStride); }
+SBK_HD void   stS(const Ctx& c, int inst, double* a, int slot, double v) { gst(a + (long long)slot*c.sStride + (long long)inst*c.sInstStride, v); }
 
 SBK_HD M3 loadR(const double* X) { M3 R;
 #pragma unroll
@@ -392,39 +452,39 @@ SBK_HD void mobilityForces(const BodyConst& bc, const ForceConst* forces, const 
 }
 
 //==============================================================================================
-//                     BODY WRAPPERS (cache records in HBM + per-thread carry)
+//                     BODY WRAPPERS (cache records in HBM + per-work-item carry)
 //==============================================================================================
 // LEAN = false: every field is stored (API realize path: getters and operators need them).
 // LEAN = true : integrator path; links ride in the carry when the tree order allows.
 
 template <int JT, bool LEAN>
-SBK_HDN void kinBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, Carry& cy) {
+SBK_BODY void kinBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, const int inst, double* cy, double* qdotDst) {
     constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
-    const CacheRef me = cacheOf(c, bc.cacheBase);
+    const CacheRef me = cacheOf(c, inst, bc.cacheBase);
     double q[NQ], u[d], qdot[NQ], qerr;
 #pragma unroll
-    for (int i = 0; i < NQ; ++i) q[i] = ldS(c, c.q, bc.q0 + i);
+    for (int i = 0; i < NQ; ++i) q[i] = ldS(c, inst, c.q, bc.q0 + i);
 #pragma unroll
-    for (int i = 0; i < d; ++i)  u[i] = ldS(c, c.u, bc.u0 + i);
+    for (int i = 0; i < d; ++i)  u[i] = ldS(c, inst, c.u, bc.u0 + i);
 
     M3 R_GP; V3 p_GP; SV V_GP;
-    if (LEAN && (bc.flags & BF_PARENT_PREV) && cy.outBody == bc.parent) { R_GP = cy.R; p_GP = cy.p; V_GP = cy.V; }
-    else { const CacheRef pa = cacheOf(c, bc.parentCacheBase); R_GP = pa.ldM3(F_XGB); p_GP = pa.ld3(F_XGB + 9); V_GP = pa.ldSV(F_VGB); }
+    if (LEAN && (bc.flags & BF_PARENT_PREV)) cyLoadOut(cy, R_GP, p_GP, V_GP);
+    else { const CacheRef pa = cacheOf(c, inst, bc.parentCacheBase); R_GP = pa.ldM3(F_XGB); p_GP = pa.ld3(F_XGB + 9); V_GP = pa.ldSV(F_VGB); }
 
     KinOut<d> o;
     kinCore<JT>(bc, q, u, R_GP, p_GP, V_GP, o, qdot, qerr);
 
     if (!LEAN || (bc.flags & BF_STORE_LINK)) { me.stM3(F_XGB, o.R); me.st3(F_XGB + 9, o.p); me.stSV(F_VGB, o.V); }
-    cy.R = o.R; cy.p = o.p; cy.V = o.V; cy.outBody = bodyIndex;
+    if (LEAN) cyStoreOut(cy, o.R, o.p, o.V);
     me.st3(F_L, o.l); me.st3(F_MK, o.c); me.stS3(F_MK + 3, o.G);
     me.stSV(F_ACOR, o.acor); me.stSV(F_GYRO, o.gyro);
 #pragma unroll
     for (int j = 0; j < d; ++j) me.stSV(F_H + 6*j, o.H[j]);
-    if (c.qdot) {
+    if (qdotDst) {
 #pragma unroll
-        for (int i = 0; i < NQ; ++i) stS(c, c.qdot, bc.q0 + i, qdot[i]);
+        for (int i = 0; i < NQ; ++i) stS(c, inst, qdotDst, bc.q0 + i, qdot[i]);
     }
-    if constexpr (JT == JT_BALL || JT == JT_FREE) { if (c.qerr) stS(c, c.qerr, bc.quat, qerr); }
+    if constexpr (JT == JT_BALL || JT == JT_FREE) { if (c.qerr) stS(c, inst, c.qerr, bc.quat, qerr); }
 }
 
 // Inward body step.  MODE bits:
@@ -436,30 +496,36 @@ SBK_HDN void kinBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, Car
 enum { IN_ABI = 1, IN_Z = 2, IN_BIAS = 4, IN_FORCES = 8 };
 
 template <int JT, int MODE, bool LEAN>
-SBK_HDN void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, Carry& cy) {
+SBK_BODY void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, const int inst, double* cy) {
     constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
-    const CacheRef me = cacheOf(c, bc.cacheBase);
+    const CacheRef me = cacheOf(c, inst, bc.cacheBase);
     SV H[d];
 #pragma unroll
     for (int j = 0; j < d; ++j) H[j] = me.ldSV(F_H + 6*j);
     const V3 c_G = me.ld3(F_MK);
+    V3 lMe = zero3();
+    if (LEAN) lMe = me.ld3(F_L);
     const bool linkToCache = !LEAN || !(bc.flags & BF_PARENT_PREV);
+    // the adjacent child (index + 1), if any, left its links in the carry
+    ABI cPP; SV czP = zeroSV(); V3 cl = zero3();
+    bool haveCarryChild = false;
+    if (LEAN && bc.nchild > 0 && c.children[bc.childStart] == bodyIndex + 1) { cyLoadIn(cy, cPP, czP, cl); haveCarryChild = true; }
 
     AbiOut<d> ao; ao.zb = zeroSV();
     if constexpr ((MODE & IN_ABI) != 0) {
         const S3 G_G = me.ldS3(F_MK + 3);
         ABI P = abiFromRigid(bc.mass, c_G, G_G);
         for (int k = 0; k < bc.nchild; ++k) {
-            const int ci = c.children[bc.childStart + k];
-            if (LEAN && ci == cy.inBody) addInto(P, shiftABI(cy.PP, cy.l));
-            else { const CacheRef ch = cacheOf(c, c.bodies[ci].cacheBase); addInto(P, shiftABI(ch.ldABI(F_PPLUS), ch.ld3(F_L))); }
+            if (k == 0 && haveCarryChild) { addInto(P, shiftABI(cPP, cl)); continue; }
+            const CacheRef ch = cacheOf(c, inst, c.bodies[c.children[bc.childStart + k]].cacheBase);
+            addInto(P, shiftABI(ch.ldABI(F_PPLUS), ch.ld3(F_L)));
         }
         abiCore<d>(P, H, me.ldSV(F_ACOR), me.ldSV(F_GYRO), ao);
         if (!ao.ok && c.status) {
 #if defined(__CUDA_ARCH__)
-            atomicOr(c.status, 2);
+            atomicOr(c.status + inst, 2);
 #else
-            *c.status |= 2;
+            c.status[inst] |= 2;
 #endif
         }
 #pragma unroll
@@ -483,34 +549,34 @@ SBK_HDN void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, 
             double q[NQ], u[d];
             if (bc.nforce > 0) {
 #pragma unroll
-                for (int i = 0; i < NQ; ++i) q[i] = ldS(c, c.q, bc.q0 + i);
+                for (int i = 0; i < NQ; ++i) q[i] = ldS(c, inst, c.q, bc.q0 + i);
 #pragma unroll
-                for (int i = 0; i < d; ++i)  u[i] = ldS(c, c.u, bc.u0 + i);
+                for (int i = 0; i < d; ++i)  u[i] = ldS(c, inst, c.u, bc.u0 + i);
             }
             mobilityForces<d>(bc, c.forces, q, u, f);
             if (c.fmobOut) {
 #pragma unroll
-                for (int j = 0; j < d; ++j) stS(c, c.fmobOut, bc.u0 + j, f[j]);
+                for (int j = 0; j < d; ++j) stS(c, inst, c.fmobOut, bc.u0 + j, f[j]);
             }
             if (c.FbodyOut) {
-                stS(c, c.FbodyOut, 6*bodyIndex+0, F.w.x); stS(c, c.FbodyOut, 6*bodyIndex+1, F.w.y); stS(c, c.FbodyOut, 6*bodyIndex+2, F.w.z);
-                stS(c, c.FbodyOut, 6*bodyIndex+3, F.v.x); stS(c, c.FbodyOut, 6*bodyIndex+4, F.v.y); stS(c, c.FbodyOut, 6*bodyIndex+5, F.v.z);
+                stS(c, inst, c.FbodyOut, 6*bodyIndex+0, F.w.x); stS(c, inst, c.FbodyOut, 6*bodyIndex+1, F.w.y); stS(c, inst, c.FbodyOut, 6*bodyIndex+2, F.w.z);
+                stS(c, inst, c.FbodyOut, 6*bodyIndex+3, F.v.x); stS(c, inst, c.FbodyOut, 6*bodyIndex+4, F.v.y); stS(c, inst, c.FbodyOut, 6*bodyIndex+5, F.v.z);
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < d; ++j) f[j] = c.fmobIn ? ldS(c, c.fmobIn, bc.u0 + j) : 0.0;
+            for (int j = 0; j < d; ++j) f[j] = c.fmobIn ? ldS(c, inst, c.fmobIn, bc.u0 + j) : 0.0;
             if (c.FbodyIn) {
-                F.w = mk(ldS(c, c.FbodyIn, 6*bodyIndex+0), ldS(c, c.FbodyIn, 6*bodyIndex+1), ldS(c, c.FbodyIn, 6*bodyIndex+2));
-                F.v = mk(ldS(c, c.FbodyIn, 6*bodyIndex+3), ldS(c, c.FbodyIn, 6*bodyIndex+4), ldS(c, c.FbodyIn, 6*bodyIndex+5));
+                F.w = mk(ldS(c, inst, c.FbodyIn, 6*bodyIndex+0), ldS(c, inst, c.FbodyIn, 6*bodyIndex+1), ldS(c, inst, c.FbodyIn, 6*bodyIndex+2));
+                F.v = mk(ldS(c, inst, c.FbodyIn, 6*bodyIndex+3), ldS(c, inst, c.FbodyIn, 6*bodyIndex+4), ldS(c, inst, c.FbodyIn, 6*bodyIndex+5));
             }
         }
         // ---- calcUDotPass1Inward (RigidBodyNodeSpec.cpp:355-400) / M^-1 pass 1 (:483-515) ------
         SV z;
         if constexpr ((MODE & IN_BIAS) != 0) z = ao.zb - F; else z = zeroSV();
         for (int k = 0; k < bc.nchild; ++k) {
-            const int ci = c.children[bc.childStart + k];
-            if (LEAN && ci == cy.inBody) z = z + phi(cy.l, cy.zP);
-            else { const CacheRef ch = cacheOf(c, c.bodies[ci].cacheBase); z = z + phi(ch.ld3(F_L), ch.ldSV(F_ZPLUS)); }
+            if (k == 0 && haveCarryChild) { z = z + phi(cl, czP); continue; }
+            const CacheRef ch = cacheOf(c, inst, c.bodies[c.children[bc.childStart + k]].cacheBase);
+            z = z + phi(ch.ld3(F_L), ch.ldSV(F_ZPLUS));
         }
         double eps[d];
         zCore<d>(H, ao.G, z, f, eps, zPlus);
@@ -518,17 +584,18 @@ SBK_HDN void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, 
         for (int j = 0; j < d; ++j) me.st(fEPS(d) + j, eps[j]);
         if (linkToCache) me.stSV(F_ZPLUS, zPlus);
     }
-    if (LEAN) { cy.PP = ao.PP; cy.zP = zPlus; cy.l = me.ld3(F_L); cy.inBody = bodyIndex; }
+    if (LEAN) cyStoreIn(cy, ao.PP, zPlus, lMe);
 }
 
 // Sweep E for one body (base->tip): udot, A_GB, qdotdot.
 template <int JT, bool WITH_COR, bool LEAN>
-SBK_HDN void outwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, Carry& cy, double* udotDst, double* qdotdotDst) {
+SBK_BODY void outwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, const int inst, double* cy,
+                         double* udotDst, double* qdotdotDst) {
     constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
-    const CacheRef me = cacheOf(c, bc.cacheBase);
+    const CacheRef me = cacheOf(c, inst, bc.cacheBase);
     SV A_GP;
-    if (LEAN && (bc.flags & BF_PARENT_PREV) && cy.outBody == bc.parent) A_GP = cy.A;
-    else A_GP = cacheOf(c, bc.parentCacheBase).ldSV(F_AGB);
+    if (LEAN && (bc.flags & BF_PARENT_PREV)) A_GP = cyLoadA(cy);
+    else A_GP = cacheOf(c, inst, bc.parentCacheBase).ldSV(F_AGB);
     SV H[d], G[d]; double DI[d*d], eps[d], udot[d];
 #pragma unroll
     for (int j = 0; j < d; ++j) { H[j] = me.ldSV(F_H + 6*j); G[j] = me.ldSV(fG(d) + 6*j); eps[j] = me.ld(fEPS(d) + j); }
@@ -539,22 +606,22 @@ SBK_HDN void outwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex,
     SV A;
     accCore<d, WITH_COR>(H, G, DI, eps, me.ld3(F_L), A_GP, acor, udot, A);
     if (!LEAN || (bc.flags & BF_STORE_LINK)) me.stSV(F_AGB, A);
-    cy.A = A; cy.outBody = bodyIndex;
+    if (LEAN) cyStoreA(cy, A);
     if (udotDst) {
 #pragma unroll
-        for (int i = 0; i < d; ++i) stS(c, udotDst, bc.u0 + i, udot[i]);
+        for (int i = 0; i < d; ++i) stS(c, inst, udotDst, bc.u0 + i, udot[i]);
     }
     if (qdotdotDst) {
         double q[NQ], u[d], qdd[NQ];
         if constexpr (JT == JT_BALL || JT == JT_FREE) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) q[i] = ldS(c, c.q, bc.q0 + i);
+            for (int i = 0; i < 4; ++i) q[i] = ldS(c, inst, c.q, bc.q0 + i);
 #pragma unroll
-            for (int i = 0; i < 3; ++i) u[i] = ldS(c, c.u, bc.u0 + i);
+            for (int i = 0; i < 3; ++i) u[i] = ldS(c, inst, c.u, bc.u0 + i);
         }
         qddCore<JT>(q, u, udot, qdd);
 #pragma unroll
-        for (int i = 0; i < NQ; ++i) stS(c, qdotdotDst, bc.q0 + i, qdd[i]);
+        for (int i = 0; i < NQ; ++i) stS(c, inst, qdotdotDst, bc.q0 + i, qdd[i]);
     }
 }
 
@@ -562,14 +629,14 @@ SBK_HDN void outwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex,
 //   WITH_VEL: residual form (adds coriolis a, gyroscopic b, applied forces).
 // The outward pass stores A in AGB; the inward pass stores F in ZPLUS.
 template <int JT, bool WITH_VEL>
-SBK_HDN void idOutBody(const Ctx& c, const BodyConst& bc) {
+SBK_BODY void idOutBody(const Ctx& c, const BodyConst& bc, const int inst) {
     constexpr int d = JointDims<JT>::nu;
-    const CacheRef me = cacheOf(c, bc.cacheBase), pa = cacheOf(c, bc.parentCacheBase);
+    const CacheRef me = cacheOf(c, inst, bc.cacheBase), pa = cacheOf(c, inst, bc.parentCacheBase);
     SV A = phiT(me.ld3(F_L), pa.ldSV(F_AGB));
     SV Hu = zeroSV();
 #pragma unroll
     for (int j = 0; j < d; ++j) {
-        const double v = c.vecIn ? ldS(c, c.vecIn, bc.u0 + j) : 0.0;
+        const double v = c.vecIn ? ldS(c, inst, c.vecIn, bc.u0 + j) : 0.0;
         Hu = Hu + v*me.ldSV(F_H + 6*j);
     }
     A = A + Hu;
@@ -577,23 +644,23 @@ SBK_HDN void idOutBody(const Ctx& c, const BodyConst& bc) {
     me.stSV(F_AGB, A);
 }
 template <int JT, bool WITH_VEL>
-SBK_HDN void idInBody(const Ctx& c, const BodyConst& bc, const int bodyIndex) {
+SBK_BODY void idInBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, const int inst) {
     constexpr int d = JointDims<JT>::nu;
-    const CacheRef me = cacheOf(c, bc.cacheBase);
+    const CacheRef me = cacheOf(c, inst, bc.cacheBase);
     const V3 c_G = me.ld3(F_MK); const S3 G_G = me.ldS3(F_MK + 3);
     SV F = mulSpatialInertia(bc.mass, c_G, G_G, me.ldSV(F_AGB));
     if constexpr (WITH_VEL) {
         F = F + me.ldSV(F_GYRO);
         if (c.FbodyIn) {
             SV Fa;
-            Fa.w = mk(ldS(c, c.FbodyIn, 6*bodyIndex+0), ldS(c, c.FbodyIn, 6*bodyIndex+1), ldS(c, c.FbodyIn, 6*bodyIndex+2));
-            Fa.v = mk(ldS(c, c.FbodyIn, 6*bodyIndex+3), ldS(c, c.FbodyIn, 6*bodyIndex+4), ldS(c, c.FbodyIn, 6*bodyIndex+5));
+            Fa.w = mk(ldS(c, inst, c.FbodyIn, 6*bodyIndex+0), ldS(c, inst, c.FbodyIn, 6*bodyIndex+1), ldS(c, inst, c.FbodyIn, 6*bodyIndex+2));
+            Fa.v = mk(ldS(c, inst, c.FbodyIn, 6*bodyIndex+3), ldS(c, inst, c.FbodyIn, 6*bodyIndex+4), ldS(c, inst, c.FbodyIn, 6*bodyIndex+5));
             F = F - Fa;
         }
     }
     for (int k = 0; k < bc.nchild; ++k) {
         const BodyConst& cb = c.bodies[c.children[bc.childStart + k]];
-        const CacheRef ch = cacheOf(c, cb.cacheBase);
+        const CacheRef ch = cacheOf(c, inst, cb.cacheBase);
         F = F + phi(ch.ld3(F_L), ch.ldSV(F_ZPLUS));
     }
     me.stSV(F_ZPLUS, F);
@@ -601,8 +668,8 @@ SBK_HDN void idInBody(const Ctx& c, const BodyConst& bc, const int bodyIndex) {
     for (int j = 0; j < d; ++j) {
         const SV Hj = me.ldSV(F_H + 6*j);
         double tau = dot(Hj.w, F.w) + dot(Hj.v, F.v);
-        if constexpr (WITH_VEL) { if (c.fmobIn) tau -= ldS(c, c.fmobIn, bc.u0 + j); }
-        stS(c, c.vecOut, bc.u0 + j, tau);
+        if constexpr (WITH_VEL) { if (c.fmobIn) tau -= ldS(c, inst, c.fmobIn, bc.u0 + j); }
+        stS(c, inst, c.vecOut, bc.u0 + j, tau);
     }
 }
 
@@ -620,49 +687,47 @@ SBK_HDN void idInBody(const Ctx& c, const BodyConst& bc, const int bodyIndex) {
         default: break;                                                             \
     }
 
-template <bool LEAN> SBK_HD void kinDispatch(const Ctx& c, int b, Carry& cy) {
+template <bool LEAN> SBK_HD void kinDispatch(const Ctx& c, int b, int inst, double* cy, double* qdotDst) {
     const BodyConst& bc = c.bodies[b];
-    SBK_DISPATCH_JOINT(bc.joint, (kinBody<JT, LEAN>(c, bc, b, cy)));
+    SBK_DISPATCH_JOINT(bc.joint, (kinBody<JT, LEAN>(c, bc, b, inst, cy, qdotDst)));
 }
-template <int MODE, bool LEAN> SBK_HD void inwardDispatch(const Ctx& c, int b, Carry& cy) {
+template <int MODE, bool LEAN> SBK_HD void inwardDispatch(const Ctx& c, int b, int inst, double* cy) {
     const BodyConst& bc = c.bodies[b];
-    SBK_DISPATCH_JOINT(bc.joint, (inwardBody<JT, MODE, LEAN>(c, bc, b, cy)));
+    SBK_DISPATCH_JOINT(bc.joint, (inwardBody<JT, MODE, LEAN>(c, bc, b, inst, cy)));
 }
-template <bool WITH_COR, bool LEAN> SBK_HD void outwardDispatch(const Ctx& c, int b, Carry& cy, double* udotDst, double* qddDst) {
+template <bool WITH_COR, bool LEAN> SBK_HD void outwardDispatch(const Ctx& c, int b, int inst, double* cy, double* udotDst, double* qddDst) {
     const BodyConst& bc = c.bodies[b];
-    SBK_DISPATCH_JOINT(bc.joint, (outwardBody<JT, WITH_COR, LEAN>(c, bc, b, cy, udotDst, qddDst)));
+    SBK_DISPATCH_JOINT(bc.joint, (outwardBody<JT, WITH_COR, LEAN>(c, bc, b, inst, cy, udotDst, qddDst)));
 }
-template <bool WITH_VEL> SBK_HD void idOutDispatch(const Ctx& c, int b) {
+template <bool WITH_VEL> SBK_HD void idOutDispatch(const Ctx& c, int b, int inst) {
     const BodyConst& bc = c.bodies[b];
-    SBK_DISPATCH_JOINT(bc.joint, (idOutBody<JT, WITH_VEL>(c, bc)));
+    SBK_DISPATCH_JOINT(bc.joint, (idOutBody<JT, WITH_VEL>(c, bc, inst)));
 }
-template <bool WITH_VEL> SBK_HD void idInDispatch(const Ctx& c, int b) {
+template <bool WITH_VEL> SBK_HD void idInDispatch(const Ctx& c, int b, int inst) {
     const BodyConst& bc = c.bodies[b];
-    SBK_DISPATCH_JOINT(bc.joint, (idInBody<JT, WITH_VEL>(c, bc, b)));
+    SBK_DISPATCH_JOINT(bc.joint, (idInBody<JT, WITH_VEL>(c, bc, b, inst)));
 }
 
 //==============================================================================================
 // Per-instance drivers for the thread-per-instance plan: body index order is a valid
 // base->tip order because a parent's MobilizedBodyIndex is always smaller than its child's.
 //==============================================================================================
-SBK_HD void resetCarry(Carry& cy) { cy.outBody = -1; cy.inBody = -1; }
-template <bool LEAN> SBK_HD void tpiKinematics(const Ctx& c, Carry& cy) {
-    cy.outBody = -1;
-    for (int b = 1; b < c.nb; ++b) kinDispatch<LEAN>(c, b, cy);
+template <bool LEAN> SBK_HD void tpiKinematics(const Ctx& c, int inst, double* cy, double* qdotDst) {
+    if (LEAN) { SV z0 = zeroSV(); cyStoreOut(cy, identity3(), zero3(), z0); }      // Ground's link for body 1
+    for (int b = 1; b < c.nb; ++b) kinDispatch<LEAN>(c, b, inst, cy, qdotDst);
 }
-template <int MODE, bool LEAN> SBK_HD void tpiInward(const Ctx& c, Carry& cy) {
-    cy.inBody = -1;
-    for (int b = c.nb - 1; b >= 1; --b) inwardDispatch<MODE, LEAN>(c, b, cy);
+template <int MODE, bool LEAN> SBK_HD void tpiInward(const Ctx& c, int inst, double* cy) {
+    for (int b = c.nb - 1; b >= 1; --b) inwardDispatch<MODE, LEAN>(c, b, inst, cy);
 }
-template <bool WITH_COR, bool LEAN> SBK_HD void tpiOutward(const Ctx& c, Carry& cy, double* udotDst, double* qddDst) {
-    cy.outBody = -1;
-    for (int b = 1; b < c.nb; ++b) outwardDispatch<WITH_COR, LEAN>(c, b, cy, udotDst, qddDst);
+template <bool WITH_COR, bool LEAN> SBK_HD void tpiOutward(const Ctx& c, int inst, double* cy, double* udotDst, double* qddDst) {
+    if (LEAN) cyStoreA(cy, zeroSV());                                               // Ground's A_GB
+    for (int b = 1; b < c.nb; ++b) outwardDispatch<WITH_COR, LEAN>(c, b, inst, cy, udotDst, qddDst);
 }
 // One full derivative evaluation = System::realize(Acceleration) for the lowered system.
-template <bool LEAN> SBK_HD void tpiEvalDerivatives(const Ctx& c, Carry& cy) {
-    tpiKinematics<LEAN>(c, cy);
-    tpiInward<IN_ABI | IN_Z | IN_BIAS | IN_FORCES, LEAN>(c, cy);
-    tpiOutward<true, LEAN>(c, cy, c.udot, c.qdotdot);
+template <bool LEAN> SBK_EVAL void tpiEvalDerivatives(const Ctx& c, int inst, double* cy, double* qdotDst, double* udotDst, double* qddDst) {
+    tpiKinematics<LEAN>(c, inst, cy, qdotDst);
+    tpiInward<IN_ABI | IN_Z | IN_BIAS | IN_FORCES, LEAN>(c, inst, cy);
+    tpiOutward<true, LEAN>(c, inst, cy, udotDst, qddDst);
 }
 
 } // namespace sbkd

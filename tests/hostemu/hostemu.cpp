@@ -50,12 +50,12 @@ Ctx makeCtx(Emu& e, int inst) {
     c.bodies = e.bodies.data(); c.children = t.children.data(); c.forces = t.forces.data();
     c.nb = t.nb; c.nq = t.nq; c.nu = t.nu; c.nquat = t.nquat;
     c.gx = t.grav[0]; c.gy = t.grav[1]; c.gz = t.grav[2];
-    c.cache = e.cache.data(); c.cStride = N; c.cOff = inst;
-    c.sStride = N; c.sOff = inst;
+    c.cache = e.cache.data(); c.cStride = N; c.cInstStride = 1;
+    c.sStride = N; c.sInstStride = 1;
     c.q = e.y.data(); c.u = e.y.data() + (size_t)t.nq*N;
     c.qdot = e.ydot.data(); c.udot = e.ydot.data() + (size_t)t.nq*N;
     c.qdotdot = e.qdd.data(); c.qerr = e.qerr.data();
-    c.status = &e.status[inst];
+    c.status = e.status.data();
     return c;
 }
 } // namespace
@@ -81,9 +81,9 @@ int emu_eval(const char* text, int N, const double* in, double* out) {
         for (int k = 0; k < N; ++k) {
             const double* p = in + (size_t)k*inStride; double* o = out + (size_t)k*outStride;
             Ctx c = makeCtx(e, k);
-            Carry cy; resetCarry(cy);
+            double cy[CARRY_ROWS];
             c.fmobOut = e.fmob.data(); c.FbodyOut = e.Fbody.data();
-            tpiEvalDerivatives<false>(c, cy);
+            tpiEvalDerivatives<false>(c, k, cy, c.qdot, c.udot, c.qdotdot);
             for (int i = 0; i < nq; ++i) *o++ = e.ydot[(size_t)i*N + k];
             for (int i = 0; i < nu; ++i) *o++ = e.ydot[(size_t)(nq+i)*N + k];
             for (int i = 0; i < nq; ++i) *o++ = e.qdd[(size_t)i*N + k];
@@ -101,31 +101,31 @@ int emu_eval(const char* text, int N, const double* in, double* out) {
             // M*a
             for (int i = 0; i < nu; ++i) e.vin[(size_t)i*N + k] = pa[i];
             c.vecIn = e.vin.data();
-            for (int b = 1; b < nb; ++b) idOutDispatch<false>(c, b);
-            for (int b = nb-1; b >= 1; --b) idInDispatch<false>(c, b);
+            for (int b = 1; b < nb; ++b) idOutDispatch<false>(c, b, k);
+            for (int b = nb-1; b >= 1; --b) idInDispatch<false>(c, b, k);
             for (int i = 0; i < nu; ++i) *o++ = e.vout[(size_t)i*N + k];
             // M^-1 v
             for (int i = 0; i < nu; ++i) e.vin[(size_t)i*N + k] = pv[i];
             c.fmobIn = e.vin.data(); c.FbodyIn = nullptr;
-            tpiInward<IN_Z, false>(c, cy);
-            tpiOutward<false, false>(c, cy, e.vout.data(), nullptr);
+            tpiInward<IN_Z, false>(c, k, cy);
+            tpiOutward<false, false>(c, k, cy, e.vout.data(), nullptr);
             for (int i = 0; i < nu; ++i) *o++ = e.vout[(size_t)i*N + k];
             // residual(f, F, udot)
             for (int i = 0; i < nu; ++i) { e.vin[(size_t)i*N + k] = pud[i]; e.vin2[(size_t)i*N + k] = pf[i]; }
             for (int i = 0; i < nb*6; ++i) e.Fin[(size_t)i*N + k] = pF[i];
             c.vecIn = e.vin.data(); c.fmobIn = e.vin2.data(); c.FbodyIn = e.Fin.data();
-            for (int b = 1; b < nb; ++b) idOutDispatch<true>(c, b);
-            for (int b = nb-1; b >= 1; --b) idInDispatch<true>(c, b);
+            for (int b = 1; b < nb; ++b) idOutDispatch<true>(c, b, k);
+            for (int b = nb-1; b >= 1; --b) idInDispatch<true>(c, b, k);
             for (int i = 0; i < nu; ++i) *o++ = e.vout[(size_t)i*N + k];
             // residual with all-zero arguments
             c.vecIn = nullptr; c.fmobIn = nullptr; c.FbodyIn = nullptr;
-            for (int b = 1; b < nb; ++b) idOutDispatch<true>(c, b);
-            for (int b = nb-1; b >= 1; --b) idInDispatch<true>(c, b);
+            for (int b = 1; b < nb; ++b) idOutDispatch<true>(c, b, k);
+            for (int b = nb-1; b >= 1; --b) idInDispatch<true>(c, b, k);
             for (int i = 0; i < nu; ++i) *o++ = e.vout[(size_t)i*N + k];
             // calcAcceleration(f, F)
             c.fmobIn = e.vin2.data(); c.FbodyIn = e.Fin.data();
-            tpiInward<IN_Z | IN_BIAS, false>(c, cy);
-            tpiOutward<true, false>(c, cy, e.vout.data(), nullptr);
+            tpiInward<IN_Z | IN_BIAS, false>(c, k, cy);
+            tpiOutward<true, false>(c, k, cy, e.vout.data(), nullptr);
             for (int i = 0; i < nu; ++i) *o++ = e.vout[(size_t)i*N + k];
             for (int b = 0; b < nb; ++b) for (int i = 0; i < 6; ++i) *o++ = rec(b, F_AGB + i);
             if (o - (out + (size_t)k*outStride) != outStride) return 3;
@@ -166,10 +166,11 @@ int emu_step(const char* text, int N, const double* in, double* out, double h, i
         }
         for (int k = 0; k < N; ++k) {
             Ctx c = makeCtx(e, k);
-            Carry cy; resetCarry(cy);
+            c.qdotdot = nullptr; c.qerr = nullptr;
+            double cy[CARRY_ROWS];
             RkmStepResult r; r.errNorm = 0; r.projected = 0; int nproj = 0;
             for (int s = 0; s < nsteps; ++s) {
-                r = lean ? tpiRkmStep<true>(c, w, h, cy) : tpiRkmStep<false>(c, w, h, cy);
+                r = lean ? tpiRkmStep<true>(c, k, w, h, cy) : tpiRkmStep<false>(c, k, w, h, cy);
                 nproj += r.projected;
             }
             double* o = out + (size_t)k*(ny+2);
