@@ -204,13 +204,17 @@ def main():
         if world > 1:
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         ms_max, e2e_ms_max = float(tmax[0]), float(tmax[1])
+        # end-of-run statistics: the only collectives of the job (NCCL): max error norm, bad-instance count
+        from simbody_b200.sharding import reduce_stats
+        errn = bm.stepBy(wl["h"], 0, want_err_norm=True)
+        max_err, nbad, _ = reduce_stats(float(np.nanmax(errn)), int(nbad), ms, dist if world > 1 else None, device="cuda")
         flop, byts = algorithmic_work(info)
         plan = bm.getPlan()
         res = {"name": name, "info": info, "N": N, "spl": spl, "ms_per_step": ms_max / steps, "plan": plan,
                "value": world * N * spl * steps / (ms_max * 1e-3),
                "e2e": world * N * spl * e2e_steps / (e2e_ms_max * 1e-3),
                "h2d": 8 * ny * N, "d2h": 8 * ny * N, "launches": launches, "kernel_ms_last": kern_ms[-1],
-               "flop_per_inst_step": flop, "bytes_per_inst_step": byts, "clocks": clocks_summary(samples), "nbad": int(nbad)}
+               "flop_per_inst_step": flop, "bytes_per_inst_step": byts, "clocks": clocks_summary(samples), "nbad": int(nbad), "max_err_norm": max_err}
         bm.close(); topo.close()
         return res
 
@@ -248,7 +252,7 @@ def main():
                        "rkm_steps_per_bench_step": r["spl"], "integrator": "RungeKuttaMerson fixed step, 5 evals/step",
                        "l2": "state+cache working set exceeds L2 for every workload but branched_tree; no flush needed"},
             "e2e": {"value": r["e2e"], "unit": "instance-steps/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
-            "gpu_launches": r["launches"], "clocks": r["clocks"], "roofline": roofline, "non_finite_instances": r["nbad"]}
+            "gpu_launches": r["launches"], "clocks": r["clocks"], "roofline": roofline, "non_finite_instances": r["nbad"], "max_err_norm_last_step": r["max_err_norm"]}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from _harness import RefDriver, have_ref
