@@ -101,6 +101,23 @@ typedef struct sbk_rkm_opts {
     int32_t project_every_step;   /* 0 default; 1 = always normalise quaternions          */
 } sbk_rkm_opts;
 
+/* Error-controlled stepping; mirrors Integrator::setAccuracy / setInitialStepSize /
+ * setMinimumStepSize / setMaximumStepSize / setAllowInterpolation
+ * (SimTKmath/Integrators/include/simmath/Integrator.h:352-394).  Values <= 0 mean "default":
+ * accuracy 1e-3, constraint_tol accuracy/10, init_step timescale/10 = 0.01
+ * (AbstractIntegratorRep.cpp:40-53), no min/max step.                                       */
+typedef struct sbk_adaptive_opts {
+    double  accuracy, constraint_tol, init_step, min_step, max_step;
+    int32_t use_infinity_norm, project_every_step;
+    int32_t allow_interpolation;   /* 0 (default) = TimeStepper::stepTo semantics (README example):
+                                      t_final bounds the internal steps, the last one lands on it
+                                      (hWasArtificiallyLimited logic, AbstractIntegratorRep.cpp:533-541);
+                                      1 = bare Integrator::stepTo(reportTime) with interpolation
+                                      allowed: steps are never shortened, the advanced state ends at
+                                      t >= t_final (the reference then reports an interpolated state) */
+    int32_t max_attempts;          /* safety cap on step attempts per instance per call (0 = 1e6) */
+} sbk_adaptive_opts;
+
 typedef struct sbk_topology sbk_topology;
 typedef struct sbk_batch    sbk_batch;
 
@@ -203,6 +220,14 @@ void sbk_rkm_default_opts(sbk_rkm_opts*);
  * err_norm (host, [N], nullable) receives the error norm of the LAST step
  * (IntegratorRep.h:454-488).                                                            */
 int sbk_rkm_step(sbk_batch*, double h, int nsteps, const sbk_rkm_opts* opts, double* err_norm);
+/* RungeKuttaMersonIntegrator with error control: Integrator::stepTo(t_final) for every instance,
+ * each with its own step size history (AbstractIntegratorRep.cpp:216-368 stepping loop,
+ * :448-502 adjustStepSize, :513-578 takeOneStep).  Per-instance outputs (host, [N], nullable):
+ * internal steps taken and attempted since the state was last set, and the last accepted step
+ * size.  sbk_get_state's t returns each instance's advanced time.  Not available in plan 3.   */
+void sbk_adaptive_default_opts(sbk_adaptive_opts*);
+int sbk_rkm_adaptive(sbk_batch*, double t_final, const sbk_adaptive_opts* opts,
+                     int32_t* steps_taken, int32_t* steps_attempted, double* last_step);
 /* Integrator::getNumStepsTaken / getNumRealizations / getNumQProjections
  * (Integrator.h:286-290): totals over the batch since creation.                         */
 int sbk_rkm_stats(sbk_batch*, int64_t* steps_taken, int64_t* realizations, int64_t* q_projections);

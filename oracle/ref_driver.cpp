@@ -193,24 +193,26 @@ static int cmdStep(RefSystem& rs, const char* inPath, const char* outPath, int N
 }
 
 // ---- adaptive (config C1) -------------------------------------------------------------------
-static int cmdAdaptive(RefSystem& rs, const char* inPath, const char* outPath, int N, double tFinal, double accuracy) {
+static int cmdAdaptive(RefSystem& rs, const char* inPath, const char* outPath, int N, double tFinal, double accuracy, bool allowInterpolation) {
     const int nq=rs.nq, nu=rs.nu, ny=nq+nu;
     std::vector<double> in = readDoubles(inPath);
-    std::vector<double> out((size_t)N*(ny+4));
+    // out per instance: advanced q, u | steps taken | steps attempted | realizations | last step | advanced time
+    std::vector<double> out((size_t)N*(ny+5));
     for (int k = 0; k < N; ++k) {
         State s = rs.defaultState;
         setQU(s, &in[(size_t)k*ny], nq, &in[(size_t)k*ny+nq], nu);
         RungeKuttaMersonIntegrator integ(rs.system);
         if (accuracy > 0) integ.setAccuracy(accuracy);
+        if (!allowInterpolation) integ.setAllowInterpolation(false);
         TimeStepper ts(rs.system, integ);
         ts.initialize(s);
         ts.stepTo(tFinal);
         const State& a = integ.getAdvancedState();
-        double* o = &out[(size_t)k*(ny+4)];
+        double* o = &out[(size_t)k*(ny+5)];
         for (int i = 0; i < nq; ++i) *o++ = a.getQ()[i];
         for (int i = 0; i < nu; ++i) *o++ = a.getU()[i];
         *o++ = integ.getNumStepsTaken(); *o++ = integ.getNumStepsAttempted();
-        *o++ = integ.getNumRealizations(); *o++ = integ.getPreviousStepSizeTaken();
+        *o++ = integ.getNumRealizations(); *o++ = integ.getPreviousStepSizeTaken(); *o++ = integ.getAdvancedTime();
     }
     writeDoubles(outPath, out);
     return 0;
@@ -262,7 +264,7 @@ int main(int argc, char** argv) {
                 "usage: ref_driver lower|slots <model.txt>\n"
                 "       ref_driver eval <model.txt> <in.bin> <out.bin> <N>\n"
                 "       ref_driver step <model.txt> <in.bin> <out.bin> <N> <h> <nsteps> [accuracy]\n"
-                "       ref_driver adaptive <model.txt> <in.bin> <out.bin> <N> <tFinal> [accuracy]\n"
+                "       ref_driver adaptive <model.txt> <in.bin> <out.bin> <N> <tFinal> [accuracy] [allowInterpolation]\n"
                 "       ref_driver bench <model.txt> <in.bin> <N> <h> <nsteps> <threads> [out.bin]\n");
             return 2;
         }
@@ -295,7 +297,8 @@ int main(int argc, char** argv) {
             return cmdStep(rs, argv[3], argv[4], std::atoi(argv[5]), std::atof(argv[6]), std::atoi(argv[7]),
                            argc > 8 ? std::atof(argv[8]) : -1);
         if (cmd == "adaptive" && argc >= 7)
-            return cmdAdaptive(rs, argv[3], argv[4], std::atoi(argv[5]), std::atof(argv[6]), argc > 7 ? std::atof(argv[7]) : -1);
+            return cmdAdaptive(rs, argv[3], argv[4], std::atoi(argv[5]), std::atof(argv[6]), argc > 7 ? std::atof(argv[7]) : -1,
+                               argc > 8 ? std::atoi(argv[8]) != 0 : true);
         std::fprintf(stderr, "ref_driver: bad command line\n");
         return 2;
     } catch (const std::exception& e) {

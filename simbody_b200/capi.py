@@ -32,6 +32,12 @@ class RkmOpts(ctypes.Structure):
                 ("use_infinity_norm", ctypes.c_int32), ("project_every_step", ctypes.c_int32)]
 
 
+class AdaptiveOpts(ctypes.Structure):
+    _fields_ = [("accuracy", ctypes.c_double), ("constraint_tol", ctypes.c_double), ("init_step", ctypes.c_double),
+                ("min_step", ctypes.c_double), ("max_step", ctypes.c_double), ("use_infinity_norm", ctypes.c_int32),
+                ("project_every_step", ctypes.c_int32), ("allow_interpolation", ctypes.c_int32), ("max_attempts", ctypes.c_int32)]
+
+
 # every symbol include/sbk.h declares: name -> (restype, argtypes)
 _P = ctypes.c_void_p
 SYMBOLS = {
@@ -74,6 +80,9 @@ SYMBOLS = {
     "sbk_calc_residual_force": (ctypes.c_int, [_P, c_double_p, c_double_p, c_double_p, c_double_p]),
     "sbk_rkm_default_opts": (None, [ctypes.POINTER(RkmOpts)]),
     "sbk_rkm_step": (ctypes.c_int, [_P, ctypes.c_double, ctypes.c_int, ctypes.POINTER(RkmOpts), c_double_p]),
+    "sbk_adaptive_default_opts": (None, [ctypes.POINTER(AdaptiveOpts)]),
+    "sbk_rkm_adaptive": (ctypes.c_int, [_P, ctypes.c_double, ctypes.POINTER(AdaptiveOpts), ctypes.POINTER(ctypes.c_int32),
+                                        ctypes.POINTER(ctypes.c_int32), c_double_p]),
     "sbk_rkm_stats": (ctypes.c_int, [_P, c_int64_p, c_int64_p, c_int64_p]),
     "sbk_get_status": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int32), c_int64_p]),
     "sbk_launch_count": (ctypes.c_int64, [_P]),

@@ -37,6 +37,7 @@ struct sbk_batch {
     size_t scratchDoubles = 0;
     int stage = ST_EMPTY; bool abiValid = false, accelValid = false;
     int64_t launches = 0, stepsTaken = 0, realizations = 0;
+    bool adaptiveInit = false;
     double lastKernelMs = 0;
     long long recTotal = 0;
 };
@@ -261,7 +262,8 @@ void sbk_batch_destroy(sbk_batch* b) {
     cudaSetDevice(b->device);
     KArgs& a = b->a;
     void* ptrs[] = {b->dTables, a.cache, a.y, a.ydot, a.qdotdot, a.qerr, a.y0, a.f0, a.fa, a.fb, a.ys, a.tcur, a.errNorm,
-                    b->dOpA, b->dOpB, b->dOpOut, b->dOpF, a.status, a.projCount, b->dScratch};
+                    b->dOpA, b->dOpB, b->dOpOut, b->dOpF, a.status, a.projCount, b->dScratch,
+                    a.hcur, a.lastStep, a.stepsTaken, a.attempts};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (b->ev0) cudaEventDestroy(b->ev0); if (b->ev1) cudaEventDestroy(b->ev1);
     if (b->ownStream && b->stream) cudaStreamDestroy(b->stream);
@@ -288,6 +290,7 @@ int sbk_synchronize(sbk_batch* b) {
 
 // ---- state ----------------------------------------------------------------------------------
 static void invalidate(sbk_batch* b) { b->stage = ST_EMPTY; b->abiValid = false; b->accelValid = false; }
+static void stateWasSet(sbk_batch* b) { invalidate(b); b->adaptiveInit = false; }
 
 int sbk_set_state(sbk_batch* b, const double* q, const double* u, const double* t) {
     if (!b) return fail(SBK_ERR_ARG, "null batch");
@@ -297,7 +300,7 @@ int sbk_set_state(sbk_batch* b, const double* q, const double* u, const double* 
     if (u) if (int rc = h2d(b, b->a.y + (size_t)T->nq*b->N, u, T->nu)) return rc;
     if (t) CUDA_TRY(cudaMemcpyAsync(b->a.tcur, t, (size_t)b->N*sizeof(double), cudaMemcpyHostToDevice, b->stream));
     CUDA_TRY(cudaStreamSynchronize(b->stream));   // the host buffers may be reused by the caller
-    invalidate(b);
+    stateWasSet(b);
     return SBK_OK;
 }
 int sbk_get_state(sbk_batch* b, double* q, double* u, double* t) {
@@ -324,7 +327,7 @@ int sbk_set_state_aos(sbk_batch* b, const double* q, const double* u) {
         CUDA_TRY(launchTranspose(b->dScratch, b->a.y + (size_t)T->nq*N, N, T->nu, b->stream)); b->launches++;
     }
     CUDA_TRY(cudaStreamSynchronize(b->stream));
-    invalidate(b);
+    stateWasSet(b);
     return SBK_OK;
 }
 int sbk_get_state_aos(sbk_batch* b, double* q, double* u) {
@@ -349,7 +352,7 @@ int sbk_state_device_ptrs(sbk_batch* b, double** q, double** u, double** t) {
     if (q) *q = b->a.y; if (u) *u = b->a.y + (size_t)b->topo->nq*b->N; if (t) *t = b->a.tcur;
     return SBK_OK;
 }
-int sbk_state_touched(sbk_batch* b) { if (!b) return fail(SBK_ERR_ARG, "null batch"); invalidate(b); return SBK_OK; }
+int sbk_state_touched(sbk_batch* b) { if (!b) return fail(SBK_ERR_ARG, "null batch"); stateWasSet(b); return SBK_OK; }
 
 // ---- realize ----------------------------------------------------------------------------------
 static int realizeKin(sbk_batch* b, int toStage) {
@@ -517,7 +520,7 @@ int sbk_rkm_step(sbk_batch* b, double h, int nsteps, const sbk_rkm_opts* opts, d
         if (b->plan == 2) {
             std::vector<int> joints(b->topo->nb);
             for (int i = 0; i < b->topo->nb; ++i) joints[i] = b->topo->bodies[i].joint;
-            CUDA_TRY(launchFusedRkm(a, joints.data(), b->stream)); b->launches++;
+            CUDA_TRY(launchFusedRkm(a, joints.data(), false, b->stream)); b->launches++;
         } else if (int rc = launch(b, OP_RKM)) return rc;
         CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
         invalidate(b);
@@ -527,6 +530,56 @@ int sbk_rkm_step(sbk_batch* b, double h, int nsteps, const sbk_rkm_opts* opts, d
         CUDA_TRY(cudaMemcpyAsync(errNorm, a.errNorm, (size_t)b->N*sizeof(double), cudaMemcpyDeviceToHost, b->stream));
         CUDA_TRY(cudaStreamSynchronize(b->stream));
     }
+    return SBK_OK;
+}
+void sbk_adaptive_default_opts(sbk_adaptive_opts* o) {
+    if (!o) return;
+    o->accuracy = 1e-3; o->constraint_tol = 1e-4; o->init_step = 0.01; o->min_step = -1; o->max_step = -1;
+    o->use_infinity_norm = 0; o->project_every_step = 0; o->allow_interpolation = 0; o->max_attempts = 0;
+}
+int sbk_rkm_adaptive(sbk_batch* b, double tFinal, const sbk_adaptive_opts* opts, int32_t* steps, int32_t* attempts, double* lastStep) {
+    if (!b) return fail(SBK_ERR_ARG, "null batch");
+    if (int rc = useDevice(b)) return rc;
+    if (b->plan == 3) return fail(SBK_ERR_ARG, "sbk_rkm_adaptive: not available in the level-parallel plan (use sbk_batch_set_plan(b, 1))");
+    sbk_adaptive_opts o; sbk_adaptive_default_opts(&o);
+    if (opts) {
+        o = *opts;
+        if (!(o.accuracy > 0)) o.accuracy = 1e-3;
+        if (!(o.constraint_tol > 0)) o.constraint_tol = o.accuracy/10;
+        if (!(o.init_step > 0)) o.init_step = 0.01;
+    }
+    KArgs& a = b->a; const size_t N = (size_t)b->N;
+    if (!a.hcur) {
+        CUDA_TRY(cudaMalloc(&a.hcur, N*sizeof(double))); CUDA_TRY(cudaMalloc(&a.lastStep, N*sizeof(double)));
+        CUDA_TRY(cudaMalloc(&a.stepsTaken, N*sizeof(int))); CUDA_TRY(cudaMalloc(&a.attempts, N*sizeof(int)));
+    }
+    if (!b->adaptiveInit) {       // Integrator::initialize: step size = initial step, counters cleared
+        double h0 = o.init_step;
+        if (o.min_step > 0) h0 = std::max(h0, o.min_step);
+        if (o.max_step > 0) h0 = std::min(h0, o.max_step);
+        std::vector<double> hv(N, h0);
+        CUDA_TRY(cudaMemcpyAsync(a.hcur, hv.data(), N*sizeof(double), cudaMemcpyHostToDevice, b->stream));
+        CUDA_TRY(cudaMemcpyAsync(a.lastStep, hv.data(), N*sizeof(double), cudaMemcpyHostToDevice, b->stream));
+        CUDA_TRY(cudaMemsetAsync(a.stepsTaken, 0, N*sizeof(int), b->stream));
+        CUDA_TRY(cudaMemsetAsync(a.attempts, 0, N*sizeof(int), b->stream));
+        CUDA_TRY(cudaStreamSynchronize(b->stream));
+        b->adaptiveInit = true;
+    }
+    a.tFinal = tFinal; a.accuracy = o.accuracy; a.consTol = o.constraint_tol; a.minStep = o.min_step; a.maxStep = o.max_step;
+    a.useInfNorm = o.use_infinity_norm; a.projectEveryStep = o.project_every_step; a.allowInterp = o.allow_interpolation;
+    a.maxAttempts = o.max_attempts > 0 ? o.max_attempts : 1000000;
+    CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
+    if (b->plan == 2) {
+        std::vector<int> joints(b->topo->nb);
+        for (int i = 0; i < b->topo->nb; ++i) joints[i] = b->topo->bodies[i].joint;
+        CUDA_TRY(launchFusedRkm(a, joints.data(), true, b->stream)); b->launches++;
+    } else if (int rc = launch(b, OP_RKM_ADAPT)) return rc;
+    CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
+    invalidate(b);
+    if (steps)    CUDA_TRY(cudaMemcpyAsync(steps, a.stepsTaken, N*sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    if (attempts) CUDA_TRY(cudaMemcpyAsync(attempts, a.attempts, N*sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    if (lastStep) CUDA_TRY(cudaMemcpyAsync(lastStep, a.lastStep, N*sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
     return SBK_OK;
 }
 int sbk_rkm_stats(sbk_batch* b, int64_t* steps, int64_t* realizations, int64_t* qproj) {

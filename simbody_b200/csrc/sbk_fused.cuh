@@ -63,15 +63,14 @@ struct Chain1 {
     }
 };
 
-// One RKM step entirely in registers (same arithmetic as tpiRkmStep; no quaternions here so the
-// q-part of the error norm is the plain RMS and there is no projection).
+// One RKM attempt entirely in registers from saved y0, f0 (same arithmetic as tpiRkmStep; no
+// quaternions here so the q-part of the error norm is the plain RMS and there is no projection).
 template <class E>
-SBK_HD double fusedRkmStep(const E& e, double* y, const double h, const int useInfNorm) {
+SBK_HD double fusedRkmAttempt(const E& e, const double* y0, const double* f0, double* y, const double h, const int useInfNorm) {
     constexpr int NY = E::NY, NQ = E::NQ, NU = E::NU;
-    double y0[NY], f0[NY], fa[NY], fb[NY], ys[NY];
-    e.eval(y, f0);
+    double fa[NY], fb[NY], ys[NY];
 #pragma unroll
-    for (int i = 0; i < NY; ++i) { y0[i] = y[i]; y[i] = y0[i] + (h/3)*f0[i]; }
+    for (int i = 0; i < NY; ++i) y[i] = y0[i] + (h/3)*f0[i];
     e.eval(y, fa);
 #pragma unroll
     for (int i = 0; i < NY; ++i) y[i] = y0[i] + (h/6)*(f0[i] + fa[i]);
@@ -99,6 +98,46 @@ SBK_HD double fusedRkmStep(const E& e, double* y, const double h, const int useI
     const double qNorm = useInfNorm ? qAcc : sqrt(qAcc/NQ);
     const double uNorm = useInfNorm ? uAcc : sqrt(uAcc/NU);
     return qNorm >= uNorm ? qNorm : uNorm;
+}
+// One fixed-size step: f0 = f(y), y0 = y, attempt.
+template <class E>
+SBK_HD double fusedRkmStep(const E& e, double* y, const double h, const int useInfNorm) {
+    constexpr int NY = E::NY;
+    double y0[NY], f0[NY];
+    e.eval(y, f0);
+#pragma unroll
+    for (int i = 0; i < NY; ++i) y0[i] = y[i];
+    return fusedRkmAttempt(e, y0, f0, y, h, useInfNorm);
+}
+// Error-controlled stepping to tFinal (cf. tpiRkmAdaptive).
+template <class E>
+SBK_HD void fusedRkmAdaptive(const E& e, double* y, const StepLimits& lim, const double tFinal, const int allowInterpolation,
+                             const int maxAttempts, const int useInfNorm, AdaptiveState& st, double& lastErr) {
+    constexpr int NY = E::NY;
+    int budget = maxAttempts;
+    while (st.t < tFinal && budget > 0) {
+        double y0[NY], f0[NY];
+        e.eval(y, f0);
+#pragma unroll
+        for (int i = 0; i < NY; ++i) y0[i] = y[i];
+        bool ok = false; double t1 = st.t;
+        do {
+            bool limited = false;
+            if (allowInterpolation) t1 = st.t + st.h;
+            else if (tFinal < st.t + 0.95*st.h)  { limited = true; t1 = tFinal; }
+            else if (tFinal > st.t + 1.001*st.h) t1 = st.t + st.h;
+            else t1 = tFinal;
+            lastErr = fusedRkmAttempt(e, y0, f0, y, t1 - st.t, useInfNorm);
+            ++st.attempts; --budget;
+            ok = adjustStepSize(lastErr, lim, limited, st.h);
+        } while (!ok && budget > 0);
+        if (!ok) {
+#pragma unroll
+            for (int i = 0; i < NY; ++i) y[i] = y0[i];
+            break;
+        }
+        st.lastStep = t1 - st.t; st.t = t1; ++st.steps;
+    }
 }
 
 } // namespace sbkd

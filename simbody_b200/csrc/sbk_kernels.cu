@@ -76,14 +76,14 @@ __global__ void __launch_bounds__(TPI_THREADS, MINB) tpiKernel(const KArgs a) {
     __shared__ Ctx sctx;                      // ONE context per CTA, read with LDS by every body step
     const unsigned char* tables = a.tables;
     if constexpr (STAGE) { tmaStage(smem, a.tables, a.tableBytes, &mbar); tables = smem; }
-    if (threadIdx.x == 0) fillCtx(sctx, a, tables, OP == OP_RKM);
+    if (threadIdx.x == 0) fillCtx(sctx, a, tables, OP == OP_RKM || OP == OP_RKM_ADAPT);
     __syncthreads();
     const int inst = blockIdx.x*blockDim.x + threadIdx.x;
     if (inst >= a.N) return;
     const Ctx& c = sctx;
     // LEAN carry: a [CARRY_ROWS][128] block of shared memory behind the staged tables
     double* cy = nullptr;
-    if constexpr (OP == OP_RKM) cy = reinterpret_cast<double*>(smem + (STAGE ? a.tableBytes : 0)) + threadIdx.x;
+    if constexpr (OP == OP_RKM || OP == OP_RKM_ADAPT) cy = reinterpret_cast<double*>(smem + (STAGE ? a.tableBytes : 0)) + threadIdx.x;
 
     if constexpr (OP == OP_KIN) {
         tpiKinematics<false>(c, inst, cy, c.qdot);
@@ -114,11 +114,23 @@ __global__ void __launch_bounds__(TPI_THREADS, MINB) tpiKernel(const KArgs a) {
         a.errNorm[inst] = r.errNorm;
         a.projCount[inst] += nproj;
         if (a.status && !(r.errNorm == r.errNorm)) atomicOr(a.status + inst, 1);   // NaN error norm
+    } else if constexpr (OP == OP_RKM_ADAPT) {
+        RkmWork w;
+        w.y = a.y; w.y0 = a.y0; w.f0 = a.f0; w.fa = a.fa; w.fb = a.fb; w.ys = a.ys;
+        w.accuracy = a.accuracy; w.consTol = a.consTol; w.useInfNorm = a.useInfNorm; w.projectEveryStep = a.projectEveryStep;
+        StepLimits lim; lim.accuracy = a.accuracy; lim.minStep = a.minStep; lim.maxStep = a.maxStep;
+        AdaptiveState st; st.t = a.tcur[inst]; st.h = a.hcur[inst]; st.lastStep = a.lastStep[inst]; st.steps = 0; st.attempts = 0;
+        double lastErr = a.errNorm[inst]; int nproj = 0;
+        tpiRkmAdaptive<true>(c, inst, w, lim, a.tFinal, a.allowInterp, a.maxAttempts, st, cy, lastErr, nproj);
+        a.tcur[inst] = st.t; a.hcur[inst] = st.h; a.lastStep[inst] = st.lastStep;
+        a.stepsTaken[inst] += st.steps; a.attempts[inst] += st.attempts;
+        a.errNorm[inst] = lastErr; a.projCount[inst] += nproj;
+        if (a.status && st.t < a.tFinal) atomicOr(a.status + inst, 4);              // attempt budget exhausted
     }
 }
 
 // Register-resident fused plan: the whole multi-step RKM loop of one instance in one thread.
-template <class E>
+template <class E, bool ADAPT>
 __global__ void __launch_bounds__(128) fusedRkmKernel(const KArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t mbar;
@@ -133,26 +145,39 @@ __global__ void __launch_bounds__(128) fusedRkmKernel(const KArgs a) {
 #pragma unroll
     for (int i = 0; i < E::NY; ++i) y[i] = a.y[(long long)i*a.N + inst];
     double err = 0;
-    for (int s = 0; s < a.nsteps; ++s) err = fusedRkmStep(e, y, a.h, a.useInfNorm);
+    if constexpr (ADAPT) {
+        StepLimits lim; lim.accuracy = a.accuracy; lim.minStep = a.minStep; lim.maxStep = a.maxStep;
+        AdaptiveState st; st.t = a.tcur[inst]; st.h = a.hcur[inst]; st.lastStep = a.lastStep[inst]; st.steps = 0; st.attempts = 0;
+        err = a.errNorm[inst];
+        fusedRkmAdaptive(e, y, lim, a.tFinal, a.allowInterp, a.maxAttempts, a.useInfNorm, st, err);
+        a.tcur[inst] = st.t; a.hcur[inst] = st.h; a.lastStep[inst] = st.lastStep;
+        a.stepsTaken[inst] += st.steps; a.attempts[inst] += st.attempts;
+        if (a.status && st.t < a.tFinal) a.status[inst] |= 4;
+    } else {
+        for (int s = 0; s < a.nsteps; ++s) err = fusedRkmStep(e, y, a.h, a.useInfNorm);
+        a.tcur[inst] += a.nsteps*a.h;
+    }
 #pragma unroll
     for (int i = 0; i < E::NY; ++i) a.y[(long long)i*a.N + inst] = y[i];
-    a.tcur[inst] += a.nsteps*a.h;
     a.errNorm[inst] = err;
     if (a.status && !(err == err)) a.status[inst] |= 1;
 }
 template <class E>
-cudaError_t launchFusedT(const KArgs& a, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(fusedRkmKernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.tableBytes);
-    if (e != cudaSuccess) return e;
-    fusedRkmKernel<E><<<(a.N + 127)/128, 128, a.tableBytes, stream>>>(a);
-    return cudaGetLastError();
+cudaError_t launchFusedT(const KArgs& a, bool adaptive, cudaStream_t stream) {
+    auto go = [&](auto kernel) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.tableBytes);
+        if (e != cudaSuccess) return e;
+        kernel<<<(a.N + 127)/128, 128, a.tableBytes, stream>>>(a);
+        return cudaGetLastError();
+    };
+    return adaptive ? go(fusedRkmKernel<E, true>) : go(fusedRkmKernel<E, false>);
 }
 
 template <int OP>
 cudaError_t launchOp(const KArgs& a, cudaStream_t stream) {
     static_assert(TPI_THREADS == SBK_CARRY_STRIDE_DEVICE, "carry columns are laid out for 128-thread CTAs");
     const int grid = (a.N + TPI_THREADS - 1)/TPI_THREADS;
-    const size_t carryBytes = (OP == OP_RKM) ? (size_t)CARRY_ROWS*TPI_THREADS*sizeof(double) : 0;
+    const size_t carryBytes = (OP == OP_RKM || OP == OP_RKM_ADAPT) ? (size_t)CARRY_ROWS*TPI_THREADS*sizeof(double) : 0;
     const size_t smemBytes = (a.stageInSmem ? a.tableBytes : 0) + carryBytes;
     auto go = [&](auto kernel) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
@@ -160,7 +185,7 @@ cudaError_t launchOp(const KArgs& a, cudaStream_t stream) {
         kernel<<<grid, TPI_THREADS, smemBytes, stream>>>(a);
         return cudaGetLastError();
     };
-    if constexpr (OP == OP_RKM) {
+    if constexpr (OP == OP_RKM || OP == OP_RKM_ADAPT) {
         if (a.lightJoints) return a.stageInSmem ? go(tpiKernel<OP, true, 4>) : go(tpiKernel<OP, false, 4>);
     }
     return a.stageInSmem ? go(tpiKernel<OP, true, 2>) : go(tpiKernel<OP, false, 2>);
@@ -374,6 +399,7 @@ cudaError_t launchTpi(KernelOp op, const KArgs& a, cudaStream_t stream) {
         case OP_MULMINV: return launchOp<OP_MULMINV>(a, stream);
         case OP_RESID:   return launchOp<OP_RESID>(a, stream);
         case OP_RKM:     return launchOp<OP_RKM>(a, stream);
+        case OP_RKM_ADAPT: return launchOp<OP_RKM_ADAPT>(a, stream);
     }
     return cudaErrorInvalidValue;
 }
@@ -387,6 +413,7 @@ cudaError_t launchLp(KernelOp op, const KArgs& a, cudaStream_t stream) {
         case OP_MULMINV: return launchLpOp<OP_MULMINV>(a, stream);
         case OP_RESID:   return launchLpOp<OP_RESID>(a, stream);
         case OP_RKM:     return launchLpOp<OP_RKM>(a, stream);
+        default: break;   // OP_RKM_ADAPT: not available in the level-parallel plan
     }
     return cudaErrorInvalidValue;
 }
@@ -396,20 +423,20 @@ bool fusedPlanSupports(int nb, const int* joints) {
     if (nb == 3) return simple(joints[1]) && simple(joints[2]);
     return false;
 }
-cudaError_t launchFusedRkm(const KArgs& a, const int* joints, cudaStream_t stream) {
+cudaError_t launchFusedRkm(const KArgs& a, const int* joints, bool adaptive, cudaStream_t stream) {
     if (a.nb == 2) {
         switch (joints[1]) {
-            case JT_PIN:       return launchFusedT<Chain1<JT_PIN>>(a, stream);
-            case JT_SLIDER:    return launchFusedT<Chain1<JT_SLIDER>>(a, stream);
-            case JT_UNIVERSAL: return launchFusedT<Chain1<JT_UNIVERSAL>>(a, stream);
+            case JT_PIN:       return launchFusedT<Chain1<JT_PIN>>(a, adaptive, stream);
+            case JT_SLIDER:    return launchFusedT<Chain1<JT_SLIDER>>(a, adaptive, stream);
+            case JT_UNIVERSAL: return launchFusedT<Chain1<JT_UNIVERSAL>>(a, adaptive, stream);
         }
     } else if (a.nb == 3) {
         const int k = joints[1]*10 + joints[2];
         switch (k) {
-            case JT_PIN*10 + JT_PIN:       return launchFusedT<Chain2<JT_PIN, JT_PIN>>(a, stream);
-            case JT_PIN*10 + JT_SLIDER:    return launchFusedT<Chain2<JT_PIN, JT_SLIDER>>(a, stream);
-            case JT_SLIDER*10 + JT_PIN:    return launchFusedT<Chain2<JT_SLIDER, JT_PIN>>(a, stream);
-            case JT_SLIDER*10 + JT_SLIDER: return launchFusedT<Chain2<JT_SLIDER, JT_SLIDER>>(a, stream);
+            case JT_PIN*10 + JT_PIN:       return launchFusedT<Chain2<JT_PIN, JT_PIN>>(a, adaptive, stream);
+            case JT_PIN*10 + JT_SLIDER:    return launchFusedT<Chain2<JT_PIN, JT_SLIDER>>(a, adaptive, stream);
+            case JT_SLIDER*10 + JT_PIN:    return launchFusedT<Chain2<JT_SLIDER, JT_PIN>>(a, adaptive, stream);
+            case JT_SLIDER*10 + JT_SLIDER: return launchFusedT<Chain2<JT_SLIDER, JT_SLIDER>>(a, adaptive, stream);
         }
     }
     return cudaErrorInvalidValue;

@@ -34,6 +34,12 @@ struct KArgs {
     double accuracy, consTol; int useInfNorm, projectEveryStep;
     double* errNorm;    // [N]
     int* projCount;     // [N] accumulated
+    // error-controlled stepping (OP_RKM_ADAPT)
+    double tFinal, minStep, maxStep; int allowInterp, maxAttempts;
+    double* hcur;       // [N] current step size
+    double* lastStep;   // [N] size of the last accepted step
+    int* stepsTaken;    // [N] accumulated
+    int* attempts;      // [N] accumulated
 };
 
 enum KernelOp {
@@ -42,14 +48,15 @@ enum KernelOp {
     OP_EVAL,           // full realize(Acceleration)
     OP_CALCACC,        // sweeps D+E with caller forces
     OP_MULM, OP_MULMINV, OP_RESID,
-    OP_RKM
+    OP_RKM,
+    OP_RKM_ADAPT       // error-controlled RKM to a final time
 };
 
 // Launch one operation for the thread-per-instance plan on `stream`.
 cudaError_t launchTpi(KernelOp op, const KArgs& a, cudaStream_t stream);
 // Register-resident fused plan (serial chains of 1-2 Pin/Slider[/Universal] mobilizers).
 bool fusedPlanSupports(int nb, const int* joints /*[nb]*/);
-cudaError_t launchFusedRkm(const KArgs& a, const int* joints, cudaStream_t stream);
+cudaError_t launchFusedRkm(const KArgs& a, const int* joints, bool adaptive, cudaStream_t stream);
 // Level-parallel plan (wide trees, small batches): one CTA per instance, threads over the bodies
 // of a tree level, __syncthreads between levels.
 cudaError_t launchLp(KernelOp op, const KArgs& a, cudaStream_t stream);

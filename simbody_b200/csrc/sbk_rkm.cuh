@@ -61,19 +61,45 @@ SBK_HD double rkmErrorNorm(const Ctx& c, const int inst, const RkmWork& w) {
     return qNorm >= uNorm ? qNorm : uNorm;
 }
 
+// AbstractIntegratorRep::adjustStepSize (AbstractIntegratorRep.cpp:448-502).  `h` is the current
+// step size (in/out); returns true ("success") iff the new step is at least as big as the old one.
+struct StepLimits { double accuracy, minStep, maxStep; };   // minStep/maxStep <= 0: no user limit
+SBK_HD bool adjustStepSize(const double err, const StepLimits& lim, const bool hWasArtificiallyLimited, double& h) {
+    const double Safety = 0.9, MinShrink = 0.1, MaxGrow = 5, HysteresisLow = 0.9, HysteresisHigh = 1.2;
+    const double cur = h; double nw;
+    if (!(fabs(err) <= 1.7976931348623157e308)) nw = MinShrink*cur;           // !isFinite(err)
+    else if (err == 0) nw = MaxGrow*cur;
+    else nw = Safety*cur*pow(lim.accuracy/err, 1.0/4.0);                      // errOrder = 4 for RKM
+    if (nw > cur) { if (hWasArtificiallyLimited || nw < HysteresisHigh*cur) nw = cur; }
+    if (nw < cur) { if (err <= lim.accuracy) nw = cur; else nw = fmin(nw, HysteresisLow*cur); }
+    nw = fmin(nw, MaxGrow*cur); nw = fmax(nw, MinShrink*cur);
+    if (lim.minStep > 0) nw = fmax(nw, lim.minStep);
+    if (lim.maxStep > 0) nw = fmin(nw, lim.maxStep);
+    h = nw;
+    return nw >= cur;
+}
+
+// One RKM attempt.  FRESH = true: start of a step -- evaluate f0 = f(y) and save y0 = y
+// (AbstractIntegratorRep.cpp:390-396).  FRESH = false: retry of a failed attempt with a smaller h
+// from the saved y0 / f0 (no re-evaluation, as in takeOneStep's do/while).
 // The caller's Ctx must have q = w.y, u = w.y + nq*sStride and null qerr / fmobOut / FbodyOut.
-template <bool LEAN>
+template <bool LEAN, bool FRESH = true>
 SBK_HD RkmStepResult tpiRkmStep(const Ctx& c, const int inst, const RkmWork& w, const double h, double* cy) {
     const int nq = c.nq, ny = c.nq + c.nu;
     const long long uoff = (long long)nq*c.sStride;
 
-    // f0 = f(y0): AbstractIntegratorRep.cpp:393 realizeStateDerivatives at the start of the step
-    tpiEvalDerivatives<LEAN>(c, inst, cy, w.f0, w.f0 + uoff, nullptr);
+    if (FRESH) {
+        // f0 = f(y0): AbstractIntegratorRep.cpp:393 realizeStateDerivatives at the start of the step
+        tpiEvalDerivatives<LEAN>(c, inst, cy, w.f0, w.f0 + uoff, nullptr);
 #pragma unroll 8
-    for (int i = 0; i < ny; ++i) {
-        const double y0 = ldS(c, inst, w.y, i);
-        stS(c, inst, w.y0, i, y0);
-        stS(c, inst, w.y, i, y0 + (h/3)*ldS(c, inst, w.f0, i));
+        for (int i = 0; i < ny; ++i) {
+            const double y0 = ldS(c, inst, w.y, i);
+            stS(c, inst, w.y0, i, y0);
+            stS(c, inst, w.y, i, y0 + (h/3)*ldS(c, inst, w.f0, i));
+        }
+    } else {
+#pragma unroll 8
+        for (int i = 0; i < ny; ++i) stS(c, inst, w.y, i, ldS(c, inst, w.y0, i) + (h/3)*ldS(c, inst, w.f0, i));
     }
     tpiEvalDerivatives<LEAN>(c, inst, cy, w.fa, w.fa + uoff, nullptr);                        // f1
 #pragma unroll 8
@@ -131,6 +157,38 @@ SBK_HD RkmStepResult tpiRkmStep(const Ctx& c, const int inst, const RkmWork& w, 
         }
     }
     return res;
+}
+
+// Integrator::stepTo(tFinal) with error control for ONE instance (AbstractIntegratorRep.cpp:216-368,
+// 513-578): internal steps until the advanced time reaches tFinal.  With allowInterpolation (the
+// reference's default) steps are never shortened to hit tFinal, so the advanced state ends at
+// t >= tFinal; without it the last step lands on tFinal (hWasArtificiallyLimited logic).
+struct AdaptiveState { double t, h, lastStep; int steps, attempts; };
+template <bool LEAN>
+SBK_HD void tpiRkmAdaptive(const Ctx& c, const int inst, const RkmWork& w, const StepLimits& lim, const double tFinal,
+                           const int allowInterpolation, const int maxAttempts, AdaptiveState& st, double* cy,
+                           double& lastErr, int& nproj) {
+    int budget = maxAttempts;
+    while (st.t < tFinal && budget > 0) {
+        bool fresh = true, ok = false; double t1 = st.t;
+        do {
+            bool limited = false;
+            if (allowInterpolation) t1 = st.t + st.h;
+            else if (tFinal < st.t + 0.95*st.h)  { limited = true; t1 = tFinal; }
+            else if (tFinal > st.t + 1.001*st.h) t1 = st.t + st.h;
+            else t1 = tFinal;
+            const double hTry = t1 - st.t;
+            const RkmStepResult r = fresh ? tpiRkmStep<LEAN, true>(c, inst, w, hTry, cy) : tpiRkmStep<LEAN, false>(c, inst, w, hTry, cy);
+            fresh = false; ++st.attempts; --budget; nproj += r.projected; lastErr = r.errNorm;
+            ok = adjustStepSize(r.errNorm, lim, limited, st.h);
+        } while (!ok && budget > 0);
+        if (!ok) {   // out of budget inside a failing step: put y0 back, report through the status word
+#pragma unroll 8
+            for (int i = 0; i < c.nq + c.nu; ++i) stS(c, inst, w.y, i, ldS(c, inst, w.y0, i));
+            break;
+        }
+        st.lastStep = t1 - st.t; st.t = t1; ++st.steps;
+    }
 }
 
 } // namespace sbkd

@@ -221,6 +221,18 @@ class BatchedMatter:
         self._chk(self.lib.sbk_rkm_step(self.handle, float(h), int(nsteps), ctypes.byref(o), _dp(err)))
         return err
 
+    def stepTo(self, t_final, accuracy=1e-3, constraint_tol=None, init_step=0.01, min_step=-1.0, max_step=-1.0,
+               allow_interpolation=False, use_infinity_norm=False, project_every_step=False, max_attempts=0):
+        """Integrator::stepTo with error control (every instance keeps its own step size).
+        Returns (steps_taken, steps_attempted, last_step) per instance."""
+        o = capi.AdaptiveOpts(accuracy, accuracy / 10 if constraint_tol is None else constraint_tol, init_step, min_step, max_step,
+                              int(use_infinity_norm), int(project_every_step), int(allow_interpolation), int(max_attempts))
+        steps = np.zeros(self.N, dtype=np.int32); att = np.zeros(self.N, dtype=np.int32); last = np.zeros(self.N)
+        ip = ctypes.POINTER(ctypes.c_int32)
+        self._chk(self.lib.sbk_rkm_adaptive(self.handle, float(t_final), ctypes.byref(o), steps.ctypes.data_as(ip),
+                                            att.ctypes.data_as(ip), _dp(last)))
+        return steps, att, last
+
     def stats(self):
         v = [ctypes.c_int64() for _ in range(3)]
         self._chk(self.lib.sbk_rkm_stats(self.handle, *[ctypes.byref(x) for x in v]))

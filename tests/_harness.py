@@ -134,15 +134,16 @@ class RefDriver:
             return np.fromfile(op, dtype=np.float64).reshape(n, info.nq + info.nu + 3)
         return self._with_model(info.text, go)
 
-    def adaptive(self, info, y, t_final, accuracy=-1):
+    def adaptive(self, info, y, t_final, accuracy=-1, allow_interpolation=True):
+        """-> [n, ny+5]: advanced q,u | steps taken | attempted | realizations | last step | advanced time"""
         y = np.ascontiguousarray(y, dtype=np.float64)
         n = y.shape[0]
 
         def go(d, mp):
             ip, op = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
             y.tofile(ip)
-            self._run(["adaptive", mp, ip, op, n, repr(float(t_final)), repr(float(accuracy))])
-            return np.fromfile(op, dtype=np.float64).reshape(n, info.nq + info.nu + 4)
+            self._run(["adaptive", mp, ip, op, n, repr(float(t_final)), repr(float(accuracy)), int(allow_interpolation)])
+            return np.fromfile(op, dtype=np.float64).reshape(n, info.nq + info.nu + 5)
         return self._with_model(info.text, go)
 
     def bench(self, info, y, h, nsteps, threads):
@@ -167,6 +168,8 @@ class HostEmu:
         self.lib.emu_eval.argtypes = [ctypes.c_char_p, ctypes.c_int, dp, dp]
         self.lib.emu_step.argtypes = [ctypes.c_char_p, ctypes.c_int, dp, dp, ctypes.c_double, ctypes.c_int,
                                       ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        self.lib.emu_adaptive.argtypes = [ctypes.c_char_p, ctypes.c_int, dp, dp, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                          ctypes.c_int, ctypes.c_int]
         self.lib.emu_model_text.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
 
     def model_text(self, name, n=0):
@@ -195,6 +198,21 @@ class HostEmu:
                                accuracy, accuracy / 10 if cons_tol is None else cons_tol, inf_norm, project_every, lean)
         assert rc == 0, rc
         return out
+
+
+def _emu_adaptive(self, info, y, t_final, accuracy=1e-3, init_step=0.01, allow_interpolation=True, fused=False):
+    """-> [n, ny+5] in the layout of RefDriver.adaptive (realizations = steps + 4*attempts)."""
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    n = y.shape[0]
+    out = np.zeros((n, info.nq + info.nu + 5))
+    dp = ctypes.POINTER(ctypes.c_double)
+    rc = self.lib.emu_adaptive(info.text.encode(), n, y.ctypes.data_as(dp), out.ctypes.data_as(dp), t_final, accuracy, init_step,
+                               int(allow_interpolation), int(fused))
+    assert rc == 0, rc
+    return out
+
+
+HostEmu.adaptive = _emu_adaptive
 
 
 def rel_err(a, b):

@@ -181,6 +181,39 @@ int emu_step(const char* text, int N, const double* in, double* out, double h, i
     } catch (const std::exception& ex) { std::fprintf(stderr, "emu: %s\n", ex.what()); return 1; }
 }
 
+// Error-controlled stepping; out [N][ny+5]: y | steps | attempts | steps+4*attempts | last step | advanced time
+int emu_adaptive(const char* text, int N, const double* in, double* out, double tFinal, double accuracy, double initStep,
+                 int allowInterpolation, int fused) {
+    try {
+        Emu e; setup(e, text, N);
+        const sbk_topology& t = e.topo; const int ny = t.nq + t.nu;
+        for (int k = 0; k < N; ++k) for (int i = 0; i < ny; ++i) e.y[(size_t)i*N + k] = in[(size_t)k*ny + i];
+        RkmWork w; w.y = e.y.data(); w.y0 = e.y0.data(); w.f0 = e.f0.data(); w.fa = e.fa.data(); w.fb = e.fb.data(); w.ys = e.ys.data();
+        w.accuracy = accuracy; w.consTol = accuracy/10; w.useInfNorm = 0; w.projectEveryStep = 0;
+        StepLimits lim; lim.accuracy = accuracy; lim.minStep = -1; lim.maxStep = -1;
+        for (int k = 0; k < N; ++k) {
+            AdaptiveState st; st.t = 0; st.h = initStep; st.lastStep = initStep; st.steps = 0; st.attempts = 0;
+            double lastErr = 0; int nproj = 0;
+            double* o = out + (size_t)k*(ny+5);
+            if (fused) {
+                if (t.nb != 3 || t.bodies[1].joint != JT_PIN || t.bodies[2].joint != JT_PIN) return 4;
+                double y[8]; for (int i = 0; i < ny; ++i) y[i] = e.y[(size_t)i*N + k];
+                Chain2<JT_PIN, JT_PIN> ch; ch.b0 = &e.bodies[1]; ch.b1 = &e.bodies[2]; ch.forces = t.forces.data();
+                ch.gx = t.grav[0]; ch.gy = t.grav[1]; ch.gz = t.grav[2];
+                fusedRkmAdaptive(ch, y, lim, tFinal, allowInterpolation, 1000000, 0, st, lastErr);
+                for (int i = 0; i < ny; ++i) o[i] = y[i];
+            } else {
+                Ctx c = makeCtx(e, k); c.qdotdot = nullptr; c.qerr = nullptr;
+                double cy[CARRY_ROWS];
+                tpiRkmAdaptive<true>(c, k, w, lim, tFinal, allowInterpolation, 1000000, st, cy, lastErr, nproj);
+                for (int i = 0; i < ny; ++i) o[i] = e.y[(size_t)i*N + k];
+            }
+            o[ny] = st.steps; o[ny+1] = st.attempts; o[ny+2] = st.steps + 4.0*st.attempts; o[ny+3] = st.lastStep; o[ny+4] = st.t;
+        }
+        return 0;
+    } catch (const std::exception& ex) { std::fprintf(stderr, "emu: %s\n", ex.what()); return 1; }
+}
+
 int emu_model_text(const char* name, int n, char* buf, int cap) {
     try {
         const std::string s = sbk::toText(sbk::makeNamedModel(name, n));

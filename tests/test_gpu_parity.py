@@ -207,3 +207,44 @@ def test_auto_plan_selection():
         bm = sb.BatchedMatter(topo, batch)
         assert bm.getPlan() == plan, (name, batch, bm.getPlan())
         bm.close(); topo.close()
+
+
+def test_adaptive_rkm_readme_double_pendulum():
+    """BASELINE config C1 on the GPU: README double pendulum, adaptive RKM (accuracy 1e-3) to 20 s.
+    The reference takes 126 steps / 169 attempts.  The step-size sequence
+    is chaotic in the last digits of the error norm, so the GPU run must reproduce the counts within a
+    few steps and every instance must land exactly on t = 20; both plans are exercised."""
+    info = ModelInfo(sb.model_text("double_pendulum"))
+    n = 256
+    q = np.zeros((2, n)); u = np.zeros((2, n)); u[1, :] = 5.0
+    for plan in (2, 1):
+        topo = sb.Topology(text=info.text); bm = sb.BatchedMatter(topo, n); bm.setPlan(plan)
+        bm.setState(q, u, t=0.0)
+        steps, att, last = bm.stepTo(20.0)
+        qq, uu, t = bm.getState()
+        assert np.all(t == 20.0)
+        assert np.all(steps == steps[0]) and np.all(att == att[0])          # identical instances, identical history
+        assert abs(int(steps[0]) - 126) <= 3 and abs(int(att[0]) - 169) <= 4, (plan, steps[0], att[0])
+        st, nbad = bm.status(); assert nbad == 0
+        bm.close(); topo.close()
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
+def test_adaptive_rkm_short_horizon_matches_live_reference():
+    """Short horizons (before chaos amplifies rounding): state, step and attempt counts against the reference."""
+    for name, tf, qs, plan in [("double_pendulum", 1.0, 2.0, 2), ("double_pendulum", 1.0, 2.0, 1), ("humanoid30", 0.2, 0.4, 1)]:
+        info = ModelInfo(sb.model_text(name))
+        nI = 64
+        qv, uv = info.random_states(nI, 21, q_scale=qs)
+        ref = RefDriver().adaptive(info, np.concatenate([qv, uv], axis=1), tf)
+        ny = info.nq + info.nu
+        topo = sb.Topology(text=info.text); bm = sb.BatchedMatter(topo, nI); bm.setPlan(plan)
+        bm.setState(soa(qv), soa(uv), t=0.0)
+        steps, att, last = bm.stepTo(tf)
+        qq, uu, t = bm.getState()
+        same = (steps == ref[:, ny]) & (att == ref[:, ny + 1])
+        assert same.mean() > 0.9, (name, plan, same.mean())
+        got = np.concatenate([qq.T, uu.T], axis=1)
+        assert rel_err(got[same], ref[same][:, :ny]) < 1e-8, (name, plan)
+        assert np.all(t == tf)
+        bm.close(); topo.close()

@@ -148,3 +148,30 @@ def test_plans_are_bitwise_identical_on_host(built):
     q, u = info.random_states(8, 6, q_scale=3.0)
     y = np.concatenate([q, u], axis=1)
     assert np.array_equal(emu.step(info, y, 1e-3, 30, lean=1), emu.step(info, y, 1e-3, 30, lean=2))
+
+
+def test_adaptive_rkm_reproduces_readme_run_on_host(built):
+    """BASELINE config C1 (README double pendulum, adaptive RKM, accuracy 1e-3, 20 s): SURVEY.md
+    section 8c records 126 steps / 169 attempts and the final state; the kernels' step-size
+    controller (host build) must reproduce them exactly."""
+    emu = HostEmu()
+    info = ModelInfo(emu.model_text("double_pendulum"))
+    y = np.array([[0.0, 0.0, 0.0, 5.0]])
+    for fused in (False, True):
+        o = emu.adaptive(info, y, 20.0, allow_interpolation=False, fused=fused)[0]
+        assert (o[4], o[5]) == (126, 169)
+        assert np.allclose(o[:4], [-0.69185519245297433, -17.50067206152189, 0.4044972455348419, -4.7180318836946675], rtol=1e-9)
+        assert abs(o[7] - 0.137659) < 1e-6 and o[8] == 20.0
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("name,n,tf,qs", [("double_pendulum", 0, 3.0, 2.0), ("mixed7", 0, 1.0, 0.5), ("humanoid30", 0, 0.3, 0.4)])
+def test_adaptive_rkm_matches_live_reference(built, name, n, tf, qs):
+    emu, ref = HostEmu(), RefDriver()
+    info = ModelInfo(emu.model_text(name, n))
+    q, u = info.random_states(5, 3, q_scale=qs)
+    y = np.concatenate([q, u], axis=1)
+    ny = info.nq + info.nu
+    r = ref.adaptive(info, y, tf); e = emu.adaptive(info, y, tf, allow_interpolation=False)
+    assert np.array_equal(r[:, ny], e[:, ny]) and np.array_equal(r[:, ny + 1], e[:, ny + 1])     # steps, attempts
+    assert rel_err(e[:, :ny], r[:, :ny]) < 1e-9 and np.array_equal(r[:, ny + 4], e[:, ny + 4])
