@@ -193,6 +193,11 @@ int sbk_get_body_accelerations(sbk_batch*, double* A_GB);
  * mobility forces [nu][N], body forces [nb][6][N] (MultibodySystem.cpp:163-177).         */
 int sbk_get_applied_forces(sbk_batch*, double* f_mob, double* F_body);
 
+/* MultibodySystem::calcKineticEnergy / calcPotentialEnergy for the lowered system
+ * (SimbodyMatterSubsystemRep.cpp:5234-5246, RigidBodyNode.cpp:182-188, Force_Gravity.cpp:555,
+ * Force.cpp:354-361).  Needs Velocity stage (ke) / Position stage (pe).  Host [N], nullable.   */
+int sbk_calc_energy(sbk_batch*, double* kinetic, double* potential);
+
 /* ---- operators ------------------------------------------------------------------------ */
 /* SimbodyMatterSubsystem::calcAcceleration / calcAccelerationIgnoringConstraints
  * (SimbodyMatterSubsystem.h:2141,2171; SimbodyMatterSubsystem.cpp:151-226).

@@ -158,6 +158,23 @@ static int cmdEval(RefSystem& rs, const char* inPath, const char* outPath, int N
     return 0;
 }
 
+// ---- energy -----------------------------------------------------------------------------------
+// in per instance: q[nq] u[nu]; out per instance: kinetic, potential
+static int cmdEnergy(RefSystem& rs, const char* inPath, const char* outPath, int N) {
+    const int nq=rs.nq, nu=rs.nu, ny=nq+nu;
+    std::vector<double> in = readDoubles(inPath);
+    if ((int)in.size() != N*ny) { std::fprintf(stderr, "energy: bad input size\n"); return 2; }
+    std::vector<double> out((size_t)N*2);
+    State s = rs.defaultState;
+    for (int k = 0; k < N; ++k) {
+        setQU(s, &in[(size_t)k*ny], nq, &in[(size_t)k*ny+nq], nu);
+        rs.system.realize(s, Stage::Dynamics);
+        out[2*k] = rs.system.calcKineticEnergy(s); out[2*k+1] = rs.system.calcPotentialEnergy(s);
+    }
+    writeDoubles(outPath, out);
+    return 0;
+}
+
 // ---- step -----------------------------------------------------------------------------------
 // in per instance: q[nq] u[nu]; out per instance: q[nq] u[nu] stepsTaken realizations qProjections
 static void configureFixed(RungeKuttaMersonIntegrator& integ, double h, double accuracy) {
@@ -262,7 +279,7 @@ int main(int argc, char** argv) {
         if (argc < 3) {
             std::fprintf(stderr,
                 "usage: ref_driver lower|slots <model.txt>\n"
-                "       ref_driver eval <model.txt> <in.bin> <out.bin> <N>\n"
+                "       ref_driver eval|energy <model.txt> <in.bin> <out.bin> <N>\n"
                 "       ref_driver step <model.txt> <in.bin> <out.bin> <N> <h> <nsteps> [accuracy]\n"
                 "       ref_driver adaptive <model.txt> <in.bin> <out.bin> <N> <tFinal> [accuracy] [allowInterpolation]\n"
                 "       ref_driver bench <model.txt> <in.bin> <N> <h> <nsteps> <threads> [out.bin]\n");
@@ -293,6 +310,7 @@ int main(int argc, char** argv) {
             return 0;
         }
         if (cmd == "eval" && argc >= 6) return cmdEval(rs, argv[3], argv[4], std::atoi(argv[5]));
+        if (cmd == "energy" && argc >= 6) return cmdEnergy(rs, argv[3], argv[4], std::atoi(argv[5]));
         if (cmd == "step" && argc >= 8)
             return cmdStep(rs, argv[3], argv[4], std::atoi(argv[5]), std::atof(argv[6]), std::atoi(argv[7]),
                            argc > 8 ? std::atof(argv[8]) : -1);

@@ -437,6 +437,18 @@ int sbk_get_applied_forces(sbk_batch* b, double* fmob, double* Fbody) {
     return SBK_OK;
 }
 
+int sbk_calc_energy(sbk_batch* b, double* ke, double* pe) {
+    if (!b) return fail(SBK_ERR_ARG, "null batch");
+    if (int rc = useDevice(b)) return rc;
+    if (int rc = needStage(b, ke ? ST_VELOCITY : ST_POSITION, "sbk_calc_energy")) return rc;
+    if (int rc = ensureScratch(b, (size_t)2*b->N)) return rc;
+    CUDA_TRY(launchEnergy(b->a, b->dScratch, b->dScratch + b->N, b->stream)); b->launches++;
+    if (ke) CUDA_TRY(cudaMemcpyAsync(ke, b->dScratch, (size_t)b->N*sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    if (pe) CUDA_TRY(cudaMemcpyAsync(pe, b->dScratch + b->N, (size_t)b->N*sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return SBK_OK;
+}
+
 // ---- operators --------------------------------------------------------------------------------
 int sbk_calc_acceleration(sbk_batch* b, const double* fmob, const double* Fbody, double* udot, double* A_GB) {
     if (!b) return fail(SBK_ERR_ARG, "null batch");

@@ -376,6 +376,41 @@ __global__ void gatherBodyFieldKernel(const KArgs a, int fieldOffset, int width,
     }
 }
 
+// Kinetic and potential energy of every instance from the realized position/velocity records:
+//   KE = sum_b 1/2 V_GB . (Mk_G V_GB) in level order   (SimbodyMatterSubsystemRep.cpp:5234-5246, RigidBodyNode.cpp:182-188)
+//   PE = gravity: -m (g . p_G_CB) per body (Force_Gravity.cpp:555) + springs: k (q-q0)^2 / 2 (Force.cpp:354-361)
+__global__ void energyKernel(const KArgs a, double* ke, double* pe) {
+    const int k = blockIdx.x*blockDim.x + threadIdx.x;
+    if (k >= a.N) return;
+    const BodyConst* bodies = reinterpret_cast<const BodyConst*>(a.tables);
+    const ForceConst* forces = reinterpret_cast<const ForceConst*>(a.tables + a.forcesOff);
+    const int* order = reinterpret_cast<const int*>(a.tables + a.levelOrderOff);
+    double kin = 0, pot = 0;
+    for (int i = 1; i < a.nb; ++i) {                       // level order (order[0] is Ground)
+        const BodyConst& bc = bodies[order[i]];
+        CacheRef me; me.p = a.cache + bc.cacheBase + (long long)k*a.cInstStride; me.stride = a.cStride;
+        const SV V = me.ldSV(F_VGB);
+        kin += dot(V, mulSpatialInertia(bc.mass, me.ld3(F_MK), me.ldS3(F_MK + 3), V))/2;
+    }
+    for (int b = 1; b < a.nb; ++b) {                       // MobilizedBodyIndex order
+        const BodyConst& bc = bodies[b];
+        CacheRef me; me.p = a.cache + bc.cacheBase + (long long)k*a.cInstStride; me.stride = a.cStride;
+        const V3 pc = me.ld3(F_XGB + 9) + me.ld3(F_MK);    // p_G_CB = p_GB + R_GB*com_B
+        pot -= bc.mass*(a.gx*pc.x + a.gy*pc.y + a.gz*pc.z + 0.0);
+    }
+    for (int b = 1; b < a.nb; ++b) {
+        const BodyConst& bc = bodies[b];
+        for (int f = 0; f < bc.nforce; ++f) {
+            const ForceConst fc = forces[bc.forceStart + f];
+            if (fc.kind != FK_SPRING) continue;
+            const double dq = a.y[(long long)(bc.q0 + fc.coord)*a.N + k] - fc.b;
+            pot += fc.a*(dq*dq)/2;
+        }
+    }
+    if (ke) ke[k] = kin;
+    if (pe) pe[k] = pot;
+}
+
 __global__ void dfmaProbeKernel(double* out, int iters) {
     double a0 = 1.0 + threadIdx.x*1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3,
            a4 = a0 + 4e-3, a5 = a0 + 5e-3, a6 = a0 + 6e-3, a7 = a0 + 7e-3;
@@ -452,6 +487,10 @@ cudaError_t launchTranspose(const double* src, double* dst, int rows, int cols, 
 }
 cudaError_t launchGatherBodyField(const KArgs& a, int fieldOffset, int width, double* out, cudaStream_t stream) {
     gatherBodyFieldKernel<<<(a.N + 127)/128, 128, 0, stream>>>(a, fieldOffset, width, out);
+    return cudaGetLastError();
+}
+cudaError_t launchEnergy(const KArgs& a, double* ke, double* pe, cudaStream_t stream) {
+    energyKernel<<<(a.N + 127)/128, 128, 0, stream>>>(a, ke, pe);
     return cudaGetLastError();
 }
 cudaError_t launchDfmaProbe(double* out, int iters, int blocks, int threads, cudaStream_t stream) {

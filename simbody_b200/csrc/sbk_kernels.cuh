@@ -66,6 +66,8 @@ cudaError_t launchInitGround(const KArgs& a, cudaStream_t stream);
 cudaError_t launchTranspose(const double* src, double* dst, int rows, int cols, cudaStream_t stream);
 // Gather one per-body cache field (width doubles at field offset) into out[(b*width+i)*N + k].
 cudaError_t launchGatherBodyField(const KArgs& a, int fieldOffset, int width, double* out, cudaStream_t stream);
+// Kinetic / potential energy per instance from the realized records (ke, pe: device [N], nullable).
+cudaError_t launchEnergy(const KArgs& a, double* ke, double* pe, cudaStream_t stream);
 // FP64 FMA throughput probe: returns flops executed; used by bench.py to measure the FP64 roofline.
 cudaError_t launchDfmaProbe(double* out, int iters, int blocks, int threads, cudaStream_t stream);
 

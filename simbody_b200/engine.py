@@ -178,6 +178,12 @@ class BatchedMatter:
         self._chk(self.lib.sbk_get_applied_forces(self.handle, _dp(f), _dp(F)))
         return f, F.reshape(self.topo.nb, 6, self.N)
 
+    def calcEnergy(self):
+        """(kinetic, potential) per instance: MultibodySystem::calcKineticEnergy / calcPotentialEnergy."""
+        ke = np.empty(self.N); pe = np.empty(self.N)
+        self._chk(self.lib.sbk_calc_energy(self.handle, _dp(ke), _dp(pe)))
+        return ke, pe
+
     # ---- operators (SimbodyMatterSubsystem.h:2141,1262,1343,2234) --------------------------------
     def calcAcceleration(self, appliedMobilityForces=None, appliedBodyForces=None):
         f = self._vec(appliedMobilityForces, self.topo.nu, "appliedMobilityForces", True)

@@ -123,6 +123,18 @@ class RefDriver:
             return np.fromfile(op, dtype=np.float64).reshape(n, info.eval_out_stride)
         return self._with_model(info.text, go)
 
+    def energy(self, info, y):
+        """-> [n, 2]: kinetic, potential energy (MultibodySystem::calcKineticEnergy / calcPotentialEnergy)"""
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        n = y.shape[0]
+
+        def go(d, mp):
+            ip, op = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
+            y.tofile(ip)
+            self._run(["energy", mp, ip, op, n])
+            return np.fromfile(op, dtype=np.float64).reshape(n, 2)
+        return self._with_model(info.text, go)
+
     def step(self, info, y, h, nsteps, accuracy=-1):
         y = np.ascontiguousarray(y, dtype=np.float64)
         n = y.shape[0]

@@ -36,8 +36,9 @@ def main():
         y0 = np.concatenate([q, u], axis=1)
         yout = ref.step(info, y0, h, nsteps)
         path = os.path.join(HERE, "%s.npz" % name)
+        energy = ref.energy(info, ein[:, :info.nq + info.nu])      # [n, 2] kinetic, potential at the eval states
         np.savez_compressed(path, text=np.array(text), eval_in=ein, eval_out=eout, step_in=y0, step_out=yout,
-                            h=h, nsteps=nsteps, slots=np.array(ref.slots(text)))
+                            h=h, nsteps=nsteps, slots=np.array(ref.slots(text)), energy=energy)
         print("wrote", path, os.path.getsize(path), "bytes")
 
 

@@ -248,3 +248,36 @@ def test_adaptive_rkm_short_horizon_matches_live_reference():
         assert rel_err(got[same], ref[same][:, :ny]) < 1e-8, (name, plan)
         assert np.all(t == tf)
         bm.close(); topo.close()
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_energy_matches_golden(name):
+    """Kinetic / potential energy against MultibodySystem::calcKineticEnergy / calcPotentialEnergy."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    info = ModelInfo(str(g["text"]))
+    ein = g["eval_in"]; n = ein.shape[0]
+    for plan in ([None, 3] if name in ("mixed7", "branched_tree") else [None]):
+        topo = sb.Topology(text=info.text); bm = sb.BatchedMatter(topo, n)
+        if plan:
+            bm.setPlan(plan)
+        bm.setState(soa(ein[:, :info.nq]), soa(ein[:, info.nq:info.nq + info.nu]))
+        bm.realizeVelocityKinematics()
+        ke, pe = bm.calcEnergy()
+        assert rel_err(ke, g["energy"][:, 0]) < 1e-12 and rel_err(pe, g["energy"][:, 1]) < 1e-12
+        bm.close(); topo.close()
+
+
+def test_energy_conservation_over_a_run():
+    """Undamped systems conserve KE+PE (reference Simbody/tests/TestForces.cpp:244-288)."""
+    for name, n, h, steps in [("double_pendulum", 0, 5e-4, 4000), ("pin_chain", 10, 5e-4, 1000)]:
+        info = ModelInfo(sb.model_text(name, n))
+        nI = 128
+        q, u = info.random_states(nI, 5, q_scale=1.0)
+        topo = sb.Topology(text=info.text); bm = sb.BatchedMatter(topo, nI)
+        bm.setState(soa(q), soa(u))
+        bm.realizeVelocityKinematics(); ke0, pe0 = bm.calcEnergy()
+        bm.stepBy(h, steps)
+        bm.realizeVelocityKinematics(); ke1, pe1 = bm.calcEnergy()
+        drift = np.abs((ke1 + pe1) - (ke0 + pe0)) / np.maximum(1.0, np.abs(ke0 + pe0))
+        assert drift.max() < 1e-7, (name, drift.max())
+        bm.close(); topo.close()
