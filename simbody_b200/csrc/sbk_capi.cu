@@ -6,6 +6,7 @@
 // every compute entry point returns SBK_ERR_CUDA.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -170,12 +171,19 @@ static int configurePlan(sbk_batch* b, int plan) {
         std::vector<int> pos(t->nb);
         for (int i = 0; i < t->nb; ++i) pos[order[i]] = i;
         for (int i = 0; i < t->nb; ++i) bodies[i].cacheBase = pos[i];
-        a.cStride = t->nb; a.cInstStride = (long long)CACHE_RECORD_MAX*t->nb;
-        cacheDoubles = a.cInstStride*n;
+        a.cStride = t->nb; a.cInstStride = 0; a.cSpan = (long long)CACHE_RECORD_MAX*t->nb; a.cShift = 0; a.cMask = 0;
+        cacheDoubles = a.cSpan*n;
     } else {
+        // field-major over the whole batch: [record field][N].  (Blocking the records by 128-instance
+        // CTA -- [block][field][lane], one contiguous span per CTA -- was measured and changes nothing:
+        // the plan is bound by L2/HBM throughput, not by DRAM-page or TLB locality.  SBK_BLOCKED=1 selects it.)
         long long off = 0;
-        for (int i = 0; i < t->nb; ++i) { bodies[i].cacheBase = off*n; off += (i == 0) ? F_H : cacheRecordSize(t->nuOf[i]); }
-        a.cStride = n; a.cInstStride = 1; cacheDoubles = off*n; b->recTotal = off;
+        const char* eb = getenv("SBK_BLOCKED"); const bool blocked = eb && atoi(eb) != 0;
+        const long long g = blocked ? 128 : n;
+        for (int i = 0; i < t->nb; ++i) { bodies[i].cacheBase = off*g; off += (i == 0) ? F_H : cacheRecordSize(t->nuOf[i]); }
+        if (blocked) { a.cStride = 128; a.cInstStride = 1; a.cSpan = off*128; a.cShift = 7; a.cMask = 127; cacheDoubles = off*128*(((long long)n + 127)/128); }
+        else         { a.cStride = n;   a.cInstStride = 1; a.cSpan = 0;       a.cShift = 30; a.cMask = 0x3fffffff; cacheDoubles = off*n; }
+        b->recTotal = off;
     }
     for (int i = 0; i < t->nb; ++i) bodies[i].parentCacheBase = bodies[bodies[i].parent].cacheBase;
     auto pad16 = [](size_t x) { return (x + 15)/16*16; };
@@ -193,8 +201,10 @@ static int configurePlan(sbk_batch* b, int plan) {
     a.tableBytes = (uint32_t)blob.size(); a.childrenOff = (uint32_t)bodiesBytes; a.forcesOff = (uint32_t)(bodiesBytes + childBytes);
     a.levelOrderOff = (uint32_t)(bodiesBytes + childBytes + forceBytes); a.levelStartOff = a.levelOrderOff + (uint32_t)orderBytes;
     a.nlevels = t->nlevels; a.plan = plan;
+    { const char* e = getenv("SBK_PREFETCH"); a.prefetch = e ? atoi(e) : 0; }
     a.lightJoints = 1;
     for (int i = 1; i < t->nb; ++i) if (t->nuOf[i] > 2) a.lightJoints = 0;
+    { const char* e = getenv("SBK_LIGHT"); if (e) a.lightJoints = atoi(e); }     // tuning override
     a.stageInSmem = (plan != 3 && blob.size() <= 96*1024) ? 1u : 0u;
     CUDA_TRY(cudaStreamSynchronize(b->stream));
     if (b->dTables) cudaFree(b->dTables);

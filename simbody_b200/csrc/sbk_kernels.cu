@@ -55,7 +55,7 @@ __device__ __forceinline__ void fillCtx(Ctx& c, const KArgs& a, const unsigned c
     c.forces   = reinterpret_cast<const ForceConst*>(tables + a.forcesOff);
     c.nb = a.nb; c.nq = a.nq; c.nu = a.nu; c.nquat = a.nquat;
     c.gx = a.gx; c.gy = a.gy; c.gz = a.gz;
-    c.cache = a.cache; c.cStride = a.cStride; c.cInstStride = a.cInstStride;
+    c.cache = a.cache; c.cStride = a.cStride; c.cInstStride = a.cInstStride; c.cSpan = a.cSpan; c.cShift = a.cShift; c.cMask = a.cMask;
     c.sStride = a.N; c.sInstStride = 1;
     c.q = a.y; c.u = a.y + (long long)a.nq*a.N;
     c.qdot = a.ydot; c.udot = a.ydot ? a.ydot + (long long)a.nq*a.N : nullptr;
@@ -83,7 +83,11 @@ __global__ void __launch_bounds__(TPI_THREADS, MINB) tpiKernel(const KArgs a) {
     const Ctx& c = sctx;
     // LEAN carry: a [CARRY_ROWS][128] block of shared memory behind the staged tables
     double* cy = nullptr;
-    if constexpr (OP == OP_RKM || OP == OP_RKM_ADAPT) cy = reinterpret_cast<double*>(smem + (STAGE ? a.tableBytes : 0)) + threadIdx.x;
+    double* pf = nullptr;                     // prefetch slot column [PF_CAP][128] behind the carry (255-register variant only)
+    if constexpr (OP == OP_RKM || OP == OP_RKM_ADAPT) {
+        cy = reinterpret_cast<double*>(smem + (STAGE ? a.tableBytes : 0)) + threadIdx.x;
+        if (a.prefetch) pf = cy + CARRY_ROWS*TPI_THREADS;
+    }
 
     if constexpr (OP == OP_KIN) {
         tpiKinematics<false>(c, inst, cy, c.qdot);
@@ -109,7 +113,7 @@ __global__ void __launch_bounds__(TPI_THREADS, MINB) tpiKernel(const KArgs a) {
         w.accuracy = a.accuracy; w.consTol = a.consTol; w.useInfNorm = a.useInfNorm; w.projectEveryStep = a.projectEveryStep;
         RkmStepResult r; r.errNorm = 0; r.projected = 0;
         int nproj = 0; double t = a.tcur[inst];
-        for (int s = 0; s < a.nsteps; ++s) { r = tpiRkmStep<true>(c, inst, w, a.h, cy); nproj += r.projected; t += a.h; }
+        for (int s = 0; s < a.nsteps; ++s) { r = tpiRkmStep<true>(c, inst, w, a.h, cy, pf); nproj += r.projected; t += a.h; }
         a.tcur[inst] = t;
         a.errNorm[inst] = r.errNorm;
         a.projCount[inst] += nproj;
@@ -121,7 +125,7 @@ __global__ void __launch_bounds__(TPI_THREADS, MINB) tpiKernel(const KArgs a) {
         StepLimits lim; lim.accuracy = a.accuracy; lim.minStep = a.minStep; lim.maxStep = a.maxStep;
         AdaptiveState st; st.t = a.tcur[inst]; st.h = a.hcur[inst]; st.lastStep = a.lastStep[inst]; st.steps = 0; st.attempts = 0;
         double lastErr = a.errNorm[inst]; int nproj = 0;
-        tpiRkmAdaptive<true>(c, inst, w, lim, a.tFinal, a.allowInterp, a.maxAttempts, st, cy, lastErr, nproj);
+        tpiRkmAdaptive<true>(c, inst, w, lim, a.tFinal, a.allowInterp, a.maxAttempts, st, cy, lastErr, nproj, pf);
         a.tcur[inst] = st.t; a.hcur[inst] = st.h; a.lastStep[inst] = st.lastStep;
         a.stepsTaken[inst] += st.steps; a.attempts[inst] += st.attempts;
         a.errNorm[inst] = lastErr; a.projCount[inst] += nproj;
@@ -177,7 +181,8 @@ template <int OP>
 cudaError_t launchOp(const KArgs& a, cudaStream_t stream) {
     static_assert(TPI_THREADS == SBK_CARRY_STRIDE_DEVICE, "carry columns are laid out for 128-thread CTAs");
     const int grid = (a.N + TPI_THREADS - 1)/TPI_THREADS;
-    const size_t carryBytes = (OP == OP_RKM || OP == OP_RKM_ADAPT) ? (size_t)CARRY_ROWS*TPI_THREADS*sizeof(double) : 0;
+    const size_t carryBytes = (OP == OP_RKM || OP == OP_RKM_ADAPT)
+        ? (size_t)(CARRY_ROWS + (a.prefetch ? PF_CAP : 0))*TPI_THREADS*sizeof(double) : 0;
     const size_t smemBytes = (a.stageInSmem ? a.tableBytes : 0) + carryBytes;
     auto go = [&](auto kernel) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
@@ -349,10 +354,13 @@ template <int OP> cudaError_t launchLpOp(const KArgs& a, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+__device__ __forceinline__ long long instOffsetK(const KArgs& a, int k) {
+    return (long long)(k >> a.cShift)*a.cSpan + (long long)(k & a.cMask)*a.cInstStride;
+}
 __global__ void initGroundKernel(const KArgs a) {
     const int k = blockIdx.x*blockDim.x + threadIdx.x;
     if (k >= a.N) return;
-    double* rec = a.cache + (long long)k*a.cInstStride;     // Ground is record base 0 in every plan
+    double* rec = a.cache + instOffsetK(a, k);     // Ground is record base 0 in every plan
     for (int f = 0; f < F_H; ++f) rec[(long long)f*a.cStride] = (f == F_XGB || f == F_XGB+4 || f == F_XGB+8) ? 1.0 : 0.0;
 }
 
@@ -371,7 +379,7 @@ __global__ void gatherBodyFieldKernel(const KArgs a, int fieldOffset, int width,
     if (k >= a.N) return;
     const BodyConst* bodies = reinterpret_cast<const BodyConst*>(a.tables);
     for (int b = 0; b < a.nb; ++b) {
-        const double* rec = a.cache + bodies[b].cacheBase + (long long)k*a.cInstStride;
+        const double* rec = a.cache + bodies[b].cacheBase + instOffsetK(a, k);
         for (int i = 0; i < width; ++i) out[((long long)b*width + i)*a.N + k] = rec[(long long)(fieldOffset + i)*a.cStride];
     }
 }
@@ -388,13 +396,13 @@ __global__ void energyKernel(const KArgs a, double* ke, double* pe) {
     double kin = 0, pot = 0;
     for (int i = 1; i < a.nb; ++i) {                       // level order (order[0] is Ground)
         const BodyConst& bc = bodies[order[i]];
-        CacheRef me; me.p = a.cache + bc.cacheBase + (long long)k*a.cInstStride; me.stride = a.cStride;
+        CacheRef me; me.p = a.cache + bc.cacheBase + instOffsetK(a, k); me.stride = a.cStride;
         const SV V = me.ldSV(F_VGB);
         kin += dot(V, mulSpatialInertia(bc.mass, me.ld3(F_MK), me.ldS3(F_MK + 3), V))/2;
     }
     for (int b = 1; b < a.nb; ++b) {                       // MobilizedBodyIndex order
         const BodyConst& bc = bodies[b];
-        CacheRef me; me.p = a.cache + bc.cacheBase + (long long)k*a.cInstStride; me.stride = a.cStride;
+        CacheRef me; me.p = a.cache + bc.cacheBase + instOffsetK(a, k); me.stride = a.cStride;
         const V3 pc = me.ld3(F_XGB + 9) + me.ld3(F_MK);    // p_G_CB = p_GB + R_GB*com_B
         pot -= bc.mass*(a.gx*pc.x + a.gy*pc.y + a.gz*pc.z + 0.0);
     }

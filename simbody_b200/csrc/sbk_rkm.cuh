@@ -84,13 +84,13 @@ SBK_HD bool adjustStepSize(const double err, const StepLimits& lim, const bool h
 // from the saved y0 / f0 (no re-evaluation, as in takeOneStep's do/while).
 // The caller's Ctx must have q = w.y, u = w.y + nq*sStride and null qerr / fmobOut / FbodyOut.
 template <bool LEAN, bool FRESH = true>
-SBK_HD RkmStepResult tpiRkmStep(const Ctx& c, const int inst, const RkmWork& w, const double h, double* cy) {
+SBK_HD RkmStepResult tpiRkmStep(const Ctx& c, const int inst, const RkmWork& w, const double h, double* cy, double* pf = nullptr) {
     const int nq = c.nq, ny = c.nq + c.nu;
     const long long uoff = (long long)nq*c.sStride;
 
     if (FRESH) {
         // f0 = f(y0): AbstractIntegratorRep.cpp:393 realizeStateDerivatives at the start of the step
-        tpiEvalDerivatives<LEAN>(c, inst, cy, w.f0, w.f0 + uoff, nullptr);
+        tpiEvalDerivatives<LEAN>(c, inst, cy, w.f0, w.f0 + uoff, nullptr, pf);
 #pragma unroll 8
         for (int i = 0; i < ny; ++i) {
             const double y0 = ldS(c, inst, w.y, i);
@@ -101,21 +101,21 @@ SBK_HD RkmStepResult tpiRkmStep(const Ctx& c, const int inst, const RkmWork& w, 
 #pragma unroll 8
         for (int i = 0; i < ny; ++i) stS(c, inst, w.y, i, ldS(c, inst, w.y0, i) + (h/3)*ldS(c, inst, w.f0, i));
     }
-    tpiEvalDerivatives<LEAN>(c, inst, cy, w.fa, w.fa + uoff, nullptr);                        // f1
+    tpiEvalDerivatives<LEAN>(c, inst, cy, w.fa, w.fa + uoff, nullptr, pf);                    // f1
 #pragma unroll 8
     for (int i = 0; i < ny; ++i)
         stS(c, inst, w.y, i, ldS(c, inst, w.y0, i) + (h/6)*(ldS(c, inst, w.f0, i) + ldS(c, inst, w.fa, i)));
-    tpiEvalDerivatives<LEAN>(c, inst, cy, w.fa, w.fa + uoff, nullptr);                        // f2 -> fa
+    tpiEvalDerivatives<LEAN>(c, inst, cy, w.fa, w.fa + uoff, nullptr, pf);                    // f2 -> fa
 #pragma unroll 8
     for (int i = 0; i < ny; ++i)
         stS(c, inst, w.y, i, ldS(c, inst, w.y0, i) + (h/8)*(ldS(c, inst, w.f0, i) + 3*ldS(c, inst, w.fa, i)));
-    tpiEvalDerivatives<LEAN>(c, inst, cy, w.fb, w.fb + uoff, nullptr);                        // f3 -> fb
+    tpiEvalDerivatives<LEAN>(c, inst, cy, w.fb, w.fb + uoff, nullptr, pf);                    // f3 -> fb
 #pragma unroll 8
     for (int i = 0; i < ny; ++i) {
         const double ys = ldS(c, inst, w.y0, i) + (h/2)*(ldS(c, inst, w.f0, i) - 3*ldS(c, inst, w.fa, i) + 4*ldS(c, inst, w.fb, i));
         stS(c, inst, w.ys, i, ys); stS(c, inst, w.y, i, ys);
     }
-    tpiEvalDerivatives<LEAN>(c, inst, cy, w.fa, w.fa + uoff, nullptr);                        // f4 -> fa
+    tpiEvalDerivatives<LEAN>(c, inst, cy, w.fa, w.fa + uoff, nullptr, pf);                    // f4 -> fa
 #pragma unroll 8
     for (int i = 0; i < ny; ++i) {
         const double y1 = ldS(c, inst, w.y0, i) + (h/6)*(ldS(c, inst, w.f0, i) + 4*ldS(c, inst, w.fb, i) + ldS(c, inst, w.fa, i));
@@ -167,7 +167,7 @@ struct AdaptiveState { double t, h, lastStep; int steps, attempts; };
 template <bool LEAN>
 SBK_HD void tpiRkmAdaptive(const Ctx& c, const int inst, const RkmWork& w, const StepLimits& lim, const double tFinal,
                            const int allowInterpolation, const int maxAttempts, AdaptiveState& st, double* cy,
-                           double& lastErr, int& nproj) {
+                           double& lastErr, int& nproj, double* pf = nullptr) {
     int budget = maxAttempts;
     while (st.t < tFinal && budget > 0) {
         bool fresh = true, ok = false; double t1 = st.t;
@@ -178,7 +178,7 @@ SBK_HD void tpiRkmAdaptive(const Ctx& c, const int inst, const RkmWork& w, const
             else if (tFinal > st.t + 1.001*st.h) t1 = st.t + st.h;
             else t1 = tFinal;
             const double hTry = t1 - st.t;
-            const RkmStepResult r = fresh ? tpiRkmStep<LEAN, true>(c, inst, w, hTry, cy) : tpiRkmStep<LEAN, false>(c, inst, w, hTry, cy);
+            const RkmStepResult r = fresh ? tpiRkmStep<LEAN, true>(c, inst, w, hTry, cy, pf) : tpiRkmStep<LEAN, false>(c, inst, w, hTry, cy, pf);
             fresh = false; ++st.attempts; --budget; nproj += r.projected; lastErr = r.errNorm;
             ok = adjustStepSize(r.errNorm, lim, limited, st.h);
         } while (!ok && budget > 0);

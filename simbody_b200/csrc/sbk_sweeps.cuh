@@ -92,7 +92,8 @@ struct Ctx {
     int nb, nq, nu, nquat;
     double gx, gy, gz;              // gravity vector g*d (Force_Gravity.cpp:532), 0 if none
     double*   cache;
-    long long cStride, cInstStride;
+    long long cStride, cInstStride, cSpan;   // cache offset of an instance: (inst >> cShift)*cSpan + (inst & cMask)*cInstStride
+    int cShift, cMask;
     long long sStride, sInstStride;
     const double* q; const double* u;
     double* qdot; double* udot; double* qdotdot; double* qerr;   // realize-path destinations (nullable)
@@ -192,9 +193,81 @@ struct CacheRef {     // accessor for one body's record
     SBK_HD ABI ldABI(int k) const { ABI P; P.M = ldS3(k); P.J = ldS3(k+6); P.F = ldM3(k+12); return P; }
     SBK_HD void stABI(int k, const ABI& P) const { stS3(k, P.M); stS3(k+6, P.J); stM3(k+12, P.F); }
 };
-SBK_HD CacheRef cacheOf(const Ctx& c, int inst, long long base) { CacheRef r; r.p = c.cache + base + (long long)inst*c.cInstStride; r.stride = c.cStride; return r; }
+// Generic instance offset: plain [field][N] records use cShift = 30 (offset = inst); the level-parallel
+// plan uses cShift = 0 (offset = inst*cSpan); the optional CTA-blocked layout uses cShift = 7.
+SBK_HD long long instOffset(const Ctx& c, int inst) { return (long long)(inst >> c.cShift)*c.cSpan + (long long)(inst & c.cMask)*c.cInstStride; }
+SBK_HD CacheRef cacheOf(const Ctx& c, int inst, long long base) { CacheRef r; r.p = c.cache + base + instOffset(c, inst); r.stride = c.cStride; return r; }
 SBK_HD double ldS(const Ctx& c, int inst, const double* a, int slot) { return gld(a + (long long)slot*c.sStride + (long long)inst*c.sInstStride); }
 SBK_HD void   stS(const Ctx& c, int inst, double* a, int slot, double v) { gst(a + (long long)slot*c.sStride + (long long)inst*c.sInstStride, v); }
+
+//----------------------------------------------------------------------------------------------
+// Asynchronous record prefetch (LEAN integrator path, device only).  A body step cannot start
+// before its record arrives from L2/HBM, and the sweeps expose that latency once per body.
+// Topology is static, so while body b computes, the rows body b+-1 will read are already being
+// copied global->shared with cp.async (LDGSTS) into this thread's slot column [row][thread]:
+// every lane copies and later reads only its own column, so no synchronisation is needed, no
+// registers are held, and every warp always has a whole record in flight (the bytes in flight
+// that Little's law asks for at HBM latency).  Rows beyond PF_CAP are read directly.
+//----------------------------------------------------------------------------------------------
+enum { PF_CAP = 40 };
+enum { SW_KIN = 0, SW_IN = 1, SW_OUT = 2 };
+SBK_HD void pfCopy8(double* dstSmem, const double* src) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dstSmem)), "l"(src) : "memory");
+#else
+    *dstSmem = *src;
+#endif
+}
+SBK_HD void pfCommit() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+SBK_HD void pfWait() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
+SBK_HD void pfRows(double* pf, const double* src, long long stride, int count, int& k) {
+    for (int i = 0; i < count && k < PF_CAP; ++i, ++k) pfCopy8(pf + k*SBK_CARRY_STRIDE, src + (long long)i*stride);
+}
+SBK_HD int dofOfJoint(int jt) { return jt == JT_FREE ? 6 : jt == JT_BALL ? 3 : jt == JT_UNIVERSAL ? 2 : 1; }
+SBK_HD int nqOfJoint(int jt)  { return jt == JT_FREE ? 7 : jt == JT_BALL ? 4 : jt == JT_UNIVERSAL ? 2 : 1; }
+// Row lists per sweep (must match pfIndex below).
+SBK_HD void pfIssue(const Ctx& c, const int inst, double* pf, const BodyConst& bc, const int sweep) {
+    int k = 0; const int d = dofOfJoint(bc.joint);
+    if (sweep == SW_KIN) {
+        pfRows(pf, c.q + (long long)bc.q0*c.sStride + (long long)inst*c.sInstStride, c.sStride, nqOfJoint(bc.joint), k);
+        pfRows(pf, c.u + (long long)bc.u0*c.sStride + (long long)inst*c.sInstStride, c.sStride, d, k);
+    } else {
+        const double* rec = c.cache + bc.cacheBase + instOffset(c, inst);
+        if (sweep == SW_IN) {
+            pfRows(pf, rec + (long long)F_L*c.cStride, c.cStride, F_ZB - F_L, k);
+            pfRows(pf, rec + (long long)F_H*c.cStride, c.cStride, 6*d, k);
+        } else {
+            pfRows(pf, rec + (long long)F_L*c.cStride, c.cStride, 3, k);
+            pfRows(pf, rec + (long long)F_ACOR*c.cStride, c.cStride, 6, k);
+            pfRows(pf, rec + (long long)F_H*c.cStride, c.cStride, 13*d + d*d, k);
+        }
+    }
+    pfCommit();
+}
+// field -> slot row, per sweep (folds at compile time: fields are constants after unrolling)
+template <int SWEEP> SBK_HD constexpr int pfIndex(int f) {
+    return SWEEP == SW_IN  ? (f < F_ZB ? f - F_L : (F_ZB - F_L) + (f - F_H))
+                           : (f < F_L + 3 ? f - F_L : (f < F_ACOR + 6 ? 3 + (f - F_ACOR) : 9 + (f - F_H)));
+}
+// Reads a record field from the prefetch slot when it is there, else from the cache in HBM.
+template <int SWEEP> struct RecReader {
+    CacheRef g; const double* slot;     // slot == nullptr: no prefetch
+    SBK_HD double ld(int f) const {
+        if (slot) { const int k = pfIndex<SWEEP>(f); if (k < PF_CAP) return slot[k*SBK_CARRY_STRIDE]; }
+        return g.ld(f);
+    }
+    SBK_HD V3 ld3(int f) const { return mk(ld(f), ld(f+1), ld(f+2)); }
+    SBK_HD SV ldSV(int f) const { SV r; r.w = ld3(f); r.v = ld3(f+3); return r; }
+    SBK_HD S3 ldS3(int f) const { S3 s; s.xx = ld(f); s.yy = ld(f+1); s.zz = ld(f+2); s.xy = ld(f+3); s.xz = ld(f+4); s.yz = ld(f+5); return s; }
+};
 
 SBK_HD M3 loadR(const double* X) { M3 R;
 #pragma unroll
@@ -458,14 +531,24 @@ SBK_HD void mobilityForces(const BodyConst& bc, const ForceConst* forces, const 
 // LEAN = true : integrator path; links ride in the carry when the tree order allows.
 
 template <int JT, bool LEAN>
-SBK_BODY void kinBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, const int inst, double* cy, double* qdotDst) {
+SBK_BODY void kinBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, const int inst, double* cy, double* qdotDst,
+                      double* pf = nullptr, const int nextBody = -1) {
     constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
     const CacheRef me = cacheOf(c, inst, bc.cacheBase);
     double q[NQ], u[d], qdot[NQ], qerr;
+    if (LEAN && pf) {
+        pfWait();
 #pragma unroll
-    for (int i = 0; i < NQ; ++i) q[i] = ldS(c, inst, c.q, bc.q0 + i);
+        for (int i = 0; i < NQ; ++i) q[i] = pf[i*SBK_CARRY_STRIDE];
 #pragma unroll
-    for (int i = 0; i < d; ++i)  u[i] = ldS(c, inst, c.u, bc.u0 + i);
+        for (int i = 0; i < d; ++i)  u[i] = pf[(NQ + i)*SBK_CARRY_STRIDE];
+        if (nextBody >= 1) pfIssue(c, inst, pf, c.bodies[nextBody], SW_KIN);
+    } else {
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) q[i] = ldS(c, inst, c.q, bc.q0 + i);
+#pragma unroll
+        for (int i = 0; i < d; ++i)  u[i] = ldS(c, inst, c.u, bc.u0 + i);
+    }
 
     M3 R_GP; V3 p_GP; SV V_GP;
     if (LEAN && (bc.flags & BF_PARENT_PREV)) cyLoadOut(cy, R_GP, p_GP, V_GP);
@@ -496,15 +579,23 @@ SBK_BODY void kinBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, co
 enum { IN_ABI = 1, IN_Z = 2, IN_BIAS = 4, IN_FORCES = 8 };
 
 template <int JT, int MODE, bool LEAN>
-SBK_BODY void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, const int inst, double* cy) {
+SBK_BODY void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, const int inst, double* cy,
+                         double* pf = nullptr, const int nextBody = -1) {
     constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
     const CacheRef me = cacheOf(c, inst, bc.cacheBase);
+    const bool usePf = LEAN && ((MODE & IN_ABI) != 0) && pf;
+    if (usePf) pfWait();
+    RecReader<SW_IN> in; in.g = me; in.slot = usePf ? pf : nullptr;
+    // every input up front (one wait); afterwards the slot is free for the next body's rows
     SV H[d];
 #pragma unroll
-    for (int j = 0; j < d; ++j) H[j] = me.ldSV(F_H + 6*j);
-    const V3 c_G = me.ld3(F_MK);
+    for (int j = 0; j < d; ++j) H[j] = in.ldSV(F_H + 6*j);
+    const V3 c_G = in.ld3(F_MK);
     V3 lMe = zero3();
-    if (LEAN) lMe = me.ld3(F_L);
+    if (LEAN) lMe = in.ld3(F_L);
+    S3 G_Gin; SV acorIn = zeroSV(), gyroIn = zeroSV();
+    if constexpr ((MODE & IN_ABI) != 0) { G_Gin = in.ldS3(F_MK + 3); acorIn = in.ldSV(F_ACOR); gyroIn = in.ldSV(F_GYRO); }
+    if (usePf && nextBody >= 1) pfIssue(c, inst, pf, c.bodies[nextBody], SW_IN);
     const bool linkToCache = !LEAN || !(bc.flags & BF_PARENT_PREV);
     // the adjacent child (index + 1), if any, left its links in the carry
     ABI cPP; SV czP = zeroSV(); V3 cl = zero3();
@@ -513,14 +604,13 @@ SBK_BODY void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex,
 
     AbiOut<d> ao; ao.zb = zeroSV();
     if constexpr ((MODE & IN_ABI) != 0) {
-        const S3 G_G = me.ldS3(F_MK + 3);
-        ABI P = abiFromRigid(bc.mass, c_G, G_G);
+        ABI P = abiFromRigid(bc.mass, c_G, G_Gin);
         for (int k = 0; k < bc.nchild; ++k) {
             if (k == 0 && haveCarryChild) { addInto(P, shiftABI(cPP, cl)); continue; }
             const CacheRef ch = cacheOf(c, inst, c.bodies[c.children[bc.childStart + k]].cacheBase);
             addInto(P, shiftABI(ch.ldABI(F_PPLUS), ch.ld3(F_L)));
         }
-        abiCore<d>(P, H, me.ldSV(F_ACOR), me.ldSV(F_GYRO), ao);
+        abiCore<d>(P, H, acorIn, gyroIn, ao);
         if (!ao.ok && c.status) {
 #if defined(__CUDA_ARCH__)
             atomicOr(c.status + inst, 2);
@@ -590,9 +680,12 @@ SBK_BODY void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex,
 // Sweep E for one body (base->tip): udot, A_GB, qdotdot.
 template <int JT, bool WITH_COR, bool LEAN>
 SBK_BODY void outwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, const int inst, double* cy,
-                         double* udotDst, double* qdotdotDst) {
+                         double* udotDst, double* qdotdotDst, double* pf = nullptr, const int nextBody = -1) {
     constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
-    const CacheRef me = cacheOf(c, inst, bc.cacheBase);
+    const CacheRef cref = cacheOf(c, inst, bc.cacheBase);
+    const bool usePf = LEAN && pf;
+    if (usePf) pfWait();
+    RecReader<SW_OUT> me; me.g = cref; me.slot = usePf ? pf : nullptr;
     SV A_GP;
     if (LEAN && (bc.flags & BF_PARENT_PREV)) A_GP = cyLoadA(cy);
     else A_GP = cacheOf(c, inst, bc.parentCacheBase).ldSV(F_AGB);
@@ -603,9 +696,11 @@ SBK_BODY void outwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex
     for (int i = 0; i < d*d; ++i) DI[i] = me.ld(fDI(d) + i);
     SV acor = zeroSV();
     if constexpr (WITH_COR) acor = me.ldSV(F_ACOR);
+    const V3 lMe = me.ld3(F_L);
+    if (usePf && nextBody >= 1) pfIssue(c, inst, pf, c.bodies[nextBody], SW_OUT);
     SV A;
-    accCore<d, WITH_COR>(H, G, DI, eps, me.ld3(F_L), A_GP, acor, udot, A);
-    if (!LEAN || (bc.flags & BF_STORE_LINK)) me.stSV(F_AGB, A);
+    accCore<d, WITH_COR>(H, G, DI, eps, lMe, A_GP, acor, udot, A);
+    if (!LEAN || (bc.flags & BF_STORE_LINK)) cref.stSV(F_AGB, A);
     if (LEAN) cyStoreA(cy, A);
     if (udotDst) {
 #pragma unroll
@@ -687,17 +782,18 @@ SBK_BODY void idInBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, c
         default: break;                                                             \
     }
 
-template <bool LEAN> SBK_HD void kinDispatch(const Ctx& c, int b, int inst, double* cy, double* qdotDst) {
+template <bool LEAN> SBK_HD void kinDispatch(const Ctx& c, int b, int inst, double* cy, double* qdotDst, double* pf = nullptr, int next = -1) {
     const BodyConst& bc = c.bodies[b];
-    SBK_DISPATCH_JOINT(bc.joint, (kinBody<JT, LEAN>(c, bc, b, inst, cy, qdotDst)));
+    SBK_DISPATCH_JOINT(bc.joint, (kinBody<JT, LEAN>(c, bc, b, inst, cy, qdotDst, pf, next)));
 }
-template <int MODE, bool LEAN> SBK_HD void inwardDispatch(const Ctx& c, int b, int inst, double* cy) {
+template <int MODE, bool LEAN> SBK_HD void inwardDispatch(const Ctx& c, int b, int inst, double* cy, double* pf = nullptr, int next = -1) {
     const BodyConst& bc = c.bodies[b];
-    SBK_DISPATCH_JOINT(bc.joint, (inwardBody<JT, MODE, LEAN>(c, bc, b, inst, cy)));
+    SBK_DISPATCH_JOINT(bc.joint, (inwardBody<JT, MODE, LEAN>(c, bc, b, inst, cy, pf, next)));
 }
-template <bool WITH_COR, bool LEAN> SBK_HD void outwardDispatch(const Ctx& c, int b, int inst, double* cy, double* udotDst, double* qddDst) {
+template <bool WITH_COR, bool LEAN> SBK_HD void outwardDispatch(const Ctx& c, int b, int inst, double* cy, double* udotDst, double* qddDst,
+                                                                double* pf = nullptr, int next = -1) {
     const BodyConst& bc = c.bodies[b];
-    SBK_DISPATCH_JOINT(bc.joint, (outwardBody<JT, WITH_COR, LEAN>(c, bc, b, inst, cy, udotDst, qddDst)));
+    SBK_DISPATCH_JOINT(bc.joint, (outwardBody<JT, WITH_COR, LEAN>(c, bc, b, inst, cy, udotDst, qddDst, pf, next)));
 }
 template <bool WITH_VEL> SBK_HD void idOutDispatch(const Ctx& c, int b, int inst) {
     const BodyConst& bc = c.bodies[b];
@@ -712,22 +808,28 @@ template <bool WITH_VEL> SBK_HD void idInDispatch(const Ctx& c, int b, int inst)
 // Per-instance drivers for the thread-per-instance plan: body index order is a valid
 // base->tip order because a parent's MobilizedBodyIndex is always smaller than its child's.
 //==============================================================================================
-template <bool LEAN> SBK_HD void tpiKinematics(const Ctx& c, int inst, double* cy, double* qdotDst) {
+// `pf` (nullable): this thread's prefetch slot column; when given (LEAN integrator path on the
+// device) every sweep keeps the next body's rows in flight while the current body computes.
+template <bool LEAN> SBK_HD void tpiKinematics(const Ctx& c, int inst, double* cy, double* qdotDst, double* pf = nullptr) {
     if (LEAN) { SV z0 = zeroSV(); cyStoreOut(cy, identity3(), zero3(), z0); }      // Ground's link for body 1
-    for (int b = 1; b < c.nb; ++b) kinDispatch<LEAN>(c, b, inst, cy, qdotDst);
+    if (LEAN && pf && c.nb > 1) pfIssue(c, inst, pf, c.bodies[1], SW_KIN);
+    for (int b = 1; b < c.nb; ++b) kinDispatch<LEAN>(c, b, inst, cy, qdotDst, pf, b + 1 < c.nb ? b + 1 : -1);
 }
-template <int MODE, bool LEAN> SBK_HD void tpiInward(const Ctx& c, int inst, double* cy) {
-    for (int b = c.nb - 1; b >= 1; --b) inwardDispatch<MODE, LEAN>(c, b, inst, cy);
+template <int MODE, bool LEAN> SBK_HD void tpiInward(const Ctx& c, int inst, double* cy, double* pf = nullptr) {
+    if (LEAN && ((MODE & IN_ABI) != 0) && pf && c.nb > 1) pfIssue(c, inst, pf, c.bodies[c.nb - 1], SW_IN);
+    for (int b = c.nb - 1; b >= 1; --b) inwardDispatch<MODE, LEAN>(c, b, inst, cy, pf, b - 1);
 }
-template <bool WITH_COR, bool LEAN> SBK_HD void tpiOutward(const Ctx& c, int inst, double* cy, double* udotDst, double* qddDst) {
+template <bool WITH_COR, bool LEAN> SBK_HD void tpiOutward(const Ctx& c, int inst, double* cy, double* udotDst, double* qddDst, double* pf = nullptr) {
     if (LEAN) cyStoreA(cy, zeroSV());                                               // Ground's A_GB
-    for (int b = 1; b < c.nb; ++b) outwardDispatch<WITH_COR, LEAN>(c, b, inst, cy, udotDst, qddDst);
+    if (LEAN && pf && c.nb > 1) pfIssue(c, inst, pf, c.bodies[1], SW_OUT);
+    for (int b = 1; b < c.nb; ++b) outwardDispatch<WITH_COR, LEAN>(c, b, inst, cy, udotDst, qddDst, pf, b + 1 < c.nb ? b + 1 : -1);
 }
 // One full derivative evaluation = System::realize(Acceleration) for the lowered system.
-template <bool LEAN> SBK_EVAL void tpiEvalDerivatives(const Ctx& c, int inst, double* cy, double* qdotDst, double* udotDst, double* qddDst) {
-    tpiKinematics<LEAN>(c, inst, cy, qdotDst);
-    tpiInward<IN_ABI | IN_Z | IN_BIAS | IN_FORCES, LEAN>(c, inst, cy);
-    tpiOutward<true, LEAN>(c, inst, cy, udotDst, qddDst);
+template <bool LEAN> SBK_EVAL void tpiEvalDerivatives(const Ctx& c, int inst, double* cy, double* qdotDst, double* udotDst, double* qddDst,
+                                                      double* pf = nullptr) {
+    tpiKinematics<LEAN>(c, inst, cy, qdotDst, pf);
+    tpiInward<IN_ABI | IN_Z | IN_BIAS | IN_FORCES, LEAN>(c, inst, cy, pf);
+    tpiOutward<true, LEAN>(c, inst, cy, udotDst, qddDst, pf);
 }
 
 } // namespace sbkd
