@@ -20,6 +20,9 @@ namespace {
 #ifndef SBK_TPI_MINBLOCKS
 #define SBK_TPI_MINBLOCKS 4
 #endif
+#ifndef SBK_HEAVY_MINB
+#define SBK_HEAVY_MINB 2
+#endif
 constexpr int TPI_THREADS = SBK_TPI_THREADS;
 constexpr int SBK_CARRY_STRIDE_DEVICE = 128;
 
@@ -193,7 +196,7 @@ cudaError_t launchOp(const KArgs& a, cudaStream_t stream) {
     if constexpr (OP == OP_RKM || OP == OP_RKM_ADAPT) {
         if (a.lightJoints) return a.stageInSmem ? go(tpiKernel<OP, true, 4>) : go(tpiKernel<OP, false, 4>);
     }
-    return a.stageInSmem ? go(tpiKernel<OP, true, 2>) : go(tpiKernel<OP, false, 2>);
+    return a.stageInSmem ? go(tpiKernel<OP, true, SBK_HEAVY_MINB>) : go(tpiKernel<OP, false, SBK_HEAVY_MINB>);
 }
 
 //==============================================================================================

@@ -595,6 +595,17 @@ SBK_BODY void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex,
     if (LEAN) lMe = in.ld3(F_L);
     S3 G_Gin; SV acorIn = zeroSV(), gyroIn = zeroSV();
     if constexpr ((MODE & IN_ABI) != 0) { G_Gin = in.ldS3(F_MK + 3); acorIn = in.ldSV(F_ACOR); gyroIn = in.ldSV(F_GYRO); }
+    // q, u for the spring/damper elements are requested here, together with the record, so that the
+    // body step waits on global memory once (not once more when the forces are evaluated)
+    double qF[NQ], uF[d];
+    if constexpr ((MODE & IN_FORCES) != 0) {
+        if (bc.nforce > 0) {
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) qF[i] = ldS(c, inst, c.q, bc.q0 + i);
+#pragma unroll
+            for (int i = 0; i < d; ++i)  uF[i] = ldS(c, inst, c.u, bc.u0 + i);
+        }
+    }
     if (usePf && nextBody >= 1) pfIssue(c, inst, pf, c.bodies[nextBody], SW_IN);
     const bool linkToCache = !LEAN || !(bc.flags & BF_PARENT_PREV);
     // the adjacent child (index + 1), if any, left its links in the carry
@@ -636,14 +647,7 @@ SBK_BODY void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex,
         SV F = zeroSV(); double f[d];
         if constexpr ((MODE & IN_FORCES) != 0) {
             F = gravityForce(bc.mass, c_G, c.gx, c.gy, c.gz);
-            double q[NQ], u[d];
-            if (bc.nforce > 0) {
-#pragma unroll
-                for (int i = 0; i < NQ; ++i) q[i] = ldS(c, inst, c.q, bc.q0 + i);
-#pragma unroll
-                for (int i = 0; i < d; ++i)  u[i] = ldS(c, inst, c.u, bc.u0 + i);
-            }
-            mobilityForces<d>(bc, c.forces, q, u, f);
+            mobilityForces<d>(bc, c.forces, qF, uF, f);
             if (c.fmobOut) {
 #pragma unroll
                 for (int j = 0; j < d; ++j) stS(c, inst, c.fmobOut, bc.u0 + j, f[j]);
