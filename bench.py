@@ -35,8 +35,11 @@ WORKLOADS = {
     "branched_tree1000_256": dict(model="branched_tree", n=1000, batch=256, h=5e-4, q_scale=0.5),
 }
 # measured DRAM bytes per instance-step (ncu --set full, profiles/r1_prof_*.txt): launch traffic / (N * steps)
-NCU_TRAFFIC_PER_INSTANCE_STEP = {"double_pendulum_1M": 5.588e7 / (1048576 * 20), "humanoid30_64k": 1.746e10 / 65536,
+NCU_TRAFFIC_PER_INSTANCE_STEP = {"double_pendulum_1M": 4.921e7 / (1048576 * 20), "humanoid30_64k": 1.332e10 / 65536,
                                  "pin_chain50_64k": 1.429e10 / 65536}
+# sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active of the same captures (the hardware's own
+# view of FP64-pipe utilisation; roofline.frac below uses the reference's ALGORITHMIC flop count instead)
+NCU_FP64_PIPE_ACTIVE = {"double_pendulum_1M": 0.753, "humanoid30_64k": 0.102, "pin_chain50_64k": 0.138}
 F_EVAL = {"PIN": 1180.0, "SLIDER": 1130.0, "UNIVERSAL": 1710.0, "BALL": 2060.0, "FREE": 3800.0}
 
 
@@ -242,6 +245,9 @@ def main():
                 "kernel": {1: "tpiKernel<OP_RKM> (thread-per-instance, LEAN records)", 2: "fusedRkmKernel (register-resident)",
                            3: "lpKernel<OP_RKM> (level-parallel)"}[r["plan"]],
                 "kernel_ms_last_launch": r["kernel_ms_last"],
+                "fp64_pipe_active_ncu": NCU_FP64_PIPE_ACTIVE.get(args.workload),
+                "hbm_traffic_frac_ncu": (NCU_TRAFFIC_PER_INSTANCE_STEP.get(args.workload, 0) * per_gpu_rate / 1e9 / peaks["hbm_gbs"])
+                                        if peaks.get("hbm_gbs") else None,
                 # dram__bytes_read+write per launch from the committed ncu captures (profiles/), scaled to this launch
                 "traffic": NCU_TRAFFIC_PER_INSTANCE_STEP.get(args.workload, 0) * r["N"] * r["spl"] or None}
 
