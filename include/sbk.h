@@ -249,6 +249,11 @@ double  sbk_last_kernel_ms(const sbk_batch*);
  * flops = 2 * 8 * iters * blocks * threads.                                               */
 int sbk_dfma_probe(int device, int blocks, int threads, int iters, double* ms_out);
 
+/* Diagnostics: time `sweeps` passes of the thread-per-instance record access pattern (nb records
+ * of rows_in loaded + rows_out stored doubles per instance, [row][N] layout) with no arithmetic;
+ * bytes moved = 8*n*nb*(rows_in+rows_out)*sweeps.  min_blocks 2 or 4 selects the occupancy.     */
+int sbk_mem_pattern_probe(int device, int n, int nb, int rows_in, int rows_out, int sweeps, int min_blocks, double* ms_out);
+
 #ifdef __cplusplus
 }
 #endif

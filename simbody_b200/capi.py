@@ -88,6 +88,7 @@ SYMBOLS = {
     "sbk_get_status": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int32), c_int64_p]),
     "sbk_launch_count": (ctypes.c_int64, [_P]),
     "sbk_last_kernel_ms": (ctypes.c_double, [_P]),
+    "sbk_mem_pattern_probe": (ctypes.c_int, [ctypes.c_int] * 7 + [c_double_p]),
     "sbk_dfma_probe": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p]),
 }
 

@@ -636,6 +636,26 @@ double sbk_last_kernel_ms(const sbk_batch* b) {
     return ms;
 }
 
+// Memory-pattern probe (diagnostics): GB/s delivered for the record access pattern of plan 1.
+int sbk_mem_pattern_probe(int device, int n, int nb, int rows_in, int rows_out, int sweeps, int min_blocks, double* ms_out) {
+    if (cudaSetDevice(device) != cudaSuccess) return fail(SBK_ERR_CUDA, "cudaSetDevice failed");
+    if (rows_in > 48 || rows_in < 0 || rows_out < 0) return fail(SBK_ERR_ARG, "rows_in must be 0..48");
+    double* d = nullptr; const size_t doubles = (size_t)nb*(rows_in + rows_out)*n;
+    CUDA_TRY(cudaMalloc(&d, doubles*sizeof(double)));
+    cudaMemset(d, 0, doubles*sizeof(double));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    launchMemPattern(d, n, nb, rows_in, rows_out, 1, min_blocks, 0);
+    cudaEventRecord(e0, 0);
+    cudaError_t le = launchMemPattern(d, n, nb, rows_in, rows_out, sweeps, min_blocks, 0);
+    cudaEventRecord(e1, 0);
+    cudaError_t se = cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    if (le != cudaSuccess || se != cudaSuccess) return fail(SBK_ERR_CUDA, "mem pattern probe failed");
+    if (ms_out) *ms_out = ms;
+    return SBK_OK;
+}
+
 // FP64 roofline probe (bench only): executes blocks*threads*iters*8 DFMAs on the batch's device.
 int sbk_dfma_probe(int device, int blocks, int threads, int iters, double* ms_out) {
     if (cudaSetDevice(device) != cudaSuccess) return fail(SBK_ERR_CUDA, "cudaSetDevice failed");

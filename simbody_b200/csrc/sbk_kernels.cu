@@ -422,6 +422,29 @@ __global__ void energyKernel(const KArgs a, double* ke, double* pe) {
     if (pe) pe[k] = pot;
 }
 
+// Memory-pattern probe (bench/diagnostics only): one thread per instance walks `nb` records of
+// `rowsIn` + `rowsOut` rows in the [row][N] layout of the thread-per-instance plan, loading rowsIn
+// doubles and storing rowsOut doubles per record with no arithmetic to speak of.  It measures what
+// the memory system delivers for the plan's access pattern at a given occupancy.
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) memPatternKernel(double* buf, int N, int nb, int rowsIn, int rowsOut, int sweeps) {
+    const int k = blockIdx.x*blockDim.x + threadIdx.x;
+    if (k >= N) return;
+    const long long rec = (long long)(rowsIn + rowsOut)*N;
+    double acc = 0;
+    for (int s = 0; s < sweeps; ++s)
+        for (int b = 0; b < nb; ++b) {
+            double* p = buf + (long long)b*rec + k;
+            double v[48];
+#pragma unroll
+            for (int i = 0; i < 48; ++i) v[i] = (i < rowsIn) ? __ldcg(p + (long long)i*N) : 0.0;
+#pragma unroll
+            for (int i = 0; i < 48; ++i) acc += v[i];
+            for (int i = 0; i < rowsOut; ++i) __stcg(p + (long long)(rowsIn + i)*N, acc + i);
+        }
+    if (acc == 12345.678) buf[k] = acc;
+}
+
 __global__ void dfmaProbeKernel(double* out, int iters) {
     double a0 = 1.0 + threadIdx.x*1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3,
            a4 = a0 + 4e-3, a5 = a0 + 5e-3, a6 = a0 + 6e-3, a7 = a0 + 7e-3;
@@ -502,6 +525,12 @@ cudaError_t launchGatherBodyField(const KArgs& a, int fieldOffset, int width, do
 }
 cudaError_t launchEnergy(const KArgs& a, double* ke, double* pe, cudaStream_t stream) {
     energyKernel<<<(a.N + 127)/128, 128, 0, stream>>>(a, ke, pe);
+    return cudaGetLastError();
+}
+cudaError_t launchMemPattern(double* buf, int N, int nb, int rowsIn, int rowsOut, int sweeps, int minBlocks, cudaStream_t stream) {
+    const int grid = (N + 127)/128;
+    if (minBlocks >= 4) memPatternKernel<4><<<grid, 128, 0, stream>>>(buf, N, nb, rowsIn, rowsOut, sweeps);
+    else                memPatternKernel<2><<<grid, 128, 0, stream>>>(buf, N, nb, rowsIn, rowsOut, sweeps);
     return cudaGetLastError();
 }
 cudaError_t launchDfmaProbe(double* out, int iters, int blocks, int threads, cudaStream_t stream) {

@@ -70,6 +70,8 @@ cudaError_t launchTranspose(const double* src, double* dst, int rows, int cols, 
 cudaError_t launchGatherBodyField(const KArgs& a, int fieldOffset, int width, double* out, cudaStream_t stream);
 // Kinetic / potential energy per instance from the realized records (ke, pe: device [N], nullable).
 cudaError_t launchEnergy(const KArgs& a, double* ke, double* pe, cudaStream_t stream);
+// Memory-pattern probe for the thread-per-instance record layout (diagnostics).
+cudaError_t launchMemPattern(double* buf, int N, int nb, int rowsIn, int rowsOut, int sweeps, int minBlocks, cudaStream_t stream);
 // FP64 FMA throughput probe: returns flops executed; used by bench.py to measure the FP64 roofline.
 cudaError_t launchDfmaProbe(double* out, int iters, int blocks, int threads, cudaStream_t stream);
 
