@@ -174,15 +174,12 @@ static int configurePlan(sbk_batch* b, int plan) {
         a.cStride = t->nb; a.cInstStride = 0; a.cSpan = (long long)CACHE_RECORD_MAX*t->nb; a.cShift = 0; a.cMask = 0;
         cacheDoubles = a.cSpan*n;
     } else {
-        // field-major over the whole batch: [record field][N].  (Blocking the records by 128-instance
-        // CTA -- [block][field][lane], one contiguous span per CTA -- was measured and changes nothing:
-        // the plan is bound by L2/HBM throughput, not by DRAM-page or TLB locality.  SBK_BLOCKED=1 selects it.)
+        // CTA-blocked records: [block of 128 instances][record field][lane]; the integrator kernels use the
+        // row stride 128 as a compile-time constant, the API kernels read it from the context.
         long long off = 0;
-        const char* eb = getenv("SBK_BLOCKED"); const bool blocked = eb && atoi(eb) != 0;
-        const long long g = blocked ? 128 : n;
-        for (int i = 0; i < t->nb; ++i) { bodies[i].cacheBase = off*g; off += (i == 0) ? F_H : cacheRecordSize(t->nuOf[i]); }
-        if (blocked) { a.cStride = 128; a.cInstStride = 1; a.cSpan = off*128; a.cShift = 7; a.cMask = 127; cacheDoubles = off*128*(((long long)n + 127)/128); }
-        else         { a.cStride = n;   a.cInstStride = 1; a.cSpan = 0;       a.cShift = 30; a.cMask = 0x3fffffff; cacheDoubles = off*n; }
+        for (int i = 0; i < t->nb; ++i) { bodies[i].cacheBase = off*BLK_LANES; off += (i == 0) ? F_H : cacheRecordSize(t->nuOf[i]); }
+        a.cStride = BLK_LANES; a.cInstStride = 1; a.cSpan = off*BLK_LANES; a.cShift = 7; a.cMask = BLK_LANES - 1;
+        cacheDoubles = off*BLK_LANES*(((long long)n + BLK_LANES - 1)/BLK_LANES);
         b->recTotal = off;
     }
     for (int i = 0; i < t->nb; ++i) bodies[i].parentCacheBase = bodies[bodies[i].parent].cacheBase;
@@ -201,7 +198,6 @@ static int configurePlan(sbk_batch* b, int plan) {
     a.tableBytes = (uint32_t)blob.size(); a.childrenOff = (uint32_t)bodiesBytes; a.forcesOff = (uint32_t)(bodiesBytes + childBytes);
     a.levelOrderOff = (uint32_t)(bodiesBytes + childBytes + forceBytes); a.levelStartOff = a.levelOrderOff + (uint32_t)orderBytes;
     a.nlevels = t->nlevels; a.plan = plan;
-    { const char* e = getenv("SBK_PREFETCH"); a.prefetch = e ? atoi(e) : 0; }
     a.lightJoints = 1;
     for (int i = 1; i < t->nb; ++i) if (t->nuOf[i] > 2) a.lightJoints = 0;
     { const char* e = getenv("SBK_LIGHT"); if (e) a.lightJoints = atoi(e); }     // tuning override
@@ -247,7 +243,9 @@ sbk_batch* sbk_batch_create(const sbk_topology* t, int n, int device, void* stre
     auto dalloc = [&](double** p, size_t doubles) { if (ok && cudaMalloc(p, std::max<size_t>(doubles, 1)*sizeof(double)) != cudaSuccess) ok = false;
                                                     if (ok) cudaMemsetAsync(*p, 0, std::max<size_t>(doubles, 1)*sizeof(double), b->stream); };
     dalloc(&a.y, ny*N); dalloc(&a.ydot, ny*N); dalloc(&a.qdotdot, (size_t)t->nq*N); dalloc(&a.qerr, (size_t)std::max(t->nquat, 1)*N);
-    dalloc(&a.y0, ny*N); dalloc(&a.f0, ny*N); dalloc(&a.fa, ny*N); dalloc(&a.fb, ny*N); dalloc(&a.ys, ny*N);
+    const size_t Nb = (N + BLK_LANES - 1)/BLK_LANES*BLK_LANES;        // integrator vectors are CTA-blocked: [block][slot][lane]
+    dalloc(&a.yb, ny*Nb);
+    dalloc(&a.y0, ny*Nb); dalloc(&a.f0, ny*Nb); dalloc(&a.fa, ny*Nb); dalloc(&a.fb, ny*Nb); dalloc(&a.ys, ny*Nb);
     dalloc(&a.tcur, N); dalloc(&a.errNorm, N);
     dalloc(&b->dOpA, (size_t)t->nu*N); dalloc(&b->dOpB, (size_t)t->nu*N); dalloc(&b->dOpOut, (size_t)t->nu*N); dalloc(&b->dOpF, (size_t)t->nb*6*N);
     if (ok && cudaMalloc(&a.status, N*sizeof(int)) != cudaSuccess) ok = false;
@@ -271,7 +269,7 @@ void sbk_batch_destroy(sbk_batch* b) {
     if (!b) return;
     cudaSetDevice(b->device);
     KArgs& a = b->a;
-    void* ptrs[] = {b->dTables, a.cache, a.y, a.ydot, a.qdotdot, a.qerr, a.y0, a.f0, a.fa, a.fb, a.ys, a.tcur, a.errNorm,
+    void* ptrs[] = {b->dTables, a.cache, a.y, a.yb, a.ydot, a.qdotdot, a.qerr, a.y0, a.f0, a.fa, a.fb, a.ys, a.tcur, a.errNorm,
                     b->dOpA, b->dOpB, b->dOpOut, b->dOpF, a.status, a.projCount, b->dScratch,
                     a.hcur, a.lastStep, a.stepsTaken, a.attempts};
     for (void* p : ptrs) if (p) cudaFree(p);

@@ -59,7 +59,7 @@ __device__ __forceinline__ void fillCtx(Ctx& c, const KArgs& a, const unsigned c
     c.nb = a.nb; c.nq = a.nq; c.nu = a.nu; c.nquat = a.nquat;
     c.gx = a.gx; c.gy = a.gy; c.gz = a.gz;
     c.cache = a.cache; c.cStride = a.cStride; c.cInstStride = a.cInstStride; c.cSpan = a.cSpan; c.cShift = a.cShift; c.cMask = a.cMask;
-    c.sStride = a.N; c.sInstStride = 1;
+    c.sStride = a.N; c.sInstStride = 1; c.sSpan = (long long)(a.nq + a.nu)*BLK_LANES;
     c.q = a.y; c.u = a.y + (long long)a.nq*a.N;
     c.qdot = a.ydot; c.udot = a.ydot ? a.ydot + (long long)a.nq*a.N : nullptr;
     c.qdotdot = a.qdotdot; c.qerr = a.qerr;
@@ -67,6 +67,18 @@ __device__ __forceinline__ void fillCtx(Ctx& c, const KArgs& a, const unsigned c
     c.vecIn = a.vecIn; c.vecOut = a.vecOut;
     c.status = a.status;
     if (integrator) { c.qdotdot = nullptr; c.qerr = nullptr; c.fmobOut = nullptr; c.FbodyOut = nullptr; }
+}
+// Thread-per-instance integrator kernels work on a CTA-blocked copy of the state ([block][slot][lane]).
+__device__ __forceinline__ void useBlockedState(Ctx& c, const KArgs& a) { c.q = a.yb; c.u = a.yb + (long long)a.nq*BLK_LANES; }
+__device__ __forceinline__ void stateToBlocked(const Ctx& c, const KArgs& a, int inst) {
+    const int ny = a.nq + a.nu;
+#pragma unroll 8
+    for (int i = 0; i < ny; ++i) a.yb[stateIndex<true>(c, inst, i)] = __ldcg(a.y + (long long)i*a.N + inst);
+}
+__device__ __forceinline__ void stateFromBlocked(const Ctx& c, const KArgs& a, int inst) {
+    const int ny = a.nq + a.nu;
+#pragma unroll 8
+    for (int i = 0; i < ny; ++i) __stcg(a.y + (long long)i*a.N + inst, a.yb[stateIndex<true>(c, inst, i)]);
 }
 
 // MINB = resident CTAs per SM the register allocation is sized for: 4 (128 registers) suits
@@ -79,18 +91,17 @@ __global__ void __launch_bounds__(TPI_THREADS, MINB) tpiKernel(const KArgs a) {
     __shared__ Ctx sctx;                      // ONE context per CTA, read with LDS by every body step
     const unsigned char* tables = a.tables;
     if constexpr (STAGE) { tmaStage(smem, a.tables, a.tableBytes, &mbar); tables = smem; }
-    if (threadIdx.x == 0) fillCtx(sctx, a, tables, OP == OP_RKM || OP == OP_RKM_ADAPT);
+    if (threadIdx.x == 0) {
+        fillCtx(sctx, a, tables, OP == OP_RKM || OP == OP_RKM_ADAPT);
+        if (OP == OP_RKM || OP == OP_RKM_ADAPT) useBlockedState(sctx, a);
+    }
     __syncthreads();
     const int inst = blockIdx.x*blockDim.x + threadIdx.x;
     if (inst >= a.N) return;
     const Ctx& c = sctx;
     // LEAN carry: a [CARRY_ROWS][128] block of shared memory behind the staged tables
     double* cy = nullptr;
-    double* pf = nullptr;                     // prefetch slot column [PF_CAP][128] behind the carry (255-register variant only)
-    if constexpr (OP == OP_RKM || OP == OP_RKM_ADAPT) {
-        cy = reinterpret_cast<double*>(smem + (STAGE ? a.tableBytes : 0)) + threadIdx.x;
-        if (a.prefetch) pf = cy + CARRY_ROWS*TPI_THREADS;
-    }
+    if constexpr (OP == OP_RKM || OP == OP_RKM_ADAPT) cy = reinterpret_cast<double*>(smem + (STAGE ? a.tableBytes : 0)) + threadIdx.x;
 
     if constexpr (OP == OP_KIN) {
         tpiKinematics<false>(c, inst, cy, c.qdot);
@@ -112,23 +123,27 @@ __global__ void __launch_bounds__(TPI_THREADS, MINB) tpiKernel(const KArgs a) {
         for (int b = c.nb - 1; b >= 1; --b) idInDispatch<true>(c, b, inst);
     } else if constexpr (OP == OP_RKM) {
         RkmWork w;
-        w.y = a.y; w.y0 = a.y0; w.f0 = a.f0; w.fa = a.fa; w.fb = a.fb; w.ys = a.ys;
+        w.y = a.yb; w.y0 = a.y0; w.f0 = a.f0; w.fa = a.fa; w.fb = a.fb; w.ys = a.ys;
         w.accuracy = a.accuracy; w.consTol = a.consTol; w.useInfNorm = a.useInfNorm; w.projectEveryStep = a.projectEveryStep;
         RkmStepResult r; r.errNorm = 0; r.projected = 0;
         int nproj = 0; double t = a.tcur[inst];
-        for (int s = 0; s < a.nsteps; ++s) { r = tpiRkmStep<true>(c, inst, w, a.h, cy, pf); nproj += r.projected; t += a.h; }
+        stateToBlocked(c, a, inst);
+        for (int s = 0; s < a.nsteps; ++s) { r = tpiRkmStep<true>(c, inst, w, a.h, cy); nproj += r.projected; t += a.h; }
+        stateFromBlocked(c, a, inst);
         a.tcur[inst] = t;
         a.errNorm[inst] = r.errNorm;
         a.projCount[inst] += nproj;
         if (a.status && !(r.errNorm == r.errNorm)) atomicOr(a.status + inst, 1);   // NaN error norm
     } else if constexpr (OP == OP_RKM_ADAPT) {
         RkmWork w;
-        w.y = a.y; w.y0 = a.y0; w.f0 = a.f0; w.fa = a.fa; w.fb = a.fb; w.ys = a.ys;
+        w.y = a.yb; w.y0 = a.y0; w.f0 = a.f0; w.fa = a.fa; w.fb = a.fb; w.ys = a.ys;
         w.accuracy = a.accuracy; w.consTol = a.consTol; w.useInfNorm = a.useInfNorm; w.projectEveryStep = a.projectEveryStep;
+        stateToBlocked(c, a, inst);
         StepLimits lim; lim.accuracy = a.accuracy; lim.minStep = a.minStep; lim.maxStep = a.maxStep;
         AdaptiveState st; st.t = a.tcur[inst]; st.h = a.hcur[inst]; st.lastStep = a.lastStep[inst]; st.steps = 0; st.attempts = 0;
         double lastErr = a.errNorm[inst]; int nproj = 0;
-        tpiRkmAdaptive<true>(c, inst, w, lim, a.tFinal, a.allowInterp, a.maxAttempts, st, cy, lastErr, nproj, pf);
+        tpiRkmAdaptive<true>(c, inst, w, lim, a.tFinal, a.allowInterp, a.maxAttempts, st, cy, lastErr, nproj);
+        stateFromBlocked(c, a, inst);
         a.tcur[inst] = st.t; a.hcur[inst] = st.h; a.lastStep[inst] = st.lastStep;
         a.stepsTaken[inst] += st.steps; a.attempts[inst] += st.attempts;
         a.errNorm[inst] = lastErr; a.projCount[inst] += nproj;
@@ -184,8 +199,7 @@ template <int OP>
 cudaError_t launchOp(const KArgs& a, cudaStream_t stream) {
     static_assert(TPI_THREADS == SBK_CARRY_STRIDE_DEVICE, "carry columns are laid out for 128-thread CTAs");
     const int grid = (a.N + TPI_THREADS - 1)/TPI_THREADS;
-    const size_t carryBytes = (OP == OP_RKM || OP == OP_RKM_ADAPT)
-        ? (size_t)(CARRY_ROWS + (a.prefetch ? PF_CAP : 0))*TPI_THREADS*sizeof(double) : 0;
+    const size_t carryBytes = (OP == OP_RKM || OP == OP_RKM_ADAPT) ? (size_t)CARRY_ROWS*TPI_THREADS*sizeof(double) : 0;
     const size_t smemBytes = (a.stageInSmem ? a.tableBytes : 0) + carryBytes;
     auto go = [&](auto kernel) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
@@ -239,9 +253,9 @@ __device__ double lpErrorNorm(const Ctx& c, const int inst, const KArgs& a, doub
     const int nq = c.nq, nu = c.nu; const bool inf = a.useInfNorm != 0;
     double uAcc = 0, qAcc = 0;
     for (int i = threadIdx.x; i < nu; i += LP_THREADS) {
-        const double u0 = fabs(ldS(c, inst, a.y0, nq + i));
+        const double u0 = fabs(ldS<false>(c, inst, a.y0, nq + i));
         const double sc = (u0*1.0 > 1.0) ? 1.0/u0 : 1.0;
-        const double v = sc*ldS(c, inst, a.ys, nq + i);
+        const double v = sc*ldS<false>(c, inst, a.ys, nq + i);
         if (inf) uAcc = fmax(uAcc, fabs(v)); else uAcc += v*v;
     }
     for (int b = 1 + threadIdx.x; b < c.nb; b += LP_THREADS) {
@@ -249,14 +263,14 @@ __device__ double lpErrorNorm(const Ctx& c, const int inst, const KArgs& a, doub
         int first = 0;
         if (bc.joint == JT_BALL || bc.joint == JT_FREE) {
             double q[4], e[4], o[4];
-            for (int i = 0; i < 4; ++i) { q[i] = ldS(c, inst, a.y, bc.q0 + i); e[i] = ldS(c, inst, a.ys, bc.q0 + i); }
+            for (int i = 0; i < 4; ++i) { q[i] = ldS<false>(c, inst, a.y, bc.q0 + i); e[i] = ldS<false>(c, inst, a.ys, bc.q0 + i); }
             const V3 du = quatNInvTimes(q, e);
             quatNTimes(q, du, o);
             for (int i = 0; i < 4; ++i) { if (inf) qAcc = fmax(qAcc, fabs(o[i])); else qAcc += o[i]*o[i]; }
             first = 4;
         }
         const int nqb = bc.joint == JT_FREE ? 7 : bc.joint == JT_BALL ? 4 : bc.joint == JT_UNIVERSAL ? 2 : 1;
-        for (int i = first; i < nqb; ++i) { const double v = ldS(c, inst, a.ys, bc.q0 + i); if (inf) qAcc = fmax(qAcc, fabs(v)); else qAcc += v*v; }
+        for (int i = first; i < nqb; ++i) { const double v = ldS<false>(c, inst, a.ys, bc.q0 + i); if (inf) qAcc = fmax(qAcc, fabs(v)); else qAcc += v*v; }
     }
     uAcc = blockReduce(uAcc, inf, red); qAcc = blockReduce(qAcc, inf, red);
     const double qNorm = inf ? qAcc : (nq ? sqrt(qAcc/nq) : 0.0), uNorm = inf ? uAcc : (nu ? sqrt(uAcc/nu) : 0.0);
@@ -297,24 +311,24 @@ __global__ void __launch_bounds__(LP_THREADS, 2) lpKernel(const KArgs a) {
         const double h = a.h; double err = 0; int nproj = 0;
         for (int s = 0; s < a.nsteps; ++s) {
             lpEval(c, inst, L, a.f0, a.f0 + uoff, nullptr);
-            for (int i = threadIdx.x; i < ny; i += LP_THREADS) { const double y0 = ldS(c, inst, a.y, i); stS(c, inst, a.y0, i, y0); stS(c, inst, a.y, i, y0 + (h/3)*ldS(c, inst, a.f0, i)); }
+            for (int i = threadIdx.x; i < ny; i += LP_THREADS) { const double y0 = ldS<false>(c, inst, a.y, i); stS<false>(c, inst, a.y0, i, y0); stS<false>(c, inst, a.y, i, y0 + (h/3)*ldS<false>(c, inst, a.f0, i)); }
             __syncthreads();
             lpEval(c, inst, L, a.fa, a.fa + uoff, nullptr);
-            for (int i = threadIdx.x; i < ny; i += LP_THREADS) stS(c, inst, a.y, i, ldS(c, inst, a.y0, i) + (h/6)*(ldS(c, inst, a.f0, i) + ldS(c, inst, a.fa, i)));
+            for (int i = threadIdx.x; i < ny; i += LP_THREADS) stS<false>(c, inst, a.y, i, ldS<false>(c, inst, a.y0, i) + (h/6)*(ldS<false>(c, inst, a.f0, i) + ldS<false>(c, inst, a.fa, i)));
             __syncthreads();
             lpEval(c, inst, L, a.fa, a.fa + uoff, nullptr);
-            for (int i = threadIdx.x; i < ny; i += LP_THREADS) stS(c, inst, a.y, i, ldS(c, inst, a.y0, i) + (h/8)*(ldS(c, inst, a.f0, i) + 3*ldS(c, inst, a.fa, i)));
+            for (int i = threadIdx.x; i < ny; i += LP_THREADS) stS<false>(c, inst, a.y, i, ldS<false>(c, inst, a.y0, i) + (h/8)*(ldS<false>(c, inst, a.f0, i) + 3*ldS<false>(c, inst, a.fa, i)));
             __syncthreads();
             lpEval(c, inst, L, a.fb, a.fb + uoff, nullptr);
             for (int i = threadIdx.x; i < ny; i += LP_THREADS) {
-                const double ys = ldS(c, inst, a.y0, i) + (h/2)*(ldS(c, inst, a.f0, i) - 3*ldS(c, inst, a.fa, i) + 4*ldS(c, inst, a.fb, i));
-                stS(c, inst, a.ys, i, ys); stS(c, inst, a.y, i, ys);
+                const double ys = ldS<false>(c, inst, a.y0, i) + (h/2)*(ldS<false>(c, inst, a.f0, i) - 3*ldS<false>(c, inst, a.fa, i) + 4*ldS<false>(c, inst, a.fb, i));
+                stS<false>(c, inst, a.ys, i, ys); stS<false>(c, inst, a.y, i, ys);
             }
             __syncthreads();
             lpEval(c, inst, L, a.fa, a.fa + uoff, nullptr);
             for (int i = threadIdx.x; i < ny; i += LP_THREADS) {
-                const double y1 = ldS(c, inst, a.y0, i) + (h/6)*(ldS(c, inst, a.f0, i) + 4*ldS(c, inst, a.fb, i) + ldS(c, inst, a.fa, i));
-                stS(c, inst, a.y, i, y1); stS(c, inst, a.ys, i, 0.2*fabs(y1 - ldS(c, inst, a.ys, i)));
+                const double y1 = ldS<false>(c, inst, a.y0, i) + (h/6)*(ldS<false>(c, inst, a.f0, i) + 4*ldS<false>(c, inst, a.fb, i) + ldS<false>(c, inst, a.fa, i));
+                stS<false>(c, inst, a.y, i, y1); stS<false>(c, inst, a.ys, i, 0.2*fabs(y1 - ldS<false>(c, inst, a.ys, i)));
             }
             __syncthreads();
             err = lpErrorNorm(c, inst, a, red);
@@ -323,7 +337,7 @@ __global__ void __launch_bounds__(LP_THREADS, 2) lpKernel(const KArgs a) {
                 for (int b = 1 + threadIdx.x; b < c.nb; b += LP_THREADS) {
                     const BodyConst& bc = c.bodies[b];
                     if (bc.joint != JT_BALL && bc.joint != JT_FREE) continue;
-                    double n2 = 0; for (int i = 0; i < 4; ++i) { const double qi = ldS(c, inst, a.y, bc.q0 + i); n2 += qi*qi; }
+                    double n2 = 0; for (int i = 0; i < 4; ++i) { const double qi = ldS<false>(c, inst, a.y, bc.q0 + i); n2 += qi*qi; }
                     const double e = sqrt(n2) - 1.0;
                     if (inf) acc = fmax(acc, fabs(e)); else acc += e*e;
                 }
@@ -334,10 +348,10 @@ __global__ void __launch_bounds__(LP_THREADS, 2) lpKernel(const KArgs a) {
                         const BodyConst& bc = c.bodies[b];
                         if (bc.joint != JT_BALL && bc.joint != JT_FREE) continue;
                         double q[4], e[4], n2 = 0;
-                        for (int i = 0; i < 4; ++i) { q[i] = ldS(c, inst, a.y, bc.q0 + i); e[i] = ldS(c, inst, a.ys, bc.q0 + i); n2 += q[i]*q[i]; }
+                        for (int i = 0; i < 4; ++i) { q[i] = ldS<false>(c, inst, a.y, bc.q0 + i); e[i] = ldS<false>(c, inst, a.ys, bc.q0 + i); n2 += q[i]*q[i]; }
                         const double n = sqrt(n2); double dt = 0;
                         for (int i = 0; i < 4; ++i) { q[i] = q[i]/n; dt += e[i]*q[i]; }
-                        for (int i = 0; i < 4; ++i) { stS(c, inst, a.y, bc.q0 + i, q[i]); stS(c, inst, a.ys, bc.q0 + i, e[i] - dt*q[i]); }
+                        for (int i = 0; i < 4; ++i) { stS<false>(c, inst, a.y, bc.q0 + i, q[i]); stS<false>(c, inst, a.ys, bc.q0 + i, e[i] - dt*q[i]); }
                     }
                     __syncthreads();
                     ++nproj;

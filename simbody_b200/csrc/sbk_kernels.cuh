@@ -13,8 +13,7 @@ struct KArgs {
     const unsigned char* tables;     // device blob
     uint32_t tableBytes, childrenOff, forcesOff, stageInSmem;
     uint32_t levelOrderOff, levelStartOff; int nlevels, plan;
-    int lightJoints, prefetch;        // prefetch: 1 = cp.async record prefetch in the integrator kernel
-    int pad0_, pad1_; //          // 1 if every mobilizer has dof <= 2 (128-register kernel variant)
+    int lightJoints, pad0_;                    // 1 if every mobilizer has dof <= 2 (128-register kernel variant)
     long long cStride, cInstStride, cSpan;  // cache addressing: base_b + field*cStride + (inst>>cShift)*cSpan + (inst&cMask)*cInstStride
     int cShift, cMask;
     int nb, nq, nu, nquat;
@@ -22,6 +21,7 @@ struct KArgs {
     int N;
     double* cache;
     double* y;          // state [nq+nu][N]
+    double* yb;         // CTA-blocked working copy of y for the thread-per-instance integrator kernels
     double* ydot;       // [nq+nu][N] (qdot, udot)
     double* qdotdot;    // [nq][N]
     double* qerr;       // [nquat][N]

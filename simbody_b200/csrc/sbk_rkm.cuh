@@ -25,15 +25,16 @@ struct RkmStepResult { double errNorm; int projected; };
 
 // Error norm of IntegratorRep::calcErrorNorm with UWeights = 1, no z.
 // err lives in w.ys (overwritten by the caller with the error estimate), q1 = current state.
+template <bool BLK>
 SBK_HD double rkmErrorNorm(const Ctx& c, const int inst, const RkmWork& w) {
     const int nq = c.nq, nu = c.nu;
     double qAcc = 0, uAcc = 0;
     // u part: uScale_i = |u0_i| > 1 ? 1/|u0_i| : 1   (calcRelativeScaling, frozen at step start)
 #pragma unroll 8
     for (int i = 0; i < nu; ++i) {
-        const double u0 = fabs(ldS(c, inst, w.y0, nq + i));
+        const double u0 = fabs(ldS<BLK>(c, inst, w.y0, nq + i));
         const double sc = (u0*1.0 > 1.0) ? 1.0/u0 : 1.0;
-        const double v  = sc*ldS(c, inst, w.ys, nq + i);
+        const double v  = sc*ldS<BLK>(c, inst, w.ys, nq + i);
         if (w.useInfNorm) uAcc = fmax(uAcc, fabs(v)); else uAcc += v*v;
     }
     // q part: dqw = N * Wu * pinv(N) * dq (scaleDQ); identity except on quaternion slots
@@ -43,7 +44,7 @@ SBK_HD double rkmErrorNorm(const Ctx& c, const int inst, const RkmWork& w) {
         if (bc.joint == JT_BALL || bc.joint == JT_FREE) {
             double q[4], e[4], o[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { q[i] = ldS(c, inst, w.y, bc.q0 + i); e[i] = ldS(c, inst, w.ys, bc.q0 + i); }
+            for (int i = 0; i < 4; ++i) { q[i] = ldS<BLK>(c, inst, w.y, bc.q0 + i); e[i] = ldS<BLK>(c, inst, w.ys, bc.q0 + i); }
             const V3 du = quatNInvTimes(q, e);
             quatNTimes(q, du, o);
 #pragma unroll
@@ -52,7 +53,7 @@ SBK_HD double rkmErrorNorm(const Ctx& c, const int inst, const RkmWork& w) {
         }
         const int nqb = bc.joint == JT_FREE ? 7 : bc.joint == JT_BALL ? 4 : bc.joint == JT_UNIVERSAL ? 2 : 1;
         for (int i = first; i < nqb; ++i) {
-            const double v = ldS(c, inst, w.ys, bc.q0 + i);
+            const double v = ldS<BLK>(c, inst, w.ys, bc.q0 + i);
             if (w.useInfNorm) qAcc = fmax(qAcc, fabs(v)); else qAcc += v*v;
         }
     }
@@ -84,47 +85,48 @@ SBK_HD bool adjustStepSize(const double err, const StepLimits& lim, const bool h
 // from the saved y0 / f0 (no re-evaluation, as in takeOneStep's do/while).
 // The caller's Ctx must have q = w.y, u = w.y + nq*sStride and null qerr / fmobOut / FbodyOut.
 template <bool LEAN, bool FRESH = true>
-SBK_HD RkmStepResult tpiRkmStep(const Ctx& c, const int inst, const RkmWork& w, const double h, double* cy, double* pf = nullptr) {
+SBK_HD RkmStepResult tpiRkmStep(const Ctx& c, const int inst, const RkmWork& w, const double h, double* cy) {
+    constexpr bool BLK = LEAN && SBK_DEV_BLK;
     const int nq = c.nq, ny = c.nq + c.nu;
-    const long long uoff = (long long)nq*c.sStride;
+    const long long uoff = BLK ? (long long)nq*BLK_LANES : (long long)nq*c.sStride;   // u rows follow the q rows
 
     if (FRESH) {
         // f0 = f(y0): AbstractIntegratorRep.cpp:393 realizeStateDerivatives at the start of the step
-        tpiEvalDerivatives<LEAN>(c, inst, cy, w.f0, w.f0 + uoff, nullptr, pf);
+        tpiEvalDerivatives<LEAN>(c, inst, cy, w.f0, w.f0 + uoff, nullptr);
 #pragma unroll 8
         for (int i = 0; i < ny; ++i) {
-            const double y0 = ldS(c, inst, w.y, i);
-            stS(c, inst, w.y0, i, y0);
-            stS(c, inst, w.y, i, y0 + (h/3)*ldS(c, inst, w.f0, i));
+            const double y0 = ldS<BLK>(c, inst, w.y, i);
+            stS<BLK>(c, inst, w.y0, i, y0);
+            stS<BLK>(c, inst, w.y, i, y0 + (h/3)*ldS<BLK>(c, inst, w.f0, i));
         }
     } else {
 #pragma unroll 8
-        for (int i = 0; i < ny; ++i) stS(c, inst, w.y, i, ldS(c, inst, w.y0, i) + (h/3)*ldS(c, inst, w.f0, i));
+        for (int i = 0; i < ny; ++i) stS<BLK>(c, inst, w.y, i, ldS<BLK>(c, inst, w.y0, i) + (h/3)*ldS<BLK>(c, inst, w.f0, i));
     }
-    tpiEvalDerivatives<LEAN>(c, inst, cy, w.fa, w.fa + uoff, nullptr, pf);                    // f1
+    tpiEvalDerivatives<LEAN>(c, inst, cy, w.fa, w.fa + uoff, nullptr);                    // f1
 #pragma unroll 8
     for (int i = 0; i < ny; ++i)
-        stS(c, inst, w.y, i, ldS(c, inst, w.y0, i) + (h/6)*(ldS(c, inst, w.f0, i) + ldS(c, inst, w.fa, i)));
-    tpiEvalDerivatives<LEAN>(c, inst, cy, w.fa, w.fa + uoff, nullptr, pf);                    // f2 -> fa
+        stS<BLK>(c, inst, w.y, i, ldS<BLK>(c, inst, w.y0, i) + (h/6)*(ldS<BLK>(c, inst, w.f0, i) + ldS<BLK>(c, inst, w.fa, i)));
+    tpiEvalDerivatives<LEAN>(c, inst, cy, w.fa, w.fa + uoff, nullptr);                    // f2 -> fa
 #pragma unroll 8
     for (int i = 0; i < ny; ++i)
-        stS(c, inst, w.y, i, ldS(c, inst, w.y0, i) + (h/8)*(ldS(c, inst, w.f0, i) + 3*ldS(c, inst, w.fa, i)));
-    tpiEvalDerivatives<LEAN>(c, inst, cy, w.fb, w.fb + uoff, nullptr, pf);                    // f3 -> fb
+        stS<BLK>(c, inst, w.y, i, ldS<BLK>(c, inst, w.y0, i) + (h/8)*(ldS<BLK>(c, inst, w.f0, i) + 3*ldS<BLK>(c, inst, w.fa, i)));
+    tpiEvalDerivatives<LEAN>(c, inst, cy, w.fb, w.fb + uoff, nullptr);                    // f3 -> fb
 #pragma unroll 8
     for (int i = 0; i < ny; ++i) {
-        const double ys = ldS(c, inst, w.y0, i) + (h/2)*(ldS(c, inst, w.f0, i) - 3*ldS(c, inst, w.fa, i) + 4*ldS(c, inst, w.fb, i));
-        stS(c, inst, w.ys, i, ys); stS(c, inst, w.y, i, ys);
+        const double ys = ldS<BLK>(c, inst, w.y0, i) + (h/2)*(ldS<BLK>(c, inst, w.f0, i) - 3*ldS<BLK>(c, inst, w.fa, i) + 4*ldS<BLK>(c, inst, w.fb, i));
+        stS<BLK>(c, inst, w.ys, i, ys); stS<BLK>(c, inst, w.y, i, ys);
     }
-    tpiEvalDerivatives<LEAN>(c, inst, cy, w.fa, w.fa + uoff, nullptr, pf);                    // f4 -> fa
+    tpiEvalDerivatives<LEAN>(c, inst, cy, w.fa, w.fa + uoff, nullptr);                    // f4 -> fa
 #pragma unroll 8
     for (int i = 0; i < ny; ++i) {
-        const double y1 = ldS(c, inst, w.y0, i) + (h/6)*(ldS(c, inst, w.f0, i) + 4*ldS(c, inst, w.fb, i) + ldS(c, inst, w.fa, i));
-        stS(c, inst, w.y, i, y1);
-        stS(c, inst, w.ys, i, 0.2*fabs(y1 - ldS(c, inst, w.ys, i)));                            // y1err
+        const double y1 = ldS<BLK>(c, inst, w.y0, i) + (h/6)*(ldS<BLK>(c, inst, w.f0, i) + 4*ldS<BLK>(c, inst, w.fb, i) + ldS<BLK>(c, inst, w.fa, i));
+        stS<BLK>(c, inst, w.y, i, y1);
+        stS<BLK>(c, inst, w.ys, i, 0.2*fabs(y1 - ldS<BLK>(c, inst, w.ys, i)));                            // y1err
     }
 
     RkmStepResult res; res.projected = 0;
-    res.errNorm = rkmErrorNorm(c, inst, w);
+    res.errNorm = rkmErrorNorm<BLK>(c, inst, w);
     // attemptDAEStep: project only if errNorm <= 2^4 * accuracy (AbstractIntegratorRep.cpp:165-166)
     if (c.nquat > 0 && !(res.errNorm > 16.0*w.accuracy)) {
         double acc = 0;
@@ -133,7 +135,7 @@ SBK_HD RkmStepResult tpiRkmStep(const Ctx& c, const int inst, const RkmWork& w, 
             if (bc.joint != JT_BALL && bc.joint != JT_FREE) continue;
             double n2 = 0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { const double qi = ldS(c, inst, w.y, bc.q0 + i); n2 += qi*qi; }
+            for (int i = 0; i < 4; ++i) { const double qi = ldS<BLK>(c, inst, w.y, bc.q0 + i); n2 += qi*qi; }
             const double e = sqrt(n2) - 1.0;
             if (w.useInfNorm) acc = fmax(acc, fabs(e)); else acc += e*e;
         }
@@ -144,16 +146,16 @@ SBK_HD RkmStepResult tpiRkmStep(const Ctx& c, const int inst, const RkmWork& w, 
                 if (bc.joint != JT_BALL && bc.joint != JT_FREE) continue;
                 double q[4], e[4], n2 = 0;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { q[i] = ldS(c, inst, w.y, bc.q0 + i); e[i] = ldS(c, inst, w.ys, bc.q0 + i); n2 += q[i]*q[i]; }
+                for (int i = 0; i < 4; ++i) { q[i] = ldS<BLK>(c, inst, w.y, bc.q0 + i); e[i] = ldS<BLK>(c, inst, w.ys, bc.q0 + i); n2 += q[i]*q[i]; }
                 const double n = sqrt(n2);
                 double dt = 0;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { q[i] = q[i]/n; dt += e[i]*q[i]; }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { stS(c, inst, w.y, bc.q0 + i, q[i]); stS(c, inst, w.ys, bc.q0 + i, e[i] - dt*q[i]); }
+                for (int i = 0; i < 4; ++i) { stS<BLK>(c, inst, w.y, bc.q0 + i, q[i]); stS<BLK>(c, inst, w.ys, bc.q0 + i, e[i] - dt*q[i]); }
             }
             res.projected = 1;
-            res.errNorm = rkmErrorNorm(c, inst, w);      // takeOneStep recomputes it (AbstractIntegratorRep.cpp:556)
+            res.errNorm = rkmErrorNorm<BLK>(c, inst, w);      // takeOneStep recomputes it (AbstractIntegratorRep.cpp:556)
         }
     }
     return res;
@@ -167,7 +169,8 @@ struct AdaptiveState { double t, h, lastStep; int steps, attempts; };
 template <bool LEAN>
 SBK_HD void tpiRkmAdaptive(const Ctx& c, const int inst, const RkmWork& w, const StepLimits& lim, const double tFinal,
                            const int allowInterpolation, const int maxAttempts, AdaptiveState& st, double* cy,
-                           double& lastErr, int& nproj, double* pf = nullptr) {
+                           double& lastErr, int& nproj) {
+    constexpr bool BLK = LEAN && SBK_DEV_BLK;
     int budget = maxAttempts;
     while (st.t < tFinal && budget > 0) {
         bool fresh = true, ok = false; double t1 = st.t;
@@ -178,13 +181,13 @@ SBK_HD void tpiRkmAdaptive(const Ctx& c, const int inst, const RkmWork& w, const
             else if (tFinal > st.t + 1.001*st.h) t1 = st.t + st.h;
             else t1 = tFinal;
             const double hTry = t1 - st.t;
-            const RkmStepResult r = fresh ? tpiRkmStep<LEAN, true>(c, inst, w, hTry, cy, pf) : tpiRkmStep<LEAN, false>(c, inst, w, hTry, cy, pf);
+            const RkmStepResult r = fresh ? tpiRkmStep<LEAN, true>(c, inst, w, hTry, cy) : tpiRkmStep<LEAN, false>(c, inst, w, hTry, cy);
             fresh = false; ++st.attempts; --budget; nproj += r.projected; lastErr = r.errNorm;
             ok = adjustStepSize(r.errNorm, lim, limited, st.h);
         } while (!ok && budget > 0);
         if (!ok) {   // out of budget inside a failing step: put y0 back, report through the status word
 #pragma unroll 8
-            for (int i = 0; i < c.nq + c.nu; ++i) stS(c, inst, w.y, i, ldS(c, inst, w.y0, i));
+            for (int i = 0; i < c.nq + c.nu; ++i) stS<BLK>(c, inst, w.y, i, ldS<BLK>(c, inst, w.y0, i));
             break;
         }
         st.lastStep = t1 - st.t; st.t = t1; ++st.steps;

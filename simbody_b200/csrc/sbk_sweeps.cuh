@@ -94,7 +94,7 @@ struct Ctx {
     double*   cache;
     long long cStride, cInstStride, cSpan;   // cache offset of an instance: (inst >> cShift)*cSpan + (inst & cMask)*cInstStride
     int cShift, cMask;
-    long long sStride, sInstStride;
+    long long sStride, sInstStride, sSpan;   // state vectors: [slot][N] (sStride = N) or CTA-blocked (sSpan = rows*128 per block)
     const double* q; const double* u;
     double* qdot; double* udot; double* qdotdot; double* qerr;   // realize-path destinations (nullable)
     // operator inputs / outputs (nullable)
@@ -174,10 +174,22 @@ SBK_HD void gst(double* p, double v) {
     *p = v;
 #endif
 }
-struct CacheRef {     // accessor for one body's record
+// Thread-per-instance plans block their arrays by 128-instance CTA -- records [block][field][lane],
+// integrator vectors [block][slot][lane] -- and the integrator path (BLK = true, device only) uses
+// the row stride 128 as a COMPILE-TIME constant: every access of a body step is then
+// `base + immediate`, with no per-access address arithmetic and no address registers.  (With a
+// run-time stride each of the ~90 accesses of a body step needed its own 64-bit address; ncu
+// showed the register pressure spilling freshly loaded values straight to local memory.)
+enum { BLK_LANES = 128 };
+#if defined(__CUDA_ARCH__)
+#define SBK_DEV_BLK 1
+#else
+#define SBK_DEV_BLK 0
+#endif
+template <bool BLK> struct CacheRefT {     // accessor for one body's record
     double* p; long long stride;
-    SBK_HD double ld(int k) const { return gld(p + (long long)k*stride); }
-    SBK_HD void   st(int k, double v) const { gst(p + (long long)k*stride, v); }
+    SBK_HD double ld(int k) const { return gld(p + (BLK ? (long long)k*BLK_LANES : (long long)k*stride)); }
+    SBK_HD void   st(int k, double v) const { gst(p + (BLK ? (long long)k*BLK_LANES : (long long)k*stride), v); }
     SBK_HD V3 ld3(int k) const { return mk(ld(k), ld(k+1), ld(k+2)); }
     SBK_HD void st3(int k, V3 v) const { st(k, v.x); st(k+1, v.y); st(k+2, v.z); }
     SBK_HD SV ldSV(int k) const { SV r; r.w = ld3(k); r.v = ld3(k+3); return r; }
@@ -193,81 +205,22 @@ struct CacheRef {     // accessor for one body's record
     SBK_HD ABI ldABI(int k) const { ABI P; P.M = ldS3(k); P.J = ldS3(k+6); P.F = ldM3(k+12); return P; }
     SBK_HD void stABI(int k, const ABI& P) const { stS3(k, P.M); stS3(k+6, P.J); stM3(k+12, P.F); }
 };
-// Generic instance offset: plain [field][N] records use cShift = 30 (offset = inst); the level-parallel
-// plan uses cShift = 0 (offset = inst*cSpan); the optional CTA-blocked layout uses cShift = 7.
+typedef CacheRefT<false> CacheRef;
+// Instance offset into the cache: CTA-blocked records use cShift = 7 (block*cSpan + lane); the
+// level-parallel plan cShift = 0 (inst*cSpan); the host emulation cShift = 30 (offset = inst).
 SBK_HD long long instOffset(const Ctx& c, int inst) { return (long long)(inst >> c.cShift)*c.cSpan + (long long)(inst & c.cMask)*c.cInstStride; }
-SBK_HD CacheRef cacheOf(const Ctx& c, int inst, long long base) { CacheRef r; r.p = c.cache + base + instOffset(c, inst); r.stride = c.cStride; return r; }
-SBK_HD double ldS(const Ctx& c, int inst, const double* a, int slot) { return gld(a + (long long)slot*c.sStride + (long long)inst*c.sInstStride); }
-SBK_HD void   stS(const Ctx& c, int inst, double* a, int slot, double v) { gst(a + (long long)slot*c.sStride + (long long)inst*c.sInstStride, v); }
-
-//----------------------------------------------------------------------------------------------
-// Asynchronous record prefetch (LEAN integrator path, device only).  A body step cannot start
-// before its record arrives from L2/HBM, and the sweeps expose that latency once per body.
-// Topology is static, so while body b computes, the rows body b+-1 will read are already being
-// copied global->shared with cp.async (LDGSTS) into this thread's slot column [row][thread]:
-// every lane copies and later reads only its own column, so no synchronisation is needed, no
-// registers are held, and every warp always has a whole record in flight (the bytes in flight
-// that Little's law asks for at HBM latency).  Rows beyond PF_CAP are read directly.
-//----------------------------------------------------------------------------------------------
-enum { PF_CAP = 40 };
-enum { SW_KIN = 0, SW_IN = 1, SW_OUT = 2 };
-SBK_HD void pfCopy8(double* dstSmem, const double* src) {
-#if defined(__CUDA_ARCH__)
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dstSmem)), "l"(src) : "memory");
-#else
-    *dstSmem = *src;
-#endif
+template <bool BLK> SBK_HD CacheRefT<BLK> cacheOf(const Ctx& c, int inst, long long base) {
+    CacheRefT<BLK> r;
+    r.p = c.cache + base + (BLK ? (long long)(inst >> 7)*c.cSpan + (inst & (BLK_LANES - 1)) : instOffset(c, inst));
+    r.stride = c.cStride; return r;
 }
-SBK_HD void pfCommit() {
-#if defined(__CUDA_ARCH__)
-    asm volatile("cp.async.commit_group;" ::: "memory");
-#endif
+// State / integrator vectors: BLK -> [block][slot][lane] with span sSpan per block; else [slot][N].
+template <bool BLK> SBK_HD long long stateIndex(const Ctx& c, int inst, int slot) {
+    return BLK ? (long long)(inst >> 7)*c.sSpan + (long long)slot*BLK_LANES + (inst & (BLK_LANES - 1))
+               : (long long)slot*c.sStride + (long long)inst*c.sInstStride;
 }
-SBK_HD void pfWait() {
-#if defined(__CUDA_ARCH__)
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-#endif
-}
-SBK_HD void pfRows(double* pf, const double* src, long long stride, int count, int& k) {
-    for (int i = 0; i < count && k < PF_CAP; ++i, ++k) pfCopy8(pf + k*SBK_CARRY_STRIDE, src + (long long)i*stride);
-}
-SBK_HD int dofOfJoint(int jt) { return jt == JT_FREE ? 6 : jt == JT_BALL ? 3 : jt == JT_UNIVERSAL ? 2 : 1; }
-SBK_HD int nqOfJoint(int jt)  { return jt == JT_FREE ? 7 : jt == JT_BALL ? 4 : jt == JT_UNIVERSAL ? 2 : 1; }
-// Row lists per sweep (must match pfIndex below).
-SBK_HD void pfIssue(const Ctx& c, const int inst, double* pf, const BodyConst& bc, const int sweep) {
-    int k = 0; const int d = dofOfJoint(bc.joint);
-    if (sweep == SW_KIN) {
-        pfRows(pf, c.q + (long long)bc.q0*c.sStride + (long long)inst*c.sInstStride, c.sStride, nqOfJoint(bc.joint), k);
-        pfRows(pf, c.u + (long long)bc.u0*c.sStride + (long long)inst*c.sInstStride, c.sStride, d, k);
-    } else {
-        const double* rec = c.cache + bc.cacheBase + instOffset(c, inst);
-        if (sweep == SW_IN) {
-            pfRows(pf, rec + (long long)F_L*c.cStride, c.cStride, F_ZB - F_L, k);
-            pfRows(pf, rec + (long long)F_H*c.cStride, c.cStride, 6*d, k);
-        } else {
-            pfRows(pf, rec + (long long)F_L*c.cStride, c.cStride, 3, k);
-            pfRows(pf, rec + (long long)F_ACOR*c.cStride, c.cStride, 6, k);
-            pfRows(pf, rec + (long long)F_H*c.cStride, c.cStride, 13*d + d*d, k);
-        }
-    }
-    pfCommit();
-}
-// field -> slot row, per sweep (folds at compile time: fields are constants after unrolling)
-template <int SWEEP> SBK_HD constexpr int pfIndex(int f) {
-    return SWEEP == SW_IN  ? (f < F_ZB ? f - F_L : (F_ZB - F_L) + (f - F_H))
-                           : (f < F_L + 3 ? f - F_L : (f < F_ACOR + 6 ? 3 + (f - F_ACOR) : 9 + (f - F_H)));
-}
-// Reads a record field from the prefetch slot when it is there, else from the cache in HBM.
-template <int SWEEP> struct RecReader {
-    CacheRef g; const double* slot;     // slot == nullptr: no prefetch
-    SBK_HD double ld(int f) const {
-        if (slot) { const int k = pfIndex<SWEEP>(f); if (k < PF_CAP) return slot[k*SBK_CARRY_STRIDE]; }
-        return g.ld(f);
-    }
-    SBK_HD V3 ld3(int f) const { return mk(ld(f), ld(f+1), ld(f+2)); }
-    SBK_HD SV ldSV(int f) const { SV r; r.w = ld3(f); r.v = ld3(f+3); return r; }
-    SBK_HD S3 ldS3(int f) const { S3 s; s.xx = ld(f); s.yy = ld(f+1); s.zz = ld(f+2); s.xy = ld(f+3); s.xz = ld(f+4); s.yz = ld(f+5); return s; }
-};
+template <bool BLK> SBK_HD double ldS(const Ctx& c, int inst, const double* a, int slot) { return gld(a + stateIndex<BLK>(c, inst, slot)); }
+template <bool BLK> SBK_HD void   stS(const Ctx& c, int inst, double* a, int slot, double v) { gst(a + stateIndex<BLK>(c, inst, slot), v); }
 
 SBK_HD M3 loadR(const double* X) { M3 R;
 #pragma unroll
@@ -531,28 +484,19 @@ SBK_HD void mobilityForces(const BodyConst& bc, const ForceConst* forces, const 
 // LEAN = true : integrator path; links ride in the carry when the tree order allows.
 
 template <int JT, bool LEAN>
-SBK_BODY void kinBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, const int inst, double* cy, double* qdotDst,
-                      double* pf = nullptr, const int nextBody = -1) {
+SBK_BODY void kinBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, const int inst, double* cy, double* qdotDst) {
     constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
-    const CacheRef me = cacheOf(c, inst, bc.cacheBase);
+    constexpr bool BLK = LEAN && SBK_DEV_BLK;
+    const CacheRefT<BLK> me = cacheOf<BLK>(c, inst, bc.cacheBase);
     double q[NQ], u[d], qdot[NQ], qerr;
-    if (LEAN && pf) {
-        pfWait();
 #pragma unroll
-        for (int i = 0; i < NQ; ++i) q[i] = pf[i*SBK_CARRY_STRIDE];
+    for (int i = 0; i < NQ; ++i) q[i] = ldS<BLK>(c, inst, c.q, bc.q0 + i);
 #pragma unroll
-        for (int i = 0; i < d; ++i)  u[i] = pf[(NQ + i)*SBK_CARRY_STRIDE];
-        if (nextBody >= 1) pfIssue(c, inst, pf, c.bodies[nextBody], SW_KIN);
-    } else {
-#pragma unroll
-        for (int i = 0; i < NQ; ++i) q[i] = ldS(c, inst, c.q, bc.q0 + i);
-#pragma unroll
-        for (int i = 0; i < d; ++i)  u[i] = ldS(c, inst, c.u, bc.u0 + i);
-    }
+    for (int i = 0; i < d; ++i)  u[i] = ldS<BLK>(c, inst, c.u, bc.u0 + i);
 
     M3 R_GP; V3 p_GP; SV V_GP;
     if (LEAN && (bc.flags & BF_PARENT_PREV)) cyLoadOut(cy, R_GP, p_GP, V_GP);
-    else { const CacheRef pa = cacheOf(c, inst, bc.parentCacheBase); R_GP = pa.ldM3(F_XGB); p_GP = pa.ld3(F_XGB + 9); V_GP = pa.ldSV(F_VGB); }
+    else { const CacheRefT<BLK> pa = cacheOf<BLK>(c, inst, bc.parentCacheBase); R_GP = pa.ldM3(F_XGB); p_GP = pa.ld3(F_XGB + 9); V_GP = pa.ldSV(F_VGB); }
 
     KinOut<d> o;
     kinCore<JT>(bc, q, u, R_GP, p_GP, V_GP, o, qdot, qerr);
@@ -565,9 +509,9 @@ SBK_BODY void kinBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, co
     for (int j = 0; j < d; ++j) me.stSV(F_H + 6*j, o.H[j]);
     if (qdotDst) {
 #pragma unroll
-        for (int i = 0; i < NQ; ++i) stS(c, inst, qdotDst, bc.q0 + i, qdot[i]);
+        for (int i = 0; i < NQ; ++i) stS<BLK>(c, inst, qdotDst, bc.q0 + i, qdot[i]);
     }
-    if constexpr (JT == JT_BALL || JT == JT_FREE) { if (c.qerr) stS(c, inst, c.qerr, bc.quat, qerr); }
+    if constexpr (JT == JT_BALL || JT == JT_FREE) { if (c.qerr) stS<BLK>(c, inst, c.qerr, bc.quat, qerr); }
 }
 
 // Inward body step.  MODE bits:
@@ -579,14 +523,12 @@ SBK_BODY void kinBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, co
 enum { IN_ABI = 1, IN_Z = 2, IN_BIAS = 4, IN_FORCES = 8 };
 
 template <int JT, int MODE, bool LEAN>
-SBK_BODY void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, const int inst, double* cy,
-                         double* pf = nullptr, const int nextBody = -1) {
+SBK_BODY void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, const int inst, double* cy) {
     constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
-    const CacheRef me = cacheOf(c, inst, bc.cacheBase);
-    const bool usePf = LEAN && ((MODE & IN_ABI) != 0) && pf;
-    if (usePf) pfWait();
-    RecReader<SW_IN> in; in.g = me; in.slot = usePf ? pf : nullptr;
-    // every input up front (one wait); afterwards the slot is free for the next body's rows
+    constexpr bool BLK = LEAN && SBK_DEV_BLK;
+    const CacheRefT<BLK> me = cacheOf<BLK>(c, inst, bc.cacheBase);
+    const CacheRefT<BLK>& in = me;
+    // every input of the body step is requested up front: one wait on global memory per body
     SV H[d];
 #pragma unroll
     for (int j = 0; j < d; ++j) H[j] = in.ldSV(F_H + 6*j);
@@ -601,12 +543,11 @@ SBK_BODY void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex,
     if constexpr ((MODE & IN_FORCES) != 0) {
         if (bc.nforce > 0) {
 #pragma unroll
-            for (int i = 0; i < NQ; ++i) qF[i] = ldS(c, inst, c.q, bc.q0 + i);
+            for (int i = 0; i < NQ; ++i) qF[i] = ldS<BLK>(c, inst, c.q, bc.q0 + i);
 #pragma unroll
-            for (int i = 0; i < d; ++i)  uF[i] = ldS(c, inst, c.u, bc.u0 + i);
+            for (int i = 0; i < d; ++i)  uF[i] = ldS<BLK>(c, inst, c.u, bc.u0 + i);
         }
     }
-    if (usePf && nextBody >= 1) pfIssue(c, inst, pf, c.bodies[nextBody], SW_IN);
     const bool linkToCache = !LEAN || !(bc.flags & BF_PARENT_PREV);
     // the adjacent child (index + 1), if any, left its links in the carry
     ABI cPP; SV czP = zeroSV(); V3 cl = zero3();
@@ -618,7 +559,7 @@ SBK_BODY void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex,
         ABI P = abiFromRigid(bc.mass, c_G, G_Gin);
         for (int k = 0; k < bc.nchild; ++k) {
             if (k == 0 && haveCarryChild) { addInto(P, shiftABI(cPP, cl)); continue; }
-            const CacheRef ch = cacheOf(c, inst, c.bodies[c.children[bc.childStart + k]].cacheBase);
+            const CacheRefT<BLK> ch = cacheOf<BLK>(c, inst, c.bodies[c.children[bc.childStart + k]].cacheBase);
             addInto(P, shiftABI(ch.ldABI(F_PPLUS), ch.ld3(F_L)));
         }
         abiCore<d>(P, H, acorIn, gyroIn, ao);
@@ -650,18 +591,18 @@ SBK_BODY void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex,
             mobilityForces<d>(bc, c.forces, qF, uF, f);
             if (c.fmobOut) {
 #pragma unroll
-                for (int j = 0; j < d; ++j) stS(c, inst, c.fmobOut, bc.u0 + j, f[j]);
+                for (int j = 0; j < d; ++j) stS<BLK>(c, inst, c.fmobOut, bc.u0 + j, f[j]);
             }
             if (c.FbodyOut) {
-                stS(c, inst, c.FbodyOut, 6*bodyIndex+0, F.w.x); stS(c, inst, c.FbodyOut, 6*bodyIndex+1, F.w.y); stS(c, inst, c.FbodyOut, 6*bodyIndex+2, F.w.z);
-                stS(c, inst, c.FbodyOut, 6*bodyIndex+3, F.v.x); stS(c, inst, c.FbodyOut, 6*bodyIndex+4, F.v.y); stS(c, inst, c.FbodyOut, 6*bodyIndex+5, F.v.z);
+                stS<BLK>(c, inst, c.FbodyOut, 6*bodyIndex+0, F.w.x); stS<BLK>(c, inst, c.FbodyOut, 6*bodyIndex+1, F.w.y); stS<BLK>(c, inst, c.FbodyOut, 6*bodyIndex+2, F.w.z);
+                stS<BLK>(c, inst, c.FbodyOut, 6*bodyIndex+3, F.v.x); stS<BLK>(c, inst, c.FbodyOut, 6*bodyIndex+4, F.v.y); stS<BLK>(c, inst, c.FbodyOut, 6*bodyIndex+5, F.v.z);
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < d; ++j) f[j] = c.fmobIn ? ldS(c, inst, c.fmobIn, bc.u0 + j) : 0.0;
+            for (int j = 0; j < d; ++j) f[j] = c.fmobIn ? ldS<BLK>(c, inst, c.fmobIn, bc.u0 + j) : 0.0;
             if (c.FbodyIn) {
-                F.w = mk(ldS(c, inst, c.FbodyIn, 6*bodyIndex+0), ldS(c, inst, c.FbodyIn, 6*bodyIndex+1), ldS(c, inst, c.FbodyIn, 6*bodyIndex+2));
-                F.v = mk(ldS(c, inst, c.FbodyIn, 6*bodyIndex+3), ldS(c, inst, c.FbodyIn, 6*bodyIndex+4), ldS(c, inst, c.FbodyIn, 6*bodyIndex+5));
+                F.w = mk(ldS<BLK>(c, inst, c.FbodyIn, 6*bodyIndex+0), ldS<BLK>(c, inst, c.FbodyIn, 6*bodyIndex+1), ldS<BLK>(c, inst, c.FbodyIn, 6*bodyIndex+2));
+                F.v = mk(ldS<BLK>(c, inst, c.FbodyIn, 6*bodyIndex+3), ldS<BLK>(c, inst, c.FbodyIn, 6*bodyIndex+4), ldS<BLK>(c, inst, c.FbodyIn, 6*bodyIndex+5));
             }
         }
         // ---- calcUDotPass1Inward (RigidBodyNodeSpec.cpp:355-400) / M^-1 pass 1 (:483-515) ------
@@ -669,7 +610,7 @@ SBK_BODY void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex,
         if constexpr ((MODE & IN_BIAS) != 0) z = ao.zb - F; else z = zeroSV();
         for (int k = 0; k < bc.nchild; ++k) {
             if (k == 0 && haveCarryChild) { z = z + phi(cl, czP); continue; }
-            const CacheRef ch = cacheOf(c, inst, c.bodies[c.children[bc.childStart + k]].cacheBase);
+            const CacheRefT<BLK> ch = cacheOf<BLK>(c, inst, c.bodies[c.children[bc.childStart + k]].cacheBase);
             z = z + phi(ch.ld3(F_L), ch.ldSV(F_ZPLUS));
         }
         double eps[d];
@@ -684,15 +625,14 @@ SBK_BODY void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex,
 // Sweep E for one body (base->tip): udot, A_GB, qdotdot.
 template <int JT, bool WITH_COR, bool LEAN>
 SBK_BODY void outwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, const int inst, double* cy,
-                         double* udotDst, double* qdotdotDst, double* pf = nullptr, const int nextBody = -1) {
+                         double* udotDst, double* qdotdotDst) {
     constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
-    const CacheRef cref = cacheOf(c, inst, bc.cacheBase);
-    const bool usePf = LEAN && pf;
-    if (usePf) pfWait();
-    RecReader<SW_OUT> me; me.g = cref; me.slot = usePf ? pf : nullptr;
+    constexpr bool BLK = LEAN && SBK_DEV_BLK;
+    const CacheRefT<BLK> cref = cacheOf<BLK>(c, inst, bc.cacheBase);
+    const CacheRefT<BLK>& me = cref;
     SV A_GP;
     if (LEAN && (bc.flags & BF_PARENT_PREV)) A_GP = cyLoadA(cy);
-    else A_GP = cacheOf(c, inst, bc.parentCacheBase).ldSV(F_AGB);
+    else A_GP = cacheOf<BLK>(c, inst, bc.parentCacheBase).ldSV(F_AGB);
     SV H[d], G[d]; double DI[d*d], eps[d], udot[d];
 #pragma unroll
     for (int j = 0; j < d; ++j) { H[j] = me.ldSV(F_H + 6*j); G[j] = me.ldSV(fG(d) + 6*j); eps[j] = me.ld(fEPS(d) + j); }
@@ -701,26 +641,25 @@ SBK_BODY void outwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex
     SV acor = zeroSV();
     if constexpr (WITH_COR) acor = me.ldSV(F_ACOR);
     const V3 lMe = me.ld3(F_L);
-    if (usePf && nextBody >= 1) pfIssue(c, inst, pf, c.bodies[nextBody], SW_OUT);
     SV A;
     accCore<d, WITH_COR>(H, G, DI, eps, lMe, A_GP, acor, udot, A);
     if (!LEAN || (bc.flags & BF_STORE_LINK)) cref.stSV(F_AGB, A);
     if (LEAN) cyStoreA(cy, A);
     if (udotDst) {
 #pragma unroll
-        for (int i = 0; i < d; ++i) stS(c, inst, udotDst, bc.u0 + i, udot[i]);
+        for (int i = 0; i < d; ++i) stS<BLK>(c, inst, udotDst, bc.u0 + i, udot[i]);
     }
     if (qdotdotDst) {
         double q[NQ], u[d], qdd[NQ];
         if constexpr (JT == JT_BALL || JT == JT_FREE) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) q[i] = ldS(c, inst, c.q, bc.q0 + i);
+            for (int i = 0; i < 4; ++i) q[i] = ldS<BLK>(c, inst, c.q, bc.q0 + i);
 #pragma unroll
-            for (int i = 0; i < 3; ++i) u[i] = ldS(c, inst, c.u, bc.u0 + i);
+            for (int i = 0; i < 3; ++i) u[i] = ldS<BLK>(c, inst, c.u, bc.u0 + i);
         }
         qddCore<JT>(q, u, udot, qdd);
 #pragma unroll
-        for (int i = 0; i < NQ; ++i) stS(c, inst, qdotdotDst, bc.q0 + i, qdd[i]);
+        for (int i = 0; i < NQ; ++i) stS<BLK>(c, inst, qdotdotDst, bc.q0 + i, qdd[i]);
     }
 }
 
@@ -730,12 +669,13 @@ SBK_BODY void outwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex
 template <int JT, bool WITH_VEL>
 SBK_BODY void idOutBody(const Ctx& c, const BodyConst& bc, const int inst) {
     constexpr int d = JointDims<JT>::nu;
-    const CacheRef me = cacheOf(c, inst, bc.cacheBase), pa = cacheOf(c, inst, bc.parentCacheBase);
+    constexpr bool BLK = false;
+    const CacheRefT<BLK> me = cacheOf<BLK>(c, inst, bc.cacheBase), pa = cacheOf<BLK>(c, inst, bc.parentCacheBase);
     SV A = phiT(me.ld3(F_L), pa.ldSV(F_AGB));
     SV Hu = zeroSV();
 #pragma unroll
     for (int j = 0; j < d; ++j) {
-        const double v = c.vecIn ? ldS(c, inst, c.vecIn, bc.u0 + j) : 0.0;
+        const double v = c.vecIn ? ldS<BLK>(c, inst, c.vecIn, bc.u0 + j) : 0.0;
         Hu = Hu + v*me.ldSV(F_H + 6*j);
     }
     A = A + Hu;
@@ -745,21 +685,22 @@ SBK_BODY void idOutBody(const Ctx& c, const BodyConst& bc, const int inst) {
 template <int JT, bool WITH_VEL>
 SBK_BODY void idInBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, const int inst) {
     constexpr int d = JointDims<JT>::nu;
-    const CacheRef me = cacheOf(c, inst, bc.cacheBase);
+    constexpr bool BLK = false;
+    const CacheRefT<BLK> me = cacheOf<BLK>(c, inst, bc.cacheBase);
     const V3 c_G = me.ld3(F_MK); const S3 G_G = me.ldS3(F_MK + 3);
     SV F = mulSpatialInertia(bc.mass, c_G, G_G, me.ldSV(F_AGB));
     if constexpr (WITH_VEL) {
         F = F + me.ldSV(F_GYRO);
         if (c.FbodyIn) {
             SV Fa;
-            Fa.w = mk(ldS(c, inst, c.FbodyIn, 6*bodyIndex+0), ldS(c, inst, c.FbodyIn, 6*bodyIndex+1), ldS(c, inst, c.FbodyIn, 6*bodyIndex+2));
-            Fa.v = mk(ldS(c, inst, c.FbodyIn, 6*bodyIndex+3), ldS(c, inst, c.FbodyIn, 6*bodyIndex+4), ldS(c, inst, c.FbodyIn, 6*bodyIndex+5));
+            Fa.w = mk(ldS<BLK>(c, inst, c.FbodyIn, 6*bodyIndex+0), ldS<BLK>(c, inst, c.FbodyIn, 6*bodyIndex+1), ldS<BLK>(c, inst, c.FbodyIn, 6*bodyIndex+2));
+            Fa.v = mk(ldS<BLK>(c, inst, c.FbodyIn, 6*bodyIndex+3), ldS<BLK>(c, inst, c.FbodyIn, 6*bodyIndex+4), ldS<BLK>(c, inst, c.FbodyIn, 6*bodyIndex+5));
             F = F - Fa;
         }
     }
     for (int k = 0; k < bc.nchild; ++k) {
         const BodyConst& cb = c.bodies[c.children[bc.childStart + k]];
-        const CacheRef ch = cacheOf(c, inst, cb.cacheBase);
+        const CacheRefT<BLK> ch = cacheOf<BLK>(c, inst, cb.cacheBase);
         F = F + phi(ch.ld3(F_L), ch.ldSV(F_ZPLUS));
     }
     me.stSV(F_ZPLUS, F);
@@ -767,8 +708,8 @@ SBK_BODY void idInBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, c
     for (int j = 0; j < d; ++j) {
         const SV Hj = me.ldSV(F_H + 6*j);
         double tau = dot(Hj.w, F.w) + dot(Hj.v, F.v);
-        if constexpr (WITH_VEL) { if (c.fmobIn) tau -= ldS(c, inst, c.fmobIn, bc.u0 + j); }
-        stS(c, inst, c.vecOut, bc.u0 + j, tau);
+        if constexpr (WITH_VEL) { if (c.fmobIn) tau -= ldS<BLK>(c, inst, c.fmobIn, bc.u0 + j); }
+        stS<BLK>(c, inst, c.vecOut, bc.u0 + j, tau);
     }
 }
 
@@ -786,18 +727,17 @@ SBK_BODY void idInBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, c
         default: break;                                                             \
     }
 
-template <bool LEAN> SBK_HD void kinDispatch(const Ctx& c, int b, int inst, double* cy, double* qdotDst, double* pf = nullptr, int next = -1) {
+template <bool LEAN> SBK_HD void kinDispatch(const Ctx& c, int b, int inst, double* cy, double* qdotDst) {
     const BodyConst& bc = c.bodies[b];
-    SBK_DISPATCH_JOINT(bc.joint, (kinBody<JT, LEAN>(c, bc, b, inst, cy, qdotDst, pf, next)));
+    SBK_DISPATCH_JOINT(bc.joint, (kinBody<JT, LEAN>(c, bc, b, inst, cy, qdotDst)));
 }
-template <int MODE, bool LEAN> SBK_HD void inwardDispatch(const Ctx& c, int b, int inst, double* cy, double* pf = nullptr, int next = -1) {
+template <int MODE, bool LEAN> SBK_HD void inwardDispatch(const Ctx& c, int b, int inst, double* cy) {
     const BodyConst& bc = c.bodies[b];
-    SBK_DISPATCH_JOINT(bc.joint, (inwardBody<JT, MODE, LEAN>(c, bc, b, inst, cy, pf, next)));
+    SBK_DISPATCH_JOINT(bc.joint, (inwardBody<JT, MODE, LEAN>(c, bc, b, inst, cy)));
 }
-template <bool WITH_COR, bool LEAN> SBK_HD void outwardDispatch(const Ctx& c, int b, int inst, double* cy, double* udotDst, double* qddDst,
-                                                                double* pf = nullptr, int next = -1) {
+template <bool WITH_COR, bool LEAN> SBK_HD void outwardDispatch(const Ctx& c, int b, int inst, double* cy, double* udotDst, double* qddDst) {
     const BodyConst& bc = c.bodies[b];
-    SBK_DISPATCH_JOINT(bc.joint, (outwardBody<JT, WITH_COR, LEAN>(c, bc, b, inst, cy, udotDst, qddDst, pf, next)));
+    SBK_DISPATCH_JOINT(bc.joint, (outwardBody<JT, WITH_COR, LEAN>(c, bc, b, inst, cy, udotDst, qddDst)));
 }
 template <bool WITH_VEL> SBK_HD void idOutDispatch(const Ctx& c, int b, int inst) {
     const BodyConst& bc = c.bodies[b];
@@ -812,28 +752,22 @@ template <bool WITH_VEL> SBK_HD void idInDispatch(const Ctx& c, int b, int inst)
 // Per-instance drivers for the thread-per-instance plan: body index order is a valid
 // base->tip order because a parent's MobilizedBodyIndex is always smaller than its child's.
 //==============================================================================================
-// `pf` (nullable): this thread's prefetch slot column; when given (LEAN integrator path on the
-// device) every sweep keeps the next body's rows in flight while the current body computes.
-template <bool LEAN> SBK_HD void tpiKinematics(const Ctx& c, int inst, double* cy, double* qdotDst, double* pf = nullptr) {
+template <bool LEAN> SBK_HD void tpiKinematics(const Ctx& c, int inst, double* cy, double* qdotDst) {
     if (LEAN) { SV z0 = zeroSV(); cyStoreOut(cy, identity3(), zero3(), z0); }      // Ground's link for body 1
-    if (LEAN && pf && c.nb > 1) pfIssue(c, inst, pf, c.bodies[1], SW_KIN);
-    for (int b = 1; b < c.nb; ++b) kinDispatch<LEAN>(c, b, inst, cy, qdotDst, pf, b + 1 < c.nb ? b + 1 : -1);
+    for (int b = 1; b < c.nb; ++b) kinDispatch<LEAN>(c, b, inst, cy, qdotDst);
 }
-template <int MODE, bool LEAN> SBK_HD void tpiInward(const Ctx& c, int inst, double* cy, double* pf = nullptr) {
-    if (LEAN && ((MODE & IN_ABI) != 0) && pf && c.nb > 1) pfIssue(c, inst, pf, c.bodies[c.nb - 1], SW_IN);
-    for (int b = c.nb - 1; b >= 1; --b) inwardDispatch<MODE, LEAN>(c, b, inst, cy, pf, b - 1);
+template <int MODE, bool LEAN> SBK_HD void tpiInward(const Ctx& c, int inst, double* cy) {
+    for (int b = c.nb - 1; b >= 1; --b) inwardDispatch<MODE, LEAN>(c, b, inst, cy);
 }
-template <bool WITH_COR, bool LEAN> SBK_HD void tpiOutward(const Ctx& c, int inst, double* cy, double* udotDst, double* qddDst, double* pf = nullptr) {
+template <bool WITH_COR, bool LEAN> SBK_HD void tpiOutward(const Ctx& c, int inst, double* cy, double* udotDst, double* qddDst) {
     if (LEAN) cyStoreA(cy, zeroSV());                                               // Ground's A_GB
-    if (LEAN && pf && c.nb > 1) pfIssue(c, inst, pf, c.bodies[1], SW_OUT);
-    for (int b = 1; b < c.nb; ++b) outwardDispatch<WITH_COR, LEAN>(c, b, inst, cy, udotDst, qddDst, pf, b + 1 < c.nb ? b + 1 : -1);
+    for (int b = 1; b < c.nb; ++b) outwardDispatch<WITH_COR, LEAN>(c, b, inst, cy, udotDst, qddDst);
 }
 // One full derivative evaluation = System::realize(Acceleration) for the lowered system.
-template <bool LEAN> SBK_EVAL void tpiEvalDerivatives(const Ctx& c, int inst, double* cy, double* qdotDst, double* udotDst, double* qddDst,
-                                                      double* pf = nullptr) {
-    tpiKinematics<LEAN>(c, inst, cy, qdotDst, pf);
-    tpiInward<IN_ABI | IN_Z | IN_BIAS | IN_FORCES, LEAN>(c, inst, cy, pf);
-    tpiOutward<true, LEAN>(c, inst, cy, udotDst, qddDst, pf);
+template <bool LEAN> SBK_EVAL void tpiEvalDerivatives(const Ctx& c, int inst, double* cy, double* qdotDst, double* udotDst, double* qddDst) {
+    tpiKinematics<LEAN>(c, inst, cy, qdotDst);
+    tpiInward<IN_ABI | IN_Z | IN_BIAS | IN_FORCES, LEAN>(c, inst, cy);
+    tpiOutward<true, LEAN>(c, inst, cy, udotDst, qddDst);
 }
 
 } // namespace sbkd

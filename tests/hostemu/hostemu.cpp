@@ -51,7 +51,7 @@ Ctx makeCtx(Emu& e, int inst) {
     c.nb = t.nb; c.nq = t.nq; c.nu = t.nu; c.nquat = t.nquat;
     c.gx = t.grav[0]; c.gy = t.grav[1]; c.gz = t.grav[2];
     c.cache = e.cache.data(); c.cStride = N; c.cInstStride = 1; c.cSpan = 0; c.cShift = 30; c.cMask = 0x3fffffff;
-    c.sStride = N; c.sInstStride = 1;
+    c.sStride = N; c.sInstStride = 1; c.sSpan = 0;
     c.q = e.y.data(); c.u = e.y.data() + (size_t)t.nq*N;
     c.qdot = e.ydot.data(); c.udot = e.ydot.data() + (size_t)t.nq*N;
     c.qdotdot = e.qdd.data(); c.qerr = e.qerr.data();
