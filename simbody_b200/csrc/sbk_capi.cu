@@ -200,6 +200,9 @@ static int configurePlan(sbk_batch* b, int plan) {
     a.nlevels = t->nlevels; a.plan = plan;
     a.lightJoints = 1;
     for (int i = 1; i < t->nb; ++i) if (t->nuOf[i] > 2) a.lightJoints = 0;
+    a.jointMask = 0;
+    for (int i = 1; i < t->nb; ++i) a.jointMask |= 1 << t->bodies[i].joint;
+    { const char* e = getenv("SBK_JMASK"); if (e) a.jointMask |= atoi(e); }           // tuning override: force a wider kernel variant
     { const char* e = getenv("SBK_LIGHT"); if (e) a.lightJoints = atoi(e); }     // tuning override
     a.stageInSmem = (plan != 3 && blob.size() <= 96*1024) ? 1u : 0u;
     CUDA_TRY(cudaStreamSynchronize(b->stream));

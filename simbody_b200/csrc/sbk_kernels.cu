@@ -18,7 +18,7 @@ namespace {
 #define SBK_TPI_THREADS 128
 #endif
 #ifndef SBK_TPI_MINBLOCKS
-#define SBK_TPI_MINBLOCKS 4
+#define SBK_TPI_MINBLOCKS 2
 #endif
 #ifndef SBK_HEAVY_MINB
 #define SBK_HEAVY_MINB 2
@@ -84,40 +84,46 @@ __device__ __forceinline__ void stateFromBlocked(const Ctx& c, const KArgs& a, i
 // MINB = resident CTAs per SM the register allocation is sized for: 4 (128 registers) suits
 // models made of 1-2 dof mobilizers, 2 (255 registers) models with Ball/Free bodies, whose 3x3 /
 // 6x6 articulated-inertia algebra would otherwise spill (measured: +46% on the humanoid).
-template <int OP, bool STAGE, int MINB>
+template <int OP, bool STAGE, int MINB, int JMASK = JM_ALL>
 __global__ void __launch_bounds__(TPI_THREADS, MINB) tpiKernel(const KArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ Ctx sctx;                      // ONE context per CTA, read with LDS by every body step
     const unsigned char* tables = a.tables;
     if constexpr (STAGE) { tmaStage(smem, a.tables, a.tableBytes, &mbar); tables = smem; }
-    if (threadIdx.x == 0) {
-        fillCtx(sctx, a, tables, OP == OP_RKM || OP == OP_RKM_ADAPT);
-        if (OP == OP_RKM || OP == OP_RKM_ADAPT) useBlockedState(sctx, a);
-    }
+    constexpr bool INTEG = OP == OP_RKM || OP == OP_RKM_ADAPT;
+    if (!INTEG && threadIdx.x == 0) fillCtx(sctx, a, tables, false);
     __syncthreads();
     const int inst = blockIdx.x*blockDim.x + threadIdx.x;
     if (inst >= a.N) return;
-    const Ctx& c = sctx;
+    // API kernels read the context from shared memory; the integrator kernels keep it as a local whose
+    // members are kernel parameters (constant bank operands) or one add away from them -- reading
+    // it from shared memory cost a generic load plus descriptor moves per access (ncu).
+    Ctx lctx;
+    if constexpr (INTEG) { fillCtx(lctx, a, tables, true); useBlockedState(lctx, a); }
+    const Ctx& c = INTEG ? lctx : sctx;
+    Tables T;                                  // address space known at compile time: shared if staged, else global
+    T.bodies = reinterpret_cast<const BodyConst*>(tables); T.children = reinterpret_cast<const int*>(tables + a.childrenOff);
+    T.forces = reinterpret_cast<const ForceConst*>(tables + a.forcesOff);
     // LEAN carry: a [CARRY_ROWS][128] block of shared memory behind the staged tables
     double* cy = nullptr;
     if constexpr (OP == OP_RKM || OP == OP_RKM_ADAPT) cy = reinterpret_cast<double*>(smem + (STAGE ? a.tableBytes : 0)) + threadIdx.x;
 
     if constexpr (OP == OP_KIN) {
-        tpiKinematics<false>(c, inst, cy, c.qdot);
+        tpiKinematics(c, inst, c.qdot);
     } else if constexpr (OP == OP_ABI) {
-        tpiInward<IN_ABI, false>(c, inst, cy);
+        tpiInward<IN_ABI>(c, inst);
     } else if constexpr (OP == OP_EVAL) {
-        tpiEvalDerivatives<false>(c, inst, cy, c.qdot, c.udot, c.qdotdot);
+        tpiEvalDerivatives<false>(c, tablesOf(c), inst, cy, c.qdot, c.udot, c.qdotdot);
     } else if constexpr (OP == OP_CALCACC) {
-        tpiInward<IN_Z | IN_BIAS, false>(c, inst, cy);
-        tpiOutward<true, false>(c, inst, cy, c.vecOut, nullptr);
+        tpiInward<IN_Z | IN_BIAS>(c, inst);
+        tpiOutward<true>(c, inst, c.vecOut, nullptr);
     } else if constexpr (OP == OP_MULM) {
         for (int b = 1; b < c.nb; ++b) idOutDispatch<false>(c, b, inst);
         for (int b = c.nb - 1; b >= 1; --b) idInDispatch<false>(c, b, inst);
     } else if constexpr (OP == OP_MULMINV) {
-        tpiInward<IN_Z, false>(c, inst, cy);             // c.fmobIn == a.vecIn, c.FbodyIn == null (set by the host)
-        tpiOutward<false, false>(c, inst, cy, c.vecOut, nullptr);
+        tpiInward<IN_Z>(c, inst);             // c.fmobIn == a.vecIn, c.FbodyIn == null (set by the host)
+        tpiOutward<false>(c, inst, c.vecOut, nullptr);
     } else if constexpr (OP == OP_RESID) {
         for (int b = 1; b < c.nb; ++b) idOutDispatch<true>(c, b, inst);
         for (int b = c.nb - 1; b >= 1; --b) idInDispatch<true>(c, b, inst);
@@ -128,7 +134,8 @@ __global__ void __launch_bounds__(TPI_THREADS, MINB) tpiKernel(const KArgs a) {
         RkmStepResult r; r.errNorm = 0; r.projected = 0;
         int nproj = 0; double t = a.tcur[inst];
         stateToBlocked(c, a, inst);
-        for (int s = 0; s < a.nsteps; ++s) { r = tpiRkmStep<true>(c, inst, w, a.h, cy); nproj += r.projected; t += a.h; }
+#pragma unroll 1
+        for (int s = 0; s < a.nsteps; ++s) { r = tpiRkmStep<true, JMASK>(c, T, inst, w, a.h, cy); nproj += r.projected; t += a.h; }
         stateFromBlocked(c, a, inst);
         a.tcur[inst] = t;
         a.errNorm[inst] = r.errNorm;
@@ -142,7 +149,7 @@ __global__ void __launch_bounds__(TPI_THREADS, MINB) tpiKernel(const KArgs a) {
         StepLimits lim; lim.accuracy = a.accuracy; lim.minStep = a.minStep; lim.maxStep = a.maxStep;
         AdaptiveState st; st.t = a.tcur[inst]; st.h = a.hcur[inst]; st.lastStep = a.lastStep[inst]; st.steps = 0; st.attempts = 0;
         double lastErr = a.errNorm[inst]; int nproj = 0;
-        tpiRkmAdaptive<true>(c, inst, w, lim, a.tFinal, a.allowInterp, a.maxAttempts, st, cy, lastErr, nproj);
+        tpiRkmAdaptive<true, JMASK>(c, T, inst, w, lim, a.tFinal, a.allowInterp, a.maxAttempts, st, cy, lastErr, nproj);
         stateFromBlocked(c, a, inst);
         a.tcur[inst] = st.t; a.hcur[inst] = st.h; a.lastStep[inst] = st.lastStep;
         a.stepsTaken[inst] += st.steps; a.attempts[inst] += st.attempts;
@@ -208,7 +215,11 @@ cudaError_t launchOp(const KArgs& a, cudaStream_t stream) {
         return cudaGetLastError();
     };
     if constexpr (OP == OP_RKM || OP == OP_RKM_ADAPT) {
-        if (a.lightJoints) return a.stageInSmem ? go(tpiKernel<OP, true, 4>) : go(tpiKernel<OP, false, 4>);
+        // integrator kernels: instantiated per set of mobilizer kinds present in the model
+        constexpr int LIGHT = JM_PIN | JM_SLIDER | JM_UNIVERSAL;
+        const int m = a.jointMask;
+        if ((m & ~JM_PIN) == 0) return a.stageInSmem ? go(tpiKernel<OP, true, SBK_TPI_MINBLOCKS, JM_PIN>) : go(tpiKernel<OP, false, SBK_TPI_MINBLOCKS, JM_PIN>);
+        if ((m & ~LIGHT) == 0)  return a.stageInSmem ? go(tpiKernel<OP, true, SBK_TPI_MINBLOCKS, LIGHT>)  : go(tpiKernel<OP, false, SBK_TPI_MINBLOCKS, LIGHT>);
     }
     return a.stageInSmem ? go(tpiKernel<OP, true, SBK_HEAVY_MINB>) : go(tpiKernel<OP, false, SBK_HEAVY_MINB>);
 }
@@ -243,9 +254,9 @@ template <class F> __device__ __forceinline__ void lpInward(const LpLevels& L, F
     }
 }
 __device__ __forceinline__ void lpEval(const Ctx& c, const int inst, const LpLevels& L, double* qdotDst, double* udotDst, double* qddDst) {
-    lpOutward(L, [&](int b) { kinDispatch<false>(c, b, inst, nullptr, qdotDst); });
-    lpInward(L,  [&](int b) { inwardDispatch<IN_ABI | IN_Z | IN_BIAS | IN_FORCES, false>(c, b, inst, nullptr); });
-    lpOutward(L, [&](int b) { outwardDispatch<true, false>(c, b, inst, nullptr, udotDst, qddDst); });
+    lpOutward(L, [&](int b) { kinDispatch(c, b, inst, qdotDst); });
+    lpInward(L,  [&](int b) { inwardDispatch<IN_ABI | IN_Z | IN_BIAS | IN_FORCES>(c, b, inst); });
+    lpOutward(L, [&](int b) { outwardDispatch<true>(c, b, inst, udotDst, qddDst); });
 }
 
 // Error norm of IntegratorRep::calcErrorNorm, threads over slots / bodies (cf. rkmErrorNorm).
@@ -289,20 +300,20 @@ __global__ void __launch_bounds__(LP_THREADS, 2) lpKernel(const KArgs a) {
     L.start = reinterpret_cast<const int*>(a.tables + a.levelStartOff); L.nlevels = a.nlevels;
 
     if constexpr (OP == OP_KIN) {
-        lpOutward(L, [&](int b) { kinDispatch<false>(c, b, inst, nullptr, c.qdot); });
+        lpOutward(L, [&](int b) { kinDispatch(c, b, inst, c.qdot); });
     } else if constexpr (OP == OP_ABI) {
-        lpInward(L, [&](int b) { inwardDispatch<IN_ABI, false>(c, b, inst, nullptr); });
+        lpInward(L, [&](int b) { inwardDispatch<IN_ABI>(c, b, inst); });
     } else if constexpr (OP == OP_EVAL) {
         lpEval(c, inst, L, c.qdot, c.udot, c.qdotdot);
     } else if constexpr (OP == OP_CALCACC) {
-        lpInward(L,  [&](int b) { inwardDispatch<IN_Z | IN_BIAS, false>(c, b, inst, nullptr); });
-        lpOutward(L, [&](int b) { outwardDispatch<true, false>(c, b, inst, nullptr, c.vecOut, nullptr); });
+        lpInward(L,  [&](int b) { inwardDispatch<IN_Z | IN_BIAS>(c, b, inst); });
+        lpOutward(L, [&](int b) { outwardDispatch<true>(c, b, inst, c.vecOut, nullptr); });
     } else if constexpr (OP == OP_MULM) {
         lpOutward(L, [&](int b) { idOutDispatch<false>(c, b, inst); });
         lpInward(L,  [&](int b) { idInDispatch<false>(c, b, inst); });
     } else if constexpr (OP == OP_MULMINV) {
-        lpInward(L,  [&](int b) { inwardDispatch<IN_Z, false>(c, b, inst, nullptr); });
-        lpOutward(L, [&](int b) { outwardDispatch<false, false>(c, b, inst, nullptr, c.vecOut, nullptr); });
+        lpInward(L,  [&](int b) { inwardDispatch<IN_Z>(c, b, inst); });
+        lpOutward(L, [&](int b) { outwardDispatch<false>(c, b, inst, c.vecOut, nullptr); });
     } else if constexpr (OP == OP_RESID) {
         lpOutward(L, [&](int b) { idOutDispatch<true>(c, b, inst); });
         lpInward(L,  [&](int b) { idInDispatch<true>(c, b, inst); });

@@ -66,6 +66,15 @@ SBK_HD M3 mul(const M3& A, const M3& B) {
             C.a[3*i+j] = A.a[3*i]*B.a[j] + A.a[3*i+1]*B.a[3+j] + A.a[3*i+2]*B.a[6+j];
     return C;
 }
+SBK_HD M3 mulABt(const M3& A, const M3& B) {   // A * ~B
+    M3 C;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            C.a[3*i+j] = A.a[3*i]*B.a[3*j] + A.a[3*i+1]*B.a[3*j+1] + A.a[3*i+2]*B.a[3*j+2];
+    return C;
+}
 SBK_HD V3 col(const M3& R, int j) { return mk(R.a[j], R.a[3+j], R.a[6+j]); }
 SBK_HD M3 identity3() { M3 R; R.a[0]=1; R.a[1]=0; R.a[2]=0; R.a[3]=0; R.a[4]=1; R.a[5]=0; R.a[6]=0; R.a[7]=0; R.a[8]=1; return R; }
 

@@ -26,7 +26,7 @@ struct RkmStepResult { double errNorm; int projected; };
 // Error norm of IntegratorRep::calcErrorNorm with UWeights = 1, no z.
 // err lives in w.ys (overwritten by the caller with the error estimate), q1 = current state.
 template <bool BLK>
-SBK_HD double rkmErrorNorm(const Ctx& c, const int inst, const RkmWork& w) {
+SBK_HD double rkmErrorNorm(const Ctx& c, const Tables& T, const int inst, const RkmWork& w) {
     const int nq = c.nq, nu = c.nu;
     double qAcc = 0, uAcc = 0;
     // u part: uScale_i = |u0_i| > 1 ? 1/|u0_i| : 1   (calcRelativeScaling, frozen at step start)
@@ -39,7 +39,7 @@ SBK_HD double rkmErrorNorm(const Ctx& c, const int inst, const RkmWork& w) {
     }
     // q part: dqw = N * Wu * pinv(N) * dq (scaleDQ); identity except on quaternion slots
     for (int b = 1; b < c.nb; ++b) {
-        const BodyConst& bc = c.bodies[b];
+        const BodyConst& bc = T.bodies[b];
         int first = 0;
         if (bc.joint == JT_BALL || bc.joint == JT_FREE) {
             double q[4], e[4], o[4];
@@ -80,58 +80,75 @@ SBK_HD bool adjustStepSize(const double err, const StepLimits& lim, const bool h
     return nw >= cur;
 }
 
+// out(i, v) for every slot i with v[j] = src_j[i]; operands are loaded a chunk of slots at a time.
+template <bool BLK, int NIN, class Fn>
+SBK_HD void rkmCombine(const Ctx& c, const int inst, const int ny, const double* s0, const double* s1, const double* s2,
+                       const double* s3, const double* s4, Fn out) {
+    constexpr int CH = NIN >= 4 ? 4 : 8;
+    const double* src[5] = {s0, s1, s2, s3, s4};
+    for (int i0 = 0; i0 < ny; i0 += CH) {
+        double v[CH][NIN];
+#pragma unroll
+        for (int k = 0; k < CH; ++k)
+#pragma unroll
+            for (int j = 0; j < NIN; ++j) v[k][j] = (i0 + k < ny) ? ldS<BLK>(c, inst, src[j], i0 + k) : 0.0;
+#pragma unroll
+        for (int k = 0; k < CH; ++k) if (i0 + k < ny) out(i0 + k, v[k]);
+    }
+}
+
 // One RKM attempt.  FRESH = true: start of a step -- evaluate f0 = f(y) and save y0 = y
 // (AbstractIntegratorRep.cpp:390-396).  FRESH = false: retry of a failed attempt with a smaller h
 // from the saved y0 / f0 (no re-evaluation, as in takeOneStep's do/while).
 // The caller's Ctx must have q = w.y, u = w.y + nq*sStride and null qerr / fmobOut / FbodyOut.
-template <bool LEAN, bool FRESH = true>
-SBK_HD RkmStepResult tpiRkmStep(const Ctx& c, const int inst, const RkmWork& w, const double h, double* cy) {
+template <bool LEAN, int JMASK = JM_ALL>
+SBK_HD RkmStepResult tpiRkmStep(const Ctx& c, const Tables& T, const int inst, const RkmWork& w, const double h, double* cy, const bool fresh = true) {
     constexpr bool BLK = LEAN && SBK_DEV_BLK;
     const int nq = c.nq, ny = c.nq + c.nu;
     const long long uoff = BLK ? (long long)nq*BLK_LANES : (long long)nq*c.sStride;   // u rows follow the q rows
 
-    if (FRESH) {
-        // f0 = f(y0): AbstractIntegratorRep.cpp:393 realizeStateDerivatives at the start of the step
-        tpiEvalDerivatives<LEAN>(c, inst, cy, w.f0, w.f0 + uoff, nullptr);
-#pragma unroll 8
-        for (int i = 0; i < ny; ++i) {
-            const double y0 = ldS<BLK>(c, inst, w.y, i);
-            stS<BLK>(c, inst, w.y0, i, y0);
-            stS<BLK>(c, inst, w.y, i, y0 + (h/3)*ldS<BLK>(c, inst, w.f0, i));
+    // The five derivative evaluations share ONE inlined call site (a loop over the stages): no
+    // function-call boundary with its register save/restore inside the step, and one copy of the
+    // sweeps in the instruction cache.  Stage combinations: all operands of a chunk of slots are
+    // requested before the first store, so a chunk costs one trip to memory (the arrays may alias
+    // as far as the compiler knows, and load-store-load-store would serialise on memory latency).
+#pragma unroll 1
+    for (int stage = 0; stage < 5; ++stage) {
+        double* fdst = stage == 0 ? w.f0 : (stage == 3 ? w.fb : w.fa);
+        // stage 0: f0 = f(y0), AbstractIntegratorRep.cpp:393 realizeStateDerivatives at the start of a step;
+        // a retry after a failed attempt keeps the saved y0 / f0
+        if (stage > 0 || fresh) tpiEvalDerivatives<LEAN, JMASK>(c, T, inst, cy, fdst, fdst + uoff, nullptr);
+        if (stage == 0) {
+            if (fresh) rkmCombine<BLK, 2>(c, inst, ny, w.y, w.f0, nullptr, nullptr, nullptr, [&](int i, const double* v) {
+                           stS<BLK>(c, inst, w.y0, i, v[0]);
+                           stS<BLK>(c, inst, w.y, i, v[0] + (h/3)*v[1]); });
+            else       rkmCombine<BLK, 2>(c, inst, ny, w.y0, w.f0, nullptr, nullptr, nullptr, [&](int i, const double* v) {
+                           stS<BLK>(c, inst, w.y, i, v[0] + (h/3)*v[1]); });
+        } else if (stage == 1) {                                                             // fa = f1
+            rkmCombine<BLK, 3>(c, inst, ny, w.y0, w.f0, w.fa, nullptr, nullptr, [&](int i, const double* v) {
+                stS<BLK>(c, inst, w.y, i, v[0] + (h/6)*(v[1] + v[2])); });
+        } else if (stage == 2) {                                                             // fa = f2
+            rkmCombine<BLK, 3>(c, inst, ny, w.y0, w.f0, w.fa, nullptr, nullptr, [&](int i, const double* v) {
+                stS<BLK>(c, inst, w.y, i, v[0] + (h/8)*(v[1] + 3*v[2])); });
+        } else if (stage == 3) {                                                             // fb = f3
+            rkmCombine<BLK, 4>(c, inst, ny, w.y0, w.f0, w.fa, w.fb, nullptr, [&](int i, const double* v) {
+                const double ys = v[0] + (h/2)*(v[1] - 3*v[2] + 4*v[3]);
+                stS<BLK>(c, inst, w.ys, i, ys); stS<BLK>(c, inst, w.y, i, ys); });
+        } else {                                                                             // fa = f4
+            rkmCombine<BLK, 5>(c, inst, ny, w.y0, w.f0, w.fb, w.fa, w.ys, [&](int i, const double* v) {
+                const double y1 = v[0] + (h/6)*(v[1] + 4*v[2] + v[3]);
+                stS<BLK>(c, inst, w.y, i, y1);
+                stS<BLK>(c, inst, w.ys, i, 0.2*fabs(y1 - v[4])); });                        // y1err
         }
-    } else {
-#pragma unroll 8
-        for (int i = 0; i < ny; ++i) stS<BLK>(c, inst, w.y, i, ldS<BLK>(c, inst, w.y0, i) + (h/3)*ldS<BLK>(c, inst, w.f0, i));
-    }
-    tpiEvalDerivatives<LEAN>(c, inst, cy, w.fa, w.fa + uoff, nullptr);                    // f1
-#pragma unroll 8
-    for (int i = 0; i < ny; ++i)
-        stS<BLK>(c, inst, w.y, i, ldS<BLK>(c, inst, w.y0, i) + (h/6)*(ldS<BLK>(c, inst, w.f0, i) + ldS<BLK>(c, inst, w.fa, i)));
-    tpiEvalDerivatives<LEAN>(c, inst, cy, w.fa, w.fa + uoff, nullptr);                    // f2 -> fa
-#pragma unroll 8
-    for (int i = 0; i < ny; ++i)
-        stS<BLK>(c, inst, w.y, i, ldS<BLK>(c, inst, w.y0, i) + (h/8)*(ldS<BLK>(c, inst, w.f0, i) + 3*ldS<BLK>(c, inst, w.fa, i)));
-    tpiEvalDerivatives<LEAN>(c, inst, cy, w.fb, w.fb + uoff, nullptr);                    // f3 -> fb
-#pragma unroll 8
-    for (int i = 0; i < ny; ++i) {
-        const double ys = ldS<BLK>(c, inst, w.y0, i) + (h/2)*(ldS<BLK>(c, inst, w.f0, i) - 3*ldS<BLK>(c, inst, w.fa, i) + 4*ldS<BLK>(c, inst, w.fb, i));
-        stS<BLK>(c, inst, w.ys, i, ys); stS<BLK>(c, inst, w.y, i, ys);
-    }
-    tpiEvalDerivatives<LEAN>(c, inst, cy, w.fa, w.fa + uoff, nullptr);                    // f4 -> fa
-#pragma unroll 8
-    for (int i = 0; i < ny; ++i) {
-        const double y1 = ldS<BLK>(c, inst, w.y0, i) + (h/6)*(ldS<BLK>(c, inst, w.f0, i) + 4*ldS<BLK>(c, inst, w.fb, i) + ldS<BLK>(c, inst, w.fa, i));
-        stS<BLK>(c, inst, w.y, i, y1);
-        stS<BLK>(c, inst, w.ys, i, 0.2*fabs(y1 - ldS<BLK>(c, inst, w.ys, i)));                            // y1err
     }
 
     RkmStepResult res; res.projected = 0;
-    res.errNorm = rkmErrorNorm<BLK>(c, inst, w);
+    res.errNorm = rkmErrorNorm<BLK>(c, T, inst, w);
     // attemptDAEStep: project only if errNorm <= 2^4 * accuracy (AbstractIntegratorRep.cpp:165-166)
     if (c.nquat > 0 && !(res.errNorm > 16.0*w.accuracy)) {
         double acc = 0;
         for (int b = 1; b < c.nb; ++b) {
-            const BodyConst& bc = c.bodies[b];
+            const BodyConst& bc = T.bodies[b];
             if (bc.joint != JT_BALL && bc.joint != JT_FREE) continue;
             double n2 = 0;
 #pragma unroll
@@ -142,7 +159,7 @@ SBK_HD RkmStepResult tpiRkmStep(const Ctx& c, const int inst, const RkmWork& w, 
         const double quatNorm = w.useInfNorm ? acc : sqrt(acc/c.nquat);
         if (quatNorm > w.consTol || w.projectEveryStep) {
             for (int b = 1; b < c.nb; ++b) {
-                const BodyConst& bc = c.bodies[b];
+                const BodyConst& bc = T.bodies[b];
                 if (bc.joint != JT_BALL && bc.joint != JT_FREE) continue;
                 double q[4], e[4], n2 = 0;
 #pragma unroll
@@ -155,7 +172,7 @@ SBK_HD RkmStepResult tpiRkmStep(const Ctx& c, const int inst, const RkmWork& w, 
                 for (int i = 0; i < 4; ++i) { stS<BLK>(c, inst, w.y, bc.q0 + i, q[i]); stS<BLK>(c, inst, w.ys, bc.q0 + i, e[i] - dt*q[i]); }
             }
             res.projected = 1;
-            res.errNorm = rkmErrorNorm<BLK>(c, inst, w);      // takeOneStep recomputes it (AbstractIntegratorRep.cpp:556)
+            res.errNorm = rkmErrorNorm<BLK>(c, T, inst, w);      // takeOneStep recomputes it (AbstractIntegratorRep.cpp:556)
         }
     }
     return res;
@@ -166,8 +183,8 @@ SBK_HD RkmStepResult tpiRkmStep(const Ctx& c, const int inst, const RkmWork& w, 
 // reference's default) steps are never shortened to hit tFinal, so the advanced state ends at
 // t >= tFinal; without it the last step lands on tFinal (hWasArtificiallyLimited logic).
 struct AdaptiveState { double t, h, lastStep; int steps, attempts; };
-template <bool LEAN>
-SBK_HD void tpiRkmAdaptive(const Ctx& c, const int inst, const RkmWork& w, const StepLimits& lim, const double tFinal,
+template <bool LEAN, int JMASK = JM_ALL>
+SBK_HD void tpiRkmAdaptive(const Ctx& c, const Tables& T, const int inst, const RkmWork& w, const StepLimits& lim, const double tFinal,
                            const int allowInterpolation, const int maxAttempts, AdaptiveState& st, double* cy,
                            double& lastErr, int& nproj) {
     constexpr bool BLK = LEAN && SBK_DEV_BLK;
@@ -181,7 +198,7 @@ SBK_HD void tpiRkmAdaptive(const Ctx& c, const int inst, const RkmWork& w, const
             else if (tFinal > st.t + 1.001*st.h) t1 = st.t + st.h;
             else t1 = tFinal;
             const double hTry = t1 - st.t;
-            const RkmStepResult r = fresh ? tpiRkmStep<LEAN, true>(c, inst, w, hTry, cy) : tpiRkmStep<LEAN, false>(c, inst, w, hTry, cy);
+            const RkmStepResult r = tpiRkmStep<LEAN, JMASK>(c, T, inst, w, hTry, cy, fresh);
             fresh = false; ++st.attempts; --budget; nproj += r.projected; lastErr = r.errNorm;
             ok = adjustStepSize(r.errNorm, lim, limited, st.h);
         } while (!ok && budget > 0);

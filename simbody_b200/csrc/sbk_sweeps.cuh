@@ -65,7 +65,9 @@ enum { CACHE_RECORD_MAX = F_H + 13*6 + 36 };   // 195
 enum { BF_PARENT_PREV = 1,   // parent is the body processed just before (index - 1): links ride in the carry
        BF_STORE_LINK  = 2,   // some child is NOT index + 1: links must also be stored in the cache
        BF_NO_R_PF     = 4,   // R_PF is exactly the identity (the reference's noR_PF template flag,
-       BF_NO_R_MB     = 8 }; // RigidBodyNodeSpec_Derived.cpp:50-64); likewise R_MB: skip the products
+       BF_NO_R_MB     = 8,   // RigidBodyNodeSpec_Derived.cpp:50-64); likewise R_MB: skip the products
+       BF_TIP         = 16 };// body index + 1 is NOT a child: the inward sweep of the integrator path starts its
+                             // reverse kinematics here, from the X_GB, V_GB the outward sweep stored
 
 // Per-body constants (batch-shared; staged into shared memory by the kernels).
 struct BodyConst {
@@ -104,14 +106,22 @@ struct Ctx {
     int* status;                                    // per-instance status words [N]
 };
 
-// Links between consecutive bodies of one instance in LEAN mode: a column of CARRY_ROWS doubles
-// per work item in SHARED memory ([row][thread], conflict-free), reused by the three sweeps:
-//   sweeps A+B : X_GB (12) + V_GB (6) of the previous body      rows 0..17
-//   sweep  C/D : P+ (21) + z+ (6) + Phi.l (3) of the next body  rows 0..29
-//   sweep  E   : A_GB (6) of the previous body                  rows 0..5
+// The batch-shared tables as the integrator kernels see them: plain local pointers derived from
+// the shared-memory staging buffer (or the global blob), so that after inlining the compiler knows
+// their address space and emits LDS / LDG instead of generic loads.
+struct Tables { const BodyConst* bodies; const int* children; const ForceConst* forces; };
+SBK_HD Tables tablesOf(const Ctx& c) { Tables t; t.bodies = c.bodies; t.children = c.children; t.forces = c.forces; return t; }
+
+// Links between consecutive bodies of one instance on the integrator (LEAN) path: a column of
+// CARRY_ROWS doubles per work item in SHARED memory ([row][thread], conflict-free), reused by
+// the three sweeps:
+//   outward sweeps : X_GB (12) + V_GB (6) of the previous body, rows 0..17; A_GB (6) rows 18..23
+//   inward sweep   : P+ (21) + z+ (6) + Phi.l (3) of the next body (a child), rows 0..29;
+//                    X_GB (12) + V_GB (6) of THIS body as recovered by that child's reverse
+//                    kinematics, rows 30..47
 // Body b-1 is always the previous body of an outward sweep and b+1 of an inward one, so no
 // bookkeeping is needed: BF_PARENT_PREV says whether the parent is b-1.
-enum { CARRY_ROWS = 30 };
+enum { CARRY_ROWS = 56, CY_A = 18, CY_SELF = 30, CY_PRE = 48 };   // rows 48..55: two coordinate preload slots
 #if defined(__CUDA_ARCH__)
 #define SBK_CARRY_STRIDE 128
 #else
@@ -254,63 +264,82 @@ template <int d> struct KinOut {     // results of sweeps A+B for one body
     SV acor, gyro;                   // mobilizer coriolis acceleration a, gyroscopic force b
 };
 
+// Position kinematics that depend on the mobilizer coordinates only (no parent quantities):
+// X_FM, H_FM, and X_PB = X_PF * X_FM * X_MB (RigidBodyNodeSpec.h:554-569).
+template <int d> struct KinLocal {
+    M3 R_FM; V3 Hw[d], Hv[d];        // H_FM columns (angular, linear), expressed in F
+    V3 r;                            // r_MB_F = R_FM * p_MB
+    M3 R_PB; V3 p_PB;                // X_PB
+    double qerr;                     // |q| - 1 for quaternion mobilizers
+};
+
 template <int JT>
-SBK_HD void kinCore(const BodyConst& bc, const double* q, const double* u,
-                    const M3& R_GP, const V3 p_GP, const SV V_GP,
-                    KinOut<JointDims<JT>::nu>& o, double* qdot, double& qerr) {
+SBK_HD void kinLocal(const BodyConst& bc, const double* q, KinLocal<JointDims<JT>::nu>& k) {
     constexpr int d = JointDims<JT>::nu;
-    // ---- mobilizer-specific: X_FM, H_FM, HDot_FM (all expressed in F) ----------------------
-    M3 R_FM; V3 p_FM = zero3();
-    V3 Hw[d], Hv[d];          // H_FM columns (angular, linear)
-    V3 HDw[d];                // HDot_FM angular part (linear part is zero for all five mobilizers)
+    V3 p_FM = zero3();
 #pragma unroll
-    for (int j = 0; j < d; ++j) { Hw[j] = zero3(); Hv[j] = zero3(); HDw[j] = zero3(); }
-    qerr = 0;
+    for (int j = 0; j < d; ++j) { k.Hw[j] = zero3(); k.Hv[j] = zero3(); }
+    k.qerr = 0;
+    M3& R_FM = k.R_FM;
 
     if constexpr (JT == JT_PIN) {                 // RigidBodyNodeSpec_Pin.h:103-140
         double s, co; sincos(q[0], &s, &co);
         R_FM.a[0] = co; R_FM.a[1] = -s; R_FM.a[2] = 0;
         R_FM.a[3] = s;  R_FM.a[4] = co; R_FM.a[5] = 0;
         R_FM.a[6] = 0;  R_FM.a[7] = 0;  R_FM.a[8] = 1;
-        Hw[0] = mk(0, 0, 1);
+        k.Hw[0] = mk(0, 0, 1);
     } else if constexpr (JT == JT_SLIDER) {       // RigidBodyNodeSpec_Slider.h:91-127
         R_FM = identity3(); p_FM = mk(q[0], 0, 0);
-        Hv[0] = mk(1, 0, 0);
+        k.Hv[0] = mk(1, 0, 0);
     } else if constexpr (JT == JT_UNIVERSAL) {    // RigidBodyNodeSpec_Universal.h:124-192, Rotation.cpp:241-264
         double s1, c1, s2, c2; sincos(q[0], &s1, &c1); sincos(q[1], &s2, &c2);
         R_FM.a[0] = c2;      R_FM.a[1] = 0;  R_FM.a[2] = s2;
         R_FM.a[3] = s2*s1;   R_FM.a[4] = c1; R_FM.a[5] = -s1*c2;
         R_FM.a[6] = -s2*c1;  R_FM.a[7] = s1; R_FM.a[8] = c1*c2;
-        Hw[0] = mk(1, 0, 0);
-        Hw[1] = col(R_FM, 1);
+        k.Hw[0] = mk(1, 0, 0);
+        k.Hw[1] = col(R_FM, 1);
     } else {                                      // Ball / Free: RigidBodyNodeSpec_Ball.h:113-180, _Free.h:142-222
         const double quatLen = sqrt(q[0]*q[0] + q[1]*q[1] + q[2]*q[2] + q[3]*q[3]);
-        qerr = quatLen - 1.0;
+        k.qerr = quatLen - 1.0;
         const double oon = 1.0/quatLen;
         R_FM = rotFromQuat(q[0]*oon, q[1]*oon, q[2]*oon, q[3]*oon);
-        Hw[0] = mk(1, 0, 0); Hw[1] = mk(0, 1, 0); Hw[2] = mk(0, 0, 1);
+        k.Hw[0] = mk(1, 0, 0); k.Hw[1] = mk(0, 1, 0); k.Hw[2] = mk(0, 0, 1);
         if constexpr (JT == JT_FREE) {
             p_FM = mk(q[4], q[5], q[6]);
-            Hv[3] = mk(1, 0, 0); Hv[4] = mk(0, 1, 0); Hv[5] = mk(0, 0, 1);
+            k.Hv[3] = mk(1, 0, 0); k.Hv[4] = mk(0, 1, 0); k.Hv[5] = mk(0, 0, 1);
         }
     }
 
-    // ---- calcBodyTransforms (RigidBodyNodeSpec.h:554-569) ------------------------------------
+    // ---- calcBodyTransforms, parent-independent part (RigidBodyNodeSpec.h:554-569) ------------
     const M3 R_PF = loadR(bc.X_PF), R_MB = loadR(bc.X_MB);
     const V3 p_PF = loadP(bc.X_PF), p_MB = loadP(bc.X_MB);
-
     // Multiplying by an exact identity is skipped (same values up to the sign of zeros), as the
     // reference does through its noR_PF / noX_MB template flags.
     const bool noRPF = (bc.flags & BF_NO_R_PF) != 0, noRMB = (bc.flags & BF_NO_R_MB) != 0;
-    const V3 r     = mul(R_FM, p_MB);                 // r_MB_F = R_FM * p_MB
-    const M3 R_FB  = noRMB ? R_FM : mul(R_FM, R_MB);  const V3 p_FB = p_FM + r;
-    const M3 R_PB  = noRPF ? R_FB : mul(R_PF, R_FB);  const V3 p_PB = p_PF + (noRPF ? p_FB : mul(R_PF, p_FB));
-    o.R = mul(R_GP, R_PB);
-    o.l = mul(R_GP, p_PB);                            // Phi: p_PB_G (RigidBodyNode.cpp:61)
+    k.r = mul(R_FM, p_MB);                             // r_MB_F = R_FM * p_MB
+    const M3 R_FB = noRMB ? R_FM : mul(R_FM, R_MB);  const V3 p_FB = p_FM + k.r;
+    k.R_PB = noRPF ? R_FB : mul(R_PF, R_FB);
+    k.p_PB = p_PF + (noRPF ? p_FB : mul(R_PF, p_FB));
+}
+
+// Everything that needs the parent's X_GP, V_GP.
+template <int JT>
+SBK_HD void kinGlobal(const BodyConst& bc, const KinLocal<JointDims<JT>::nu>& k, const double* q, const double* u,
+                      const M3& R_GP, const V3 p_GP, const SV V_GP,
+                      KinOut<JointDims<JT>::nu>& o, double* qdot) {
+    constexpr int d = JointDims<JT>::nu;
+    const bool noRPF = (bc.flags & BF_NO_R_PF) != 0;
+    const V3* Hw = k.Hw; const V3* Hv = k.Hv; const V3 r = k.r;
+    V3 HDw[d];                // HDot_FM angular part (linear part is zero for all five mobilizers)
+#pragma unroll
+    for (int j = 0; j < d; ++j) HDw[j] = zero3();
+
+    o.R = mul(R_GP, k.R_PB);
+    o.l = mul(R_GP, k.p_PB);                          // Phi: p_PB_G (RigidBodyNode.cpp:61)
     o.p = p_GP + o.l;
 
     // ---- H = R_GF (H_FM + H_MB_F)  (RigidBodyNodeSpec.cpp:44-74) -----------------------------
-    const M3 R_GF = noRPF ? R_GP : mul(R_GP, R_PF);
+    const M3 R_GF = noRPF ? R_GP : mul(R_GP, loadR(bc.X_PF));
 #pragma unroll
     for (int j = 0; j < d; ++j) {
         o.H[j].w = mul(R_GF, Hw[j]);
@@ -326,7 +355,7 @@ SBK_HD void kinCore(const BodyConst& bc, const double* q, const double* u,
     V3 w_FM = zero3(); SV V_PB = zeroSV();
 #pragma unroll
     for (int j = 0; j < d; ++j) { w_FM = w_FM + u[j]*Hw[j]; V_PB = V_PB + u[j]*o.H[j]; }
-    if constexpr (JT == JT_UNIVERSAL) HDw[1] = cross(w_FM, col(R_FM, 1));   // _Universal.h:176-190
+    if constexpr (JT == JT_UNIVERSAL) HDw[1] = cross(w_FM, col(k.R_FM, 1));   // _Universal.h:176-190
 
     // HDot (RigidBodyNodeSpec.cpp:82-129) and VD = HDot*u
     const V3 w_GP = V_GP.w, v_GP = V_GP.v;
@@ -357,6 +386,45 @@ SBK_HD void kinCore(const BodyConst& bc, const double* q, const double* u,
 #pragma unroll
         for (int i = 0; i < d; ++i) qdot[i] = u[i];
     }
+}
+
+template <int JT>
+SBK_HD void kinCore(const BodyConst& bc, const double* q, const double* u,
+                    const M3& R_GP, const V3 p_GP, const SV V_GP,
+                    KinOut<JointDims<JT>::nu>& o, double* qdot, double& qerr) {
+    KinLocal<JointDims<JT>::nu> k;
+    kinLocal<JT>(bc, q, k);
+    kinGlobal<JT>(bc, k, q, u, R_GP, p_GP, V_GP, o, qdot);
+    qerr = k.qerr;
+}
+
+// The recurrences X_GB = X_GP * X_PB and V_GB = ~Phi V_GP + H u run base->tip; the integrator
+// path also needs them tip->base (the articulated-inertia sweep), and instead of storing every
+// body's kinematics in HBM for that sweep it INVERTS the recurrence: given the body's own
+// X_GB, V_GB it recovers the parent's,
+//     R_GP = R_GB * ~R_PB,  p_GP = p_GB - R_GP p_PB,  V_GP = Phi^-T (V_GB - H u),
+// and then recomputes the body's kinematic quantities from (X_GP, V_GP) with the same formulas
+// as the outward sweeps.  Exact in exact arithmetic; in FP64 the recovered parent transform
+// differs from the stored one by a few ulp per body (orthogonal factors, no amplification).
+template <int JT>
+SBK_HD void kinReverse(const BodyConst& bc, const KinLocal<JointDims<JT>::nu>& k, const double* u,
+                       const M3& R_GB, const V3 p_GB, const SV V_GB, M3& R_GP, V3& p_GP, SV& V_GP) {
+    constexpr int d = JointDims<JT>::nu;
+    R_GP = mulABt(R_GB, k.R_PB);
+    const V3 l = mul(R_GP, k.p_PB);
+    p_GP = p_GB - l;
+    const bool noRPF = (bc.flags & BF_NO_R_PF) != 0;
+    const M3 R_GF = noRPF ? R_GP : mul(R_GP, loadR(bc.X_PF));
+    SV V_PB = zeroSV();
+#pragma unroll
+    for (int j = 0; j < d; ++j) {
+        SV Hj;
+        Hj.w = mul(R_GF, k.Hw[j]);
+        Hj.v = mul(R_GF, k.Hv[j] + cross(k.Hw[j], k.r));
+        V_PB = V_PB + u[j]*Hj;
+    }
+    V_GP.w = V_GB.w - V_PB.w;
+    V_GP.v = (V_GB.v - V_PB.v) - cross(V_GP.w, l);
 }
 
 template <int d> struct AbiOut { SV G[d]; double DI[d*d]; ABI PP; SV zb; bool ok; };
@@ -478,40 +546,36 @@ SBK_HD void mobilityForces(const BodyConst& bc, const ForceConst* forces, const 
 }
 
 //==============================================================================================
-//                     BODY WRAPPERS (cache records in HBM + per-work-item carry)
+//                     BODY WRAPPERS, FULL records (API realize path)
 //==============================================================================================
-// LEAN = false: every field is stored (API realize path: getters and operators need them).
-// LEAN = true : integrator path; links ride in the carry when the tree order allows.
+// Every field of the per-body record is stored: getters and the operator forms need them.
 
-template <int JT, bool LEAN>
-SBK_BODY void kinBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, const int inst, double* cy, double* qdotDst) {
+template <int JT>
+SBK_BODY void kinBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, const int inst, double* qdotDst) {
     constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
-    constexpr bool BLK = LEAN && SBK_DEV_BLK;
-    const CacheRefT<BLK> me = cacheOf<BLK>(c, inst, bc.cacheBase);
+    const CacheRef me = cacheOf<false>(c, inst, bc.cacheBase);
     double q[NQ], u[d], qdot[NQ], qerr;
 #pragma unroll
-    for (int i = 0; i < NQ; ++i) q[i] = ldS<BLK>(c, inst, c.q, bc.q0 + i);
+    for (int i = 0; i < NQ; ++i) q[i] = ldS<false>(c, inst, c.q, bc.q0 + i);
 #pragma unroll
-    for (int i = 0; i < d; ++i)  u[i] = ldS<BLK>(c, inst, c.u, bc.u0 + i);
+    for (int i = 0; i < d; ++i)  u[i] = ldS<false>(c, inst, c.u, bc.u0 + i);
 
-    M3 R_GP; V3 p_GP; SV V_GP;
-    if (LEAN && (bc.flags & BF_PARENT_PREV)) cyLoadOut(cy, R_GP, p_GP, V_GP);
-    else { const CacheRefT<BLK> pa = cacheOf<BLK>(c, inst, bc.parentCacheBase); R_GP = pa.ldM3(F_XGB); p_GP = pa.ld3(F_XGB + 9); V_GP = pa.ldSV(F_VGB); }
+    const CacheRef pa = cacheOf<false>(c, inst, bc.parentCacheBase);
+    const M3 R_GP = pa.ldM3(F_XGB); const V3 p_GP = pa.ld3(F_XGB + 9); const SV V_GP = pa.ldSV(F_VGB);
 
     KinOut<d> o;
     kinCore<JT>(bc, q, u, R_GP, p_GP, V_GP, o, qdot, qerr);
 
-    if (!LEAN || (bc.flags & BF_STORE_LINK)) { me.stM3(F_XGB, o.R); me.st3(F_XGB + 9, o.p); me.stSV(F_VGB, o.V); }
-    if (LEAN) cyStoreOut(cy, o.R, o.p, o.V);
+    me.stM3(F_XGB, o.R); me.st3(F_XGB + 9, o.p); me.stSV(F_VGB, o.V);
     me.st3(F_L, o.l); me.st3(F_MK, o.c); me.stS3(F_MK + 3, o.G);
     me.stSV(F_ACOR, o.acor); me.stSV(F_GYRO, o.gyro);
 #pragma unroll
     for (int j = 0; j < d; ++j) me.stSV(F_H + 6*j, o.H[j]);
     if (qdotDst) {
 #pragma unroll
-        for (int i = 0; i < NQ; ++i) stS<BLK>(c, inst, qdotDst, bc.q0 + i, qdot[i]);
+        for (int i = 0; i < NQ; ++i) stS<false>(c, inst, qdotDst, bc.q0 + i, qdot[i]);
     }
-    if constexpr (JT == JT_BALL || JT == JT_FREE) { if (c.qerr) stS<BLK>(c, inst, c.qerr, bc.quat, qerr); }
+    if constexpr (JT == JT_BALL || JT == JT_FREE) { if (c.qerr) stS<false>(c, inst, c.qerr, bc.quat, qerr); }
 }
 
 // Inward body step.  MODE bits:
@@ -522,117 +586,97 @@ SBK_BODY void kinBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, co
 //             rather than from c.fmobIn / c.FbodyIn
 enum { IN_ABI = 1, IN_Z = 2, IN_BIAS = 4, IN_FORCES = 8 };
 
-template <int JT, int MODE, bool LEAN>
-SBK_BODY void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, const int inst, double* cy) {
+SBK_HD void setSingular(const Ctx& c, const int inst) {
+    if (!c.status) return;
+#if defined(__CUDA_ARCH__)
+    atomicOr(c.status + inst, 2);
+#else
+    c.status[inst] |= 2;
+#endif
+}
+
+template <int JT, int MODE>
+SBK_BODY void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, const int inst) {
     constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
-    constexpr bool BLK = LEAN && SBK_DEV_BLK;
-    const CacheRefT<BLK> me = cacheOf<BLK>(c, inst, bc.cacheBase);
-    const CacheRefT<BLK>& in = me;
-    // every input of the body step is requested up front: one wait on global memory per body
+    const CacheRef me = cacheOf<false>(c, inst, bc.cacheBase);
     SV H[d];
 #pragma unroll
-    for (int j = 0; j < d; ++j) H[j] = in.ldSV(F_H + 6*j);
-    const V3 c_G = in.ld3(F_MK);
-    V3 lMe = zero3();
-    if (LEAN) lMe = in.ld3(F_L);
-    S3 G_Gin; SV acorIn = zeroSV(), gyroIn = zeroSV();
-    if constexpr ((MODE & IN_ABI) != 0) { G_Gin = in.ldS3(F_MK + 3); acorIn = in.ldSV(F_ACOR); gyroIn = in.ldSV(F_GYRO); }
-    // q, u for the spring/damper elements are requested here, together with the record, so that the
-    // body step waits on global memory once (not once more when the forces are evaluated)
-    double qF[NQ], uF[d];
-    if constexpr ((MODE & IN_FORCES) != 0) {
-        if (bc.nforce > 0) {
-#pragma unroll
-            for (int i = 0; i < NQ; ++i) qF[i] = ldS<BLK>(c, inst, c.q, bc.q0 + i);
-#pragma unroll
-            for (int i = 0; i < d; ++i)  uF[i] = ldS<BLK>(c, inst, c.u, bc.u0 + i);
-        }
-    }
-    const bool linkToCache = !LEAN || !(bc.flags & BF_PARENT_PREV);
-    // the adjacent child (index + 1), if any, left its links in the carry
-    ABI cPP; SV czP = zeroSV(); V3 cl = zero3();
-    bool haveCarryChild = false;
-    if (LEAN && bc.nchild > 0 && c.children[bc.childStart] == bodyIndex + 1) { cyLoadIn(cy, cPP, czP, cl); haveCarryChild = true; }
+    for (int j = 0; j < d; ++j) H[j] = me.ldSV(F_H + 6*j);
+    const V3 c_G = me.ld3(F_MK);
 
     AbiOut<d> ao; ao.zb = zeroSV();
     if constexpr ((MODE & IN_ABI) != 0) {
-        ABI P = abiFromRigid(bc.mass, c_G, G_Gin);
+        const S3 G_G = me.ldS3(F_MK + 3); const SV acor = me.ldSV(F_ACOR), gyro = me.ldSV(F_GYRO);
+        ABI P = abiFromRigid(bc.mass, c_G, G_G);
         for (int k = 0; k < bc.nchild; ++k) {
-            if (k == 0 && haveCarryChild) { addInto(P, shiftABI(cPP, cl)); continue; }
-            const CacheRefT<BLK> ch = cacheOf<BLK>(c, inst, c.bodies[c.children[bc.childStart + k]].cacheBase);
+            const CacheRef ch = cacheOf<false>(c, inst, c.bodies[c.children[bc.childStart + k]].cacheBase);
             addInto(P, shiftABI(ch.ldABI(F_PPLUS), ch.ld3(F_L)));
         }
-        abiCore<d>(P, H, acorIn, gyroIn, ao);
-        if (!ao.ok && c.status) {
-#if defined(__CUDA_ARCH__)
-            atomicOr(c.status + inst, 2);
-#else
-            c.status[inst] |= 2;
-#endif
-        }
+        abiCore<d>(P, H, acor, gyro, ao);
+        if (!ao.ok) setSingular(c, inst);
 #pragma unroll
         for (int j = 0; j < d; ++j) me.stSV(fG(d) + 6*j, ao.G[j]);
 #pragma unroll
         for (int i = 0; i < d*d; ++i) me.st(fDI(d) + i, ao.DI[i]);
-        if (linkToCache) me.stABI(F_PPLUS, ao.PP);
-        if (!LEAN) me.stSV(F_ZB, ao.zb);
+        me.stABI(F_PPLUS, ao.PP);
+        me.stSV(F_ZB, ao.zb);
     } else {
 #pragma unroll
         for (int j = 0; j < d; ++j) ao.G[j] = me.ldSV(fG(d) + 6*j);
         if constexpr ((MODE & IN_BIAS) != 0) ao.zb = me.ldSV(F_ZB);
     }
 
-    SV zPlus = zeroSV();
     if constexpr ((MODE & IN_Z) != 0) {
         // ---- applied forces -------------------------------------------------------------------
         SV F = zeroSV(); double f[d];
         if constexpr ((MODE & IN_FORCES) != 0) {
+            double qF[NQ], uF[d];
+            if (bc.nforce > 0) {
+#pragma unroll
+                for (int i = 0; i < NQ; ++i) qF[i] = ldS<false>(c, inst, c.q, bc.q0 + i);
+#pragma unroll
+                for (int i = 0; i < d; ++i)  uF[i] = ldS<false>(c, inst, c.u, bc.u0 + i);
+            }
             F = gravityForce(bc.mass, c_G, c.gx, c.gy, c.gz);
             mobilityForces<d>(bc, c.forces, qF, uF, f);
             if (c.fmobOut) {
 #pragma unroll
-                for (int j = 0; j < d; ++j) stS<BLK>(c, inst, c.fmobOut, bc.u0 + j, f[j]);
+                for (int j = 0; j < d; ++j) stS<false>(c, inst, c.fmobOut, bc.u0 + j, f[j]);
             }
             if (c.FbodyOut) {
-                stS<BLK>(c, inst, c.FbodyOut, 6*bodyIndex+0, F.w.x); stS<BLK>(c, inst, c.FbodyOut, 6*bodyIndex+1, F.w.y); stS<BLK>(c, inst, c.FbodyOut, 6*bodyIndex+2, F.w.z);
-                stS<BLK>(c, inst, c.FbodyOut, 6*bodyIndex+3, F.v.x); stS<BLK>(c, inst, c.FbodyOut, 6*bodyIndex+4, F.v.y); stS<BLK>(c, inst, c.FbodyOut, 6*bodyIndex+5, F.v.z);
+                stS<false>(c, inst, c.FbodyOut, 6*bodyIndex+0, F.w.x); stS<false>(c, inst, c.FbodyOut, 6*bodyIndex+1, F.w.y); stS<false>(c, inst, c.FbodyOut, 6*bodyIndex+2, F.w.z);
+                stS<false>(c, inst, c.FbodyOut, 6*bodyIndex+3, F.v.x); stS<false>(c, inst, c.FbodyOut, 6*bodyIndex+4, F.v.y); stS<false>(c, inst, c.FbodyOut, 6*bodyIndex+5, F.v.z);
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < d; ++j) f[j] = c.fmobIn ? ldS<BLK>(c, inst, c.fmobIn, bc.u0 + j) : 0.0;
+            for (int j = 0; j < d; ++j) f[j] = c.fmobIn ? ldS<false>(c, inst, c.fmobIn, bc.u0 + j) : 0.0;
             if (c.FbodyIn) {
-                F.w = mk(ldS<BLK>(c, inst, c.FbodyIn, 6*bodyIndex+0), ldS<BLK>(c, inst, c.FbodyIn, 6*bodyIndex+1), ldS<BLK>(c, inst, c.FbodyIn, 6*bodyIndex+2));
-                F.v = mk(ldS<BLK>(c, inst, c.FbodyIn, 6*bodyIndex+3), ldS<BLK>(c, inst, c.FbodyIn, 6*bodyIndex+4), ldS<BLK>(c, inst, c.FbodyIn, 6*bodyIndex+5));
+                F.w = mk(ldS<false>(c, inst, c.FbodyIn, 6*bodyIndex+0), ldS<false>(c, inst, c.FbodyIn, 6*bodyIndex+1), ldS<false>(c, inst, c.FbodyIn, 6*bodyIndex+2));
+                F.v = mk(ldS<false>(c, inst, c.FbodyIn, 6*bodyIndex+3), ldS<false>(c, inst, c.FbodyIn, 6*bodyIndex+4), ldS<false>(c, inst, c.FbodyIn, 6*bodyIndex+5));
             }
         }
         // ---- calcUDotPass1Inward (RigidBodyNodeSpec.cpp:355-400) / M^-1 pass 1 (:483-515) ------
         SV z;
         if constexpr ((MODE & IN_BIAS) != 0) z = ao.zb - F; else z = zeroSV();
         for (int k = 0; k < bc.nchild; ++k) {
-            if (k == 0 && haveCarryChild) { z = z + phi(cl, czP); continue; }
-            const CacheRefT<BLK> ch = cacheOf<BLK>(c, inst, c.bodies[c.children[bc.childStart + k]].cacheBase);
+            const CacheRef ch = cacheOf<false>(c, inst, c.bodies[c.children[bc.childStart + k]].cacheBase);
             z = z + phi(ch.ld3(F_L), ch.ldSV(F_ZPLUS));
         }
-        double eps[d];
+        double eps[d]; SV zPlus;
         zCore<d>(H, ao.G, z, f, eps, zPlus);
 #pragma unroll
         for (int j = 0; j < d; ++j) me.st(fEPS(d) + j, eps[j]);
-        if (linkToCache) me.stSV(F_ZPLUS, zPlus);
+        me.stSV(F_ZPLUS, zPlus);
     }
-    if (LEAN) cyStoreIn(cy, ao.PP, zPlus, lMe);
 }
 
 // Sweep E for one body (base->tip): udot, A_GB, qdotdot.
-template <int JT, bool WITH_COR, bool LEAN>
-SBK_BODY void outwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, const int inst, double* cy,
+template <int JT, bool WITH_COR>
+SBK_BODY void outwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, const int inst,
                          double* udotDst, double* qdotdotDst) {
     constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
-    constexpr bool BLK = LEAN && SBK_DEV_BLK;
-    const CacheRefT<BLK> cref = cacheOf<BLK>(c, inst, bc.cacheBase);
-    const CacheRefT<BLK>& me = cref;
-    SV A_GP;
-    if (LEAN && (bc.flags & BF_PARENT_PREV)) A_GP = cyLoadA(cy);
-    else A_GP = cacheOf<BLK>(c, inst, bc.parentCacheBase).ldSV(F_AGB);
+    const CacheRef me = cacheOf<false>(c, inst, bc.cacheBase);
+    const SV A_GP = cacheOf<false>(c, inst, bc.parentCacheBase).ldSV(F_AGB);
     SV H[d], G[d]; double DI[d*d], eps[d], udot[d];
 #pragma unroll
     for (int j = 0; j < d; ++j) { H[j] = me.ldSV(F_H + 6*j); G[j] = me.ldSV(fG(d) + 6*j); eps[j] = me.ld(fEPS(d) + j); }
@@ -643,20 +687,200 @@ SBK_BODY void outwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex
     const V3 lMe = me.ld3(F_L);
     SV A;
     accCore<d, WITH_COR>(H, G, DI, eps, lMe, A_GP, acor, udot, A);
-    if (!LEAN || (bc.flags & BF_STORE_LINK)) cref.stSV(F_AGB, A);
-    if (LEAN) cyStoreA(cy, A);
+    me.stSV(F_AGB, A);
     if (udotDst) {
 #pragma unroll
-        for (int i = 0; i < d; ++i) stS<BLK>(c, inst, udotDst, bc.u0 + i, udot[i]);
+        for (int i = 0; i < d; ++i) stS<false>(c, inst, udotDst, bc.u0 + i, udot[i]);
     }
     if (qdotdotDst) {
         double q[NQ], u[d], qdd[NQ];
         if constexpr (JT == JT_BALL || JT == JT_FREE) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) q[i] = ldS<BLK>(c, inst, c.q, bc.q0 + i);
+            for (int i = 0; i < 4; ++i) q[i] = ldS<false>(c, inst, c.q, bc.q0 + i);
 #pragma unroll
-            for (int i = 0; i < 3; ++i) u[i] = ldS<BLK>(c, inst, c.u, bc.u0 + i);
+            for (int i = 0; i < 3; ++i) u[i] = ldS<false>(c, inst, c.u, bc.u0 + i);
         }
+        qddCore<JT>(q, u, udot, qdd);
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) stS<false>(c, inst, qdotdotDst, bc.q0 + i, qdd[i]);
+    }
+}
+
+//==============================================================================================
+//        BODY WRAPPERS, integrator path (LEAN): reversible kinematics, 7*dof doubles per body
+//==============================================================================================
+// One derivative evaluation = three sweeps over the bodies of one instance:
+//   1 outward  position/velocity recurrences only; X_GB, V_GB ride in the carry and are stored
+//              just where a later sweep cannot get them from the carry (tips, branch points)
+//   2 inward   per body: recover the parent's X, V from the body's own (kinReverse), recompute the
+//              body's kinematics, then articulated inertia + residual; stores G (6 dof) and
+//              nu = DI*eps (dof)
+//   3 outward  recompute the kinematics (bit-identical to sweep 1), udot = nu - ~G A+, A_GB
+// HBM traffic per body and evaluation: 7*dof doubles written + read (Pin: 112 B) instead of the
+// 728 B of a design that stages every body's kinematics between the sweeps; the price is ~2x the
+// algorithmic flop count, paid on an FP64 pipe that the staged design left 85% idle.
+// LEAN record rows (inside the body's FULL record region, which is larger):
+enum { LF_XGB = 0, LF_VGB = 12, LF_L = 18, LF_PPLUS = 21, LF_ZPLUS = 42, LF_AGB = 48, LF_G = 54 };
+SBK_HD constexpr int lfNU(int d) { return LF_G + 6*d; }
+
+// Coordinates of the NEXT body of a sweep, requested one body step ahead: every body step starts
+// with sin/cos of q, so a load issued at its top stalls the step for a full trip to memory.  The
+// request is an asynchronous global->shared copy (cp.async, SASS LDGSTS) into two alternating
+// 4-row slots of the carry column -- registers would not do: the compiler spills a value that is
+// live across the joint switch, and the spill store waits for the load.  Two slots each for q and
+// u cover Pin / Slider / Universal; Ball / Free bodies load their own.
+SBK_HD void preloadCoords(const Ctx& c, const int inst, const BodyConst& nx, double* slot) {
+    constexpr bool BLK = SBK_DEV_BLK;
+    const int u1 = nx.u0 + 1 < c.nu ? nx.u0 + 1 : nx.u0;       // stay inside the u rows
+    const double* src[4] = { c.q + stateIndex<BLK>(c, inst, nx.q0), c.q + stateIndex<BLK>(c, inst, nx.q0 + 1),   // q0 + 1 <= nq: a valid row of [q; u]
+                             c.u + stateIndex<BLK>(c, inst, nx.u0), c.u + stateIndex<BLK>(c, inst, u1) };
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(slot + k*SBK_CARRY_STRIDE)), "l"(src[k]) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#else
+    for (int k = 0; k < 4; ++k) slot[k*SBK_CARRY_STRIDE] = *src[k];
+#endif
+}
+// Wait until every request but the most recent one has landed.
+SBK_HD void preloadWait() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+#endif
+}
+template <int JT, bool BLK> SBK_HD void takeCoords(const Ctx& c, const int inst, const BodyConst& bc, const double* slot, double* q, double* u) {
+    constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
+    if constexpr (NQ <= 2) {
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) q[i] = slot[i*SBK_CARRY_STRIDE];
+#pragma unroll
+        for (int i = 0; i < d; ++i)  u[i] = slot[(2 + i)*SBK_CARRY_STRIDE];
+    } else {
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) q[i] = ldS<BLK>(c, inst, c.q, bc.q0 + i);
+#pragma unroll
+        for (int i = 0; i < d; ++i)  u[i] = ldS<BLK>(c, inst, c.u, bc.u0 + i);
+    }
+}
+
+template <int JT>
+SBK_BODY void leanKinBody(const Ctx& c, const BodyConst& bc, const int inst, double* cy, const double* pre, double* qdotDst) {
+    constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
+    constexpr bool BLK = SBK_DEV_BLK;
+    double q[NQ], u[d], qdot[NQ], qerr;
+    takeCoords<JT, BLK>(c, inst, bc, pre, q, u);
+    M3 R_GP; V3 p_GP; SV V_GP;
+    if (bc.flags & BF_PARENT_PREV) cyLoadOut(cy, R_GP, p_GP, V_GP);
+    else { const CacheRefT<BLK> pa = cacheOf<BLK>(c, inst, bc.parentCacheBase); R_GP = pa.ldM3(LF_XGB); p_GP = pa.ld3(LF_XGB + 9); V_GP = pa.ldSV(LF_VGB); }
+    KinOut<d> o;
+    kinCore<JT>(bc, q, u, R_GP, p_GP, V_GP, o, qdot, qerr);     // unused outputs are dead code here
+    if (bc.flags & (BF_STORE_LINK | BF_TIP)) {
+        const CacheRefT<BLK> me = cacheOf<BLK>(c, inst, bc.cacheBase);
+        me.stM3(LF_XGB, o.R); me.st3(LF_XGB + 9, o.p); me.stSV(LF_VGB, o.V);
+    }
+    cyStoreOut(cy, o.R, o.p, o.V);
+    if (qdotDst) {
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) stS<BLK>(c, inst, qdotDst, bc.q0 + i, qdot[i]);
+    }
+}
+
+template <int JT>
+SBK_BODY void leanInwardBody(const Ctx& c, const Tables& T, const BodyConst& bc, const int bodyIndex, const int inst, double* cy, const double* pre) {
+    constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
+    constexpr bool BLK = SBK_DEV_BLK;
+    const CacheRefT<BLK> me = cacheOf<BLK>(c, inst, bc.cacheBase);
+    double q[NQ], u[d], qdot[NQ];
+    takeCoords<JT, BLK>(c, inst, bc, pre, q, u);
+    const bool haveCarryChild = !(bc.flags & BF_TIP);      // body index + 1 is a child and left its links in the carry
+    M3 R_GB; V3 p_GB; SV V_GB;
+    if (haveCarryChild) cyLoadOut(cy + CY_SELF*SBK_CARRY_STRIDE, R_GB, p_GB, V_GB);
+    else { R_GB = me.ldM3(LF_XGB); p_GB = me.ld3(LF_XGB + 9); V_GB = me.ldSV(LF_VGB); }
+
+    KinLocal<d> kl; kinLocal<JT>(bc, q, kl);
+    M3 R_GP; V3 p_GP; SV V_GP;
+    kinReverse<JT>(bc, kl, u, R_GB, p_GB, V_GB, R_GP, p_GP, V_GP);
+    KinOut<d> o;
+    kinGlobal<JT>(bc, kl, q, u, R_GP, p_GP, V_GP, o, qdot);
+
+    // ---- articulated inertia (RigidBodyNodeSpec.cpp:249-325) ------------------------------------
+    ABI cPP; SV czP = zeroSV(); V3 cl = zero3();
+    if (haveCarryChild) cyLoadIn(cy, cPP, czP, cl);
+    ABI P = abiFromRigid(bc.mass, o.c, o.G);
+    for (int k = 0; k < bc.nchild; ++k) {
+        if (k == 0 && haveCarryChild) { addInto(P, shiftABI(cPP, cl)); continue; }
+        const CacheRefT<BLK> ch = cacheOf<BLK>(c, inst, T.bodies[T.children[bc.childStart + k]].cacheBase);
+        addInto(P, shiftABI(ch.ldABI(LF_PPLUS), ch.ld3(LF_L)));
+    }
+    AbiOut<d> ao;
+    abiCore<d>(P, o.H, o.acor, o.gyro, ao);
+    if (!ao.ok) setSingular(c, inst);
+
+    // ---- forces and residual (RigidBodyNodeSpec.cpp:355-400) -------------------------------------
+    double f[d];
+    const SV F = gravityForce(bc.mass, o.c, c.gx, c.gy, c.gz);
+    mobilityForces<d>(bc, T.forces, q, u, f);
+    SV z = ao.zb - F;
+    for (int k = 0; k < bc.nchild; ++k) {
+        if (k == 0 && haveCarryChild) { z = z + phi(cl, czP); continue; }
+        const CacheRefT<BLK> ch = cacheOf<BLK>(c, inst, T.bodies[T.children[bc.childStart + k]].cacheBase);
+        z = z + phi(ch.ld3(LF_L), ch.ldSV(LF_ZPLUS));
+    }
+    double eps[d]; SV zPlus;
+    zCore<d>(o.H, ao.G, z, f, eps, zPlus);
+#pragma unroll
+    for (int j = 0; j < d; ++j) me.stSV(LF_G + 6*j, ao.G[j]);
+#pragma unroll
+    for (int i = 0; i < d; ++i) {                      // nu = DI*eps, the first term of udot (RigidBodyNodeSpec.cpp:432)
+        double sum = 0;
+#pragma unroll
+        for (int j = 0; j < d; ++j) sum += ao.DI[d*i+j]*eps[j];
+        me.st(lfNU(d) + i, sum);
+    }
+    if (bc.flags & BF_PARENT_PREV) {
+        cyStoreIn(cy, ao.PP, zPlus, o.l);
+        cyStoreOut(cy + CY_SELF*SBK_CARRY_STRIDE, R_GP, p_GP, V_GP);
+    } else {
+        me.stABI(LF_PPLUS, ao.PP); me.stSV(LF_ZPLUS, zPlus); me.st3(LF_L, o.l);
+    }
+}
+
+template <int JT>
+SBK_BODY void leanOutwardBody(const Ctx& c, const BodyConst& bc, const int inst, double* cy, const double* pre, double* udotDst, double* qdotdotDst) {
+    constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
+    constexpr bool BLK = SBK_DEV_BLK;
+    const CacheRefT<BLK> me = cacheOf<BLK>(c, inst, bc.cacheBase);
+    double q[NQ], u[d], qdot[NQ], qerr, nu[d], udot[d];
+    SV G[d];
+#pragma unroll
+    for (int j = 0; j < d; ++j) { G[j] = me.ldSV(LF_G + 6*j); nu[j] = me.ld(lfNU(d) + j); }
+    takeCoords<JT, BLK>(c, inst, bc, pre, q, u);
+    M3 R_GP; V3 p_GP; SV V_GP, A_GP;
+    if (bc.flags & BF_PARENT_PREV) { cyLoadOut(cy, R_GP, p_GP, V_GP); A_GP = cyLoadA(cy + CY_A*SBK_CARRY_STRIDE); }
+    else {
+        const CacheRefT<BLK> pa = cacheOf<BLK>(c, inst, bc.parentCacheBase);
+        R_GP = pa.ldM3(LF_XGB); p_GP = pa.ld3(LF_XGB + 9); V_GP = pa.ldSV(LF_VGB); A_GP = pa.ldSV(LF_AGB);
+    }
+    KinOut<d> o;
+    kinCore<JT>(bc, q, u, R_GP, p_GP, V_GP, o, qdot, qerr);     // mass properties are dead code here
+    // calcUDotPass2Outward (RigidBodyNodeSpec.cpp:408-446) with nu = DI*eps from the inward sweep
+    const SV APlus = phiT(o.l, A_GP);
+    SV Hu = zeroSV();
+#pragma unroll
+    for (int i = 0; i < d; ++i) {
+        udot[i] = nu[i] - (dot(G[i].w, APlus.w) + dot(G[i].v, APlus.v));
+        Hu = Hu + udot[i]*o.H[i];
+    }
+    const SV A = (APlus + Hu) + o.acor;
+    if (bc.flags & BF_STORE_LINK) me.stSV(LF_AGB, A);            // X_GB, V_GB are still there from sweep 1
+    cyStoreOut(cy, o.R, o.p, o.V); cyStoreA(cy + CY_A*SBK_CARRY_STRIDE, A);
+    if (udotDst) {
+#pragma unroll
+        for (int i = 0; i < d; ++i) stS<BLK>(c, inst, udotDst, bc.u0 + i, udot[i]);
+    }
+    if (qdotdotDst) {
+        double qdd[NQ];
         qddCore<JT>(q, u, udot, qdd);
 #pragma unroll
         for (int i = 0; i < NQ; ++i) stS<BLK>(c, inst, qdotdotDst, bc.q0 + i, qdd[i]);
@@ -727,18 +951,33 @@ SBK_BODY void idInBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, c
         default: break;                                                             \
     }
 
-template <bool LEAN> SBK_HD void kinDispatch(const Ctx& c, int b, int inst, double* cy, double* qdotDst) {
+SBK_HD void kinDispatch(const Ctx& c, int b, int inst, double* qdotDst) {
     const BodyConst& bc = c.bodies[b];
-    SBK_DISPATCH_JOINT(bc.joint, (kinBody<JT, LEAN>(c, bc, b, inst, cy, qdotDst)));
+    SBK_DISPATCH_JOINT(bc.joint, (kinBody<JT>(c, bc, b, inst, qdotDst)));
 }
-template <int MODE, bool LEAN> SBK_HD void inwardDispatch(const Ctx& c, int b, int inst, double* cy) {
+template <int MODE> SBK_HD void inwardDispatch(const Ctx& c, int b, int inst) {
     const BodyConst& bc = c.bodies[b];
-    SBK_DISPATCH_JOINT(bc.joint, (inwardBody<JT, MODE, LEAN>(c, bc, b, inst, cy)));
+    SBK_DISPATCH_JOINT(bc.joint, (inwardBody<JT, MODE>(c, bc, b, inst)));
 }
-template <bool WITH_COR, bool LEAN> SBK_HD void outwardDispatch(const Ctx& c, int b, int inst, double* cy, double* udotDst, double* qddDst) {
+template <bool WITH_COR> SBK_HD void outwardDispatch(const Ctx& c, int b, int inst, double* udotDst, double* qddDst) {
     const BodyConst& bc = c.bodies[b];
-    SBK_DISPATCH_JOINT(bc.joint, (outwardBody<JT, WITH_COR, LEAN>(c, bc, b, inst, cy, udotDst, qddDst)));
+    SBK_DISPATCH_JOINT(bc.joint, (outwardBody<JT, WITH_COR>(c, bc, b, inst, udotDst, qddDst)));
 }
+// Same, restricted at compile time to the mobilizer kinds in JMASK (bit JT_x set = kind present): the
+// integrator kernels are instantiated for a few masks so that a model made of Pin joints only does
+// not carry (and register-allocate for) the Ball / Free code.
+enum { JM_PIN = 1 << JT_PIN, JM_SLIDER = 1 << JT_SLIDER, JM_UNIVERSAL = 1 << JT_UNIVERSAL, JM_BALL = 1 << JT_BALL, JM_FREE = 1 << JT_FREE,
+       JM_ALL = JM_PIN | JM_SLIDER | JM_UNIVERSAL | JM_BALL | JM_FREE };
+#define SBK_DISPATCH_JOINT_M(JMASK, jt, CALL)                                                                       \
+    switch (jt) {                                                                                                   \
+        case JT_PIN:       if constexpr (((JMASK) & JM_PIN) != 0)       { constexpr int JT = JT_PIN;       CALL; } break; \
+        case JT_SLIDER:    if constexpr (((JMASK) & JM_SLIDER) != 0)    { constexpr int JT = JT_SLIDER;    CALL; } break; \
+        case JT_UNIVERSAL: if constexpr (((JMASK) & JM_UNIVERSAL) != 0) { constexpr int JT = JT_UNIVERSAL; CALL; } break; \
+        case JT_BALL:      if constexpr (((JMASK) & JM_BALL) != 0)      { constexpr int JT = JT_BALL;      CALL; } break; \
+        case JT_FREE:      if constexpr (((JMASK) & JM_FREE) != 0)      { constexpr int JT = JT_FREE;      CALL; } break; \
+        default: break;                                                                                             \
+    }
+
 template <bool WITH_VEL> SBK_HD void idOutDispatch(const Ctx& c, int b, int inst) {
     const BodyConst& bc = c.bodies[b];
     SBK_DISPATCH_JOINT(bc.joint, (idOutBody<JT, WITH_VEL>(c, bc, inst)));
@@ -752,22 +991,54 @@ template <bool WITH_VEL> SBK_HD void idInDispatch(const Ctx& c, int b, int inst)
 // Per-instance drivers for the thread-per-instance plan: body index order is a valid
 // base->tip order because a parent's MobilizedBodyIndex is always smaller than its child's.
 //==============================================================================================
-template <bool LEAN> SBK_HD void tpiKinematics(const Ctx& c, int inst, double* cy, double* qdotDst) {
-    if (LEAN) { SV z0 = zeroSV(); cyStoreOut(cy, identity3(), zero3(), z0); }      // Ground's link for body 1
-    for (int b = 1; b < c.nb; ++b) kinDispatch<LEAN>(c, b, inst, cy, qdotDst);
+SBK_HD void tpiKinematics(const Ctx& c, int inst, double* qdotDst) {
+    for (int b = 1; b < c.nb; ++b) kinDispatch(c, b, inst, qdotDst);
 }
-template <int MODE, bool LEAN> SBK_HD void tpiInward(const Ctx& c, int inst, double* cy) {
-    for (int b = c.nb - 1; b >= 1; --b) inwardDispatch<MODE, LEAN>(c, b, inst, cy);
+template <int MODE> SBK_HD void tpiInward(const Ctx& c, int inst) {
+    for (int b = c.nb - 1; b >= 1; --b) inwardDispatch<MODE>(c, b, inst);
 }
-template <bool WITH_COR, bool LEAN> SBK_HD void tpiOutward(const Ctx& c, int inst, double* cy, double* udotDst, double* qddDst) {
-    if (LEAN) cyStoreA(cy, zeroSV());                                               // Ground's A_GB
-    for (int b = 1; b < c.nb; ++b) outwardDispatch<WITH_COR, LEAN>(c, b, inst, cy, udotDst, qddDst);
+template <bool WITH_COR> SBK_HD void tpiOutward(const Ctx& c, int inst, double* udotDst, double* qddDst) {
+    for (int b = 1; b < c.nb; ++b) outwardDispatch<WITH_COR>(c, b, inst, udotDst, qddDst);
 }
 // One full derivative evaluation = System::realize(Acceleration) for the lowered system.
-template <bool LEAN> SBK_EVAL void tpiEvalDerivatives(const Ctx& c, int inst, double* cy, double* qdotDst, double* udotDst, double* qddDst) {
-    tpiKinematics<LEAN>(c, inst, cy, qdotDst);
-    tpiInward<IN_ABI | IN_Z | IN_BIAS | IN_FORCES, LEAN>(c, inst, cy);
-    tpiOutward<true, LEAN>(c, inst, cy, udotDst, qddDst);
+//   LEAN = false: FULL records (every cache entry a getter may ask for); cy unused
+//   LEAN = true : integrator path, reversible kinematics (see above); cy = the work item's carry column
+template <bool LEAN, int JMASK = JM_ALL> SBK_HD void tpiEvalDerivatives(const Ctx& c, const Tables& T, int inst, double* cy, double* qdotDst, double* udotDst, double* qddDst) {
+    if constexpr (!LEAN) {
+        tpiKinematics(c, inst, qdotDst);
+        tpiInward<IN_ABI | IN_Z | IN_BIAS | IN_FORCES>(c, inst);
+        tpiOutward<true>(c, inst, udotDst, qddDst);
+    } else {
+        const SV z0 = zeroSV();
+        // pre(k): the coordinate slot of the k-th body step of this evaluation (two alternate)
+        #define SBK_PRE(k) (cy + (CY_PRE + 4*((k) & 1))*SBK_CARRY_STRIDE)
+        int k = 0;
+        cyStoreOut(cy, identity3(), zero3(), z0);                                 // Ground's link for body 1
+        preloadCoords(c, inst, T.bodies[1], SBK_PRE(0));
+#pragma unroll 1
+        for (int b = 1; b < c.nb; ++b, ++k) {
+            const BodyConst& bc = T.bodies[b];
+            preloadCoords(c, inst, T.bodies[b + 1 < c.nb ? b + 1 : c.nb - 1], SBK_PRE(k + 1));   // after the last body: the first of the inward sweep
+            preloadWait();
+            SBK_DISPATCH_JOINT_M(JMASK, bc.joint, (leanKinBody<JT>(c, bc, inst, cy, SBK_PRE(k), qdotDst)));
+        }
+#pragma unroll 1
+        for (int b = c.nb - 1; b >= 1; --b, ++k) {
+            const BodyConst& bc = T.bodies[b];
+            preloadCoords(c, inst, T.bodies[b > 1 ? b - 1 : 1], SBK_PRE(k + 1));                  // after body 1: the first of the outward sweep
+            preloadWait();
+            SBK_DISPATCH_JOINT_M(JMASK, bc.joint, (leanInwardBody<JT>(c, T, bc, b, inst, cy, SBK_PRE(k))));
+        }
+        cyStoreOut(cy, identity3(), zero3(), z0); cyStoreA(cy + CY_A*SBK_CARRY_STRIDE, z0);
+#pragma unroll 1
+        for (int b = 1; b < c.nb; ++b, ++k) {
+            const BodyConst& bc = T.bodies[b];
+            preloadCoords(c, inst, T.bodies[b + 1 < c.nb ? b + 1 : b], SBK_PRE(k + 1));
+            preloadWait();
+            SBK_DISPATCH_JOINT_M(JMASK, bc.joint, (leanOutwardBody<JT>(c, bc, inst, cy, SBK_PRE(k), udotDst, qddDst)));
+        }
+        #undef SBK_PRE
+    }
 }
 
 } // namespace sbkd

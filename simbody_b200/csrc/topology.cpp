@@ -86,6 +86,7 @@ void compileTopology(const ModelSpec& spec, sbk_topology& t) {
         if (isIdentityR(bc.X_MB)) bc.flags |= sbkd::BF_NO_R_MB;
         if (b >= 1 && d.parent == b - 1) bc.flags |= sbkd::BF_PARENT_PREV;
         for (int k : kids[b]) if (k != b + 1) bc.flags |= sbkd::BF_STORE_LINK;
+        if (b >= 1 && (kids[b].empty() || kids[b][0] != b + 1)) bc.flags |= sbkd::BF_TIP;
         bc.nchild = (int)kids[b].size(); bc.childStart = (int)t.children.size();
         for (int k : kids[b]) t.children.push_back(k);
         bc.nforce = (int)perBody[b].size(); bc.forceStart = (int)t.forces.size();

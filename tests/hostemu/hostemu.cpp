@@ -83,7 +83,7 @@ int emu_eval(const char* text, int N, const double* in, double* out) {
             Ctx c = makeCtx(e, k);
             double cy[CARRY_ROWS];
             c.fmobOut = e.fmob.data(); c.FbodyOut = e.Fbody.data();
-            tpiEvalDerivatives<false>(c, k, cy, c.qdot, c.udot, c.qdotdot);
+            tpiEvalDerivatives<false>(c, tablesOf(c), k, cy, c.qdot, c.udot, c.qdotdot);
             for (int i = 0; i < nq; ++i) *o++ = e.ydot[(size_t)i*N + k];
             for (int i = 0; i < nu; ++i) *o++ = e.ydot[(size_t)(nq+i)*N + k];
             for (int i = 0; i < nq; ++i) *o++ = e.qdd[(size_t)i*N + k];
@@ -107,8 +107,8 @@ int emu_eval(const char* text, int N, const double* in, double* out) {
             // M^-1 v
             for (int i = 0; i < nu; ++i) e.vin[(size_t)i*N + k] = pv[i];
             c.fmobIn = e.vin.data(); c.FbodyIn = nullptr;
-            tpiInward<IN_Z, false>(c, k, cy);
-            tpiOutward<false, false>(c, k, cy, e.vout.data(), nullptr);
+            tpiInward<IN_Z>(c, k);
+            tpiOutward<false>(c, k, e.vout.data(), nullptr);
             for (int i = 0; i < nu; ++i) *o++ = e.vout[(size_t)i*N + k];
             // residual(f, F, udot)
             for (int i = 0; i < nu; ++i) { e.vin[(size_t)i*N + k] = pud[i]; e.vin2[(size_t)i*N + k] = pf[i]; }
@@ -124,8 +124,8 @@ int emu_eval(const char* text, int N, const double* in, double* out) {
             for (int i = 0; i < nu; ++i) *o++ = e.vout[(size_t)i*N + k];
             // calcAcceleration(f, F)
             c.fmobIn = e.vin2.data(); c.FbodyIn = e.Fin.data();
-            tpiInward<IN_Z | IN_BIAS, false>(c, k, cy);
-            tpiOutward<true, false>(c, k, cy, e.vout.data(), nullptr);
+            tpiInward<IN_Z | IN_BIAS>(c, k);
+            tpiOutward<true>(c, k, e.vout.data(), nullptr);
             for (int i = 0; i < nu; ++i) *o++ = e.vout[(size_t)i*N + k];
             for (int b = 0; b < nb; ++b) for (int i = 0; i < 6; ++i) *o++ = rec(b, F_AGB + i);
             if (o - (out + (size_t)k*outStride) != outStride) return 3;
@@ -170,7 +170,7 @@ int emu_step(const char* text, int N, const double* in, double* out, double h, i
             double cy[CARRY_ROWS];
             RkmStepResult r; r.errNorm = 0; r.projected = 0; int nproj = 0;
             for (int s = 0; s < nsteps; ++s) {
-                r = lean ? tpiRkmStep<true>(c, k, w, h, cy) : tpiRkmStep<false>(c, k, w, h, cy);
+                r = lean ? tpiRkmStep<true>(c, tablesOf(c), k, w, h, cy) : tpiRkmStep<false>(c, tablesOf(c), k, w, h, cy);
                 nproj += r.projected;
             }
             double* o = out + (size_t)k*(ny+2);
@@ -205,7 +205,7 @@ int emu_adaptive(const char* text, int N, const double* in, double* out, double 
             } else {
                 Ctx c = makeCtx(e, k); c.qdotdot = nullptr; c.qerr = nullptr;
                 double cy[CARRY_ROWS];
-                tpiRkmAdaptive<true>(c, k, w, lim, tFinal, allowInterpolation, 1000000, st, cy, lastErr, nproj);
+                tpiRkmAdaptive<true>(c, tablesOf(c), k, w, lim, tFinal, allowInterpolation, 1000000, st, cy, lastErr, nproj);
                 for (int i = 0; i < ny; ++i) o[i] = e.y[(size_t)i*N + k];
             }
             o[ny] = st.steps; o[ny+1] = st.attempts; o[ny+2] = st.steps + 4.0*st.attempts; o[ny+3] = st.lastStep; o[ny+4] = st.t;

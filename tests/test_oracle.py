@@ -134,20 +134,24 @@ def test_slot_rules_match_reference(built):
         assert int(t[3]) == info.q0[b] and int(t[7]) == info.u0[b]
 
 
-def test_plans_are_bitwise_identical_on_host(built):
-    """LEAN (carry links), FULL (all records) and the register-resident fused plan run the same
-    cores in the same order: without FMA contraction (host build) they agree bit for bit."""
+def test_plans_agree_on_host(built):
+    """FULL (all records) and the register-resident fused plan run the same cores in the same
+    order: without FMA contraction (host build) they agree bit for bit.  The integrator (LEAN)
+    path recovers each parent transform by inverting the kinematic recurrence in its inward sweep
+    (kinReverse), so it agrees with them to a few ulp per body, not bitwise."""
     emu = HostEmu()
-    for name, n in [("double_pendulum", 0), ("pin_chain", 9), ("mixed7", 0), ("humanoid30", 0), ("branched_tree", 25)]:
+    for name, n in [("double_pendulum", 0), ("pin_chain", 9), ("pin_chain", 50), ("mixed7", 0), ("humanoid30", 0), ("branched_tree", 25)]:
         info = ModelInfo(emu.model_text(name, n))
+        ny = info.nq + info.nu
         q, u = info.random_states(3, 5, q_scale=0.5)
         y = np.concatenate([q, u], axis=1)
         a = emu.step(info, y, 1e-3, 6, lean=1); b = emu.step(info, y, 1e-3, 6, lean=0)
-        assert np.array_equal(a, b), name
+        assert rel_err(a[:, :ny], b[:, :ny]) < 1e-13, name
+        assert np.allclose(a[:, ny], b[:, ny], rtol=1e-3, atol=1e-15) and np.array_equal(a[:, ny + 1], b[:, ny + 1]), name
     info = ModelInfo(emu.model_text("double_pendulum"))
     q, u = info.random_states(8, 6, q_scale=3.0)
     y = np.concatenate([q, u], axis=1)
-    assert np.array_equal(emu.step(info, y, 1e-3, 30, lean=1), emu.step(info, y, 1e-3, 30, lean=2))
+    assert np.array_equal(emu.step(info, y, 1e-3, 30, lean=0), emu.step(info, y, 1e-3, 30, lean=2))
 
 
 def test_adaptive_rkm_reproduces_readme_run_on_host(built):
