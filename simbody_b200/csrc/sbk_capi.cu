@@ -204,7 +204,7 @@ static int configurePlan(sbk_batch* b, int plan) {
     for (int i = 1; i < t->nb; ++i) a.jointMask |= 1 << t->bodies[i].joint;
     { const char* e = getenv("SBK_JMASK"); if (e) a.jointMask |= atoi(e); }           // tuning override: force a wider kernel variant
     { const char* e = getenv("SBK_LIGHT"); if (e) a.lightJoints = atoi(e); }     // tuning override
-    a.stageInSmem = (plan != 3 && blob.size() <= 96*1024) ? 1u : 0u;
+    a.stageInSmem = (plan != 3 && blob.size() <= 28*1024) ? 1u : 0u;   // two resident CTAs: 2 x (tables + 84 KB carry) <= 227 KB
     CUDA_TRY(cudaStreamSynchronize(b->stream));
     if (b->dTables) cudaFree(b->dTables);
     if (a.cache) cudaFree(a.cache);
@@ -252,6 +252,9 @@ sbk_batch* sbk_batch_create(const sbk_topology* t, int n, int device, void* stre
     dalloc(&a.tcur, N); dalloc(&a.errNorm, N);
     dalloc(&b->dOpA, (size_t)t->nu*N); dalloc(&b->dOpB, (size_t)t->nu*N); dalloc(&b->dOpOut, (size_t)t->nu*N); dalloc(&b->dOpF, (size_t)t->nb*6*N);
     if (ok && cudaMalloc(&a.status, N*sizeof(int)) != cudaSuccess) ok = false;
+    { const size_t nblk = (N + BLK_LANES - 1)/BLK_LANES;
+      if (ok && cudaMalloc(&a.taskCounter, (1 + nblk)*sizeof(int)) != cudaSuccess) ok = false;
+      if (ok) a.blockDone = a.taskCounter + 1; }
     if (ok && cudaMalloc(&a.projCount, N*sizeof(int)) != cudaSuccess) ok = false;
     if (!ok) return bail(std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
     cudaMemsetAsync(a.status, 0, N*sizeof(int), b->stream);
@@ -274,7 +277,7 @@ void sbk_batch_destroy(sbk_batch* b) {
     KArgs& a = b->a;
     void* ptrs[] = {b->dTables, a.cache, a.y, a.yb, a.ydot, a.qdotdot, a.qerr, a.y0, a.f0, a.fa, a.fb, a.ys, a.tcur, a.errNorm,
                     b->dOpA, b->dOpB, b->dOpOut, b->dOpF, a.status, a.projCount, b->dScratch,
-                    a.hcur, a.lastStep, a.stepsTaken, a.attempts};
+                    a.hcur, a.lastStep, a.stepsTaken, a.attempts, a.taskCounter};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (b->ev0) cudaEventDestroy(b->ev0); if (b->ev1) cudaEventDestroy(b->ev1);
     if (b->ownStream && b->stream) cudaStreamDestroy(b->stream);

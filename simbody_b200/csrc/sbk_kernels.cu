@@ -7,6 +7,7 @@
 // (cp.async.bulk.shared::cluster.global + mbarrier complete_tx) and then read as warp
 // broadcasts.  FP64 throughout; no tensor cores (6x6 spatial operators are not a dense
 // contraction).
+#include <algorithm>
 #include "sbk_kernels.cuh"
 #include "sbk_fused.cuh"
 
@@ -94,6 +95,56 @@ __global__ void __launch_bounds__(TPI_THREADS, MINB) tpiKernel(const KArgs a) {
     constexpr bool INTEG = OP == OP_RKM || OP == OP_RKM_ADAPT;
     if (!INTEG && threadIdx.x == 0) fillCtx(sctx, a, tables, false);
     __syncthreads();
+    if constexpr (OP == OP_RKM) {
+        // Fixed-step integrator: PERSISTENT CTAs (the grid is what fits the machine at once) pull
+        // (block of 128 instances, step) tasks from a global counter, step-major.  A batch whose
+        // CTA count is not a multiple of the resident slots (65536 instances = 512 CTAs on 296
+        // slots) then costs nsteps*512/296 rounds instead of nsteps*2.  Steps of one block are
+        // ordered through blockDone[block] (release after the step, acquire before the next one);
+        // tasks are claimed in order, so the task a CTA waits for is always held by a running CTA.
+        __shared__ int sTask;
+        Ctx lctx; fillCtx(lctx, a, tables, true); useBlockedState(lctx, a);
+        const Ctx& c = lctx;
+        Tables T;
+        T.bodies = reinterpret_cast<const BodyConst*>(tables); T.children = reinterpret_cast<const int*>(tables + a.childrenOff);
+        T.forces = reinterpret_cast<const ForceConst*>(tables + a.forcesOff);
+        double* cy = reinterpret_cast<double*>(smem + (STAGE ? a.tableBytes : 0)) + threadIdx.x;
+        RkmWork w;
+        w.y = a.yb; w.y0 = a.y0; w.f0 = a.f0; w.fa = a.fa; w.fb = a.fb; w.ys = a.ys;
+        w.accuracy = a.accuracy; w.consTol = a.consTol; w.useInfNorm = a.useInfNorm; w.projectEveryStep = a.projectEveryStep;
+        const int nblk = (a.N + TPI_THREADS - 1)/TPI_THREADS, total = nblk*a.nsteps;
+#pragma unroll 1
+        for (;;) {
+            if (threadIdx.x == 0) {
+                const int t = atomicAdd(a.taskCounter, 1);
+                if (t < total) {
+                    const int blk = t % nblk, step = t / nblk; int done;
+                    do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(a.blockDone + blk) : "memory"); if (done < step) __nanosleep(200); } while (done < step);
+                }
+                sTask = t;
+            }
+            __syncthreads();
+            const int t = sTask;
+            if (t >= total) break;
+            const int blk = t % nblk, step = t / nblk;
+            const int inst = blk*TPI_THREADS + threadIdx.x;
+            if (inst < a.N) {
+                if (step == 0) stateToBlocked(c, a, inst);
+                const RkmStepResult r = tpiRkmStep<true, JMASK>(c, T, inst, w, a.h, cy);
+                a.tcur[inst] += a.h;
+                if (r.projected) a.projCount[inst] += 1;
+                if (step == a.nsteps - 1) {
+                    stateFromBlocked(c, a, inst);
+                    a.errNorm[inst] = r.errNorm;
+                }
+                if (a.status && !(r.errNorm == r.errNorm)) atomicOr(a.status + inst, 1);   // NaN error norm
+            }
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(a.blockDone + blk), "r"(step + 1) : "memory");
+        }
+        return;
+    }
     const int inst = blockIdx.x*blockDim.x + threadIdx.x;
     if (inst >= a.N) return;
     // API kernels read the context from shared memory; the integrator kernels keep it as a local whose
@@ -127,20 +178,6 @@ __global__ void __launch_bounds__(TPI_THREADS, MINB) tpiKernel(const KArgs a) {
     } else if constexpr (OP == OP_RESID) {
         for (int b = 1; b < c.nb; ++b) idOutDispatch<true>(c, b, inst);
         for (int b = c.nb - 1; b >= 1; --b) idInDispatch<true>(c, b, inst);
-    } else if constexpr (OP == OP_RKM) {
-        RkmWork w;
-        w.y = a.yb; w.y0 = a.y0; w.f0 = a.f0; w.fa = a.fa; w.fb = a.fb; w.ys = a.ys;
-        w.accuracy = a.accuracy; w.consTol = a.consTol; w.useInfNorm = a.useInfNorm; w.projectEveryStep = a.projectEveryStep;
-        RkmStepResult r; r.errNorm = 0; r.projected = 0;
-        int nproj = 0; double t = a.tcur[inst];
-        stateToBlocked(c, a, inst);
-#pragma unroll 1
-        for (int s = 0; s < a.nsteps; ++s) { r = tpiRkmStep<true, JMASK>(c, T, inst, w, a.h, cy); nproj += r.projected; t += a.h; }
-        stateFromBlocked(c, a, inst);
-        a.tcur[inst] = t;
-        a.errNorm[inst] = r.errNorm;
-        a.projCount[inst] += nproj;
-        if (a.status && !(r.errNorm == r.errNorm)) atomicOr(a.status + inst, 1);   // NaN error norm
     } else if constexpr (OP == OP_RKM_ADAPT) {
         RkmWork w;
         w.y = a.yb; w.y0 = a.y0; w.f0 = a.f0; w.fa = a.fa; w.fb = a.fb; w.ys = a.ys;
@@ -211,7 +248,18 @@ cudaError_t launchOp(const KArgs& a, cudaStream_t stream) {
     auto go = [&](auto kernel) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
         if (e != cudaSuccess) return e;
-        kernel<<<grid, TPI_THREADS, smemBytes, stream>>>(a);
+        int g = grid;
+        if constexpr (OP == OP_RKM) {             // persistent: as many CTAs as are resident at once
+            int dev = 0, sms = 0, perSm = 0;
+            cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, TPI_THREADS, smemBytes);
+            if (e != cudaSuccess) return e;
+            if (perSm < 1) return cudaErrorLaunchOutOfResources;
+            g = std::min(grid, sms*perSm);
+            e = cudaMemsetAsync(a.taskCounter, 0, sizeof(int)*(size_t)(1 + grid), stream);   // counter + blockDone[grid]
+            if (e != cudaSuccess) return e;
+        }
+        kernel<<<g, TPI_THREADS, smemBytes, stream>>>(a);
         return cudaGetLastError();
     };
     if constexpr (OP == OP_RKM || OP == OP_RKM_ADAPT) {

@@ -42,6 +42,8 @@ struct KArgs {
     double* lastStep;   // [N] size of the last accepted step
     int* stepsTaken;    // [N] accumulated
     int* attempts;      // [N] accumulated
+    int* taskCounter;   // fixed-step integrator task queue: [0] = next task, blockDone = taskCounter + 1 .. [nblocks]
+    int* blockDone;     // steps completed per block of 128 instances (this launch)
 };
 
 enum KernelOp {

@@ -121,7 +121,8 @@ SBK_HD Tables tablesOf(const Ctx& c) { Tables t; t.bodies = c.bodies; t.children
 //                    kinematics, rows 30..47
 // Body b-1 is always the previous body of an outward sweep and b+1 of an inward one, so no
 // bookkeeping is needed: BF_PARENT_PREV says whether the parent is b-1.
-enum { CARRY_ROWS = 56, CY_A = 18, CY_SELF = 30, CY_PRE = 48 };   // rows 48..55: two coordinate preload slots
+enum { CARRY_ROWS = 84, CY_A = 18, CY_SELF = 30, CY_PRE = 48, CY_GNU = 56, GNU_ROWS = 14 };
+// rows 48..55: two coordinate preload slots; rows 56..83: two G / nu preload slots (acceleration sweep, dof <= 2)
 #if defined(__CUDA_ARCH__)
 #define SBK_CARRY_STRIDE 128
 #else
@@ -720,6 +721,7 @@ SBK_BODY void outwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex
 // 728 B of a design that stages every body's kinematics between the sweeps; the price is ~2x the
 // algorithmic flop count, paid on an FP64 pipe that the staged design left 85% idle.
 // LEAN record rows (inside the body's FULL record region, which is larger):
+
 enum { LF_XGB = 0, LF_VGB = 12, LF_L = 18, LF_PPLUS = 21, LF_ZPLUS = 42, LF_AGB = 48, LF_G = 54 };
 SBK_HD constexpr int lfNU(int d) { return LF_G + 6*d; }
 
@@ -742,6 +744,22 @@ SBK_HD void preloadCoords(const Ctx& c, const int inst, const BodyConst& nx, dou
 #else
     for (int k = 0; k < 4; ++k) slot[k*SBK_CARRY_STRIDE] = *src[k];
 #endif
+}
+// G and nu = DI*eps of the next body of the acceleration sweep (7*dof contiguous record rows, dof <= 2),
+// requested together with its coordinates.  Joins the commit group of the following preloadCoords.
+SBK_HD void preloadGNu(const Ctx& c, const int inst, const BodyConst& nx, double* slot) {
+    constexpr bool BLK = SBK_DEV_BLK;
+    const int d = (nx.joint == JT_UNIVERSAL) ? 2 : 1;
+    if (nx.joint > JT_UNIVERSAL) return;
+    const CacheRefT<BLK> rec = cacheOf<BLK>(c, inst, nx.cacheBase);
+    for (int k = 0; k < 7*d; ++k) {
+        const double* src = rec.p + (BLK ? (long long)(LF_G + k)*BLK_LANES : (long long)(LF_G + k)*rec.stride);
+#if defined(__CUDA_ARCH__)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(slot + k*SBK_CARRY_STRIDE)), "l"(src) : "memory");
+#else
+        slot[k*SBK_CARRY_STRIDE] = *src;
+#endif
+    }
 }
 // Wait until every request but the most recent one has landed.
 SBK_HD void preloadWait() {
@@ -847,14 +865,23 @@ SBK_BODY void leanInwardBody(const Ctx& c, const Tables& T, const BodyConst& bc,
 }
 
 template <int JT>
-SBK_BODY void leanOutwardBody(const Ctx& c, const BodyConst& bc, const int inst, double* cy, const double* pre, double* udotDst, double* qdotdotDst) {
+SBK_BODY void leanOutwardBody(const Ctx& c, const BodyConst& bc, const int inst, double* cy, const double* pre, const double* gnu, double* udotDst, double* qdotdotDst) {
     constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
     constexpr bool BLK = SBK_DEV_BLK;
     const CacheRefT<BLK> me = cacheOf<BLK>(c, inst, bc.cacheBase);
     double q[NQ], u[d], qdot[NQ], qerr, nu[d], udot[d];
     SV G[d];
+    if (d <= 2 && gnu) {                                  // preloaded into the carry column (preloadGNu)
 #pragma unroll
-    for (int j = 0; j < d; ++j) { G[j] = me.ldSV(LF_G + 6*j); nu[j] = me.ld(lfNU(d) + j); }
+        for (int j = 0; j < d; ++j) {
+            G[j].w = mk(gnu[(6*j+0)*SBK_CARRY_STRIDE], gnu[(6*j+1)*SBK_CARRY_STRIDE], gnu[(6*j+2)*SBK_CARRY_STRIDE]);
+            G[j].v = mk(gnu[(6*j+3)*SBK_CARRY_STRIDE], gnu[(6*j+4)*SBK_CARRY_STRIDE], gnu[(6*j+5)*SBK_CARRY_STRIDE]);
+            nu[j] = gnu[(6*d+j)*SBK_CARRY_STRIDE];
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < d; ++j) { G[j] = me.ldSV(LF_G + 6*j); nu[j] = me.ld(lfNU(d) + j); }
+    }
     takeCoords<JT, BLK>(c, inst, bc, pre, q, u);
     M3 R_GP; V3 p_GP; SV V_GP, A_GP;
     if (bc.flags & BF_PARENT_PREV) { cyLoadOut(cy, R_GP, p_GP, V_GP); A_GP = cyLoadA(cy + CY_A*SBK_CARRY_STRIDE); }
@@ -1012,6 +1039,7 @@ template <bool LEAN, int JMASK = JM_ALL> SBK_HD void tpiEvalDerivatives(const Ct
         const SV z0 = zeroSV();
         // pre(k): the coordinate slot of the k-th body step of this evaluation (two alternate)
         #define SBK_PRE(k) (cy + (CY_PRE + 4*((k) & 1))*SBK_CARRY_STRIDE)
+        #define SBK_GNU(k) (cy + (CY_GNU + GNU_ROWS*((k) & 1))*SBK_CARRY_STRIDE)
         int k = 0;
         cyStoreOut(cy, identity3(), zero3(), z0);                                 // Ground's link for body 1
         preloadCoords(c, inst, T.bodies[1], SBK_PRE(0));
@@ -1033,11 +1061,14 @@ template <bool LEAN, int JMASK = JM_ALL> SBK_HD void tpiEvalDerivatives(const Ct
 #pragma unroll 1
         for (int b = 1; b < c.nb; ++b, ++k) {
             const BodyConst& bc = T.bodies[b];
+            if (b + 1 < c.nb) preloadGNu(c, inst, T.bodies[b + 1], SBK_GNU(k + 1));
             preloadCoords(c, inst, T.bodies[b + 1 < c.nb ? b + 1 : b], SBK_PRE(k + 1));
             preloadWait();
-            SBK_DISPATCH_JOINT_M(JMASK, bc.joint, (leanOutwardBody<JT>(c, bc, inst, cy, SBK_PRE(k), udotDst, qddDst)));
+            // body 1 wrote its G / nu at the very end of the inward sweep: it loads them directly
+            SBK_DISPATCH_JOINT_M(JMASK, bc.joint, (leanOutwardBody<JT>(c, bc, inst, cy, SBK_PRE(k), b > 1 ? SBK_GNU(k) : nullptr, udotDst, qddDst)));
         }
         #undef SBK_PRE
+        #undef SBK_GNU
     }
 }
 
