@@ -265,6 +265,21 @@ template <int d> struct KinOut {     // results of sweeps A+B for one body
     SV acor, gyro;                   // mobilizer coriolis acceleration a, gyroscopic force b
 };
 
+// The H_FM columns of the five mobilizers are unit frame axes (or zero) except Universal's second
+// one; these helpers spell out products with them so that no flop is spent multiplying by a
+// literal 0 or 1 (the compiler may not drop x*0: NaN/Inf semantics).  Same values as the dense
+// expressions up to the sign of zeros.
+template <int A> SBK_HD V3 axisCross(V3 v) {          // e_A x v
+    if constexpr (A == 0) return mk(0, -v.z, v.y);
+    else if constexpr (A == 1) return mk(v.z, 0, -v.x);
+    else return mk(-v.y, v.x, 0);
+}
+template <int A> SBK_HD V3 mulSkip(const M3& R, V3 t) {   // R * t for a t whose component A is zero
+    if constexpr (A == 0) return mk(R.a[1]*t.y + R.a[2]*t.z, R.a[4]*t.y + R.a[5]*t.z, R.a[7]*t.y + R.a[8]*t.z);
+    else if constexpr (A == 1) return mk(R.a[0]*t.x + R.a[2]*t.z, R.a[3]*t.x + R.a[5]*t.z, R.a[6]*t.x + R.a[8]*t.z);
+    else return mk(R.a[0]*t.x + R.a[1]*t.y, R.a[3]*t.x + R.a[4]*t.y, R.a[6]*t.x + R.a[7]*t.y);
+}
+
 // Position kinematics that depend on the mobilizer coordinates only (no parent quantities):
 // X_FM, H_FM, and X_PB = X_PF * X_FM * X_MB (RigidBodyNodeSpec.h:554-569).
 template <int d> struct KinLocal {
@@ -317,10 +332,54 @@ SBK_HD void kinLocal(const BodyConst& bc, const double* q, KinLocal<JointDims<JT
     // Multiplying by an exact identity is skipped (same values up to the sign of zeros), as the
     // reference does through its noR_PF / noX_MB template flags.
     const bool noRPF = (bc.flags & BF_NO_R_PF) != 0, noRMB = (bc.flags & BF_NO_R_MB) != 0;
-    k.r = mul(R_FM, p_MB);                             // r_MB_F = R_FM * p_MB
-    const M3 R_FB = noRMB ? R_FM : mul(R_FM, R_MB);  const V3 p_FB = p_FM + k.r;
+    M3 R_FB;
+    if constexpr (JT == JT_PIN) {                      // R_FM = Rz(q): products written out without the 0 / 1 entries
+        const double co = R_FM.a[0], si = R_FM.a[3];
+        k.r = mk(co*p_MB.x - si*p_MB.y, si*p_MB.x + co*p_MB.y, p_MB.z);
+        if (noRMB) R_FB = R_FM;
+        else {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                R_FB.a[j]     = co*R_MB.a[j] - si*R_MB.a[3+j];
+                R_FB.a[3 + j] = si*R_MB.a[j] + co*R_MB.a[3+j];
+                R_FB.a[6 + j] = R_MB.a[6+j];
+            }
+        }
+    } else if constexpr (JT == JT_SLIDER) {            // R_FM = I
+        k.r = p_MB; R_FB = R_MB;
+    } else {
+        k.r = mul(R_FM, p_MB);                         // r_MB_F = R_FM * p_MB
+        R_FB = noRMB ? R_FM : mul(R_FM, R_MB);
+    }
+    const V3 p_FB = p_FM + k.r;
     k.R_PB = noRPF ? R_FB : mul(R_PF, R_FB);
     k.p_PB = p_PF + (noRPF ? p_FB : mul(R_PF, p_FB));
+}
+
+// H = R_GF (H_FM + H_MB_F), H_MB_F[1] = -r x H_FM[0]  (RigidBodyNodeSpec.cpp:44-74)
+template <int JT>
+SBK_HD void jointH(const M3& R_GF, const KinLocal<JointDims<JT>::nu>& k, SV* H) {
+    const V3 r = k.r;
+    #define SBK_ROTCOL(j, A) { H[j].w = col(R_GF, A); H[j].v = mulSkip<A>(R_GF, axisCross<A>(r)); }
+    #define SBK_TRCOL(j, A)  { H[j].w = zero3(); H[j].v = col(R_GF, A); }
+    if constexpr (JT == JT_PIN) SBK_ROTCOL(0, 2)
+    else if constexpr (JT == JT_SLIDER) SBK_TRCOL(0, 0)
+    else if constexpr (JT == JT_UNIVERSAL) {
+        SBK_ROTCOL(0, 0)
+        H[1].w = mul(R_GF, k.Hw[1]); H[1].v = mul(R_GF, cross(k.Hw[1], r));
+    } else {
+        SBK_ROTCOL(0, 0) SBK_ROTCOL(1, 1) SBK_ROTCOL(2, 2)
+        if constexpr (JT == JT_FREE) { SBK_TRCOL(3, 0) SBK_TRCOL(4, 1) SBK_TRCOL(5, 2) }
+    }
+    #undef SBK_ROTCOL
+    #undef SBK_TRCOL
+}
+// w_FM = H_FM(angular) u
+template <int JT> SBK_HD V3 jointWFM(const KinLocal<JointDims<JT>::nu>& k, const double* u) {
+    if constexpr (JT == JT_PIN) return mk(0, 0, u[0]);
+    else if constexpr (JT == JT_SLIDER) return zero3();
+    else if constexpr (JT == JT_UNIVERSAL) return mk(u[0], 0, 0) + u[1]*k.Hw[1];
+    else return mk(u[0], u[1], u[2]);
 }
 
 // Everything that needs the parent's X_GP, V_GP.
@@ -330,10 +389,7 @@ SBK_HD void kinGlobal(const BodyConst& bc, const KinLocal<JointDims<JT>::nu>& k,
                       KinOut<JointDims<JT>::nu>& o, double* qdot) {
     constexpr int d = JointDims<JT>::nu;
     const bool noRPF = (bc.flags & BF_NO_R_PF) != 0;
-    const V3* Hw = k.Hw; const V3* Hv = k.Hv; const V3 r = k.r;
-    V3 HDw[d];                // HDot_FM angular part (linear part is zero for all five mobilizers)
-#pragma unroll
-    for (int j = 0; j < d; ++j) HDw[j] = zero3();
+    const V3 r = k.r;
 
     o.R = mul(R_GP, k.R_PB);
     o.l = mul(R_GP, k.p_PB);                          // Phi: p_PB_G (RigidBodyNode.cpp:61)
@@ -341,11 +397,7 @@ SBK_HD void kinGlobal(const BodyConst& bc, const KinLocal<JointDims<JT>::nu>& k,
 
     // ---- H = R_GF (H_FM + H_MB_F)  (RigidBodyNodeSpec.cpp:44-74) -----------------------------
     const M3 R_GF = noRPF ? R_GP : mul(R_GP, loadR(bc.X_PF));
-#pragma unroll
-    for (int j = 0; j < d; ++j) {
-        o.H[j].w = mul(R_GF, Hw[j]);
-        o.H[j].v = mul(R_GF, Hv[j] + cross(Hw[j], r));  // H_MB_F[1] = -r x H_FM[0]
-    }
+    jointH<JT>(R_GF, k, o.H);
 
     // ---- mass properties in Ground (RigidBodyNode.cpp:54-84) ---------------------------------
     S3 G_B; G_B.xx = bc.G_B[0]; G_B.yy = bc.G_B[1]; G_B.zz = bc.G_B[2]; G_B.xy = bc.G_B[3]; G_B.xz = bc.G_B[4]; G_B.yz = bc.G_B[5];
@@ -353,22 +405,34 @@ SBK_HD void kinGlobal(const BodyConst& bc, const KinLocal<JointDims<JT>::nu>& k,
     o.c = mul(o.R, mk(bc.com_B[0], bc.com_B[1], bc.com_B[2]));
 
     // ---- velocity (RigidBodyNodeSpec.h:305-333) ------------------------------------------------
-    V3 w_FM = zero3(); SV V_PB = zeroSV();
+    const V3 w_FM = jointWFM<JT>(k, u);
+    SV V_PB = u[0]*o.H[0];
 #pragma unroll
-    for (int j = 0; j < d; ++j) { w_FM = w_FM + u[j]*Hw[j]; V_PB = V_PB + u[j]*o.H[j]; }
-    if constexpr (JT == JT_UNIVERSAL) HDw[1] = cross(w_FM, col(k.R_FM, 1));   // _Universal.h:176-190
+    for (int j = 1; j < d; ++j) V_PB = V_PB + u[j]*o.H[j];
 
-    // HDot (RigidBodyNodeSpec.cpp:82-129) and VD = HDot*u
+    // HDot (RigidBodyNodeSpec.cpp:82-129) and VD = HDot*u.  HDot_FM is zero for every column but
+    // Universal's second (_Universal.h:176-190), and translational columns have no angular part.
     const V3 w_GP = V_GP.w, v_GP = V_GP.v;
     const V3 wxr = cross(w_FM, r);
     SV VD = zeroSV();
-#pragma unroll
-    for (int j = 0; j < d; ++j) {
+    #define SBK_ROTCOL_D(j, A) { SV HD; HD.w = cross(w_GP, o.H[j].w); \
+                                 HD.v = mulSkip<A>(R_GF, axisCross<A>(wxr)) + cross(w_GP, o.H[j].v); VD = VD + u[j]*HD; }
+    #define SBK_TRCOL_D(j)     { SV HD; HD.w = zero3(); HD.v = cross(w_GP, o.H[j].v); VD = VD + u[j]*HD; }
+    if constexpr (JT == JT_PIN) SBK_ROTCOL_D(0, 2)
+    else if constexpr (JT == JT_SLIDER) SBK_TRCOL_D(0)
+    else if constexpr (JT == JT_UNIVERSAL) {
+        SBK_ROTCOL_D(0, 0)
+        const V3 HDw1 = cross(w_FM, col(k.R_FM, 1));
         SV HD;
-        HD.w = mul(R_GF, HDw[j]) + cross(w_GP, o.H[j].w);
-        HD.v = mul(R_GF, cross(HDw[j], r) + cross(Hw[j], wxr)) + cross(w_GP, o.H[j].v);
-        VD = VD + u[j]*HD;
+        HD.w = mul(R_GF, HDw1) + cross(w_GP, o.H[1].w);
+        HD.v = mul(R_GF, cross(HDw1, r) + cross(k.Hw[1], wxr)) + cross(w_GP, o.H[1].v);
+        VD = VD + u[1]*HD;
+    } else {
+        SBK_ROTCOL_D(0, 0) SBK_ROTCOL_D(1, 1) SBK_ROTCOL_D(2, 2)
+        if constexpr (JT == JT_FREE) { SBK_TRCOL_D(3) SBK_TRCOL_D(4) SBK_TRCOL_D(5) }
     }
+    #undef SBK_ROTCOL_D
+    #undef SBK_TRCOL_D
 
     // ---- joint-independent velocity kinematics (RigidBodyNode.cpp:97-174) ----------------------
     o.V = phiT(o.l, V_GP) + V_PB;
@@ -416,14 +480,11 @@ SBK_HD void kinReverse(const BodyConst& bc, const KinLocal<JointDims<JT>::nu>& k
     p_GP = p_GB - l;
     const bool noRPF = (bc.flags & BF_NO_R_PF) != 0;
     const M3 R_GF = noRPF ? R_GP : mul(R_GP, loadR(bc.X_PF));
-    SV V_PB = zeroSV();
+    SV H[d];
+    jointH<JT>(R_GF, k, H);
+    SV V_PB = u[0]*H[0];
 #pragma unroll
-    for (int j = 0; j < d; ++j) {
-        SV Hj;
-        Hj.w = mul(R_GF, k.Hw[j]);
-        Hj.v = mul(R_GF, k.Hv[j] + cross(k.Hw[j], k.r));
-        V_PB = V_PB + u[j]*Hj;
-    }
+    for (int j = 1; j < d; ++j) V_PB = V_PB + u[j]*H[j];
     V_GP.w = V_GB.w - V_PB.w;
     V_GP.v = (V_GB.v - V_PB.v) - cross(V_GP.w, l);
 }
