@@ -44,10 +44,30 @@ F_EVAL = {"PIN": 1180.0, "SLIDER": 1130.0, "UNIVERSAL": 1710.0, "BALL": 2060.0, 
 
 
 def algorithmic_work(info):
-    """(flop, compulsory HBM bytes) per instance-step, SURVEY.md section 8(d)."""
+    """(flop, compulsory HBM bytes) per instance-step, SURVEY.md section 8(d): the reference's own flop
+    accounting per derivative evaluation and mobilizer kind for general frames; a body whose R_PF is
+    exactly the identity (the reference's noR_PF template flag) saves one transform compose and one
+    H re-expression (about 120 flop, section 8(d): Pin 1.18k -> 1.06k), a leaf body has no child
+    inertia / force shift (about 110 flop: 1.06k -> 0.95k)."""
     ny = info.nq + info.nu
-    flop = 5.0 * sum(F_EVAL[j] for j in info.joints if j in F_EVAL) + 30.0 * ny
-    return flop, 2.0 * 8.0 * ny
+    nchild = [0] * info.nb
+    for b, p in enumerate(info.parents):
+        if b > 0:
+            nchild[p] += 1
+    ident = ["1", "0", "0", "0", "1", "0", "0", "0", "1"]
+    flop = 0.0
+    for line in info.text.splitlines():
+        tok = line.split()
+        if not tok or tok[0] != "body" or tok[3] not in F_EVAL:
+            continue
+        b = int(tok[1])
+        f = F_EVAL[tok[3]]
+        if [str(int(float(x))) if float(x) in (0.0, 1.0) else x for x in tok[14:23]] == ident:
+            f -= 120.0
+        if nchild[b] == 0:
+            f -= 110.0
+        flop += 5.0 * f
+    return flop + 30.0 * ny, 2.0 * 8.0 * ny
 
 
 def sample_clocks(stop, out):
@@ -242,7 +262,7 @@ def main():
                 "peak_source": "measured live: sbk_dfma_probe DFMA kernel on this GPU (MEASURED_PEAKS.json has no FP64 entry)",
                 "hbm_algorithmic_GBs": per_gpu_rate * r["bytes_per_inst_step"] / 1e9,
                 "hbm_peak_GBs": peaks.get("hbm_gbs"),
-                "kernel": {1: "tpiKernel<OP_RKM> (thread-per-instance, LEAN records)", 2: "fusedRkmKernel (register-resident)",
+                "kernel": {1: "tpiKernel<OP_RKM> (thread-per-instance, reversible kinematics, persistent task queue)", 2: "fusedRkmKernel (register-resident)",
                            3: "lpKernel<OP_RKM> (level-parallel)"}[r["plan"]],
                 "kernel_ms_last_launch": r["kernel_ms_last"],
                 "fp64_pipe_active_ncu": NCU_FP64_PIPE_ACTIVE.get(args.workload),

@@ -198,6 +198,19 @@ int sbk_get_applied_forces(sbk_batch*, double* f_mob, double* F_body);
  * Force.cpp:354-361).  Needs Velocity stage (ke) / Position stage (pe).  Host [N], nullable.   */
 int sbk_calc_energy(sbk_batch*, double* kinetic, double* potential);
 
+/* SimbodyMatterSubsystem::calcMobilizerReactionForces (SimbodyMatterSubsystem.h:2479,
+ * SimbodyMatterSubsystemRep.cpp:5788-5832): the spatial force each mobilizer applies to its outboard
+ * body at the origin of the outboard frame M, expressed in Ground; entry 0 is the reaction that
+ * holds Ground.  Needs the acceleration stage (SBK_ERR_STAGE otherwise, also after an operator call
+ * that reused the acceleration cache).  Host FM_G [nb][6][N].                                  */
+int sbk_calc_mobilizer_reaction_forces(sbk_batch*, double* FM_G);
+
+/* SimbodyMatterSubsystem::multiplyBySystemJacobian / multiplyBySystemJacobianTranspose
+ * (SimbodyMatterSubsystem.h:554,646; RigidBodyNodeSpec.cpp:760-815).  Position stage.
+ * v [nu][N] -> Jv [nb][6][N] (body origin spatial velocities);  F [nb][6][N] -> JtF [nu][N].  */
+int sbk_multiply_by_system_jacobian(sbk_batch*, const double* v, double* Jv);
+int sbk_multiply_by_system_jacobian_transpose(sbk_batch*, const double* F_body, double* JtF);
+
 /* ---- operators ------------------------------------------------------------------------ */
 /* SimbodyMatterSubsystem::calcAcceleration / calcAccelerationIgnoringConstraints
  * (SimbodyMatterSubsystem.h:2141,2171; SimbodyMatterSubsystem.cpp:151-226).

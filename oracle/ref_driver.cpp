@@ -7,6 +7,7 @@
 //   slots  : prints the q/u slot map Simbody assigned
 //   eval   : for N states, dumps realize(Acceleration) results and the matter operators
 //            (calcAcceleration, multiplyByM, multiplyByMInv, calcResidualForceIgnoringConstraints)
+//   extras : calcMobilizerReactionForces, multiplyBySystemJacobian[Transpose]
 //   step   : RungeKuttaMersonIntegrator, fixed step h, nsteps steps, for N states
 //   adaptive: RungeKuttaMersonIntegrator with error control to a final time (config C1)
 //   bench  : CPU baseline -- one independent System+State+Integrator per host thread
@@ -175,6 +176,37 @@ static int cmdEnergy(RefSystem& rs, const char* inPath, const char* outPath, int
     return 0;
 }
 
+// ---- extras ---------------------------------------------------------------------------------
+// in  per instance: q[nq] u[nu] v[nu] F[nb*6]
+// out per instance: FM_G[nb*6]  calcMobilizerReactionForces at realize(Acceleration)
+//                   Jv[nb*6]    multiplyBySystemJacobian(v)
+//                   JtF[nu]     multiplyBySystemJacobianTranspose(F)
+static int cmdExtras(RefSystem& rs, const char* inPath, const char* outPath, int N) {
+    const int nb=rs.nb, nq=rs.nq, nu=rs.nu;
+    const int inStride = nq + 2*nu + 6*nb, outStride = 12*nb + nu;
+    std::vector<double> in = readDoubles(inPath);
+    if ((int)in.size() != N*inStride) { std::fprintf(stderr, "extras: bad input size\n"); return 2; }
+    std::vector<double> out((size_t)N*outStride);
+    State s = rs.defaultState;
+    for (int k = 0; k < N; ++k) {
+        const double* p = &in[(size_t)k*inStride];
+        double* o = &out[(size_t)k*outStride];
+        setQU(s, p, nq, p+nq, nu);
+        rs.system.realize(s, Stage::Acceleration);
+        Vector_<SpatialVec> FM; rs.matter.calcMobilizerReactionForces(s, FM);
+        for (int b = 0; b < nb; ++b) { for (int i = 0; i < 3; ++i) *o++ = FM[b][0][i]; for (int i = 0; i < 3; ++i) *o++ = FM[b][1][i]; }
+        Vector v(nu); for (int i = 0; i < nu; ++i) v[i] = p[nq+nu+i];
+        Vector_<SpatialVec> Jv; rs.matter.multiplyBySystemJacobian(s, v, Jv);
+        for (int b = 0; b < nb; ++b) { for (int i = 0; i < 3; ++i) *o++ = Jv[b][0][i]; for (int i = 0; i < 3; ++i) *o++ = Jv[b][1][i]; }
+        Vector_<SpatialVec> F(nb); const double* pF = p + nq + 2*nu;
+        for (int b = 0; b < nb; ++b) F[b] = SpatialVec(Vec3(pF[6*b],pF[6*b+1],pF[6*b+2]), Vec3(pF[6*b+3],pF[6*b+4],pF[6*b+5]));
+        Vector JtF; rs.matter.multiplyBySystemJacobianTranspose(s, F, JtF);
+        for (int i = 0; i < nu; ++i) *o++ = JtF[i];
+    }
+    writeDoubles(outPath, out);
+    return 0;
+}
+
 // ---- step -----------------------------------------------------------------------------------
 // in per instance: q[nq] u[nu]; out per instance: q[nq] u[nu] stepsTaken realizations qProjections
 static void configureFixed(RungeKuttaMersonIntegrator& integ, double h, double accuracy) {
@@ -311,6 +343,7 @@ int main(int argc, char** argv) {
         }
         if (cmd == "eval" && argc >= 6) return cmdEval(rs, argv[3], argv[4], std::atoi(argv[5]));
         if (cmd == "energy" && argc >= 6) return cmdEnergy(rs, argv[3], argv[4], std::atoi(argv[5]));
+        if (cmd == "extras" && argc >= 6) return cmdExtras(rs, argv[3], argv[4], std::atoi(argv[5]));
         if (cmd == "step" && argc >= 8)
             return cmdStep(rs, argv[3], argv[4], std::atoi(argv[5]), std::atof(argv[6]), std::atoi(argv[7]),
                            argc > 8 ? std::atof(argv[8]) : -1);

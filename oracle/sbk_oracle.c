@@ -354,6 +354,54 @@ int oracle_eval(int nb, const int* parent, const int* joint, const double* mass,
     return 0;
 }
 
+/* calcMobilizerReactionForces (SimbodyMatterSubsystemRep.cpp:5788-5832): FB = zPlus + PPlus*(~Phi A_GP), reported at
+ * the M frame origin: FM = (m - (R_GB p_BM) x f, f).  Ground collects its base bodies (RigidBodyNode_Weld.cpp:197-222).
+ * multiplyBySystemJacobian / Transpose: RigidBodyNodeSpec.cpp:760-815.
+ * in  per instance: q[nq] u[nu] v[nu] F[nb*6];  out: FM_G[nb*6] Jv[nb*6] JtF[nu]   (same layout as `ref_driver extras`) */
+int oracle_extras(int nb, const int* parent, const int* joint, const double* mass, const double* com, const double* ui,
+                  const double* XPF, const double* XBM, int nf, const int* fkind, const int* fbody, const int* fcoord,
+                  const double* fa, const double* fb, const double* fdir, int N, const double* in, double* out) {
+    Model M = mkModel(nb, parent, joint, mass, com, ui, XPF, XBM, nf, fkind, fbody, fcoord, fa, fb, fdir);
+    int nq, nu, nquat; Body* B = setupBodies(&M, &nq, &nu, &nquat);
+    const int inStride = nq + 2*nu + 6*nb, outStride = 12*nb + nu;
+    double* ydot = (double*)malloc(sizeof(double)*(size_t)(nq+nu+1));
+    double* qerr = (double*)malloc(sizeof(double)*(size_t)(nquat+1));
+    double* z = (double*)malloc(sizeof(double)*(size_t)(6*nb));
+    for (int k = 0; k < N; ++k) {
+        const double* p = in + (size_t)k*inStride; double* o = out + (size_t)k*outStride;
+        derivs(&M, B, nq, nu, p, ydot, NULL, qerr, NULL);
+        /* reactions */
+        double z0[6]; for (int i = 0; i < 6; ++i) z0[i] = -B[0].Fapp[i];
+        for (int c = 1; c < nb; ++c) if (parent[c] == 0) { double t[6]; phiF(B[c].l, B[c].zP, t); for (int i = 0; i < 6; ++i) z0[i] += t[i]; }
+        for (int i = 0; i < 6; ++i) o[i] = z0[i];
+        for (int b = 1; b < nb; ++b) {
+            const Body* me = &B[b]; const Body* pa = &B[parent[b]];
+            double pPB[3] = {me->p[0]-pa->p[0], me->p[1]-pa->p[1], me->p[2]-pa->p[2]}, Ap[6], PA[6], FB[6], pBM[3], t[3];
+            phiT(pPB, pa->A, Ap); mat6vec(me->PP, Ap, PA);
+            for (int i = 0; i < 6; ++i) FB[i] = me->zP[i] + PA[i];
+            matvec3(me->R, M.X_BM + 12*b + 9, pBM); cross(pBM, FB+3, t);
+            for (int i = 0; i < 3; ++i) { o[6*b+i] = FB[i] - t[i]; o[6*b+3+i] = FB[3+i]; }
+        }
+        /* J v */
+        const double* v = p + nq + nu; double* Jv = o + 6*nb;
+        for (int i = 0; i < 6; ++i) Jv[i] = 0;
+        for (int b = 1; b < nb; ++b) {
+            const Body* me = &B[b]; double sh[6]; phiT(me->l, Jv + 6*parent[b], sh);
+            for (int i = 0; i < 6; ++i) { double s = 0; for (int j = 0; j < me->nu; ++j) s += me->H[j][i]*v[me->u0+j]; Jv[6*b+i] = sh[i] + s; }
+        }
+        /* ~J F */
+        const double* F = p + nq + 2*nu; double* JtF = o + 12*nb;
+        memcpy(z, F, sizeof(double)*(size_t)(6*nb));
+        for (int b = nb-1; b >= 1; --b) {
+            const Body* me = &B[b];
+            for (int c = b+1; c < nb; ++c) if (parent[c] == b) { double t[6]; phiF(B[c].l, z + 6*c, t); for (int i = 0; i < 6; ++i) z[6*b+i] += t[i]; }
+            for (int j = 0; j < me->nu; ++j) { double s = 0; for (int i = 0; i < 6; ++i) s += me->H[j][i]*z[6*b+i]; JtF[me->u0+j] = s; }
+        }
+    }
+    free(ydot); free(qerr); free(z); free(B);
+    return 0;
+}
+
 static double errNorm(const Model* M, const Body* B, int nq, int nu, const double* y1, const double* y0, const double* err, int infNorm) {
     double qa = 0, ua = 0;
     for (int i = 0; i < nu; ++i) { double a = fabs(y0[nq+i]), sc = a > 1.0 ? 1.0/a : 1.0, v = sc*err[nq+i]; if (infNorm) { if (fabs(v) > ua) ua = fabs(v); } else ua += v*v; }

@@ -75,6 +75,9 @@ SYMBOLS = {
     "sbk_get_body_accelerations": (ctypes.c_int, [_P, c_double_p]),
     "sbk_get_applied_forces": (ctypes.c_int, [_P, c_double_p, c_double_p]),
     "sbk_calc_energy": (ctypes.c_int, [_P, c_double_p, c_double_p]),
+    "sbk_calc_mobilizer_reaction_forces": (ctypes.c_int, [_P, c_double_p]),
+    "sbk_multiply_by_system_jacobian": (ctypes.c_int, [_P, c_double_p, c_double_p]),
+    "sbk_multiply_by_system_jacobian_transpose": (ctypes.c_int, [_P, c_double_p, c_double_p]),
     "sbk_calc_acceleration": (ctypes.c_int, [_P, c_double_p, c_double_p, c_double_p, c_double_p]),
     "sbk_multiply_by_M": (ctypes.c_int, [_P, c_double_p, c_double_p]),
     "sbk_multiply_by_MInv": (ctypes.c_int, [_P, c_double_p, c_double_p]),

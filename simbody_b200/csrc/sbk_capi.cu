@@ -463,6 +463,37 @@ int sbk_calc_energy(sbk_batch* b, double* ke, double* pe) {
     return SBK_OK;
 }
 
+int sbk_calc_mobilizer_reaction_forces(sbk_batch* b, double* FM_G) {
+    if (!b || !FM_G) return fail(SBK_ERR_ARG, "sbk_calc_mobilizer_reaction_forces: null argument");
+    if (int rc = useDevice(b)) return rc;
+    if (int rc = needStage(b, ST_ACCELERATION, "sbk_calc_mobilizer_reaction_forces")) return rc;
+    if (!b->accelValid) return fail(SBK_ERR_STAGE, "sbk_calc_mobilizer_reaction_forces: an operator call overwrote the acceleration cache; realize acceleration again");
+    const size_t rows = (size_t)b->topo->nb*6;
+    if (int rc = ensureScratch(b, rows*b->N)) return rc;
+    CUDA_TRY(launchReaction(b->a, b->dScratch, b->stream)); b->launches++;
+    return d2h(b, FM_G, b->dScratch, rows);
+}
+int sbk_multiply_by_system_jacobian(sbk_batch* b, const double* v, double* Jv) {
+    if (!b || !v || !Jv) return fail(SBK_ERR_ARG, "sbk_multiply_by_system_jacobian: null argument");
+    if (int rc = useDevice(b)) return rc;
+    if (int rc = needStage(b, ST_POSITION, "sbk_multiply_by_system_jacobian")) return rc;
+    const size_t rows = (size_t)b->topo->nb*6;
+    if (int rc = ensureScratch(b, rows*b->N)) return rc;
+    if (int rc = h2d(b, b->dOpB, v, b->topo->nu)) return rc;
+    CUDA_TRY(launchJacobian(b->a, b->dOpB, b->dScratch, b->stream)); b->launches++;
+    return d2h(b, Jv, b->dScratch, rows);
+}
+int sbk_multiply_by_system_jacobian_transpose(sbk_batch* b, const double* F, double* JtF) {
+    if (!b || !F || !JtF) return fail(SBK_ERR_ARG, "sbk_multiply_by_system_jacobian_transpose: null argument");
+    if (int rc = useDevice(b)) return rc;
+    if (int rc = needStage(b, ST_POSITION, "sbk_multiply_by_system_jacobian_transpose")) return rc;
+    const size_t rows = (size_t)b->topo->nb*6;
+    if (int rc = ensureScratch(b, 2*rows*b->N)) return rc;
+    if (int rc = h2d(b, b->dScratch, F, rows)) return rc;
+    CUDA_TRY(launchJacobianTranspose(b->a, b->dScratch, b->dScratch + rows*b->N, b->dOpOut, b->stream)); b->launches++;
+    return d2h(b, JtF, b->dOpOut, b->topo->nu);
+}
+
 // ---- operators --------------------------------------------------------------------------------
 int sbk_calc_acceleration(sbk_batch* b, const double* fmob, const double* Fbody, double* udot, double* A_GB) {
     if (!b) return fail(SBK_ERR_ARG, "null batch");

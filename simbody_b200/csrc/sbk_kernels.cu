@@ -495,6 +495,82 @@ __global__ void energyKernel(const KArgs a, double* ke, double* pe) {
     if (pe) pe[k] = pot;
 }
 
+// calcMobilizerReactionForces (SimbodyMatterSubsystemRep.cpp:5788-5832) from the records of a realized
+// acceleration stage: FB = zPlus + PPlus*(~Phi A_GP) at the body origin, reported at the origin of the
+// outboard frame M (FM = (m - (R_GB p_BM) x f, f)), expressed in Ground.  Ground's entry collects the
+// base bodies (RigidBodyNode_Weld.cpp:197-222; the lowered force elements apply nothing to Ground).
+__global__ void reactionKernel(const KArgs a, double* out) {
+    const int k = blockIdx.x*blockDim.x + threadIdx.x;
+    if (k >= a.N) return;
+    const BodyConst* bodies = reinterpret_cast<const BodyConst*>(a.tables);
+    auto rec = [&](int b) { CacheRef r; r.p = a.cache + bodies[b].cacheBase + instOffsetK(a, k); r.stride = a.cStride; return r; };
+    auto put = [&](int b, SV F) {
+        double* o = out + (long long)b*6*a.N + k;
+        o[0] = F.w.x; o[(long long)a.N] = F.w.y; o[2LL*a.N] = F.w.z; o[3LL*a.N] = F.v.x; o[4LL*a.N] = F.v.y; o[5LL*a.N] = F.v.z;
+    };
+    SV z0 = zeroSV();
+    for (int b = 1; b < a.nb; ++b) {
+        const BodyConst& bc = bodies[b];
+        const CacheRef me = rec(b), pa = rec(bc.parent);
+        const V3 pPB = me.ld3(F_XGB + 9) - pa.ld3(F_XGB + 9);
+        const SV APlus = phiT(pPB, pa.ldSV(F_AGB));
+        const SV zP = me.ldSV(F_ZPLUS);
+        const SV FB = zP + mul(me.ldABI(F_PPLUS), APlus);
+        const V3 pBM = mul(me.ldM3(F_XGB), mk(bc.p_BM[0], bc.p_BM[1], bc.p_BM[2]));
+        SV FM; FM.w = FB.w - cross(pBM, FB.v); FM.v = FB.v;
+        put(b, FM);
+        if (bc.parent == 0) z0 = z0 + phi(me.ld3(F_L), zP);
+    }
+    put(0, z0);
+}
+
+// multiplyBySystemJacobian (RigidBodyNodeSpec.cpp:760-780): Jv_b = ~Phi_b Jv_parent + H_b v_b, base to tip.
+__global__ void jacobianKernel(const KArgs a, const double* v, double* out) {
+    const int k = blockIdx.x*blockDim.x + threadIdx.x;
+    if (k >= a.N) return;
+    const BodyConst* bodies = reinterpret_cast<const BodyConst*>(a.tables);
+    const long long N = a.N;
+    for (int i = 0; i < 6; ++i) out[i*N + k] = 0.0;
+    for (int b = 1; b < a.nb; ++b) {
+        const BodyConst& bc = bodies[b];
+        CacheRef me; me.p = a.cache + bc.cacheBase + instOffsetK(a, k); me.stride = a.cStride;
+        const double* po = out + (long long)bc.parent*6*N + k;
+        SV JP; JP.w = mk(po[0], po[N], po[2*N]); JP.v = mk(po[3*N], po[4*N], po[5*N]);
+        const SV sh = phiT(me.ld3(F_L), JP);
+        SV Hv = zeroSV();
+        const int d = dofOfJoint(bc.joint);
+        for (int j = 0; j < d; ++j) Hv = Hv + v[(long long)(bc.u0 + j)*N + k]*me.ldSV(F_H + 6*j);
+        const SV J = sh + Hv;
+        double* o = out + (long long)b*6*N + k;
+        o[0] = J.w.x; o[N] = J.w.y; o[2*N] = J.w.z; o[3*N] = J.v.x; o[4*N] = J.v.y; o[5*N] = J.v.z;
+    }
+}
+
+// multiplyBySystemJacobianTranspose (RigidBodyNodeSpec.cpp:790-815): z_b = F_b + sum Phi_c z_c, out_b = ~H_b z_b,
+// tip to base.  z [nb*6][N] is scratch.
+__global__ void jacobianTransposeKernel(const KArgs a, const double* F, double* z, double* out) {
+    const int k = blockIdx.x*blockDim.x + threadIdx.x;
+    if (k >= a.N) return;
+    const BodyConst* bodies = reinterpret_cast<const BodyConst*>(a.tables);
+    const int* children = reinterpret_cast<const int*>(a.tables + a.childrenOff);
+    const long long N = a.N;
+    auto ld6 = [&](const double* p, int b) { const double* q = p + (long long)b*6*N + k; SV r; r.w = mk(q[0], q[N], q[2*N]); r.v = mk(q[3*N], q[4*N], q[5*N]); return r; };
+    for (int b = a.nb - 1; b >= 1; --b) {
+        const BodyConst& bc = bodies[b];
+        CacheRef me; me.p = a.cache + bc.cacheBase + instOffsetK(a, k); me.stride = a.cStride;
+        SV zb = ld6(F, b);
+        for (int c = 0; c < bc.nchild; ++c) {
+            const int cb = children[bc.childStart + c];
+            CacheRef ch; ch.p = a.cache + bodies[cb].cacheBase + instOffsetK(a, k); ch.stride = a.cStride;
+            zb = zb + phi(ch.ld3(F_L), ld6(z, cb));
+        }
+        double* o = z + (long long)b*6*N + k;
+        o[0] = zb.w.x; o[N] = zb.w.y; o[2*N] = zb.w.z; o[3*N] = zb.v.x; o[4*N] = zb.v.y; o[5*N] = zb.v.z;
+        const int d = dofOfJoint(bc.joint);
+        for (int j = 0; j < d; ++j) out[(long long)(bc.u0 + j)*N + k] = dot(me.ldSV(F_H + 6*j), zb);
+    }
+}
+
 // Memory-pattern probe (bench/diagnostics only): one thread per instance walks `nb` records of
 // `rowsIn` + `rowsOut` rows in the [row][N] layout of the thread-per-instance plan, loading rowsIn
 // doubles and storing rowsOut doubles per record with no arithmetic to speak of.  It measures what
@@ -598,6 +674,18 @@ cudaError_t launchGatherBodyField(const KArgs& a, int fieldOffset, int width, do
 }
 cudaError_t launchEnergy(const KArgs& a, double* ke, double* pe, cudaStream_t stream) {
     energyKernel<<<(a.N + 127)/128, 128, 0, stream>>>(a, ke, pe);
+    return cudaGetLastError();
+}
+cudaError_t launchReaction(const KArgs& a, double* out, cudaStream_t stream) {
+    reactionKernel<<<(a.N + 127)/128, 128, 0, stream>>>(a, out);
+    return cudaGetLastError();
+}
+cudaError_t launchJacobian(const KArgs& a, const double* v, double* out, cudaStream_t stream) {
+    jacobianKernel<<<(a.N + 127)/128, 128, 0, stream>>>(a, v, out);
+    return cudaGetLastError();
+}
+cudaError_t launchJacobianTranspose(const KArgs& a, const double* F, double* z, double* out, cudaStream_t stream) {
+    jacobianTransposeKernel<<<(a.N + 127)/128, 128, 0, stream>>>(a, F, z, out);
     return cudaGetLastError();
 }
 cudaError_t launchMemPattern(double* buf, int N, int nb, int rowsIn, int rowsOut, int sweeps, int minBlocks, cudaStream_t stream) {

@@ -72,6 +72,11 @@ cudaError_t launchTranspose(const double* src, double* dst, int rows, int cols, 
 cudaError_t launchGatherBodyField(const KArgs& a, int fieldOffset, int width, double* out, cudaStream_t stream);
 // Kinetic / potential energy per instance from the realized records (ke, pe: device [N], nullable).
 cudaError_t launchEnergy(const KArgs& a, double* ke, double* pe, cudaStream_t stream);
+// Mobilizer reaction forces at the M frame origins, in Ground: out [nb*6][N] (needs a realized acceleration stage).
+cudaError_t launchReaction(const KArgs& a, double* out, cudaStream_t stream);
+// System Jacobian products from the realized position records: Jv [nb*6][N] = J v;  JtF [nu][N] = ~J F (z: scratch [nb*6][N]).
+cudaError_t launchJacobian(const KArgs& a, const double* v, double* out, cudaStream_t stream);
+cudaError_t launchJacobianTranspose(const KArgs& a, const double* F, double* z, double* out, cudaStream_t stream);
 // Memory-pattern probe for the thread-per-instance record layout (diagnostics).
 cudaError_t launchMemPattern(double* buf, int N, int nb, int rowsIn, int rowsOut, int sweeps, int minBlocks, cudaStream_t stream);
 // FP64 FMA throughput probe: returns flops executed; used by bench.py to measure the FP64 roofline.

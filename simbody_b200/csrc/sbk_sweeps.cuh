@@ -76,6 +76,7 @@ struct BodyConst {
     double mass;
     double com_B[3];
     double G_B[6];          // unit inertia about Bo in B: xx yy zz xy xz yz
+    double p_BM[4];         // origin of the outboard frame M in B (X_BM.p; reaction forces are reported there); [3] pads
     long long cacheBase;    // element offset of this body's cache record (plan dependent)
     long long parentCacheBase;
     int joint, parent, q0, u0;
@@ -233,6 +234,7 @@ template <bool BLK> SBK_HD long long stateIndex(const Ctx& c, int inst, int slot
 template <bool BLK> SBK_HD double ldS(const Ctx& c, int inst, const double* a, int slot) { return gld(a + stateIndex<BLK>(c, inst, slot)); }
 template <bool BLK> SBK_HD void   stS(const Ctx& c, int inst, double* a, int slot, double v) { gst(a + stateIndex<BLK>(c, inst, slot), v); }
 
+SBK_HD int dofOfJoint(int jt) { return jt == JT_FREE ? 6 : jt == JT_BALL ? 3 : jt == JT_UNIVERSAL ? 2 : jt == JT_GROUND ? 0 : 1; }
 SBK_HD M3 loadR(const double* X) { M3 R;
 #pragma unroll
     for (int i = 0; i < 9; ++i) R.a[i] = X[i]; return R; }

@@ -75,6 +75,7 @@ void compileTopology(const ModelSpec& spec, sbk_topology& t) {
         for (int i = 0; i < 3; ++i)
             bc.X_MB[9+i] = -(bc.X_MB[3*i]*d.X_BM[9] + bc.X_MB[3*i+1]*d.X_BM[10] + bc.X_MB[3*i+2]*d.X_BM[11]);
         bc.mass = d.mass;
+        for (int i = 0; i < 3; ++i) bc.p_BM[i] = d.X_BM[9+i];
         for (int i = 0; i < 3; ++i) bc.com_B[i] = d.com_B[i];
         for (int i = 0; i < 6; ++i) bc.G_B[i] = d.unit_inertia_OB_B[i];
         bc.joint = d.joint_type; bc.parent = d.parent < 0 ? 0 : d.parent;

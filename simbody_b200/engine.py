@@ -184,6 +184,27 @@ class BatchedMatter:
         self._chk(self.lib.sbk_calc_energy(self.handle, _dp(ke), _dp(pe)))
         return ke, pe
 
+    def calcMobilizerReactionForces(self):
+        """SimbodyMatterSubsystem::calcMobilizerReactionForces (SimbodyMatterSubsystem.h:2479): [nb, 6, N] spatial
+        forces at the M frame origins, in Ground; needs realizeAcceleration()."""
+        F = np.empty((self.topo.nb * 6, self.N))
+        self._chk(self.lib.sbk_calc_mobilizer_reaction_forces(self.handle, _dp(F)))
+        return F.reshape(self.topo.nb, 6, self.N)
+
+    def multiplyBySystemJacobian(self, v):
+        """J v: [nu, N] -> [nb, 6, N] (SimbodyMatterSubsystem.h:554); position stage."""
+        v = self._vec(v, self.topo.nu, "v")
+        out = np.empty((self.topo.nb * 6, self.N))
+        self._chk(self.lib.sbk_multiply_by_system_jacobian(self.handle, _dp(v), _dp(out)))
+        return out.reshape(self.topo.nb, 6, self.N)
+
+    def multiplyBySystemJacobianTranspose(self, F_G):
+        """~J F: [nb, 6, N] -> [nu, N] (SimbodyMatterSubsystem.h:646); position stage."""
+        F = self._vec(np.asarray(F_G).reshape(-1, self.N), self.topo.nb * 6, "F_G")
+        out = np.empty((self.topo.nu, self.N))
+        self._chk(self.lib.sbk_multiply_by_system_jacobian_transpose(self.handle, _dp(F), _dp(out)))
+        return out
+
     # ---- operators (SimbodyMatterSubsystem.h:2141,1262,1343,2234) --------------------------------
     def calcAcceleration(self, appliedMobilityForces=None, appliedBodyForces=None):
         f = self._vec(appliedMobilityForces, self.topo.nu, "appliedMobilityForces", True)

@@ -6,6 +6,7 @@
 //   calcAcceleration / calcAccelerationIgnoringConstraints   (:2141,:2171)
 //   multiplyByM / multiplyByMInv              (:1262,:1343)
 //   calcResidualForceIgnoringConstraints      (:2234)
+//   calcMobilizerReactionForces, multiplyBySystemJacobian[Transpose]   (:2479,:554,:646)
 //   RungeKuttaMersonIntegrator + Integrator::setFixedStepSize / setAccuracy /
 //   setConstraintTolerance / setUseInfinityNorm / setProjectEveryStep / stepBy / getNumStepsTaken /
 //   getNumRealizations                        (simmath/Integrator.h:143-394)
@@ -92,6 +93,19 @@ public:
     }
     void multiplyByMInv(const std::vector<double>& v, std::vector<double>& MinvV) {
         need(v, topo_.getNU(), "v"); MinvV.resize(v.size()); throwOnError(sbk_multiply_by_MInv(h_, v.data(), MinvV.data()));
+    }
+    // SimbodyMatterSubsystem::calcMobilizerReactionForces (:2479): FM_G [nb][6][N], needs realizeAcceleration()
+    void calcMobilizerReactionForces(std::vector<double>& FM_G) {
+        FM_G.resize((size_t)6*topo_.getNumBodies()*n_); throwOnError(sbk_calc_mobilizer_reaction_forces(h_, FM_G.data()));
+    }
+    // multiplyBySystemJacobian / multiplyBySystemJacobianTranspose (:554,:646)
+    void multiplyBySystemJacobian(const std::vector<double>& v, std::vector<double>& Jv) {
+        need(v, topo_.getNU(), "v"); Jv.resize((size_t)6*topo_.getNumBodies()*n_);
+        throwOnError(sbk_multiply_by_system_jacobian(h_, v.data(), Jv.data()));
+    }
+    void multiplyBySystemJacobianTranspose(const std::vector<double>& F_G, std::vector<double>& JtF) {
+        need(F_G, 6*topo_.getNumBodies(), "F_G"); JtF.resize((size_t)topo_.getNU()*n_);
+        throwOnError(sbk_multiply_by_system_jacobian_transpose(h_, F_G.data(), JtF.data()));
     }
     void calcResidualForceIgnoringConstraints(const std::vector<double>& appliedMobilityForces, const std::vector<double>& appliedBodyForces,
                                               const std::vector<double>& knownUdot, std::vector<double>& residual) {

@@ -4,6 +4,7 @@ Run where /root/reference was compiled by `make -C oracle`:   python tests/golde
 Each fixture holds the model text, seeded inputs, and the reference's outputs for
   * realize(Acceleration) + the matter operators   (ref_driver eval)
   * fixed-step RungeKuttaMerson                      (ref_driver step)
+  * calcMobilizerReactionForces, multiplyBySystemJacobian[Transpose]   (ref_driver extras)
 so that the parity tests can run on machines without the reference sources.
 """
 import os
@@ -37,8 +38,10 @@ def main():
         yout = ref.step(info, y0, h, nsteps)
         path = os.path.join(HERE, "%s.npz" % name)
         energy = ref.energy(info, ein[:, :info.nq + info.nu])      # [n, 2] kinetic, potential at the eval states
+        xin = info.random_extras_input(neval, 3000 + len(name), q_scale=qs)    # reactions, J v, ~J F  (ref_driver extras)
+        xout = ref.extras(info, xin)
         np.savez_compressed(path, text=np.array(text), eval_in=ein, eval_out=eout, step_in=y0, step_out=yout,
-                            h=h, nsteps=nsteps, slots=np.array(ref.slots(text)), energy=energy)
+                            h=h, nsteps=nsteps, slots=np.array(ref.slots(text)), energy=energy, extras_in=xin, extras_out=xout)
         print("wrote", path, os.path.getsize(path), "bytes")
 
 

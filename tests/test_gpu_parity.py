@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 
 import simbody_b200 as sb
-from _harness import ModelInfo, RefDriver, have_ref, rel_err
+from _harness import ModelInfo, RefDriver, check_sdfast2, have_ref, rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-11
@@ -281,3 +281,55 @@ def test_energy_conservation_over_a_run():
         drift = np.abs((ke1 + pe1) - (ke0 + pe0)) / np.maximum(1.0, np.abs(ke0 + pe0))
         assert drift.max() < 1e-7, (name, drift.max())
         bm.close(); topo.close()
+
+
+def run_extras(info, xin, plan=None):
+    n = xin.shape[0]; nq, nu, nb = info.nq, info.nu, info.nb
+    topo = sb.Topology(text=info.text); bm = sb.BatchedMatter(topo, n)
+    if plan is not None:
+        bm.setPlan(plan)
+    bm.setState(soa(xin[:, :nq]), soa(xin[:, nq:nq + nu]))
+    with pytest.raises(sb.SbkError):
+        bm.calcMobilizerReactionForces()            # Stage::Acceleration not realized yet
+    bm.realizeAcceleration()
+    res = {"FM_G": bm.calcMobilizerReactionForces().reshape(nb * 6, n).T,
+           "Jv": bm.multiplyBySystemJacobian(soa(xin[:, nq + nu:nq + 2 * nu])).reshape(nb * 6, n).T,
+           "JtF": bm.multiplyBySystemJacobianTranspose(soa(xin[:, nq + 2 * nu:])).T,
+           "X_GB": bm.getBodyTransforms().reshape(nb * 12, n).T}
+    bm.close(); topo.close()
+    return res
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_reactions_and_jacobian_match_golden(name):
+    """calcMobilizerReactionForces, multiplyBySystemJacobian[Transpose] against the reference's recorded outputs."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    info = ModelInfo(str(g["text"]))
+    ref = info.split_extras_out(g["extras_out"])
+    got = run_extras(info, g["extras_in"])
+    for k in ref:
+        assert rel_err(got[k], ref[k]) < TOL, (name, k, rel_err(got[k], ref[k]))
+    if name in ("mixed7", "humanoid30", "branched_tree"):
+        got3 = run_extras(info, g["extras_in"], plan=3)        # level-parallel record layout
+        for k in ref:
+            assert rel_err(got3[k], ref[k]) < TOL, (name, k, "plan 3")
+
+
+def test_reaction_forces_match_sdfast_known_answers():
+    """TestMobilizerReactionForces.cpp:408-436: values generated by SD/FAST, independent of Simbody."""
+    def react(info, q, u):
+        xin = np.concatenate([q, u, np.zeros((q.shape[0], info.nu + 6 * info.nb))], axis=1)
+        r = run_extras(info, xin)
+        return r["FM_G"], r["X_GB"]
+    check_sdfast2(react)
+
+
+def test_jacobian_transpose_is_adjoint_of_jacobian():
+    """Size-independent property at a full-size batch: <J v, F> == <v, ~J F> for every instance."""
+    info = ModelInfo(sb.model_text("humanoid30"))
+    n = 4096
+    x = info.random_extras_input(n, 77, q_scale=0.5)
+    r = run_extras(info, x)
+    v = x[:, info.nq + info.nu:info.nq + 2 * info.nu]; F = x[:, info.nq + 2 * info.nu:]
+    lhs = np.sum(r["Jv"] * F, axis=1); rhs = np.sum(v * r["JtF"], axis=1)
+    assert np.max(np.abs(lhs - rhs) / (1 + np.abs(lhs))) < 1e-12

@@ -11,7 +11,7 @@ import os
 import numpy as np
 import pytest
 
-from _harness import COracle, HostEmu, ModelInfo, RefDriver, have_ref, rel_err, ROOT
+from _harness import COracle, HostEmu, ModelInfo, RefDriver, check_sdfast2, have_ref, rel_err, ROOT
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 MODELS = ["double_pendulum", "pin_chain", "mixed7", "humanoid30", "branched_tree"]
@@ -49,6 +49,28 @@ def test_kernel_math_on_host_matches_reference_golden(built, name):
     ny = info.nq + info.nu
     ys = HostEmu().step(info, g["step_in"], float(g["h"]), int(g["nsteps"]))
     assert rel_err(ys[:, :ny], g["step_out"][:, :ny]) < 1e-10
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_c_oracle_extras_match_reference_golden(built, name):
+    """calcMobilizerReactionForces and the system Jacobian products of the C restatement against the
+    reference's recorded outputs (ref_driver extras)."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    info = ModelInfo(str(g["text"]))
+    ref = info.split_extras_out(g["extras_out"])
+    got = info.split_extras_out(COracle().extras(info, g["extras_in"]))
+    for k in ref:
+        assert rel_err(got[k], ref[k]) < 1e-10, (name, k, rel_err(got[k], ref[k]))
+
+
+def test_c_oracle_reaction_forces_match_sdfast(built):
+    """Known answers that do not come from Simbody: TestMobilizerReactionForces.cpp:408-436."""
+    def react(info, q, u):
+        co = COracle()
+        xin = np.concatenate([q, u, np.zeros((q.shape[0], info.nu + 6 * info.nb))], axis=1)
+        ein = np.concatenate([q, u, np.zeros((q.shape[0], 4 * info.nu + 6 * info.nb))], axis=1)
+        return info.split_extras_out(co.extras(info, xin))["FM_G"], info.split_eval_out(co.eval(info, ein))["X_GB"]
+    check_sdfast2(react)
 
 
 def test_survey_golden_double_pendulum(built):
