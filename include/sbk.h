@@ -64,7 +64,9 @@ enum {
 enum {
     SBK_FORCE_GRAVITY = 1,  /* Force::Gravity: a = magnitude g, dir = unit "down"        */
     SBK_FORCE_SPRING  = 2,  /* Force::MobilityLinearSpring: body, coord, a = k, b = q0   */
-    SBK_FORCE_DAMPER  = 3   /* Force::MobilityLinearDamper: body, coord, a = c           */
+    SBK_FORCE_DAMPER  = 3,  /* Force::MobilityLinearDamper: body, coord, a = c           */
+    SBK_FORCE_UNIFORM_GRAVITY = 4, /* Force::UniformGravity (Force.cpp:1034-1057): dir = the gravity VECTOR g in Ground, zero height 0 */
+    SBK_FORCE_GLOBAL_DAMPER   = 5  /* Force::GlobalDamper (Force.cpp:996-998): f -= a*u on every mobility          */
 };
 
 /* One mobilized body, in MobilizedBodyIndex order; entry 0 must be Ground.
@@ -86,9 +88,9 @@ typedef struct sbk_force_desc {
     int32_t body;                 /* spring/damper: MobilizedBodyIndex                    */
     int32_t coord;                /* spring: MobilizerQIndex; damper: MobilizerUIndex     */
     int32_t pad_;
-    double  a;                    /* gravity g | spring k | damper c                      */
+    double  a;                    /* gravity g | spring k | damper c | global damper c    */
     double  b;                    /* spring q0                                            */
-    double  dir[3];               /* gravity: unit down direction in Ground               */
+    double  dir[3];               /* gravity: unit down direction | uniform gravity: vector g */
 } sbk_force_desc;
 
 /* Integrator options; mirrors Integrator::setAccuracy / setConstraintTolerance /

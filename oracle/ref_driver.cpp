@@ -84,6 +84,10 @@ struct RefSystem {
             else if (f.kind == SBK_FORCE_DAMPER)
                 Force::MobilityLinearDamper(forces, matter.getMobilizedBody(MobilizedBodyIndex(f.body)),
                                             MobilizerUIndex(f.coord), f.a);
+            else if (f.kind == SBK_FORCE_UNIFORM_GRAVITY)
+                Force::UniformGravity(forces, matter, Vec3(f.dir[0],f.dir[1],f.dir[2]));
+            else if (f.kind == SBK_FORCE_GLOBAL_DAMPER)
+                Force::GlobalDamper(forces, matter, f.a);
         }
         defaultState = system.realizeTopology();
         system.realizeModel(defaultState);

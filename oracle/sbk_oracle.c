@@ -35,7 +35,7 @@
 #include <string.h>
 
 enum { PIN = 1, SLIDER = 2, UNIVERSAL = 3, BALL = 4, FREE = 5 };
-enum { F_GRAVITY = 1, F_SPRING = 2, F_DAMPER = 3 };
+enum { F_GRAVITY = 1, F_SPRING = 2, F_DAMPER = 3, F_UNIFORM_GRAVITY = 4, F_GLOBAL_DAMPER = 5 };
 #define MAXD 6
 
 typedef struct {
@@ -248,11 +248,13 @@ static void systemForces(const Model* M, Body* B, const double* q, const double*
     for (int i = 0; i < nu; ++i) fmob[i] = 0;
     for (int b = 0; b < M->nb; ++b) memset(B[b].Fapp, 0, sizeof B[b].Fapp);
     for (int k = 0; k < M->nf; ++k) {
-        if (M->fkind[k] == F_GRAVITY) {
-            const double g[3] = {M->fa[k]*M->fdir[3*k], M->fa[k]*M->fdir[3*k+1], M->fa[k]*M->fdir[3*k+2]};
+        if (M->fkind[k] == F_GRAVITY || M->fkind[k] == F_UNIFORM_GRAVITY) {   /* Force_Gravity.cpp:532 g*d; Force.cpp:1053 the vector itself */
+            const int uni = M->fkind[k] == F_UNIFORM_GRAVITY;
+            const double g[3] = {uni ? M->fdir[3*k] : M->fa[k]*M->fdir[3*k], uni ? M->fdir[3*k+1] : M->fa[k]*M->fdir[3*k+1], uni ? M->fdir[3*k+2] : M->fa[k]*M->fdir[3*k+2]};
             for (int b = 1; b < M->nb; ++b) { double F[3] = {B[b].m*g[0], B[b].m*g[1], B[b].m*g[2]}, t[3]; cross(B[b].c, F, t);
                 for (int i = 0; i < 3; ++i) { B[b].Fapp[i] += t[i]; B[b].Fapp[3+i] += F[i]; } }
         } else if (M->fkind[k] == F_SPRING) { const Body* me = &B[M->fbody[k]]; fmob[me->u0 + M->fcoord[k]] += -M->fa[k]*(q[me->q0 + M->fcoord[k]] - M->fb[k]); }
+        else if (M->fkind[k] == F_GLOBAL_DAMPER) { for (int i = 0; i < nu; ++i) fmob[i] -= M->fa[k]*u[i]; }   /* Force.cpp:997 */
         else if (M->fkind[k] == F_DAMPER) { const Body* me = &B[M->fbody[k]]; fmob[me->u0 + M->fcoord[k]] += -M->fa[k]*u[me->u0 + M->fcoord[k]]; }
     }
 }

@@ -50,9 +50,20 @@ void compileTopology(const ModelSpec& spec, sbk_topology& t) {
     for (size_t i = 0; i < spec.forces.size(); ++i) {
         const sbk_force_desc& f = spec.forces[i];
         if (f.kind == SBK_FORCE_GRAVITY) {
-            if (++ngrav > 1) throw std::runtime_error("topology: more than one Force::Gravity element is not supported");
+            if (++ngrav > 1) throw std::runtime_error("topology: more than one gravity element is not supported");
             // Force_Gravity.cpp:532: gravity = g * d
             t.grav[0] = f.a*f.dir[0]; t.grav[1] = f.a*f.dir[1]; t.grav[2] = f.a*f.dir[2];
+        } else if (f.kind == SBK_FORCE_UNIFORM_GRAVITY) {
+            if (++ngrav > 1) throw std::runtime_error("topology: more than one gravity element is not supported");
+            // Force.cpp:1053: frc_G = m*g with the user's vector g
+            t.grav[0] = f.dir[0]; t.grav[1] = f.dir[1]; t.grav[2] = f.dir[2];
+        } else if (f.kind == SBK_FORCE_GLOBAL_DAMPER) {
+            // Force.cpp:997: mobilityForces -= damping*u, i.e. a linear damper on every mobility, at this force index
+            for (int b = 1; b < nb; ++b)
+                for (int j = 0; j < jointNU(spec.bodies[b].joint_type); ++j) {
+                    sbkd::ForceConst fc; fc.kind = SBK_FORCE_DAMPER; fc.coord = j; fc.a = f.a; fc.b = 0;
+                    perBody[b].push_back(fc);
+                }
         } else if (f.kind == SBK_FORCE_SPRING || f.kind == SBK_FORCE_DAMPER) {
             if (f.body < 1 || f.body >= nb) throw std::runtime_error("topology: force " + std::to_string(i) + " acts on invalid body");
             const int jt = spec.bodies[f.body].joint_type;

@@ -13,7 +13,8 @@
 //   Force::Gravity::getDefaultDownDirection / getDefaultMagnitude (Force_Gravity.h:276-278),
 //   Force::MobilityLinearSpring::getDefaultStiffness / getDefaultQZero
 //   (Force_MobilityLinearSpring.h:109,113), Force::MobilityLinearDamper::getDefaultDamping
-//   (Force_MobilityLinearDamper.h:87).
+//   (Force_MobilityLinearDamper.h:87), Force::UniformGravity::getGravity / getZeroHeight (Force.h:385-387);
+//   Force::GlobalDamper has no getter: its constant is probed through Force::calcForceContribution.
 // The spring/damper classes do not expose WHICH mobility they act on, so it is recovered by
 // probing Force::calcForceContribution (Force.h:130) at a state where every q-q0 (resp. u)
 // is non-zero: exactly one mobility force entry is non-zero.
@@ -127,9 +128,25 @@ inline ModelSpec lowerSimbodySystem(const SimTK::MultibodySystem&        system,
                 if (nhit != 1) throw std::runtime_error("lowerSimbodySystem: could not locate damper mobility");
                 int body, coord; slotToBodyCoord(hit, body, coord);
                 spec.forces.push_back(damperForce(body, coord, d.getDefaultDamping()));
+            } else if (Force::UniformGravity::isInstanceOf(f)) {
+                const Force::UniformGravity& g = Force::UniformGravity::downcast(f);
+                if (g.getZeroHeight() != 0)
+                    throw std::runtime_error("lowerSimbodySystem: UniformGravity with a non-zero zero-height is not supported");
+                const Vec3 gv = g.getGravity();
+                spec.forces.push_back(uniformGravityForce(gv[0], gv[1], gv[2]));
+            } else if (Force::GlobalDamper::isInstanceOf(f)) {
+                // no getter for the damping constant: probe it (f = -c*u at u = 1 on every mobility)
+                State probe = system.getDefaultState();
+                probe.updU() = 1;
+                system.realize(probe, Stage::Velocity);
+                Vector_<SpatialVec> bf; Vector_<Vec3> pf; Vector mf;
+                f.calcForceContribution(probe, bf, pf, mf);
+                if (mf.size() == 0) throw std::runtime_error("lowerSimbodySystem: GlobalDamper on a system without mobilities");
+                for (int i = 1; i < mf.size(); ++i) if (mf[i] != mf[0]) throw std::runtime_error("lowerSimbodySystem: unexpected GlobalDamper response");
+                spec.forces.push_back(globalDamperForce(-mf[0]));
             } else {
                 throw std::runtime_error("lowerSimbodySystem: force element " + std::to_string((int)fx) +
-                                         " is outside {Gravity, MobilityLinearSpring, MobilityLinearDamper}");
+                                         " is outside {Gravity, UniformGravity, MobilityLinearSpring, MobilityLinearDamper, GlobalDamper}");
             }
         }
     }

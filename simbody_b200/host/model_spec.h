@@ -6,8 +6,8 @@
 // public Simbody API and lowers it back with lower_simbody.h.  It carries exactly what the
 // reference's mobilized-body constructors take (Simbody/include/simbody/internal/
 // MobilizedBody_Pin.h etc.): parent, mobilizer kind, MassProperties, X_PF, X_BM; plus the
-// three in-scope force elements (Force_Gravity.h:70, Force_MobilityLinearSpring.h:66,
-// Force_MobilityLinearDamper.h:61).
+// in-scope force elements (Force_Gravity.h:70, Force_MobilityLinearSpring.h:66,
+// Force_MobilityLinearDamper.h:61, Force::UniformGravity and Force::GlobalDamper, Force.h:356-390).
 //
 // Header-only, no dependencies beyond the C++ standard library and include/sbk.h.
 #pragma once
@@ -103,6 +103,15 @@ inline sbk_force_desc springForce(int body, int coord, double k, double q0) {
 inline sbk_force_desc damperForce(int body, int coord, double c) {
     sbk_force_desc f; std::memset(&f, 0, sizeof f);
     f.kind = SBK_FORCE_DAMPER; f.body = body; f.coord = coord; f.a = c; return f;
+}
+
+inline sbk_force_desc uniformGravityForce(double gx, double gy, double gz) {
+    sbk_force_desc f; std::memset(&f, 0, sizeof f);
+    f.kind = SBK_FORCE_UNIFORM_GRAVITY; f.body = -1; f.a = 1; f.dir[0] = gx; f.dir[1] = gy; f.dir[2] = gz; return f;
+}
+inline sbk_force_desc globalDamperForce(double c) {
+    sbk_force_desc f; std::memset(&f, 0, sizeof f);
+    f.kind = SBK_FORCE_GLOBAL_DAMPER; f.body = -1; f.a = c; return f;
 }
 
 // ---- built-in models (BASELINE.json configs) -------------------------
@@ -243,10 +252,24 @@ inline ModelSpec makeBranchedTree(int n) {
     return m;
 }
 
+// A small mixed tree driven by Force::UniformGravity (a gravity vector that is not axis aligned) and
+// Force::GlobalDamper plus one spring: Ball -> Universal -> Pin -> Slider with a Pin branch off body 1.
+inline ModelSpec makeUgDamp5() {
+    ModelSpec m = makeMixed7(); m.name = "ugdamp5";
+    m.bodies.erase(m.bodies.begin() + 1);                                   // drop the Free root
+    for (size_t i = 1; i < m.bodies.size(); ++i) m.bodies[i].parent = (i == 5) ? 1 : (int)i - 1;
+    m.forces.clear();
+    m.forces.push_back(uniformGravityForce(0.3, -9.7, 0.4));
+    m.forces.push_back(springForce(3, 0, 12.0, -0.1));
+    m.forces.push_back(globalDamperForce(0.8));
+    return m;
+}
+
 inline ModelSpec makeNamedModel(const std::string& name, int n) {
     if (name == "double_pendulum") return makePinChain(2, "double_pendulum");
     if (name == "pin_chain")       return makePinChain(n > 0 ? n : 50);
     if (name == "mixed7")          return makeMixed7();
+    if (name == "ugdamp5")         return makeUgDamp5();
     if (name == "humanoid30")      return makeHumanoid30();
     if (name == "branched_tree")   return makeBranchedTree(n > 0 ? n : 1000);
     throw std::runtime_error("unknown model '" + name + "'");
@@ -269,6 +292,8 @@ inline std::string toText(const ModelSpec& m) {
         if (f.kind == SBK_FORCE_GRAVITY) { out += "gravity"; num(f.a); num(f.dir[0]); num(f.dir[1]); num(f.dir[2]); }
         else if (f.kind == SBK_FORCE_SPRING) { out += "spring " + std::to_string(f.body) + " " + std::to_string(f.coord); num(f.a); num(f.b); }
         else if (f.kind == SBK_FORCE_DAMPER) { out += "damper " + std::to_string(f.body) + " " + std::to_string(f.coord); num(f.a); }
+        else if (f.kind == SBK_FORCE_UNIFORM_GRAVITY) { out += "ugravity"; num(f.dir[0]); num(f.dir[1]); num(f.dir[2]); }
+        else if (f.kind == SBK_FORCE_GLOBAL_DAMPER) { out += "gdamper"; num(f.a); }
         else throw std::runtime_error("bad force kind");
         out += "\n";
     }
@@ -299,6 +324,8 @@ inline ModelSpec fromText(const std::string& text) {
         if (tok == "gravity") { f.kind = SBK_FORCE_GRAVITY; f.body = -1; in >> f.a >> f.dir[0] >> f.dir[1] >> f.dir[2]; }
         else if (tok == "spring") { f.kind = SBK_FORCE_SPRING; in >> f.body >> f.coord >> f.a >> f.b; }
         else if (tok == "damper") { f.kind = SBK_FORCE_DAMPER; in >> f.body >> f.coord >> f.a; }
+        else if (tok == "ugravity") { f.kind = SBK_FORCE_UNIFORM_GRAVITY; f.body = -1; f.a = 1; in >> f.dir[0] >> f.dir[1] >> f.dir[2]; }
+        else if (tok == "gdamper") { f.kind = SBK_FORCE_GLOBAL_DAMPER; f.body = -1; in >> f.a; }
         else throw std::runtime_error("bad force token " + tok);
         if (!in) throw std::runtime_error("truncated force line");
         m.forces.push_back(f);
