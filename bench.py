@@ -40,7 +40,7 @@ NCU_TRAFFIC_PER_INSTANCE_STEP = {"double_pendulum_1M": 4.921e7 / (1048576 * 20),
 # sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active of the same captures (the hardware's own
 # view of FP64-pipe utilisation; roofline.frac below uses the reference's ALGORITHMIC flop count instead)
 NCU_FP64_PIPE_ACTIVE = {"double_pendulum_1M": 0.753, "humanoid30_64k": 0.102, "pin_chain50_64k": 0.138}
-F_EVAL = {"PIN": 1180.0, "SLIDER": 1130.0, "UNIVERSAL": 1710.0, "BALL": 2060.0, "FREE": 3800.0}
+F_EVAL = {"PIN": 1180.0, "SLIDER": 1130.0, "UNIVERSAL": 1710.0, "BALL": 2060.0, "FREE": 3800.0, "WELD": 700.0}
 
 
 def algorithmic_work(info):

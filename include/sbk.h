@@ -57,7 +57,8 @@ enum {
     SBK_JOINT_SLIDER    = 2,  /* nq=1 nu=1, translation along x of F/M                   */
     SBK_JOINT_UNIVERSAL = 3,  /* nq=2 nu=2, body-fixed x then y                          */
     SBK_JOINT_BALL      = 4,  /* nq=4 nu=3, quaternion (scalar first)                    */
-    SBK_JOINT_FREE      = 5   /* nq=7 nu=6, quaternion + translation in F                */
+    SBK_JOINT_FREE      = 5,  /* nq=7 nu=6, quaternion + translation in F                */
+    SBK_JOINT_WELD      = 6   /* nq=0 nu=0, F and M coincide (RigidBodyNode_Weld.cpp:369)  */
 };
 
 /* ---- force elements (Simbody/src/Force_Gravity.cpp:514-577, Force.cpp:339-351,434-443) */

@@ -72,6 +72,7 @@ struct RefSystem {
               case SBK_JOINT_UNIVERSAL: { MobilizedBody::Universal m(parent, X_PF, body, X_BM); break; }
               case SBK_JOINT_BALL:      { MobilizedBody::Ball      m(parent, X_PF, body, X_BM); break; }
               case SBK_JOINT_FREE:      { MobilizedBody::Free      m(parent, X_PF, body, X_BM); break; }
+              case SBK_JOINT_WELD:      { MobilizedBody::Weld      m(parent, X_PF, body, X_BM); break; }
               default: throw std::runtime_error("ref_driver: bad joint type");
             }
         }

@@ -34,7 +34,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-enum { PIN = 1, SLIDER = 2, UNIVERSAL = 3, BALL = 4, FREE = 5 };
+enum { PIN = 1, SLIDER = 2, UNIVERSAL = 3, BALL = 4, FREE = 5, WELD = 6 };
 enum { F_GRAVITY = 1, F_SPRING = 2, F_DAMPER = 3, F_UNIFORM_GRAVITY = 4, F_GLOBAL_DAMPER = 5 };
 #define MAXD 6
 
@@ -82,6 +82,7 @@ static void mkTimes(const Body* B, const double* V, double* o) {
 /* General inverse by LU with partial pivoting (dgetrf + dgetri); n <= 6. Closed forms for n <= 3
  * as in SmallMatrixMixed.h:841-1006. */
 static int invertD(int n, const double* D, double* DI) {
+    if (n == 0) return 1;
     if (n == 1) { DI[0] = 1.0/D[0]; return D[0] != 0; }
     if (n == 2) { double det = D[0]*D[3] - D[1]*D[2], ood = 1.0/det; DI[0] = ood*D[3]; DI[1] = -ood*D[1]; DI[2] = -ood*D[2]; DI[3] = ood*D[0]; return det != 0; }
     if (n == 3) {
@@ -152,6 +153,7 @@ static void kinematics(const Model* M, Body* B, const double* q, const double* u
             double c1 = cos(qb[0]), s1 = sin(qb[0]), c2 = cos(qb[1]), s2 = sin(qb[1]);
             Rfm[0] = c2; Rfm[1] = 0; Rfm[2] = s2; Rfm[3] = s2*s1; Rfm[4] = c1; Rfm[5] = -s1*c2; Rfm[6] = -s2*c1; Rfm[7] = s1; Rfm[8] = c1*c2;
             Hw[0][0] = 1; Hw[1][0] = Rfm[1]; Hw[1][1] = Rfm[4]; Hw[1][2] = Rfm[7];
+        } else if (jt == WELD) {      /* X_FM = I, no mobilities (RigidBodyNode_Weld.cpp:369-420) */
         } else {                      /* Ball / Free, quaternion (Rotation.cpp:600-611) */
             double n = sqrt(qb[0]*qb[0] + qb[1]*qb[1] + qb[2]*qb[2] + qb[3]*qb[3]);
             if (qerr) qerr[iq] = n - 1.0; ++iq;

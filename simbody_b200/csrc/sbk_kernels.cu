@@ -264,10 +264,12 @@ cudaError_t launchOp(const KArgs& a, cudaStream_t stream) {
     };
     if constexpr (OP == OP_RKM || OP == OP_RKM_ADAPT) {
         // integrator kernels: instantiated per set of mobilizer kinds present in the model
-        constexpr int LIGHT = JM_PIN | JM_SLIDER | JM_UNIVERSAL;
+        constexpr int LIGHT = JM_PIN | JM_SLIDER | JM_UNIVERSAL | JM_WELD;
         const int m = a.jointMask;
         if ((m & ~JM_PIN) == 0) return a.stageInSmem ? go(tpiKernel<OP, true, SBK_TPI_MINBLOCKS, JM_PIN>) : go(tpiKernel<OP, false, SBK_TPI_MINBLOCKS, JM_PIN>);
         if ((m & ~LIGHT) == 0)  return a.stageInSmem ? go(tpiKernel<OP, true, SBK_TPI_MINBLOCKS, LIGHT>)  : go(tpiKernel<OP, false, SBK_TPI_MINBLOCKS, LIGHT>);
+        constexpr int MOBILE = JM_ALL & ~JM_WELD;     // the five mobilizers with coordinates, no Weld code
+        if ((m & ~MOBILE) == 0) return a.stageInSmem ? go(tpiKernel<OP, true, SBK_HEAVY_MINB, MOBILE>) : go(tpiKernel<OP, false, SBK_HEAVY_MINB, MOBILE>);
     }
     return a.stageInSmem ? go(tpiKernel<OP, true, SBK_HEAVY_MINB>) : go(tpiKernel<OP, false, SBK_HEAVY_MINB>);
 }
@@ -328,7 +330,7 @@ __device__ double lpErrorNorm(const Ctx& c, const int inst, const KArgs& a, doub
             for (int i = 0; i < 4; ++i) { if (inf) qAcc = fmax(qAcc, fabs(o[i])); else qAcc += o[i]*o[i]; }
             first = 4;
         }
-        const int nqb = bc.joint == JT_FREE ? 7 : bc.joint == JT_BALL ? 4 : bc.joint == JT_UNIVERSAL ? 2 : 1;
+        const int nqb = nqOfJoint(bc.joint);
         for (int i = first; i < nqb; ++i) { const double v = ldS<false>(c, inst, a.ys, bc.q0 + i); if (inf) qAcc = fmax(qAcc, fabs(v)); else qAcc += v*v; }
     }
     uAcc = blockReduce(uAcc, inf, red); qAcc = blockReduce(qAcc, inf, red);

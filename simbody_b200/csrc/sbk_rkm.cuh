@@ -51,7 +51,7 @@ SBK_HD double rkmErrorNorm(const Ctx& c, const Tables& T, const int inst, const 
             for (int i = 0; i < 4; ++i) { if (w.useInfNorm) qAcc = fmax(qAcc, fabs(o[i])); else qAcc += o[i]*o[i]; }
             first = 4;
         }
-        const int nqb = bc.joint == JT_FREE ? 7 : bc.joint == JT_BALL ? 4 : bc.joint == JT_UNIVERSAL ? 2 : 1;
+        const int nqb = nqOfJoint(bc.joint);
         for (int i = first; i < nqb; ++i) {
             const double v = ldS<BLK>(c, inst, w.ys, bc.q0 + i);
             if (w.useInfNorm) qAcc = fmax(qAcc, fabs(v)); else qAcc += v*v;

@@ -42,7 +42,7 @@
 
 namespace sbkd {
 
-enum { JT_GROUND = 0, JT_PIN = 1, JT_SLIDER = 2, JT_UNIVERSAL = 3, JT_BALL = 4, JT_FREE = 5 };
+enum { JT_GROUND = 0, JT_PIN = 1, JT_SLIDER = 2, JT_UNIVERSAL = 3, JT_BALL = 4, JT_FREE = 5, JT_WELD = 6 };
 enum { FK_SPRING = 2, FK_DAMPER = 3 };
 
 template <int JT> struct JointDims;
@@ -51,6 +51,9 @@ template <> struct JointDims<JT_SLIDER>    { enum { nq = 1, nu = 1 }; };
 template <> struct JointDims<JT_UNIVERSAL> { enum { nq = 2, nu = 2 }; };
 template <> struct JointDims<JT_BALL>      { enum { nq = 4, nu = 3 }; };
 template <> struct JointDims<JT_FREE>      { enum { nq = 7, nu = 6 }; };
+template <> struct JointDims<JT_WELD>      { enum { nq = 0, nu = 0 }; };   // RigidBodyNode_Weld.cpp:369: no q, no u
+// array extent for a dof count that may be zero
+SBK_HD constexpr int dim1(int d) { return d > 0 ? d : 1; }
 
 // cache record layout
 enum { F_XGB = 0, F_VGB = 12, F_L = 18, F_MK = 21, F_ACOR = 30, F_GYRO = 36, F_ZB = 42,
@@ -234,7 +237,8 @@ template <bool BLK> SBK_HD long long stateIndex(const Ctx& c, int inst, int slot
 template <bool BLK> SBK_HD double ldS(const Ctx& c, int inst, const double* a, int slot) { return gld(a + stateIndex<BLK>(c, inst, slot)); }
 template <bool BLK> SBK_HD void   stS(const Ctx& c, int inst, double* a, int slot, double v) { gst(a + stateIndex<BLK>(c, inst, slot), v); }
 
-SBK_HD int dofOfJoint(int jt) { return jt == JT_FREE ? 6 : jt == JT_BALL ? 3 : jt == JT_UNIVERSAL ? 2 : jt == JT_GROUND ? 0 : 1; }
+SBK_HD int dofOfJoint(int jt) { return jt == JT_FREE ? 6 : jt == JT_BALL ? 3 : jt == JT_UNIVERSAL ? 2 : (jt == JT_GROUND || jt == JT_WELD) ? 0 : 1; }
+SBK_HD int nqOfJoint(int jt)  { return jt == JT_FREE ? 7 : jt == JT_BALL ? 4 : jt == JT_UNIVERSAL ? 2 : (jt == JT_GROUND || jt == JT_WELD) ? 0 : 1; }
 SBK_HD M3 loadR(const double* X) { M3 R;
 #pragma unroll
     for (int i = 0; i < 9; ++i) R.a[i] = X[i]; return R; }
@@ -263,7 +267,7 @@ SBK_HD V3 quatNInvTimes(const double* q, const double* qd) {
 //==============================================================================================
 template <int d> struct KinOut {     // results of sweeps A+B for one body
     M3 R; V3 p; SV V;                // X_GB, V_GB
-    SV H[d]; V3 l; V3 c; S3 G;       // H_PB_G columns, Phi.l, com in G, unit inertia in G
+    SV H[dim1(d)]; V3 l; V3 c; S3 G; // H_PB_G columns, Phi.l, com in G, unit inertia in G
     SV acor, gyro;                   // mobilizer coriolis acceleration a, gyroscopic force b
 };
 
@@ -285,7 +289,7 @@ template <int A> SBK_HD V3 mulSkip(const M3& R, V3 t) {   // R * t for a t whose
 // Position kinematics that depend on the mobilizer coordinates only (no parent quantities):
 // X_FM, H_FM, and X_PB = X_PF * X_FM * X_MB (RigidBodyNodeSpec.h:554-569).
 template <int d> struct KinLocal {
-    M3 R_FM; V3 Hw[d], Hv[d];        // H_FM columns (angular, linear), expressed in F
+    M3 R_FM; V3 Hw[dim1(d)], Hv[dim1(d)];   // H_FM columns (angular, linear), expressed in F
     V3 r;                            // r_MB_F = R_FM * p_MB
     M3 R_PB; V3 p_PB;                // X_PB
     double qerr;                     // |q| - 1 for quaternion mobilizers
@@ -306,6 +310,8 @@ SBK_HD void kinLocal(const BodyConst& bc, const double* q, KinLocal<JointDims<JT
         R_FM.a[3] = s;  R_FM.a[4] = co; R_FM.a[5] = 0;
         R_FM.a[6] = 0;  R_FM.a[7] = 0;  R_FM.a[8] = 1;
         k.Hw[0] = mk(0, 0, 1);
+    } else if constexpr (JT == JT_WELD) {         // RigidBodyNode_Weld.cpp:390-398: X_FM = I
+        R_FM = identity3();
     } else if constexpr (JT == JT_SLIDER) {       // RigidBodyNodeSpec_Slider.h:91-127
         R_FM = identity3(); p_FM = mk(q[0], 0, 0);
         k.Hv[0] = mk(1, 0, 0);
@@ -347,7 +353,7 @@ SBK_HD void kinLocal(const BodyConst& bc, const double* q, KinLocal<JointDims<JT
                 R_FB.a[6 + j] = R_MB.a[6+j];
             }
         }
-    } else if constexpr (JT == JT_SLIDER) {            // R_FM = I
+    } else if constexpr (JT == JT_SLIDER || JT == JT_WELD) {   // R_FM = I
         k.r = p_MB; R_FB = R_MB;
     } else {
         k.r = mul(R_FM, p_MB);                         // r_MB_F = R_FM * p_MB
@@ -364,7 +370,8 @@ SBK_HD void jointH(const M3& R_GF, const KinLocal<JointDims<JT>::nu>& k, SV* H) 
     const V3 r = k.r;
     #define SBK_ROTCOL(j, A) { H[j].w = col(R_GF, A); H[j].v = mulSkip<A>(R_GF, axisCross<A>(r)); }
     #define SBK_TRCOL(j, A)  { H[j].w = zero3(); H[j].v = col(R_GF, A); }
-    if constexpr (JT == JT_PIN) SBK_ROTCOL(0, 2)
+    if constexpr (JT == JT_WELD) { (void)r; (void)H; }
+    else if constexpr (JT == JT_PIN) SBK_ROTCOL(0, 2)
     else if constexpr (JT == JT_SLIDER) SBK_TRCOL(0, 0)
     else if constexpr (JT == JT_UNIVERSAL) {
         SBK_ROTCOL(0, 0)
@@ -379,7 +386,7 @@ SBK_HD void jointH(const M3& R_GF, const KinLocal<JointDims<JT>::nu>& k, SV* H) 
 // w_FM = H_FM(angular) u
 template <int JT> SBK_HD V3 jointWFM(const KinLocal<JointDims<JT>::nu>& k, const double* u) {
     if constexpr (JT == JT_PIN) return mk(0, 0, u[0]);
-    else if constexpr (JT == JT_SLIDER) return zero3();
+    else if constexpr (JT == JT_SLIDER || JT == JT_WELD) return zero3();
     else if constexpr (JT == JT_UNIVERSAL) return mk(u[0], 0, 0) + u[1]*k.Hw[1];
     else return mk(u[0], u[1], u[2]);
 }
@@ -408,7 +415,8 @@ SBK_HD void kinGlobal(const BodyConst& bc, const KinLocal<JointDims<JT>::nu>& k,
 
     // ---- velocity (RigidBodyNodeSpec.h:305-333) ------------------------------------------------
     const V3 w_FM = jointWFM<JT>(k, u);
-    SV V_PB = u[0]*o.H[0];
+    SV V_PB = zeroSV();
+    if constexpr (d > 0) V_PB = u[0]*o.H[0];
 #pragma unroll
     for (int j = 1; j < d; ++j) V_PB = V_PB + u[j]*o.H[j];
 
@@ -420,7 +428,8 @@ SBK_HD void kinGlobal(const BodyConst& bc, const KinLocal<JointDims<JT>::nu>& k,
     #define SBK_ROTCOL_D(j, A) { SV HD; HD.w = cross(w_GP, o.H[j].w); \
                                  HD.v = mulSkip<A>(R_GF, axisCross<A>(wxr)) + cross(w_GP, o.H[j].v); VD = VD + u[j]*HD; }
     #define SBK_TRCOL_D(j)     { SV HD; HD.w = zero3(); HD.v = cross(w_GP, o.H[j].v); VD = VD + u[j]*HD; }
-    if constexpr (JT == JT_PIN) SBK_ROTCOL_D(0, 2)
+    if constexpr (JT == JT_WELD) { (void)wxr; }
+    else if constexpr (JT == JT_PIN) SBK_ROTCOL_D(0, 2)
     else if constexpr (JT == JT_SLIDER) SBK_TRCOL_D(0)
     else if constexpr (JT == JT_UNIVERSAL) {
         SBK_ROTCOL_D(0, 0)
@@ -482,24 +491,28 @@ SBK_HD void kinReverse(const BodyConst& bc, const KinLocal<JointDims<JT>::nu>& k
     p_GP = p_GB - l;
     const bool noRPF = (bc.flags & BF_NO_R_PF) != 0;
     const M3 R_GF = noRPF ? R_GP : mul(R_GP, loadR(bc.X_PF));
-    SV H[d];
+    SV H[dim1(d)];
     jointH<JT>(R_GF, k, H);
-    SV V_PB = u[0]*H[0];
+    SV V_PB = zeroSV();
+    if constexpr (d > 0) V_PB = u[0]*H[0];
 #pragma unroll
     for (int j = 1; j < d; ++j) V_PB = V_PB + u[j]*H[j];
     V_GP.w = V_GB.w - V_PB.w;
     V_GP.v = (V_GB.v - V_PB.v) - cross(V_GP.w, l);
 }
 
-template <int d> struct AbiOut { SV G[d]; double DI[d*d]; ABI PP; SV zb; bool ok; };
+template <int d> struct AbiOut { SV G[dim1(d)]; double DI[dim1(d*d)]; ABI PP; SV zb; bool ok; };
 
 // Sweep C for one body, given P = Mk + sum of shifted children P+ (RigidBodyNodeSpec.cpp:249-325).
 template <int d>
 SBK_HD void abiCore(const ABI& P, const SV* H, const SV acor, const SV gyro, AbiOut<d>& o) {
-    SV PH[d];
+    if constexpr (d == 0) {        // Weld: P+ = P (RigidBodyNode_Weld.cpp:437-450)
+        o.PP = P; o.ok = true; o.zb = mul(P, acor) + gyro; return;
+    } else {
+    SV PH[dim1(d)];
 #pragma unroll
     for (int j = 0; j < d; ++j) PH[j] = mul(P, H[j]);
-    double D[d*d];
+    double D[dim1(d*d)];
 #pragma unroll
     for (int i = 0; i < d; ++i)
 #pragma unroll
@@ -537,6 +550,7 @@ SBK_HD void abiCore(const ABI& P, const SV* H, const SV acor, const SV gyro, Abi
     for (int i = 0; i < 9; ++i) o.PP.F.a[i] = P.F.a[i] - mm[i];
     // realizeArticulatedBodyVelocityCache (RigidBodyNode.cpp:201-213): P*a + b
     o.zb = mul(P, acor) + gyro;
+    }
 }
 
 // Sweep D for one body: z already holds (P a + b - F) + sum Phi*z+ of the children.
@@ -618,7 +632,7 @@ template <int JT>
 SBK_BODY void kinBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, const int inst, double* qdotDst) {
     constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
     const CacheRef me = cacheOf<false>(c, inst, bc.cacheBase);
-    double q[NQ], u[d], qdot[NQ], qerr;
+    double q[dim1(NQ)], u[dim1(d)], qdot[dim1(NQ)], qerr;
 #pragma unroll
     for (int i = 0; i < NQ; ++i) q[i] = ldS<false>(c, inst, c.q, bc.q0 + i);
 #pragma unroll
@@ -663,7 +677,7 @@ template <int JT, int MODE>
 SBK_BODY void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, const int inst) {
     constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
     const CacheRef me = cacheOf<false>(c, inst, bc.cacheBase);
-    SV H[d];
+    SV H[dim1(d)];
 #pragma unroll
     for (int j = 0; j < d; ++j) H[j] = me.ldSV(F_H + 6*j);
     const V3 c_G = me.ld3(F_MK);
@@ -692,9 +706,9 @@ SBK_BODY void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex,
 
     if constexpr ((MODE & IN_Z) != 0) {
         // ---- applied forces -------------------------------------------------------------------
-        SV F = zeroSV(); double f[d];
+        SV F = zeroSV(); double f[dim1(d)];
         if constexpr ((MODE & IN_FORCES) != 0) {
-            double qF[NQ], uF[d];
+            double qF[dim1(NQ)], uF[dim1(d)];
             if (bc.nforce > 0) {
 #pragma unroll
                 for (int i = 0; i < NQ; ++i) qF[i] = ldS<false>(c, inst, c.q, bc.q0 + i);
@@ -726,7 +740,7 @@ SBK_BODY void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex,
             const CacheRef ch = cacheOf<false>(c, inst, c.bodies[c.children[bc.childStart + k]].cacheBase);
             z = z + phi(ch.ld3(F_L), ch.ldSV(F_ZPLUS));
         }
-        double eps[d]; SV zPlus;
+        double eps[dim1(d)]; SV zPlus;
         zCore<d>(H, ao.G, z, f, eps, zPlus);
 #pragma unroll
         for (int j = 0; j < d; ++j) me.st(fEPS(d) + j, eps[j]);
@@ -741,7 +755,7 @@ SBK_BODY void outwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex
     constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
     const CacheRef me = cacheOf<false>(c, inst, bc.cacheBase);
     const SV A_GP = cacheOf<false>(c, inst, bc.parentCacheBase).ldSV(F_AGB);
-    SV H[d], G[d]; double DI[d*d], eps[d], udot[d];
+    SV H[dim1(d)], G[dim1(d)]; double DI[dim1(d*d)], eps[dim1(d)], udot[dim1(d)];
 #pragma unroll
     for (int j = 0; j < d; ++j) { H[j] = me.ldSV(F_H + 6*j); G[j] = me.ldSV(fG(d) + 6*j); eps[j] = me.ld(fEPS(d) + j); }
 #pragma unroll
@@ -757,7 +771,7 @@ SBK_BODY void outwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex
         for (int i = 0; i < d; ++i) stS<false>(c, inst, udotDst, bc.u0 + i, udot[i]);
     }
     if (qdotdotDst) {
-        double q[NQ], u[d], qdd[NQ];
+        double q[dim1(NQ)], u[dim1(d)], qdd[dim1(NQ)];
         if constexpr (JT == JT_BALL || JT == JT_FREE) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) q[i] = ldS<false>(c, inst, c.q, bc.q0 + i);
@@ -796,9 +810,13 @@ SBK_HD constexpr int lfNU(int d) { return LF_G + 6*d; }
 // u cover Pin / Slider / Universal; Ball / Free bodies load their own.
 SBK_HD void preloadCoords(const Ctx& c, const int inst, const BodyConst& nx, double* slot) {
     constexpr bool BLK = SBK_DEV_BLK;
-    const int u1 = nx.u0 + 1 < c.nu ? nx.u0 + 1 : nx.u0;       // stay inside the u rows
-    const double* src[4] = { c.q + stateIndex<BLK>(c, inst, nx.q0), c.q + stateIndex<BLK>(c, inst, nx.q0 + 1),   // q0 + 1 <= nq: a valid row of [q; u]
-                             c.u + stateIndex<BLK>(c, inst, nx.u0), c.u + stateIndex<BLK>(c, inst, u1) };
+    // rows of [q; u] (the u rows follow the q rows), clamped: a Weld owns no slots and the slot after the
+    // last one does not exist
+    const int last = c.nq + c.nu - 1;
+    const int r0 = nx.q0 < last ? nx.q0 : last, r1 = nx.q0 + 1 < last ? nx.q0 + 1 : last;
+    const int r2 = c.nq + nx.u0 < last ? c.nq + nx.u0 : last, r3 = c.nq + nx.u0 + 1 < last ? c.nq + nx.u0 + 1 : last;
+    const double* src[4] = { c.q + stateIndex<BLK>(c, inst, r0), c.q + stateIndex<BLK>(c, inst, r1),
+                             c.q + stateIndex<BLK>(c, inst, r2), c.q + stateIndex<BLK>(c, inst, r3) };
 #if defined(__CUDA_ARCH__)
 #pragma unroll
     for (int k = 0; k < 4; ++k)
@@ -849,7 +867,7 @@ template <int JT>
 SBK_BODY void leanKinBody(const Ctx& c, const BodyConst& bc, const int inst, double* cy, const double* pre, double* qdotDst) {
     constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
     constexpr bool BLK = SBK_DEV_BLK;
-    double q[NQ], u[d], qdot[NQ], qerr;
+    double q[dim1(NQ)], u[dim1(d)], qdot[dim1(NQ)], qerr;
     takeCoords<JT, BLK>(c, inst, bc, pre, q, u);
     M3 R_GP; V3 p_GP; SV V_GP;
     if (bc.flags & BF_PARENT_PREV) cyLoadOut(cy, R_GP, p_GP, V_GP);
@@ -872,7 +890,7 @@ SBK_BODY void leanInwardBody(const Ctx& c, const Tables& T, const BodyConst& bc,
     constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
     constexpr bool BLK = SBK_DEV_BLK;
     const CacheRefT<BLK> me = cacheOf<BLK>(c, inst, bc.cacheBase);
-    double q[NQ], u[d], qdot[NQ];
+    double q[dim1(NQ)], u[dim1(d)], qdot[dim1(NQ)];
     takeCoords<JT, BLK>(c, inst, bc, pre, q, u);
     const bool haveCarryChild = !(bc.flags & BF_TIP);      // body index + 1 is a child and left its links in the carry
     M3 R_GB; V3 p_GB; SV V_GB;
@@ -899,7 +917,7 @@ SBK_BODY void leanInwardBody(const Ctx& c, const Tables& T, const BodyConst& bc,
     if (!ao.ok) setSingular(c, inst);
 
     // ---- forces and residual (RigidBodyNodeSpec.cpp:355-400) -------------------------------------
-    double f[d];
+    double f[dim1(d)];
     const SV F = gravityForce(bc.mass, o.c, c.gx, c.gy, c.gz);
     mobilityForces<d>(bc, T.forces, q, u, f);
     SV z = ao.zb - F;
@@ -908,7 +926,7 @@ SBK_BODY void leanInwardBody(const Ctx& c, const Tables& T, const BodyConst& bc,
         const CacheRefT<BLK> ch = cacheOf<BLK>(c, inst, T.bodies[T.children[bc.childStart + k]].cacheBase);
         z = z + phi(ch.ld3(LF_L), ch.ldSV(LF_ZPLUS));
     }
-    double eps[d]; SV zPlus;
+    double eps[dim1(d)]; SV zPlus;
     zCore<d>(o.H, ao.G, z, f, eps, zPlus);
 #pragma unroll
     for (int j = 0; j < d; ++j) me.stSV(LF_G + 6*j, ao.G[j]);
@@ -932,8 +950,8 @@ SBK_BODY void leanOutwardBody(const Ctx& c, const BodyConst& bc, const int inst,
     constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
     constexpr bool BLK = SBK_DEV_BLK;
     const CacheRefT<BLK> me = cacheOf<BLK>(c, inst, bc.cacheBase);
-    double q[NQ], u[d], qdot[NQ], qerr, nu[d], udot[d];
-    SV G[d];
+    double q[dim1(NQ)], u[dim1(d)], qdot[dim1(NQ)], qerr, nu[dim1(d)], udot[dim1(d)];
+    SV G[dim1(d)];
     if (d <= 2 && gnu) {                                  // preloaded into the carry column (preloadGNu)
 #pragma unroll
         for (int j = 0; j < d; ++j) {
@@ -970,7 +988,7 @@ SBK_BODY void leanOutwardBody(const Ctx& c, const BodyConst& bc, const int inst,
         for (int i = 0; i < d; ++i) stS<BLK>(c, inst, udotDst, bc.u0 + i, udot[i]);
     }
     if (qdotdotDst) {
-        double qdd[NQ];
+        double qdd[dim1(NQ)];
         qddCore<JT>(q, u, udot, qdd);
 #pragma unroll
         for (int i = 0; i < NQ; ++i) stS<BLK>(c, inst, qdotdotDst, bc.q0 + i, qdd[i]);
@@ -1038,6 +1056,7 @@ SBK_BODY void idInBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, c
         case JT_UNIVERSAL: { constexpr int JT = JT_UNIVERSAL; CALL; } break;        \
         case JT_BALL:      { constexpr int JT = JT_BALL;      CALL; } break;        \
         case JT_FREE:      { constexpr int JT = JT_FREE;      CALL; } break;        \
+        case JT_WELD:      { constexpr int JT = JT_WELD;      CALL; } break;        \
         default: break;                                                             \
     }
 
@@ -1057,7 +1076,7 @@ template <bool WITH_COR> SBK_HD void outwardDispatch(const Ctx& c, int b, int in
 // integrator kernels are instantiated for a few masks so that a model made of Pin joints only does
 // not carry (and register-allocate for) the Ball / Free code.
 enum { JM_PIN = 1 << JT_PIN, JM_SLIDER = 1 << JT_SLIDER, JM_UNIVERSAL = 1 << JT_UNIVERSAL, JM_BALL = 1 << JT_BALL, JM_FREE = 1 << JT_FREE,
-       JM_ALL = JM_PIN | JM_SLIDER | JM_UNIVERSAL | JM_BALL | JM_FREE };
+       JM_WELD = 1 << JT_WELD, JM_ALL = JM_PIN | JM_SLIDER | JM_UNIVERSAL | JM_BALL | JM_FREE | JM_WELD };
 #define SBK_DISPATCH_JOINT_M(JMASK, jt, CALL)                                                                       \
     switch (jt) {                                                                                                   \
         case JT_PIN:       if constexpr (((JMASK) & JM_PIN) != 0)       { constexpr int JT = JT_PIN;       CALL; } break; \
@@ -1065,6 +1084,7 @@ enum { JM_PIN = 1 << JT_PIN, JM_SLIDER = 1 << JT_SLIDER, JM_UNIVERSAL = 1 << JT_
         case JT_UNIVERSAL: if constexpr (((JMASK) & JM_UNIVERSAL) != 0) { constexpr int JT = JT_UNIVERSAL; CALL; } break; \
         case JT_BALL:      if constexpr (((JMASK) & JM_BALL) != 0)      { constexpr int JT = JT_BALL;      CALL; } break; \
         case JT_FREE:      if constexpr (((JMASK) & JM_FREE) != 0)      { constexpr int JT = JT_FREE;      CALL; } break; \
+        case JT_WELD:      if constexpr (((JMASK) & JM_WELD) != 0)      { constexpr int JT = JT_WELD;      CALL; } break; \
         default: break;                                                                                             \
     }
 

@@ -65,8 +65,9 @@ inline ModelSpec lowerSimbodySystem(const SimTK::MultibodySystem&        system,
         else if (MobilizedBody::Universal::isInstanceOf(mobod)) b.joint_type = SBK_JOINT_UNIVERSAL;
         else if (MobilizedBody::Ball::isInstanceOf(mobod))      b.joint_type = SBK_JOINT_BALL;
         else if (MobilizedBody::Free::isInstanceOf(mobod))      b.joint_type = SBK_JOINT_FREE;
+        else if (MobilizedBody::Weld::isInstanceOf(mobod))      b.joint_type = SBK_JOINT_WELD;
         else throw std::runtime_error("lowerSimbodySystem: body " + std::to_string((int)mbx) +
-                                      " uses a mobilizer outside {Pin,Slider,Universal,Ball,Free}");
+                                      " uses a mobilizer outside {Pin,Slider,Universal,Ball,Free,Weld}");
         // NOTE: the public API has no getter for MobilizedBody::Direction; reversed mobilizers
         // are out of scope and must not be used with this lowering.
         const MassProperties& mp = mobod.getDefaultMassProperties();

@@ -41,12 +41,13 @@ inline int jointNU(int jt) {
 inline const char* jointName(int jt) {
     switch (jt) { case SBK_JOINT_GROUND: return "GROUND"; case SBK_JOINT_PIN: return "PIN";
                   case SBK_JOINT_SLIDER: return "SLIDER"; case SBK_JOINT_UNIVERSAL: return "UNIVERSAL";
-                  case SBK_JOINT_BALL: return "BALL"; case SBK_JOINT_FREE: return "FREE"; default: return "?"; }
+                  case SBK_JOINT_BALL: return "BALL"; case SBK_JOINT_FREE: return "FREE"; case SBK_JOINT_WELD: return "WELD"; default: return "?"; }
 }
 inline int jointFromName(const std::string& s) {
     if (s == "GROUND") return SBK_JOINT_GROUND; if (s == "PIN") return SBK_JOINT_PIN;
     if (s == "SLIDER") return SBK_JOINT_SLIDER; if (s == "UNIVERSAL") return SBK_JOINT_UNIVERSAL;
     if (s == "BALL") return SBK_JOINT_BALL; if (s == "FREE") return SBK_JOINT_FREE;
+    if (s == "WELD") return SBK_JOINT_WELD;
     throw std::runtime_error("unknown joint name " + s);
 }
 
@@ -265,11 +266,26 @@ inline ModelSpec makeUgDamp5() {
     return m;
 }
 
+// mixed7 with two Weld mobilizers: one in the middle of the chain (bodies keep moving outboard of
+// it) and one as a leaf carrying extra mass.
+inline ModelSpec makeWelded8() {
+    ModelSpec m = makeMixed7(); m.name = "welded8";
+    m.bodies[3].joint_type = SBK_JOINT_WELD;                 // was Universal: Free -> Ball -> WELD -> Pin -> Slider
+    sbk_body_desc leaf = m.bodies[6]; leaf.parent = 4; leaf.joint_type = SBK_JOINT_WELD; leaf.mass = 0.7;
+    m.bodies.push_back(leaf);
+    m.forces.clear();
+    m.forces.push_back(gravityForce(9.81, 0, -1, 0));
+    m.forces.push_back(springForce(4, 0, 30.0, 0.2));
+    m.forces.push_back(damperForce(5, 0, 1.5));
+    return m;
+}
+
 inline ModelSpec makeNamedModel(const std::string& name, int n) {
     if (name == "double_pendulum") return makePinChain(2, "double_pendulum");
     if (name == "pin_chain")       return makePinChain(n > 0 ? n : 50);
     if (name == "mixed7")          return makeMixed7();
     if (name == "ugdamp5")         return makeUgDamp5();
+    if (name == "welded8")         return makeWelded8();
     if (name == "humanoid30")      return makeHumanoid30();
     if (name == "branched_tree")   return makeBranchedTree(n > 0 ? n : 1000);
     throw std::runtime_error("unknown model '" + name + "'");

@@ -21,6 +21,7 @@ CASES = [  # name, size param, n eval states, (h, nsteps), q_scale
     ("pin_chain", 50, 4, (1e-3, 5), 1.0),
     ("mixed7", 0, 8, (1e-3, 25), 1.0),
     ("ugdamp5", 0, 6, (1e-3, 20), 0.7),          # Force::UniformGravity + Force::GlobalDamper
+    ("welded8", 0, 6, (1e-3, 20), 0.7),          # MobilizedBody::Weld inside the chain and as a leaf
     ("humanoid30", 0, 4, (1e-3, 10), 0.5),
     ("branched_tree", 100, 2, (5e-4, 4), 0.5),
 ]
