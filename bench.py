@@ -263,7 +263,7 @@ def main():
                 "hbm_algorithmic_GBs": per_gpu_rate * r["bytes_per_inst_step"] / 1e9,
                 "hbm_peak_GBs": peaks.get("hbm_gbs"),
                 "kernel": {1: "tpiKernel<OP_RKM> (thread-per-instance, reversible kinematics, persistent task queue)", 2: "fusedRkmKernel (register-resident)",
-                           3: "lpKernel<OP_RKM> (level-parallel)"}[r["plan"]],
+                           3: "lpKernel<OP_RKM> (level-parallel)", 4: "glRkmKernel (grid-level-parallel, persistent cooperative grid)"}[r["plan"]],
                 "kernel_ms_last_launch": r["kernel_ms_last"],
                 "fp64_pipe_active_ncu": NCU_FP64_PIPE_ACTIVE.get(args.workload),
                 "hbm_traffic_frac_ncu": (NCU_TRAFFIC_PER_INSTANCE_STEP.get(args.workload, 0) * per_gpu_rate / 1e9 / peaks["hbm_gbs"])

@@ -152,7 +152,9 @@ sbk_batch* sbk_batch_create(const sbk_topology*, int n_instances, int device, vo
 void sbk_batch_destroy(sbk_batch*);
 int  sbk_batch_size(const sbk_batch*);
 /* Execution plan: 0 = auto, 1 = generic thread-per-instance, 2 = register-resident fused
- * (small models), 3 = level-parallel CTA-per-instance (wide trees).                     */
+ * (small models), 3 = level-parallel CTA-per-instance (wide trees), 4 = grid-level-parallel
+ * integrator (wide trees, small batches: the whole GPU works on one tree level of the batch;
+ * other operations run as in plan 1).                                                    */
 int  sbk_batch_set_plan(sbk_batch*, int plan);
 int  sbk_batch_get_plan(const sbk_batch*);
 int  sbk_synchronize(sbk_batch*);
@@ -245,7 +247,7 @@ int sbk_rkm_step(sbk_batch*, double h, int nsteps, const sbk_rkm_opts* opts, dou
  * each with its own step size history (AbstractIntegratorRep.cpp:216-368 stepping loop,
  * :448-502 adjustStepSize, :513-578 takeOneStep).  Per-instance outputs (host, [N], nullable):
  * internal steps taken and attempted since the state was last set, and the last accepted step
- * size.  sbk_get_state's t returns each instance's advanced time.  Not available in plan 3.   */
+ * size.  sbk_get_state's t returns each instance's advanced time.  Not available in plans 3 and 4. */
 void sbk_adaptive_default_opts(sbk_adaptive_opts*);
 int sbk_rkm_adaptive(sbk_batch*, double t_final, const sbk_adaptive_opts* opts,
                      int32_t* steps_taken, int32_t* steps_attempted, double* last_step);

@@ -152,11 +152,11 @@ static bool fusedOk(const sbk_batch* b) {
 static int autoPlan(const sbk_batch* b) {
     if (fusedOk(b)) return 2;
     // wide tree + batch too small to fill 148 SMs with one thread per instance
-    if (b->N < 16384 && b->topo->nb >= 128 && b->topo->maxLevelWidth >= 32) return 3;
+    if (b->N < 16384 && b->topo->nb >= 128 && b->topo->maxLevelWidth >= 32) return 4;
     return 1;
 }
 // (Re)build the batch-shared tables and the per-body cache for an execution plan.
-//   plans 1/2: record (body b, field k, instance i) at cache[(base_b + k)*N + i]
+//   plans 1/2/4: CTA-blocked records, see below (plan 4 differs from 1 only in its fixed-step integrator kernel)
 //   plan 3   : cache[i*(KMAX*nb) + k*nb + pos_b], pos_b = position in (level, joint) order, so
 //              that the threads of a CTA (bodies of one level) touch adjacent addresses.
 static int configurePlan(sbk_batch* b, int plan) {
@@ -288,7 +288,7 @@ int sbk_batch_set_plan(sbk_batch* b, int plan) {
     if (!b) return fail(SBK_ERR_ARG, "null batch");
     if (int rc = useDevice(b)) return rc;
     if (plan == 0) plan = autoPlan(b);
-    if (plan < 1 || plan > 3) return fail(SBK_ERR_ARG, "sbk_batch_set_plan: plan must be 0..3");
+    if (plan < 1 || plan > 4) return fail(SBK_ERR_ARG, "sbk_batch_set_plan: plan must be 0..4");
     if (plan == 2 && !fusedOk(b))
         return fail(SBK_ERR_ARG, "sbk_batch_set_plan: the register-resident fused plan needs a serial chain of 1-2 Pin/Slider mobilizers");
     if (plan == b->plan) return SBK_OK;
@@ -578,6 +578,8 @@ int sbk_rkm_step(sbk_batch* b, double h, int nsteps, const sbk_rkm_opts* opts, d
             std::vector<int> joints(b->topo->nb);
             for (int i = 0; i < b->topo->nb; ++i) joints[i] = b->topo->bodies[i].joint;
             CUDA_TRY(launchFusedRkm(a, joints.data(), false, b->stream)); b->launches++;
+        } else if (b->plan == 4) {
+            CUDA_TRY(launchGlRkm(a, b->stream)); b->launches++;
         } else if (int rc = launch(b, OP_RKM)) return rc;
         CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
         invalidate(b);
@@ -597,7 +599,7 @@ void sbk_adaptive_default_opts(sbk_adaptive_opts* o) {
 int sbk_rkm_adaptive(sbk_batch* b, double tFinal, const sbk_adaptive_opts* opts, int32_t* steps, int32_t* attempts, double* lastStep) {
     if (!b) return fail(SBK_ERR_ARG, "null batch");
     if (int rc = useDevice(b)) return rc;
-    if (b->plan == 3) return fail(SBK_ERR_ARG, "sbk_rkm_adaptive: not available in the level-parallel plan (use sbk_batch_set_plan(b, 1))");
+    if (b->plan == 3 || b->plan == 4) return fail(SBK_ERR_ARG, "sbk_rkm_adaptive: not available in the level-parallel plans (use sbk_batch_set_plan(b, 1))");
     sbk_adaptive_opts o; sbk_adaptive_default_opts(&o);
     if (opts) {
         o = *opts;

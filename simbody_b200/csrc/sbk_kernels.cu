@@ -432,6 +432,160 @@ template <int OP> cudaError_t launchLpOp(const KArgs& a, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+//==============================================================================================
+// Grid-level-parallel integrator (plan 4): wide trees, small batches.
+// A work item is (one body of a tree level, one warp of 32 instances): every warp of a persistent,
+// co-resident grid takes items of the current level in a grid-stride loop, so a level of w bodies
+// offers w * N/32 warps of work to the whole GPU (plan 3 gives one CTA per instance and idles most
+// of its threads on narrow levels).  Lanes are instances, so the joint switch stays warp-uniform
+// and the CTA-blocked records are read fully coalesced.  Levels are separated by a grid barrier
+// (a monotonic counter; the grid is sized by the occupancy API so every CTA is resident).
+//==============================================================================================
+constexpr int GL_THREADS = 128;
+
+__device__ __forceinline__ void gridBarrier(unsigned* bar, unsigned nblocks, unsigned& target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += nblocks;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        unsigned v;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while (v < target);
+    }
+    __syncthreads();
+}
+// f(body, instance) for every (body of level l, instance); lanes of a warp = 32 consecutive instances
+template <class F> __device__ __forceinline__ void glLevel(const LpLevels& L, int l, int N, F f) {
+    const int nwi = (N + 31) >> 5;                                  // instance warps
+    const int items = (L.start[l+1] - L.start[l])*nwi;
+    const int warp = (blockIdx.x*GL_THREADS + threadIdx.x) >> 5, nwarps = (gridDim.x*GL_THREADS) >> 5, lane = threadIdx.x & 31;
+    for (int it = warp; it < items; it += nwarps) {
+        const int body = L.order[L.start[l] + it / nwi], inst = (it % nwi)*32 + lane;
+        if (inst < N) f(body, inst);
+    }
+}
+__device__ __forceinline__ double warpReduce(double v, bool isMax) {
+    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, v, o); v = isMax ? fmax(v, t) : v + t; }
+    return v;
+}
+// IntegratorRep::calcErrorNorm for one instance by one warp (lanes over slots / bodies), cf. lpErrorNorm
+__device__ double glErrorNorm(const Ctx& c, const int inst, const KArgs& a) {
+    const int nq = c.nq, nu = c.nu, lane = threadIdx.x & 31; const bool inf = a.useInfNorm != 0;
+    double uAcc = 0, qAcc = 0;
+    for (int i = lane; i < nu; i += 32) {
+        const double u0 = fabs(ldS<false>(c, inst, a.y0, nq + i));
+        const double sc = (u0*1.0 > 1.0) ? 1.0/u0 : 1.0;
+        const double v = sc*ldS<false>(c, inst, a.ys, nq + i);
+        if (inf) uAcc = fmax(uAcc, fabs(v)); else uAcc += v*v;
+    }
+    for (int b = 1 + lane; b < c.nb; b += 32) {
+        const BodyConst& bc = c.bodies[b];
+        int first = 0;
+        if (bc.joint == JT_BALL || bc.joint == JT_FREE) {
+            double q[4], e[4], o[4];
+            for (int i = 0; i < 4; ++i) { q[i] = ldS<false>(c, inst, a.y, bc.q0 + i); e[i] = ldS<false>(c, inst, a.ys, bc.q0 + i); }
+            const V3 du = quatNInvTimes(q, e);
+            quatNTimes(q, du, o);
+            for (int i = 0; i < 4; ++i) { if (inf) qAcc = fmax(qAcc, fabs(o[i])); else qAcc += o[i]*o[i]; }
+            first = 4;
+        }
+        const int nqb = nqOfJoint(bc.joint);
+        for (int i = first; i < nqb; ++i) { const double v = ldS<false>(c, inst, a.ys, bc.q0 + i); if (inf) qAcc = fmax(qAcc, fabs(v)); else qAcc += v*v; }
+    }
+    uAcc = warpReduce(uAcc, inf); qAcc = warpReduce(qAcc, inf);
+    const double qNorm = inf ? qAcc : (nq ? sqrt(qAcc/nq) : 0.0), uNorm = inf ? uAcc : (nu ? sqrt(uAcc/nu) : 0.0);
+    return qNorm >= uNorm ? qNorm : uNorm;
+}
+
+#ifndef SBK_GL_MINB
+#define SBK_GL_MINB 2
+#endif
+__global__ void __launch_bounds__(GL_THREADS, SBK_GL_MINB) glRkmKernel(const KArgs a) {
+    __shared__ Ctx sctx;
+    if (threadIdx.x == 0) fillCtx(sctx, a, a.tables, true);
+    __syncthreads();
+    const Ctx& c = sctx;
+    LpLevels L; L.order = reinterpret_cast<const int*>(a.tables + a.levelOrderOff);
+    L.start = reinterpret_cast<const int*>(a.tables + a.levelStartOff); L.nlevels = a.nlevels;
+    unsigned target = 0; unsigned* bar = reinterpret_cast<unsigned*>(a.taskCounter);
+    const int N = a.N, nq = c.nq, ny = c.nq + c.nu; const long long uoff = (long long)nq*N;
+    const long long tid = (long long)blockIdx.x*GL_THREADS + threadIdx.x, nth = (long long)gridDim.x*GL_THREADS, nel = (long long)ny*N;
+    const double h = a.h;
+    for (int s = 0; s < a.nsteps; ++s) {
+#pragma unroll 1
+        for (int stage = 0; stage < 5; ++stage) {
+            double* fdst = stage == 0 ? a.f0 : (stage == 3 ? a.fb : a.fa);
+            double* qd = fdst; double* ud = fdst + uoff;
+#pragma unroll 1
+            for (int l = 1; l < L.nlevels; ++l) { glLevel(L, l, N, [&](int b, int i) { kinDispatch(c, b, i, qd); }); gridBarrier(bar, gridDim.x, target); }
+#pragma unroll 1
+            for (int l = L.nlevels - 1; l >= 1; --l) { glLevel(L, l, N, [&](int b, int i) { inwardDispatch<IN_ABI | IN_Z | IN_BIAS | IN_FORCES>(c, b, i); }); gridBarrier(bar, gridDim.x, target); }
+#pragma unroll 1
+            for (int l = 1; l < L.nlevels; ++l) { glLevel(L, l, N, [&](int b, int i) { outwardDispatch<true>(c, b, i, ud, nullptr); }); gridBarrier(bar, gridDim.x, target); }
+            // stage combination over the flat [slot][N] vectors (element e = slot*N + instance)
+            for (long long e = tid; e < nel; e += nth) {
+                const double y0 = stage == 0 ? a.y[e] : a.y0[e], f0 = a.f0[e];
+                if (stage == 0)      { a.y0[e] = y0; a.y[e] = y0 + (h/3)*f0; }
+                else if (stage == 1) { a.y[e] = y0 + (h/6)*(f0 + a.fa[e]); }
+                else if (stage == 2) { a.y[e] = y0 + (h/8)*(f0 + 3*a.fa[e]); }
+                else if (stage == 3) { const double ys = y0 + (h/2)*(f0 - 3*a.fa[e] + 4*a.fb[e]); a.ys[e] = ys; a.y[e] = ys; }
+                else                 { const double y1 = y0 + (h/6)*(f0 + 4*a.fb[e] + a.fa[e]); a.y[e] = y1; a.ys[e] = 0.2*fabs(y1 - a.ys[e]); }
+            }
+            gridBarrier(bar, gridDim.x, target);
+        }
+        // error norm and quaternion projection: one warp per instance (AbstractIntegratorRep.cpp:137-208)
+        {
+            const int warp = (int)(tid >> 5), nwarps = (int)(nth >> 5), lane = threadIdx.x & 31;
+            for (int inst = warp; inst < N; inst += nwarps) {
+                double err = glErrorNorm(c, inst, a); int proj = 0;
+                if (c.nquat > 0 && !(err > 16.0*a.accuracy)) {
+                    double acc = 0; const bool inf = a.useInfNorm != 0;
+                    for (int b = 1 + lane; b < c.nb; b += 32) {
+                        const BodyConst& bc = c.bodies[b];
+                        if (bc.joint != JT_BALL && bc.joint != JT_FREE) continue;
+                        double n2 = 0; for (int i = 0; i < 4; ++i) { const double qi = ldS<false>(c, inst, a.y, bc.q0 + i); n2 += qi*qi; }
+                        const double e = sqrt(n2) - 1.0;
+                        if (inf) acc = fmax(acc, fabs(e)); else acc += e*e;
+                    }
+                    acc = warpReduce(acc, inf);
+                    const double quatNorm = inf ? acc : sqrt(acc/c.nquat);
+                    if (quatNorm > a.consTol || a.projectEveryStep) {
+                        for (int b = 1 + lane; b < c.nb; b += 32) {
+                            const BodyConst& bc = c.bodies[b];
+                            if (bc.joint != JT_BALL && bc.joint != JT_FREE) continue;
+                            double q[4], e[4], n2 = 0;
+                            for (int i = 0; i < 4; ++i) { q[i] = ldS<false>(c, inst, a.y, bc.q0 + i); e[i] = ldS<false>(c, inst, a.ys, bc.q0 + i); n2 += q[i]*q[i]; }
+                            const double n = sqrt(n2); double dt = 0;
+                            for (int i = 0; i < 4; ++i) { q[i] = q[i]/n; dt += e[i]*q[i]; }
+                            for (int i = 0; i < 4; ++i) { stS<false>(c, inst, a.y, bc.q0 + i, q[i]); stS<false>(c, inst, a.ys, bc.q0 + i, e[i] - dt*q[i]); }
+                        }
+                        __syncwarp();
+                        proj = 1;
+                        err = glErrorNorm(c, inst, a);
+                    }
+                }
+                if (lane == 0) {
+                    a.tcur[inst] += a.h; a.errNorm[inst] = err; a.projCount[inst] += proj;
+                    if (a.status && !(err == err)) a.status[inst] |= 1;
+                }
+            }
+        }
+        gridBarrier(bar, gridDim.x, target);
+    }
+}
+cudaError_t launchGlRkmImpl(const KArgs& a, cudaStream_t stream) {
+    int dev = 0, sms = 0, perSm = 0;
+    cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, glRkmKernel, GL_THREADS, 0);
+    if (e != cudaSuccess) return e;
+    if (perSm < 1) return cudaErrorLaunchOutOfResources;
+    e = cudaMemsetAsync(a.taskCounter, 0, sizeof(int), stream);           // the barrier counter
+    if (e != cudaSuccess) return e;
+    void* args[] = { const_cast<KArgs*>(&a) };
+    // cooperative launch: the driver guarantees (or refuses) co-residency of the whole grid
+    return cudaLaunchCooperativeKernel((const void*)glRkmKernel, dim3(sms*perSm), dim3(GL_THREADS), args, 0, stream);
+}
+
 __device__ __forceinline__ long long instOffsetK(const KArgs& a, int k) {
     return (long long)(k >> a.cShift)*a.cSpan + (long long)(k & a.cMask)*a.cInstStride;
 }
@@ -637,6 +791,7 @@ cudaError_t launchLp(KernelOp op, const KArgs& a, cudaStream_t stream) {
     }
     return cudaErrorInvalidValue;
 }
+cudaError_t launchGlRkm(const KArgs& a, cudaStream_t stream) { return launchGlRkmImpl(a, stream); }
 bool fusedPlanSupports(int nb, const int* joints) {
     auto simple = [](int j) { return j == JT_PIN || j == JT_SLIDER; };
     if (nb == 2) return simple(joints[1]) || joints[1] == JT_UNIVERSAL;

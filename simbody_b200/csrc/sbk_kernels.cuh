@@ -64,6 +64,9 @@ cudaError_t launchFusedRkm(const KArgs& a, const int* joints, bool adaptive, cud
 // Level-parallel plan (wide trees, small batches): one CTA per instance, threads over the bodies
 // of a tree level, __syncthreads between levels.
 cudaError_t launchLp(KernelOp op, const KArgs& a, cudaStream_t stream);
+// Grid-level-parallel fixed-step integrator (plan 4): persistent cooperative grid, work items = (body of a level, warp of
+// instances), grid barriers between levels.  Uses the thread-per-instance record layout and the [slot][N] work vectors.
+cudaError_t launchGlRkm(const KArgs& a, cudaStream_t stream);
 // Ground record (identity transform, zero velocity/acceleration) for every instance.
 cudaError_t launchInitGround(const KArgs& a, cudaStream_t stream);
 // dst[k*len + i] <-> src[i*N + k]

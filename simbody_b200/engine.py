@@ -125,7 +125,8 @@ class BatchedMatter:
         return [x.value for x in p]
 
     def setPlan(self, plan):
-        """0 auto, 1 thread-per-instance (per-body cache in HBM), 2 register-resident fused (tiny chains)."""
+        """0 auto, 1 thread-per-instance, 2 register-resident fused (tiny chains), 3 level-parallel CTA per instance,
+        4 grid-level-parallel integrator (wide trees, small batches)."""
         self._chk(self.lib.sbk_batch_set_plan(self.handle, int(plan)))
 
     def getPlan(self):

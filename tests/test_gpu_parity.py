@@ -198,9 +198,40 @@ def test_level_parallel_plan_matches_golden(name):
     bm.close(); topo.close()
 
 
+@pytest.mark.parametrize("name", ["mixed7", "welded8", "humanoid30", "branched_tree"])
+def test_grid_level_parallel_plan_matches_golden(name):
+    """Plan 4 (persistent grid, work items = body of a level x warp of instances, grid barriers between
+    levels) against the reference: fixed-step RKM, plus agreement with plan 1 on a batch that is not a
+    multiple of the warp size and spans several record blocks."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    info = ModelInfo(str(g["text"]))
+    y0, yref = g["step_in"], g["step_out"]
+    n, ny = y0.shape[0], info.nq + info.nu
+    topo = sb.Topology(text=info.text); bm = sb.BatchedMatter(topo, n); bm.setPlan(4); assert bm.getPlan() == 4
+    bm.setState(soa(y0[:, :info.nq]), soa(y0[:, info.nq:]), t=0.0)
+    err = bm.stepBy(float(g["h"]), int(g["nsteps"]), want_err_norm=True)
+    q, u, t = bm.getState()
+    assert np.all(np.isfinite(err)) and np.allclose(t, float(g["h"]) * int(g["nsteps"]))
+    assert rel_err(np.concatenate([q.T, u.T], axis=1), yref[:, :ny]) < 1e-10
+    bm.close()
+    nb = 300
+    qq, uu = info.random_states(nb, 31, q_scale=0.5)
+    out = {}
+    for plan in (1, 4):
+        bm = sb.BatchedMatter(topo, nb); bm.setPlan(plan)
+        bm.setState(soa(qq), soa(uu), t=0.0)
+        e = bm.stepBy(1e-3, 3, want_err_norm=True)
+        a, b, _ = bm.getState()
+        out[plan] = (a, b, e)
+        bm.close()
+    assert rel_err(out[4][0], out[1][0]) < 1e-10 and rel_err(out[4][1], out[1][1]) < 1e-10, (rel_err(out[4][0], out[1][0]), rel_err(out[4][1], out[1][1]))
+    assert np.allclose(out[4][2], out[1][2], rtol=1e-3, atol=1e-14)
+    topo.close()
+
+
 def test_auto_plan_selection():
     for name, n, batch, plan in [("double_pendulum", 0, 1024, 2), ("pin_chain", 50, 1024, 1), ("humanoid30", 0, 1024, 1),
-                                 ("branched_tree", 1000, 64, 3), ("branched_tree", 1000, 65536 // 64 * 16, 1)]:
+                                 ("branched_tree", 1000, 64, 4), ("branched_tree", 1000, 65536 // 64 * 16, 1)]:
         topo = sb.Topology(text=sb.model_text(name, n))
         if name == "branched_tree" and batch > 64:
             batch = 16384       # large batches of wide trees go thread-per-instance
