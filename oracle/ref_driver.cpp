@@ -73,6 +73,9 @@ struct RefSystem {
               case SBK_JOINT_BALL:      { MobilizedBody::Ball      m(parent, X_PF, body, X_BM); break; }
               case SBK_JOINT_FREE:      { MobilizedBody::Free      m(parent, X_PF, body, X_BM); break; }
               case SBK_JOINT_WELD:      { MobilizedBody::Weld      m(parent, X_PF, body, X_BM); break; }
+              case SBK_JOINT_TRANSLATION: { MobilizedBody::Translation m(parent, X_PF, body, X_BM); break; }
+              case SBK_JOINT_CYLINDER:  { MobilizedBody::Cylinder  m(parent, X_PF, body, X_BM); break; }
+              case SBK_JOINT_PLANAR:    { MobilizedBody::Planar    m(parent, X_PF, body, X_BM); break; }
               default: throw std::runtime_error("ref_driver: bad joint type");
             }
         }

@@ -34,7 +34,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-enum { PIN = 1, SLIDER = 2, UNIVERSAL = 3, BALL = 4, FREE = 5, WELD = 6 };
+enum { PIN = 1, SLIDER = 2, UNIVERSAL = 3, BALL = 4, FREE = 5, WELD = 6, TRANSLATION = 7, CYLINDER = 8, PLANAR = 9 };
 enum { F_GRAVITY = 1, F_SPRING = 2, F_DAMPER = 3, F_UNIFORM_GRAVITY = 4, F_GLOBAL_DAMPER = 5 };
 #define MAXD 6
 
@@ -58,8 +58,8 @@ typedef struct {   /* per-body cache, dense */
     int q0, u0, nq, nu;
 } Body;
 
-static int NQ(int j) { return j == PIN || j == SLIDER ? 1 : j == UNIVERSAL ? 2 : j == BALL ? 4 : j == FREE ? 7 : 0; }
-static int NU(int j) { return j == PIN || j == SLIDER ? 1 : j == UNIVERSAL ? 2 : j == BALL ? 3 : j == FREE ? 6 : 0; }
+static int NQ(int j) { return j == PIN || j == SLIDER ? 1 : (j == UNIVERSAL || j == CYLINDER) ? 2 : (j == TRANSLATION || j == PLANAR) ? 3 : j == BALL ? 4 : j == FREE ? 7 : 0; }
+static int NU(int j) { return j == PIN || j == SLIDER ? 1 : (j == UNIVERSAL || j == CYLINDER) ? 2 : (j == BALL || j == TRANSLATION || j == PLANAR) ? 3 : j == FREE ? 6 : 0; }
 
 static void matvec3(const double* R, const double* v, double* o) { for (int i = 0; i < 3; ++i) o[i] = R[3*i]*v[0] + R[3*i+1]*v[1] + R[3*i+2]*v[2]; }
 static void matmul3(const double* A, const double* B, double* C) {
@@ -154,6 +154,11 @@ static void kinematics(const Model* M, Body* B, const double* q, const double* u
             Rfm[0] = c2; Rfm[1] = 0; Rfm[2] = s2; Rfm[3] = s2*s1; Rfm[4] = c1; Rfm[5] = -s1*c2; Rfm[6] = -s2*c1; Rfm[7] = s1; Rfm[8] = c1*c2;
             Hw[0][0] = 1; Hw[1][0] = Rfm[1]; Hw[1][1] = Rfm[4]; Hw[1][2] = Rfm[7];
         } else if (jt == WELD) {      /* X_FM = I, no mobilities (RigidBodyNode_Weld.cpp:369-420) */
+        } else if (jt == TRANSLATION) { pfm[0] = qb[0]; pfm[1] = qb[1]; pfm[2] = qb[2]; Hv[0][0] = Hv[1][1] = Hv[2][2] = 1;   /* _Translation.h:100-130 */
+        } else if (jt == CYLINDER) {  /* _Cylinder.h:110-139 */
+            double c = cos(qb[0]), s = sin(qb[0]); Rfm[0] = c; Rfm[1] = -s; Rfm[3] = s; Rfm[4] = c; pfm[2] = qb[1]; Hw[0][2] = 1; Hv[1][2] = 1;
+        } else if (jt == PLANAR) {    /* _Planar.h:126-157 */
+            double c = cos(qb[0]), s = sin(qb[0]); Rfm[0] = c; Rfm[1] = -s; Rfm[3] = s; Rfm[4] = c; pfm[0] = qb[1]; pfm[1] = qb[2]; Hw[0][2] = 1; Hv[1][0] = 1; Hv[2][1] = 1;
         } else {                      /* Ball / Free, quaternion (Rotation.cpp:600-611) */
             double n = sqrt(qb[0]*qb[0] + qb[1]*qb[1] + qb[2]*qb[2] + qb[3]*qb[3]);
             if (qerr) qerr[iq] = n - 1.0; ++iq;

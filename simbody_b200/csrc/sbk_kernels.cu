@@ -1,12 +1,13 @@
-// sbk_kernels.cu -- sm_100a kernels of the thread-per-instance plan.
+// sbk_kernels.cu -- sm_100a kernels.
 //
-// Mapping: one thread = one instance; a warp = 32 instances walking the SAME body at the same
-// time, so the joint-type switch is warp-uniform and every cache/state access
-// cache[(record+field)*N + instance] is a fully coalesced 256-byte warp transaction.
-// Batch-shared body constants are staged into shared memory once per CTA by a TMA bulk copy
-// (cp.async.bulk.shared::cluster.global + mbarrier complete_tx) and then read as warp
-// broadcasts.  FP64 throughout; no tensor cores (6x6 spatial operators are not a dense
-// contraction).
+// Thread-per-instance plans (1, 2, and the API operations of 4): one thread = one instance; a warp = 32
+// instances walking the SAME body at the same time, so the joint-type switch is warp-uniform and every
+// access to the CTA-blocked records / state ([block of 128][row][lane]) is a fully coalesced 256-byte warp
+// transaction.  Batch-shared body constants are staged into shared memory once per CTA by a TMA bulk copy
+// (cp.async.bulk.shared::cluster.global + mbarrier complete_tx) and then read as warp broadcasts.
+// The fixed-step integrator kernel is persistent (task queue over block x step).  Plan 3 maps a CTA to an
+// instance and threads to the bodies of a level; plan 4 maps the whole (cooperative) grid to one tree level
+// of the batch.  FP64 throughout; no tensor cores (6x6 spatial operators are not a dense contraction).
 #include <algorithm>
 #include "sbk_kernels.cuh"
 #include "sbk_fused.cuh"
@@ -268,7 +269,7 @@ cudaError_t launchOp(const KArgs& a, cudaStream_t stream) {
         const int m = a.jointMask;
         if ((m & ~JM_PIN) == 0) return a.stageInSmem ? go(tpiKernel<OP, true, SBK_TPI_MINBLOCKS, JM_PIN>) : go(tpiKernel<OP, false, SBK_TPI_MINBLOCKS, JM_PIN>);
         if ((m & ~LIGHT) == 0)  return a.stageInSmem ? go(tpiKernel<OP, true, SBK_TPI_MINBLOCKS, LIGHT>)  : go(tpiKernel<OP, false, SBK_TPI_MINBLOCKS, LIGHT>);
-        constexpr int MOBILE = JM_ALL & ~JM_WELD;     // the five mobilizers with coordinates, no Weld code
+        constexpr int MOBILE = JM_MOBILE5;            // the north_star mobilizer set: no Weld / Cartesian mobilizer code
         if ((m & ~MOBILE) == 0) return a.stageInSmem ? go(tpiKernel<OP, true, SBK_HEAVY_MINB, MOBILE>) : go(tpiKernel<OP, false, SBK_HEAVY_MINB, MOBILE>);
     }
     return a.stageInSmem ? go(tpiKernel<OP, true, SBK_HEAVY_MINB>) : go(tpiKernel<OP, false, SBK_HEAVY_MINB>);

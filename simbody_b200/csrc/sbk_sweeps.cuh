@@ -4,15 +4,18 @@
 //   *Core functions*  pure register arithmetic for ONE body of ONE instance (no memory
 //                     traffic): kinCore (sweeps A+B), abiCore (sweep C + bias), zCore (sweep D),
 //                     accCore (sweep E), qddCore, forceCore.
-//   *Body wrappers*   move a body's data between the cores and the per-body cache records in
-//                     HBM (thread-per-instance and level-parallel plans), optionally in LEAN
-//                     mode: parent->child and child->parent links ride in a per-thread carry
-//                     (registers / L1-resident stack) and only what a later sweep needs is stored.
+//   *Body wrappers*   FULL: move a body's data between the cores and the per-body cache records
+//                     in HBM (API realize path of every plan; getters and operators read them).
+//                     LEAN (integrator path of the thread-per-instance plan): reversible
+//                     kinematics -- parent/child links ride in a per-thread carry column in shared
+//                     memory, the inward sweep recovers each parent transform by inverting the
+//                     recurrence, and only G and nu = DI*eps (7*dof doubles) per body reach HBM.
 //   The register-resident fused plan (sbk_fused.cuh) calls the cores directly.
 //
 // Reference file:line each core replaces
 //   kinCore   RigidBodyNodeSpec.h:229-333,554-569; RigidBodyNodeSpec.cpp:44-129;
-//             RigidBodyNode.cpp:54-174; RigidBodyNodeSpec_{Pin,Slider,Universal,Ball,Free}.h
+//             RigidBodyNode.cpp:54-174; RigidBodyNodeSpec_{Pin,Slider,Universal,Ball,Free}.h;
+//             RigidBodyNode_Weld.cpp:369-450 (Weld)
 //   abiCore   RigidBodyNodeSpec.cpp:249-325 (ABI), RigidBodyNode.cpp:201-213 (P*a+b)
 //   zCore     RigidBodyNodeSpec.cpp:355-400 (forward dynamics), :483-515 (M^-1 pass 1)
 //   accCore   RigidBodyNodeSpec.cpp:408-446, :521-552
@@ -25,24 +28,16 @@
 #pragma once
 #include "sbk_math.cuh"
 
-// Where the function-call boundaries sit.  An ABI call makes the callee save and restore every
-// callee-saved register it touches (~100 registers = ~800 bytes of local-memory traffic per call
-// for these FP64-heavy bodies, measured with ncu), so the integrator calls ONE non-inlined
-// function per derivative evaluation and inlines the per-body steps into it.
-#ifndef SBK_INLINE_BODIES
-#define SBK_INLINE_BODIES 1
-#endif
-#if SBK_INLINE_BODIES
+// Body wrappers are force-inlined into their sweep drivers.  (An ABI call makes the callee save and
+// restore every callee-saved register it touches -- ~100 registers = ~800 bytes of local-memory
+// traffic per call for these FP64-heavy bodies, measured with ncu -- so the integrator has ONE inlined
+// copy of the sweeps inside its stage loop, see tpiRkmStep.)
 #define SBK_BODY SBK_HD
-#define SBK_EVAL SBK_HDN
-#else
-#define SBK_BODY SBK_HDN
-#define SBK_EVAL SBK_HD
-#endif
 
 namespace sbkd {
 
-enum { JT_GROUND = 0, JT_PIN = 1, JT_SLIDER = 2, JT_UNIVERSAL = 3, JT_BALL = 4, JT_FREE = 5, JT_WELD = 6 };
+enum { JT_GROUND = 0, JT_PIN = 1, JT_SLIDER = 2, JT_UNIVERSAL = 3, JT_BALL = 4, JT_FREE = 5, JT_WELD = 6,
+       JT_TRANSLATION = 7, JT_CYLINDER = 8, JT_PLANAR = 9 };
 enum { FK_SPRING = 2, FK_DAMPER = 3 };
 
 template <int JT> struct JointDims;
@@ -52,8 +47,17 @@ template <> struct JointDims<JT_UNIVERSAL> { enum { nq = 2, nu = 2 }; };
 template <> struct JointDims<JT_BALL>      { enum { nq = 4, nu = 3 }; };
 template <> struct JointDims<JT_FREE>      { enum { nq = 7, nu = 6 }; };
 template <> struct JointDims<JT_WELD>      { enum { nq = 0, nu = 0 }; };   // RigidBodyNode_Weld.cpp:369: no q, no u
+template <> struct JointDims<JT_TRANSLATION> { enum { nq = 3, nu = 3 }; };
+template <> struct JointDims<JT_CYLINDER>  { enum { nq = 2, nu = 2 }; };
+template <> struct JointDims<JT_PLANAR>    { enum { nq = 3, nu = 3 }; };
 // array extent for a dof count that may be zero
 SBK_HD constexpr int dim1(int d) { return d > 0 ? d : 1; }
+
+// mobilizer-kind masks (bit JT_x set = kind present), see SBK_DISPATCH_JOINT_M
+enum { JM_PIN = 1 << JT_PIN, JM_SLIDER = 1 << JT_SLIDER, JM_UNIVERSAL = 1 << JT_UNIVERSAL, JM_BALL = 1 << JT_BALL, JM_FREE = 1 << JT_FREE,
+       JM_WELD = 1 << JT_WELD, JM_TRANSLATION = 1 << JT_TRANSLATION, JM_CYLINDER = 1 << JT_CYLINDER, JM_PLANAR = 1 << JT_PLANAR,
+       JM_MOBILE5 = JM_PIN | JM_SLIDER | JM_UNIVERSAL | JM_BALL | JM_FREE,       // the north_star mobilizer set
+       JM_ALL = JM_MOBILE5 | JM_WELD | JM_TRANSLATION | JM_CYLINDER | JM_PLANAR };
 
 // cache record layout
 enum { F_XGB = 0, F_VGB = 12, F_L = 18, F_MK = 21, F_ACOR = 30, F_GYRO = 36, F_ZB = 42,
@@ -237,8 +241,10 @@ template <bool BLK> SBK_HD long long stateIndex(const Ctx& c, int inst, int slot
 template <bool BLK> SBK_HD double ldS(const Ctx& c, int inst, const double* a, int slot) { return gld(a + stateIndex<BLK>(c, inst, slot)); }
 template <bool BLK> SBK_HD void   stS(const Ctx& c, int inst, double* a, int slot, double v) { gst(a + stateIndex<BLK>(c, inst, slot), v); }
 
-SBK_HD int dofOfJoint(int jt) { return jt == JT_FREE ? 6 : jt == JT_BALL ? 3 : jt == JT_UNIVERSAL ? 2 : (jt == JT_GROUND || jt == JT_WELD) ? 0 : 1; }
-SBK_HD int nqOfJoint(int jt)  { return jt == JT_FREE ? 7 : jt == JT_BALL ? 4 : jt == JT_UNIVERSAL ? 2 : (jt == JT_GROUND || jt == JT_WELD) ? 0 : 1; }
+SBK_HD int dofOfJoint(int jt) { return jt == JT_FREE ? 6 : (jt == JT_BALL || jt == JT_TRANSLATION || jt == JT_PLANAR) ? 3 : (jt == JT_UNIVERSAL || jt == JT_CYLINDER) ? 2
+                                      : (jt == JT_GROUND || jt == JT_WELD) ? 0 : 1; }
+SBK_HD int nqOfJoint(int jt)  { return jt == JT_FREE ? 7 : jt == JT_BALL ? 4 : (jt == JT_TRANSLATION || jt == JT_PLANAR) ? 3 : (jt == JT_UNIVERSAL || jt == JT_CYLINDER) ? 2
+                                      : (jt == JT_GROUND || jt == JT_WELD) ? 0 : 1; }
 SBK_HD M3 loadR(const double* X) { M3 R;
 #pragma unroll
     for (int i = 0; i < 9; ++i) R.a[i] = X[i]; return R; }
@@ -304,12 +310,17 @@ SBK_HD void kinLocal(const BodyConst& bc, const double* q, KinLocal<JointDims<JT
     k.qerr = 0;
     M3& R_FM = k.R_FM;
 
-    if constexpr (JT == JT_PIN) {                 // RigidBodyNodeSpec_Pin.h:103-140
+    if constexpr (JT == JT_PIN || JT == JT_CYLINDER || JT == JT_PLANAR) {   // R_FM = Rz(q0): _Pin.h:103-140, _Cylinder.h:110-139, _Planar.h:126-157
         double s, co; sincos(q[0], &s, &co);
         R_FM.a[0] = co; R_FM.a[1] = -s; R_FM.a[2] = 0;
         R_FM.a[3] = s;  R_FM.a[4] = co; R_FM.a[5] = 0;
         R_FM.a[6] = 0;  R_FM.a[7] = 0;  R_FM.a[8] = 1;
         k.Hw[0] = mk(0, 0, 1);
+        if constexpr (JT == JT_CYLINDER) { p_FM = mk(0, 0, q[1]); k.Hv[1] = mk(0, 0, 1); }
+        if constexpr (JT == JT_PLANAR)   { p_FM = mk(q[1], q[2], 0); k.Hv[1] = mk(1, 0, 0); k.Hv[2] = mk(0, 1, 0); }
+    } else if constexpr (JT == JT_TRANSLATION) {  // RigidBodyNodeSpec_Translation.h:100-130
+        R_FM = identity3(); p_FM = mk(q[0], q[1], q[2]);
+        k.Hv[0] = mk(1, 0, 0); k.Hv[1] = mk(0, 1, 0); k.Hv[2] = mk(0, 0, 1);
     } else if constexpr (JT == JT_WELD) {         // RigidBodyNode_Weld.cpp:390-398: X_FM = I
         R_FM = identity3();
     } else if constexpr (JT == JT_SLIDER) {       // RigidBodyNodeSpec_Slider.h:91-127
@@ -341,7 +352,7 @@ SBK_HD void kinLocal(const BodyConst& bc, const double* q, KinLocal<JointDims<JT
     // reference does through its noR_PF / noX_MB template flags.
     const bool noRPF = (bc.flags & BF_NO_R_PF) != 0, noRMB = (bc.flags & BF_NO_R_MB) != 0;
     M3 R_FB;
-    if constexpr (JT == JT_PIN) {                      // R_FM = Rz(q): products written out without the 0 / 1 entries
+    if constexpr (JT == JT_PIN || JT == JT_CYLINDER || JT == JT_PLANAR) {   // R_FM = Rz(q0): products written out without the 0 / 1 entries
         const double co = R_FM.a[0], si = R_FM.a[3];
         k.r = mk(co*p_MB.x - si*p_MB.y, si*p_MB.x + co*p_MB.y, p_MB.z);
         if (noRMB) R_FB = R_FM;
@@ -353,7 +364,7 @@ SBK_HD void kinLocal(const BodyConst& bc, const double* q, KinLocal<JointDims<JT
                 R_FB.a[6 + j] = R_MB.a[6+j];
             }
         }
-    } else if constexpr (JT == JT_SLIDER || JT == JT_WELD) {   // R_FM = I
+    } else if constexpr (JT == JT_SLIDER || JT == JT_WELD || JT == JT_TRANSLATION) {   // R_FM = I
         k.r = p_MB; R_FB = R_MB;
     } else {
         k.r = mul(R_FM, p_MB);                         // r_MB_F = R_FM * p_MB
@@ -373,6 +384,9 @@ SBK_HD void jointH(const M3& R_GF, const KinLocal<JointDims<JT>::nu>& k, SV* H) 
     if constexpr (JT == JT_WELD) { (void)r; (void)H; }
     else if constexpr (JT == JT_PIN) SBK_ROTCOL(0, 2)
     else if constexpr (JT == JT_SLIDER) SBK_TRCOL(0, 0)
+    else if constexpr (JT == JT_TRANSLATION) { SBK_TRCOL(0, 0) SBK_TRCOL(1, 1) SBK_TRCOL(2, 2) }
+    else if constexpr (JT == JT_CYLINDER) { SBK_ROTCOL(0, 2) SBK_TRCOL(1, 2) }
+    else if constexpr (JT == JT_PLANAR) { SBK_ROTCOL(0, 2) SBK_TRCOL(1, 0) SBK_TRCOL(2, 1) }
     else if constexpr (JT == JT_UNIVERSAL) {
         SBK_ROTCOL(0, 0)
         H[1].w = mul(R_GF, k.Hw[1]); H[1].v = mul(R_GF, cross(k.Hw[1], r));
@@ -385,8 +399,8 @@ SBK_HD void jointH(const M3& R_GF, const KinLocal<JointDims<JT>::nu>& k, SV* H) 
 }
 // w_FM = H_FM(angular) u
 template <int JT> SBK_HD V3 jointWFM(const KinLocal<JointDims<JT>::nu>& k, const double* u) {
-    if constexpr (JT == JT_PIN) return mk(0, 0, u[0]);
-    else if constexpr (JT == JT_SLIDER || JT == JT_WELD) return zero3();
+    if constexpr (JT == JT_PIN || JT == JT_CYLINDER || JT == JT_PLANAR) return mk(0, 0, u[0]);
+    else if constexpr (JT == JT_SLIDER || JT == JT_WELD || JT == JT_TRANSLATION) return zero3();
     else if constexpr (JT == JT_UNIVERSAL) return mk(u[0], 0, 0) + u[1]*k.Hw[1];
     else return mk(u[0], u[1], u[2]);
 }
@@ -431,6 +445,9 @@ SBK_HD void kinGlobal(const BodyConst& bc, const KinLocal<JointDims<JT>::nu>& k,
     if constexpr (JT == JT_WELD) { (void)wxr; }
     else if constexpr (JT == JT_PIN) SBK_ROTCOL_D(0, 2)
     else if constexpr (JT == JT_SLIDER) SBK_TRCOL_D(0)
+    else if constexpr (JT == JT_TRANSLATION) { SBK_TRCOL_D(0) SBK_TRCOL_D(1) SBK_TRCOL_D(2) }
+    else if constexpr (JT == JT_CYLINDER) { SBK_ROTCOL_D(0, 2) SBK_TRCOL_D(1) }
+    else if constexpr (JT == JT_PLANAR) { SBK_ROTCOL_D(0, 2) SBK_TRCOL_D(1) SBK_TRCOL_D(2) }
     else if constexpr (JT == JT_UNIVERSAL) {
         SBK_ROTCOL_D(0, 0)
         const V3 HDw1 = cross(w_FM, col(k.R_FM, 1));
@@ -808,8 +825,11 @@ SBK_HD constexpr int lfNU(int d) { return LF_G + 6*d; }
 // 4-row slots of the carry column -- registers would not do: the compiler spills a value that is
 // live across the joint switch, and the spill store waits for the load.  Two slots each for q and
 // u cover Pin / Slider / Universal; Ball / Free bodies load their own.
+template <int JMASK>
 SBK_HD void preloadCoords(const Ctx& c, const int inst, const BodyConst& nx, double* slot) {
     constexpr bool BLK = SBK_DEV_BLK;
+    // a model made of 1-dof mobilizers only needs one q and one u row per body (every cp.async costs: measured)
+    constexpr bool ONE = (JMASK & ~(JM_PIN | JM_SLIDER | JM_WELD)) == 0;
     // rows of [q; u] (the u rows follow the q rows), clamped: a Weld owns no slots and the slot after the
     // last one does not exist
     const int last = c.nq + c.nu - 1;
@@ -820,7 +840,8 @@ SBK_HD void preloadCoords(const Ctx& c, const int inst, const BodyConst& nx, dou
 #if defined(__CUDA_ARCH__)
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(slot + k*SBK_CARRY_STRIDE)), "l"(src[k]) : "memory");
+        if (!ONE || k == 0 || k == 2)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(slot + k*SBK_CARRY_STRIDE)), "l"(src[k]) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
 #else
     for (int k = 0; k < 4; ++k) slot[k*SBK_CARRY_STRIDE] = *src[k];
@@ -952,7 +973,7 @@ SBK_BODY void leanOutwardBody(const Ctx& c, const BodyConst& bc, const int inst,
     const CacheRefT<BLK> me = cacheOf<BLK>(c, inst, bc.cacheBase);
     double q[dim1(NQ)], u[dim1(d)], qdot[dim1(NQ)], qerr, nu[dim1(d)], udot[dim1(d)];
     SV G[dim1(d)];
-    if (d <= 2 && gnu) {                                  // preloaded into the carry column (preloadGNu)
+    if ((JT == JT_PIN || JT == JT_SLIDER || JT == JT_UNIVERSAL) && gnu) {   // preloaded into the carry column (preloadGNu)
 #pragma unroll
         for (int j = 0; j < d; ++j) {
             G[j].w = mk(gnu[(6*j+0)*SBK_CARRY_STRIDE], gnu[(6*j+1)*SBK_CARRY_STRIDE], gnu[(6*j+2)*SBK_CARRY_STRIDE]);
@@ -1057,6 +1078,9 @@ SBK_BODY void idInBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, c
         case JT_BALL:      { constexpr int JT = JT_BALL;      CALL; } break;        \
         case JT_FREE:      { constexpr int JT = JT_FREE;      CALL; } break;        \
         case JT_WELD:      { constexpr int JT = JT_WELD;      CALL; } break;        \
+        case JT_TRANSLATION: { constexpr int JT = JT_TRANSLATION; CALL; } break;    \
+        case JT_CYLINDER:  { constexpr int JT = JT_CYLINDER;  CALL; } break;        \
+        case JT_PLANAR:    { constexpr int JT = JT_PLANAR;    CALL; } break;        \
         default: break;                                                             \
     }
 
@@ -1075,8 +1099,6 @@ template <bool WITH_COR> SBK_HD void outwardDispatch(const Ctx& c, int b, int in
 // Same, restricted at compile time to the mobilizer kinds in JMASK (bit JT_x set = kind present): the
 // integrator kernels are instantiated for a few masks so that a model made of Pin joints only does
 // not carry (and register-allocate for) the Ball / Free code.
-enum { JM_PIN = 1 << JT_PIN, JM_SLIDER = 1 << JT_SLIDER, JM_UNIVERSAL = 1 << JT_UNIVERSAL, JM_BALL = 1 << JT_BALL, JM_FREE = 1 << JT_FREE,
-       JM_WELD = 1 << JT_WELD, JM_ALL = JM_PIN | JM_SLIDER | JM_UNIVERSAL | JM_BALL | JM_FREE | JM_WELD };
 #define SBK_DISPATCH_JOINT_M(JMASK, jt, CALL)                                                                       \
     switch (jt) {                                                                                                   \
         case JT_PIN:       if constexpr (((JMASK) & JM_PIN) != 0)       { constexpr int JT = JT_PIN;       CALL; } break; \
@@ -1085,6 +1107,9 @@ enum { JM_PIN = 1 << JT_PIN, JM_SLIDER = 1 << JT_SLIDER, JM_UNIVERSAL = 1 << JT_
         case JT_BALL:      if constexpr (((JMASK) & JM_BALL) != 0)      { constexpr int JT = JT_BALL;      CALL; } break; \
         case JT_FREE:      if constexpr (((JMASK) & JM_FREE) != 0)      { constexpr int JT = JT_FREE;      CALL; } break; \
         case JT_WELD:      if constexpr (((JMASK) & JM_WELD) != 0)      { constexpr int JT = JT_WELD;      CALL; } break; \
+        case JT_TRANSLATION: if constexpr (((JMASK) & JM_TRANSLATION) != 0) { constexpr int JT = JT_TRANSLATION; CALL; } break; \
+        case JT_CYLINDER:  if constexpr (((JMASK) & JM_CYLINDER) != 0)  { constexpr int JT = JT_CYLINDER;  CALL; } break; \
+        case JT_PLANAR:    if constexpr (((JMASK) & JM_PLANAR) != 0)    { constexpr int JT = JT_PLANAR;    CALL; } break; \
         default: break;                                                                                             \
     }
 
@@ -1125,18 +1150,18 @@ template <bool LEAN, int JMASK = JM_ALL> SBK_HD void tpiEvalDerivatives(const Ct
         #define SBK_GNU(k) (cy + (CY_GNU + GNU_ROWS*((k) & 1))*SBK_CARRY_STRIDE)
         int k = 0;
         cyStoreOut(cy, identity3(), zero3(), z0);                                 // Ground's link for body 1
-        preloadCoords(c, inst, T.bodies[1], SBK_PRE(0));
+        preloadCoords<JMASK>(c, inst, T.bodies[1], SBK_PRE(0));
 #pragma unroll 1
         for (int b = 1; b < c.nb; ++b, ++k) {
             const BodyConst& bc = T.bodies[b];
-            preloadCoords(c, inst, T.bodies[b + 1 < c.nb ? b + 1 : c.nb - 1], SBK_PRE(k + 1));   // after the last body: the first of the inward sweep
+            preloadCoords<JMASK>(c, inst, T.bodies[b + 1 < c.nb ? b + 1 : c.nb - 1], SBK_PRE(k + 1));   // after the last body: the first of the inward sweep
             preloadWait();
             SBK_DISPATCH_JOINT_M(JMASK, bc.joint, (leanKinBody<JT>(c, bc, inst, cy, SBK_PRE(k), qdotDst)));
         }
 #pragma unroll 1
         for (int b = c.nb - 1; b >= 1; --b, ++k) {
             const BodyConst& bc = T.bodies[b];
-            preloadCoords(c, inst, T.bodies[b > 1 ? b - 1 : 1], SBK_PRE(k + 1));                  // after body 1: the first of the outward sweep
+            preloadCoords<JMASK>(c, inst, T.bodies[b > 1 ? b - 1 : 1], SBK_PRE(k + 1));                  // after body 1: the first of the outward sweep
             preloadWait();
             SBK_DISPATCH_JOINT_M(JMASK, bc.joint, (leanInwardBody<JT>(c, T, bc, b, inst, cy, SBK_PRE(k))));
         }
@@ -1145,7 +1170,7 @@ template <bool LEAN, int JMASK = JM_ALL> SBK_HD void tpiEvalDerivatives(const Ct
         for (int b = 1; b < c.nb; ++b, ++k) {
             const BodyConst& bc = T.bodies[b];
             if (b + 1 < c.nb) preloadGNu(c, inst, T.bodies[b + 1], SBK_GNU(k + 1));
-            preloadCoords(c, inst, T.bodies[b + 1 < c.nb ? b + 1 : b], SBK_PRE(k + 1));
+            preloadCoords<JMASK>(c, inst, T.bodies[b + 1 < c.nb ? b + 1 : b], SBK_PRE(k + 1));
             preloadWait();
             // body 1 wrote its G / nu at the very end of the inward sweep: it loads them directly
             SBK_DISPATCH_JOINT_M(JMASK, bc.joint, (leanOutwardBody<JT>(c, bc, inst, cy, SBK_PRE(k), b > 1 ? SBK_GNU(k) : nullptr, udotDst, qddDst)));

@@ -66,8 +66,11 @@ inline ModelSpec lowerSimbodySystem(const SimTK::MultibodySystem&        system,
         else if (MobilizedBody::Ball::isInstanceOf(mobod))      b.joint_type = SBK_JOINT_BALL;
         else if (MobilizedBody::Free::isInstanceOf(mobod))      b.joint_type = SBK_JOINT_FREE;
         else if (MobilizedBody::Weld::isInstanceOf(mobod))      b.joint_type = SBK_JOINT_WELD;
+        else if (MobilizedBody::Translation::isInstanceOf(mobod)) b.joint_type = SBK_JOINT_TRANSLATION;
+        else if (MobilizedBody::Cylinder::isInstanceOf(mobod))  b.joint_type = SBK_JOINT_CYLINDER;
+        else if (MobilizedBody::Planar::isInstanceOf(mobod))    b.joint_type = SBK_JOINT_PLANAR;
         else throw std::runtime_error("lowerSimbodySystem: body " + std::to_string((int)mbx) +
-                                      " uses a mobilizer outside {Pin,Slider,Universal,Ball,Free,Weld}");
+                                      " uses a mobilizer outside {Pin,Slider,Universal,Ball,Free,Weld,Translation,Cylinder,Planar}");
         // NOTE: the public API has no getter for MobilizedBody::Direction; reversed mobilizers
         // are out of scope and must not be used with this lowering.
         const MassProperties& mp = mobod.getDefaultMassProperties();
