@@ -253,8 +253,8 @@ sbk_batch* sbk_batch_create(const sbk_topology* t, int n, int device, void* stre
     dalloc(&b->dOpA, (size_t)t->nu*N); dalloc(&b->dOpB, (size_t)t->nu*N); dalloc(&b->dOpOut, (size_t)t->nu*N); dalloc(&b->dOpF, (size_t)t->nb*6*N);
     if (ok && cudaMalloc(&a.status, N*sizeof(int)) != cudaSuccess) ok = false;
     { const size_t nblk = (N + BLK_LANES - 1)/BLK_LANES;
-      if (ok && cudaMalloc(&a.taskCounter, (1 + nblk)*sizeof(int)) != cudaSuccess) ok = false;
-      if (ok) a.blockDone = a.taskCounter + 1; }
+      if (ok && cudaMalloc(&a.taskCounter, (2 + nblk)*sizeof(int)) != cudaSuccess) ok = false;   // 64-bit task counter, then blockDone[nblk]
+      if (ok) a.blockDone = a.taskCounter + 2; }
     if (ok && cudaMalloc(&a.projCount, N*sizeof(int)) != cudaSuccess) ok = false;
     if (!ok) return bail(std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
     cudaMemsetAsync(a.status, 0, N*sizeof(int), b->stream);

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(TPI_THREADS, MINB) tpiKernel(const KArgs a) {
         // slots) then costs nsteps*512/296 rounds instead of nsteps*2.  Steps of one block are
         // ordered through blockDone[block] (release after the step, acquire before the next one);
         // tasks are claimed in order, so the task a CTA waits for is always held by a running CTA.
-        __shared__ int sTask;
+        __shared__ long long sTask;          // 64-bit: blocks x steps can exceed 2^31
         Ctx lctx; fillCtx(lctx, a, tables, true); useBlockedState(lctx, a);
         const Ctx& c = lctx;
         Tables T;
@@ -113,21 +113,21 @@ __global__ void __launch_bounds__(TPI_THREADS, MINB) tpiKernel(const KArgs a) {
         RkmWork w;
         w.y = a.yb; w.y0 = a.y0; w.f0 = a.f0; w.fa = a.fa; w.fb = a.fb; w.ys = a.ys;
         w.accuracy = a.accuracy; w.consTol = a.consTol; w.useInfNorm = a.useInfNorm; w.projectEveryStep = a.projectEveryStep;
-        const int nblk = (a.N + TPI_THREADS - 1)/TPI_THREADS, total = nblk*a.nsteps;
+        const int nblk = (a.N + TPI_THREADS - 1)/TPI_THREADS; const long long total = (long long)nblk*a.nsteps;
 #pragma unroll 1
         for (;;) {
             if (threadIdx.x == 0) {
-                const int t = atomicAdd(a.taskCounter, 1);
+                const long long t = (long long)atomicAdd(reinterpret_cast<unsigned long long*>(a.taskCounter), 1ULL);
                 if (t < total) {
-                    const int blk = t % nblk, step = t / nblk; int done;
+                    const int blk = (int)(t % nblk), step = (int)(t / nblk); int done;
                     do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(a.blockDone + blk) : "memory"); if (done < step) __nanosleep(200); } while (done < step);
                 }
                 sTask = t;
             }
             __syncthreads();
-            const int t = sTask;
+            const long long t = sTask;
             if (t >= total) break;
-            const int blk = t % nblk, step = t / nblk;
+            const int blk = (int)(t % nblk), step = (int)(t / nblk);
             const int inst = blk*TPI_THREADS + threadIdx.x;
             if (inst < a.N) {
                 if (step == 0) stateToBlocked(c, a, inst);
@@ -257,7 +257,7 @@ cudaError_t launchOp(const KArgs& a, cudaStream_t stream) {
             if (e != cudaSuccess) return e;
             if (perSm < 1) return cudaErrorLaunchOutOfResources;
             g = std::min(grid, sms*perSm);
-            e = cudaMemsetAsync(a.taskCounter, 0, sizeof(int)*(size_t)(1 + grid), stream);   // counter + blockDone[grid]
+            e = cudaMemsetAsync(a.taskCounter, 0, sizeof(int)*(size_t)(2 + grid), stream);   // 64-bit counter + blockDone[grid]
             if (e != cudaSuccess) return e;
         }
         kernel<<<g, TPI_THREADS, smemBytes, stream>>>(a);
@@ -444,14 +444,14 @@ template <int OP> cudaError_t launchLpOp(const KArgs& a, cudaStream_t stream) {
 //==============================================================================================
 constexpr int GL_THREADS = 128;
 
-__device__ __forceinline__ void gridBarrier(unsigned* bar, unsigned nblocks, unsigned& target) {
+__device__ __forceinline__ void gridBarrier(unsigned long long* bar, unsigned nblocks, unsigned long long& target) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        target += nblocks;
+        target += nblocks;                   // 64-bit: 141 barriers per step never wrap
         __threadfence();
-        atomicAdd(bar, 1u);
-        unsigned v;
-        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while (v < target);
+        atomicAdd(bar, 1ULL);
+        unsigned long long v;
+        do { asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory"); } while (v < target);
     }
     __syncthreads();
 }
@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(GL_THREADS, SBK_GL_MINB) glRkmKernel(const KAr
     const Ctx& c = sctx;
     LpLevels L; L.order = reinterpret_cast<const int*>(a.tables + a.levelOrderOff);
     L.start = reinterpret_cast<const int*>(a.tables + a.levelStartOff); L.nlevels = a.nlevels;
-    unsigned target = 0; unsigned* bar = reinterpret_cast<unsigned*>(a.taskCounter);
+    unsigned long long target = 0; unsigned long long* bar = reinterpret_cast<unsigned long long*>(a.taskCounter);
     const int N = a.N, nq = c.nq, ny = c.nq + c.nu; const long long uoff = (long long)nq*N;
     const long long tid = (long long)blockIdx.x*GL_THREADS + threadIdx.x, nth = (long long)gridDim.x*GL_THREADS, nel = (long long)ny*N;
     const double h = a.h;
@@ -580,7 +580,7 @@ cudaError_t launchGlRkmImpl(const KArgs& a, cudaStream_t stream) {
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, glRkmKernel, GL_THREADS, 0);
     if (e != cudaSuccess) return e;
     if (perSm < 1) return cudaErrorLaunchOutOfResources;
-    e = cudaMemsetAsync(a.taskCounter, 0, sizeof(int), stream);           // the barrier counter
+    e = cudaMemsetAsync(a.taskCounter, 0, 2*sizeof(int), stream);         // the 64-bit barrier counter
     if (e != cudaSuccess) return e;
     void* args[] = { const_cast<KArgs*>(&a) };
     // cooperative launch: the driver guarantees (or refuses) co-residency of the whole grid

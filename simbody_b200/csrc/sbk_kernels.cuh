@@ -42,7 +42,7 @@ struct KArgs {
     double* lastStep;   // [N] size of the last accepted step
     int* stepsTaken;    // [N] accumulated
     int* attempts;      // [N] accumulated
-    int* taskCounter;   // fixed-step integrator task queue: [0] = next task, blockDone = taskCounter + 1 .. [nblocks]
+    int* taskCounter;   // fixed-step integrator task queue: a 64-bit next-task counter (also plan 4's barrier counter); blockDone = taskCounter + 2
     int* blockDone;     // steps completed per block of 128 instances (this launch)
 };
 
