@@ -53,7 +53,7 @@ def test_topology_from_descs_and_errors():
     with pytest.raises(sb.SbkError):       # parent after child: not a tree in MobilizedBodyIndex order
         sb.Topology(bodies=[body(-1, 0, 0.0), body(2, 1), body(0, 1)])
     with pytest.raises(sb.SbkError):       # unsupported mobilizer kind
-        sb.Topology(bodies=[body(-1, 0, 0.0), body(0, 9)])
+        sb.Topology(bodies=[body(-1, 0, 0.0), body(0, 42)])
     s = capi.ForceDesc(); s.kind = 2; s.body = 1; s.coord = 0; s.a = 1.0
     with pytest.raises(sb.SbkError):       # spring on a quaternion mobilizer (reference quirk, Force.cpp:348)
         sb.Topology(bodies=[body(-1, 0, 0.0), body(0, 4)], forces=[s])
