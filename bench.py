@@ -41,7 +41,7 @@ NCU_TRAFFIC_PER_INSTANCE_STEP = {"double_pendulum_1M": 4.764e7 / (1048576 * 20),
 # view of FP64-pipe utilisation; roofline.frac below uses the reference's ALGORITHMIC flop count instead)
 NCU_FP64_PIPE_ACTIVE = {"double_pendulum_1M": 0.716, "humanoid30_64k": 0.246, "pin_chain50_64k": 0.343}
 F_EVAL = {"PIN": 1180.0, "SLIDER": 1130.0, "UNIVERSAL": 1710.0, "BALL": 2060.0, "FREE": 3800.0, "WELD": 700.0,
-          "TRANSLATION": 1800.0, "CYLINDER": 1650.0, "PLANAR": 1950.0}
+          "TRANSLATION": 1800.0, "CYLINDER": 1650.0, "PLANAR": 1950.0, "GIMBAL": 2300.0}
 
 
 def algorithmic_work(info):

@@ -61,7 +61,8 @@ enum {
     SBK_JOINT_WELD      = 6,  /* nq=0 nu=0, F and M coincide (RigidBodyNode_Weld.cpp:369)  */
     SBK_JOINT_TRANSLATION = 7, /* nq=3 nu=3, Cartesian translation in F (RigidBodyNodeSpec_Translation.h) */
     SBK_JOINT_CYLINDER  = 8,  /* nq=2 nu=2, rotation about then translation along z (RigidBodyNodeSpec_Cylinder.h) */
-    SBK_JOINT_PLANAR    = 9   /* nq=3 nu=3, rotation about z, translation x,y in F (RigidBodyNodeSpec_Planar.h)   */
+    SBK_JOINT_PLANAR    = 9,  /* nq=3 nu=3, rotation about z, translation x,y in F (RigidBodyNodeSpec_Planar.h)   */
+    SBK_JOINT_GIMBAL    = 10  /* nq=3 nu=3, body-fixed x-y-z Euler angles, u = qdot (RigidBodyNodeSpec_Gimbal.h)  */
 };
 
 /* ---- force elements (Simbody/src/Force_Gravity.cpp:514-577, Force.cpp:339-351,434-443) */

@@ -76,6 +76,7 @@ struct RefSystem {
               case SBK_JOINT_TRANSLATION: { MobilizedBody::Translation m(parent, X_PF, body, X_BM); break; }
               case SBK_JOINT_CYLINDER:  { MobilizedBody::Cylinder  m(parent, X_PF, body, X_BM); break; }
               case SBK_JOINT_PLANAR:    { MobilizedBody::Planar    m(parent, X_PF, body, X_BM); break; }
+              case SBK_JOINT_GIMBAL:    { MobilizedBody::Gimbal    m(parent, X_PF, body, X_BM); break; }
               default: throw std::runtime_error("ref_driver: bad joint type");
             }
         }

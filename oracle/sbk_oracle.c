@@ -34,7 +34,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-enum { PIN = 1, SLIDER = 2, UNIVERSAL = 3, BALL = 4, FREE = 5, WELD = 6, TRANSLATION = 7, CYLINDER = 8, PLANAR = 9 };
+enum { PIN = 1, SLIDER = 2, UNIVERSAL = 3, BALL = 4, FREE = 5, WELD = 6, TRANSLATION = 7, CYLINDER = 8, PLANAR = 9, GIMBAL = 10 };
 enum { F_GRAVITY = 1, F_SPRING = 2, F_DAMPER = 3, F_UNIFORM_GRAVITY = 4, F_GLOBAL_DAMPER = 5 };
 #define MAXD 6
 
@@ -58,8 +58,8 @@ typedef struct {   /* per-body cache, dense */
     int q0, u0, nq, nu;
 } Body;
 
-static int NQ(int j) { return j == PIN || j == SLIDER ? 1 : (j == UNIVERSAL || j == CYLINDER) ? 2 : (j == TRANSLATION || j == PLANAR) ? 3 : j == BALL ? 4 : j == FREE ? 7 : 0; }
-static int NU(int j) { return j == PIN || j == SLIDER ? 1 : (j == UNIVERSAL || j == CYLINDER) ? 2 : (j == BALL || j == TRANSLATION || j == PLANAR) ? 3 : j == FREE ? 6 : 0; }
+static int NQ(int j) { return j == PIN || j == SLIDER ? 1 : (j == UNIVERSAL || j == CYLINDER) ? 2 : (j == TRANSLATION || j == PLANAR || j == GIMBAL) ? 3 : j == BALL ? 4 : j == FREE ? 7 : 0; }
+static int NU(int j) { return j == PIN || j == SLIDER ? 1 : (j == UNIVERSAL || j == CYLINDER) ? 2 : (j == BALL || j == TRANSLATION || j == PLANAR || j == GIMBAL) ? 3 : j == FREE ? 6 : 0; }
 
 static void matvec3(const double* R, const double* v, double* o) { for (int i = 0; i < 3; ++i) o[i] = R[3*i]*v[0] + R[3*i+1]*v[1] + R[3*i+2]*v[2]; }
 static void matmul3(const double* A, const double* B, double* C) {
@@ -157,6 +157,14 @@ static void kinematics(const Model* M, Body* B, const double* q, const double* u
         } else if (jt == TRANSLATION) { pfm[0] = qb[0]; pfm[1] = qb[1]; pfm[2] = qb[2]; Hv[0][0] = Hv[1][1] = Hv[2][2] = 1;   /* _Translation.h:100-130 */
         } else if (jt == CYLINDER) {  /* _Cylinder.h:110-139 */
             double c = cos(qb[0]), s = sin(qb[0]); Rfm[0] = c; Rfm[1] = -s; Rfm[3] = s; Rfm[4] = c; pfm[2] = qb[1]; Hw[0][2] = 1; Hv[1][2] = 1;
+        } else if (jt == GIMBAL) {    /* _Gimbal.h:108-176, Rotation.h:342-349; u = qdot */
+            double c0 = cos(qb[0]), c1 = cos(qb[1]), c2 = cos(qb[2]), s0 = sin(qb[0]), s1 = sin(qb[1]), s2 = sin(qb[2]);
+            double s0s1 = s0*s1, s2c0 = s2*c0, c0c2 = c0*c2, nc1 = -c1;
+            Rfm[0] = c1*c2; Rfm[1] = s2*nc1; Rfm[2] = s1; Rfm[3] = s2c0 + s0s1*c2; Rfm[4] = c0c2 - s0s1*s2; Rfm[5] = s0*nc1;
+            Rfm[6] = s0*s2 - s1*c0c2; Rfm[7] = s0*c2 + s1*s2c0; Rfm[8] = c0*c1;
+            Hw[0][0] = 1; Hw[1][1] = c0; Hw[1][2] = s0; Hw[2][0] = s1; Hw[2][1] = -s0*c1; Hw[2][2] = c0*c1;
+            { double qd0 = ub[0], qd1 = ub[1], dc0 = -s0*qd0, dc1 = -s1*qd1, ds0 = c0*qd0, ds1 = c1*qd1;
+              HDw[1][1] = dc0; HDw[1][2] = ds0; HDw[2][0] = ds1; HDw[2][1] = -ds0*c1 - s0*dc1; HDw[2][2] = dc0*c1 + c0*dc1; }
         } else if (jt == PLANAR) {    /* _Planar.h:126-157 */
             double c = cos(qb[0]), s = sin(qb[0]); Rfm[0] = c; Rfm[1] = -s; Rfm[3] = s; Rfm[4] = c; pfm[0] = qb[1]; pfm[1] = qb[2]; Hw[0][2] = 1; Hv[1][0] = 1; Hv[2][1] = 1;
         } else {                      /* Ball / Free, quaternion (Rotation.cpp:600-611) */

@@ -37,7 +37,7 @@
 namespace sbkd {
 
 enum { JT_GROUND = 0, JT_PIN = 1, JT_SLIDER = 2, JT_UNIVERSAL = 3, JT_BALL = 4, JT_FREE = 5, JT_WELD = 6,
-       JT_TRANSLATION = 7, JT_CYLINDER = 8, JT_PLANAR = 9 };
+       JT_TRANSLATION = 7, JT_CYLINDER = 8, JT_PLANAR = 9, JT_GIMBAL = 10 };
 enum { FK_SPRING = 2, FK_DAMPER = 3 };
 
 template <int JT> struct JointDims;
@@ -50,14 +50,15 @@ template <> struct JointDims<JT_WELD>      { enum { nq = 0, nu = 0 }; };   // Ri
 template <> struct JointDims<JT_TRANSLATION> { enum { nq = 3, nu = 3 }; };
 template <> struct JointDims<JT_CYLINDER>  { enum { nq = 2, nu = 2 }; };
 template <> struct JointDims<JT_PLANAR>    { enum { nq = 3, nu = 3 }; };
+template <> struct JointDims<JT_GIMBAL>    { enum { nq = 3, nu = 3 }; };   // body-fixed x-y-z angles, u = qdot
 // array extent for a dof count that may be zero
 SBK_HD constexpr int dim1(int d) { return d > 0 ? d : 1; }
 
 // mobilizer-kind masks (bit JT_x set = kind present), see SBK_DISPATCH_JOINT_M
 enum { JM_PIN = 1 << JT_PIN, JM_SLIDER = 1 << JT_SLIDER, JM_UNIVERSAL = 1 << JT_UNIVERSAL, JM_BALL = 1 << JT_BALL, JM_FREE = 1 << JT_FREE,
-       JM_WELD = 1 << JT_WELD, JM_TRANSLATION = 1 << JT_TRANSLATION, JM_CYLINDER = 1 << JT_CYLINDER, JM_PLANAR = 1 << JT_PLANAR,
+       JM_WELD = 1 << JT_WELD, JM_TRANSLATION = 1 << JT_TRANSLATION, JM_CYLINDER = 1 << JT_CYLINDER, JM_PLANAR = 1 << JT_PLANAR, JM_GIMBAL = 1 << JT_GIMBAL,
        JM_MOBILE5 = JM_PIN | JM_SLIDER | JM_UNIVERSAL | JM_BALL | JM_FREE,       // the north_star mobilizer set
-       JM_ALL = JM_MOBILE5 | JM_WELD | JM_TRANSLATION | JM_CYLINDER | JM_PLANAR };
+       JM_ALL = JM_MOBILE5 | JM_WELD | JM_TRANSLATION | JM_CYLINDER | JM_PLANAR | JM_GIMBAL };
 
 // cache record layout
 enum { F_XGB = 0, F_VGB = 12, F_L = 18, F_MK = 21, F_ACOR = 30, F_GYRO = 36, F_ZB = 42,
@@ -241,9 +242,9 @@ template <bool BLK> SBK_HD long long stateIndex(const Ctx& c, int inst, int slot
 template <bool BLK> SBK_HD double ldS(const Ctx& c, int inst, const double* a, int slot) { return gld(a + stateIndex<BLK>(c, inst, slot)); }
 template <bool BLK> SBK_HD void   stS(const Ctx& c, int inst, double* a, int slot, double v) { gst(a + stateIndex<BLK>(c, inst, slot), v); }
 
-SBK_HD int dofOfJoint(int jt) { return jt == JT_FREE ? 6 : (jt == JT_BALL || jt == JT_TRANSLATION || jt == JT_PLANAR) ? 3 : (jt == JT_UNIVERSAL || jt == JT_CYLINDER) ? 2
+SBK_HD int dofOfJoint(int jt) { return jt == JT_FREE ? 6 : (jt == JT_BALL || jt == JT_TRANSLATION || jt == JT_PLANAR || jt == JT_GIMBAL) ? 3 : (jt == JT_UNIVERSAL || jt == JT_CYLINDER) ? 2
                                       : (jt == JT_GROUND || jt == JT_WELD) ? 0 : 1; }
-SBK_HD int nqOfJoint(int jt)  { return jt == JT_FREE ? 7 : jt == JT_BALL ? 4 : (jt == JT_TRANSLATION || jt == JT_PLANAR) ? 3 : (jt == JT_UNIVERSAL || jt == JT_CYLINDER) ? 2
+SBK_HD int nqOfJoint(int jt)  { return jt == JT_FREE ? 7 : jt == JT_BALL ? 4 : (jt == JT_TRANSLATION || jt == JT_PLANAR || jt == JT_GIMBAL) ? 3 : (jt == JT_UNIVERSAL || jt == JT_CYLINDER) ? 2
                                       : (jt == JT_GROUND || jt == JT_WELD) ? 0 : 1; }
 SBK_HD M3 loadR(const double* X) { M3 R;
 #pragma unroll
@@ -299,6 +300,7 @@ template <int d> struct KinLocal {
     V3 r;                            // r_MB_F = R_FM * p_MB
     M3 R_PB; V3 p_PB;                // X_PB
     double qerr;                     // |q| - 1 for quaternion mobilizers
+    double sc[4];                    // Gimbal: c0, s0, c1, s1 (the reference's q pool, _Gimbal.h:108-126)
 };
 
 template <int JT>
@@ -318,6 +320,14 @@ SBK_HD void kinLocal(const BodyConst& bc, const double* q, KinLocal<JointDims<JT
         k.Hw[0] = mk(0, 0, 1);
         if constexpr (JT == JT_CYLINDER) { p_FM = mk(0, 0, q[1]); k.Hv[1] = mk(0, 0, 1); }
         if constexpr (JT == JT_PLANAR)   { p_FM = mk(q[1], q[2], 0); k.Hv[1] = mk(1, 0, 0); k.Hv[2] = mk(0, 1, 0); }
+    } else if constexpr (JT == JT_GIMBAL) {       // RigidBodyNodeSpec_Gimbal.h:108-176, Rotation.h:342-349
+        double s0, c0, s1, c1, s2, c2; sincos(q[0], &s0, &c0); sincos(q[1], &s1, &c1); sincos(q[2], &s2, &c2);
+        const double s0s1 = s0*s1, s2c0 = s2*c0, c0c2 = c0*c2, nc1 = -c1;
+        R_FM.a[0] = c1*c2;             R_FM.a[1] = s2*nc1;            R_FM.a[2] = s1;
+        R_FM.a[3] = s2c0 + s0s1*c2;    R_FM.a[4] = c0c2 - s0s1*s2;    R_FM.a[5] = s0*nc1;
+        R_FM.a[6] = s0*s2 - s1*c0c2;   R_FM.a[7] = s0*c2 + s1*s2c0;   R_FM.a[8] = c0*c1;
+        k.Hw[0] = mk(1, 0, 0); k.Hw[1] = mk(0, c0, s0); k.Hw[2] = mk(s1, -s0*c1, c0*c1);
+        k.sc[0] = c0; k.sc[1] = s0; k.sc[2] = c1; k.sc[3] = s1;
     } else if constexpr (JT == JT_TRANSLATION) {  // RigidBodyNodeSpec_Translation.h:100-130
         R_FM = identity3(); p_FM = mk(q[0], q[1], q[2]);
         k.Hv[0] = mk(1, 0, 0); k.Hv[1] = mk(0, 1, 0); k.Hv[2] = mk(0, 0, 1);
@@ -390,6 +400,10 @@ SBK_HD void jointH(const M3& R_GF, const KinLocal<JointDims<JT>::nu>& k, SV* H) 
     else if constexpr (JT == JT_UNIVERSAL) {
         SBK_ROTCOL(0, 0)
         H[1].w = mul(R_GF, k.Hw[1]); H[1].v = mul(R_GF, cross(k.Hw[1], r));
+    } else if constexpr (JT == JT_GIMBAL) {
+        SBK_ROTCOL(0, 0)
+        H[1].w = mul(R_GF, k.Hw[1]); H[1].v = mul(R_GF, cross(k.Hw[1], r));
+        H[2].w = mul(R_GF, k.Hw[2]); H[2].v = mul(R_GF, cross(k.Hw[2], r));
     } else {
         SBK_ROTCOL(0, 0) SBK_ROTCOL(1, 1) SBK_ROTCOL(2, 2)
         if constexpr (JT == JT_FREE) { SBK_TRCOL(3, 0) SBK_TRCOL(4, 1) SBK_TRCOL(5, 2) }
@@ -402,6 +416,7 @@ template <int JT> SBK_HD V3 jointWFM(const KinLocal<JointDims<JT>::nu>& k, const
     if constexpr (JT == JT_PIN || JT == JT_CYLINDER || JT == JT_PLANAR) return mk(0, 0, u[0]);
     else if constexpr (JT == JT_SLIDER || JT == JT_WELD || JT == JT_TRANSLATION) return zero3();
     else if constexpr (JT == JT_UNIVERSAL) return mk(u[0], 0, 0) + u[1]*k.Hw[1];
+    else if constexpr (JT == JT_GIMBAL) return (mk(u[0], 0, 0) + u[1]*k.Hw[1]) + u[2]*k.Hw[2];
     else return mk(u[0], u[1], u[2]);
 }
 
@@ -455,6 +470,18 @@ SBK_HD void kinGlobal(const BodyConst& bc, const KinLocal<JointDims<JT>::nu>& k,
         HD.w = mul(R_GF, HDw1) + cross(w_GP, o.H[1].w);
         HD.v = mul(R_GF, cross(HDw1, r) + cross(k.Hw[1], wxr)) + cross(w_GP, o.H[1].v);
         VD = VD + u[1]*HD;
+    } else if constexpr (JT == JT_GIMBAL) {          // _Gimbal.h:150-176 with qdot = u
+        SBK_ROTCOL_D(0, 0)
+        const double c0 = k.sc[0], s0 = k.sc[1], c1 = k.sc[2], s1 = k.sc[3];
+        const double dc0 = -s0*u[0], dc1 = -s1*u[1], ds0 = c0*u[0], ds1 = c1*u[1];
+        const V3 HDwj[2] = { mk(0, dc0, ds0), mk(ds1, -ds0*c1 - s0*dc1, dc0*c1 + c0*dc1) };
+#pragma unroll
+        for (int j = 1; j < 3; ++j) {
+            SV HD;
+            HD.w = mul(R_GF, HDwj[j-1]) + cross(w_GP, o.H[j].w);
+            HD.v = mul(R_GF, cross(HDwj[j-1], r) + cross(k.Hw[j], wxr)) + cross(w_GP, o.H[j].v);
+            VD = VD + u[j]*HD;
+        }
     } else {
         SBK_ROTCOL_D(0, 0) SBK_ROTCOL_D(1, 1) SBK_ROTCOL_D(2, 2)
         if constexpr (JT == JT_FREE) { SBK_TRCOL_D(3) SBK_TRCOL_D(4) SBK_TRCOL_D(5) }
@@ -1081,6 +1108,7 @@ SBK_BODY void idInBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, c
         case JT_TRANSLATION: { constexpr int JT = JT_TRANSLATION; CALL; } break;    \
         case JT_CYLINDER:  { constexpr int JT = JT_CYLINDER;  CALL; } break;        \
         case JT_PLANAR:    { constexpr int JT = JT_PLANAR;    CALL; } break;        \
+        case JT_GIMBAL:    { constexpr int JT = JT_GIMBAL;    CALL; } break;        \
         default: break;                                                             \
     }
 
@@ -1110,6 +1138,7 @@ template <bool WITH_COR> SBK_HD void outwardDispatch(const Ctx& c, int b, int in
         case JT_TRANSLATION: if constexpr (((JMASK) & JM_TRANSLATION) != 0) { constexpr int JT = JT_TRANSLATION; CALL; } break; \
         case JT_CYLINDER:  if constexpr (((JMASK) & JM_CYLINDER) != 0)  { constexpr int JT = JT_CYLINDER;  CALL; } break; \
         case JT_PLANAR:    if constexpr (((JMASK) & JM_PLANAR) != 0)    { constexpr int JT = JT_PLANAR;    CALL; } break; \
+        case JT_GIMBAL:    if constexpr (((JMASK) & JM_GIMBAL) != 0)    { constexpr int JT = JT_GIMBAL;    CALL; } break; \
         default: break;                                                                                             \
     }
 

@@ -21,7 +21,7 @@ void compileTopology(const ModelSpec& spec, sbk_topology& t) {
         if (d.parent < 0 || d.parent >= b)
             throw std::runtime_error("topology: body " + std::to_string(b) + " has parent " + std::to_string(d.parent) +
                                      "; a tree needs 0 <= parent < body index");
-        if (d.joint_type < SBK_JOINT_PIN || d.joint_type > SBK_JOINT_PLANAR)
+        if (d.joint_type < SBK_JOINT_PIN || d.joint_type > SBK_JOINT_GIMBAL)
             throw std::runtime_error("topology: body " + std::to_string(b) + " has unsupported mobilizer kind " + std::to_string(d.joint_type));
         if (!(d.mass > 0)) throw std::runtime_error("topology: body " + std::to_string(b) + " needs mass > 0");
         if (d.parent != b - 1) chain = false;

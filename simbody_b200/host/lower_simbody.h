@@ -69,8 +69,9 @@ inline ModelSpec lowerSimbodySystem(const SimTK::MultibodySystem&        system,
         else if (MobilizedBody::Translation::isInstanceOf(mobod)) b.joint_type = SBK_JOINT_TRANSLATION;
         else if (MobilizedBody::Cylinder::isInstanceOf(mobod))  b.joint_type = SBK_JOINT_CYLINDER;
         else if (MobilizedBody::Planar::isInstanceOf(mobod))    b.joint_type = SBK_JOINT_PLANAR;
+        else if (MobilizedBody::Gimbal::isInstanceOf(mobod))    b.joint_type = SBK_JOINT_GIMBAL;
         else throw std::runtime_error("lowerSimbodySystem: body " + std::to_string((int)mbx) +
-                                      " uses a mobilizer outside {Pin,Slider,Universal,Ball,Free,Weld,Translation,Cylinder,Planar}");
+                                      " uses a mobilizer outside {Pin,Slider,Universal,Ball,Free,Weld,Translation,Cylinder,Planar,Gimbal}");
         // NOTE: the public API has no getter for MobilizedBody::Direction; reversed mobilizers
         // are out of scope and must not be used with this lowering.
         const MassProperties& mp = mobod.getDefaultMassProperties();

@@ -32,18 +32,20 @@ struct ModelSpec {
 
 inline int jointNQ(int jt) {
     switch (jt) { case SBK_JOINT_PIN: case SBK_JOINT_SLIDER: return 1; case SBK_JOINT_UNIVERSAL: case SBK_JOINT_CYLINDER: return 2;
-                  case SBK_JOINT_TRANSLATION: case SBK_JOINT_PLANAR: return 3;
+                  case SBK_JOINT_TRANSLATION: case SBK_JOINT_PLANAR: case SBK_JOINT_GIMBAL: return 3;
                   case SBK_JOINT_BALL: return 4; case SBK_JOINT_FREE: return 7; default: return 0; }
 }
 inline int jointNU(int jt) {
     switch (jt) { case SBK_JOINT_PIN: case SBK_JOINT_SLIDER: return 1; case SBK_JOINT_UNIVERSAL: case SBK_JOINT_CYLINDER: return 2;
-                  case SBK_JOINT_BALL: case SBK_JOINT_TRANSLATION: case SBK_JOINT_PLANAR: return 3; case SBK_JOINT_FREE: return 6; default: return 0; }
+                  case SBK_JOINT_BALL: case SBK_JOINT_TRANSLATION: case SBK_JOINT_PLANAR: case SBK_JOINT_GIMBAL: return 3;
+                  case SBK_JOINT_FREE: return 6; default: return 0; }
 }
 inline const char* jointName(int jt) {
     switch (jt) { case SBK_JOINT_GROUND: return "GROUND"; case SBK_JOINT_PIN: return "PIN";
                   case SBK_JOINT_SLIDER: return "SLIDER"; case SBK_JOINT_UNIVERSAL: return "UNIVERSAL";
                   case SBK_JOINT_BALL: return "BALL"; case SBK_JOINT_FREE: return "FREE"; case SBK_JOINT_WELD: return "WELD";
                   case SBK_JOINT_TRANSLATION: return "TRANSLATION"; case SBK_JOINT_CYLINDER: return "CYLINDER"; case SBK_JOINT_PLANAR: return "PLANAR";
+                  case SBK_JOINT_GIMBAL: return "GIMBAL";
                   default: return "?"; }
 }
 inline int jointFromName(const std::string& s) {
@@ -52,6 +54,7 @@ inline int jointFromName(const std::string& s) {
     if (s == "BALL") return SBK_JOINT_BALL; if (s == "FREE") return SBK_JOINT_FREE;
     if (s == "WELD") return SBK_JOINT_WELD; if (s == "TRANSLATION") return SBK_JOINT_TRANSLATION;
     if (s == "CYLINDER") return SBK_JOINT_CYLINDER; if (s == "PLANAR") return SBK_JOINT_PLANAR;
+    if (s == "GIMBAL") return SBK_JOINT_GIMBAL;
     throw std::runtime_error("unknown joint name " + s);
 }
 
@@ -284,14 +287,15 @@ inline ModelSpec makeWelded8() {
     return m;
 }
 
-// Planar -> Cylinder -> Translation -> Pin chain with a Slider branch: the axis-aligned mobilizers with
+// Planar -> Cylinder -> Translation -> Pin -> Gimbal chain with Slider and Cylinder branches: the axis-aligned mobilizers with
 // Cartesian coordinates, general frames, a spring on a translational and one on a rotational coordinate.
-inline ModelSpec makeCartesian6() {
-    ModelSpec m = makeMixed7(); m.name = "cartesian6";
+inline ModelSpec makeCartesian8() {
+    ModelSpec m = makeMixed7(); m.name = "cartesian8";
     m.bodies[1].joint_type = SBK_JOINT_PLANAR; m.bodies[2].joint_type = SBK_JOINT_CYLINDER;
     m.bodies[3].joint_type = SBK_JOINT_TRANSLATION; m.bodies[4].joint_type = SBK_JOINT_PIN; m.bodies[5].joint_type = SBK_JOINT_SLIDER;
     m.bodies[5].parent = 2;
     m.bodies[6].joint_type = SBK_JOINT_CYLINDER;
+    sbk_body_desc g = m.bodies[4]; g.parent = 4; g.joint_type = SBK_JOINT_GIMBAL; m.bodies.push_back(g);   // body 7: Gimbal off the Pin
     m.forces.clear();
     m.forces.push_back(gravityForce(9.81, 0, -1, 0));
     m.forces.push_back(springForce(3, 1, 25.0, 0.1));
@@ -306,7 +310,7 @@ inline ModelSpec makeNamedModel(const std::string& name, int n) {
     if (name == "mixed7")          return makeMixed7();
     if (name == "ugdamp5")         return makeUgDamp5();
     if (name == "welded8")         return makeWelded8();
-    if (name == "cartesian6")      return makeCartesian6();
+    if (name == "cartesian8")      return makeCartesian8();
     if (name == "humanoid30")      return makeHumanoid30();
     if (name == "branched_tree")   return makeBranchedTree(n > 0 ? n : 1000);
     throw std::runtime_error("unknown model '" + name + "'");

@@ -22,7 +22,7 @@ CASES = [  # name, size param, n eval states, (h, nsteps), q_scale
     ("mixed7", 0, 8, (1e-3, 25), 1.0),
     ("ugdamp5", 0, 6, (1e-3, 20), 0.7),          # Force::UniformGravity + Force::GlobalDamper
     ("welded8", 0, 6, (1e-3, 20), 0.7),          # MobilizedBody::Weld inside the chain and as a leaf
-    ("cartesian6", 0, 6, (1e-3, 20), 0.7),       # MobilizedBody::Planar / Cylinder / Translation
+    ("cartesian8", 0, 6, (1e-3, 20), 0.7),       # MobilizedBody::Planar / Cylinder / Translation
     ("humanoid30", 0, 4, (1e-3, 10), 0.5),
     ("branched_tree", 100, 2, (5e-4, 4), 0.5),
 ]
