@@ -234,11 +234,20 @@ def main():
         max_err, nbad, _ = reduce_stats(float(np.nanmax(errn)), int(nbad), ms, dist if world > 1 else None, device="cuda")
         flop, byts = algorithmic_work(info)
         plan = bm.getPlan()
+        # operator form of the same path: System::realize(Acceleration) on the resident state (FULL records)
+        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+        lib.sbk_state_touched(bm.handle); sb.capi.check(lib, lib.sbk_realize_acceleration(bm.handle))
+        barrier(); ev0.record(stream)
+        nrep = 5
+        for _ in range(nrep):
+            lib.sbk_state_touched(bm.handle); sb.capi.check(lib, lib.sbk_realize_acceleration(bm.handle))
+        ev1.record(stream); barrier()
+        realize_per_s = world * N * nrep / (ev0.elapsed_time(ev1) * 1e-3)
         res = {"name": name, "info": info, "N": N, "spl": spl, "ms_per_step": ms_max / steps, "plan": plan,
                "value": world * N * spl * steps / (ms_max * 1e-3),
                "e2e": world * N * spl * e2e_steps / (e2e_ms_max * 1e-3),
                "h2d": 8 * ny * N, "d2h": 8 * ny * N, "launches": launches, "kernel_ms_last": kern_ms[-1],
-               "flop_per_inst_step": flop, "bytes_per_inst_step": byts, "clocks": clocks_summary(samples), "nbad": int(nbad), "max_err_norm": max_err}
+               "flop_per_inst_step": flop, "bytes_per_inst_step": byts, "realize_per_s": realize_per_s, "clocks": clocks_summary(samples), "nbad": int(nbad), "max_err_norm": max_err}
         bm.close(); topo.close()
         return res
 
@@ -279,7 +288,8 @@ def main():
                        "rkm_steps_per_bench_step": r["spl"], "integrator": "RungeKuttaMerson fixed step, 5 evals/step",
                        "l2": "state+cache working set exceeds L2 for every workload but branched_tree; no flush needed"},
             "e2e": {"value": r["e2e"], "unit": "instance-steps/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
-            "gpu_launches": r["launches"], "clocks": r["clocks"], "roofline": roofline, "non_finite_instances": r["nbad"], "max_err_norm_last_step": r["max_err_norm"]}
+            "gpu_launches": r["launches"], "clocks": r["clocks"], "roofline": roofline,
+            "realize_acceleration_per_s": r["realize_per_s"], "non_finite_instances": r["nbad"], "max_err_norm_last_step": r["max_err_norm"]}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from _harness import RefDriver, have_ref
@@ -304,7 +314,8 @@ def main():
             rr = measure(name, dict(WORKLOADS[name]), max(3, args.steps // 2), args.warmup, 0)
             tf = rr["value"] / world * rr["flop_per_inst_step"] / 1e12
             extra[name] = {"value": rr["value"], "e2e": rr["e2e"], "ms_per_step": rr["ms_per_step"], "fp64_frac": tf / fp64_peak_tflops,
-                           "achieved_tflops": tf, "rkm_steps_per_bench_step": rr["spl"], "instances_per_gpu": rr["N"]}
+                           "achieved_tflops": tf, "rkm_steps_per_bench_step": rr["spl"], "instances_per_gpu": rr["N"],
+                           "realize_acceleration_per_s": rr["realize_per_s"], "plan": rr["plan"]}
         line["workloads"] = extra
 
     if rank == 0:

@@ -58,6 +58,11 @@ enum KernelOp {
 
 // Launch one operation for the thread-per-instance plan on `stream`.
 cudaError_t launchTpi(KernelOp op, const KArgs& a, cudaStream_t stream);
+// Integrator kernels of the thread-per-instance plan, one family per set of mobilizer kinds (op = OP_RKM / OP_RKM_ADAPT).
+cudaError_t launchTpiRkmPin(KernelOp op, const KArgs& a, cudaStream_t stream);      // Pin only
+cudaError_t launchTpiRkmLight(KernelOp op, const KArgs& a, cudaStream_t stream);    // Pin / Slider / Universal / Weld
+cudaError_t launchTpiRkmMobile5(KernelOp op, const KArgs& a, cudaStream_t stream);  // Pin / Slider / Universal / Ball / Free
+cudaError_t launchTpiRkmAll(KernelOp op, const KArgs& a, cudaStream_t stream);      // every supported mobilizer
 // Register-resident fused plan (serial chains of 1-2 Pin/Slider[/Universal] mobilizers).
 bool fusedPlanSupports(int nb, const int* joints /*[nb]*/);
 cudaError_t launchFusedRkm(const KArgs& a, const int* joints, bool adaptive, cudaStream_t stream);

@@ -57,6 +57,7 @@ SBK_HD constexpr int dim1(int d) { return d > 0 ? d : 1; }
 // mobilizer-kind masks (bit JT_x set = kind present), see SBK_DISPATCH_JOINT_M
 enum { JM_PIN = 1 << JT_PIN, JM_SLIDER = 1 << JT_SLIDER, JM_UNIVERSAL = 1 << JT_UNIVERSAL, JM_BALL = 1 << JT_BALL, JM_FREE = 1 << JT_FREE,
        JM_WELD = 1 << JT_WELD, JM_TRANSLATION = 1 << JT_TRANSLATION, JM_CYLINDER = 1 << JT_CYLINDER, JM_PLANAR = 1 << JT_PLANAR, JM_GIMBAL = 1 << JT_GIMBAL,
+       JM_LIGHT = JM_PIN | JM_SLIDER | JM_UNIVERSAL | JM_WELD,                   // dof <= 2
        JM_MOBILE5 = JM_PIN | JM_SLIDER | JM_UNIVERSAL | JM_BALL | JM_FREE,       // the north_star mobilizer set
        JM_ALL = JM_MOBILE5 | JM_WELD | JM_TRANSLATION | JM_CYLINDER | JM_PLANAR | JM_GIMBAL };
 

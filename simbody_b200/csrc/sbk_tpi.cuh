@@ -1,0 +1,227 @@
+// sbk_tpi.cuh -- the thread-per-instance kernel template (API operations and the integrator), shared by the
+// translation units that instantiate it: sbk_kernels.cu (API operations) and sbk_rkm_{pin,light,mobile5,all}.cu
+// (one integrator kernel family per set of mobilizer kinds, compiled in parallel).
+#pragma once
+#include <algorithm>
+#include "sbk_kernels.cuh"
+
+namespace sbkd {
+namespace {
+
+#ifndef SBK_TPI_THREADS
+#define SBK_TPI_THREADS 128
+#endif
+#ifndef SBK_TPI_MINBLOCKS
+#define SBK_TPI_MINBLOCKS 2
+#endif
+#ifndef SBK_HEAVY_MINB
+#define SBK_HEAVY_MINB 2
+#endif
+constexpr int TPI_THREADS = SBK_TPI_THREADS;
+constexpr int SBK_CARRY_STRIDE_DEVICE = 128;
+
+__device__ __forceinline__ uint32_t smemAddr(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// Stage `bytes` (multiple of 16) from global to shared with one TMA bulk copy.
+__device__ __forceinline__ void tmaStage(void* dst, const void* src, uint32_t bytes, uint64_t* mbar) {
+    const uint32_t bar = smemAddr(mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smemAddr(dst)), "l"(src), "r"(bytes), "r"(bar) : "memory");
+    }
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar) : "memory");
+    }
+}
+
+__device__ __forceinline__ void fillCtx(Ctx& c, const KArgs& a, const unsigned char* tables, bool integrator) {
+    c.bodies   = reinterpret_cast<const BodyConst*>(tables);
+    c.children = reinterpret_cast<const int*>(tables + a.childrenOff);
+    c.forces   = reinterpret_cast<const ForceConst*>(tables + a.forcesOff);
+    c.nb = a.nb; c.nq = a.nq; c.nu = a.nu; c.nquat = a.nquat;
+    c.gx = a.gx; c.gy = a.gy; c.gz = a.gz;
+    c.cache = a.cache; c.cStride = a.cStride; c.cInstStride = a.cInstStride; c.cSpan = a.cSpan; c.cShift = a.cShift; c.cMask = a.cMask;
+    c.sStride = a.N; c.sInstStride = 1; c.sSpan = (long long)(a.nq + a.nu)*BLK_LANES;
+    c.q = a.y; c.u = a.y + (long long)a.nq*a.N;
+    c.qdot = a.ydot; c.udot = a.ydot ? a.ydot + (long long)a.nq*a.N : nullptr;
+    c.qdotdot = a.qdotdot; c.qerr = a.qerr;
+    c.fmobIn = a.fmobIn; c.FbodyIn = a.FbodyIn; c.fmobOut = a.fmobOut; c.FbodyOut = a.FbodyOut;
+    c.vecIn = a.vecIn; c.vecOut = a.vecOut;
+    c.status = a.status;
+    if (integrator) { c.qdotdot = nullptr; c.qerr = nullptr; c.fmobOut = nullptr; c.FbodyOut = nullptr; }
+}
+// Thread-per-instance integrator kernels work on a CTA-blocked copy of the state ([block][slot][lane]).
+__device__ __forceinline__ void useBlockedState(Ctx& c, const KArgs& a) { c.q = a.yb; c.u = a.yb + (long long)a.nq*BLK_LANES; }
+__device__ __forceinline__ void stateToBlocked(const Ctx& c, const KArgs& a, int inst) {
+    const int ny = a.nq + a.nu;
+#pragma unroll 8
+    for (int i = 0; i < ny; ++i) a.yb[stateIndex<true>(c, inst, i)] = __ldcg(a.y + (long long)i*a.N + inst);
+}
+__device__ __forceinline__ void stateFromBlocked(const Ctx& c, const KArgs& a, int inst) {
+    const int ny = a.nq + a.nu;
+#pragma unroll 8
+    for (int i = 0; i < ny; ++i) __stcg(a.y + (long long)i*a.N + inst, a.yb[stateIndex<true>(c, inst, i)]);
+}
+
+// MINB = resident CTAs per SM the register allocation is sized for: 4 (128 registers) suits
+// models made of 1-2 dof mobilizers, 2 (255 registers) models with Ball/Free bodies, whose 3x3 /
+// 6x6 articulated-inertia algebra would otherwise spill (measured: +46% on the humanoid).
+template <int OP, bool STAGE, int MINB, int JMASK = JM_ALL>
+__global__ void __launch_bounds__(TPI_THREADS, MINB) tpiKernel(const KArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ Ctx sctx;                      // ONE context per CTA, read with LDS by every body step
+    const unsigned char* tables = a.tables;
+    if constexpr (STAGE) { tmaStage(smem, a.tables, a.tableBytes, &mbar); tables = smem; }
+    constexpr bool INTEG = OP == OP_RKM || OP == OP_RKM_ADAPT;
+    if (!INTEG && threadIdx.x == 0) fillCtx(sctx, a, tables, false);
+    __syncthreads();
+    if constexpr (OP == OP_RKM) {
+        // Fixed-step integrator: PERSISTENT CTAs (the grid is what fits the machine at once) pull
+        // (block of 128 instances, step) tasks from a global counter, step-major.  A batch whose
+        // CTA count is not a multiple of the resident slots (65536 instances = 512 CTAs on 296
+        // slots) then costs nsteps*512/296 rounds instead of nsteps*2.  Steps of one block are
+        // ordered through blockDone[block] (release after the step, acquire before the next one);
+        // tasks are claimed in order, so the task a CTA waits for is always held by a running CTA.
+        __shared__ long long sTask;          // 64-bit: blocks x steps can exceed 2^31
+        Ctx lctx; fillCtx(lctx, a, tables, true); useBlockedState(lctx, a);
+        const Ctx& c = lctx;
+        Tables T;
+        T.bodies = reinterpret_cast<const BodyConst*>(tables); T.children = reinterpret_cast<const int*>(tables + a.childrenOff);
+        T.forces = reinterpret_cast<const ForceConst*>(tables + a.forcesOff);
+        double* cy = reinterpret_cast<double*>(smem + (STAGE ? a.tableBytes : 0)) + threadIdx.x;
+        RkmWork w;
+        w.y = a.yb; w.y0 = a.y0; w.f0 = a.f0; w.fa = a.fa; w.fb = a.fb; w.ys = a.ys;
+        w.accuracy = a.accuracy; w.consTol = a.consTol; w.useInfNorm = a.useInfNorm; w.projectEveryStep = a.projectEveryStep;
+        const int nblk = (a.N + TPI_THREADS - 1)/TPI_THREADS; const long long total = (long long)nblk*a.nsteps;
+#pragma unroll 1
+        for (;;) {
+            if (threadIdx.x == 0) {
+                const long long t = (long long)atomicAdd(reinterpret_cast<unsigned long long*>(a.taskCounter), 1ULL);
+                if (t < total) {
+                    const int blk = (int)(t % nblk), step = (int)(t / nblk); int done;
+                    do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(a.blockDone + blk) : "memory"); if (done < step) __nanosleep(200); } while (done < step);
+                }
+                sTask = t;
+            }
+            __syncthreads();
+            const long long t = sTask;
+            if (t >= total) break;
+            const int blk = (int)(t % nblk), step = (int)(t / nblk);
+            const int inst = blk*TPI_THREADS + threadIdx.x;
+            if (inst < a.N) {
+                if (step == 0) stateToBlocked(c, a, inst);
+                const RkmStepResult r = tpiRkmStep<true, JMASK>(c, T, inst, w, a.h, cy);
+                a.tcur[inst] += a.h;
+                if (r.projected) a.projCount[inst] += 1;
+                if (step == a.nsteps - 1) {
+                    stateFromBlocked(c, a, inst);
+                    a.errNorm[inst] = r.errNorm;
+                }
+                if (a.status && !(r.errNorm == r.errNorm)) atomicOr(a.status + inst, 1);   // NaN error norm
+            }
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(a.blockDone + blk), "r"(step + 1) : "memory");
+        }
+        return;
+    }
+    const int inst = blockIdx.x*blockDim.x + threadIdx.x;
+    if (inst >= a.N) return;
+    // API kernels read the context from shared memory; the integrator kernels keep it as a local whose
+    // members are kernel parameters (constant bank operands) or one add away from them -- reading
+    // it from shared memory cost a generic load plus descriptor moves per access (ncu).
+    Ctx lctx;
+    if constexpr (INTEG) { fillCtx(lctx, a, tables, true); useBlockedState(lctx, a); }
+    const Ctx& c = INTEG ? lctx : sctx;
+    Tables T;                                  // address space known at compile time: shared if staged, else global
+    T.bodies = reinterpret_cast<const BodyConst*>(tables); T.children = reinterpret_cast<const int*>(tables + a.childrenOff);
+    T.forces = reinterpret_cast<const ForceConst*>(tables + a.forcesOff);
+    // LEAN carry: a [CARRY_ROWS][128] block of shared memory behind the staged tables
+    double* cy = nullptr;
+    if constexpr (OP == OP_RKM || OP == OP_RKM_ADAPT) cy = reinterpret_cast<double*>(smem + (STAGE ? a.tableBytes : 0)) + threadIdx.x;
+
+    if constexpr (OP == OP_KIN) {
+        tpiKinematics(c, inst, c.qdot);
+    } else if constexpr (OP == OP_ABI) {
+        tpiInward<IN_ABI>(c, inst);
+    } else if constexpr (OP == OP_EVAL) {
+        tpiEvalDerivatives<false>(c, tablesOf(c), inst, cy, c.qdot, c.udot, c.qdotdot);
+    } else if constexpr (OP == OP_CALCACC) {
+        tpiInward<IN_Z | IN_BIAS>(c, inst);
+        tpiOutward<true>(c, inst, c.vecOut, nullptr);
+    } else if constexpr (OP == OP_MULM) {
+        for (int b = 1; b < c.nb; ++b) idOutDispatch<false>(c, b, inst);
+        for (int b = c.nb - 1; b >= 1; --b) idInDispatch<false>(c, b, inst);
+    } else if constexpr (OP == OP_MULMINV) {
+        tpiInward<IN_Z>(c, inst);             // c.fmobIn == a.vecIn, c.FbodyIn == null (set by the host)
+        tpiOutward<false>(c, inst, c.vecOut, nullptr);
+    } else if constexpr (OP == OP_RESID) {
+        for (int b = 1; b < c.nb; ++b) idOutDispatch<true>(c, b, inst);
+        for (int b = c.nb - 1; b >= 1; --b) idInDispatch<true>(c, b, inst);
+    } else if constexpr (OP == OP_RKM_ADAPT) {
+        RkmWork w;
+        w.y = a.yb; w.y0 = a.y0; w.f0 = a.f0; w.fa = a.fa; w.fb = a.fb; w.ys = a.ys;
+        w.accuracy = a.accuracy; w.consTol = a.consTol; w.useInfNorm = a.useInfNorm; w.projectEveryStep = a.projectEveryStep;
+        stateToBlocked(c, a, inst);
+        StepLimits lim; lim.accuracy = a.accuracy; lim.minStep = a.minStep; lim.maxStep = a.maxStep;
+        AdaptiveState st; st.t = a.tcur[inst]; st.h = a.hcur[inst]; st.lastStep = a.lastStep[inst]; st.steps = 0; st.attempts = 0;
+        double lastErr = a.errNorm[inst]; int nproj = 0;
+        tpiRkmAdaptive<true, JMASK>(c, T, inst, w, lim, a.tFinal, a.allowInterp, a.maxAttempts, st, cy, lastErr, nproj);
+        stateFromBlocked(c, a, inst);
+        a.tcur[inst] = st.t; a.hcur[inst] = st.h; a.lastStep[inst] = st.lastStep;
+        a.stepsTaken[inst] += st.steps; a.attempts[inst] += st.attempts;
+        a.errNorm[inst] = lastErr; a.projCount[inst] += nproj;
+        if (a.status && st.t < a.tFinal) atomicOr(a.status + inst, 4);              // attempt budget exhausted
+    }
+}
+
+// Launch one thread-per-instance operation.  JMASK only matters for the integrator kernels.
+template <int OP, int MINB, int JMASK>
+cudaError_t launchOp(const KArgs& a, cudaStream_t stream) {
+    static_assert(TPI_THREADS == SBK_CARRY_STRIDE_DEVICE, "carry columns are laid out for 128-thread CTAs");
+    const int grid = (a.N + TPI_THREADS - 1)/TPI_THREADS;
+    const size_t carryBytes = (OP == OP_RKM || OP == OP_RKM_ADAPT) ? (size_t)CARRY_ROWS*TPI_THREADS*sizeof(double) : 0;
+    const size_t smemBytes = (a.stageInSmem ? a.tableBytes : 0) + carryBytes;
+    auto go = [&](auto kernel) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
+        if (e != cudaSuccess) return e;
+        int g = grid;
+        if constexpr (OP == OP_RKM) {             // persistent: as many CTAs as are resident at once
+            int dev = 0, sms = 0, perSm = 0;
+            cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, TPI_THREADS, smemBytes);
+            if (e != cudaSuccess) return e;
+            if (perSm < 1) return cudaErrorLaunchOutOfResources;
+            g = std::min(grid, sms*perSm);
+            e = cudaMemsetAsync(a.taskCounter, 0, sizeof(int)*(size_t)(2 + grid), stream);   // 64-bit counter + blockDone[grid]
+            if (e != cudaSuccess) return e;
+        }
+        kernel<<<g, TPI_THREADS, smemBytes, stream>>>(a);
+        return cudaGetLastError();
+    };
+    return a.stageInSmem ? go(tpiKernel<OP, true, MINB, JMASK>) : go(tpiKernel<OP, false, MINB, JMASK>);
+}
+// Body of one integrator translation unit (sbk_rkm_<variant>.cu)
+#define SBK_DEFINE_RKM_VARIANT(NAME, MINB, JMASK)                                                   \
+    namespace sbkd {                                                                                \
+    cudaError_t NAME(KernelOp op, const KArgs& a, cudaStream_t stream) {                            \
+        if (op == OP_RKM)       return launchOp<OP_RKM, MINB, JMASK>(a, stream);                    \
+        if (op == OP_RKM_ADAPT) return launchOp<OP_RKM_ADAPT, MINB, JMASK>(a, stream);              \
+        return cudaErrorInvalidValue;                                                               \
+    } }
+
+} // namespace
+} // namespace sbkd
