@@ -21,7 +21,7 @@ struct Chain2 {
            NQ = NQ0 + NQ1, NU = D0 + D1, NY = NQ + NU, NB = 3 };
     const BodyConst* b0; const BodyConst* b1; const ForceConst* forces; double gx, gy, gz;
 
-    SBK_HDN void eval(const double* y, double* ydot) const {
+    SBK_HD void eval(const double* y, double* ydot) const {
         const double* q0 = y; const double* q1 = y + NQ0; const double* u0 = y + NQ; const double* u1 = y + NQ + D0;
         double qe;
         KinOut<D0> k0; KinOut<D1> k1;
@@ -51,7 +51,7 @@ struct Chain1 {
     enum { NQ = JointDims<J0>::nq, NU = JointDims<J0>::nu, NY = NQ + NU, NB = 2 };
     const BodyConst* b0; const BodyConst* b1; const ForceConst* forces; double gx, gy, gz;
 
-    SBK_HDN void eval(const double* y, double* ydot) const {
+    SBK_HD void eval(const double* y, double* ydot) const {
         const double* q0 = y; const double* u0 = y + NQ;
         double qe; KinOut<NU> k0;
         kinCore<J0>(*b0, q0, u0, identity3(), zero3(), zeroSV(), k0, ydot, qe);
@@ -63,51 +63,62 @@ struct Chain1 {
     }
 };
 
-// One RKM attempt entirely in registers from saved y0, f0 (same arithmetic as tpiRkmStep; no
-// quaternions here so the q-part of the error norm is the plain RMS and there is no projection).
+// One RKM attempt entirely in registers (same arithmetic as tpiRkmStep; no quaternions here so the
+// q-part of the error norm is the plain RMS and there is no projection).  The five derivative
+// evaluations share ONE inlined copy of eval() inside a loop over the stages: no call boundary (and
+// no generic loads through a `this` pointer) in the step, one copy of the sweeps in the instruction
+// cache.  fresh = true: start of a step, evaluates f0 = f(y) and saves y0 = y; fresh = false: retry
+// of a failed attempt from the saved y0 / f0 with a new h.
 template <class E>
-SBK_HD double fusedRkmAttempt(const E& e, const double* y0, const double* f0, double* y, const double h, const int useInfNorm) {
+SBK_HD double fusedRkmAttempt(const E& e, double* y0, double* f0, double* y, const double h, const int useInfNorm, const bool fresh) {
     constexpr int NY = E::NY, NQ = E::NQ, NU = E::NU;
-    double fa[NY], fb[NY], ys[NY];
-#pragma unroll
-    for (int i = 0; i < NY; ++i) y[i] = y0[i] + (h/3)*f0[i];
-    e.eval(y, fa);
-#pragma unroll
-    for (int i = 0; i < NY; ++i) y[i] = y0[i] + (h/6)*(f0[i] + fa[i]);
-    e.eval(y, fa);
-#pragma unroll
-    for (int i = 0; i < NY; ++i) y[i] = y0[i] + (h/8)*(f0[i] + 3*fa[i]);
-    e.eval(y, fb);
-#pragma unroll
-    for (int i = 0; i < NY; ++i) { ys[i] = y0[i] + (h/2)*(f0[i] - 3*fa[i] + 4*fb[i]); y[i] = ys[i]; }
-    e.eval(y, fa);
+    double fa[NY], fb[NY], ys[NY], ft[NY];
     double qAcc = 0, uAcc = 0;
+    if (!fresh) {
 #pragma unroll
-    for (int i = 0; i < NY; ++i) {
-        const double y1 = y0[i] + (h/6)*(f0[i] + 4*fb[i] + fa[i]);
-        y[i] = y1;
-        const double err = 0.2*fabs(y1 - ys[i]);
-        if (i < NQ) { if (useInfNorm) qAcc = fmax(qAcc, fabs(err)); else qAcc += err*err; }
-        else {
-            const double a0 = fabs(y0[i]);
-            const double sc = (a0*1.0 > 1.0) ? 1.0/a0 : 1.0;
-            const double v = sc*err;
-            if (useInfNorm) uAcc = fmax(uAcc, fabs(v)); else uAcc += v*v;
+        for (int i = 0; i < NY; ++i) y[i] = y0[i] + (h/3)*f0[i];
+    }
+#pragma unroll 1
+    for (int stage = fresh ? 0 : 1; stage < 5; ++stage) {
+        e.eval(y, ft);
+        if (stage == 0) {
+#pragma unroll
+            for (int i = 0; i < NY; ++i) { f0[i] = ft[i]; y0[i] = y[i]; y[i] = y0[i] + (h/3)*f0[i]; }
+        } else if (stage == 1) {
+#pragma unroll
+            for (int i = 0; i < NY; ++i) { fa[i] = ft[i]; y[i] = y0[i] + (h/6)*(f0[i] + fa[i]); }
+        } else if (stage == 2) {
+#pragma unroll
+            for (int i = 0; i < NY; ++i) { fa[i] = ft[i]; y[i] = y0[i] + (h/8)*(f0[i] + 3*fa[i]); }
+        } else if (stage == 3) {
+#pragma unroll
+            for (int i = 0; i < NY; ++i) { fb[i] = ft[i]; ys[i] = y0[i] + (h/2)*(f0[i] - 3*fa[i] + 4*fb[i]); y[i] = ys[i]; }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NY; ++i) {
+                const double y1 = y0[i] + (h/6)*(f0[i] + 4*fb[i] + ft[i]);
+                y[i] = y1;
+                const double err = 0.2*fabs(y1 - ys[i]);
+                if (i < NQ) { if (useInfNorm) qAcc = fmax(qAcc, fabs(err)); else qAcc += err*err; }
+                else {
+                    const double a0 = fabs(y0[i]);
+                    const double sc = (a0*1.0 > 1.0) ? 1.0/a0 : 1.0;
+                    const double v = sc*err;
+                    if (useInfNorm) uAcc = fmax(uAcc, fabs(v)); else uAcc += v*v;
+                }
+            }
         }
     }
     const double qNorm = useInfNorm ? qAcc : sqrt(qAcc/NQ);
     const double uNorm = useInfNorm ? uAcc : sqrt(uAcc/NU);
     return qNorm >= uNorm ? qNorm : uNorm;
 }
-// One fixed-size step: f0 = f(y), y0 = y, attempt.
+// One fixed-size step.
 template <class E>
 SBK_HD double fusedRkmStep(const E& e, double* y, const double h, const int useInfNorm) {
     constexpr int NY = E::NY;
     double y0[NY], f0[NY];
-    e.eval(y, f0);
-#pragma unroll
-    for (int i = 0; i < NY; ++i) y0[i] = y[i];
-    return fusedRkmAttempt(e, y0, f0, y, h, useInfNorm);
+    return fusedRkmAttempt(e, y0, f0, y, h, useInfNorm, true);
 }
 // Error-controlled stepping to tFinal (cf. tpiRkmAdaptive).
 template <class E>
@@ -117,18 +128,15 @@ SBK_HD void fusedRkmAdaptive(const E& e, double* y, const StepLimits& lim, const
     int budget = maxAttempts;
     while (st.t < tFinal && budget > 0) {
         double y0[NY], f0[NY];
-        e.eval(y, f0);
-#pragma unroll
-        for (int i = 0; i < NY; ++i) y0[i] = y[i];
-        bool ok = false; double t1 = st.t;
+        bool ok = false, fresh = true; double t1 = st.t;
         do {
             bool limited = false;
             if (allowInterpolation) t1 = st.t + st.h;
             else if (tFinal < st.t + 0.95*st.h)  { limited = true; t1 = tFinal; }
             else if (tFinal > st.t + 1.001*st.h) t1 = st.t + st.h;
             else t1 = tFinal;
-            lastErr = fusedRkmAttempt(e, y0, f0, y, t1 - st.t, useInfNorm);
-            ++st.attempts; --budget;
+            lastErr = fusedRkmAttempt(e, y0, f0, y, t1 - st.t, useInfNorm, fresh);
+            fresh = false; ++st.attempts; --budget;
             ok = adjustStepSize(lastErr, lim, limited, st.h);
         } while (!ok && budget > 0);
         if (!ok) {
