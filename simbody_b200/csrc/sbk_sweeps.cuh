@@ -131,7 +131,10 @@ SBK_HD Tables tablesOf(const Ctx& c) { Tables t; t.bodies = c.bodies; t.children
 //                    kinematics, rows 30..47
 // Body b-1 is always the previous body of an outward sweep and b+1 of an inward one, so no
 // bookkeeping is needed: BF_PARENT_PREV says whether the parent is b-1.
-enum { CARRY_ROWS = 84, CY_A = 18, CY_SELF = 30, CY_PRE = 48, CY_GNU = 56, GNU_ROWS = 14 };
+#ifndef SBK_GNU_ROWS
+#define SBK_GNU_ROWS 14
+#endif
+enum { CY_A = 18, CY_SELF = 30, CY_PRE = 48, CY_GNU = 56, GNU_ROWS = SBK_GNU_ROWS, CARRY_ROWS = CY_GNU + 2*GNU_ROWS };
 // rows 48..55: two coordinate preload slots; rows 56..83: two G / nu preload slots (acceleration sweep, dof <= 2)
 #if defined(__CUDA_ARCH__)
 #define SBK_CARRY_STRIDE 128
