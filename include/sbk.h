@@ -220,6 +220,12 @@ int sbk_calc_mobilizer_reaction_forces(sbk_batch*, double* FM_G);
 int sbk_multiply_by_system_jacobian(sbk_batch*, const double* v, double* Jv);
 int sbk_multiply_by_system_jacobian_transpose(sbk_batch*, const double* F_body, double* JtF);
 
+/* SimbodyMatterSubsystem::calcCompositeBodyInertias (SimbodyMatterSubsystemRep.cpp:5196-5205,
+ * RigidBodyNode.cpp:231-243): for every body the spatial inertia of the rigid body obtained by
+ * locking all joints outboard of it, about the body origin, in Ground.  Position stage.
+ * Host R [nb][10][N]: mass, mass centre (3), unit inertia xx yy zz xy xz yz; Ground = infinite mass. */
+int sbk_calc_composite_body_inertias(sbk_batch*, double* R);
+
 /* ---- operators ------------------------------------------------------------------------ */
 /* SimbodyMatterSubsystem::calcAcceleration / calcAccelerationIgnoringConstraints
  * (SimbodyMatterSubsystem.h:2141,2171; SimbodyMatterSubsystem.cpp:151-226).

@@ -190,9 +190,10 @@ static int cmdEnergy(RefSystem& rs, const char* inPath, const char* outPath, int
 // out per instance: FM_G[nb*6]  calcMobilizerReactionForces at realize(Acceleration)
 //                   Jv[nb*6]    multiplyBySystemJacobian(v)
 //                   JtF[nu]     multiplyBySystemJacobianTranspose(F)
+//                   CBI[nb*10]  calcCompositeBodyInertias: mass, com(3), unit inertia xx yy zz xy xz yz
 static int cmdExtras(RefSystem& rs, const char* inPath, const char* outPath, int N) {
     const int nb=rs.nb, nq=rs.nq, nu=rs.nu;
-    const int inStride = nq + 2*nu + 6*nb, outStride = 12*nb + nu;
+    const int inStride = nq + 2*nu + 6*nb, outStride = 12*nb + nu + 10*nb;
     std::vector<double> in = readDoubles(inPath);
     if ((int)in.size() != N*inStride) { std::fprintf(stderr, "extras: bad input size\n"); return 2; }
     std::vector<double> out((size_t)N*outStride);
@@ -211,6 +212,12 @@ static int cmdExtras(RefSystem& rs, const char* inPath, const char* outPath, int
         for (int b = 0; b < nb; ++b) F[b] = SpatialVec(Vec3(pF[6*b],pF[6*b+1],pF[6*b+2]), Vec3(pF[6*b+3],pF[6*b+4],pF[6*b+5]));
         Vector JtF; rs.matter.multiplyBySystemJacobianTranspose(s, F, JtF);
         for (int i = 0; i < nu; ++i) *o++ = JtF[i];
+        Array_<SpatialInertia, MobilizedBodyIndex> R; rs.matter.calcCompositeBodyInertias(s, R);
+        for (MobilizedBodyIndex b(0); b < nb; ++b) {
+            *o++ = R[b].getMass(); for (int i = 0; i < 3; ++i) *o++ = R[b].getMassCenter()[i];
+            const Vec3& mo = R[b].getUnitInertia().getMoments(); const Vec3& pr = R[b].getUnitInertia().getProducts();
+            for (int i = 0; i < 3; ++i) *o++ = mo[i]; for (int i = 0; i < 3; ++i) *o++ = pr[i];
+        }
     }
     writeDoubles(outPath, out);
     return 0;

@@ -374,13 +374,14 @@ int oracle_eval(int nb, const int* parent, const int* joint, const double* mass,
 /* calcMobilizerReactionForces (SimbodyMatterSubsystemRep.cpp:5788-5832): FB = zPlus + PPlus*(~Phi A_GP), reported at
  * the M frame origin: FM = (m - (R_GB p_BM) x f, f).  Ground collects its base bodies (RigidBodyNode_Weld.cpp:197-222).
  * multiplyBySystemJacobian / Transpose: RigidBodyNodeSpec.cpp:760-815.
- * in  per instance: q[nq] u[nu] v[nu] F[nb*6];  out: FM_G[nb*6] Jv[nb*6] JtF[nu]   (same layout as `ref_driver extras`) */
+ * calcCompositeBodyInertias: RigidBodyNode.cpp:231-243, MassProperties.h:1037-1045,1110-1116 (SpatialInertia += and shift).
+ * in  per instance: q[nq] u[nu] v[nu] F[nb*6];  out: FM_G[nb*6] Jv[nb*6] JtF[nu] CBI[nb*10]   (same layout as `ref_driver extras`) */
 int oracle_extras(int nb, const int* parent, const int* joint, const double* mass, const double* com, const double* ui,
                   const double* XPF, const double* XBM, int nf, const int* fkind, const int* fbody, const int* fcoord,
                   const double* fa, const double* fb, const double* fdir, int N, const double* in, double* out) {
     Model M = mkModel(nb, parent, joint, mass, com, ui, XPF, XBM, nf, fkind, fbody, fcoord, fa, fb, fdir);
     int nq, nu, nquat; Body* B = setupBodies(&M, &nq, &nu, &nquat);
-    const int inStride = nq + 2*nu + 6*nb, outStride = 12*nb + nu;
+    const int inStride = nq + 2*nu + 6*nb, outStride = 12*nb + nu + 10*nb;
     double* ydot = (double*)malloc(sizeof(double)*(size_t)(nq+nu+1));
     double* qerr = (double*)malloc(sizeof(double)*(size_t)(nquat+1));
     double* z = (double*)malloc(sizeof(double)*(size_t)(6*nb));
@@ -413,6 +414,26 @@ int oracle_extras(int nb, const int* parent, const int* joint, const double* mas
             const Body* me = &B[b];
             for (int c = b+1; c < nb; ++c) if (parent[c] == b) { double t[6]; phiF(B[c].l, z + 6*c, t); for (int i = 0; i < 6; ++i) z[6*b+i] += t[i]; }
             for (int j = 0; j < me->nu; ++j) { double s = 0; for (int i = 0; i < 6; ++i) s += me->H[j][i]*z[6*b+i]; JtF[me->u0+j] = s; }
+        }
+        /* composite body inertias, tip to base: R_b = Mk_b + sum R_c.shift(-l_c) */
+        double* R = o + 12*nb + nu;
+        R[0] = INFINITY; R[1] = R[2] = R[3] = 0; R[4] = R[5] = R[6] = 1; R[7] = R[8] = R[9] = 0;
+        for (int b = nb-1; b >= 1; --b) {
+            const Body* me = &B[b]; double* Rb = R + 10*b;
+            Rb[0] = me->m; for (int i = 0; i < 3; ++i) Rb[1+i] = me->c[i];
+            Rb[4] = me->G[0]; Rb[5] = me->G[4]; Rb[6] = me->G[8]; Rb[7] = me->G[1]; Rb[8] = me->G[2]; Rb[9] = me->G[5];
+            for (int c = b+1; c < nb; ++c) if (parent[c] == b) {
+                const double* Rc = R + 10*c; double p[3] = {Rc[1], Rc[2], Rc[3]}, G[6] = {Rc[4], Rc[5], Rc[6], Rc[7], Rc[8], Rc[9]}, pn[3];
+                /* shift(S = -l): to centroid, then to the new origin: p' = p - S = p + l */
+                G[0] -= p[1]*p[1]+p[2]*p[2]; G[1] -= p[0]*p[0]+p[2]*p[2]; G[2] -= p[0]*p[0]+p[1]*p[1]; G[3] -= -p[0]*p[1]; G[4] -= -p[0]*p[2]; G[5] -= -p[1]*p[2];
+                for (int i = 0; i < 3; ++i) pn[i] = p[i] + B[c].l[i];
+                G[0] += pn[1]*pn[1]+pn[2]*pn[2]; G[1] += pn[0]*pn[0]+pn[2]*pn[2]; G[2] += pn[0]*pn[0]+pn[1]*pn[1]; G[3] += -pn[0]*pn[1]; G[4] += -pn[0]*pn[2]; G[5] += -pn[1]*pn[2];
+                /* += */
+                const double mt = Rb[0] + Rc[0], oo = 1.0/mt;
+                for (int i = 0; i < 3; ++i) Rb[1+i] = oo*(Rb[0]*Rb[1+i] + Rc[0]*pn[i]);
+                for (int i = 0; i < 6; ++i) Rb[4+i] = oo*(Rb[0]*Rb[4+i] + Rc[0]*G[i]);
+                Rb[0] = mt;
+            }
         }
     }
     free(ydot); free(qerr); free(z); free(B);

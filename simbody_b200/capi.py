@@ -76,6 +76,7 @@ SYMBOLS = {
     "sbk_get_applied_forces": (ctypes.c_int, [_P, c_double_p, c_double_p]),
     "sbk_calc_energy": (ctypes.c_int, [_P, c_double_p, c_double_p]),
     "sbk_calc_mobilizer_reaction_forces": (ctypes.c_int, [_P, c_double_p]),
+    "sbk_calc_composite_body_inertias": (ctypes.c_int, [_P, c_double_p]),
     "sbk_multiply_by_system_jacobian": (ctypes.c_int, [_P, c_double_p, c_double_p]),
     "sbk_multiply_by_system_jacobian_transpose": (ctypes.c_int, [_P, c_double_p, c_double_p]),
     "sbk_calc_acceleration": (ctypes.c_int, [_P, c_double_p, c_double_p, c_double_p, c_double_p]),

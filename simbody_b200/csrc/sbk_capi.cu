@@ -495,6 +495,16 @@ int sbk_multiply_by_system_jacobian_transpose(sbk_batch* b, const double* F, dou
     return d2h(b, JtF, b->dOpOut, b->topo->nu);
 }
 
+int sbk_calc_composite_body_inertias(sbk_batch* b, double* R) {
+    if (!b || !R) return fail(SBK_ERR_ARG, "sbk_calc_composite_body_inertias: null argument");
+    if (int rc = useDevice(b)) return rc;
+    if (int rc = needStage(b, ST_POSITION, "sbk_calc_composite_body_inertias")) return rc;
+    const size_t rows = (size_t)b->topo->nb*10;
+    if (int rc = ensureScratch(b, rows*b->N)) return rc;
+    CUDA_TRY(launchCompositeBodyInertias(b->a, b->dScratch, b->stream)); b->launches++;
+    return d2h(b, R, b->dScratch, rows);
+}
+
 // ---- operators --------------------------------------------------------------------------------
 int sbk_calc_acceleration(sbk_batch* b, const double* fmob, const double* Fbody, double* udot, double* A_GB) {
     if (!b) return fail(SBK_ERR_ARG, "null batch");

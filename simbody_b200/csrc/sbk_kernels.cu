@@ -9,6 +9,7 @@
 // instance and threads to the bodies of a level; plan 4 maps the whole (cooperative) grid to one tree level
 // of the batch.  FP64 throughout; no tensor cores (6x6 spatial operators are not a dense contraction).
 #include <algorithm>
+#include <math_constants.h>
 #include "sbk_kernels.cuh"
 #include "sbk_fused.cuh"
 #include "sbk_tpi.cuh"
@@ -514,6 +515,44 @@ __global__ void jacobianTransposeKernel(const KArgs a, const double* F, double* 
     }
 }
 
+// calcCompositeBodyInertias (SimbodyMatterSubsystemRep.cpp:5196-5205, RigidBodyNode.cpp:231-243): the spatial inertia
+// of the rigid body made by locking every joint outboard of a body, about the body origin, in Ground:
+//   R_b = Mk_b + sum_children R_c.shift(-l_c)     (SpatialInertia shift / +=, MassProperties.h:1037-1045,1110-1116)
+// out [nb*10][N]: mass, com (3), unit inertia xx yy zz xy xz yz.  Ground: infinite mass (RigidBodyNode_Weld.cpp:168-171).
+__global__ void cbiKernel(const KArgs a, double* out) {
+    const int k = blockIdx.x*blockDim.x + threadIdx.x;
+    if (k >= a.N) return;
+    const BodyConst* bodies = reinterpret_cast<const BodyConst*>(a.tables);
+    const int* children = reinterpret_cast<const int*>(a.tables + a.childrenOff);
+    const long long N = a.N;
+    auto row = [&](int b, int i) -> double& { return out[((long long)b*10 + i)*N + k]; };
+    row(0, 0) = CUDART_INF; row(0, 1) = 0; row(0, 2) = 0; row(0, 3) = 0; row(0, 4) = 1; row(0, 5) = 1; row(0, 6) = 1; row(0, 7) = 0; row(0, 8) = 0; row(0, 9) = 0;
+    for (int b = a.nb - 1; b >= 1; --b) {
+        const BodyConst& bc = bodies[b];
+        CacheRef me; me.p = a.cache + bc.cacheBase + instOffsetK(a, k); me.stride = a.cStride;
+        double m = bc.mass; V3 p = me.ld3(F_MK); S3 G = me.ldS3(F_MK + 3);
+        for (int c = 0; c < bc.nchild; ++c) {
+            const int cb = children[bc.childStart + c];
+            CacheRef ch; ch.p = a.cache + bodies[cb].cacheBase + instOffsetK(a, k); ch.stride = a.cStride;
+            const double mc = row(cb, 0); const V3 pc = mk(row(cb, 1), row(cb, 2), row(cb, 3));
+            S3 Gc; Gc.xx = row(cb, 4); Gc.yy = row(cb, 5); Gc.zz = row(cb, 6); Gc.xy = row(cb, 7); Gc.xz = row(cb, 8); Gc.yz = row(cb, 9);
+            // shift(-l): to the centroid, then out to the parent origin (the com is at pc + l from there)
+            Gc.xx -= pc.y*pc.y + pc.z*pc.z; Gc.yy -= pc.x*pc.x + pc.z*pc.z; Gc.zz -= pc.x*pc.x + pc.y*pc.y;
+            Gc.xy -= -pc.x*pc.y; Gc.xz -= -pc.x*pc.z; Gc.yz -= -pc.y*pc.z;
+            const V3 pn = pc + ch.ld3(F_L);
+            Gc.xx += pn.y*pn.y + pn.z*pn.z; Gc.yy += pn.x*pn.x + pn.z*pn.z; Gc.zz += pn.x*pn.x + pn.y*pn.y;
+            Gc.xy += -pn.x*pn.y; Gc.xz += -pn.x*pn.z; Gc.yz += -pn.y*pn.z;
+            const double mt = m + mc, oo = 1.0/mt;
+            p = oo*(m*p + mc*pn);
+            G.xx = oo*(m*G.xx + mc*Gc.xx); G.yy = oo*(m*G.yy + mc*Gc.yy); G.zz = oo*(m*G.zz + mc*Gc.zz);
+            G.xy = oo*(m*G.xy + mc*Gc.xy); G.xz = oo*(m*G.xz + mc*Gc.xz); G.yz = oo*(m*G.yz + mc*Gc.yz);
+            m = mt;
+        }
+        row(b, 0) = m; row(b, 1) = p.x; row(b, 2) = p.y; row(b, 3) = p.z;
+        row(b, 4) = G.xx; row(b, 5) = G.yy; row(b, 6) = G.zz; row(b, 7) = G.xy; row(b, 8) = G.xz; row(b, 9) = G.yz;
+    }
+}
+
 // Memory-pattern probe (bench/diagnostics only): one thread per instance walks `nb` records of
 // `rowsIn` + `rowsOut` rows in the [row][N] layout of the thread-per-instance plan, loading rowsIn
 // doubles and storing rowsOut doubles per record with no arithmetic to speak of.  It measures what
@@ -636,6 +675,10 @@ cudaError_t launchJacobian(const KArgs& a, const double* v, double* out, cudaStr
 }
 cudaError_t launchJacobianTranspose(const KArgs& a, const double* F, double* z, double* out, cudaStream_t stream) {
     jacobianTransposeKernel<<<(a.N + 127)/128, 128, 0, stream>>>(a, F, z, out);
+    return cudaGetLastError();
+}
+cudaError_t launchCompositeBodyInertias(const KArgs& a, double* out, cudaStream_t stream) {
+    cbiKernel<<<(a.N + 127)/128, 128, 0, stream>>>(a, out);
     return cudaGetLastError();
 }
 cudaError_t launchMemPattern(double* buf, int N, int nb, int rowsIn, int rowsOut, int sweeps, int minBlocks, cudaStream_t stream) {

@@ -85,6 +85,8 @@ cudaError_t launchReaction(const KArgs& a, double* out, cudaStream_t stream);
 // System Jacobian products from the realized position records: Jv [nb*6][N] = J v;  JtF [nu][N] = ~J F (z: scratch [nb*6][N]).
 cudaError_t launchJacobian(const KArgs& a, const double* v, double* out, cudaStream_t stream);
 cudaError_t launchJacobianTranspose(const KArgs& a, const double* F, double* z, double* out, cudaStream_t stream);
+// Composite body inertias from the realized position records: out [nb*10][N] (mass, com, unit inertia).
+cudaError_t launchCompositeBodyInertias(const KArgs& a, double* out, cudaStream_t stream);
 // Memory-pattern probe for the thread-per-instance record layout (diagnostics).
 cudaError_t launchMemPattern(double* buf, int N, int nb, int rowsIn, int rowsOut, int sweeps, int minBlocks, cudaStream_t stream);
 // FP64 FMA throughput probe: returns flops executed; used by bench.py to measure the FP64 roofline.

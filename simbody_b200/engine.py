@@ -192,6 +192,13 @@ class BatchedMatter:
         self._chk(self.lib.sbk_calc_mobilizer_reaction_forces(self.handle, _dp(F)))
         return F.reshape(self.topo.nb, 6, self.N)
 
+    def calcCompositeBodyInertias(self):
+        """SimbodyMatterSubsystem::calcCompositeBodyInertias: [nb, 10, N] = mass, com(3), unit inertia xx yy zz xy xz yz
+        about each body origin, in Ground; position stage."""
+        R = np.empty((self.topo.nb * 10, self.N))
+        self._chk(self.lib.sbk_calc_composite_body_inertias(self.handle, _dp(R)))
+        return R.reshape(self.topo.nb, 10, self.N)
+
     def multiplyBySystemJacobian(self, v):
         """J v: [nu, N] -> [nb, 6, N] (SimbodyMatterSubsystem.h:554); position stage."""
         v = self._vec(v, self.topo.nu, "v")

@@ -98,6 +98,10 @@ public:
     void calcMobilizerReactionForces(std::vector<double>& FM_G) {
         FM_G.resize((size_t)6*topo_.getNumBodies()*n_); throwOnError(sbk_calc_mobilizer_reaction_forces(h_, FM_G.data()));
     }
+    // calcCompositeBodyInertias: R [nb][10][N] = mass, com(3), unit inertia xx yy zz xy xz yz
+    void calcCompositeBodyInertias(std::vector<double>& R) {
+        R.resize((size_t)10*topo_.getNumBodies()*n_); throwOnError(sbk_calc_composite_body_inertias(h_, R.data()));
+    }
     // multiplyBySystemJacobian / multiplyBySystemJacobianTranspose (:554,:646)
     void multiplyBySystemJacobian(const std::vector<double>& v, std::vector<double>& Jv) {
         need(v, topo_.getNU(), "v"); Jv.resize((size_t)6*topo_.getNumBodies()*n_);

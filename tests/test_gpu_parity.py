@@ -326,6 +326,7 @@ def run_extras(info, xin, plan=None):
     res = {"FM_G": bm.calcMobilizerReactionForces().reshape(nb * 6, n).T,
            "Jv": bm.multiplyBySystemJacobian(soa(xin[:, nq + nu:nq + 2 * nu])).reshape(nb * 6, n).T,
            "JtF": bm.multiplyBySystemJacobianTranspose(soa(xin[:, nq + 2 * nu:])).T,
+           "CBI": bm.calcCompositeBodyInertias().reshape(nb * 10, n).T[:, 10:],
            "X_GB": bm.getBodyTransforms().reshape(nb * 12, n).T}
     bm.close(); topo.close()
     return res
