@@ -35,11 +35,11 @@ WORKLOADS = {
     "branched_tree1000_256": dict(model="branched_tree", n=1000, batch=256, h=5e-4, q_scale=0.5),
 }
 # measured DRAM bytes per instance-step (ncu --set full, profiles/r1_prof_<workload>.txt): launch traffic / (N * steps)
-NCU_TRAFFIC_PER_INSTANCE_STEP = {"double_pendulum_1M": 4.764e7 / (1048576 * 20), "humanoid30_64k": 2.763e10 / (65536 * 4),
-                                 "pin_chain50_64k": 1.408e10 / (65536 * 4)}
+NCU_TRAFFIC_PER_INSTANCE_STEP = {"double_pendulum_1M": 4.272e7 / (1048576 * 20), "humanoid30_64k": 2.761e10 / (65536 * 4),
+                                 "pin_chain50_64k": 1.409e10 / (65536 * 4)}
 # sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active of the same captures (the hardware's own
 # view of FP64-pipe utilisation; roofline.frac below uses the reference's ALGORITHMIC flop count instead)
-NCU_FP64_PIPE_ACTIVE = {"double_pendulum_1M": 0.716, "humanoid30_64k": 0.246, "pin_chain50_64k": 0.343}
+NCU_FP64_PIPE_ACTIVE = {"double_pendulum_1M": 0.776, "humanoid30_64k": 0.240, "pin_chain50_64k": 0.332}
 F_EVAL = {"PIN": 1180.0, "SLIDER": 1130.0, "UNIVERSAL": 1710.0, "BALL": 2060.0, "FREE": 3800.0, "WELD": 700.0,
           "TRANSLATION": 1800.0, "CYLINDER": 1650.0, "PLANAR": 1950.0, "GIMBAL": 2300.0}
 

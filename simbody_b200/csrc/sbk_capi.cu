@@ -51,7 +51,7 @@ int useDevice(const sbk_batch* b) {
     return SBK_OK;
 }
 int launch(sbk_batch* b, KernelOp op) {
-    CUDA_TRY(b->plan == 3 ? launchLp(op, b->a, b->stream) : launchTpi(op, b->a, b->stream));
+    CUDA_TRY(b->plan == 3 ? launchLp(op, b->a, b->stream) : b->plan == 4 ? launchGl(op, b->a, b->stream) : launchTpi(op, b->a, b->stream));
     b->launches++;
     return SBK_OK;
 }

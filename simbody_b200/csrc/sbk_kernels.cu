@@ -361,18 +361,67 @@ __global__ void __launch_bounds__(GL_THREADS, SBK_GL_MINB) glRkmKernel(const KAr
         gridBarrier(bar, gridDim.x, target);
     }
 }
-cudaError_t launchGlRkmImpl(const KArgs& a, cudaStream_t stream) {
+// API operations of plan 4 with the same mapping (one launch = the sweeps of one operation).
+template <int OP>
+__global__ void __launch_bounds__(GL_THREADS, SBK_GL_MINB) glOpKernel(const KArgs a) {
+    __shared__ Ctx sctx;
+    if (threadIdx.x == 0) fillCtx(sctx, a, a.tables, false);
+    __syncthreads();
+    const Ctx& c = sctx;
+    LpLevels L; L.order = reinterpret_cast<const int*>(a.tables + a.levelOrderOff);
+    L.start = reinterpret_cast<const int*>(a.tables + a.levelStartOff); L.nlevels = a.nlevels;
+    unsigned long long target = 0; unsigned long long* bar = reinterpret_cast<unsigned long long*>(a.taskCounter);
+    const int N = a.N;
+    auto outward = [&](auto f) { for (int l = 1; l < L.nlevels; ++l) { glLevel(L, l, N, f); gridBarrier(bar, gridDim.x, target); } };
+    auto inward  = [&](auto f) { for (int l = L.nlevels - 1; l >= 1; --l) { glLevel(L, l, N, f); gridBarrier(bar, gridDim.x, target); } };
+    if constexpr (OP == OP_KIN) {
+        outward([&](int b, int i) { kinDispatch(c, b, i, c.qdot); });
+    } else if constexpr (OP == OP_ABI) {
+        inward([&](int b, int i) { inwardDispatch<IN_ABI>(c, b, i); });
+    } else if constexpr (OP == OP_EVAL) {
+        outward([&](int b, int i) { kinDispatch(c, b, i, c.qdot); });
+        inward([&](int b, int i) { inwardDispatch<IN_ABI | IN_Z | IN_BIAS | IN_FORCES>(c, b, i); });
+        outward([&](int b, int i) { outwardDispatch<true>(c, b, i, c.udot, c.qdotdot); });
+    } else if constexpr (OP == OP_CALCACC) {
+        inward([&](int b, int i) { inwardDispatch<IN_Z | IN_BIAS>(c, b, i); });
+        outward([&](int b, int i) { outwardDispatch<true>(c, b, i, c.vecOut, nullptr); });
+    } else if constexpr (OP == OP_MULM) {
+        outward([&](int b, int i) { idOutDispatch<false>(c, b, i); });
+        inward([&](int b, int i) { idInDispatch<false>(c, b, i); });
+    } else if constexpr (OP == OP_MULMINV) {
+        inward([&](int b, int i) { inwardDispatch<IN_Z>(c, b, i); });
+        outward([&](int b, int i) { outwardDispatch<false>(c, b, i, c.vecOut, nullptr); });
+    } else if constexpr (OP == OP_RESID) {
+        outward([&](int b, int i) { idOutDispatch<true>(c, b, i); });
+        inward([&](int b, int i) { idInDispatch<true>(c, b, i); });
+    }
+}
+template <class K> cudaError_t launchGlCoop(K kernel, const KArgs& a, cudaStream_t stream) {
     int dev = 0, sms = 0, perSm = 0;
     cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, glRkmKernel, GL_THREADS, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, GL_THREADS, 0);
     if (e != cudaSuccess) return e;
     if (perSm < 1) return cudaErrorLaunchOutOfResources;
     e = cudaMemsetAsync(a.taskCounter, 0, 2*sizeof(int), stream);         // the 64-bit barrier counter
     if (e != cudaSuccess) return e;
     void* args[] = { const_cast<KArgs*>(&a) };
     // cooperative launch: the driver guarantees (or refuses) co-residency of the whole grid
-    return cudaLaunchCooperativeKernel((const void*)glRkmKernel, dim3(sms*perSm), dim3(GL_THREADS), args, 0, stream);
+    return cudaLaunchCooperativeKernel((const void*)kernel, dim3(sms*perSm), dim3(GL_THREADS), args, 0, stream);
 }
+cudaError_t launchGlOpImpl(KernelOp op, const KArgs& a, cudaStream_t stream) {
+    switch (op) {
+        case OP_KIN:     return launchGlCoop(glOpKernel<OP_KIN>, a, stream);
+        case OP_ABI:     return launchGlCoop(glOpKernel<OP_ABI>, a, stream);
+        case OP_EVAL:    return launchGlCoop(glOpKernel<OP_EVAL>, a, stream);
+        case OP_CALCACC: return launchGlCoop(glOpKernel<OP_CALCACC>, a, stream);
+        case OP_MULM:    return launchGlCoop(glOpKernel<OP_MULM>, a, stream);
+        case OP_MULMINV: return launchGlCoop(glOpKernel<OP_MULMINV>, a, stream);
+        case OP_RESID:   return launchGlCoop(glOpKernel<OP_RESID>, a, stream);
+        default: break;
+    }
+    return cudaErrorInvalidValue;
+}
+cudaError_t launchGlRkmImpl(const KArgs& a, cudaStream_t stream) { return launchGlCoop(glRkmKernel, a, stream); }
 
 __device__ __forceinline__ long long instOffsetK(const KArgs& a, int k) {
     return (long long)(k >> a.cShift)*a.cSpan + (long long)(k & a.cMask)*a.cInstStride;
@@ -624,6 +673,7 @@ cudaError_t launchLp(KernelOp op, const KArgs& a, cudaStream_t stream) {
     return cudaErrorInvalidValue;
 }
 cudaError_t launchGlRkm(const KArgs& a, cudaStream_t stream) { return launchGlRkmImpl(a, stream); }
+cudaError_t launchGl(KernelOp op, const KArgs& a, cudaStream_t stream) { return op == OP_RKM ? launchGlRkmImpl(a, stream) : launchGlOpImpl(op, a, stream); }
 bool fusedPlanSupports(int nb, const int* joints) {
     auto simple = [](int j) { return j == JT_PIN || j == JT_SLIDER; };
     if (nb == 2) return simple(joints[1]) || joints[1] == JT_UNIVERSAL;

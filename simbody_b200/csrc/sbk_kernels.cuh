@@ -72,6 +72,8 @@ cudaError_t launchLp(KernelOp op, const KArgs& a, cudaStream_t stream);
 // Grid-level-parallel fixed-step integrator (plan 4): persistent cooperative grid, work items = (body of a level, warp of
 // instances), grid barriers between levels.  Uses the thread-per-instance record layout and the [slot][N] work vectors.
 cudaError_t launchGlRkm(const KArgs& a, cudaStream_t stream);
+// Every operation of plan 4 (OP_RKM and the API operations; OP_RKM_ADAPT is not available).
+cudaError_t launchGl(KernelOp op, const KArgs& a, cudaStream_t stream);
 // Ground record (identity transform, zero velocity/acceleration) for every instance.
 cudaError_t launchInitGround(const KArgs& a, cudaStream_t stream);
 // dst[k*len + i] <-> src[i*N + k]

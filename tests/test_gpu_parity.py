@@ -205,6 +205,10 @@ def test_grid_level_parallel_plan_matches_golden(name):
     multiple of the warp size and spans several record blocks."""
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     info = ModelInfo(str(g["text"]))
+    ref = info.split_eval_out(g["eval_out"])
+    got = run_eval(info, g["eval_in"], plan=4)            # the API operations run as grid-level sweeps too
+    for k in ref:
+        assert rel_err(got[k], ref[k]) < TOL, (name, k, rel_err(got[k], ref[k]))
     y0, yref = g["step_in"], g["step_out"]
     n, ny = y0.shape[0], info.nq + info.nu
     topo = sb.Topology(text=info.text); bm = sb.BatchedMatter(topo, n); bm.setPlan(4); assert bm.getPlan() == 4
@@ -342,9 +346,10 @@ def test_reactions_and_jacobian_match_golden(name):
     for k in ref:
         assert rel_err(got[k], ref[k]) < TOL, (name, k, rel_err(got[k], ref[k]))
     if name in ("mixed7", "welded8", "cartesian8", "humanoid30", "branched_tree"):
-        got3 = run_extras(info, g["extras_in"], plan=3)        # level-parallel record layout
-        for k in ref:
-            assert rel_err(got3[k], ref[k]) < TOL, (name, k, "plan 3")
+        for plan in (3, 4):                                    # level-parallel record layout; grid-level realize
+            gotp = run_extras(info, g["extras_in"], plan=plan)
+            for k in ref:
+                assert rel_err(gotp[k], ref[k]) < TOL, (name, k, "plan %d" % plan)
 
 
 def test_reaction_forces_match_sdfast_known_answers():
