@@ -71,7 +71,8 @@ enum {
     SBK_FORCE_SPRING  = 2,  /* Force::MobilityLinearSpring: body, coord, a = k, b = q0   */
     SBK_FORCE_DAMPER  = 3,  /* Force::MobilityLinearDamper: body, coord, a = c           */
     SBK_FORCE_UNIFORM_GRAVITY = 4, /* Force::UniformGravity (Force.cpp:1034-1057): dir = the gravity VECTOR g in Ground, zero height 0 */
-    SBK_FORCE_GLOBAL_DAMPER   = 5  /* Force::GlobalDamper (Force.cpp:996-998): f -= a*u on every mobility          */
+    SBK_FORCE_GLOBAL_DAMPER   = 5, /* Force::GlobalDamper (Force.cpp:996-998): f -= a*u on every mobility          */
+    SBK_FORCE_MOBILITY_CONSTANT = 6 /* Force::MobilityConstantForce (Force_MobilityConstantForce.h:45): body, coord, a = f */
 };
 
 /* One mobilized body, in MobilizedBodyIndex order; entry 0 must be Ground.

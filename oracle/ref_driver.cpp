@@ -93,6 +93,8 @@ struct RefSystem {
                 Force::UniformGravity(forces, matter, Vec3(f.dir[0],f.dir[1],f.dir[2]));
             else if (f.kind == SBK_FORCE_GLOBAL_DAMPER)
                 Force::GlobalDamper(forces, matter, f.a);
+            else if (f.kind == SBK_FORCE_MOBILITY_CONSTANT)
+                Force::MobilityConstantForce(forces, matter.getMobilizedBody(MobilizedBodyIndex(f.body)), MobilizerUIndex(f.coord), f.a);
         }
         defaultState = system.realizeTopology();
         system.realizeModel(defaultState);

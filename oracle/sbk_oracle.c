@@ -35,7 +35,7 @@
 #include <string.h>
 
 enum { PIN = 1, SLIDER = 2, UNIVERSAL = 3, BALL = 4, FREE = 5, WELD = 6, TRANSLATION = 7, CYLINDER = 8, PLANAR = 9, GIMBAL = 10 };
-enum { F_GRAVITY = 1, F_SPRING = 2, F_DAMPER = 3, F_UNIFORM_GRAVITY = 4, F_GLOBAL_DAMPER = 5 };
+enum { F_GRAVITY = 1, F_SPRING = 2, F_DAMPER = 3, F_UNIFORM_GRAVITY = 4, F_GLOBAL_DAMPER = 5, F_MOBILITY_CONSTANT = 6 };
 #define MAXD 6
 
 typedef struct {
@@ -269,6 +269,7 @@ static void systemForces(const Model* M, Body* B, const double* q, const double*
             for (int b = 1; b < M->nb; ++b) { double F[3] = {B[b].m*g[0], B[b].m*g[1], B[b].m*g[2]}, t[3]; cross(B[b].c, F, t);
                 for (int i = 0; i < 3; ++i) { B[b].Fapp[i] += t[i]; B[b].Fapp[3+i] += F[i]; } }
         } else if (M->fkind[k] == F_SPRING) { const Body* me = &B[M->fbody[k]]; fmob[me->u0 + M->fcoord[k]] += -M->fa[k]*(q[me->q0 + M->fcoord[k]] - M->fb[k]); }
+        else if (M->fkind[k] == F_MOBILITY_CONSTANT) { const Body* me = &B[M->fbody[k]]; fmob[me->u0 + M->fcoord[k]] += M->fa[k]; }
         else if (M->fkind[k] == F_GLOBAL_DAMPER) { for (int i = 0; i < nu; ++i) fmob[i] -= M->fa[k]*u[i]; }   /* Force.cpp:997 */
         else if (M->fkind[k] == F_DAMPER) { const Body* me = &B[M->fbody[k]]; fmob[me->u0 + M->fcoord[k]] += -M->fa[k]*u[me->u0 + M->fcoord[k]]; }
     }

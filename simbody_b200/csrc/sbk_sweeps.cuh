@@ -38,7 +38,7 @@ namespace sbkd {
 
 enum { JT_GROUND = 0, JT_PIN = 1, JT_SLIDER = 2, JT_UNIVERSAL = 3, JT_BALL = 4, JT_FREE = 5, JT_WELD = 6,
        JT_TRANSLATION = 7, JT_CYLINDER = 8, JT_PLANAR = 9, JT_GIMBAL = 10 };
-enum { FK_SPRING = 2, FK_DAMPER = 3 };
+enum { FK_SPRING = 2, FK_DAMPER = 3, FK_CONSTANT = 6 };
 
 template <int JT> struct JointDims;
 template <> struct JointDims<JT_PIN>       { enum { nq = 1, nu = 1 }; };
@@ -655,7 +655,8 @@ SBK_HD SV gravityForce(const double mass, const V3 c_G, const double gx, const d
     const V3 Fc = mass*mk(gx, gy, gz);
     SV F; F.w = cross(c_G, Fc); F.v = Fc; return F;
 }
-// MobilityLinearSpring / Damper of one body in force-index order (Force.cpp:339-351,434-443);
+// MobilityLinearSpring / Damper / MobilityConstantForce of one body in force-index order (Force.cpp:339-351,434-443,
+// Force_MobilityConstantForce.cpp);
 // q, u are the body's own coordinates.
 template <int d>
 SBK_HD void mobilityForces(const BodyConst& bc, const ForceConst* forces, const double* q, const double* u, double* f) {
@@ -665,7 +666,7 @@ SBK_HD void mobilityForces(const BodyConst& bc, const ForceConst* forces, const 
         const ForceConst fc = forces[bc.forceStart + k];
 #pragma unroll
         for (int j = 0; j < d; ++j) if (j == fc.coord) {
-            const double frc = (fc.kind == FK_SPRING) ? -fc.a*(q[j] - fc.b) : -fc.a*u[j];
+            const double frc = (fc.kind == FK_SPRING) ? -fc.a*(q[j] - fc.b) : (fc.kind == FK_CONSTANT) ? fc.a : -fc.a*u[j];
             f[j] += frc;
         }
     }

@@ -64,7 +64,7 @@ void compileTopology(const ModelSpec& spec, sbk_topology& t) {
                     sbkd::ForceConst fc; fc.kind = SBK_FORCE_DAMPER; fc.coord = j; fc.a = f.a; fc.b = 0;
                     perBody[b].push_back(fc);
                 }
-        } else if (f.kind == SBK_FORCE_SPRING || f.kind == SBK_FORCE_DAMPER) {
+        } else if (f.kind == SBK_FORCE_SPRING || f.kind == SBK_FORCE_DAMPER || f.kind == SBK_FORCE_MOBILITY_CONSTANT) {
             if (f.body < 1 || f.body >= nb) throw std::runtime_error("topology: force " + std::to_string(i) + " acts on invalid body");
             const int jt = spec.bodies[f.body].joint_type;
             if (f.coord < 0 || f.coord >= jointNU(jt)) throw std::runtime_error("topology: force " + std::to_string(i) + " has invalid coordinate");

@@ -133,6 +133,19 @@ inline ModelSpec lowerSimbodySystem(const SimTK::MultibodySystem&        system,
                 if (nhit != 1) throw std::runtime_error("lowerSimbodySystem: could not locate damper mobility");
                 int body, coord; slotToBodyCoord(hit, body, coord);
                 spec.forces.push_back(damperForce(body, coord, d.getDefaultDamping()));
+            } else if (Force::MobilityConstantForce::isInstanceOf(f)) {
+                const Force::MobilityConstantForce& mc = Force::MobilityConstantForce::downcast(f);
+                const Real f0 = mc.getDefaultForce();
+                if (f0 == 0) continue;                              // contributes nothing; its mobility cannot be located
+                State probe = system.getDefaultState();
+                system.realize(probe, Stage::Velocity);
+                Vector_<SpatialVec> bf; Vector_<Vec3> pf; Vector mf;
+                f.calcForceContribution(probe, bf, pf, mf);
+                int hit = -1, nhit = 0;
+                for (int i = 0; i < mf.size(); ++i) if (mf[i] != 0) { hit = i; ++nhit; }
+                if (nhit != 1) throw std::runtime_error("lowerSimbodySystem: could not locate MobilityConstantForce mobility");
+                int body, coord; slotToBodyCoord(hit, body, coord);
+                spec.forces.push_back(mobilityConstantForce(body, coord, f0));
             } else if (Force::UniformGravity::isInstanceOf(f)) {
                 const Force::UniformGravity& g = Force::UniformGravity::downcast(f);
                 if (g.getZeroHeight() != 0)
@@ -151,7 +164,7 @@ inline ModelSpec lowerSimbodySystem(const SimTK::MultibodySystem&        system,
                 spec.forces.push_back(globalDamperForce(-mf[0]));
             } else {
                 throw std::runtime_error("lowerSimbodySystem: force element " + std::to_string((int)fx) +
-                                         " is outside {Gravity, UniformGravity, MobilityLinearSpring, MobilityLinearDamper, GlobalDamper}");
+                                         " is outside {Gravity, UniformGravity, MobilityLinearSpring, MobilityLinearDamper, MobilityConstantForce, GlobalDamper}");
             }
         }
     }

@@ -117,6 +117,10 @@ inline sbk_force_desc uniformGravityForce(double gx, double gy, double gz) {
     sbk_force_desc f; std::memset(&f, 0, sizeof f);
     f.kind = SBK_FORCE_UNIFORM_GRAVITY; f.body = -1; f.a = 1; f.dir[0] = gx; f.dir[1] = gy; f.dir[2] = gz; return f;
 }
+inline sbk_force_desc mobilityConstantForce(int body, int coord, double f0) {
+    sbk_force_desc f; std::memset(&f, 0, sizeof f);
+    f.kind = SBK_FORCE_MOBILITY_CONSTANT; f.body = body; f.coord = coord; f.a = f0; return f;
+}
 inline sbk_force_desc globalDamperForce(double c) {
     sbk_force_desc f; std::memset(&f, 0, sizeof f);
     f.kind = SBK_FORCE_GLOBAL_DAMPER; f.body = -1; f.a = c; return f;
@@ -270,6 +274,7 @@ inline ModelSpec makeUgDamp5() {
     m.forces.push_back(uniformGravityForce(0.3, -9.7, 0.4));
     m.forces.push_back(springForce(3, 0, 12.0, -0.1));
     m.forces.push_back(globalDamperForce(0.8));
+    m.forces.push_back(mobilityConstantForce(2, 1, 1.7));      // a motor torque on the Universal's second speed
     return m;
 }
 
@@ -335,6 +340,7 @@ inline std::string toText(const ModelSpec& m) {
         else if (f.kind == SBK_FORCE_DAMPER) { out += "damper " + std::to_string(f.body) + " " + std::to_string(f.coord); num(f.a); }
         else if (f.kind == SBK_FORCE_UNIFORM_GRAVITY) { out += "ugravity"; num(f.dir[0]); num(f.dir[1]); num(f.dir[2]); }
         else if (f.kind == SBK_FORCE_GLOBAL_DAMPER) { out += "gdamper"; num(f.a); }
+        else if (f.kind == SBK_FORCE_MOBILITY_CONSTANT) { out += "mconst " + std::to_string(f.body) + " " + std::to_string(f.coord); num(f.a); }
         else throw std::runtime_error("bad force kind");
         out += "\n";
     }
@@ -367,6 +373,7 @@ inline ModelSpec fromText(const std::string& text) {
         else if (tok == "damper") { f.kind = SBK_FORCE_DAMPER; in >> f.body >> f.coord >> f.a; }
         else if (tok == "ugravity") { f.kind = SBK_FORCE_UNIFORM_GRAVITY; f.body = -1; f.a = 1; in >> f.dir[0] >> f.dir[1] >> f.dir[2]; }
         else if (tok == "gdamper") { f.kind = SBK_FORCE_GLOBAL_DAMPER; f.body = -1; in >> f.a; }
+        else if (tok == "mconst") { f.kind = SBK_FORCE_MOBILITY_CONSTANT; in >> f.body >> f.coord >> f.a; }
         else throw std::runtime_error("bad force token " + tok);
         if (!in) throw std::runtime_error("truncated force line");
         m.forces.push_back(f);
