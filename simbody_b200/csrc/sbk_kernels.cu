@@ -305,11 +305,11 @@ __global__ void __launch_bounds__(GL_THREADS, SBK_GL_MINB) glRkmKernel(const KAr
             double* fdst = stage == 0 ? a.f0 : (stage == 3 ? a.fb : a.fa);
             double* qd = fdst; double* ud = fdst + uoff;
 #pragma unroll 1
-            for (int l = 1; l < L.nlevels; ++l) { glLevel(L, l, N, [&](int b, int i) { kinDispatch(c, b, i, qd); }); gridBarrier(bar, gridDim.x, target); }
+            for (int l = 1; l < L.nlevels; ++l) { glLevel(L, l, N, [&](int b, int i) { kinDispatch<true>(c, b, i, qd); }); gridBarrier(bar, gridDim.x, target); }
 #pragma unroll 1
-            for (int l = L.nlevels - 1; l >= 1; --l) { glLevel(L, l, N, [&](int b, int i) { inwardDispatch<IN_ABI | IN_Z | IN_BIAS | IN_FORCES>(c, b, i); }); gridBarrier(bar, gridDim.x, target); }
+            for (int l = L.nlevels - 1; l >= 1; --l) { glLevel(L, l, N, [&](int b, int i) { inwardDispatch<IN_ABI | IN_Z | IN_BIAS | IN_FORCES, true>(c, b, i); }); gridBarrier(bar, gridDim.x, target); }
 #pragma unroll 1
-            for (int l = 1; l < L.nlevels; ++l) { glLevel(L, l, N, [&](int b, int i) { outwardDispatch<true>(c, b, i, ud, nullptr); }); gridBarrier(bar, gridDim.x, target); }
+            for (int l = 1; l < L.nlevels; ++l) { glLevel(L, l, N, [&](int b, int i) { outwardDispatch<true, true>(c, b, i, ud, nullptr); }); gridBarrier(bar, gridDim.x, target); }
             // stage combination over the flat [slot][N] vectors (element e = slot*N + instance)
             for (long long e = tid; e < nel; e += nth) {
                 const double y0 = stage == 0 ? a.y[e] : a.y0[e], f0 = a.f0[e];
@@ -375,25 +375,25 @@ __global__ void __launch_bounds__(GL_THREADS, SBK_GL_MINB) glOpKernel(const KArg
     auto outward = [&](auto f) { for (int l = 1; l < L.nlevels; ++l) { glLevel(L, l, N, f); gridBarrier(bar, gridDim.x, target); } };
     auto inward  = [&](auto f) { for (int l = L.nlevels - 1; l >= 1; --l) { glLevel(L, l, N, f); gridBarrier(bar, gridDim.x, target); } };
     if constexpr (OP == OP_KIN) {
-        outward([&](int b, int i) { kinDispatch(c, b, i, c.qdot); });
+        outward([&](int b, int i) { kinDispatch<true>(c, b, i, c.qdot); });
     } else if constexpr (OP == OP_ABI) {
-        inward([&](int b, int i) { inwardDispatch<IN_ABI>(c, b, i); });
+        inward([&](int b, int i) { inwardDispatch<IN_ABI, true>(c, b, i); });
     } else if constexpr (OP == OP_EVAL) {
-        outward([&](int b, int i) { kinDispatch(c, b, i, c.qdot); });
-        inward([&](int b, int i) { inwardDispatch<IN_ABI | IN_Z | IN_BIAS | IN_FORCES>(c, b, i); });
-        outward([&](int b, int i) { outwardDispatch<true>(c, b, i, c.udot, c.qdotdot); });
+        outward([&](int b, int i) { kinDispatch<true>(c, b, i, c.qdot); });
+        inward([&](int b, int i) { inwardDispatch<IN_ABI | IN_Z | IN_BIAS | IN_FORCES, true>(c, b, i); });
+        outward([&](int b, int i) { outwardDispatch<true, true>(c, b, i, c.udot, c.qdotdot); });
     } else if constexpr (OP == OP_CALCACC) {
-        inward([&](int b, int i) { inwardDispatch<IN_Z | IN_BIAS>(c, b, i); });
-        outward([&](int b, int i) { outwardDispatch<true>(c, b, i, c.vecOut, nullptr); });
+        inward([&](int b, int i) { inwardDispatch<IN_Z | IN_BIAS, true>(c, b, i); });
+        outward([&](int b, int i) { outwardDispatch<true, true>(c, b, i, c.vecOut, nullptr); });
     } else if constexpr (OP == OP_MULM) {
-        outward([&](int b, int i) { idOutDispatch<false>(c, b, i); });
-        inward([&](int b, int i) { idInDispatch<false>(c, b, i); });
+        outward([&](int b, int i) { idOutDispatch<false, true>(c, b, i); });
+        inward([&](int b, int i) { idInDispatch<false, true>(c, b, i); });
     } else if constexpr (OP == OP_MULMINV) {
-        inward([&](int b, int i) { inwardDispatch<IN_Z>(c, b, i); });
-        outward([&](int b, int i) { outwardDispatch<false>(c, b, i, c.vecOut, nullptr); });
+        inward([&](int b, int i) { inwardDispatch<IN_Z, true>(c, b, i); });
+        outward([&](int b, int i) { outwardDispatch<false, true>(c, b, i, c.vecOut, nullptr); });
     } else if constexpr (OP == OP_RESID) {
-        outward([&](int b, int i) { idOutDispatch<true>(c, b, i); });
-        inward([&](int b, int i) { idInDispatch<true>(c, b, i); });
+        outward([&](int b, int i) { idOutDispatch<true, true>(c, b, i); });
+        inward([&](int b, int i) { idInDispatch<true, true>(c, b, i); });
     }
 }
 template <class K> cudaError_t launchGlCoop(K kernel, const KArgs& a, cudaStream_t stream) {

@@ -676,18 +676,19 @@ SBK_HD void mobilityForces(const BodyConst& bc, const ForceConst* forces, const 
 //                     BODY WRAPPERS, FULL records (API realize path)
 //==============================================================================================
 // Every field of the per-body record is stored: getters and the operator forms need them.
+// CB = true: the records are CTA-blocked (plans 1 and 4 on the device) and the row stride is the compile-time 128.
 
-template <int JT>
+template <int JT, bool CB = false>
 SBK_BODY void kinBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, const int inst, double* qdotDst) {
     constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
-    const CacheRef me = cacheOf<false>(c, inst, bc.cacheBase);
+    const CacheRefT<CB> me = cacheOf<CB>(c, inst, bc.cacheBase);
     double q[dim1(NQ)], u[dim1(d)], qdot[dim1(NQ)], qerr;
 #pragma unroll
     for (int i = 0; i < NQ; ++i) q[i] = ldS<false>(c, inst, c.q, bc.q0 + i);
 #pragma unroll
     for (int i = 0; i < d; ++i)  u[i] = ldS<false>(c, inst, c.u, bc.u0 + i);
 
-    const CacheRef pa = cacheOf<false>(c, inst, bc.parentCacheBase);
+    const CacheRefT<CB> pa = cacheOf<CB>(c, inst, bc.parentCacheBase);
     const M3 R_GP = pa.ldM3(F_XGB); const V3 p_GP = pa.ld3(F_XGB + 9); const SV V_GP = pa.ldSV(F_VGB);
 
     KinOut<d> o;
@@ -722,10 +723,10 @@ SBK_HD void setSingular(const Ctx& c, const int inst) {
 #endif
 }
 
-template <int JT, int MODE>
+template <int JT, int MODE, bool CB = false>
 SBK_BODY void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, const int inst) {
     constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
-    const CacheRef me = cacheOf<false>(c, inst, bc.cacheBase);
+    const CacheRefT<CB> me = cacheOf<CB>(c, inst, bc.cacheBase);
     SV H[dim1(d)];
 #pragma unroll
     for (int j = 0; j < d; ++j) H[j] = me.ldSV(F_H + 6*j);
@@ -736,7 +737,7 @@ SBK_BODY void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex,
         const S3 G_G = me.ldS3(F_MK + 3); const SV acor = me.ldSV(F_ACOR), gyro = me.ldSV(F_GYRO);
         ABI P = abiFromRigid(bc.mass, c_G, G_G);
         for (int k = 0; k < bc.nchild; ++k) {
-            const CacheRef ch = cacheOf<false>(c, inst, c.bodies[c.children[bc.childStart + k]].cacheBase);
+            const CacheRefT<CB> ch = cacheOf<CB>(c, inst, c.bodies[c.children[bc.childStart + k]].cacheBase);
             addInto(P, shiftABI(ch.ldABI(F_PPLUS), ch.ld3(F_L)));
         }
         abiCore<d>(P, H, acor, gyro, ao);
@@ -786,7 +787,7 @@ SBK_BODY void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex,
         SV z;
         if constexpr ((MODE & IN_BIAS) != 0) z = ao.zb - F; else z = zeroSV();
         for (int k = 0; k < bc.nchild; ++k) {
-            const CacheRef ch = cacheOf<false>(c, inst, c.bodies[c.children[bc.childStart + k]].cacheBase);
+            const CacheRefT<CB> ch = cacheOf<CB>(c, inst, c.bodies[c.children[bc.childStart + k]].cacheBase);
             z = z + phi(ch.ld3(F_L), ch.ldSV(F_ZPLUS));
         }
         double eps[dim1(d)]; SV zPlus;
@@ -798,12 +799,12 @@ SBK_BODY void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex,
 }
 
 // Sweep E for one body (base->tip): udot, A_GB, qdotdot.
-template <int JT, bool WITH_COR>
+template <int JT, bool WITH_COR, bool CB = false>
 SBK_BODY void outwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, const int inst,
                          double* udotDst, double* qdotdotDst) {
     constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
-    const CacheRef me = cacheOf<false>(c, inst, bc.cacheBase);
-    const SV A_GP = cacheOf<false>(c, inst, bc.parentCacheBase).ldSV(F_AGB);
+    const CacheRefT<CB> me = cacheOf<CB>(c, inst, bc.cacheBase);
+    const SV A_GP = cacheOf<CB>(c, inst, bc.parentCacheBase).ldSV(F_AGB);
     SV H[dim1(d)], G[dim1(d)]; double DI[dim1(d*d)], eps[dim1(d)], udot[dim1(d)];
 #pragma unroll
     for (int j = 0; j < d; ++j) { H[j] = me.ldSV(F_H + 6*j); G[j] = me.ldSV(fG(d) + 6*j); eps[j] = me.ld(fEPS(d) + j); }
@@ -1051,11 +1052,11 @@ SBK_BODY void leanOutwardBody(const Ctx& c, const BodyConst& bc, const int inst,
 // multiplyByM / inverse dynamics passes (RigidBodyNodeSpec.cpp:566-695).
 //   WITH_VEL: residual form (adds coriolis a, gyroscopic b, applied forces).
 // The outward pass stores A in AGB; the inward pass stores F in ZPLUS.
-template <int JT, bool WITH_VEL>
+template <int JT, bool WITH_VEL, bool CB = false>
 SBK_BODY void idOutBody(const Ctx& c, const BodyConst& bc, const int inst) {
     constexpr int d = JointDims<JT>::nu;
     constexpr bool BLK = false;
-    const CacheRefT<BLK> me = cacheOf<BLK>(c, inst, bc.cacheBase), pa = cacheOf<BLK>(c, inst, bc.parentCacheBase);
+    const CacheRefT<CB> me = cacheOf<CB>(c, inst, bc.cacheBase), pa = cacheOf<CB>(c, inst, bc.parentCacheBase);
     SV A = phiT(me.ld3(F_L), pa.ldSV(F_AGB));
     SV Hu = zeroSV();
 #pragma unroll
@@ -1067,11 +1068,11 @@ SBK_BODY void idOutBody(const Ctx& c, const BodyConst& bc, const int inst) {
     if constexpr (WITH_VEL) A = A + me.ldSV(F_ACOR);
     me.stSV(F_AGB, A);
 }
-template <int JT, bool WITH_VEL>
+template <int JT, bool WITH_VEL, bool CB = false>
 SBK_BODY void idInBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, const int inst) {
     constexpr int d = JointDims<JT>::nu;
     constexpr bool BLK = false;
-    const CacheRefT<BLK> me = cacheOf<BLK>(c, inst, bc.cacheBase);
+    const CacheRefT<CB> me = cacheOf<CB>(c, inst, bc.cacheBase);
     const V3 c_G = me.ld3(F_MK); const S3 G_G = me.ldS3(F_MK + 3);
     SV F = mulSpatialInertia(bc.mass, c_G, G_G, me.ldSV(F_AGB));
     if constexpr (WITH_VEL) {
@@ -1085,7 +1086,7 @@ SBK_BODY void idInBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, c
     }
     for (int k = 0; k < bc.nchild; ++k) {
         const BodyConst& cb = c.bodies[c.children[bc.childStart + k]];
-        const CacheRefT<BLK> ch = cacheOf<BLK>(c, inst, cb.cacheBase);
+        const CacheRefT<CB> ch = cacheOf<CB>(c, inst, cb.cacheBase);
         F = F + phi(ch.ld3(F_L), ch.ldSV(F_ZPLUS));
     }
     me.stSV(F_ZPLUS, F);
@@ -1117,17 +1118,17 @@ SBK_BODY void idInBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, c
         default: break;                                                             \
     }
 
-SBK_HD void kinDispatch(const Ctx& c, int b, int inst, double* qdotDst) {
+template <bool CB = false> SBK_HD void kinDispatch(const Ctx& c, int b, int inst, double* qdotDst) {
     const BodyConst& bc = c.bodies[b];
-    SBK_DISPATCH_JOINT(bc.joint, (kinBody<JT>(c, bc, b, inst, qdotDst)));
+    SBK_DISPATCH_JOINT(bc.joint, (kinBody<JT, CB>(c, bc, b, inst, qdotDst)));
 }
-template <int MODE> SBK_HD void inwardDispatch(const Ctx& c, int b, int inst) {
+template <int MODE, bool CB = false> SBK_HD void inwardDispatch(const Ctx& c, int b, int inst) {
     const BodyConst& bc = c.bodies[b];
-    SBK_DISPATCH_JOINT(bc.joint, (inwardBody<JT, MODE>(c, bc, b, inst)));
+    SBK_DISPATCH_JOINT(bc.joint, (inwardBody<JT, MODE, CB>(c, bc, b, inst)));
 }
-template <bool WITH_COR> SBK_HD void outwardDispatch(const Ctx& c, int b, int inst, double* udotDst, double* qddDst) {
+template <bool WITH_COR, bool CB = false> SBK_HD void outwardDispatch(const Ctx& c, int b, int inst, double* udotDst, double* qddDst) {
     const BodyConst& bc = c.bodies[b];
-    SBK_DISPATCH_JOINT(bc.joint, (outwardBody<JT, WITH_COR>(c, bc, b, inst, udotDst, qddDst)));
+    SBK_DISPATCH_JOINT(bc.joint, (outwardBody<JT, WITH_COR, CB>(c, bc, b, inst, udotDst, qddDst)));
 }
 // Same, restricted at compile time to the mobilizer kinds in JMASK (bit JT_x set = kind present): the
 // integrator kernels are instantiated for a few masks so that a model made of Pin joints only does
@@ -1147,36 +1148,36 @@ template <bool WITH_COR> SBK_HD void outwardDispatch(const Ctx& c, int b, int in
         default: break;                                                                                             \
     }
 
-template <bool WITH_VEL> SBK_HD void idOutDispatch(const Ctx& c, int b, int inst) {
+template <bool WITH_VEL, bool CB = false> SBK_HD void idOutDispatch(const Ctx& c, int b, int inst) {
     const BodyConst& bc = c.bodies[b];
-    SBK_DISPATCH_JOINT(bc.joint, (idOutBody<JT, WITH_VEL>(c, bc, inst)));
+    SBK_DISPATCH_JOINT(bc.joint, (idOutBody<JT, WITH_VEL, CB>(c, bc, inst)));
 }
-template <bool WITH_VEL> SBK_HD void idInDispatch(const Ctx& c, int b, int inst) {
+template <bool WITH_VEL, bool CB = false> SBK_HD void idInDispatch(const Ctx& c, int b, int inst) {
     const BodyConst& bc = c.bodies[b];
-    SBK_DISPATCH_JOINT(bc.joint, (idInBody<JT, WITH_VEL>(c, bc, b, inst)));
+    SBK_DISPATCH_JOINT(bc.joint, (idInBody<JT, WITH_VEL, CB>(c, bc, b, inst)));
 }
 
 //==============================================================================================
 // Per-instance drivers for the thread-per-instance plan: body index order is a valid
 // base->tip order because a parent's MobilizedBodyIndex is always smaller than its child's.
 //==============================================================================================
-SBK_HD void tpiKinematics(const Ctx& c, int inst, double* qdotDst) {
-    for (int b = 1; b < c.nb; ++b) kinDispatch(c, b, inst, qdotDst);
+template <bool CB = false> SBK_HD void tpiKinematics(const Ctx& c, int inst, double* qdotDst) {
+    for (int b = 1; b < c.nb; ++b) kinDispatch<CB>(c, b, inst, qdotDst);
 }
-template <int MODE> SBK_HD void tpiInward(const Ctx& c, int inst) {
-    for (int b = c.nb - 1; b >= 1; --b) inwardDispatch<MODE>(c, b, inst);
+template <int MODE, bool CB = false> SBK_HD void tpiInward(const Ctx& c, int inst) {
+    for (int b = c.nb - 1; b >= 1; --b) inwardDispatch<MODE, CB>(c, b, inst);
 }
-template <bool WITH_COR> SBK_HD void tpiOutward(const Ctx& c, int inst, double* udotDst, double* qddDst) {
-    for (int b = 1; b < c.nb; ++b) outwardDispatch<WITH_COR>(c, b, inst, udotDst, qddDst);
+template <bool WITH_COR, bool CB = false> SBK_HD void tpiOutward(const Ctx& c, int inst, double* udotDst, double* qddDst) {
+    for (int b = 1; b < c.nb; ++b) outwardDispatch<WITH_COR, CB>(c, b, inst, udotDst, qddDst);
 }
 // One full derivative evaluation = System::realize(Acceleration) for the lowered system.
 //   LEAN = false: FULL records (every cache entry a getter may ask for); cy unused
 //   LEAN = true : integrator path, reversible kinematics (see above); cy = the work item's carry column
-template <bool LEAN, int JMASK = JM_ALL> SBK_HD void tpiEvalDerivatives(const Ctx& c, const Tables& T, int inst, double* cy, double* qdotDst, double* udotDst, double* qddDst) {
+template <bool LEAN, int JMASK = JM_ALL, bool CB = false> SBK_HD void tpiEvalDerivatives(const Ctx& c, const Tables& T, int inst, double* cy, double* qdotDst, double* udotDst, double* qddDst) {
     if constexpr (!LEAN) {
-        tpiKinematics(c, inst, qdotDst);
-        tpiInward<IN_ABI | IN_Z | IN_BIAS | IN_FORCES>(c, inst);
-        tpiOutward<true>(c, inst, udotDst, qddDst);
+        tpiKinematics<CB>(c, inst, qdotDst);
+        tpiInward<IN_ABI | IN_Z | IN_BIAS | IN_FORCES, CB>(c, inst);
+        tpiOutward<true, CB>(c, inst, udotDst, qddDst);
     } else {
         const SV z0 = zeroSV();
         // pre(k): the coordinate slot of the k-th body step of this evaluation (two alternate)

@@ -154,23 +154,23 @@ __global__ void __launch_bounds__(TPI_THREADS, MINB) tpiKernel(const KArgs a) {
     if constexpr (OP == OP_RKM || OP == OP_RKM_ADAPT) cy = reinterpret_cast<double*>(smem + (STAGE ? a.tableBytes : 0)) + threadIdx.x;
 
     if constexpr (OP == OP_KIN) {
-        tpiKinematics(c, inst, c.qdot);
+        tpiKinematics<true>(c, inst, c.qdot);
     } else if constexpr (OP == OP_ABI) {
-        tpiInward<IN_ABI>(c, inst);
+        tpiInward<IN_ABI, true>(c, inst);
     } else if constexpr (OP == OP_EVAL) {
-        tpiEvalDerivatives<false>(c, tablesOf(c), inst, cy, c.qdot, c.udot, c.qdotdot);
+        tpiEvalDerivatives<false, JM_ALL, true>(c, tablesOf(c), inst, cy, c.qdot, c.udot, c.qdotdot);
     } else if constexpr (OP == OP_CALCACC) {
-        tpiInward<IN_Z | IN_BIAS>(c, inst);
-        tpiOutward<true>(c, inst, c.vecOut, nullptr);
+        tpiInward<IN_Z | IN_BIAS, true>(c, inst);
+        tpiOutward<true, true>(c, inst, c.vecOut, nullptr);
     } else if constexpr (OP == OP_MULM) {
-        for (int b = 1; b < c.nb; ++b) idOutDispatch<false>(c, b, inst);
-        for (int b = c.nb - 1; b >= 1; --b) idInDispatch<false>(c, b, inst);
+        for (int b = 1; b < c.nb; ++b) idOutDispatch<false, true>(c, b, inst);
+        for (int b = c.nb - 1; b >= 1; --b) idInDispatch<false, true>(c, b, inst);
     } else if constexpr (OP == OP_MULMINV) {
-        tpiInward<IN_Z>(c, inst);             // c.fmobIn == a.vecIn, c.FbodyIn == null (set by the host)
-        tpiOutward<false>(c, inst, c.vecOut, nullptr);
+        tpiInward<IN_Z, true>(c, inst);             // c.fmobIn == a.vecIn, c.FbodyIn == null (set by the host)
+        tpiOutward<false, true>(c, inst, c.vecOut, nullptr);
     } else if constexpr (OP == OP_RESID) {
-        for (int b = 1; b < c.nb; ++b) idOutDispatch<true>(c, b, inst);
-        for (int b = c.nb - 1; b >= 1; --b) idInDispatch<true>(c, b, inst);
+        for (int b = 1; b < c.nb; ++b) idOutDispatch<true, true>(c, b, inst);
+        for (int b = c.nb - 1; b >= 1; --b) idInDispatch<true, true>(c, b, inst);
     } else if constexpr (OP == OP_RKM_ADAPT) {
         RkmWork w;
         w.y = a.yb; w.y0 = a.y0; w.f0 = a.f0; w.fa = a.fa; w.fb = a.fb; w.ys = a.ys;
