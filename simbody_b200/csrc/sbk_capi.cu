@@ -198,12 +198,9 @@ static int configurePlan(sbk_batch* b, int plan) {
     a.tableBytes = (uint32_t)blob.size(); a.childrenOff = (uint32_t)bodiesBytes; a.forcesOff = (uint32_t)(bodiesBytes + childBytes);
     a.levelOrderOff = (uint32_t)(bodiesBytes + childBytes + forceBytes); a.levelStartOff = a.levelOrderOff + (uint32_t)orderBytes;
     a.nlevels = t->nlevels; a.plan = plan;
-    a.lightJoints = 1;
-    for (int i = 1; i < t->nb; ++i) if (t->nuOf[i] > 2) a.lightJoints = 0;
     a.jointMask = 0;
     for (int i = 1; i < t->nb; ++i) a.jointMask |= 1 << t->bodies[i].joint;
     { const char* e = getenv("SBK_JMASK"); if (e) a.jointMask |= atoi(e); }           // tuning override: force a wider kernel variant
-    { const char* e = getenv("SBK_LIGHT"); if (e) a.lightJoints = atoi(e); }     // tuning override
     a.stageInSmem = (plan != 3 && blob.size() <= 28*1024) ? 1u : 0u;
     { const char* e = getenv("SBK_NOSTAGE"); if (e && atoi(e)) a.stageInSmem = 0; }   // tuning override: read the tables through L1/L2   // two resident CTAs: 2 x (tables + 84 KB carry) <= 227 KB
     CUDA_TRY(cudaStreamSynchronize(b->stream));

@@ -13,7 +13,7 @@ struct KArgs {
     const unsigned char* tables;     // device blob
     uint32_t tableBytes, childrenOff, forcesOff, stageInSmem;
     uint32_t levelOrderOff, levelStartOff; int nlevels, plan;
-    int lightJoints, jointMask;                // 1 if every mobilizer has dof <= 2; bit JT_x set = mobilizer kind x present
+    int pad0_, jointMask;                      // bit JT_x set = mobilizer kind x present in the model
     long long cStride, cInstStride, cSpan;  // cache addressing: base_b + field*cStride + (inst>>cShift)*cSpan + (inst&cMask)*cInstStride
     int cShift, cMask;
     int nb, nq, nu, nquat;
