@@ -42,6 +42,15 @@ int main() {
         matter.calcAcceleration(f, F, udot, A);
         matter.calcResidualForceIgnoringConstraints(f, F, udot, resid);
         double e2 = 0; for (double r : resid) e2 = std::fmax(e2, std::fabs(r));
+        // reactions, Jacobian products, composite inertias: <J v, F> == <v, ~J F>; the reaction on Ground balances gravity at rest
+        std::vector<double> FM, Jv, JtF, R;
+        matter.realizeAcceleration(); matter.calcMobilizerReactionForces(FM);
+        matter.multiplyBySystemJacobian(v, Jv); matter.multiplyBySystemJacobianTranspose(F, JtF); matter.calcCompositeBodyInertias(R);
+        double lhs = 0, rhs = 0;
+        for (int i = 0; i < 6*nb; ++i) lhs += Jv[(size_t)i*N]*F[(size_t)i*N];
+        for (int i = 0; i < nu; ++i)   rhs += v[(size_t)i*N]*JtF[(size_t)i*N];
+        if (!(std::fabs(lhs - rhs) < 1e-9*(1 + std::fabs(lhs))) || FM.size() != (size_t)6*nb*N || R.size() != (size_t)10*nb*N) {
+            std::printf("FAIL: Jacobian adjoint %.3e vs %.3e\n", lhs, rhs); return 1; }
         sbk::BatchedRungeKuttaMerson integ(matter);
         integ.setFixedStepSize(1e-3); integ.stepBy(10);
         std::printf("facade_smoke: |Minv(M v)-v|=%.3e  |ID(FD)|=%.3e  steps=%lld realizations=%lld\n", e1, e2,

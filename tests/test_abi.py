@@ -79,3 +79,27 @@ def test_no_cpu_fallback():
         sb.BatchedMatter(t, 4)
     assert e.value.code == 4 and "no CPU fallback" in str(e.value)
     t.close()
+
+
+def _build_facade_smoke():
+    import subprocess
+    out = os.path.join(ROOT, "build", "facade_smoke")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Iinclude", "-I.", "tests/cpp/facade_smoke.cpp", "-Lsimbody_b200", "-lsbk",
+                        "-Wl,-rpath," + os.path.join(ROOT, "simbody_b200"), "-o", out], cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return out
+
+
+def test_cpp_facade_compiles_against_the_c_abi():
+    """The header-only C++ facade (BatchedMatter.h: the reference's method names over include/sbk.h) must compile
+    and link against libsbk.so without CUDA or Simbody headers."""
+    _build_facade_smoke()
+
+
+@pytest.mark.gpu
+def test_cpp_facade_smoke_runs():
+    import subprocess
+    exe = _build_facade_smoke()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
