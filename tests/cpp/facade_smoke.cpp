@@ -52,10 +52,11 @@ int main() {
         if (!(std::fabs(lhs - rhs) < 1e-9*(1 + std::fabs(lhs))) || FM.size() != (size_t)6*nb*N || R.size() != (size_t)10*nb*N) {
             std::printf("FAIL: Jacobian adjoint %.3e vs %.3e\n", lhs, rhs); return 1; }
         sbk::BatchedRungeKuttaMerson integ(matter);
+        const long long r0 = integ.getNumRealizations();      // the explicit realizeAcceleration() above is counted too
         integ.setFixedStepSize(1e-3); integ.stepBy(10);
         std::printf("facade_smoke: |Minv(M v)-v|=%.3e  |ID(FD)|=%.3e  steps=%lld realizations=%lld\n", e1, e2,
                     integ.getNumStepsTaken(), integ.getNumRealizations());
-        if (!(e1 < 1e-9 && e2 < 1e-8 && integ.getNumStepsTaken() == 10LL*N && integ.getNumRealizations() == 50LL*N)) { std::printf("FAIL\n"); return 1; }
+        if (!(e1 < 1e-9 && e2 < 1e-8 && integ.getNumStepsTaken() == 10LL*N && integ.getNumRealizations() - r0 == 50LL*N)) { std::printf("FAIL\n"); return 1; }
         std::printf("OK\n");
         return 0;
     } catch (const std::exception& e) { std::printf("FAIL: %s\n", e.what()); return 1; }
