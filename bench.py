@@ -142,7 +142,8 @@ def main():
     ap.add_argument("--steps-per-launch", type=int, default=0, help="RKM steps per bench step (0 = per-workload default)")
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--all-workloads", action="store_true", help="also report the other configs in 'workloads'")
+    ap.add_argument("--all-workloads", action="store_true", help="(default behaviour now) also report the other configs in 'workloads'")
+    ap.add_argument("--no-extra-workloads", action="store_true", help="report only --workload")
     args = ap.parse_args()
 
     from _harness import ModelInfo
@@ -309,16 +310,25 @@ def main():
         else:
             line["cpu_baseline"] = {"value": None, "unit": "instance-steps/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
 
-    if args.all_workloads:
+    # the other BASELINE configs ride along in 'workloads' (a few seconds each); only the default workload's line is
+    # the contract, so a failure here is reported, not fatal
+    if not args.no_extra_workloads and (args.all_workloads or args.workload == "double_pendulum_1M"):
         extra = {}
         for name in sorted(WORKLOADS):
             if name == args.workload:
                 continue
-            rr = measure(name, dict(WORKLOADS[name]), max(3, args.steps // 2), args.warmup, 0)
+            try:
+                rr = measure(name, dict(WORKLOADS[name]), max(3, args.steps // 2), args.warmup, 0)
+            except Exception as ex:           # noqa: BLE001
+                extra[name] = {"error": str(ex)[:200]}
+                continue
             tf = rr["value"] / world * rr["flop_per_inst_step"] / 1e12
             extra[name] = {"value": rr["value"], "e2e": rr["e2e"], "ms_per_step": rr["ms_per_step"], "fp64_frac": tf / fp64_peak_tflops,
                            "achieved_tflops": tf, "rkm_steps_per_bench_step": rr["spl"], "instances_per_gpu": rr["N"],
-                           "realize_acceleration_per_s": rr["realize_per_s"], "plan": rr["plan"]}
+                           "realize_acceleration_per_s": rr["realize_per_s"], "plan": rr["plan"],
+                           "fp64_pipe_active_ncu": NCU_FP64_PIPE_ACTIVE.get(name),
+                           "hbm_traffic_frac_ncu": (NCU_TRAFFIC_PER_INSTANCE_STEP.get(name, 0) * rr["value"] / world / 1e9 / peaks["hbm_gbs"])
+                                                   if peaks.get("hbm_gbs") else None}
         line["workloads"] = extra
 
     if rank == 0:
