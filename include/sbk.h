@@ -137,6 +137,13 @@ int         sbk_device_count(void);
 
 /* ---- topology: replaces SimbodyMatterSubsystemRep::endConstruction
  *      (Simbody/src/SimbodyMatterSubsystemRep.cpp:256-330) for the supported subset ------ */
+/* Flags of sbk_topology_create_ex.  SBK_TOPOLOGY_EULER_ANGLES mirrors SimbodyMatterSubsystem::setUseEulerAngles
+ * (SimbodyMatterSubsystem.h): Ball / Free orientations are three body-fixed x-y-z angles instead of a
+ * quaternion (RigidBodyNodeSpec_Ball.h:118-160, _Free.h:147-250); the q slots keep their quaternion-sized
+ * allocation (the last one is unused), there are no quaternion constraints to project.            */
+enum { SBK_TOPOLOGY_EULER_ANGLES = 1 };
+sbk_topology* sbk_topology_create_ex(const sbk_body_desc* bodies, int nb,
+                                     const sbk_force_desc* forces, int nf, unsigned flags);
 sbk_topology* sbk_topology_create(const sbk_body_desc* bodies, int nb,
                                   const sbk_force_desc* forces, int nf);
 void sbk_topology_destroy(sbk_topology*);

@@ -97,6 +97,7 @@ struct RefSystem {
                 Force::MobilityConstantForce(forces, matter.getMobilizedBody(MobilizedBodyIndex(f.body)), MobilizerUIndex(f.coord), f.a);
         }
         defaultState = system.realizeTopology();
+        if (spec.useEulerAngles) matter.setUseEulerAngles(defaultState, true);
         system.realizeModel(defaultState);
         nq = defaultState.getNQ(); nu = defaultState.getNU();
         nquat = matter.getNumQuaternionsInUse(defaultState);
@@ -344,7 +345,7 @@ int main(int argc, char** argv) {
         }
         RefSystem rs(spec);
         if (cmd == "lower") {
-            sbk::ModelSpec low = sbk::lowerSimbodySystem(rs.system, rs.matter, &rs.forces, spec.name);
+            sbk::ModelSpec low = sbk::lowerSimbodySystem(rs.system, rs.matter, &rs.forces, spec.name, &rs.defaultState);
             std::fputs(sbk::toText(low).c_str(), stdout);
             return 0;
         }

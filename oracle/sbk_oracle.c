@@ -34,7 +34,8 @@
 #include <stdlib.h>
 #include <string.h>
 
-enum { PIN = 1, SLIDER = 2, UNIVERSAL = 3, BALL = 4, FREE = 5, WELD = 6, TRANSLATION = 7, CYLINDER = 8, PLANAR = 9, GIMBAL = 10 };
+enum { PIN = 1, SLIDER = 2, UNIVERSAL = 3, BALL = 4, FREE = 5, WELD = 6, TRANSLATION = 7, CYLINDER = 8, PLANAR = 9, GIMBAL = 10,
+       BALL_EULER = 11, FREE_EULER = 12 };   /* Ball / Free under setUseEulerAngles: x-y-z angles, last q slot unused */
 enum { F_GRAVITY = 1, F_SPRING = 2, F_DAMPER = 3, F_UNIFORM_GRAVITY = 4, F_GLOBAL_DAMPER = 5, F_MOBILITY_CONSTANT = 6 };
 #define MAXD 6
 
@@ -58,8 +59,8 @@ typedef struct {   /* per-body cache, dense */
     int q0, u0, nq, nu;
 } Body;
 
-static int NQ(int j) { return j == PIN || j == SLIDER ? 1 : (j == UNIVERSAL || j == CYLINDER) ? 2 : (j == TRANSLATION || j == PLANAR || j == GIMBAL) ? 3 : j == BALL ? 4 : j == FREE ? 7 : 0; }
-static int NU(int j) { return j == PIN || j == SLIDER ? 1 : (j == UNIVERSAL || j == CYLINDER) ? 2 : (j == BALL || j == TRANSLATION || j == PLANAR || j == GIMBAL) ? 3 : j == FREE ? 6 : 0; }
+static int NQ(int j) { return j == PIN || j == SLIDER ? 1 : (j == UNIVERSAL || j == CYLINDER) ? 2 : (j == TRANSLATION || j == PLANAR || j == GIMBAL) ? 3 : (j == BALL || j == BALL_EULER) ? 4 : (j == FREE || j == FREE_EULER) ? 7 : 0; }
+static int NU(int j) { return j == PIN || j == SLIDER ? 1 : (j == UNIVERSAL || j == CYLINDER) ? 2 : (j == BALL || j == BALL_EULER || j == TRANSLATION || j == PLANAR || j == GIMBAL) ? 3 : (j == FREE || j == FREE_EULER) ? 6 : 0; }
 
 static void matvec3(const double* R, const double* v, double* o) { for (int i = 0; i < 3; ++i) o[i] = R[3*i]*v[0] + R[3*i+1]*v[1] + R[3*i+2]*v[2]; }
 static void matmul3(const double* A, const double* B, double* C) {
@@ -157,6 +158,13 @@ static void kinematics(const Model* M, Body* B, const double* q, const double* u
         } else if (jt == TRANSLATION) { pfm[0] = qb[0]; pfm[1] = qb[1]; pfm[2] = qb[2]; Hv[0][0] = Hv[1][1] = Hv[2][2] = 1;   /* _Translation.h:100-130 */
         } else if (jt == CYLINDER) {  /* _Cylinder.h:110-139 */
             double c = cos(qb[0]), s = sin(qb[0]); Rfm[0] = c; Rfm[1] = -s; Rfm[3] = s; Rfm[4] = c; pfm[2] = qb[1]; Hw[0][2] = 1; Hv[1][2] = 1;
+        } else if (jt == BALL_EULER || jt == FREE_EULER) {   /* _Ball.h:118-160, _Free.h:147-180: x-y-z angles, H_FM = I */
+            double c0 = cos(qb[0]), c1 = cos(qb[1]), c2 = cos(qb[2]), s0 = sin(qb[0]), s1 = sin(qb[1]), s2 = sin(qb[2]);
+            double s0s1 = s0*s1, s2c0 = s2*c0, c0c2 = c0*c2, nc1 = -c1;
+            Rfm[0] = c1*c2; Rfm[1] = s2*nc1; Rfm[2] = s1; Rfm[3] = s2c0 + s0s1*c2; Rfm[4] = c0c2 - s0s1*s2; Rfm[5] = s0*nc1;
+            Rfm[6] = s0*s2 - s1*c0c2; Rfm[7] = s0*c2 + s1*s2c0; Rfm[8] = c0*c1;
+            Hw[0][0] = Hw[1][1] = Hw[2][2] = 1;
+            if (jt == FREE_EULER) { pfm[0] = qb[3]; pfm[1] = qb[4]; pfm[2] = qb[5]; Hv[3][0] = Hv[4][1] = Hv[5][2] = 1; }
         } else if (jt == GIMBAL) {    /* _Gimbal.h:108-176, Rotation.h:342-349; u = qdot */
             double c0 = cos(qb[0]), c1 = cos(qb[1]), c2 = cos(qb[2]), s0 = sin(qb[0]), s1 = sin(qb[1]), s2 = sin(qb[2]);
             double s0s1 = s0*s1, s2c0 = s2*c0, c0c2 = c0*c2, nc1 = -c1;
@@ -223,7 +231,12 @@ static void kinematics(const Model* M, Body* B, const double* q, const double* u
         for (int i = 0; i < 3; ++i) { me->a[i] = VD[i]; me->a[3+i] = VD[3+i] + wdv[i]; }
         /* qdot */
         if (qdot) {
-            if (jt == BALL || jt == FREE) { quatN(qb, ub, qdot + me->q0); if (jt == FREE) for (int i = 0; i < 3; ++i) qdot[me->q0+4+i] = ub[3+i]; }
+            if (jt == BALL_EULER || jt == FREE_EULER) {   /* qdot = N_P w (Rotation.h:395-406); unused slot 0 */
+                double c0 = cos(qb[0]), s0 = sin(qb[0]), s1 = sin(qb[1]), oc = 1/cos(qb[1]), t = (s0*ub[1] - c0*ub[2])*oc;
+                qdot[me->q0] = ub[0] + t*s1; qdot[me->q0+1] = c0*ub[1] + s0*ub[2]; qdot[me->q0+2] = -t;
+                if (jt == FREE_EULER) { for (int i = 0; i < 3; ++i) qdot[me->q0+3+i] = ub[3+i]; qdot[me->q0+6] = 0; } else qdot[me->q0+3] = 0;
+            }
+            else if (jt == BALL || jt == FREE) { quatN(qb, ub, qdot + me->q0); if (jt == FREE) for (int i = 0; i < 3; ++i) qdot[me->q0+4+i] = ub[3+i]; }
             else for (int i = 0; i < d; ++i) qdot[me->q0+i] = ub[i];
         }
     }
@@ -296,7 +309,14 @@ static void accelerations(const Model* M, Body* B, const double* fmob, int withB
 static void qdotdot(const Model* M, const Body* B, const double* q, const double* u, const double* udot, double* qdd) {
     for (int b = 1; b < M->nb; ++b) {
         const Body* me = &B[b]; const int jt = M->joint[b];
-        if (jt == BALL || jt == FREE) {
+        if (jt == BALL_EULER || jt == FREE_EULER) {   /* Rotation.h:1041-1060 */
+            const double* qb = q + me->q0; const double* w = u + me->u0; const double* b = udot + me->u0;
+            double c0 = cos(qb[0]), s0 = sin(qb[0]), c1 = cos(qb[1]), s1 = sin(qb[1]), oc = 1/c1;
+            double t = (s0*w[1] - c0*w[2])*oc, qd0 = w[0] + t*s1, qd1 = c0*w[1] + s0*w[2], qd2 = -t;
+            double tb = (s0*b[1] - c0*b[2])*oc, q1oc1 = qd1*oc;
+            qdd[me->q0] = (b[0] + tb*s1) + (qd0*s1 - qd2)*q1oc1; qdd[me->q0+1] = (c0*b[1] + s0*b[2]) + qd0*qd2*c1; qdd[me->q0+2] = -tb + (qd2*s1 - qd0)*q1oc1;
+            if (jt == FREE_EULER) { for (int i = 0; i < 3; ++i) qdd[me->q0+3+i] = udot[me->u0+3+i]; qdd[me->q0+6] = 0; } else qdd[me->q0+3] = 0;
+        } else if (jt == BALL || jt == FREE) {
             const double* w = u + me->u0; double Nb[4]; quatN(q + me->q0, udot + me->u0, Nb);
             double k = -0.25*(w[0]*w[0] + w[1]*w[1] + w[2]*w[2]);
             for (int i = 0; i < 4; ++i) qdd[me->q0+i] = Nb[i] + k*q[me->q0+i];

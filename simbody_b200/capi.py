@@ -45,6 +45,7 @@ SYMBOLS = {
     "sbk_last_error": (ctypes.c_char_p, []),
     "sbk_device_count": (ctypes.c_int, []),
     "sbk_topology_create": (_P, [ctypes.POINTER(BodyDesc), ctypes.c_int, ctypes.POINTER(ForceDesc), ctypes.c_int]),
+    "sbk_topology_create_ex": (_P, [ctypes.POINTER(BodyDesc), ctypes.c_int, ctypes.POINTER(ForceDesc), ctypes.c_int, ctypes.c_uint]),
     "sbk_topology_destroy": (None, [_P]),
     "sbk_topology_counts": (ctypes.c_int, [_P, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
     "sbk_topology_slots": (ctypes.c_int, [_P, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),

@@ -101,9 +101,12 @@ int sbk_device_count(void) {
 
 // ---- topology -----------------------------------------------------------------------------
 sbk_topology* sbk_topology_create(const sbk_body_desc* bodies, int nb, const sbk_force_desc* forces, int nf) {
+    return sbk_topology_create_ex(bodies, nb, forces, nf, 0u);
+}
+sbk_topology* sbk_topology_create_ex(const sbk_body_desc* bodies, int nb, const sbk_force_desc* forces, int nf, unsigned flags) {
     if (!bodies || nb < 1 || nf < 0 || (nf > 0 && !forces)) { fail(SBK_ERR_ARG, "sbk_topology_create: bad arguments"); return nullptr; }
     try {
-        sbk::ModelSpec spec; spec.name = "user";
+        sbk::ModelSpec spec; spec.name = "user"; spec.useEulerAngles = (flags & SBK_TOPOLOGY_EULER_ANGLES) != 0;
         spec.bodies.assign(bodies, bodies + nb);
         if (nf) spec.forces.assign(forces, forces + nf);
         sbk_topology* t = new sbk_topology();

@@ -37,7 +37,8 @@
 namespace sbkd {
 
 enum { JT_GROUND = 0, JT_PIN = 1, JT_SLIDER = 2, JT_UNIVERSAL = 3, JT_BALL = 4, JT_FREE = 5, JT_WELD = 6,
-       JT_TRANSLATION = 7, JT_CYLINDER = 8, JT_PLANAR = 9, JT_GIMBAL = 10 };
+       JT_TRANSLATION = 7, JT_CYLINDER = 8, JT_PLANAR = 9, JT_GIMBAL = 10,
+       JT_BALL_EULER = 11, JT_FREE_EULER = 12 };   // internal: Ball / Free in Euler-angle mode (setUseEulerAngles)
 enum { FK_SPRING = 2, FK_DAMPER = 3, FK_CONSTANT = 6 };
 
 template <int JT> struct JointDims;
@@ -51,15 +52,21 @@ template <> struct JointDims<JT_TRANSLATION> { enum { nq = 3, nu = 3 }; };
 template <> struct JointDims<JT_CYLINDER>  { enum { nq = 2, nu = 2 }; };
 template <> struct JointDims<JT_PLANAR>    { enum { nq = 3, nu = 3 }; };
 template <> struct JointDims<JT_GIMBAL>    { enum { nq = 3, nu = 3 }; };   // body-fixed x-y-z angles, u = qdot
+template <> struct JointDims<JT_BALL_EULER> { enum { nq = 4, nu = 3 }; };  // 3 angles + 1 unused slot, u = w_FM
+template <> struct JointDims<JT_FREE_EULER> { enum { nq = 7, nu = 6 }; };  // 3 angles, 3 translations, 1 unused slot
+SBK_HD constexpr bool isBallLike(int jt) { return jt == JT_BALL || jt == JT_BALL_EULER; }
+SBK_HD constexpr bool isFreeLike(int jt) { return jt == JT_FREE || jt == JT_FREE_EULER; }
+SBK_HD constexpr bool isEulerKind(int jt) { return jt == JT_BALL_EULER || jt == JT_FREE_EULER; }
 // array extent for a dof count that may be zero
 SBK_HD constexpr int dim1(int d) { return d > 0 ? d : 1; }
 
 // mobilizer-kind masks (bit JT_x set = kind present), see SBK_DISPATCH_JOINT_M
 enum { JM_PIN = 1 << JT_PIN, JM_SLIDER = 1 << JT_SLIDER, JM_UNIVERSAL = 1 << JT_UNIVERSAL, JM_BALL = 1 << JT_BALL, JM_FREE = 1 << JT_FREE,
        JM_WELD = 1 << JT_WELD, JM_TRANSLATION = 1 << JT_TRANSLATION, JM_CYLINDER = 1 << JT_CYLINDER, JM_PLANAR = 1 << JT_PLANAR, JM_GIMBAL = 1 << JT_GIMBAL,
+       JM_BALL_EULER = 1 << JT_BALL_EULER, JM_FREE_EULER = 1 << JT_FREE_EULER,
        JM_LIGHT = JM_PIN | JM_SLIDER | JM_UNIVERSAL | JM_WELD,                   // dof <= 2
        JM_MOBILE5 = JM_PIN | JM_SLIDER | JM_UNIVERSAL | JM_BALL | JM_FREE,       // the north_star mobilizer set
-       JM_ALL = JM_MOBILE5 | JM_WELD | JM_TRANSLATION | JM_CYLINDER | JM_PLANAR | JM_GIMBAL };
+       JM_ALL = JM_MOBILE5 | JM_WELD | JM_TRANSLATION | JM_CYLINDER | JM_PLANAR | JM_GIMBAL | JM_BALL_EULER | JM_FREE_EULER };
 
 // cache record layout
 enum { F_XGB = 0, F_VGB = 12, F_L = 18, F_MK = 21, F_ACOR = 30, F_GYRO = 36, F_ZB = 42,
@@ -246,9 +253,9 @@ template <bool BLK> SBK_HD long long stateIndex(const Ctx& c, int inst, int slot
 template <bool BLK> SBK_HD double ldS(const Ctx& c, int inst, const double* a, int slot) { return gld(a + stateIndex<BLK>(c, inst, slot)); }
 template <bool BLK> SBK_HD void   stS(const Ctx& c, int inst, double* a, int slot, double v) { gst(a + stateIndex<BLK>(c, inst, slot), v); }
 
-SBK_HD int dofOfJoint(int jt) { return jt == JT_FREE ? 6 : (jt == JT_BALL || jt == JT_TRANSLATION || jt == JT_PLANAR || jt == JT_GIMBAL) ? 3 : (jt == JT_UNIVERSAL || jt == JT_CYLINDER) ? 2
+SBK_HD int dofOfJoint(int jt) { return isFreeLike(jt) ? 6 : (isBallLike(jt) || jt == JT_TRANSLATION || jt == JT_PLANAR || jt == JT_GIMBAL) ? 3 : (jt == JT_UNIVERSAL || jt == JT_CYLINDER) ? 2
                                       : (jt == JT_GROUND || jt == JT_WELD) ? 0 : 1; }
-SBK_HD int nqOfJoint(int jt)  { return jt == JT_FREE ? 7 : jt == JT_BALL ? 4 : (jt == JT_TRANSLATION || jt == JT_PLANAR || jt == JT_GIMBAL) ? 3 : (jt == JT_UNIVERSAL || jt == JT_CYLINDER) ? 2
+SBK_HD int nqOfJoint(int jt)  { return isFreeLike(jt) ? 7 : isBallLike(jt) ? 4 : (jt == JT_TRANSLATION || jt == JT_PLANAR || jt == JT_GIMBAL) ? 3 : (jt == JT_UNIVERSAL || jt == JT_CYLINDER) ? 2
                                       : (jt == JT_GROUND || jt == JT_WELD) ? 0 : 1; }
 SBK_HD M3 loadR(const double* X) { M3 R;
 #pragma unroll
@@ -263,6 +270,12 @@ SBK_HD void quatNTimes(const double* q, V3 w, double* out) {
     out[1] = e0*w.x  + e3*w.y  + ne2*w.z;
     out[2] = ne3*w.x + e0*w.y  + e1*w.z;
     out[3] = e2*w.x  + ne1*w.y + e0*w.z;
+}
+// Body-fixed x-y-z Euler angles: qdot = N_P(q) * w with sc = {c0, s0, c1, s1, 1/c1} (Rotation.h:395-406)
+SBK_HD V3 eulerNTimes(const double* sc, V3 w) {
+    const double c0 = sc[0], s0 = sc[1], s1 = sc[3], oocosy = sc[4];
+    const double t = (s0*w.y - c0*w.z)*oocosy;
+    return mk(w.x + t*s1, c0*w.y + s0*w.z, -t);
 }
 // Unnormalised NInv(q) * qd (Rotation.h:742-748)
 SBK_HD V3 quatNInvTimes(const double* q, const double* qd) {
@@ -304,7 +317,7 @@ template <int d> struct KinLocal {
     V3 r;                            // r_MB_F = R_FM * p_MB
     M3 R_PB; V3 p_PB;                // X_PB
     double qerr;                     // |q| - 1 for quaternion mobilizers
-    double sc[4];                    // Gimbal: c0, s0, c1, s1 (the reference's q pool, _Gimbal.h:108-126)
+    double sc[5];                    // Gimbal / Euler-angle mode: c0, s0, c1, s1, 1/c1 (the reference's q pool)
 };
 
 template <int JT>
@@ -324,6 +337,18 @@ SBK_HD void kinLocal(const BodyConst& bc, const double* q, KinLocal<JointDims<JT
         k.Hw[0] = mk(0, 0, 1);
         if constexpr (JT == JT_CYLINDER) { p_FM = mk(0, 0, q[1]); k.Hv[1] = mk(0, 0, 1); }
         if constexpr (JT == JT_PLANAR)   { p_FM = mk(q[1], q[2], 0); k.Hv[1] = mk(1, 0, 0); k.Hv[2] = mk(0, 1, 0); }
+    } else if constexpr (JT == JT_BALL_EULER || JT == JT_FREE_EULER) {   // _Ball.h:118-160, _Free.h:147-180: x-y-z angles, H_FM = I
+        double s0, c0, s1, c1, s2, c2; sincos(q[0], &s0, &c0); sincos(q[1], &s1, &c1); sincos(q[2], &s2, &c2);
+        const double s0s1 = s0*s1, s2c0 = s2*c0, c0c2 = c0*c2, nc1 = -c1;
+        R_FM.a[0] = c1*c2;             R_FM.a[1] = s2*nc1;            R_FM.a[2] = s1;
+        R_FM.a[3] = s2c0 + s0s1*c2;    R_FM.a[4] = c0c2 - s0s1*s2;    R_FM.a[5] = s0*nc1;
+        R_FM.a[6] = s0*s2 - s1*c0c2;   R_FM.a[7] = s0*c2 + s1*s2c0;   R_FM.a[8] = c0*c1;
+        k.Hw[0] = mk(1, 0, 0); k.Hw[1] = mk(0, 1, 0); k.Hw[2] = mk(0, 0, 1);
+        k.sc[0] = c0; k.sc[1] = s0; k.sc[2] = c1; k.sc[3] = s1; k.sc[4] = 1/c1;      // trouble at +-90 degrees, as in the reference
+        if constexpr (JT == JT_FREE_EULER) {
+            p_FM = mk(q[3], q[4], q[5]);
+            k.Hv[3] = mk(1, 0, 0); k.Hv[4] = mk(0, 1, 0); k.Hv[5] = mk(0, 0, 1);
+        }
     } else if constexpr (JT == JT_GIMBAL) {       // RigidBodyNodeSpec_Gimbal.h:108-176, Rotation.h:342-349
         double s0, c0, s1, c1, s2, c2; sincos(q[0], &s0, &c0); sincos(q[1], &s1, &c1); sincos(q[2], &s2, &c2);
         const double s0s1 = s0*s1, s2c0 = s2*c0, c0c2 = c0*c2, nc1 = -c1;
@@ -410,7 +435,7 @@ SBK_HD void jointH(const M3& R_GF, const KinLocal<JointDims<JT>::nu>& k, SV* H) 
         H[2].w = mul(R_GF, k.Hw[2]); H[2].v = mul(R_GF, cross(k.Hw[2], r));
     } else {
         SBK_ROTCOL(0, 0) SBK_ROTCOL(1, 1) SBK_ROTCOL(2, 2)
-        if constexpr (JT == JT_FREE) { SBK_TRCOL(3, 0) SBK_TRCOL(4, 1) SBK_TRCOL(5, 2) }
+        if constexpr (isFreeLike(JT)) { SBK_TRCOL(3, 0) SBK_TRCOL(4, 1) SBK_TRCOL(5, 2) }
     }
     #undef SBK_ROTCOL
     #undef SBK_TRCOL
@@ -488,7 +513,7 @@ SBK_HD void kinGlobal(const BodyConst& bc, const KinLocal<JointDims<JT>::nu>& k,
         }
     } else {
         SBK_ROTCOL_D(0, 0) SBK_ROTCOL_D(1, 1) SBK_ROTCOL_D(2, 2)
-        if constexpr (JT == JT_FREE) { SBK_TRCOL_D(3) SBK_TRCOL_D(4) SBK_TRCOL_D(5) }
+        if constexpr (isFreeLike(JT)) { SBK_TRCOL_D(3) SBK_TRCOL_D(4) SBK_TRCOL_D(5) }
     }
     #undef SBK_ROTCOL_D
     #undef SBK_TRCOL_D
@@ -500,7 +525,12 @@ SBK_HD void kinGlobal(const BodyConst& bc, const KinLocal<JointDims<JT>::nu>& k,
     o.acor.w = VD.w; o.acor.v = VD.v + cross(w_GP, o.V.v - v_GP);
 
     // ---- qdot = N(q) u  ------------------------------------------------------------------------
-    if constexpr (JT == JT_BALL || JT == JT_FREE) {
+    if constexpr (isEulerKind(JT)) {              // qdot = N_P(q) w_FM (Rotation.h:395-406); unused slot = 0 (_Free.h:238-249)
+        const V3 qd = eulerNTimes(k.sc, mk(u[0], u[1], u[2]));
+        qdot[0] = qd.x; qdot[1] = qd.y; qdot[2] = qd.z;
+        if constexpr (JT == JT_FREE_EULER) { qdot[3] = u[3]; qdot[4] = u[4]; qdot[5] = u[5]; qdot[6] = 0; }
+        else qdot[3] = 0;
+    } else if constexpr (JT == JT_BALL || JT == JT_FREE) {
         quatNTimes(q, mk(u[0], u[1], u[2]), qdot);
         if constexpr (JT == JT_FREE) {
 #pragma unroll
@@ -634,7 +664,16 @@ SBK_HD void accCore(const SV* H, const SV* G, const double* DI, const double* ep
 template <int JT>
 SBK_HD void qddCore(const double* q, const double* u, const double* udot, double* qdd) {
     constexpr int d = JointDims<JT>::nu;
-    if constexpr (JT == JT_BALL || JT == JT_FREE) {
+    if constexpr (isEulerKind(JT)) {              // qdotdot = N b + NDot w (Rotation.h:1041-1060)
+        double sc[5]; double s2unused, c2unused;
+        sincos(q[0], &sc[1], &sc[0]); sincos(q[1], &sc[3], &sc[2]); sc[4] = 1/sc[2]; (void)s2unused; (void)c2unused;
+        const V3 qd = eulerNTimes(sc, mk(u[0], u[1], u[2]));
+        const V3 Nb = eulerNTimes(sc, mk(udot[0], udot[1], udot[2]));
+        const double q1oc1 = qd.y*sc[4];
+        qdd[0] = Nb.x + (qd.x*sc[3] - qd.z)*q1oc1; qdd[1] = Nb.y + qd.x*qd.z*sc[2]; qdd[2] = Nb.z + (qd.z*sc[3] - qd.x)*q1oc1;
+        if constexpr (JT == JT_FREE_EULER) { qdd[3] = udot[3]; qdd[4] = udot[4]; qdd[5] = udot[5]; qdd[6] = 0; }
+        else qdd[3] = 0;
+    } else if constexpr (JT == JT_BALL || JT == JT_FREE) {
         const V3 w = mk(u[0], u[1], u[2]);
         double Nb[4]; quatNTimes(q, mk(udot[0], udot[1], udot[2]), Nb);
         const double k = -0.25*dot(w, w);
@@ -822,7 +861,7 @@ SBK_BODY void outwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex
     }
     if (qdotdotDst) {
         double q[dim1(NQ)], u[dim1(d)], qdd[dim1(NQ)];
-        if constexpr (JT == JT_BALL || JT == JT_FREE) {
+        if constexpr (JT == JT_BALL || JT == JT_FREE || isEulerKind(JT)) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) q[i] = ldS<false>(c, inst, c.q, bc.q0 + i);
 #pragma unroll
@@ -1115,6 +1154,8 @@ SBK_BODY void idInBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, c
         case JT_CYLINDER:  { constexpr int JT = JT_CYLINDER;  CALL; } break;        \
         case JT_PLANAR:    { constexpr int JT = JT_PLANAR;    CALL; } break;        \
         case JT_GIMBAL:    { constexpr int JT = JT_GIMBAL;    CALL; } break;        \
+        case JT_BALL_EULER: { constexpr int JT = JT_BALL_EULER; CALL; } break;      \
+        case JT_FREE_EULER: { constexpr int JT = JT_FREE_EULER; CALL; } break;      \
         default: break;                                                             \
     }
 
@@ -1145,6 +1186,8 @@ template <bool WITH_COR, bool CB = false> SBK_HD void outwardDispatch(const Ctx&
         case JT_CYLINDER:  if constexpr (((JMASK) & JM_CYLINDER) != 0)  { constexpr int JT = JT_CYLINDER;  CALL; } break; \
         case JT_PLANAR:    if constexpr (((JMASK) & JM_PLANAR) != 0)    { constexpr int JT = JT_PLANAR;    CALL; } break; \
         case JT_GIMBAL:    if constexpr (((JMASK) & JM_GIMBAL) != 0)    { constexpr int JT = JT_GIMBAL;    CALL; } break; \
+        case JT_BALL_EULER: if constexpr (((JMASK) & JM_BALL_EULER) != 0) { constexpr int JT = JT_BALL_EULER; CALL; } break; \
+        case JT_FREE_EULER: if constexpr (((JMASK) & JM_FREE_EULER) != 0) { constexpr int JT = JT_FREE_EULER; CALL; } break; \
         default: break;                                                                                             \
     }
 

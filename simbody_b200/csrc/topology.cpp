@@ -28,7 +28,7 @@ void compileTopology(const ModelSpec& spec, sbk_topology& t) {
         t.level[b] = t.level[d.parent] + 1;
         t.q0[b] = nextQ; t.nqOf[b] = jointNQ(d.joint_type); nextQ += t.nqOf[b];
         t.u0[b] = nextU; t.nuOf[b] = jointNU(d.joint_type); nextU += t.nuOf[b];
-        if (d.joint_type == SBK_JOINT_BALL || d.joint_type == SBK_JOINT_FREE) t.quatIndex[b] = nextQuat++;
+        if ((d.joint_type == SBK_JOINT_BALL || d.joint_type == SBK_JOINT_FREE) && !spec.useEulerAngles) t.quatIndex[b] = nextQuat++;
         kids[d.parent].push_back(b);
     }
     t.nq = nextQ; t.nu = nextU; t.nquat = nextQuat; t.isChain = chain && nb > 1;
@@ -90,6 +90,8 @@ void compileTopology(const ModelSpec& spec, sbk_topology& t) {
         for (int i = 0; i < 3; ++i) bc.com_B[i] = d.com_B[i];
         for (int i = 0; i < 6; ++i) bc.G_B[i] = d.unit_inertia_OB_B[i];
         bc.joint = d.joint_type; bc.parent = d.parent < 0 ? 0 : d.parent;
+        if (spec.useEulerAngles && d.joint_type == SBK_JOINT_BALL) bc.joint = sbkd::JT_BALL_EULER;     // internal kinds: x-y-z angles
+        if (spec.useEulerAngles && d.joint_type == SBK_JOINT_FREE) bc.joint = sbkd::JT_FREE_EULER;
         bc.q0 = t.q0[b]; bc.u0 = t.u0[b]; bc.quat = t.quatIndex[b]; bc.level = t.level[b];
         bc.flags = 0;
         auto isIdentityR = [](const double* X) { return X[0] == 1 && X[4] == 1 && X[8] == 1 && X[1] == 0 && X[2] == 0 &&

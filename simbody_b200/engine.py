@@ -31,7 +31,7 @@ def model_text(name, n=0):
 
 
 class Topology:
-    def __init__(self, text=None, bodies=None, forces=None):
+    def __init__(self, text=None, bodies=None, forces=None, use_euler_angles=False):
         self.lib = load_library()
         if text is not None:
             self.handle = self.lib.sbk_topology_from_text(text.encode())
@@ -39,7 +39,7 @@ class Topology:
             nb, nf = len(bodies), len(forces or [])
             barr = (capi.BodyDesc * nb)(*bodies)
             farr = (capi.ForceDesc * max(nf, 1))(*(forces or []))
-            self.handle = self.lib.sbk_topology_create(barr, nb, farr if nf else None, nf)
+            self.handle = self.lib.sbk_topology_create_ex(barr, nb, farr if nf else None, nf, 1 if use_euler_angles else 0)
         if not self.handle:
             raise SbkError(3, self.lib.sbk_last_error().decode())
         v = [ctypes.c_int() for _ in range(5)]

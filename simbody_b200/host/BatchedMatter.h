@@ -36,8 +36,9 @@ inline void throwOnError(int rc) {
 class Topology {
 public:
     explicit Topology(const ModelSpec& spec)
-    :   h_(sbk_topology_create(spec.bodies.data(), (int)spec.bodies.size(),
-                               spec.forces.empty() ? nullptr : spec.forces.data(), (int)spec.forces.size())) {
+    :   h_(sbk_topology_create_ex(spec.bodies.data(), (int)spec.bodies.size(),
+                                  spec.forces.empty() ? nullptr : spec.forces.data(), (int)spec.forces.size(),
+                                  spec.useEulerAngles ? SBK_TOPOLOGY_EULER_ANGLES : 0u)) {
         if (!h_) throw std::runtime_error(sbk_last_error());
         throwOnError(sbk_topology_counts(h_, &nb_, &nq_, &nu_, &nquat_, &nlevels_));
     }

@@ -21,7 +21,7 @@
 //
 // Requires the Simbody headers; it is compiled only into programs that link Simbody
 // (oracle/ref_driver.cpp here, the user's program in production).  Unsupported features
-// (other mobilizers, reversed mobilizers, constraints, other force types, Euler-angle mode)
+// (other mobilizers, reversed mobilizers, constraints, other force types)
 // raise std::runtime_error rather than being silently dropped.
 #pragma once
 #include <string>
@@ -38,7 +38,8 @@ inline void lowerTransform(const SimTK::Transform& X, double out[12]) {
 inline ModelSpec lowerSimbodySystem(const SimTK::MultibodySystem&        system,
                                     const SimTK::SimbodyMatterSubsystem& matter,
                                     const SimTK::GeneralForceSubsystem*  forces,
-                                    const std::string& name = "lowered")
+                                    const std::string& name = "lowered",
+                                    const SimTK::State* modelState = nullptr)   // where the modeling options live (Euler-angle mode)
 {
     using namespace SimTK;
     if (!system.systemTopologyHasBeenRealized())
@@ -51,8 +52,7 @@ inline ModelSpec lowerSimbodySystem(const SimTK::MultibodySystem&        system,
     ModelSpec spec; spec.name = name;
     const int nb = matter.getNumBodies();
     State state = system.getDefaultState();
-    if (matter.getUseEulerAngles(state))
-        throw std::runtime_error("lowerSimbodySystem: Euler-angle mode is not supported (quaternions only)");
+    spec.useEulerAngles = modelState ? matter.getUseEulerAngles(*modelState) : matter.getUseEulerAngles(state);
 
     std::vector<int> uFirst(nb, 0), uCount(nb, 0);
     for (MobilizedBodyIndex mbx(0); mbx < nb; ++mbx) {

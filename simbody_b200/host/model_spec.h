@@ -28,6 +28,7 @@ struct ModelSpec {
     std::string                 name;
     std::vector<sbk_body_desc>  bodies;   // [0] = Ground, MobilizedBodyIndex order
     std::vector<sbk_force_desc> forces;
+    bool                        useEulerAngles = false;   // SimbodyMatterSubsystem::setUseEulerAngles: Ball / Free use x-y-z angles
 };
 
 inline int jointNQ(int jt) {
@@ -313,6 +314,7 @@ inline ModelSpec makeNamedModel(const std::string& name, int n) {
     if (name == "double_pendulum") return makePinChain(2, "double_pendulum");
     if (name == "pin_chain")       return makePinChain(n > 0 ? n : 50);
     if (name == "mixed7")          return makeMixed7();
+    if (name == "mixed7e")         { ModelSpec m = makeMixed7(); m.name = "mixed7e"; m.useEulerAngles = true; return m; }   // Euler-angle mode
     if (name == "ugdamp5")         return makeUgDamp5();
     if (name == "welded8")         return makeWelded8();
     if (name == "cartesian8")      return makeCartesian8();
@@ -325,7 +327,7 @@ inline ModelSpec makeNamedModel(const std::string& name, int n) {
 inline std::string toText(const ModelSpec& m) {
     std::string out; char buf[64];
     auto num = [&](double v) { std::snprintf(buf, sizeof buf, " %.17g", v); out += buf; };
-    out += "sbkmodel 1\nname " + m.name + "\nnb " + std::to_string(m.bodies.size()) + "\n";
+    out += "sbkmodel 1\nname " + m.name + "\n" + (m.useEulerAngles ? "euler 1\n" : "") + "nb " + std::to_string(m.bodies.size()) + "\n";
     for (size_t i = 0; i < m.bodies.size(); ++i) {
         const sbk_body_desc& b = m.bodies[i];
         out += "body " + std::to_string(i) + " " + std::to_string(b.parent) + " " + jointName(b.joint_type);
@@ -353,7 +355,9 @@ inline ModelSpec fromText(const std::string& text) {
     if (!(in >> tok >> ver) || tok != "sbkmodel" || ver != 1) throw std::runtime_error("not an sbkmodel v1 text");
     ModelSpec m; int nb = 0, nf = 0;
     in >> tok >> m.name;  if (tok != "name") throw std::runtime_error("expected 'name'");
-    in >> tok >> nb;      if (tok != "nb" || nb < 1) throw std::runtime_error("expected 'nb'");
+    in >> tok >> nb;
+    if (tok == "euler") { m.useEulerAngles = nb != 0; in >> tok >> nb; }
+    if (tok != "nb" || nb < 1) throw std::runtime_error("expected 'nb'");
     for (int i = 0; i < nb; ++i) {
         int idx; std::string jn; sbk_body_desc b; std::memset(&b, 0, sizeof b);
         in >> tok >> idx >> b.parent >> jn;

@@ -20,6 +20,7 @@ CASES = [  # name, size param, n eval states, (h, nsteps), q_scale
     ("double_pendulum", 0, 8, (1e-3, 25), 3.0),
     ("pin_chain", 50, 4, (1e-3, 5), 1.0),
     ("mixed7", 0, 8, (1e-3, 25), 1.0),
+    ("mixed7e", 0, 6, (1e-3, 25), 0.6),          # SimbodyMatterSubsystem::setUseEulerAngles: Ball / Free with x-y-z angles
     ("ugdamp5", 0, 6, (1e-3, 20), 0.7),          # Force::UniformGravity + Force::GlobalDamper
     ("welded8", 0, 6, (1e-3, 20), 0.7),          # MobilizedBody::Weld inside the chain and as a leaf
     ("cartesian8", 0, 6, (1e-3, 20), 0.7),       # MobilizedBody::Planar / Cylinder / Translation

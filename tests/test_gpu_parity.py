@@ -20,7 +20,7 @@ from _harness import ModelInfo, RefDriver, check_sdfast2, have_ref, rel_err
 pytestmark = pytest.mark.gpu
 TOL = 1e-11
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-MODELS = ["double_pendulum", "pin_chain", "mixed7", "ugdamp5", "welded8", "cartesian8", "humanoid30", "branched_tree"]
+MODELS = ["double_pendulum", "pin_chain", "mixed7", "mixed7e", "ugdamp5", "welded8", "cartesian8", "humanoid30", "branched_tree"]
 
 
 def soa(a):
@@ -178,7 +178,7 @@ def test_fused_plan_matches_generic_plan():
     bm.close(); topo.close()
 
 
-@pytest.mark.parametrize("name", ["mixed7", "welded8", "cartesian8", "humanoid30", "branched_tree"])
+@pytest.mark.parametrize("name", ["mixed7", "mixed7e", "welded8", "cartesian8", "humanoid30", "branched_tree"])
 def test_level_parallel_plan_matches_golden(name):
     """Plan 3 (CTA per instance, threads over the bodies of a level) against the reference."""
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
@@ -198,7 +198,7 @@ def test_level_parallel_plan_matches_golden(name):
     bm.close(); topo.close()
 
 
-@pytest.mark.parametrize("name", ["mixed7", "welded8", "cartesian8", "humanoid30", "branched_tree"])
+@pytest.mark.parametrize("name", ["mixed7", "mixed7e", "welded8", "cartesian8", "humanoid30", "branched_tree"])
 def test_grid_level_parallel_plan_matches_golden(name):
     """Plan 4 (persistent grid, work items = body of a level x warp of instances, grid barriers between
     levels) against the reference: fixed-step RKM, plus agreement with plan 1 on a batch that is not a
@@ -345,7 +345,7 @@ def test_reactions_and_jacobian_match_golden(name):
     got = run_extras(info, g["extras_in"])
     for k in ref:
         assert rel_err(got[k], ref[k]) < TOL, (name, k, rel_err(got[k], ref[k]))
-    if name in ("mixed7", "welded8", "cartesian8", "humanoid30", "branched_tree"):
+    if name in ("mixed7", "mixed7e", "welded8", "cartesian8", "humanoid30", "branched_tree"):
         for plan in (3, 4):                                    # level-parallel record layout; grid-level realize
             gotp = run_extras(info, g["extras_in"], plan=plan)
             for k in ref:

@@ -14,7 +14,7 @@ import pytest
 from _harness import COracle, HostEmu, ModelInfo, RefDriver, check_sdfast2, have_ref, rel_err, ROOT
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-MODELS = ["double_pendulum", "pin_chain", "mixed7", "ugdamp5", "welded8", "cartesian8", "humanoid30", "branched_tree"]
+MODELS = ["double_pendulum", "pin_chain", "mixed7", "mixed7e", "ugdamp5", "welded8", "cartesian8", "humanoid30", "branched_tree"]
 
 
 @pytest.fixture(scope="module")
