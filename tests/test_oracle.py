@@ -128,7 +128,8 @@ def test_quaternion_projection_rule(built):
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
-@pytest.mark.parametrize("name,n", [("double_pendulum", 0), ("pin_chain", 12), ("mixed7", 0), ("humanoid30", 0), ("branched_tree", 33)])
+@pytest.mark.parametrize("name,n", [("double_pendulum", 0), ("pin_chain", 12), ("mixed7", 0), ("mixed7e", 0), ("ugdamp5", 0), ("welded8", 0),
+                                    ("cartesian8", 0), ("humanoid30", 0), ("branched_tree", 33)])
 def test_live_reference_differential(built, name, n):
     emu, ref, co = HostEmu(), RefDriver(), COracle()
     text = emu.model_text(name, n)
@@ -191,7 +192,8 @@ def test_adaptive_rkm_reproduces_readme_run_on_host(built):
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
-@pytest.mark.parametrize("name,n,tf,qs", [("double_pendulum", 0, 3.0, 2.0), ("mixed7", 0, 1.0, 0.5), ("humanoid30", 0, 0.3, 0.4)])
+@pytest.mark.parametrize("name,n,tf,qs", [("double_pendulum", 0, 3.0, 2.0), ("mixed7", 0, 1.0, 0.5), ("mixed7e", 0, 1.0, 0.5), ("cartesian8", 0, 1.0, 0.5),
+                                           ("humanoid30", 0, 0.3, 0.4)])
 def test_adaptive_rkm_matches_live_reference(built, name, n, tf, qs):
     emu, ref = HostEmu(), RefDriver()
     info = ModelInfo(emu.model_text(name, n))
