@@ -1223,35 +1223,36 @@ template <bool LEAN, int JMASK = JM_ALL, bool CB = false> SBK_HD void tpiEvalDer
         tpiOutward<true, CB>(c, inst, udotDst, qddDst);
     } else {
         const SV z0 = zeroSV();
-        // pre(k): the coordinate slot of the k-th body step of this evaluation (two alternate)
-        #define SBK_PRE(k) (cy + (CY_PRE + 4*((k) & 1))*SBK_CARRY_STRIDE)
-        #define SBK_GNU(k) (cy + (CY_GNU + GNU_ROWS*((k) & 1))*SBK_CARRY_STRIDE)
-        int k = 0;
+        // Two coordinate / G-nu slots alternate from body step to body step.  The slot parity follows from the
+        // body index alone (outward sweeps: (b-1)&1, inward sweep: b&1 -- consecutive across the sweep changes),
+        // so no step counter has to live across the joint switch.
+        #define SBK_PRE(par) (cy + (CY_PRE + 4*((par) & 1))*SBK_CARRY_STRIDE)
+        #define SBK_GNU(par) (cy + (CY_GNU + GNU_ROWS*((par) & 1))*SBK_CARRY_STRIDE)
         cyStoreOut(cy, identity3(), zero3(), z0);                                 // Ground's link for body 1
         preloadCoords<JMASK>(c, inst, T.bodies[1], SBK_PRE(0));
 #pragma unroll 1
-        for (int b = 1; b < c.nb; ++b, ++k) {
+        for (int b = 1; b < c.nb; ++b) {
             const BodyConst& bc = T.bodies[b];
-            preloadCoords<JMASK>(c, inst, T.bodies[b + 1 < c.nb ? b + 1 : c.nb - 1], SBK_PRE(k + 1));   // after the last body: the first of the inward sweep
+            preloadCoords<JMASK>(c, inst, T.bodies[b + 1 < c.nb ? b + 1 : c.nb - 1], SBK_PRE(b));       // after the last body: the first of the inward sweep
             preloadWait();
-            SBK_DISPATCH_JOINT_M(JMASK, bc.joint, (leanKinBody<JT>(c, bc, inst, cy, SBK_PRE(k), qdotDst)));
+            SBK_DISPATCH_JOINT_M(JMASK, bc.joint, (leanKinBody<JT>(c, bc, inst, cy, SBK_PRE(b - 1), qdotDst)));
         }
 #pragma unroll 1
-        for (int b = c.nb - 1; b >= 1; --b, ++k) {
+        for (int b = c.nb - 1; b >= 1; --b) {
             const BodyConst& bc = T.bodies[b];
-            preloadCoords<JMASK>(c, inst, T.bodies[b > 1 ? b - 1 : 1], SBK_PRE(k + 1));                  // after body 1: the first of the outward sweep
+            preloadCoords<JMASK>(c, inst, T.bodies[b > 1 ? b - 1 : 1], SBK_PRE(b - 1));                  // after body 1: the first of the outward sweep
             preloadWait();
-            SBK_DISPATCH_JOINT_M(JMASK, bc.joint, (leanInwardBody<JT>(c, T, bc, b, inst, cy, SBK_PRE(k))));
+            SBK_DISPATCH_JOINT_M(JMASK, bc.joint, (leanInwardBody<JT>(c, T, bc, b, inst, cy, SBK_PRE(b))));
         }
         cyStoreOut(cy, identity3(), zero3(), z0); cyStoreA(cy + CY_A*SBK_CARRY_STRIDE, z0);
 #pragma unroll 1
-        for (int b = 1; b < c.nb; ++b, ++k) {
+        for (int b = 1; b < c.nb; ++b) {
             const BodyConst& bc = T.bodies[b];
-            if (b + 1 < c.nb) preloadGNu(c, inst, T.bodies[b + 1], SBK_GNU(k + 1));
-            preloadCoords<JMASK>(c, inst, T.bodies[b + 1 < c.nb ? b + 1 : b], SBK_PRE(k + 1));
+            if (b + 1 < c.nb) preloadGNu(c, inst, T.bodies[b + 1], SBK_GNU(b));
+            preloadCoords<JMASK>(c, inst, T.bodies[b + 1 < c.nb ? b + 1 : b], SBK_PRE(b));
             preloadWait();
             // body 1 wrote its G / nu at the very end of the inward sweep: it loads them directly
-            SBK_DISPATCH_JOINT_M(JMASK, bc.joint, (leanOutwardBody<JT>(c, bc, inst, cy, SBK_PRE(k), b > 1 ? SBK_GNU(k) : nullptr, udotDst, qddDst)));
+            SBK_DISPATCH_JOINT_M(JMASK, bc.joint, (leanOutwardBody<JT>(c, bc, inst, cy, SBK_PRE(b - 1), b > 1 ? SBK_GNU(b - 1) : nullptr, udotDst, qddDst)));
         }
         #undef SBK_PRE
         #undef SBK_GNU
