@@ -141,7 +141,9 @@ SBK_HD Tables tablesOf(const Ctx& c) { Tables t; t.bodies = c.bodies; t.children
 #ifndef SBK_GNU_ROWS
 #define SBK_GNU_ROWS 14
 #endif
-enum { CY_A = 18, CY_SELF = 30, CY_PRE = 48, CY_GNU = 56, GNU_ROWS = SBK_GNU_ROWS, CARRY_ROWS = CY_GNU + 2*GNU_ROWS };
+enum { CY_A = 18, CY_SELF = 30, CY_PRE = 48, CY_GNU = 56, GNU_ROWS = SBK_GNU_ROWS, CY_LOOP = CY_GNU + 2*GNU_ROWS, CARRY_ROWS = CY_LOOP + 1 };
+// row CY_LOOP: the body-loop counter of the sweep drivers (parked in shared memory across a body step instead of
+// a register that the compiler would spill to local memory: its reload showed up as long-scoreboard stalls)
 // rows 48..55: two coordinate preload slots; rows 56..83: two G / nu preload slots (acceleration sweep, dof <= 2)
 #if defined(__CUDA_ARCH__)
 #define SBK_CARRY_STRIDE 128
@@ -1228,6 +1230,9 @@ template <bool LEAN, int JMASK = JM_ALL, bool CB = false> SBK_HD void tpiEvalDer
         // so no step counter has to live across the joint switch.
         #define SBK_PRE(par) (cy + (CY_PRE + 4*((par) & 1))*SBK_CARRY_STRIDE)
         #define SBK_GNU(par) (cy + (CY_GNU + GNU_ROWS*((par) & 1))*SBK_CARRY_STRIDE)
+        volatile int* bslot = reinterpret_cast<volatile int*>(cy + CY_LOOP*SBK_CARRY_STRIDE);
+        #define SBK_PARK(b)   (*bslot = (b))
+        #define SBK_UNPARK(b) ((b) = *bslot)
         cyStoreOut(cy, identity3(), zero3(), z0);                                 // Ground's link for body 1
         preloadCoords<JMASK>(c, inst, T.bodies[1], SBK_PRE(0));
 #pragma unroll 1
@@ -1235,14 +1240,18 @@ template <bool LEAN, int JMASK = JM_ALL, bool CB = false> SBK_HD void tpiEvalDer
             const BodyConst& bc = T.bodies[b];
             preloadCoords<JMASK>(c, inst, T.bodies[b + 1 < c.nb ? b + 1 : c.nb - 1], SBK_PRE(b));       // after the last body: the first of the inward sweep
             preloadWait();
+            SBK_PARK(b);
             SBK_DISPATCH_JOINT_M(JMASK, bc.joint, (leanKinBody<JT>(c, bc, inst, cy, SBK_PRE(b - 1), qdotDst)));
+            SBK_UNPARK(b);
         }
 #pragma unroll 1
         for (int b = c.nb - 1; b >= 1; --b) {
             const BodyConst& bc = T.bodies[b];
             preloadCoords<JMASK>(c, inst, T.bodies[b > 1 ? b - 1 : 1], SBK_PRE(b - 1));                  // after body 1: the first of the outward sweep
             preloadWait();
+            SBK_PARK(b);
             SBK_DISPATCH_JOINT_M(JMASK, bc.joint, (leanInwardBody<JT>(c, T, bc, b, inst, cy, SBK_PRE(b))));
+            SBK_UNPARK(b);
         }
         cyStoreOut(cy, identity3(), zero3(), z0); cyStoreA(cy + CY_A*SBK_CARRY_STRIDE, z0);
 #pragma unroll 1
@@ -1252,10 +1261,14 @@ template <bool LEAN, int JMASK = JM_ALL, bool CB = false> SBK_HD void tpiEvalDer
             preloadCoords<JMASK>(c, inst, T.bodies[b + 1 < c.nb ? b + 1 : b], SBK_PRE(b));
             preloadWait();
             // body 1 wrote its G / nu at the very end of the inward sweep: it loads them directly
+            SBK_PARK(b);
             SBK_DISPATCH_JOINT_M(JMASK, bc.joint, (leanOutwardBody<JT>(c, bc, inst, cy, SBK_PRE(b - 1), b > 1 ? SBK_GNU(b - 1) : nullptr, udotDst, qddDst)));
+            SBK_UNPARK(b);
         }
         #undef SBK_PRE
         #undef SBK_GNU
+        #undef SBK_PARK
+        #undef SBK_UNPARK
     }
 }
 
