@@ -35,12 +35,12 @@ WORKLOADS = {
     "branched_tree1000_256": dict(model="branched_tree", n=1000, batch=256, h=5e-4, q_scale=0.5),
 }
 # measured DRAM bytes per instance-step (ncu --set full, profiles/r1_prof_<workload>.txt): launch traffic / (N * steps)
-NCU_TRAFFIC_PER_INSTANCE_STEP = {"double_pendulum_1M": 4.272e7 / (1048576 * 20), "humanoid30_64k": 2.761e10 / (65536 * 4),
-                                 "pin_chain50_64k": 1.410e10 / (65536 * 4),
-                                 "branched_tree1000_256": 1.785e9 / 256}
+NCU_TRAFFIC_PER_INSTANCE_STEP = {"double_pendulum_1M": 4.276e7 / (1048576 * 20), "humanoid30_64k": 2.726e10 / (65536 * 4),
+                                 "pin_chain50_64k": 1.407e10 / (65536 * 4),
+                                 "branched_tree1000_256": 1.762e9 / 256}
 # sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active of the same captures (the hardware's own
 # view of FP64-pipe utilisation; roofline.frac below uses the reference's ALGORITHMIC flop count instead)
-NCU_FP64_PIPE_ACTIVE = {"double_pendulum_1M": 0.776, "humanoid30_64k": 0.240, "pin_chain50_64k": 0.332, "branched_tree1000_256": 0.038}
+NCU_FP64_PIPE_ACTIVE = {"double_pendulum_1M": 0.776, "humanoid30_64k": 0.246, "pin_chain50_64k": 0.335, "branched_tree1000_256": 0.037}
 F_EVAL = {"PIN": 1180.0, "SLIDER": 1130.0, "UNIVERSAL": 1710.0, "BALL": 2060.0, "FREE": 3800.0, "WELD": 700.0,
           "TRANSLATION": 1800.0, "CYLINDER": 1650.0, "PLANAR": 1950.0, "GIMBAL": 2300.0}
 
