@@ -907,8 +907,11 @@ SBK_HD void preloadCoords(const Ctx& c, const int inst, const BodyConst& nx, dou
     // rows of [q; u] (the u rows follow the q rows), clamped: a Weld owns no slots and the slot after the
     // last one does not exist
     const int last = c.nq + c.nu - 1;
+    // a quaternion mobilizer gets its four quaternion rows (the body step starts with |q|; its u is needed later and
+    // loaded directly); every other kind its first two q and two u rows
+    const bool quat = (JMASK & (JM_BALL | JM_FREE)) != 0 && (nx.joint == JT_BALL || nx.joint == JT_FREE);
     const int r0 = nx.q0 < last ? nx.q0 : last, r1 = nx.q0 + 1 < last ? nx.q0 + 1 : last;
-    const int r2 = c.nq + nx.u0 < last ? c.nq + nx.u0 : last, r3 = c.nq + nx.u0 + 1 < last ? c.nq + nx.u0 + 1 : last;
+    const int r2 = quat ? nx.q0 + 2 : (c.nq + nx.u0 < last ? c.nq + nx.u0 : last), r3 = quat ? nx.q0 + 3 : (c.nq + nx.u0 + 1 < last ? c.nq + nx.u0 + 1 : last);
     const double* src[4] = { c.q + stateIndex<BLK>(c, inst, r0), c.q + stateIndex<BLK>(c, inst, r1),
                              c.q + stateIndex<BLK>(c, inst, r2), c.q + stateIndex<BLK>(c, inst, r3) };
 #if defined(__CUDA_ARCH__)
@@ -950,6 +953,13 @@ template <int JT, bool BLK> SBK_HD void takeCoords(const Ctx& c, const int inst,
         for (int i = 0; i < NQ; ++i) q[i] = slot[i*SBK_CARRY_STRIDE];
 #pragma unroll
         for (int i = 0; i < d; ++i)  u[i] = slot[(2 + i)*SBK_CARRY_STRIDE];
+    } else if constexpr (JT == JT_BALL || JT == JT_FREE) {     // the quaternion was preloaded, the rest is needed later
+#pragma unroll
+        for (int i = 0; i < 4; ++i) q[i] = slot[i*SBK_CARRY_STRIDE];
+#pragma unroll
+        for (int i = 4; i < NQ; ++i) q[i] = ldS<BLK>(c, inst, c.q, bc.q0 + i);
+#pragma unroll
+        for (int i = 0; i < d; ++i)  u[i] = ldS<BLK>(c, inst, c.u, bc.u0 + i);
     } else {
 #pragma unroll
         for (int i = 0; i < NQ; ++i) q[i] = ldS<BLK>(c, inst, c.q, bc.q0 + i);
