@@ -33,7 +33,7 @@ struct sbk_batch {
     cudaStream_t stream = nullptr; bool ownStream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     KArgs a;                      // device pointers + constants
-    unsigned char* dTables = nullptr;
+    unsigned char* dTables = nullptr; unsigned char* dLTables = nullptr;
     double *dOpA = nullptr, *dOpB = nullptr, *dOpF = nullptr, *dOpOut = nullptr, *dScratch = nullptr;
     size_t scratchDoubles = 0;
     int stage = ST_EMPTY; bool abiValid = false, accelValid = false;
@@ -214,6 +214,28 @@ static int configurePlan(sbk_batch* b, int plan) {
     CUDA_TRY(cudaMemcpyAsync(b->dTables, blob.data(), blob.size(), cudaMemcpyHostToDevice, b->stream));
     CUDA_TRY(cudaStreamSynchronize(b->stream));
     a.tables = b->dTables;
+    // body-frame integrator tables (sbk_local.cuh): plans 1 / 4, models made of Pin / Slider / Universal / Ball / Free
+    if (b->dLTables) cudaFree(b->dLTables);
+    b->dLTables = nullptr; a.ltables = nullptr; a.ltableBytes = 0; a.lstageInSmem = 0;
+    { const char* e = getenv("SBK_NOLOCAL");
+      if (t->localOk && plan != 3 && !(e && atoi(e))) {
+        const size_t lb = pad16(t->lbodies.size()*sizeof(LBody));
+        const size_t fcoefBytes = pad16(t->lfcoef.size()*sizeof(double));
+        std::vector<unsigned char> lblob(lb + childBytes + forceBytes + fcoefBytes, 0);
+        std::memcpy(lblob.data() + lb + childBytes + forceBytes, t->lfcoef.data(), t->lfcoef.size()*sizeof(double));
+        a.lfcoefOff = (uint32_t)(lb + childBytes + forceBytes);
+        a.localMinB = 2;
+        { const char* e3 = getenv("SBK_LOCAL_MINB"); if (e3) a.localMinB = atoi(e3); }     // tuning override
+        std::memcpy(lblob.data(), t->lbodies.data(), t->lbodies.size()*sizeof(LBody));
+        std::memcpy(lblob.data() + lb, t->children.data(), t->children.size()*sizeof(int));
+        std::memcpy(lblob.data() + lb + childBytes, t->forces.data(), t->forces.size()*sizeof(ForceConst));
+        CUDA_TRY(cudaMalloc(&b->dLTables, lblob.size()));
+        CUDA_TRY(cudaMemcpyAsync(b->dLTables, lblob.data(), lblob.size(), cudaMemcpyHostToDevice, b->stream));
+        CUDA_TRY(cudaStreamSynchronize(b->stream));
+        a.ltables = b->dLTables; a.ltableBytes = (uint32_t)lblob.size(); a.lchildrenOff = (uint32_t)lb; a.lforcesOff = (uint32_t)(lb + childBytes);
+        a.lstageInSmem = (lblob.size() <= 48*1024 && a.stageInSmem != 0) || (lblob.size() <= 48*1024 && blob.size() > 28*1024) ? 1u : 0u;
+        { const char* e2 = getenv("SBK_NOSTAGE"); if (e2 && atoi(e2)) a.lstageInSmem = 0; }
+      } }
     CUDA_TRY(cudaMalloc(&a.cache, (size_t)cacheDoubles*sizeof(double)));
     CUDA_TRY(cudaMemsetAsync(a.cache, 0, (size_t)cacheDoubles*sizeof(double), b->stream));
     CUDA_TRY(launchInitGround(a, b->stream)); b->launches++;
@@ -257,9 +279,11 @@ sbk_batch* sbk_batch_create(const sbk_topology* t, int n, int device, void* stre
       if (ok && cudaMalloc(&a.taskCounter, (2 + nblk)*sizeof(int)) != cudaSuccess) ok = false;   // 64-bit task counter, then blockDone[nblk]
       if (ok) a.blockDone = a.taskCounter + 2; }
     if (ok && cudaMalloc(&a.projCount, N*sizeof(int)) != cudaSuccess) ok = false;
+    if (ok && cudaMalloc(&a.lflags, N*sizeof(int)) != cudaSuccess) ok = false;
     if (!ok) return bail(std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
     cudaMemsetAsync(a.status, 0, N*sizeof(int), b->stream);
     cudaMemsetAsync(a.projCount, 0, N*sizeof(int), b->stream);
+    cudaMemsetAsync(a.lflags, 0, N*sizeof(int), b->stream);
     // default state: q = 0 except quaternions (1,0,0,0), like the reference's default State
     if (t->nquat) {
         std::vector<double> q0((size_t)t->nq*N, 0.0);
@@ -276,9 +300,9 @@ void sbk_batch_destroy(sbk_batch* b) {
     if (!b) return;
     cudaSetDevice(b->device);
     KArgs& a = b->a;
-    void* ptrs[] = {b->dTables, a.cache, a.y, a.yb, a.ydot, a.qdotdot, a.qerr, a.y0, a.f0, a.fa, a.fb, a.ys, a.tcur, a.errNorm,
+    void* ptrs[] = {b->dTables, b->dLTables, a.cache, a.y, a.yb, a.ydot, a.qdotdot, a.qerr, a.y0, a.f0, a.fa, a.fb, a.ys, a.tcur, a.errNorm,
                     b->dOpA, b->dOpB, b->dOpOut, b->dOpF, a.status, a.projCount, b->dScratch,
-                    a.hcur, a.lastStep, a.stepsTaken, a.attempts, a.taskCounter};
+                    a.hcur, a.lastStep, a.stepsTaken, a.attempts, a.taskCounter, a.lflags};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (b->ev0) cudaEventDestroy(b->ev0); if (b->ev1) cudaEventDestroy(b->ev1);
     if (b->ownStream && b->stream) cudaStreamDestroy(b->stream);

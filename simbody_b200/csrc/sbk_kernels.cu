@@ -650,6 +650,14 @@ cudaError_t launchTpi(KernelOp op, const KArgs& a, cudaStream_t stream) {
         case OP_RKM: case OP_RKM_ADAPT: {
             // integrator kernels: instantiated per set of mobilizer kinds present in the model (one translation unit each)
             const int m = a.jointMask;
+            if (a.ltables) {            // body-frame sweeps
+                const bool pin = (m & ~JM_PIN) == 0;
+                switch (a.localMinB) {
+                    case 4:  return pin ? launchTpiRkmLocalPin_m4(op, a, stream) : launchTpiRkmLocal_m4(op, a, stream);
+                    case 3:  return pin ? launchTpiRkmLocalPin_m3(op, a, stream) : launchTpiRkmLocal_m3(op, a, stream);
+                    default: return pin ? launchTpiRkmLocalPin_m2(op, a, stream) : launchTpiRkmLocal_m2(op, a, stream);
+                }
+            }
             if ((m & ~JM_PIN) == 0)     return launchTpiRkmPin(op, a, stream);
             if ((m & ~JM_LIGHT) == 0)   return launchTpiRkmLight(op, a, stream);
             if ((m & ~JM_MOBILE5) == 0) return launchTpiRkmMobile5(op, a, stream);

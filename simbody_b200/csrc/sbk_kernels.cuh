@@ -13,7 +13,9 @@ struct KArgs {
     const unsigned char* tables;     // device blob
     uint32_t tableBytes, childrenOff, forcesOff, stageInSmem;
     uint32_t levelOrderOff, levelStartOff; int nlevels, plan;
-    int pad0_, jointMask;                      // bit JT_x set = mobilizer kind x present in the model
+    // body-frame integrator path (sbk_local.cuh): [ LBody[nb] | children | forces ], null when the model has other mobilizers
+    const unsigned char* ltables; uint32_t ltableBytes, lchildrenOff, lforcesOff, lstageInSmem, lfcoefOff, lpad_;
+    int localMinB, jointMask;                  // localMinB: register budget variant of the body-frame integrator kernels (2, 3, 4 CTAs / SM)                      // bit JT_x set = mobilizer kind x present in the model
     long long cStride, cInstStride, cSpan;  // cache addressing: base_b + field*cStride + (inst>>cShift)*cSpan + (inst&cMask)*cInstStride
     int cShift, cMask;
     int nb, nq, nu, nquat;
@@ -44,6 +46,7 @@ struct KArgs {
     int* attempts;      // [N] accumulated
     int* taskCounter;   // fixed-step integrator task queue: a 64-bit next-task counter (also plan 4's barrier counter); blockDone = taskCounter + 2
     int* blockDone;     // steps completed per block of 128 instances (this launch)
+    int* lflags;        // [N] fused body-frame integrator: 1 = the velocity data left by the previous step are current
 };
 
 enum KernelOp {
@@ -63,6 +66,10 @@ cudaError_t launchTpiRkmPin(KernelOp op, const KArgs& a, cudaStream_t stream);  
 cudaError_t launchTpiRkmLight(KernelOp op, const KArgs& a, cudaStream_t stream);    // Pin / Slider / Universal / Weld
 cudaError_t launchTpiRkmMobile5(KernelOp op, const KArgs& a, cudaStream_t stream);  // Pin / Slider / Universal / Ball / Free
 cudaError_t launchTpiRkmAll(KernelOp op, const KArgs& a, cudaStream_t stream);      // every supported mobilizer
+// body-frame sweeps (Pin / Slider / Universal / Ball / Free, and Pin only), built for 2 / 3 / 4 resident CTAs per SM
+cudaError_t launchTpiRkmLocal_m2(KernelOp op, const KArgs& a, cudaStream_t stream); cudaError_t launchTpiRkmLocalPin_m2(KernelOp op, const KArgs& a, cudaStream_t stream);
+cudaError_t launchTpiRkmLocal_m3(KernelOp op, const KArgs& a, cudaStream_t stream); cudaError_t launchTpiRkmLocalPin_m3(KernelOp op, const KArgs& a, cudaStream_t stream);
+cudaError_t launchTpiRkmLocal_m4(KernelOp op, const KArgs& a, cudaStream_t stream); cudaError_t launchTpiRkmLocalPin_m4(KernelOp op, const KArgs& a, cudaStream_t stream);
 // Register-resident fused plan (serial chains of 1-2 Pin/Slider[/Universal] mobilizers).
 bool fusedPlanSupports(int nb, const int* joints /*[nb]*/);
 cudaError_t launchFusedRkm(const KArgs& a, const int* joints, bool adaptive, cudaStream_t stream);

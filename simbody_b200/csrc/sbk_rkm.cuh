@@ -11,6 +11,7 @@
 // measured for the reference.
 #pragma once
 #include "sbk_sweeps.cuh"
+#include "sbk_local.cuh"
 
 namespace sbkd {
 
@@ -25,8 +26,8 @@ struct RkmStepResult { double errNorm; int projected; };
 
 // Error norm of IntegratorRep::calcErrorNorm with UWeights = 1, no z.
 // err lives in w.ys (overwritten by the caller with the error estimate), q1 = current state.
-template <bool BLK>
-SBK_HD double rkmErrorNorm(const Ctx& c, const Tables& T, const int inst, const RkmWork& w) {
+template <bool BLK, class TBL>
+SBK_HD double rkmErrorNorm(const Ctx& c, const TBL& T, const int inst, const RkmWork& w) {
     const int nq = c.nq, nu = c.nu;
     double qAcc = 0, uAcc = 0;
     // u part: uScale_i = |u0_i| > 1 ? 1/|u0_i| : 1   (calcRelativeScaling, frozen at step start)
@@ -39,7 +40,7 @@ SBK_HD double rkmErrorNorm(const Ctx& c, const Tables& T, const int inst, const 
     }
     // q part: dqw = N * Wu * pinv(N) * dq (scaleDQ); identity except on quaternion slots
     for (int b = 1; b < c.nb; ++b) {
-        const BodyConst& bc = T.bodies[b];
+        const auto& bc = T.bodies[b];
         int first = 0;
         if (bc.joint == JT_BALL || bc.joint == JT_FREE) {
             double q[4], e[4], o[4];
@@ -101,8 +102,17 @@ SBK_HD void rkmCombine(const Ctx& c, const int inst, const int ny, const double*
 // (AbstractIntegratorRep.cpp:390-396).  FRESH = false: retry of a failed attempt with a smaller h
 // from the saved y0 / f0 (no re-evaluation, as in takeOneStep's do/while).
 // The caller's Ctx must have q = w.y, u = w.y + nq*sStride and null qerr / fmobOut / FbodyOut.
-template <bool LEAN, int JMASK = JM_ALL>
-SBK_HD RkmStepResult tpiRkmStep(const Ctx& c, const Tables& T, const int inst, const RkmWork& w, const double h, double* cy, const bool fresh = true) {
+// The derivative evaluation behind a table type: Tables = ground-frame sweeps (FULL records or LEAN reversible
+// kinematics), LTables = body-frame sweeps (sbk_local.cuh).
+template <bool LEAN, int JMASK> SBK_HD void rkmEval(const Ctx& c, const Tables& T, const int inst, double* cy, double* qd, double* ud) {
+    tpiEvalDerivatives<LEAN, JMASK>(c, T, inst, cy, qd, ud, nullptr);
+}
+template <bool LEAN, int JMASK> SBK_HD void rkmEval(const Ctx& c, const LTables& T, const int inst, double* cy, double* qd, double* ud) {
+    lEvalDerivatives<JMASK>(c, T, inst, cy, qd, ud);
+}
+
+template <bool LEAN, int JMASK = JM_ALL, class TBL = Tables>
+SBK_HD RkmStepResult tpiRkmStep(const Ctx& c, const TBL& T, const int inst, const RkmWork& w, const double h, double* cy, const bool fresh = true) {
     constexpr bool BLK = LEAN && SBK_DEV_BLK;
     const int nq = c.nq, ny = c.nq + c.nu;
     const long long uoff = BLK ? (long long)nq*BLK_LANES : (long long)nq*c.sStride;   // u rows follow the q rows
@@ -117,7 +127,7 @@ SBK_HD RkmStepResult tpiRkmStep(const Ctx& c, const Tables& T, const int inst, c
         double* fdst = stage == 0 ? w.f0 : (stage == 3 ? w.fb : w.fa);
         // stage 0: f0 = f(y0), AbstractIntegratorRep.cpp:393 realizeStateDerivatives at the start of a step;
         // a retry after a failed attempt keeps the saved y0 / f0
-        if (stage > 0 || fresh) tpiEvalDerivatives<LEAN, JMASK>(c, T, inst, cy, fdst, fdst + uoff, nullptr);
+        if (stage > 0 || fresh) rkmEval<LEAN, JMASK>(c, T, inst, cy, fdst, fdst + uoff);
         if (stage == 0) {
             if (fresh) rkmCombine<BLK, 2>(c, inst, ny, w.y, w.f0, nullptr, nullptr, nullptr, [&](int i, const double* v) {
                            stS<BLK>(c, inst, w.y0, i, v[0]);
@@ -148,7 +158,7 @@ SBK_HD RkmStepResult tpiRkmStep(const Ctx& c, const Tables& T, const int inst, c
     if (c.nquat > 0 && !(res.errNorm > 16.0*w.accuracy)) {
         double acc = 0;
         for (int b = 1; b < c.nb; ++b) {
-            const BodyConst& bc = T.bodies[b];
+            const auto& bc = T.bodies[b];
             if (bc.joint != JT_BALL && bc.joint != JT_FREE) continue;
             double n2 = 0;
 #pragma unroll
@@ -159,7 +169,7 @@ SBK_HD RkmStepResult tpiRkmStep(const Ctx& c, const Tables& T, const int inst, c
         const double quatNorm = w.useInfNorm ? acc : sqrt(acc/c.nquat);
         if (quatNorm > w.consTol || w.projectEveryStep) {
             for (int b = 1; b < c.nb; ++b) {
-                const BodyConst& bc = T.bodies[b];
+                const auto& bc = T.bodies[b];
                 if (bc.joint != JT_BALL && bc.joint != JT_FREE) continue;
                 double q[4], e[4], n2 = 0;
 #pragma unroll
@@ -183,8 +193,8 @@ SBK_HD RkmStepResult tpiRkmStep(const Ctx& c, const Tables& T, const int inst, c
 // reference's default) steps are never shortened to hit tFinal, so the advanced state ends at
 // t >= tFinal; without it the last step lands on tFinal (hWasArtificiallyLimited logic).
 struct AdaptiveState { double t, h, lastStep; int steps, attempts; };
-template <bool LEAN, int JMASK = JM_ALL>
-SBK_HD void tpiRkmAdaptive(const Ctx& c, const Tables& T, const int inst, const RkmWork& w, const StepLimits& lim, const double tFinal,
+template <bool LEAN, int JMASK = JM_ALL, class TBL = Tables>
+SBK_HD void tpiRkmAdaptive(const Ctx& c, const TBL& T, const int inst, const RkmWork& w, const StepLimits& lim, const double tFinal,
                            const int allowInterpolation, const int maxAttempts, AdaptiveState& st, double* cy,
                            double& lastErr, int& nproj) {
     constexpr bool BLK = LEAN && SBK_DEV_BLK;

@@ -66,7 +66,8 @@ enum { JM_PIN = 1 << JT_PIN, JM_SLIDER = 1 << JT_SLIDER, JM_UNIVERSAL = 1 << JT_
        JM_BALL_EULER = 1 << JT_BALL_EULER, JM_FREE_EULER = 1 << JT_FREE_EULER,
        JM_LIGHT = JM_PIN | JM_SLIDER | JM_UNIVERSAL | JM_WELD,                   // dof <= 2
        JM_MOBILE5 = JM_PIN | JM_SLIDER | JM_UNIVERSAL | JM_BALL | JM_FREE,       // the north_star mobilizer set
-       JM_ALL = JM_MOBILE5 | JM_WELD | JM_TRANSLATION | JM_CYLINDER | JM_PLANAR | JM_GIMBAL | JM_BALL_EULER | JM_FREE_EULER };
+       JM_ALL = JM_MOBILE5 | JM_WELD | JM_TRANSLATION | JM_CYLINDER | JM_PLANAR | JM_GIMBAL | JM_BALL_EULER | JM_FREE_EULER,
+       JM_LOCAL = 1 << 30 };   // integrator kernels only: body-frame sweeps (sbk_local.cuh) instead of the ground-frame ones
 
 // cache record layout
 enum { F_XGB = 0, F_VGB = 12, F_L = 18, F_MK = 21, F_ACOR = 30, F_GYRO = 36, F_ZB = 42,

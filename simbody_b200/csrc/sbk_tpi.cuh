@@ -3,7 +3,9 @@
 // (one integrator kernel family per set of mobilizer kinds, compiled in parallel).
 #pragma once
 #include <algorithm>
+#include <type_traits>
 #include "sbk_kernels.cuh"
+#include "sbk_lrkm.cuh"
 
 namespace sbkd {
 namespace {
@@ -69,10 +71,26 @@ __device__ __forceinline__ void stateToBlocked(const Ctx& c, const KArgs& a, int
 #pragma unroll 8
     for (int i = 0; i < ny; ++i) a.yb[stateIndex<true>(c, inst, i)] = __ldcg(a.y + (long long)i*a.N + inst);
 }
-__device__ __forceinline__ void stateFromBlocked(const Ctx& c, const KArgs& a, int inst) {
+__device__ __forceinline__ void stateFromBlocked(const Ctx& c, const KArgs& a, int inst, const double* yb = nullptr) {
     const int ny = a.nq + a.nu;
+    if (!yb) yb = a.yb;
 #pragma unroll 8
-    for (int i = 0; i < ny; ++i) __stcg(a.y + (long long)i*a.N + inst, a.yb[stateIndex<true>(c, inst, i)]);
+    for (int i = 0; i < ny; ++i) __stcg(a.y + (long long)i*a.N + inst, yb[stateIndex<true>(c, inst, i)]);
+}
+__device__ __forceinline__ LRkmWork fusedWork(const KArgs& a) {
+    LRkmWork w; w.Y = a.yb; w.W = a.ys; w.F0 = a.f0; w.F2 = a.fa; w.F3 = a.fb; w.Ynext = a.yb;
+    w.accuracy = a.accuracy; w.consTol = a.consTol; w.useInfNorm = a.useInfNorm; w.projectEveryStep = a.projectEveryStep;
+    return w;
+}
+
+template <class TBL> __device__ __forceinline__ TBL makeTables(const unsigned char* base, const KArgs& a);
+template <> __device__ __forceinline__ Tables makeTables<Tables>(const unsigned char* base, const KArgs& a) {
+    Tables T; T.bodies = reinterpret_cast<const BodyConst*>(base); T.children = reinterpret_cast<const int*>(base + a.childrenOff);
+    T.forces = reinterpret_cast<const ForceConst*>(base + a.forcesOff); return T;
+}
+template <> __device__ __forceinline__ LTables makeTables<LTables>(const unsigned char* base, const KArgs& a) {
+    LTables T; T.bodies = reinterpret_cast<const LBody*>(base); T.children = reinterpret_cast<const int*>(base + a.lchildrenOff);
+    T.forces = reinterpret_cast<const ForceConst*>(base + a.lforcesOff); T.fcoef = reinterpret_cast<const double*>(base + a.lfcoefOff); return T;
 }
 
 // MINB = resident CTAs per SM the register allocation is sized for: 4 (128 registers) suits
@@ -83,9 +101,12 @@ __global__ void __launch_bounds__(TPI_THREADS, MINB) tpiKernel(const KArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ Ctx sctx;                      // ONE context per CTA, read with LDS by every body step
-    const unsigned char* tables = a.tables;
-    if constexpr (STAGE) { tmaStage(smem, a.tables, a.tableBytes, &mbar); tables = smem; }
     constexpr bool INTEG = OP == OP_RKM || OP == OP_RKM_ADAPT;
+    constexpr bool LOCAL = INTEG && (JMASK & JM_LOCAL) != 0;        // body-frame sweeps with their own (smaller) tables
+    typedef std::conditional_t<LOCAL, LTables, Tables> TBL;
+    const unsigned char* tables = LOCAL ? a.ltables : a.tables;
+    const uint32_t tableBytes = LOCAL ? a.ltableBytes : a.tableBytes;
+    if constexpr (STAGE) { tmaStage(smem, tables, tableBytes, &mbar); tables = smem; }
     if (!INTEG && threadIdx.x == 0) fillCtx(sctx, a, tables, false);
     __syncthreads();
     if constexpr (OP == OP_RKM) {
@@ -98,10 +119,8 @@ __global__ void __launch_bounds__(TPI_THREADS, MINB) tpiKernel(const KArgs a) {
         __shared__ long long sTask;          // 64-bit: blocks x steps can exceed 2^31
         Ctx lctx; fillCtx(lctx, a, tables, true); useBlockedState(lctx, a);
         const Ctx& c = lctx;
-        Tables T;
-        T.bodies = reinterpret_cast<const BodyConst*>(tables); T.children = reinterpret_cast<const int*>(tables + a.childrenOff);
-        T.forces = reinterpret_cast<const ForceConst*>(tables + a.forcesOff);
-        double* cy = reinterpret_cast<double*>(smem + (STAGE ? a.tableBytes : 0)) + threadIdx.x;
+        const TBL T = makeTables<TBL>(tables, a);
+        double* cy = reinterpret_cast<double*>(smem + (STAGE ? tableBytes : 0)) + threadIdx.x;
         RkmWork w;
         w.y = a.yb; w.y0 = a.y0; w.f0 = a.f0; w.fa = a.fa; w.fb = a.fb; w.ys = a.ys;
         w.accuracy = a.accuracy; w.consTol = a.consTol; w.useInfNorm = a.useInfNorm; w.projectEveryStep = a.projectEveryStep;
@@ -123,7 +142,15 @@ __global__ void __launch_bounds__(TPI_THREADS, MINB) tpiKernel(const KArgs a) {
             const int inst = blk*TPI_THREADS + threadIdx.x;
             if (inst < a.N) {
                 if (step == 0) stateToBlocked(c, a, inst);
-                const RkmStepResult r = tpiRkmStep<true, JMASK>(c, T, inst, w, a.h, cy);
+                RkmStepResult r;
+                if constexpr (LOCAL) {
+                    // fused two-sweep step (sbk_lrkm.cuh).  The velocity buffer alternates with every outward sweep (5 per step);
+                    // the data left by the previous step are current unless this is the first step of a launch or that step
+                    // projected quaternions (lflags, written by whichever CTA ran it).
+                    LRkmState st; st.vb = (step & 1) ? LR_VBUF : 0; st.velValid = step > 0 && a.lflags[inst] != 0;
+                    r = lRkmAttempt<JMASK>(c, T, inst, fusedWork(a), a.h, cy, st);
+                    a.lflags[inst] = st.velValid ? 1 : 0;
+                } else r = tpiRkmStep<true, JMASK>(c, T, inst, w, a.h, cy);
                 a.tcur[inst] += a.h;
                 if (r.projected) a.projCount[inst] += 1;
                 if (step == a.nsteps - 1) {
@@ -146,12 +173,10 @@ __global__ void __launch_bounds__(TPI_THREADS, MINB) tpiKernel(const KArgs a) {
     Ctx lctx;
     if constexpr (INTEG) { fillCtx(lctx, a, tables, true); useBlockedState(lctx, a); }
     const Ctx& c = INTEG ? lctx : sctx;
-    Tables T;                                  // address space known at compile time: shared if staged, else global
-    T.bodies = reinterpret_cast<const BodyConst*>(tables); T.children = reinterpret_cast<const int*>(tables + a.childrenOff);
-    T.forces = reinterpret_cast<const ForceConst*>(tables + a.forcesOff);
+    const TBL T = makeTables<TBL>(tables, a);  // address space known at compile time: shared if staged, else global
     // LEAN carry: a [CARRY_ROWS][128] block of shared memory behind the staged tables
     double* cy = nullptr;
-    if constexpr (OP == OP_RKM || OP == OP_RKM_ADAPT) cy = reinterpret_cast<double*>(smem + (STAGE ? a.tableBytes : 0)) + threadIdx.x;
+    if constexpr (OP == OP_RKM || OP == OP_RKM_ADAPT) cy = reinterpret_cast<double*>(smem + (STAGE ? tableBytes : 0)) + threadIdx.x;
 
     if constexpr (OP == OP_KIN) {
         tpiKinematics<true>(c, inst, c.qdot);
@@ -179,8 +204,15 @@ __global__ void __launch_bounds__(TPI_THREADS, MINB) tpiKernel(const KArgs a) {
         StepLimits lim; lim.accuracy = a.accuracy; lim.minStep = a.minStep; lim.maxStep = a.maxStep;
         AdaptiveState st; st.t = a.tcur[inst]; st.h = a.hcur[inst]; st.lastStep = a.lastStep[inst]; st.steps = 0; st.attempts = 0;
         double lastErr = a.errNorm[inst]; int nproj = 0;
-        tpiRkmAdaptive<true, JMASK>(c, T, inst, w, lim, a.tFinal, a.allowInterp, a.maxAttempts, st, cy, lastErr, nproj);
-        stateFromBlocked(c, a, inst);
+        if constexpr (LOCAL) {
+            LRkmWork lw = fusedWork(a); lw.Ynext = a.y0;             // y1 goes to the second state buffer; the two swap on acceptance
+            LRkmState ls; ls.vb = 0; ls.velValid = false;
+            lRkmAdaptive<JMASK>(c, T, inst, lw, lim, a.tFinal, a.allowInterp, a.maxAttempts, st, cy, ls, lastErr, nproj);
+            stateFromBlocked(c, a, inst, lw.Y);
+        } else {
+            tpiRkmAdaptive<true, JMASK>(c, T, inst, w, lim, a.tFinal, a.allowInterp, a.maxAttempts, st, cy, lastErr, nproj);
+            stateFromBlocked(c, a, inst);
+        }
         a.tcur[inst] = st.t; a.hcur[inst] = st.h; a.lastStep[inst] = st.lastStep;
         a.stepsTaken[inst] += st.steps; a.attempts[inst] += st.attempts;
         a.errNorm[inst] = lastErr; a.projCount[inst] += nproj;
@@ -193,8 +225,10 @@ template <int OP, int MINB, int JMASK>
 cudaError_t launchOp(const KArgs& a, cudaStream_t stream) {
     static_assert(TPI_THREADS == SBK_CARRY_STRIDE_DEVICE, "carry columns are laid out for 128-thread CTAs");
     const int grid = (a.N + TPI_THREADS - 1)/TPI_THREADS;
-    const size_t carryBytes = (OP == OP_RKM || OP == OP_RKM_ADAPT) ? (size_t)CARRY_ROWS*TPI_THREADS*sizeof(double) : 0;
-    const size_t smemBytes = (a.stageInSmem ? a.tableBytes : 0) + carryBytes;
+    constexpr bool LOCAL = (OP == OP_RKM || OP == OP_RKM_ADAPT) && (JMASK & JM_LOCAL) != 0;
+    const size_t carryBytes = (OP == OP_RKM || OP == OP_RKM_ADAPT) ? (size_t)(LOCAL ? (int)LFCARRY_ROWS : (int)CARRY_ROWS)*TPI_THREADS*sizeof(double) : 0;
+    const bool stage = LOCAL ? a.lstageInSmem != 0 : a.stageInSmem != 0;
+    const size_t smemBytes = (stage ? (LOCAL ? a.ltableBytes : a.tableBytes) : 0) + carryBytes;
     auto go = [&](auto kernel) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
         if (e != cudaSuccess) return e;
@@ -212,7 +246,7 @@ cudaError_t launchOp(const KArgs& a, cudaStream_t stream) {
         kernel<<<g, TPI_THREADS, smemBytes, stream>>>(a);
         return cudaGetLastError();
     };
-    return a.stageInSmem ? go(tpiKernel<OP, true, MINB, JMASK>) : go(tpiKernel<OP, false, MINB, JMASK>);
+    return stage ? go(tpiKernel<OP, true, MINB, JMASK>) : go(tpiKernel<OP, false, MINB, JMASK>);
 }
 // Body of one integrator translation unit (sbk_rkm_<variant>.cu)
 #define SBK_DEFINE_RKM_VARIANT(NAME, MINB, JMASK)                                                   \

@@ -5,6 +5,72 @@
 
 namespace sbk {
 
+// Constants of the body-frame integrator path (sbk_local.cuh): every body's quantities are expressed in its own
+// outboard frame M.  X_T = X_MB(parent) * X_PF takes the child's inboard frame F to the parent's M; the mass
+// properties move from (Bo, B) to (Mo, M) once, here.
+static void compileLocalTables(sbk_topology& t) {
+    const int nb = t.nb;
+    t.localOk = nb > 1; t.lbodies.clear(); t.lrows = 0;
+    for (int b = 1; b < nb; ++b) {
+        const int jt = t.bodies[b].joint;
+        if (jt != sbkd::JT_PIN && jt != sbkd::JT_SLIDER && jt != sbkd::JT_UNIVERSAL && jt != sbkd::JT_BALL && jt != sbkd::JT_FREE) t.localOk = false;
+    }
+    if (!t.localOk) return;
+    t.lbodies.assign(nb, sbkd::LBody());
+    int row = 0;
+    for (int b = 0; b < nb; ++b) {
+        const sbkd::BodyConst& bc = t.bodies[b];
+        sbkd::LBody& lb = t.lbodies[b];
+        std::memset(&lb, 0, sizeof lb);
+        const double* Rmb = bc.X_MB; const double* pmb = bc.X_MB + 9;              // this body's X_MB (B -> M)
+        // parent's X_MB (identity for Ground and for b == 0)
+        double Rp[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, pp[3] = {0, 0, 0};
+        if (b > 0 && bc.parent > 0) { std::memcpy(Rp, t.bodies[bc.parent].X_MB, sizeof Rp); std::memcpy(pp, t.bodies[bc.parent].X_MB + 9, sizeof pp); }
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) lb.RT[3*i+j] = Rp[3*i]*bc.X_PF[j] + Rp[3*i+1]*bc.X_PF[3+j] + Rp[3*i+2]*bc.X_PF[6+j];
+            lb.pT[i] = pp[i] + (Rp[3*i]*bc.X_PF[9] + Rp[3*i+1]*bc.X_PF[10] + Rp[3*i+2]*bc.X_PF[11]);
+        }
+        // mass properties about Mo in M
+        const double m = bc.mass; lb.m = m;
+        double cM[3], dB[3];                                                    // com from Mo, in M and in B
+        for (int i = 0; i < 3; ++i) cM[i] = Rmb[3*i]*bc.com_B[0] + Rmb[3*i+1]*bc.com_B[1] + Rmb[3*i+2]*bc.com_B[2] + pmb[i];
+        for (int i = 0; i < 3; ++i) { dB[i] = bc.com_B[i] - bc.p_BM[i]; lb.h[i] = m*cM[i]; }
+        const double* cB = bc.com_B;
+        double IB[3][3] = {{bc.G_B[0], bc.G_B[3], bc.G_B[4]}, {bc.G_B[3], bc.G_B[1], bc.G_B[5]}, {bc.G_B[4], bc.G_B[5], bc.G_B[2]}};   // unit inertia about Bo
+        const double c2 = cB[0]*cB[0] + cB[1]*cB[1] + cB[2]*cB[2], d2 = dB[0]*dB[0] + dB[1]*dB[1] + dB[2]*dB[2];
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j)                 // to the mass centre, then out to Mo (per unit mass, B axes)
+            IB[i][j] += -((i == j ? c2 : 0) - cB[i]*cB[j]) + ((i == j ? d2 : 0) - dB[i]*dB[j]);
+        double IM[3][3];
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+            double s = 0;
+            for (int k = 0; k < 3; ++k) for (int l = 0; l < 3; ++l) s += Rmb[3*i+k]*IB[k][l]*Rmb[3*j+l];
+            IM[i][j] = m*s;
+        }
+        lb.I[0] = IM[0][0]; lb.I[1] = IM[1][1]; lb.I[2] = IM[2][2];
+        lb.I[3] = 0.5*(IM[0][1] + IM[1][0]); lb.I[4] = 0.5*(IM[0][2] + IM[2][0]); lb.I[5] = 0.5*(IM[1][2] + IM[2][1]);
+        lb.joint = bc.joint; lb.parent = bc.parent; lb.q0 = bc.q0; lb.u0 = bc.u0;
+        lb.flags = bc.flags & (sbkd::BF_PARENT_PREV | sbkd::BF_STORE_LINK | sbkd::BF_TIP);
+        bool idRT = true;
+        for (int i = 0; i < 9; ++i) if (lb.RT[i] != ((i % 4 == 0) ? 1.0 : 0.0)) idRT = false;
+        if (idRT) lb.flags |= sbkd::BF_NO_RT;
+        lb.nchild = bc.nchild; lb.childStart = bc.childStart; lb.nforce = bc.nforce; lb.forceStart = bc.forceStart;
+        lb.rec = row; row += sbkd::lrSize(t.nuOf[b]);
+    }
+    for (int b = 1; b < nb; ++b) { const int p = t.lbodies[b].parent; t.lbodies[b].parentLink = t.lbodies[p].rec + sbkd::lrV(t.nuOf[p]); }
+    t.lrows = row;
+    t.lfcoef.assign((size_t)3*std::max(1, t.nu), 0.0);
+    for (int b = 1; b < nb; ++b) {
+        const sbkd::BodyConst& bc = t.bodies[b];
+        for (int k = 0; k < bc.nforce; ++k) {
+            const sbkd::ForceConst& fc = t.forces[bc.forceStart + k];
+            double* c = &t.lfcoef[(size_t)3*(bc.u0 + fc.coord)];
+            if (fc.kind == sbkd::FK_SPRING) { c[0] += fc.a*fc.b; c[1] -= fc.a; }
+            else if (fc.kind == sbkd::FK_CONSTANT) c[0] += fc.a;
+            else c[2] -= fc.a;
+        }
+    }
+}
+
 void compileTopology(const ModelSpec& spec, sbk_topology& t) {
     const int nb = (int)spec.bodies.size();
     if (nb < 1) throw std::runtime_error("topology: no bodies (entry 0 must be Ground)");
@@ -106,6 +172,7 @@ void compileTopology(const ModelSpec& spec, sbk_topology& t) {
         bc.nforce = (int)perBody[b].size(); bc.forceStart = (int)t.forces.size();
         for (const auto& fc : perBody[b]) t.forces.push_back(fc);
     }
+    compileLocalTables(t);
     if (t.children.empty()) t.children.push_back(0);
     if (t.forces.empty()) { sbkd::ForceConst z; std::memset(&z, 0, sizeof z); t.forces.push_back(z); }
 }

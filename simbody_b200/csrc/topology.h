@@ -14,6 +14,7 @@
 #include <vector>
 #include "sbk.h"
 #include "sbk_sweeps.cuh"
+#include "sbk_local.cuh"
 #include "../host/model_spec.h"
 
 struct sbk_topology {
@@ -23,6 +24,10 @@ struct sbk_topology {
     std::vector<sbkd::BodyConst>  bodies;     // cacheBase fields filled per batch/plan
     std::vector<int>              children;   // concatenated child lists
     std::vector<sbkd::ForceConst> forces;     // concatenated per-body mobility force lists
+    std::vector<sbkd::LBody>      lbodies;    // body-frame integrator path (sbk_local.cuh); empty unless localOk
+    std::vector<double>           lfcoef;     // [nu][3]: tau_j = A + B*q_j + C*u_j of the lowered mobility forces (sbk_local.cuh)
+    int                           lrows = 0;  // scratch rows per instance of the body-frame path
+    bool                          localOk = false;   // every mobilizer is Pin / Slider / Universal / Ball / Free (quaternion mode)
     std::vector<int>              levelOrder; // body indices sorted by level (stable)
     std::vector<int>              levelStart; // nlevels+1 offsets into levelOrder
     double grav[3] = {0, 0, 0};

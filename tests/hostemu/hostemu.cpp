@@ -11,6 +11,7 @@
 #include <vector>
 #include "../../simbody_b200/csrc/topology.h"
 #include "../../simbody_b200/csrc/sbk_fused.cuh"
+#include "../../simbody_b200/csrc/sbk_lrkm.cuh"
 
 using namespace sbkd;
 
@@ -164,18 +165,56 @@ int emu_step(const char* text, int N, const double* in, double* out, double h, i
             }
             return 0;
         }
+        if (lean >= 3 && !t.localOk) return 5;
+        if (lean == 4) {        // fused two-sweep integrator on the body-frame cores (sbk_lrkm.cuh); Ynext == Y (fixed step)
+            LTables LT; LT.bodies = t.lbodies.data(); LT.children = t.children.data(); LT.forces = t.forces.data(); LT.fcoef = t.lfcoef.data();
+            for (int k = 0; k < N; ++k) {
+                Ctx c = makeCtx(e, k); c.qdotdot = nullptr; c.qerr = nullptr;
+                double cy[CARRY_ROWS];
+                LRkmWork lw; lw.Y = e.y.data(); lw.W = e.ys.data(); lw.F0 = e.f0.data(); lw.F2 = e.fa.data(); lw.F3 = e.fb.data(); lw.Ynext = e.y.data();
+                lw.accuracy = accuracy; lw.consTol = consTol; lw.useInfNorm = useInfNorm; lw.projectEveryStep = projectEveryStep;
+                LRkmState st; st.vb = 0; st.velValid = false;
+                RkmStepResult r; r.errNorm = 0; r.projected = 0; int nproj = 0;
+                for (int s = 0; s < nsteps; ++s) { r = lRkmAttempt<JM_MOBILE5>(c, LT, k, lw, h, cy, st); nproj += r.projected; }
+                double* o = out + (size_t)k*(ny+2);
+                for (int i = 0; i < ny; ++i) o[i] = e.y[(size_t)i*N + k];
+                o[ny] = r.errNorm; o[ny+1] = nproj;
+            }
+            return 0;
+        }
+        LTables LT; LT.bodies = t.lbodies.data(); LT.children = t.children.data(); LT.forces = t.forces.data(); LT.fcoef = t.lfcoef.data();
         for (int k = 0; k < N; ++k) {
             Ctx c = makeCtx(e, k);
             c.qdotdot = nullptr; c.qerr = nullptr;
             double cy[CARRY_ROWS];
             RkmStepResult r; r.errNorm = 0; r.projected = 0; int nproj = 0;
             for (int s = 0; s < nsteps; ++s) {
-                r = lean ? tpiRkmStep<true>(c, tablesOf(c), k, w, h, cy) : tpiRkmStep<false>(c, tablesOf(c), k, w, h, cy);
+                r = lean == 3 ? tpiRkmStep<true, JM_ALL>(c, LT, k, w, h, cy)          // body-frame sweeps (sbk_local.cuh)
+                  : lean ? tpiRkmStep<true>(c, tablesOf(c), k, w, h, cy) : tpiRkmStep<false>(c, tablesOf(c), k, w, h, cy);
                 nproj += r.projected;
             }
             double* o = out + (size_t)k*(ny+2);
             for (int i = 0; i < ny; ++i) o[i] = e.y[(size_t)i*N + k];
             o[ny] = r.errNorm; o[ny+1] = nproj;
+        }
+        return 0;
+    } catch (const std::exception& ex) { std::fprintf(stderr, "emu: %s\n", ex.what()); return 1; }
+}
+
+// Derivatives only: in [N][nq+nu] -> out [N][nq+nu] (qdot, udot).  local = 1: body-frame sweeps, 0: LEAN ground-frame sweeps.
+int emu_deriv(const char* text, int N, const double* in, double* out, int local) {
+    try {
+        Emu e; setup(e, text, N);
+        const sbk_topology& t = e.topo; const int ny = t.nq + t.nu;
+        if (local && !t.localOk) return 5;
+        for (int k = 0; k < N; ++k) for (int i = 0; i < ny; ++i) e.y[(size_t)i*N + k] = in[(size_t)k*ny + i];
+        LTables LT; LT.bodies = t.lbodies.data(); LT.children = t.children.data(); LT.forces = t.forces.data(); LT.fcoef = t.lfcoef.data();
+        for (int k = 0; k < N; ++k) {
+            Ctx c = makeCtx(e, k); c.qdotdot = nullptr; c.qerr = nullptr;
+            double cy[CARRY_ROWS];
+            if (local) lEvalDerivatives(c, LT, k, cy, c.qdot, c.udot);
+            else tpiEvalDerivatives<true>(c, tablesOf(c), k, cy, c.qdot, c.udot, nullptr);
+            for (int i = 0; i < ny; ++i) out[(size_t)k*ny + i] = e.ydot[(size_t)i*N + k];
         }
         return 0;
     } catch (const std::exception& ex) { std::fprintf(stderr, "emu: %s\n", ex.what()); return 1; }
@@ -195,13 +234,23 @@ int emu_adaptive(const char* text, int N, const double* in, double* out, double 
             AdaptiveState st; st.t = 0; st.h = initStep; st.lastStep = initStep; st.steps = 0; st.attempts = 0;
             double lastErr = 0; int nproj = 0;
             double* o = out + (size_t)k*(ny+5);
-            if (fused) {
+            if (fused == 1) {
                 if (t.nb != 3 || t.bodies[1].joint != JT_PIN || t.bodies[2].joint != JT_PIN) return 4;
                 double y[8]; for (int i = 0; i < ny; ++i) y[i] = e.y[(size_t)i*N + k];
                 Chain2<JT_PIN, JT_PIN> ch; ch.b0 = &e.bodies[1]; ch.b1 = &e.bodies[2]; ch.forces = t.forces.data();
                 ch.gx = t.grav[0]; ch.gy = t.grav[1]; ch.gz = t.grav[2];
                 fusedRkmAdaptive(ch, y, lim, tFinal, allowInterpolation, 1000000, 0, st, lastErr);
                 for (int i = 0; i < ny; ++i) o[i] = y[i];
+            } else if (fused == 2) {   // fused two-sweep integrator on the body-frame cores
+                if (!t.localOk) return 5;
+                LTables LT; LT.bodies = t.lbodies.data(); LT.children = t.children.data(); LT.forces = t.forces.data(); LT.fcoef = t.lfcoef.data();
+                Ctx c = makeCtx(e, k); c.qdotdot = nullptr; c.qerr = nullptr;
+                double cy[CARRY_ROWS];
+                LRkmWork lw; lw.Y = e.y.data(); lw.W = e.ys.data(); lw.F0 = e.f0.data(); lw.F2 = e.fa.data(); lw.F3 = e.fb.data(); lw.Ynext = e.y0.data();
+                lw.accuracy = accuracy; lw.consTol = accuracy/10; lw.useInfNorm = 0; lw.projectEveryStep = 0;
+                LRkmState ls; ls.vb = 0; ls.velValid = false;
+                lRkmAdaptive<JM_MOBILE5>(c, LT, k, lw, lim, tFinal, allowInterpolation, 1000000, st, cy, ls, lastErr, nproj);
+                for (int i = 0; i < ny; ++i) o[i] = lw.Y[(size_t)i*N + k];
             } else {
                 Ctx c = makeCtx(e, k); c.qdotdot = nullptr; c.qerr = nullptr;
                 double cy[CARRY_ROWS];
