@@ -39,6 +39,8 @@ struct sbk_batch {
     int stage = ST_EMPTY; bool abiValid = false, accelValid = false;
     int64_t launches = 0, stepsTaken = 0, realizations = 0;
     bool adaptiveInit = false;
+    int64_t adaptStepsSeen = 0, adaptAttemptsSeen = 0;   // sums of the per-instance adaptive counters already folded into the stats
+    bool integInit = false;       // Integrator::initialize's forced projection has run for the current state
     double lastKernelMs = 0;
     long long recTotal = 0;
 };
@@ -252,6 +254,12 @@ sbk_batch* sbk_batch_create(const sbk_topology* t, int n, int device, void* stre
                            " (this library has no CPU fallback)");
         return nullptr;
     }
+    { cudaDeviceProp prop;
+      if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+          cudaGetLastError();
+          fail(SBK_ERR_CUDA, "sbk_batch_create: device " + std::to_string(device) + " is not an sm_100 GPU (the kernels are built for sm_100a only)");
+          return nullptr;
+      } }
     sbk_batch* b = new sbk_batch();
     b->topo = t; b->N = n; b->device = device;
     auto bail = [&](const std::string& m) { fail(SBK_ERR_CUDA, m); sbk_batch_destroy(b); return (sbk_batch*)nullptr; };
@@ -329,7 +337,19 @@ int sbk_synchronize(sbk_batch* b) {
 
 // ---- state ----------------------------------------------------------------------------------
 static void invalidate(sbk_batch* b) { b->stage = ST_EMPTY; b->abiValid = false; b->accelValid = false; }
-static void stateWasSet(sbk_batch* b) { invalidate(b); b->adaptiveInit = false; }
+static void stateWasSet(sbk_batch* b) {
+    invalidate(b); b->adaptiveInit = false; b->integInit = false;
+    // a new state starts a new history: the per-instance status words describe the operations since the last set_state
+    cudaMemsetAsync(b->a.status, 0, (size_t)b->N*sizeof(int), b->stream);
+}
+// Integrator::initialize (Integrator.cpp:367-377): realizeAndProjectKinematicsWithThrow(ForceProjection) normalises every
+// quaternion before the first step and counts one q projection (IntegratorRep.h:799-801) when the model has any.
+static int integratorInitialize(sbk_batch* b) {
+    if (b->integInit) return SBK_OK;
+    if (b->topo->nquat > 0) { CUDA_TRY(launchInitProject(b->a, b->stream)); b->launches++; }
+    b->integInit = true;
+    return SBK_OK;
+}
 
 int sbk_set_state(sbk_batch* b, const double* q, const double* u, const double* t) {
     if (!b) return fail(SBK_ERR_ARG, "null batch");
@@ -608,6 +628,7 @@ int sbk_rkm_step(sbk_batch* b, double h, int nsteps, const sbk_rkm_opts* opts, d
     a.h = h; a.nsteps = nsteps; a.accuracy = o.accuracy; a.consTol = o.constraint_tol;
     a.useInfNorm = o.use_infinity_norm; a.projectEveryStep = o.project_every_step;
     if (nsteps > 0) {
+        if (int rc = integratorInitialize(b)) return rc;
         CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
         if (b->plan == 2) {
             std::vector<int> joints(b->topo->nb);
@@ -634,7 +655,7 @@ void sbk_adaptive_default_opts(sbk_adaptive_opts* o) {
 int sbk_rkm_adaptive(sbk_batch* b, double tFinal, const sbk_adaptive_opts* opts, int32_t* steps, int32_t* attempts, double* lastStep) {
     if (!b) return fail(SBK_ERR_ARG, "null batch");
     if (int rc = useDevice(b)) return rc;
-    if (b->plan == 3 || b->plan == 4) return fail(SBK_ERR_ARG, "sbk_rkm_adaptive: not available in the level-parallel plans (use sbk_batch_set_plan(b, 1))");
+    if (b->plan == 3) return fail(SBK_ERR_ARG, "sbk_rkm_adaptive: not available in plan 3 (use sbk_batch_set_plan(b, 0 or 1))");
     sbk_adaptive_opts o; sbk_adaptive_default_opts(&o);
     if (opts) {
         o = *opts;
@@ -656,22 +677,37 @@ int sbk_rkm_adaptive(sbk_batch* b, double tFinal, const sbk_adaptive_opts* opts,
         CUDA_TRY(cudaMemcpyAsync(a.lastStep, hv.data(), N*sizeof(double), cudaMemcpyHostToDevice, b->stream));
         CUDA_TRY(cudaMemsetAsync(a.stepsTaken, 0, N*sizeof(int), b->stream));
         CUDA_TRY(cudaMemsetAsync(a.attempts, 0, N*sizeof(int), b->stream));
+        b->adaptStepsSeen = 0; b->adaptAttemptsSeen = 0;
         CUDA_TRY(cudaStreamSynchronize(b->stream));
         b->adaptiveInit = true;
     }
     a.tFinal = tFinal; a.accuracy = o.accuracy; a.consTol = o.constraint_tol; a.minStep = o.min_step; a.maxStep = o.max_step;
     a.useInfNorm = o.use_infinity_norm; a.projectEveryStep = o.project_every_step; a.allowInterp = o.allow_interpolation;
     a.maxAttempts = o.max_attempts > 0 ? o.max_attempts : 1000000;
+    if (int rc = integratorInitialize(b)) return rc;
     CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
     if (b->plan == 2) {
         std::vector<int> joints(b->topo->nb);
         for (int i = 0; i < b->topo->nb; ++i) joints[i] = b->topo->bodies[i].joint;
         CUDA_TRY(launchFusedRkm(a, joints.data(), true, b->stream)); b->launches++;
-    } else if (int rc = launch(b, OP_RKM_ADAPT)) return rc;
+    } else {
+        // plans 1 and 4 share the record layout: error-controlled stepping always runs the thread-per-instance kernel
+        // (every instance keeps its own step-size history; the grid-level plan steps the whole batch in lockstep)
+        CUDA_TRY(launchTpi(OP_RKM_ADAPT, a, b->stream)); b->launches++;
+    }
     CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
     invalidate(b);
-    if (steps)    CUDA_TRY(cudaMemcpyAsync(steps, a.stepsTaken, N*sizeof(int), cudaMemcpyDeviceToHost, b->stream));
-    if (attempts) CUDA_TRY(cudaMemcpyAsync(attempts, a.attempts, N*sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    {   // Integrator::getNumStepsTaken / getNumRealizations over the batch: one fresh evaluation per step + 4 per attempt
+        std::vector<int> hs(N), ha(N);
+        CUDA_TRY(cudaMemcpyAsync(hs.data(), a.stepsTaken, N*sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+        CUDA_TRY(cudaMemcpyAsync(ha.data(), a.attempts, N*sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+        CUDA_TRY(cudaStreamSynchronize(b->stream));
+        int64_t ss = 0, sa = 0; for (size_t k = 0; k < N; ++k) { ss += hs[k]; sa += ha[k]; }
+        b->stepsTaken += ss - b->adaptStepsSeen; b->realizations += (ss - b->adaptStepsSeen) + 4*(sa - b->adaptAttemptsSeen);
+        b->adaptStepsSeen = ss; b->adaptAttemptsSeen = sa;
+        if (steps)    std::memcpy(steps, hs.data(), N*sizeof(int));
+        if (attempts) std::memcpy(attempts, ha.data(), N*sizeof(int));
+    }
     if (lastStep) CUDA_TRY(cudaMemcpyAsync(lastStep, a.lastStep, N*sizeof(double), cudaMemcpyDeviceToHost, b->stream));
     CUDA_TRY(cudaStreamSynchronize(b->stream));
     return SBK_OK;

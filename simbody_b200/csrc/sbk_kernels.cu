@@ -433,6 +433,21 @@ __global__ void initGroundKernel(const KArgs a) {
     for (int f = 0; f < F_H; ++f) rec[(long long)f*a.cStride] = (f == F_XGB || f == F_XGB+4 || f == F_XGB+8) ? 1.0 : 0.0;
 }
 
+// Integrator::initialize (Integrator.cpp:367-377, ProjectOptions::ForceProjection): SimbodyMatterSubsystemRep::normalizeQuaternions
+// (:4448-4476) -> RBNodeBall/Free::enforceQuaternionConstraints (RigidBodyNodeSpec_Ball.h:417-434): quat /= |quat|, one projection counted.
+__global__ void initProjectKernel(const KArgs a) {
+    const int k = blockIdx.x*blockDim.x + threadIdx.x;
+    if (k >= a.N) return;
+    const BodyConst* bodies = reinterpret_cast<const BodyConst*>(a.tables);
+    for (int b = 1; b < a.nb; ++b) {
+        if (bodies[b].joint != JT_BALL && bodies[b].joint != JT_FREE) continue;
+        double* q = a.y + (long long)bodies[b].q0*a.N + k; const long long N = a.N;
+        const double n = sqrt(q[0]*q[0] + q[N]*q[N] + q[2*N]*q[2*N] + q[3*N]*q[3*N]);
+        q[0] = q[0]/n; q[N] = q[N]/n; q[2*N] = q[2*N]/n; q[3*N] = q[3*N]/n;
+    }
+    a.projCount[k] += 1;
+}
+
 // 32x32 tiled transpose: src is [rows][cols] row-major -> dst [cols][rows]
 __global__ void transposeKernel(const double* __restrict__ src, double* __restrict__ dst, int rows, int cols) {
     __shared__ double tile[32][33];
@@ -705,6 +720,10 @@ cudaError_t launchFusedRkm(const KArgs& a, const int* joints, bool adaptive, cud
         }
     }
     return cudaErrorInvalidValue;
+}
+cudaError_t launchInitProject(const KArgs& a, cudaStream_t stream) {
+    initProjectKernel<<<(a.N + 255)/256, 256, 0, stream>>>(a);
+    return cudaGetLastError();
 }
 cudaError_t launchInitGround(const KArgs& a, cudaStream_t stream) {
     initGroundKernel<<<(a.N + 255)/256, 256, 0, stream>>>(a);

@@ -81,6 +81,8 @@ cudaError_t launchLp(KernelOp op, const KArgs& a, cudaStream_t stream);
 cudaError_t launchGlRkm(const KArgs& a, cudaStream_t stream);
 // Every operation of plan 4 (OP_RKM and the API operations; OP_RKM_ADAPT is not available).
 cudaError_t launchGl(KernelOp op, const KArgs& a, cudaStream_t stream);
+// Integrator::initialize's forced projection: normalise every quaternion of y, count one projection per instance.
+cudaError_t launchInitProject(const KArgs& a, cudaStream_t stream);
 // Ground record (identity transform, zero velocity/acceleration) for every instance.
 cudaError_t launchInitGround(const KArgs& a, cudaStream_t stream);
 // dst[k*len + i] <-> src[i*N + k]

@@ -476,6 +476,84 @@ SBK_HD void lInUniversal(const ABI& P, const SV zsum, const SV pA, const SV cc, 
 }
 
 //==============================================================================================
+// Prefetch of a body's inputs, one body step ahead.  A body step starts with loads whose values feed its
+// first arithmetic (sin/cos rows -> rotation, coordinates, G / nu, the stage vectors): issued at the top of
+// the step they cost a full trip to HBM with two warps per scheduler to cover it (ncu: 50% of the stall
+// samples were long-scoreboard).  Every address is known from the body table alone, so the sweep drivers
+// request the NEXT body's rows while the current one computes: asynchronous global->shared copies
+// (cp.async, SASS LDGSTS) into one of two slots of the work item's shared-memory column, consumed with LDS.
+// Layouts are compile-time per mobilizer kind (same functions on the producer and the consumer side).
+//==============================================================================================
+enum { LPF_ROWS = 32 };                     // rows per prefetch slot (two slots per work item)
+SBK_HD void lpfCopy(double* dst, const double* src) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+#else
+    *dst = *src;
+#endif
+}
+SBK_HD void lpfCommit() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+SBK_HD void lpfWait() {                      // every request but the most recent one has landed
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+#endif
+}
+SBK_HD void lpfWaitAll() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
+// slot rows of the inward sweep: SC | q u | V (tips)
+template <int JT> struct LPfIn  { enum { SC = 0, QU = lscCount<JT>(), V = QU + JointDims<JT>::nq + JointDims<JT>::nu }; };
+// slot rows of the fused outward sweep: G | NU | SC | q u | Y slots | F0 slots | F2 or F3 slots; the heavy mobilizers leave
+// the last one or two groups to direct loads (32 rows)
+template <int JT> struct LPfOut {
+    enum { NS = JointDims<JT>::nq + JointDims<JT>::nu, G = 0, NU = lgCount<JT>(), SC = NU + JointDims<JT>::nu, QU = SC + lscCount<JT>(),
+           Y = QU + NS, F0 = Y + NS, F23 = F0 + NS,
+           HAS_F0 = (JT != JT_BALL && JT != JT_FREE) ? 1 : 0, HAS_F23 = (JT == JT_PIN || JT == JT_SLIDER) ? 1 : 0 };
+};
+// Row counts of a mobilizer kind at run time (the producer works on the NEXT body, whose kind is not a template parameter:
+// one compact loop per row group instead of an unrolled copy sequence per kind keeps the prefetch out of the instruction cache's way).
+struct LPfDims { int g, d, nsc, nq; };
+SBK_HD LPfDims lpfDims(const int joint) {
+    LPfDims r;
+    r.g   = joint == JT_BALL ? 9 : joint == JT_FREE ? 0 : joint == JT_UNIVERSAL ? 12 : 6;
+    r.d   = joint == JT_BALL ? 3 : joint == JT_FREE ? 6 : joint == JT_UNIVERSAL ? 2 : 1;
+    r.nsc = joint == JT_PIN ? 2 : joint == JT_UNIVERSAL ? 4 : 0;
+    r.nq  = joint == JT_BALL ? 4 : joint == JT_FREE ? 7 : joint == JT_UNIVERSAL ? 2 : 1;
+    return r;
+}
+// A kernel built for ONE mobilizer kind (the Pin-only variant) knows the counts at compile time: straight-line copies.
+template <int JMASK> SBK_HD LPfDims lpfDimsM(const int joint) {
+    if constexpr ((JMASK & JM_ALL) == JM_PIN) return lpfDims(JT_PIN);
+    else return lpfDims(joint);
+}
+template <int JMASK>
+SBK_HD void lpfRows(double* dst, const double* src, const long long srcStride, const int n) {
+    if constexpr ((JMASK & JM_ALL) == JM_PIN) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) if (i < n) lpfCopy(dst + i*SBK_CARRY_STRIDE, src + i*srcStride);
+    } else {
+#pragma unroll 1
+        for (int i = 0; i < n; ++i) lpfCopy(dst + i*SBK_CARRY_STRIDE, src + i*srcStride);
+    }
+}
+template <int JMASK, bool BLK>
+SBK_HD void lPrefetchIn(const Ctx& c, const LBody& bc, const int inst, double* pf, const double* S, const int vb) {
+    const LPfDims n = lpfDimsM<JMASK>(bc.joint);
+    const CacheRefT<BLK> me = lrecOf<BLK>(c, inst, bc.rec);
+    const long long rs = BLK ? BLK_LANES : me.stride, ss = BLK ? BLK_LANES : c.sStride;
+    lpfRows<JMASK>(pf, me.p + LR_SC*rs, rs, n.nsc);                                                        // LPfIn::SC = 0
+    lpfRows<JMASK>(pf + n.nsc*SBK_CARRY_STRIDE, S + stateIndex<BLK>(c, inst, bc.q0), ss, n.nq);             // LPfIn::QU
+    lpfRows<JMASK>(pf + (n.nsc + n.nq)*SBK_CARRY_STRIDE, S + stateIndex<BLK>(c, inst, c.nq + bc.u0), ss, n.d);
+    if (bc.flags & BF_TIP) lpfRows<JMASK>(pf + (n.nsc + n.nq + n.d)*SBK_CARRY_STRIDE, me.p + (lrV(n.d) + vb)*rs, rs, 6);   // LPfIn::V
+}
+
+//==============================================================================================
 // Body steps (generic form: dense S through abiCore / zCore)
 //==============================================================================================
 // Velocity sweep, base -> tip: v = X v_parent + S u'.  Stores sin/cos; v only at tips / branch points.
@@ -506,17 +584,26 @@ SBK_BODY void lVelBody(const Ctx& c, const LBody& bc, const int inst, double* cy
 // Inward sweep, tip -> base: articulated inertia and bias force in M, G = U*DI and nu = DI*eps to the record,
 // P+ / z+ handed to the parent in the parent's frame.
 template <int JT>
-SBK_BODY void lInwardBody(const Ctx& c, const LTables& T, const LBody& bc, const int inst, double* cy, const int vb = 0) {
+SBK_BODY void lInwardBody(const Ctx& c, const LTables& T, const LBody& bc, const int inst, double* cy, const int vb = 0, const double* pf = nullptr) {
     constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
     constexpr bool BLK = SBK_DEV_BLK;
     const CacheRefT<BLK> me = lrecOf<BLK>(c, inst, bc.rec);
     double q[dim1(NQ)], u[dim1(d)], up[dim1(d)], sc[LSC_ROWS];
-    lloadCoords<JT, BLK>(c, inst, bc, q, u);
+    if (pf) {            // requested one body step ahead (lPrefetchIn)
 #pragma unroll
-    for (int i = 0; i < lscCount<JT>(); ++i) sc[i] = me.ld(LR_SC + i);
+        for (int i = 0; i < NQ; ++i) q[i] = pf[(LPfIn<JT>::QU + i)*SBK_CARRY_STRIDE];
+#pragma unroll
+        for (int i = 0; i < d; ++i)  u[i] = pf[(LPfIn<JT>::QU + NQ + i)*SBK_CARRY_STRIDE];
+#pragma unroll
+        for (int i = 0; i < lscCount<JT>(); ++i) sc[i] = pf[(LPfIn<JT>::SC + i)*SBK_CARRY_STRIDE];
+    } else {
+        lloadCoords<JT, BLK>(c, inst, bc, q, u);
+#pragma unroll
+        for (int i = 0; i < lscCount<JT>(); ++i) sc[i] = me.ld(LR_SC + i);
+    }
     LJoint<JT> k; ljoint<JT, false>(bc, q, sc, k);
     const bool haveCarryChild = !(bc.flags & BF_TIP);
-    const SV v = haveCarryChild ? lcyLoadSV(cy + LC_VSELF*SBK_CARRY_STRIDE) : me.ldSV(lrV(d) + vb);
+    const SV v = haveCarryChild ? lcyLoadSV(cy + LC_VSELF*SBK_CARRY_STRIDE) : pf ? lcyLoadSV(pf + LPfIn<JT>::V*SBK_CARRY_STRIDE) : me.ldSV(lrV(d) + vb);
     SV vJ, cJ; ljointVel<JT>(k, u, up, vJ, cJ);
     const SV cc = cJ + crossMotion(v, vJ);
 

@@ -23,7 +23,8 @@ struct LRkmWork {
 };
 // carry rows of the fused outward sweep: v of the evaluated state, a, v of the next stage's state, then the
 // running error sums of the last stage (q part, u part, sum of (|quat| - 1)^2)
-enum { LF_V = 0, LF_A = 6, LF_V2 = 12, LF_QACC = 18, LF_UACC = 19, LF_QUATACC = 20, LFCARRY_ROWS = 33 };
+// then the two prefetch slots (sbk_local.cuh)
+enum { LF_V = 0, LF_A = 6, LF_V2 = 12, LF_QACC = 18, LF_UACC = 19, LF_QUATACC = 20, LF_PF = 33, LFCARRY_ROWS = LF_PF + 2*LPF_ROWS };
 
 // NaN / Inf must survive an Inf-norm accumulation (fmax drops NaN): IntegratorRep.h:454-488 + adjustStepSize's
 // isFinite test need a non-finite norm to come out non-finite.
@@ -46,23 +47,66 @@ SBK_HD LStage lstageOf(const int stage, const double h, const LRkmWork& w) {
     return s;
 }
 
+// Request the rows the fused outward step of body bc will read (layout LPfOut<kind of bc>).
+template <int JMASK, bool BLK>
+SBK_HD void lPrefetchOut(const Ctx& c, const LBody& bc, const int inst, double* pf, const LRkmWork& w, const double* S, const LStage& sg) {
+    const LPfDims n = lpfDimsM<JMASK>(bc.joint);
+    const int ns = n.nq + n.d, oQU = n.g + n.d + n.nsc;
+    const CacheRefT<BLK> me = lrecOf<BLK>(c, inst, bc.rec);
+    const long long rs = BLK ? BLK_LANES : me.stride, ss = BLK ? BLK_LANES : c.sStride;
+    const long long offQ = stateIndex<BLK>(c, inst, bc.q0), offU = stateIndex<BLK>(c, inst, c.nq + bc.u0);
+    lpfRows<JMASK>(pf + oQU*SBK_CARRY_STRIDE, S + offQ, ss, n.nq);
+    lpfRows<JMASK>(pf + (oQU + n.nq)*SBK_CARRY_STRIDE, S + offU, ss, n.d);
+    if (sg.stage < 0) return;
+    lpfRows<JMASK>(pf, me.p + LR_G*rs, rs, n.g);
+    lpfRows<JMASK>(pf + n.g*SBK_CARRY_STRIDE, me.p + lrNU(n.d)*rs, rs, n.d);
+    lpfRows<JMASK>(pf + (n.g + n.d)*SBK_CARRY_STRIDE, me.p + LR_SC*rs, rs, n.nsc);
+    if (sg.stage > 0) {
+        lpfRows<JMASK>(pf + (oQU + ns)*SBK_CARRY_STRIDE, w.Y + offQ, ss, n.nq);
+        lpfRows<JMASK>(pf + (oQU + ns + n.nq)*SBK_CARRY_STRIDE, w.Y + offU, ss, n.d);
+        if (bc.joint != JT_BALL && bc.joint != JT_FREE) {                  // LPfOut::HAS_F0
+            lpfRows<JMASK>(pf + (oQU + 2*ns)*SBK_CARRY_STRIDE, w.F0 + offQ, ss, n.nq);
+            lpfRows<JMASK>(pf + (oQU + 2*ns + n.nq)*SBK_CARRY_STRIDE, w.F0 + offU, ss, n.d);
+        }
+        const double* f23 = sg.m2 != 0 ? w.F2 : sg.m3 != 0 ? w.F3 : nullptr;
+        if (f23 && (bc.joint == JT_PIN || bc.joint == JT_SLIDER)) {        // LPfOut::HAS_F23
+            lpfRows<JMASK>(pf + (oQU + 3*ns)*SBK_CARRY_STRIDE, f23 + offQ, ss, n.nq);
+            lpfRows<JMASK>(pf + (oQU + 3*ns + n.nq)*SBK_CARRY_STRIDE, f23 + offU, ss, n.d);
+        }
+    }
+}
+
 // One body of the fused outward sweep.  Phase 0 (stage >= 0): acceleration of the evaluation at state S (S = Y for
 // stage 0, W otherwise) and the body's slots of the next state; phase 1: sin/cos and velocity of that next state.
 // Both phases run the same joint / velocity code (a two-trip loop, one copy in the instruction cache).  stage < 0:
 // phase 1 only, on the state in S (the stand-alone velocity sweep).  vr / vw: velocity buffer read / written.
 template <int JT>
 SBK_BODY void lFusedOutBody(const Ctx& c, const LBody& bc, const int inst, double* cy, const LRkmWork& w, const double* S,
-                            const LStage& sg, const int vr, const int vw) {
+                            const LStage& sg, const int vr, const int vw, const double* pf) {
     constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
     constexpr bool BLK = SBK_DEV_BLK;
+    typedef LPfOut<JT> L;
     const CacheRefT<BLK> me = lrecOf<BLK>(c, inst, bc.rec);
     const int nq = c.nq, stage = sg.stage;
     double qu[dim1(NQ + d)], up[dim1(d)], sc[LSC_ROWS];
 #pragma unroll
-    for (int i = 0; i < NQ + d; ++i) qu[i] = ldS<BLK>(c, inst, S, i < NQ ? bc.q0 + i : nq + bc.u0 + (i - NQ));
+    for (int i = 0; i < NQ + d; ++i) qu[i] = pf[(L::QU + i)*SBK_CARRY_STRIDE];
     if (stage >= 0) {
 #pragma unroll
-        for (int i = 0; i < lscCount<JT>(); ++i) sc[i] = me.ld(LR_SC + i);
+        for (int i = 0; i < lscCount<JT>(); ++i) sc[i] = pf[(L::SC + i)*SBK_CARRY_STRIDE];
+    }
+    // stage vectors that were too many rows for the slot: requested now, consumed after the acceleration arithmetic
+    double f0d[dim1(NQ + d)], f23d[dim1(NQ + d)];
+    if (stage > 0) {
+        if constexpr (L::HAS_F0 == 0) {
+#pragma unroll
+            for (int i = 0; i < NQ + d; ++i) f0d[i] = ldS<BLK>(c, inst, w.F0, i < NQ ? bc.q0 + i : nq + bc.u0 + (i - NQ));
+        }
+        if constexpr (L::HAS_F23 == 0) {
+            const double* f23 = sg.m2 != 0 ? w.F2 : sg.m3 != 0 ? w.F3 : nullptr;
+#pragma unroll
+            for (int i = 0; i < NQ + d; ++i) f23d[i] = f23 ? ldS<BLK>(c, inst, f23, i < NQ ? bc.q0 + i : nq + bc.u0 + (i - NQ)) : 0.0;
+        }
     }
 #pragma unroll 1
     for (int ph = stage < 0 ? 1 : 0; ph < 2; ++ph) {
@@ -88,9 +132,9 @@ SBK_BODY void lFusedOutBody(const Ctx& c, const LBody& bc, const int inst, doubl
         // ---- acceleration sweep of this evaluation (cf. lOutwardBody) ----------------------------------------
         double nu[dim1(d)], upd[dim1(d)], f[dim1(NQ + d)], G[dim1(lgCount<JT>())];
 #pragma unroll
-        for (int i = 0; i < lgCount<JT>(); ++i) G[i] = me.ld(LR_G + i);
+        for (int i = 0; i < lgCount<JT>(); ++i) G[i] = pf[(L::G + i)*SBK_CARRY_STRIDE];
 #pragma unroll
-        for (int j = 0; j < d; ++j) nu[j] = me.ld(lrNU(d) + j);
+        for (int j = 0; j < d; ++j) nu[j] = pf[(L::NU + j)*SBK_CARRY_STRIDE];
         const SV aP = fromCarry ? lcyLoadSV(cy + LF_A*SBK_CARRY_STRIDE) : pa.ldSV(6);
         const SV cc = cJ + crossMotion(v, vJ);
         const SV aPlus = xMotion(k.R, k.p, aP);
@@ -126,10 +170,10 @@ SBK_BODY void lFusedOutBody(const Ctx& c, const LBody& bc, const int inst, doubl
 #pragma unroll
         for (int i = 0; i < NQ + d; ++i) {
             const int slot = i < NQ ? bc.q0 + i : nq + bc.u0 + (i - NQ);
-            const double y0 = (stage == 0) ? qu[i] : ldS<BLK>(c, inst, w.Y, slot);
-            const double f0 = (sg.a0 != 0) ? ldS<BLK>(c, inst, w.F0, slot) : 0.0;
-            const double f2 = (sg.m2 != 0) ? ldS<BLK>(c, inst, w.F2, slot) : 0.0;
-            const double f3 = (sg.m3 != 0) ? ldS<BLK>(c, inst, w.F3, slot) : 0.0;
+            const double y0 = (stage == 0) ? qu[i] : pf[(L::Y + i)*SBK_CARRY_STRIDE];
+            const double f0 = (sg.a0 != 0) ? (L::HAS_F0 != 0 ? pf[(L::F0 + i)*SBK_CARRY_STRIDE] : f0d[i]) : 0.0;
+            const double f23 = (sg.m2 != 0 || sg.m3 != 0) ? (L::HAS_F23 != 0 ? pf[(L::F23 + i)*SBK_CARRY_STRIDE] : f23d[i]) : 0.0;
+            const double f2 = (sg.m2 != 0) ? f23 : 0.0, f3 = (sg.m3 != 0) ? f23 : 0.0;
             if (sg.fdst) stS<BLK>(c, inst, sg.fdst, slot, f[i]);
             const double r = y0 + sg.hk*(((sg.a0*f0 + sg.m2*f2) + sg.m3*f3) + sg.mf*f[i]);
             if (last) { err[i] = 0.2*fabs(r - qu[i]); stS<BLK>(c, inst, w.Ynext, slot, r); stS<BLK>(c, inst, w.W, slot, err[i]); }
@@ -168,9 +212,15 @@ SBK_BODY void lFusedOutBody(const Ctx& c, const LBody& bc, const int inst, doubl
 // Ctx::q/u and buffer 0).
 template <int JMASK>
 SBK_HD void lInwardSweep(const Ctx& c0, const LTables& T, const int inst, double* cy, const double* S, const int vb) {
-    Ctx c = c0; c.q = S; c.u = S + (SBK_DEV_BLK ? (long long)c.nq*BLK_LANES : (long long)c.nq*c.sStride);
+    constexpr bool BLK = SBK_DEV_BLK;
+    Ctx c = c0; c.q = S; c.u = S + (BLK ? (long long)c.nq*BLK_LANES : (long long)c.nq*c.sStride);
+    #define SBK_PFSLOT(par) (cy + (LF_PF + LPF_ROWS*((par) & 1))*SBK_CARRY_STRIDE)
 #pragma unroll 1
-    for (int b = c.nb - 1; b >= 1; --b) { const LBody& bc = T.bodies[b]; SBK_DISPATCH_LOCAL(JMASK, bc.joint, (lInwardBody<JT>(c, T, bc, inst, cy, vb))); }
+    for (int b = c.nb; b >= 1; --b) {          // trip b = nb only requests the first body's rows
+        if (b > 1) lPrefetchIn<JMASK, BLK>(c, T.bodies[b - 1], inst, SBK_PFSLOT(b - 1), S, vb);
+        lpfCommit(); lpfWait();
+        if (b < c.nb) { const LBody& bc = T.bodies[b]; SBK_DISPATCH_LOCAL(JMASK, bc.joint, (lInwardBody<JT>(c, T, bc, inst, cy, vb, SBK_PFSLOT(b)))); }
+    }
 }
 // stage 0..4: acceleration sweep of the evaluation at S + next stage state + its velocity data; stage < 0: velocity data of S only
 template <int JMASK>
@@ -186,7 +236,12 @@ SBK_HD void lFusedOutSweep(const Ctx& c, const LTables& T, const int inst, doubl
     }
     if (stage == 4) { cy[LF_QACC*SBK_CARRY_STRIDE] = 0; cy[LF_UACC*SBK_CARRY_STRIDE] = 0; cy[LF_QUATACC*SBK_CARRY_STRIDE] = 0; }
 #pragma unroll 1
-    for (int b = 1; b < c.nb; ++b) { const LBody& bc = T.bodies[b]; SBK_DISPATCH_LOCAL(JMASK, bc.joint, (lFusedOutBody<JT>(c, bc, inst, cy, w, S, sg, vr, vw))); }
+    for (int b = 0; b < c.nb; ++b) {           // trip b = 0 only requests the first body's rows
+        if (b + 1 < c.nb) lPrefetchOut<JMASK, BLK>(c, T.bodies[b + 1], inst, SBK_PFSLOT(b + 1), w, S, sg);
+        lpfCommit(); lpfWait();
+        if (b >= 1) { const LBody& bc = T.bodies[b]; SBK_DISPATCH_LOCAL(JMASK, bc.joint, (lFusedOutBody<JT>(c, bc, inst, cy, w, S, sg, vr, vw, SBK_PFSLOT(b)))); }
+    }
+    #undef SBK_PFSLOT
 }
 template <int JMASK>
 SBK_HD void lVelSweep(const Ctx& c, const LTables& T, const int inst, double* cy, const LRkmWork& w, const double* S, const int vb) {

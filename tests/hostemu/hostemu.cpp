@@ -82,7 +82,7 @@ int emu_eval(const char* text, int N, const double* in, double* out) {
         for (int k = 0; k < N; ++k) {
             const double* p = in + (size_t)k*inStride; double* o = out + (size_t)k*outStride;
             Ctx c = makeCtx(e, k);
-            double cy[CARRY_ROWS];
+            double cy[CARRY_ROWS + LFCARRY_ROWS];
             c.fmobOut = e.fmob.data(); c.FbodyOut = e.Fbody.data();
             tpiEvalDerivatives<false>(c, tablesOf(c), k, cy, c.qdot, c.udot, c.qdotdot);
             for (int i = 0; i < nq; ++i) *o++ = e.ydot[(size_t)i*N + k];
@@ -170,7 +170,7 @@ int emu_step(const char* text, int N, const double* in, double* out, double h, i
             LTables LT; LT.bodies = t.lbodies.data(); LT.children = t.children.data(); LT.forces = t.forces.data(); LT.fcoef = t.lfcoef.data();
             for (int k = 0; k < N; ++k) {
                 Ctx c = makeCtx(e, k); c.qdotdot = nullptr; c.qerr = nullptr;
-                double cy[CARRY_ROWS];
+                double cy[CARRY_ROWS + LFCARRY_ROWS];
                 LRkmWork lw; lw.Y = e.y.data(); lw.W = e.ys.data(); lw.F0 = e.f0.data(); lw.F2 = e.fa.data(); lw.F3 = e.fb.data(); lw.Ynext = e.y.data();
                 lw.accuracy = accuracy; lw.consTol = consTol; lw.useInfNorm = useInfNorm; lw.projectEveryStep = projectEveryStep;
                 LRkmState st; st.vb = 0; st.velValid = false;
@@ -186,7 +186,7 @@ int emu_step(const char* text, int N, const double* in, double* out, double h, i
         for (int k = 0; k < N; ++k) {
             Ctx c = makeCtx(e, k);
             c.qdotdot = nullptr; c.qerr = nullptr;
-            double cy[CARRY_ROWS];
+            double cy[CARRY_ROWS + LFCARRY_ROWS];
             RkmStepResult r; r.errNorm = 0; r.projected = 0; int nproj = 0;
             for (int s = 0; s < nsteps; ++s) {
                 r = lean == 3 ? tpiRkmStep<true, JM_ALL>(c, LT, k, w, h, cy)          // body-frame sweeps (sbk_local.cuh)
@@ -211,7 +211,7 @@ int emu_deriv(const char* text, int N, const double* in, double* out, int local)
         LTables LT; LT.bodies = t.lbodies.data(); LT.children = t.children.data(); LT.forces = t.forces.data(); LT.fcoef = t.lfcoef.data();
         for (int k = 0; k < N; ++k) {
             Ctx c = makeCtx(e, k); c.qdotdot = nullptr; c.qerr = nullptr;
-            double cy[CARRY_ROWS];
+            double cy[CARRY_ROWS + LFCARRY_ROWS];
             if (local) lEvalDerivatives(c, LT, k, cy, c.qdot, c.udot);
             else tpiEvalDerivatives<true>(c, tablesOf(c), k, cy, c.qdot, c.udot, nullptr);
             for (int i = 0; i < ny; ++i) out[(size_t)k*ny + i] = e.ydot[(size_t)i*N + k];
@@ -245,7 +245,7 @@ int emu_adaptive(const char* text, int N, const double* in, double* out, double 
                 if (!t.localOk) return 5;
                 LTables LT; LT.bodies = t.lbodies.data(); LT.children = t.children.data(); LT.forces = t.forces.data(); LT.fcoef = t.lfcoef.data();
                 Ctx c = makeCtx(e, k); c.qdotdot = nullptr; c.qerr = nullptr;
-                double cy[CARRY_ROWS];
+                double cy[CARRY_ROWS + LFCARRY_ROWS];
                 LRkmWork lw; lw.Y = e.y.data(); lw.W = e.ys.data(); lw.F0 = e.f0.data(); lw.F2 = e.fa.data(); lw.F3 = e.fb.data(); lw.Ynext = e.y0.data();
                 lw.accuracy = accuracy; lw.consTol = accuracy/10; lw.useInfNorm = 0; lw.projectEveryStep = 0;
                 LRkmState ls; ls.vb = 0; ls.velValid = false;
@@ -253,7 +253,7 @@ int emu_adaptive(const char* text, int N, const double* in, double* out, double 
                 for (int i = 0; i < ny; ++i) o[i] = lw.Y[(size_t)i*N + k];
             } else {
                 Ctx c = makeCtx(e, k); c.qdotdot = nullptr; c.qerr = nullptr;
-                double cy[CARRY_ROWS];
+                double cy[CARRY_ROWS + LFCARRY_ROWS];
                 tpiRkmAdaptive<true>(c, tablesOf(c), k, w, lim, tFinal, allowInterpolation, 1000000, st, cy, lastErr, nproj);
                 for (int i = 0; i < ny; ++i) o[i] = e.y[(size_t)i*N + k];
             }
