@@ -228,17 +228,25 @@ static int cmdExtras(RefSystem& rs, const char* inPath, const char* outPath, int
 
 // ---- step -----------------------------------------------------------------------------------
 // in per instance: q[nq] u[nu]; out per instance: q[nq] u[nu] stepsTaken realizations qProjections
-static void configureFixed(RungeKuttaMersonIntegrator& integ, double h, double accuracy) {
+// Integrator options a command line may set (Integrator.h:352-394): constraint tolerance, infinity norm, project every step
+struct IntegOpts { double consTol = -1; int infNorm = 0; int projectEvery = 0; };
+static void applyOpts(RungeKuttaMersonIntegrator& integ, const IntegOpts& o) {
+    if (o.consTol > 0) integ.setConstraintTolerance(o.consTol);
+    if (o.infNorm) integ.setUseInfinityNorm(true);
+    if (o.projectEvery) integ.setProjectEveryStep(true);
+}
+static void configureFixed(RungeKuttaMersonIntegrator& integ, double h, double accuracy, const IntegOpts& o = IntegOpts()) {
     integ.setFixedStepSize(h);
     integ.setAllowInterpolation(false);
     if (accuracy > 0) integ.setAccuracy(accuracy);
+    applyOpts(integ, o);
 }
 // The first stepTo() after initialize() returns at once (StartOfContinuousInterval), so loop
 // until the advanced time reaches tFinal; every internal step has size h.
 static void advanceTo(RungeKuttaMersonIntegrator& integ, double tFinal) {
     while (integ.getAdvancedTime() < tFinal*(1 - 1e-12)) integ.stepTo(tFinal);
 }
-static int cmdStep(RefSystem& rs, const char* inPath, const char* outPath, int N, double h, int nsteps, double accuracy) {
+static int cmdStep(RefSystem& rs, const char* inPath, const char* outPath, int N, double h, int nsteps, double accuracy, const IntegOpts& opts) {
     const int nq=rs.nq, nu=rs.nu, ny=nq+nu;
     std::vector<double> in = readDoubles(inPath);
     if ((int)in.size() != N*ny) { std::fprintf(stderr, "step: input has %zu doubles, expected %d\n", in.size(), N*ny); return 2; }
@@ -247,7 +255,7 @@ static int cmdStep(RefSystem& rs, const char* inPath, const char* outPath, int N
         State s = rs.defaultState;
         setQU(s, &in[(size_t)k*ny], nq, &in[(size_t)k*ny+nq], nu);
         RungeKuttaMersonIntegrator integ(rs.system);
-        configureFixed(integ, h, accuracy);
+        configureFixed(integ, h, accuracy, opts);
         integ.initialize(s);
         advanceTo(integ, nsteps*h);
         const State& a = integ.getAdvancedState();
@@ -261,26 +269,29 @@ static int cmdStep(RefSystem& rs, const char* inPath, const char* outPath, int N
 }
 
 // ---- adaptive (config C1) -------------------------------------------------------------------
-static int cmdAdaptive(RefSystem& rs, const char* inPath, const char* outPath, int N, double tFinal, double accuracy, bool allowInterpolation) {
+static int cmdAdaptive(RefSystem& rs, const char* inPath, const char* outPath, int N, double tFinal, double accuracy, bool allowInterpolation,
+                       const IntegOpts& opts) {
     const int nq=rs.nq, nu=rs.nu, ny=nq+nu;
     std::vector<double> in = readDoubles(inPath);
-    // out per instance: advanced q, u | steps taken | steps attempted | realizations | last step | advanced time
-    std::vector<double> out((size_t)N*(ny+5));
+    // out per instance: advanced q, u | steps taken | steps attempted | realizations | last step | advanced time | q projections
+    std::vector<double> out((size_t)N*(ny+6));
     for (int k = 0; k < N; ++k) {
         State s = rs.defaultState;
         setQU(s, &in[(size_t)k*ny], nq, &in[(size_t)k*ny+nq], nu);
         RungeKuttaMersonIntegrator integ(rs.system);
         if (accuracy > 0) integ.setAccuracy(accuracy);
         if (!allowInterpolation) integ.setAllowInterpolation(false);
+        applyOpts(integ, opts);
         TimeStepper ts(rs.system, integ);
         ts.initialize(s);
         ts.stepTo(tFinal);
         const State& a = integ.getAdvancedState();
-        double* o = &out[(size_t)k*(ny+5)];
+        double* o = &out[(size_t)k*(ny+6)];
         for (int i = 0; i < nq; ++i) *o++ = a.getQ()[i];
         for (int i = 0; i < nu; ++i) *o++ = a.getU()[i];
         *o++ = integ.getNumStepsTaken(); *o++ = integ.getNumStepsAttempted();
         *o++ = integ.getNumRealizations(); *o++ = integ.getPreviousStepSizeTaken(); *o++ = integ.getAdvancedTime();
+        *o++ = integ.getNumQProjections();
     }
     writeDoubles(outPath, out);
     return 0;
@@ -330,13 +341,19 @@ int main(int argc, char** argv) {
         if (argc < 3) {
             std::fprintf(stderr,
                 "usage: ref_driver lower|slots <model.txt>\n"
+                "       ref_driver model <name> <n>     (prints the text of a built-in model, simbody_b200/host/model_spec.h)\n"
                 "       ref_driver eval|energy <model.txt> <in.bin> <out.bin> <N>\n"
-                "       ref_driver step <model.txt> <in.bin> <out.bin> <N> <h> <nsteps> [accuracy]\n"
-                "       ref_driver adaptive <model.txt> <in.bin> <out.bin> <N> <tFinal> [accuracy] [allowInterpolation]\n"
+                "       ref_driver step <model.txt> <in.bin> <out.bin> <N> <h> <nsteps> [accuracy] [consTol] [infNorm] [projectEveryStep]\n"
+                "       ref_driver adaptive <model.txt> <in.bin> <out.bin> <N> <tFinal> [accuracy] [allowInterpolation] [consTol] [infNorm] [projectEveryStep]\n"
                 "       ref_driver bench <model.txt> <in.bin> <N> <h> <nsteps> <threads> [out.bin]\n");
             return 2;
         }
         const std::string cmd = argv[1];
+        if (cmd == "model") {       // the built-in model texts, so that a caller needs no other library to obtain them
+            if (argc < 4) return 2;
+            std::fputs(sbk::toText(sbk::makeNamedModel(argv[2], std::atoi(argv[3]))).c_str(), stdout);
+            return 0;
+        }
         const sbk::ModelSpec spec = sbk::fromText(slurp(argv[2]));
         if (cmd == "bench") {
             if (argc < 8) return 2;
@@ -363,12 +380,14 @@ int main(int argc, char** argv) {
         if (cmd == "eval" && argc >= 6) return cmdEval(rs, argv[3], argv[4], std::atoi(argv[5]));
         if (cmd == "energy" && argc >= 6) return cmdEnergy(rs, argv[3], argv[4], std::atoi(argv[5]));
         if (cmd == "extras" && argc >= 6) return cmdExtras(rs, argv[3], argv[4], std::atoi(argv[5]));
+        auto optsFrom = [&](int first) { IntegOpts o; if (argc > first) o.consTol = std::atof(argv[first]);
+                                         if (argc > first + 1) o.infNorm = std::atoi(argv[first + 1]); if (argc > first + 2) o.projectEvery = std::atoi(argv[first + 2]); return o; };
         if (cmd == "step" && argc >= 8)
             return cmdStep(rs, argv[3], argv[4], std::atoi(argv[5]), std::atof(argv[6]), std::atoi(argv[7]),
-                           argc > 8 ? std::atof(argv[8]) : -1);
+                           argc > 8 ? std::atof(argv[8]) : -1, optsFrom(9));
         if (cmd == "adaptive" && argc >= 7)
             return cmdAdaptive(rs, argv[3], argv[4], std::atoi(argv[5]), std::atof(argv[6]), argc > 7 ? std::atof(argv[7]) : -1,
-                               argc > 8 ? std::atoi(argv[8]) != 0 : true);
+                               argc > 8 ? std::atoi(argv[8]) != 0 : true, optsFrom(9));
         std::fprintf(stderr, "ref_driver: bad command line\n");
         return 2;
     } catch (const std::exception& e) {

@@ -505,7 +505,10 @@ int oracle_step(int nb, const int* parent, const int* joint, const double* mass,
                 for (int b = 1; b < nb; ++b) if (joint[b] == BALL || joint[b] == FREE) { const double* qq = y + B[b].q0;
                     double e = sqrt(qq[0]*qq[0] + qq[1]*qq[1] + qq[2]*qq[2] + qq[3]*qq[3]) - 1.0; if (infNorm) { if (fabs(e) > acc) acc = fabs(e); } else acc += e*e; }
                 double qn = infNorm ? acc : sqrt(acc/nquat);
-                if (qn > consTol || projectEveryStep) {
+                /* AbstractIntegratorRep.cpp:165-190: beyond max(2 tol, sqrt(tol)) the step is a convergence failure: error norm = Infinity, no projection */
+                const double plim = (2*consTol > sqrt(consTol)) ? 2*consTol : sqrt(consTol);
+                if (qn > plim) en = INFINITY;
+                else if (qn > consTol || projectEveryStep) {
                     for (int b = 1; b < nb; ++b) if (joint[b] == BALL || joint[b] == FREE) { double* qq = y + B[b].q0; double* ee = er + B[b].q0;
                         double n = sqrt(qq[0]*qq[0] + qq[1]*qq[1] + qq[2]*qq[2] + qq[3]*qq[3]), dt = 0;
                         for (int i = 0; i < 4; ++i) { qq[i] = qq[i]/n; dt += ee[i]*qq[i]; }

@@ -99,19 +99,19 @@ SBK_HD double fusedRkmAttempt(const E& e, double* y0, double* f0, double* y, con
                 const double y1 = y0[i] + (h/6)*(f0[i] + 4*fb[i] + ft[i]);
                 y[i] = y1;
                 const double err = 0.2*fabs(y1 - ys[i]);
-                if (i < NQ) { if (useInfNorm) qAcc = fmax(qAcc, fabs(err)); else qAcc += err*err; }
+                if (i < NQ) qAcc = normAcc(qAcc, err, useInfNorm);
                 else {
                     const double a0 = fabs(y0[i]);
                     const double sc = (a0*1.0 > 1.0) ? 1.0/a0 : 1.0;
                     const double v = sc*err;
-                    if (useInfNorm) uAcc = fmax(uAcc, fabs(v)); else uAcc += v*v;
+                    uAcc = normAcc(uAcc, v, useInfNorm);
                 }
             }
         }
     }
     const double qNorm = useInfNorm ? qAcc : sqrt(qAcc/NQ);
     const double uNorm = useInfNorm ? uAcc : sqrt(uAcc/NU);
-    return qNorm >= uNorm ? qNorm : uNorm;
+    return normMax(uNorm, qNorm);
 }
 // One fixed-size step.
 template <class E>

@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(128) fusedRkmKernel(const KArgs a) {
 #pragma unroll
     for (int i = 0; i < E::NY; ++i) a.y[(long long)i*a.N + inst] = y[i];
     a.errNorm[inst] = err;
-    if (a.status && !(err == err)) a.status[inst] |= 1;
+    if (a.status && !finiteNorm(err)) a.status[inst] |= 1;
 }
 template <class E>
 cudaError_t launchFusedT(const KArgs& a, bool adaptive, cudaStream_t stream) {
@@ -68,12 +68,12 @@ cudaError_t launchFusedT(const KArgs& a, bool adaptive, cudaStream_t stream) {
 constexpr int LP_THREADS = 256;
 
 __device__ __forceinline__ double blockReduce(double v, bool isMax, double* red) {
-    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, v, o); v = isMax ? fmax(v, t) : v + t; }
+    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, v, o); v = isMax ? normMax(v, t) : v + t; }
     __syncthreads();
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
     double r = isMax ? 0.0 : 0.0;
-    for (int w = 0; w < LP_THREADS/32; ++w) r = isMax ? fmax(r, red[w]) : r + red[w];
+    for (int w = 0; w < LP_THREADS/32; ++w) r = isMax ? normMax(r, red[w]) : r + red[w];
     return r;
 }
 
@@ -105,7 +105,7 @@ __device__ double lpErrorNorm(const Ctx& c, const int inst, const KArgs& a, doub
         const double u0 = fabs(ldS<false>(c, inst, a.y0, nq + i));
         const double sc = (u0*1.0 > 1.0) ? 1.0/u0 : 1.0;
         const double v = sc*ldS<false>(c, inst, a.ys, nq + i);
-        if (inf) uAcc = fmax(uAcc, fabs(v)); else uAcc += v*v;
+        uAcc = normAcc(uAcc, v, inf);
     }
     for (int b = 1 + threadIdx.x; b < c.nb; b += LP_THREADS) {
         const BodyConst& bc = c.bodies[b];
@@ -115,15 +115,15 @@ __device__ double lpErrorNorm(const Ctx& c, const int inst, const KArgs& a, doub
             for (int i = 0; i < 4; ++i) { q[i] = ldS<false>(c, inst, a.y, bc.q0 + i); e[i] = ldS<false>(c, inst, a.ys, bc.q0 + i); }
             const V3 du = quatNInvTimes(q, e);
             quatNTimes(q, du, o);
-            for (int i = 0; i < 4; ++i) { if (inf) qAcc = fmax(qAcc, fabs(o[i])); else qAcc += o[i]*o[i]; }
+            for (int i = 0; i < 4; ++i) qAcc = normAcc(qAcc, o[i], inf);
             first = 4;
         }
         const int nqb = nqOfJoint(bc.joint);
-        for (int i = first; i < nqb; ++i) { const double v = ldS<false>(c, inst, a.ys, bc.q0 + i); if (inf) qAcc = fmax(qAcc, fabs(v)); else qAcc += v*v; }
+        for (int i = first; i < nqb; ++i) qAcc = normAcc(qAcc, ldS<false>(c, inst, a.ys, bc.q0 + i), inf);
     }
     uAcc = blockReduce(uAcc, inf, red); qAcc = blockReduce(qAcc, inf, red);
     const double qNorm = inf ? qAcc : (nq ? sqrt(qAcc/nq) : 0.0), uNorm = inf ? uAcc : (nu ? sqrt(uAcc/nu) : 0.0);
-    return qNorm >= uNorm ? qNorm : uNorm;
+    return normMax(uNorm, qNorm);
 }
 
 template <int OP>
@@ -188,11 +188,12 @@ __global__ void __launch_bounds__(LP_THREADS, 2) lpKernel(const KArgs a) {
                     if (bc.joint != JT_BALL && bc.joint != JT_FREE) continue;
                     double n2 = 0; for (int i = 0; i < 4; ++i) { const double qi = ldS<false>(c, inst, a.y, bc.q0 + i); n2 += qi*qi; }
                     const double e = sqrt(n2) - 1.0;
-                    if (inf) acc = fmax(acc, fabs(e)); else acc += e*e;
+                    acc = normAcc(acc, e, inf);
                 }
                 acc = blockReduce(acc, inf, red);
                 const double quatNorm = inf ? acc : sqrt(acc/c.nquat);
-                if (quatNorm > a.consTol || a.projectEveryStep) {
+                if (quatNorm > projectionLimit(a.consTol)) err = CUDART_INF;      // convergence failure (AbstractIntegratorRep.cpp:165-190)
+                else if (quatNorm > a.consTol || a.projectEveryStep) {
                     for (int b = 1 + threadIdx.x; b < c.nb; b += LP_THREADS) {
                         const BodyConst& bc = c.bodies[b];
                         if (bc.joint != JT_BALL && bc.joint != JT_FREE) continue;
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(LP_THREADS, 2) lpKernel(const KArgs a) {
         }
         if (threadIdx.x == 0) {
             a.tcur[inst] += a.nsteps*a.h; a.errNorm[inst] = err; a.projCount[inst] += nproj;
-            if (a.status && !(err == err)) a.status[inst] |= 1;
+            if (a.status && !finiteNorm(err)) a.status[inst] |= 1;
         }
     }
 }
@@ -253,7 +254,7 @@ template <class F> __device__ __forceinline__ void glLevel(const LpLevels& L, in
     }
 }
 __device__ __forceinline__ double warpReduce(double v, bool isMax) {
-    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, v, o); v = isMax ? fmax(v, t) : v + t; }
+    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, v, o); v = isMax ? normMax(v, t) : v + t; }
     return v;
 }
 // IntegratorRep::calcErrorNorm for one instance by one warp (lanes over slots / bodies), cf. lpErrorNorm
@@ -264,7 +265,7 @@ __device__ double glErrorNorm(const Ctx& c, const int inst, const KArgs& a) {
         const double u0 = fabs(ldS<false>(c, inst, a.y0, nq + i));
         const double sc = (u0*1.0 > 1.0) ? 1.0/u0 : 1.0;
         const double v = sc*ldS<false>(c, inst, a.ys, nq + i);
-        if (inf) uAcc = fmax(uAcc, fabs(v)); else uAcc += v*v;
+        uAcc = normAcc(uAcc, v, inf);
     }
     for (int b = 1 + lane; b < c.nb; b += 32) {
         const BodyConst& bc = c.bodies[b];
@@ -274,15 +275,15 @@ __device__ double glErrorNorm(const Ctx& c, const int inst, const KArgs& a) {
             for (int i = 0; i < 4; ++i) { q[i] = ldS<false>(c, inst, a.y, bc.q0 + i); e[i] = ldS<false>(c, inst, a.ys, bc.q0 + i); }
             const V3 du = quatNInvTimes(q, e);
             quatNTimes(q, du, o);
-            for (int i = 0; i < 4; ++i) { if (inf) qAcc = fmax(qAcc, fabs(o[i])); else qAcc += o[i]*o[i]; }
+            for (int i = 0; i < 4; ++i) qAcc = normAcc(qAcc, o[i], inf);
             first = 4;
         }
         const int nqb = nqOfJoint(bc.joint);
-        for (int i = first; i < nqb; ++i) { const double v = ldS<false>(c, inst, a.ys, bc.q0 + i); if (inf) qAcc = fmax(qAcc, fabs(v)); else qAcc += v*v; }
+        for (int i = first; i < nqb; ++i) qAcc = normAcc(qAcc, ldS<false>(c, inst, a.ys, bc.q0 + i), inf);
     }
     uAcc = warpReduce(uAcc, inf); qAcc = warpReduce(qAcc, inf);
     const double qNorm = inf ? qAcc : (nq ? sqrt(qAcc/nq) : 0.0), uNorm = inf ? uAcc : (nu ? sqrt(uAcc/nu) : 0.0);
-    return qNorm >= uNorm ? qNorm : uNorm;
+    return normMax(uNorm, qNorm);
 }
 
 #ifndef SBK_GL_MINB
@@ -333,11 +334,12 @@ __global__ void __launch_bounds__(GL_THREADS, SBK_GL_MINB) glRkmKernel(const KAr
                         if (bc.joint != JT_BALL && bc.joint != JT_FREE) continue;
                         double n2 = 0; for (int i = 0; i < 4; ++i) { const double qi = ldS<false>(c, inst, a.y, bc.q0 + i); n2 += qi*qi; }
                         const double e = sqrt(n2) - 1.0;
-                        if (inf) acc = fmax(acc, fabs(e)); else acc += e*e;
+                        acc = normAcc(acc, e, inf);
                     }
                     acc = warpReduce(acc, inf);
                     const double quatNorm = inf ? acc : sqrt(acc/c.nquat);
-                    if (quatNorm > a.consTol || a.projectEveryStep) {
+                    if (quatNorm > projectionLimit(a.consTol)) err = CUDART_INF;
+                    else if (quatNorm > a.consTol || a.projectEveryStep) {
                         for (int b = 1 + lane; b < c.nb; b += 32) {
                             const BodyConst& bc = c.bodies[b];
                             if (bc.joint != JT_BALL && bc.joint != JT_FREE) continue;
@@ -354,7 +356,7 @@ __global__ void __launch_bounds__(GL_THREADS, SBK_GL_MINB) glRkmKernel(const KAr
                 }
                 if (lane == 0) {
                     a.tcur[inst] += a.h; a.errNorm[inst] = err; a.projCount[inst] += proj;
-                    if (a.status && !(err == err)) a.status[inst] |= 1;
+                    if (a.status && !finiteNorm(err)) a.status[inst] |= 1;
                 }
             }
         }

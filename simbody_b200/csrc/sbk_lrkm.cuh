@@ -26,13 +26,6 @@ struct LRkmWork {
 // then the two prefetch slots (sbk_local.cuh)
 enum { LF_V = 0, LF_A = 6, LF_V2 = 12, LF_QACC = 18, LF_UACC = 19, LF_QUATACC = 20, LF_PF = 33, LFCARRY_ROWS = LF_PF + 2*LPF_ROWS };
 
-// NaN / Inf must survive an Inf-norm accumulation (fmax drops NaN): IntegratorRep.h:454-488 + adjustStepSize's
-// isFinite test need a non-finite norm to come out non-finite.
-SBK_HD double normAcc(const double acc, const double v, const int useInf) {
-    const double t = useInf ? fabs(v) : v*v;
-    return useInf ? ((t > acc || t != t) ? t : acc) : acc + t;
-}
-
 // Stage combination as data (RungeKuttaMersonIntegrator.cpp:86-140): the next stage state is
 //   y0 + hk * (((a0*f0 + m2*f2) + m3*f3) + mf*f)      f = this evaluation's derivative
 // which evaluates to the reference's expressions term by term (absent terms contribute an exact 0).
@@ -301,12 +294,13 @@ SBK_HD RkmStepResult lRkmAttempt(const Ctx& c, const LTables& T, const int inst,
     const double qAcc = cy[LF_QACC*SBK_CARRY_STRIDE], uAcc = cy[LF_UACC*SBK_CARRY_STRIDE];
     const double uNorm = w.useInfNorm ? uAcc : (nu ? sqrt(uAcc/nu) : 0.0);
     double qNorm = w.useInfNorm ? qAcc : (nq ? sqrt(qAcc/nq) : 0.0);
-    res.errNorm = (qNorm >= uNorm || qNorm != qNorm) ? qNorm : uNorm;
+    res.errNorm = normMax(uNorm, qNorm);
     // attemptDAEStep: project only if errNorm <= 2^4 * accuracy (AbstractIntegratorRep.cpp:165-166)
     if (c.nquat > 0 && !(res.errNorm > 16.0*w.accuracy)) {
         const double acc = cy[LF_QUATACC*SBK_CARRY_STRIDE];
         const double quatNorm = w.useInfNorm ? acc : sqrt(acc/c.nquat);
-        if (quatNorm > w.consTol || w.projectEveryStep) {
+        if (quatNorm > projectionLimit(w.consTol)) res.errNorm = 1.0/0.0;      // convergence failure: too far off the manifold to project
+        else if (quatNorm > w.consTol || w.projectEveryStep) {
             for (int b = 1; b < c.nb; ++b) {
                 const LBody& bc = T.bodies[b];
                 if (bc.joint != JT_BALL && bc.joint != JT_FREE) continue;
@@ -323,7 +317,7 @@ SBK_HD RkmStepResult lRkmAttempt(const Ctx& c, const LTables& T, const int inst,
             res.projected = 1;
             const double qAcc2 = lqErrAcc<BLK>(c, T, inst, w);        // the u part does not change (takeOneStep recomputes the norm, AbstractIntegratorRep.cpp:556)
             qNorm = w.useInfNorm ? qAcc2 : (nq ? sqrt(qAcc2/nq) : 0.0);
-            res.errNorm = (qNorm >= uNorm || qNorm != qNorm) ? qNorm : uNorm;
+            res.errNorm = normMax(uNorm, qNorm);
             st.velValid = false;                                       // the quaternions moved: velocity data must be redone
         }
     }

@@ -24,6 +24,19 @@ struct RkmWork {          // SoA work vectors, each [ny][N] with ny = nq + nu (q
 
 struct RkmStepResult { double errNorm; int projected; };
 
+// Error-norm accumulation (IntegratorRep.h:454-488; weightedNormRMS / normInf): sum of squares, or the largest magnitude in
+// Inf-norm mode.  A NaN must survive the Inf-norm (fmax would drop it): adjustStepSize's isFinite test (AbstractIntegratorRep.cpp:
+// 451-456) has to see a non-finite norm for a diverged instance.
+SBK_HD double normAcc(const double acc, const double v, const int useInf) {
+    const double t = useInf ? fabs(v) : v*v;
+    return useInf ? ((t > acc || t != t) ? t : acc) : acc + t;
+}
+SBK_HD double normMax(const double a, const double b) { return (b > a || b != b) ? b : a; }     // NaN-propagating max (a NaN a stays)
+SBK_HD bool finiteNorm(const double e) { return fabs(e) <= 1.7976931348623157e308; }
+// attemptDAEStep's projection limit (AbstractIntegratorRep.cpp:165-190): a constraint violation beyond max(2 tol, sqrt(tol)) is a
+// convergence failure of the step (error norm = Infinity, no projection)
+SBK_HD double projectionLimit(const double consTol) { const double r = sqrt(consTol); return 2*consTol > r ? 2*consTol : r; }
+
 // Error norm of IntegratorRep::calcErrorNorm with UWeights = 1, no z.
 // err lives in w.ys (overwritten by the caller with the error estimate), q1 = current state.
 template <bool BLK, class TBL>
@@ -36,7 +49,7 @@ SBK_HD double rkmErrorNorm(const Ctx& c, const TBL& T, const int inst, const Rkm
         const double u0 = fabs(ldS<BLK>(c, inst, w.y0, nq + i));
         const double sc = (u0*1.0 > 1.0) ? 1.0/u0 : 1.0;
         const double v  = sc*ldS<BLK>(c, inst, w.ys, nq + i);
-        if (w.useInfNorm) uAcc = fmax(uAcc, fabs(v)); else uAcc += v*v;
+        uAcc = normAcc(uAcc, v, w.useInfNorm);
     }
     // q part: dqw = N * Wu * pinv(N) * dq (scaleDQ); identity except on quaternion slots
     for (int b = 1; b < c.nb; ++b) {
@@ -49,18 +62,17 @@ SBK_HD double rkmErrorNorm(const Ctx& c, const TBL& T, const int inst, const Rkm
             const V3 du = quatNInvTimes(q, e);
             quatNTimes(q, du, o);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { if (w.useInfNorm) qAcc = fmax(qAcc, fabs(o[i])); else qAcc += o[i]*o[i]; }
+            for (int i = 0; i < 4; ++i) qAcc = normAcc(qAcc, o[i], w.useInfNorm);
             first = 4;
         }
         const int nqb = nqOfJoint(bc.joint);
         for (int i = first; i < nqb; ++i) {
-            const double v = ldS<BLK>(c, inst, w.ys, bc.q0 + i);
-            if (w.useInfNorm) qAcc = fmax(qAcc, fabs(v)); else qAcc += v*v;
+            qAcc = normAcc(qAcc, ldS<BLK>(c, inst, w.ys, bc.q0 + i), w.useInfNorm);
         }
     }
     const double qNorm = w.useInfNorm ? qAcc : (nq ? sqrt(qAcc/nq) : 0.0);
     const double uNorm = w.useInfNorm ? uAcc : (nu ? sqrt(uAcc/nu) : 0.0);
-    return qNorm >= uNorm ? qNorm : uNorm;
+    return normMax(uNorm, qNorm);
 }
 
 // AbstractIntegratorRep::adjustStepSize (AbstractIntegratorRep.cpp:448-502).  `h` is the current
@@ -164,10 +176,11 @@ SBK_HD RkmStepResult tpiRkmStep(const Ctx& c, const TBL& T, const int inst, cons
 #pragma unroll
             for (int i = 0; i < 4; ++i) { const double qi = ldS<BLK>(c, inst, w.y, bc.q0 + i); n2 += qi*qi; }
             const double e = sqrt(n2) - 1.0;
-            if (w.useInfNorm) acc = fmax(acc, fabs(e)); else acc += e*e;
+            acc = normAcc(acc, e, w.useInfNorm);
         }
         const double quatNorm = w.useInfNorm ? acc : sqrt(acc/c.nquat);
-        if (quatNorm > w.consTol || w.projectEveryStep) {
+        if (quatNorm > projectionLimit(w.consTol)) res.errNorm = 1.0/0.0;      // convergence failure: too far off the manifold to project
+        else if (quatNorm > w.consTol || w.projectEveryStep) {
             for (int b = 1; b < c.nb; ++b) {
                 const auto& bc = T.bodies[b];
                 if (bc.joint != JT_BALL && bc.joint != JT_FREE) continue;

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(TPI_THREADS, MINB) tpiKernel(const KArgs a) {
                     stateFromBlocked(c, a, inst);
                     a.errNorm[inst] = r.errNorm;
                 }
-                if (a.status && !(r.errNorm == r.errNorm)) atomicOr(a.status + inst, 1);   // NaN error norm
+                if (a.status && !finiteNorm(r.errNorm)) atomicOr(a.status + inst, 1);   // non-finite error norm
             }
             __threadfence();
             __syncthreads();

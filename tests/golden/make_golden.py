@@ -26,12 +26,17 @@ CASES = [  # name, size param, n eval states, (h, nsteps), q_scale
     ("cartesian8", 0, 6, (1e-3, 20), 0.7),       # MobilizedBody::Planar / Cylinder / Translation
     ("humanoid30", 0, 4, (1e-3, 10), 0.5),
     ("branched_tree", 100, 2, (5e-4, 4), 0.5),
+    ("branched_tree", 1000, 2, (5e-4, 2), 0.5),  # BASELINE config 5 at full size (11 levels, width 489): file branched_tree1000.npz
 ]
 
 
 def main():
     emu, ref = HostEmu(), RefDriver()
+    only = sys.argv[1:]                       # optional: fixture file stems to (re)generate
     for name, n, neval, (h, nsteps), qs in CASES:
+        stem = name + (str(n) if (name, n) == ("branched_tree", 1000) else "")
+        if only and stem not in only:
+            continue
         text = emu.model_text(name, n)
         info = ModelInfo(text)
         assert ref.lower(text) == text, "lowering must reproduce the spec for " + name
@@ -40,7 +45,7 @@ def main():
         q, u = info.random_states(neval, 2000 + len(name), q_scale=qs)
         y0 = np.concatenate([q, u], axis=1)
         yout = ref.step(info, y0, h, nsteps)
-        path = os.path.join(HERE, "%s.npz" % name)
+        path = os.path.join(HERE, "%s.npz" % stem)
         energy = ref.energy(info, ein[:, :info.nq + info.nu])      # [n, 2] kinetic, potential at the eval states
         xin = info.random_extras_input(neval, 3000 + len(name), q_scale=qs)    # reactions, J v, ~J F  (ref_driver extras)
         xout = ref.extras(info, xin)

@@ -392,3 +392,202 @@ def test_ragged_batch_sizes(n):
     assert rel_err(np.concatenate([q.T, u.T], axis=1), yref[:, :ny]) < 1e-10
     st, nbad = bm.status(); assert nbad == 0
     bm.close(); topo.close()
+
+
+# ============================================================================================================
+# Round-2 parity additions: the benched configurations at their real sizes, the projection / norm options against the
+# live reference, Integrator::initialize's projection, the per-instance status word.
+# ============================================================================================================
+def _with_env(**kw):
+    """Context manager: environment overrides read at sbk_batch_create (e.g. SBK_NOLOCAL=1 -> ground-frame integrator)."""
+    import contextlib
+
+    @contextlib.contextmanager
+    def cm():
+        old = {k: os.environ.get(k) for k in kw}
+        os.environ.update({k: str(v) for k, v in kw.items()})
+        try:
+            yield
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+    return cm()
+
+
+@pytest.mark.parametrize("plan", [1, 3, 4])
+def test_branched_tree_1000_matches_golden(plan):
+    """BASELINE config 5 at its benched size (1000 bodies, 11 levels, width 489; tables too large to stage): every operator
+    and a fixed-step RKM run against the reference's recorded outputs, through every plan that can run it."""
+    g = np.load(os.path.join(GOLDEN, "branched_tree1000.npz"))
+    info = ModelInfo(str(g["text"]))
+    assert info.nb == 1001
+    ref = info.split_eval_out(g["eval_out"])
+    got = run_eval(info, g["eval_in"], plan=plan)
+    for k in ref:
+        assert rel_err(got[k], ref[k]) < 1e-10, (plan, k, rel_err(got[k], ref[k]))
+    y0, yref = g["step_in"], g["step_out"]
+    n, ny = y0.shape[0], info.nq + info.nu
+    topo = sb.Topology(text=info.text); bm = sb.BatchedMatter(topo, n); bm.setPlan(plan); assert bm.getPlan() == plan
+    bm.setState(soa(y0[:, :info.nq]), soa(y0[:, info.nq:]), t=0.0)
+    bm.stepBy(float(g["h"]), int(g["nsteps"]))
+    q, u, t = bm.getState()
+    assert rel_err(np.concatenate([q.T, u.T], axis=1), yref[:, :ny]) < 1e-10, plan
+    assert bm.stats()["q_projections"] == int(yref[:, ny + 2].sum())      # only the forced projection of initialize()
+    bm.close(); topo.close()
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("name,n,batch,h,nsteps,qs", [("double_pendulum", 0, 1048576, 1e-3, 200, 3.0), ("pin_chain", 50, 65536, 1e-3, 10, 1.0),
+                                                      ("humanoid30", 0, 65536, 1e-3, 10, 0.5), ("branched_tree", 1000, 256, 5e-4, 2, 0.5)])
+def test_full_size_batches_match_live_reference(name, n, batch, h, nsteps, qs):
+    """The four BASELINE batches at the size and the steps-per-launch bench.py runs (several rounds of the persistent
+    task queue / the whole cooperative grid): a strided sample of 64+ instances -- first, last, spread over every
+    block round -- against the real Simbody on the same states."""
+    info = ModelInfo(sb.model_text(name, n))
+    ny = info.nq + info.nu
+    q, u = info.random_states(batch, 12345, q_scale=qs)
+    topo = sb.Topology(text=info.text); bm = sb.BatchedMatter(topo, batch)
+    bm.setState(soa(q), soa(u), t=0.0)
+    bm.stepBy(h, nsteps)
+    qg, ug, t = bm.getState()
+    st, nbad = bm.status(); assert nbad == 0
+    idx = np.unique(np.concatenate([np.linspace(0, batch - 1, 64).astype(int), [0, 1, 127, 128, batch - 129, batch - 2, batch - 1]]))
+    yref = RefDriver().step(info, np.concatenate([q[idx], u[idx]], axis=1), h, nsteps)[:, :ny]
+    got = np.concatenate([qg.T[idx], ug.T[idx]], axis=1)
+    assert rel_err(got, yref) < 1e-10, (name, rel_err(got, yref))
+    assert np.allclose(t, h * nsteps, rtol=1e-12)
+    bm.close(); topo.close()
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("variant", ["local", "ground", "plan3", "plan4"])
+def test_projection_options_match_live_reference(variant):
+    """In-step quaternion projection in a regime where it FIRES (AbstractIntegratorRep.cpp:137-208): state and the number of
+    projections (initialize()'s forced one included, Integrator.cpp:367-377) against the real Simbody, for the consTol rule,
+    setProjectEveryStep and setUseInfinityNorm; then a start from unnormalised quaternions."""
+    info = ModelInfo(sb.model_text("mixed7")); ny = info.nq + info.nu
+    nI = 48
+    q, u = info.random_states(nI, 5, q_scale=0.7)
+    y0 = np.concatenate([q, u], axis=1)
+    env = dict(SBK_NOLOCAL=1) if variant == "ground" else {}
+    plan = {"plan3": 3, "plan4": 4}.get(variant, 1)
+    fired = 0
+    cases = [(dict(), {}, 2e-2, 20), (dict(cons_tol=1e-12), dict(constraint_tol=1e-12), 2e-2, 20),
+             (dict(project_every=1), dict(project_every_step=True), 1e-2, 20),
+             (dict(inf_norm=1, cons_tol=1e-12), dict(use_infinity_norm=True, constraint_tol=1e-12), 2e-2, 20)]
+    with _with_env(**env):
+        for rkw, gkw, h, n in cases:
+            r = RefDriver().step(info, y0, h, n, **rkw)
+            topo = sb.Topology(text=info.text); bm = sb.BatchedMatter(topo, nI); bm.setPlan(plan)
+            bm.setState(soa(q), soa(u), t=0.0)
+            bm.stepBy(h, n, **gkw)
+            qg, ug, _ = bm.getState()
+            assert rel_err(np.concatenate([qg.T, ug.T], axis=1), r[:, :ny]) < 1e-10, (variant, rkw)
+            assert bm.stats()["q_projections"] == int(r[:, ny + 2].sum()), (variant, rkw, bm.stats(), r[:, ny + 2].sum())
+            fired += int(r[:, ny + 2].sum()) - nI
+            bm.close(); topo.close()
+        assert fired > 500
+        y1 = y0.copy(); y1[:, 0:4] *= 1.3; y1[:, 7:11] *= 0.8           # off the unit sphere: initialize() projects first
+        r = RefDriver().step(info, y1, 1e-2, 10)
+        topo = sb.Topology(text=info.text); bm = sb.BatchedMatter(topo, nI); bm.setPlan(plan)
+        bm.setState(soa(y1[:, :info.nq]), soa(y1[:, info.nq:]), t=0.0)
+        bm.stepBy(1e-2, 10)
+        qg, ug, _ = bm.getState()
+        assert rel_err(np.concatenate([qg.T, ug.T], axis=1), r[:, :ny]) < 1e-10, variant
+        bm.close(); topo.close()
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("name,tf,qs,kw", [("mixed7", 0.5, 0.5, dict(inf_norm=1)), ("humanoid30", 0.2, 0.4, dict(inf_norm=1)),
+                                           ("mixed7", 0.5, 0.5, dict(cons_tol=1e-9)), ("humanoid30", 0.2, 0.4, dict())])
+def test_adaptive_options_match_live_reference(name, tf, qs, kw):
+    """Error-controlled stepping with setUseInfinityNorm / a tight constraint tolerance: step and attempt counts, projection
+    counts and the state against the real Simbody (fused body-frame integrator and the ground-frame one)."""
+    info = ModelInfo(sb.model_text(name)); ny = info.nq + info.nu
+    nI = 32
+    qv, uv = info.random_states(nI, 21, q_scale=qs)
+    ref = RefDriver().adaptive(info, np.concatenate([qv, uv], axis=1), tf, allow_interpolation=False, **kw)
+    gkw = dict(use_infinity_norm=bool(kw.get("inf_norm", 0)))
+    if "cons_tol" in kw:
+        gkw["constraint_tol"] = kw["cons_tol"]
+    for env in ({}, dict(SBK_NOLOCAL=1)):
+        with _with_env(**env):
+            topo = sb.Topology(text=info.text); bm = sb.BatchedMatter(topo, nI)
+            bm.setState(soa(qv), soa(uv), t=0.0)
+            steps, att, last = bm.stepTo(tf, **gkw)
+            qq, uu, t = bm.getState()
+            same = (steps == ref[:, ny]) & (att == ref[:, ny + 1])
+            assert same.mean() > 0.9, (name, env, same.mean())
+            got = np.concatenate([qq.T, uu.T], axis=1)
+            assert rel_err(got[same], ref[same][:, :ny]) < 1e-8, (name, env)
+            if same.all():
+                assert bm.stats()["q_projections"] == int(ref[:, ny + 5].sum()), (name, env)
+                s = bm.stats()
+                assert s["steps_taken"] == int(ref[:, ny].sum()) and s["realizations"] == int(ref[:, ny].sum() + 4 * ref[:, ny + 1].sum())
+            assert np.all(t == tf)
+            bm.close(); topo.close()
+
+
+def test_adaptive_runs_in_the_auto_plan_of_wide_trees():
+    """stepTo() must work out of the box on the models the auto plan sends to plan 4 (per-instance step histories run the
+    thread-per-instance kernel on the shared record layout)."""
+    info = ModelInfo(sb.model_text("branched_tree", 200))
+    nI = 8
+    q, u = info.random_states(nI, 3, q_scale=0.4)
+    topo = sb.Topology(text=info.text); bm = sb.BatchedMatter(topo, nI); assert bm.getPlan() == 4
+    bm.setState(soa(q), soa(u), t=0.0)
+    steps, att, last = bm.stepTo(0.02)
+    qa, ua, t = bm.getState()
+    assert np.all(t == 0.02) and np.all(steps >= 1)
+    bm.close()
+    bm = sb.BatchedMatter(topo, nI); bm.setPlan(1)
+    bm.setState(soa(q), soa(u), t=0.0)
+    s1, a1, _ = bm.stepTo(0.02)
+    q1, u1, _ = bm.getState()
+    assert np.array_equal(s1, steps) and np.array_equal(a1, att) and rel_err(qa, q1) < 1e-12
+    bm.close(); topo.close()
+
+
+@pytest.mark.parametrize("variant", ["local", "ground", "plan3", "plan4", "fused2"])
+def test_status_word_flags_bad_instances_only(variant):
+    """Per-instance status word: bit 0 = non-finite error norm (a NaN state, RMS and Inf norm), bit 1 = singular joint-space
+    inertia D; healthy instances of the same batch stay 0 and finite; a new state clears the word."""
+    if variant == "fused2":
+        info = ModelInfo(sb.model_text("double_pendulum")); plan = 2
+    else:
+        info = ModelInfo(sb.model_text("mixed7")); plan = {"plan3": 3, "plan4": 4}.get(variant, 1)
+    nI = 200
+    q, u = info.random_states(nI, 9, q_scale=0.3)
+    bad = [3, 131, 199]
+    with _with_env(**(dict(SBK_NOLOCAL=1) if variant == "ground" else {})):
+        for inf in (False, True):
+            ub = u.copy(); ub[bad, 1] = np.nan
+            topo = sb.Topology(text=info.text); bm = sb.BatchedMatter(topo, nI); bm.setPlan(plan)
+            bm.setState(soa(q), soa(ub), t=0.0)
+            err = bm.stepBy(1e-3, 3, use_infinity_norm=inf, want_err_norm=True)
+            st, nbad = bm.status()
+            assert nbad == len(bad) and sorted(np.nonzero(st)[0].tolist()) == bad and np.all(st[bad] & 1), (variant, inf, np.nonzero(st)[0])
+            good = np.setdiff1d(np.arange(nI), bad)
+            assert np.all(np.isfinite(err[good])) and not np.any(np.isfinite(err[bad]))
+            qg, ug, _ = bm.getState()
+            assert np.all(np.isfinite(qg[:, good])) and np.all(np.isfinite(ug[:, good]))
+            bm.setState(soa(q), soa(u), t=0.0)                     # a new state starts a new history
+            bm.stepBy(1e-3, 1)
+            st, nbad = bm.status(); assert nbad == 0
+            bm.close(); topo.close()
+    if variant in ("local", "ground", "plan3", "plan4"):
+        # a leaf Pin body with no inertia about its own axis: D = ~H P H = 0 (RigidBodyNodeSpec.cpp:293 inverts it)
+        text = sb.model_text("double_pendulum").splitlines()
+        tok = text[5].split(); assert tok[0] == "body" and tok[1] == "2"
+        tok[8:14] = ["0"] * 6; tok[-3:] = ["0"] * 3                # unit inertia := 0 and M at the body origin (com is already there)
+        text[5] = " ".join(tok)
+        with _with_env(**(dict(SBK_NOLOCAL=1) if variant == "ground" else {})):
+            topo = sb.Topology(text="\n".join(text) + "\n"); bm = sb.BatchedMatter(topo, 40); bm.setPlan(plan if plan != 1 else 1)
+            bm.setState(np.full((2, 40), 0.3), np.zeros((2, 40)), t=0.0)
+            bm.stepBy(1e-3, 1)
+            st, nbad = bm.status()
+            assert nbad == 40 and np.all(st & 2), (variant, st[:4])
+            bm.close(); topo.close()

@@ -203,3 +203,90 @@ def test_adaptive_rkm_matches_live_reference(built, name, n, tf, qs):
     r = ref.adaptive(info, y, tf); e = emu.adaptive(info, y, tf, allow_interpolation=False)
     assert np.array_equal(r[:, ny], e[:, ny]) and np.array_equal(r[:, ny + 1], e[:, ny + 1])     # steps, attempts
     assert rel_err(e[:, :ny], r[:, :ny]) < 1e-9 and np.array_equal(r[:, ny + 4], e[:, ny + 4])
+
+
+# ---- body-frame ("local") sweeps and the fused two-sweep integrator (sbk_local.cuh, sbk_lrkm.cuh) ------------------------
+LOCAL_MODELS = ["double_pendulum", "pin_chain", "mixed7", "humanoid30", "branched_tree"]
+
+
+@pytest.mark.parametrize("name", LOCAL_MODELS)
+def test_body_frame_sweeps_match_reference_golden(built, name):
+    """udot / qdot of the body-frame recursion against the reference's recorded realize(Acceleration) outputs, and the two
+    integrators built on it (three sweeps per evaluation; fused two sweeps) against the recorded RKM run."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    info = ModelInfo(str(g["text"]))
+    ref = info.split_eval_out(g["eval_out"])
+    ny = info.nq + info.nu
+    d = HostEmu().deriv(info, g["eval_in"][:, :ny], local=1)
+    assert rel_err(d[:, :info.nq], ref["qdot"]) < 1e-13 and rel_err(d[:, info.nq:], ref["udot"]) < 1e-10, name
+    for lean in (3, 4):
+        ys = HostEmu().step(info, g["step_in"], float(g["h"]), int(g["nsteps"]), lean=lean)
+        assert rel_err(ys[:, :ny], g["step_out"][:, :ny]) < 1e-10, (name, lean)
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("name,n", [("pin_chain", 50), ("mixed7", 0), ("humanoid30", 0), ("branched_tree", 257)])
+def test_body_frame_sweeps_match_live_reference(built, name, n):
+    emu, ref = HostEmu(), RefDriver()
+    info = ModelInfo(emu.model_text(name, n))
+    inp = info.random_eval_input(8, 99, q_scale=0.6)
+    r = info.split_eval_out(ref.eval(info, inp))
+    d = emu.deriv(info, inp[:, :info.nq + info.nu], local=1)
+    assert rel_err(d[:, info.nq:], r["udot"]) < 1e-10 and rel_err(d[:, :info.nq], r["qdot"]) < 1e-13
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
+def test_projection_and_norm_options_match_live_reference(built):
+    """In-step quaternion projection (AbstractIntegratorRep.cpp:137-208): state AND projection count against the real
+    Simbody for the consTol rule, setProjectEveryStep, setUseInfinityNorm, and -- through Integrator::initialize's forced
+    projection (Integrator.cpp:367-377) -- a start from unnormalised quaternions.  Both ground-frame and fused body-frame
+    integrators, plus the C restatement."""
+    emu, ref, co = HostEmu(), RefDriver(), COracle()
+    info = ModelInfo(emu.model_text("mixed7")); ny = info.nq + info.nu
+    q, u = info.random_states(12, 5, q_scale=0.7)
+    y0 = np.concatenate([q, u], axis=1)
+    fired = 0
+    for kw, h, n in [({}, 2e-2, 20), (dict(cons_tol=1e-6), 2e-2, 20), (dict(cons_tol=1e-12), 2e-2, 20), (dict(project_every=1), 1e-2, 20),
+                     (dict(inf_norm=1, cons_tol=1e-12), 2e-2, 20)]:
+        r = ref.step(info, y0, h, n, **kw)
+        nref = r[:, ny + 2] - 1                                   # minus the forced projection of initialize()
+        fired += int(nref.sum())
+        for impl, lean in ((emu, 1), (emu, 4), (co, None)):
+            o = impl.step(info, y0, h, n, **kw) if lean is None else impl.step(info, y0, h, n, lean=lean, **kw)
+            assert rel_err(o[:, :ny], r[:, :ny]) < 1e-10, (kw, lean)
+            assert np.array_equal(o[:, ny + 1], nref), (kw, lean, o[:, ny + 1], nref)
+    assert fired > 200                                            # the regime really exercises the projection branch
+    # a start off the unit sphere: the reference normalises in initialize(); the engine does the same before its first step
+    y1 = y0.copy(); y1[:, 0:4] *= 1.3; y1[:, 7:11] *= 0.8
+    r = ref.step(info, y1, 1e-2, 10)
+    yn = y1.copy()
+    for s0 in info.quat_q0:
+        yn[:, s0:s0 + 4] /= np.linalg.norm(yn[:, s0:s0 + 4], axis=1, keepdims=True)
+    for lean in (1, 4):
+        assert rel_err(emu.step(info, yn, 1e-2, 10, lean=lean)[:, :ny], r[:, :ny]) < 1e-10
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("name,tf,qs", [("double_pendulum", 3.0, 2.0), ("mixed7", 1.0, 0.5), ("humanoid30", 0.3, 0.4)])
+def test_fused_body_frame_adaptive_matches_live_reference(built, name, tf, qs):
+    emu, ref = HostEmu(), RefDriver()
+    info = ModelInfo(emu.model_text(name, 0))
+    q, u = info.random_states(5, 3, q_scale=qs)
+    y = np.concatenate([q, u], axis=1)
+    ny = info.nq + info.nu
+    r = ref.adaptive(info, y, tf); e = emu.adaptive(info, y, tf, allow_interpolation=False, fused=2)
+    assert np.array_equal(r[:, ny], e[:, ny]) and np.array_equal(r[:, ny + 1], e[:, ny + 1])     # steps, attempts
+    assert rel_err(e[:, :ny], r[:, :ny]) < 1e-9 and np.array_equal(r[:, ny + 4], e[:, ny + 4])
+
+
+def test_non_finite_error_norm_survives_the_infinity_norm(built):
+    """A NaN state must give a non-finite error norm in Inf-norm mode too (fmax would drop the NaN and the controller would
+    accept the step and grow h): every integrator variant."""
+    emu = HostEmu()
+    info = ModelInfo(emu.model_text("mixed7")); ny = info.nq + info.nu
+    q, u = info.random_states(2, 1, q_scale=0.3)
+    y = np.concatenate([q, u], axis=1); y[0, info.nq + 3] = np.nan
+    for lean in (0, 1, 3, 4):
+        for inf in (0, 1):
+            o = emu.step(info, y, 1e-3, 2, inf_norm=inf, lean=lean)
+            assert not np.isfinite(o[0, ny]) and np.isfinite(o[1, ny]), (lean, inf, o[:, ny])
