@@ -177,6 +177,11 @@ int  sbk_synchronize(sbk_batch*);
  * all realized stages, as in the reference.                                             */
 int sbk_set_state(sbk_batch*, const double* q, const double* u, const double* t);
 int sbk_get_state(sbk_batch*, double* q, double* u, double* t);
+/* Asynchronous variants for PINNED (page-locked) host buffers: the copies are queued on the batch's stream and the call
+ * returns at once; the buffers must stay untouched until sbk_synchronize().  (State::updQ()/getQ() have no asynchronous
+ * analogue in the reference; these exist so that a set -> step -> get round trip costs one synchronisation.) */
+int sbk_set_state_async(sbk_batch*, const double* q, const double* u, const double* t);
+int sbk_get_state_async(sbk_batch*, double* q, double* u, double* t);
 int sbk_set_state_aos(sbk_batch*, const double* q /*[N][nq]*/, const double* u /*[N][nu]*/);
 int sbk_get_state_aos(sbk_batch*, double* q, double* u);
 /* Device pointers of the resident SoA state (for zero-copy plumbing, e.g. torch).       */
@@ -272,10 +277,18 @@ int sbk_rkm_adaptive(sbk_batch*, double t_final, const sbk_adaptive_opts* opts,
 /* Integrator::getNumStepsTaken / getNumRealizations / getNumQProjections
  * (Integrator.h:286-290): totals over the batch since creation.                         */
 int sbk_rkm_stats(sbk_batch*, int64_t* steps_taken, int64_t* realizations, int64_t* q_projections);
-/* Per-instance status word of the last operation: 0 ok, bit0 non-finite, bit1 singular D. */
+/* Per-instance status word, OR-accumulated over the operations since the last sbk_set_state* (which clears it):
+ *   bit 0 (1) non-finite error norm of an integrator step (NaN / Inf state, or a step whose constraint violation exceeded the
+ *             projection limit, AbstractIntegratorRep.cpp:165-190)
+ *   bit 1 (2) singular joint-space inertia D = ~H P H (RigidBodyNodeSpec.cpp:293 would divide by it)
+ *   bit 2 (4) sbk_rkm_adaptive ran out of its attempt budget before reaching t_final
+ * n_bad = number of instances with a non-zero word. */
 int sbk_get_status(sbk_batch*, int32_t* status /*[N]*/, int64_t* n_bad);
 /* Number of kernels launched by this batch since creation (for bench accounting).       */
 int64_t sbk_launch_count(const sbk_batch*);
+/* Name of the fixed-step integrator kernel the batch's plan launches, spelled like a profiler's demangled name
+ * (e.g. "tpiKernel<7, 1, 2, 1073741886>"): lets a bench line be matched with a committed ncu capture. */
+int sbk_integrator_kernel_name(const sbk_batch*, char* buf, int cap);
 /* Device time in ms of the kernels launched by the last sbk_rkm_step call, measured with
  * CUDA events on the batch's stream (0 if events disabled).                              */
 double  sbk_last_kernel_ms(const sbk_batch*);

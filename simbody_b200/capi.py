@@ -59,6 +59,9 @@ SYMBOLS = {
     "sbk_synchronize": (ctypes.c_int, [_P]),
     "sbk_set_state": (ctypes.c_int, [_P, c_double_p, c_double_p, c_double_p]),
     "sbk_get_state": (ctypes.c_int, [_P, c_double_p, c_double_p, c_double_p]),
+    "sbk_set_state_async": (ctypes.c_int, [_P, c_double_p, c_double_p, c_double_p]),
+    "sbk_get_state_async": (ctypes.c_int, [_P, c_double_p, c_double_p, c_double_p]),
+    "sbk_integrator_kernel_name": (ctypes.c_int, [_P, ctypes.c_char_p, ctypes.c_int]),
     "sbk_set_state_aos": (ctypes.c_int, [_P, c_double_p, c_double_p]),
     "sbk_get_state_aos": (ctypes.c_int, [_P, c_double_p, c_double_p]),
     "sbk_state_device_ptrs": (ctypes.c_int, [_P, ctypes.POINTER(_P), ctypes.POINTER(_P), ctypes.POINTER(_P)]),

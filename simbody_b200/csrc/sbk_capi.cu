@@ -362,6 +362,28 @@ int sbk_set_state(sbk_batch* b, const double* q, const double* u, const double* 
     stateWasSet(b);
     return SBK_OK;
 }
+// Asynchronous variants for PINNED host buffers: the copies are queued on the batch's stream and the call returns at once;
+// the caller must not touch the buffers before sbk_synchronize() (or a later synchronous call).  One synchronisation per
+// set -> step -> get round trip instead of three (several processes sharing one host serialise on those).
+int sbk_set_state_async(sbk_batch* b, const double* q, const double* u, const double* t) {
+    if (!b) return fail(SBK_ERR_ARG, "null batch");
+    if (int rc = useDevice(b)) return rc;
+    const sbk_topology* T = b->topo;
+    if (q) if (int rc = h2d(b, b->a.y, q, T->nq)) return rc;
+    if (u) if (int rc = h2d(b, b->a.y + (size_t)T->nq*b->N, u, T->nu)) return rc;
+    if (t) CUDA_TRY(cudaMemcpyAsync(b->a.tcur, t, (size_t)b->N*sizeof(double), cudaMemcpyHostToDevice, b->stream));
+    stateWasSet(b);
+    return SBK_OK;
+}
+int sbk_get_state_async(sbk_batch* b, double* q, double* u, double* t) {
+    if (!b) return fail(SBK_ERR_ARG, "null batch");
+    if (int rc = useDevice(b)) return rc;
+    const sbk_topology* T = b->topo;
+    if (q) CUDA_TRY(cudaMemcpyAsync(q, b->a.y, (size_t)T->nq*b->N*sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    if (u) CUDA_TRY(cudaMemcpyAsync(u, b->a.y + (size_t)T->nq*b->N, (size_t)T->nu*b->N*sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    if (t) CUDA_TRY(cudaMemcpyAsync(t, b->a.tcur, (size_t)b->N*sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    return SBK_OK;
+}
 int sbk_get_state(sbk_batch* b, double* q, double* u, double* t) {
     if (!b) return fail(SBK_ERR_ARG, "null batch");
     if (int rc = useDevice(b)) return rc;
@@ -735,6 +757,24 @@ int sbk_get_status(sbk_batch* b, int32_t* status, int64_t* nbad) {
     return SBK_OK;
 }
 int64_t sbk_launch_count(const sbk_batch* b) { return b ? b->launches : 0; }
+// Name of the fixed-step integrator kernel the batch's plan launches, spelled like the demangled name a profiler prints
+// (bench.py matches its live runs with the committed ncu captures by it).
+int sbk_integrator_kernel_name(const sbk_batch* b, char* buf, int cap) {
+    if (!b || !buf || cap < 1) return fail(SBK_ERR_ARG, "sbk_integrator_kernel_name: bad arguments");
+    std::string s;
+    if (b->plan == 2) s = "fusedRkmKernel";
+    else if (b->plan == 3) s = "lpKernel<7>";
+    else if (b->plan == 4) s = "glRkmKernel";
+    else {
+        const KArgs& a = b->a; const int m = a.jointMask;
+        int jm, minb = 2, stage;
+        if (a.ltables) { jm = (((m & ~JM_PIN) == 0) ? JM_PIN : JM_MOBILE5) | JM_LOCAL; minb = (a.localMinB == 3 || a.localMinB == 4) ? a.localMinB : 2; stage = a.lstageInSmem ? 1 : 0; }
+        else { jm = (m & ~JM_PIN) == 0 ? JM_PIN : (m & ~JM_LIGHT) == 0 ? JM_LIGHT : (m & ~JM_MOBILE5) == 0 ? JM_MOBILE5 : JM_ALL; stage = a.stageInSmem ? 1 : 0; }
+        s = "tpiKernel<7, " + std::to_string(stage) + ", " + std::to_string(minb) + ", " + std::to_string(jm) + ">";
+    }
+    std::snprintf(buf, (size_t)cap, "%s", s.c_str());
+    return SBK_OK;
+}
 double sbk_last_kernel_ms(const sbk_batch* b) {
     if (!b || !b->ev0 || !b->ev1) return 0;
     cudaSetDevice(b->device);

@@ -278,6 +278,11 @@ class BatchedMatter:
         self._chk(self.lib.sbk_get_status(self.handle, st.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), ctypes.byref(nbad)))
         return st, nbad.value
 
+    def integratorKernelName(self):
+        buf = ctypes.create_string_buffer(256)
+        self._chk(self.lib.sbk_integrator_kernel_name(self.handle, buf, 256))
+        return buf.value.decode()
+
     def launchCount(self):
         return int(self.lib.sbk_launch_count(self.handle))
 
