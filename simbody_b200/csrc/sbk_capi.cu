@@ -33,7 +33,8 @@ struct sbk_batch {
     cudaStream_t stream = nullptr; bool ownStream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     KArgs a;                      // device pointers + constants
-    unsigned char* dTables = nullptr; unsigned char* dLTables = nullptr;
+    unsigned char* dTables = nullptr; unsigned char* dLTables = nullptr; unsigned char* dLTablesLevel = nullptr;
+    int clusterSize = 0;          // plan 5: CTAs per cluster
     double *dOpA = nullptr, *dOpB = nullptr, *dOpF = nullptr, *dOpOut = nullptr, *dScratch = nullptr;
     size_t scratchDoubles = 0;
     int stage = ST_EMPTY; bool abiValid = false, accelValid = false;
@@ -53,7 +54,7 @@ int useDevice(const sbk_batch* b) {
     return SBK_OK;
 }
 int launch(sbk_batch* b, KernelOp op) {
-    CUDA_TRY(b->plan == 3 ? launchLp(op, b->a, b->stream) : b->plan == 4 ? launchGl(op, b->a, b->stream) : launchTpi(op, b->a, b->stream));
+    CUDA_TRY(b->plan == 3 ? launchLp(op, b->a, b->stream) : (b->plan == 4 || b->plan == 5) ? launchGl(op, b->a, b->stream) : launchTpi(op, b->a, b->stream));
     b->launches++;
     return SBK_OK;
 }
@@ -156,8 +157,13 @@ static bool fusedOk(const sbk_batch* b) {
 }
 static int autoPlan(const sbk_batch* b) {
     if (fusedOk(b)) return 2;
-    // wide tree + batch too small to fill 148 SMs with one thread per instance
-    if (b->N < 16384 && b->topo->nb >= 128 && b->topo->maxLevelWidth >= 32) return 4;
+    // wide tree + batch too small to fill 148 SMs with one thread per instance: level-parallel plans (5 = clusters on the
+    // body-frame sweeps where the model allows and the device can host a cluster, else 4 = cooperative grid)
+    if (b->N < 16384 && b->topo->nb >= 128 && b->topo->maxLevelWidth >= 32) {
+        const char* e = getenv("SBK_NOLOCAL");
+        if (b->topo->localOk && !(e && atoi(e)) && ctreeMaxClusterSize() >= 2) return 5;
+        return 4;
+    }
     return 1;
 }
 // (Re)build the batch-shared tables and the per-body cache for an execution plan.
@@ -219,6 +225,8 @@ static int configurePlan(sbk_batch* b, int plan) {
     // body-frame integrator tables (sbk_local.cuh): plans 1 / 4, models made of Pin / Slider / Universal / Ball / Free
     if (b->dLTables) cudaFree(b->dLTables);
     b->dLTables = nullptr; a.ltables = nullptr; a.ltableBytes = 0; a.lstageInSmem = 0;
+    if (b->dLTablesLevel) cudaFree(b->dLTablesLevel);
+    b->dLTablesLevel = nullptr; a.ltablesLevel = nullptr;
     { const char* e = getenv("SBK_NOLOCAL");
       if (t->localOk && plan != 3 && !(e && atoi(e))) {
         const size_t lb = pad16(t->lbodies.size()*sizeof(LBody));
@@ -237,7 +245,30 @@ static int configurePlan(sbk_batch* b, int plan) {
         a.ltables = b->dLTables; a.ltableBytes = (uint32_t)lblob.size(); a.lchildrenOff = (uint32_t)lb; a.lforcesOff = (uint32_t)(lb + childBytes);
         a.lstageInSmem = (lblob.size() <= 48*1024 && a.stageInSmem != 0) || (lblob.size() <= 48*1024 && blob.size() > 28*1024) ? 1u : 0u;
         { const char* e2 = getenv("SBK_NOSTAGE"); if (e2 && atoi(e2)) a.lstageInSmem = 0; }
+        if (plan == 5) {          // a second blob with the link flags of the cut-tree schedule + the subtree walks, and the clusters' scratch
+            b->clusterSize = ctreeMaxClusterSize();
+            { const char* e4 = getenv("SBK_CLUSTER"); if (e4 && atoi(e4) > 0) b->clusterSize = std::min(b->clusterSize, atoi(e4)); }   // tuning override
+            if (b->clusterSize < 1) return fail(SBK_ERR_CUDA, "plan 5: the device cannot host a thread-block cluster of the integrator kernel");
+            const int nwarps = b->clusterSize*8;
+            const sbk::TreeCut cut = sbk::cutTreeForWarps(*t, nwarps, 8);
+            const size_t soBytes = pad16(cut.lists.size()*sizeof(int)), ssBytes = pad16(cut.listStart.size()*sizeof(int));
+            std::vector<unsigned char> lv(lblob.size() + soBytes + ssBytes, 0);
+            std::memcpy(lv.data(), lblob.data(), lblob.size());
+            std::memcpy(lv.data(), cut.bodies.data(), cut.bodies.size()*sizeof(LBody));
+            std::memcpy(lv.data() + lblob.size(), cut.lists.data(), cut.lists.size()*sizeof(int));
+            std::memcpy(lv.data() + lblob.size() + soBytes, cut.listStart.data(), cut.listStart.size()*sizeof(int));
+            a.llistsOff = (uint32_t)lblob.size(); a.llistStartOff = (uint32_t)(lblob.size() + soBytes);
+            a.nsub = (int)cut.subStart.size() - 1; a.cutLevel = cut.cutLevel;
+            CUDA_TRY(cudaMalloc(&b->dLTablesLevel, lv.size()));
+            CUDA_TRY(cudaMemcpyAsync(b->dLTablesLevel, lv.data(), lv.size(), cudaMemcpyHostToDevice, b->stream));
+            CUDA_TRY(cudaStreamSynchronize(b->stream));
+            a.ltablesLevel = b->dLTablesLevel;
+            if (a.treeScratch) cudaFree(a.treeScratch);
+            a.treeScratch = nullptr;
+            CUDA_TRY(cudaMalloc(&a.treeScratch, ctreeScratchDoubles(n, 16)*sizeof(double)));
+        }
       } }
+    if (plan == 5 && !a.ltablesLevel) return fail(SBK_ERR_ARG, "plan 5 needs a model made of Pin / Slider / Universal / Ball / Free mobilizers (quaternion mode)");
     CUDA_TRY(cudaMalloc(&a.cache, (size_t)cacheDoubles*sizeof(double)));
     CUDA_TRY(cudaMemsetAsync(a.cache, 0, (size_t)cacheDoubles*sizeof(double), b->stream));
     CUDA_TRY(launchInitGround(a, b->stream)); b->launches++;
@@ -308,7 +339,7 @@ void sbk_batch_destroy(sbk_batch* b) {
     if (!b) return;
     cudaSetDevice(b->device);
     KArgs& a = b->a;
-    void* ptrs[] = {b->dTables, b->dLTables, a.cache, a.y, a.yb, a.ydot, a.qdotdot, a.qerr, a.y0, a.f0, a.fa, a.fb, a.ys, a.tcur, a.errNorm,
+    void* ptrs[] = {b->dTables, b->dLTables, b->dLTablesLevel, a.treeScratch, a.cache, a.y, a.yb, a.ydot, a.qdotdot, a.qerr, a.y0, a.f0, a.fa, a.fb, a.ys, a.tcur, a.errNorm,
                     b->dOpA, b->dOpB, b->dOpOut, b->dOpF, a.status, a.projCount, b->dScratch,
                     a.hcur, a.lastStep, a.stepsTaken, a.attempts, a.taskCounter, a.lflags};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -321,7 +352,8 @@ int sbk_batch_set_plan(sbk_batch* b, int plan) {
     if (!b) return fail(SBK_ERR_ARG, "null batch");
     if (int rc = useDevice(b)) return rc;
     if (plan == 0) plan = autoPlan(b);
-    if (plan < 1 || plan > 4) return fail(SBK_ERR_ARG, "sbk_batch_set_plan: plan must be 0..4");
+    if (plan < 1 || plan > 5) return fail(SBK_ERR_ARG, "sbk_batch_set_plan: plan must be 0..5");
+    if (plan == 5 && !b->topo->localOk) return fail(SBK_ERR_ARG, "sbk_batch_set_plan: plan 5 needs a model made of Pin / Slider / Universal / Ball / Free mobilizers (quaternion mode)");
     if (plan == 2 && !fusedOk(b))
         return fail(SBK_ERR_ARG, "sbk_batch_set_plan: the register-resident fused plan needs a serial chain of 1-2 Pin/Slider mobilizers");
     if (plan == b->plan) return SBK_OK;
@@ -658,6 +690,8 @@ int sbk_rkm_step(sbk_batch* b, double h, int nsteps, const sbk_rkm_opts* opts, d
             CUDA_TRY(launchFusedRkm(a, joints.data(), false, b->stream)); b->launches++;
         } else if (b->plan == 4) {
             CUDA_TRY(launchGlRkm(a, b->stream)); b->launches++;
+        } else if (b->plan == 5) {
+            CUDA_TRY(launchCtreeRkm(a, b->clusterSize, b->stream)); b->launches++;
         } else if (int rc = launch(b, OP_RKM)) return rc;
         CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
         invalidate(b);
@@ -765,6 +799,7 @@ int sbk_integrator_kernel_name(const sbk_batch* b, char* buf, int cap) {
     if (b->plan == 2) s = "fusedRkmKernel";
     else if (b->plan == 3) s = "lpKernel<7>";
     else if (b->plan == 4) s = "glRkmKernel";
+    else if (b->plan == 5) s = "ctreeRkmKernel";
     else {
         const KArgs& a = b->a; const int m = a.jointMask;
         int jm, minb = 2, stage;

@@ -14,6 +14,9 @@ struct KArgs {
     uint32_t tableBytes, childrenOff, forcesOff, stageInSmem;
     uint32_t levelOrderOff, levelStartOff; int nlevels, plan;
     // body-frame integrator path (sbk_local.cuh): [ LBody[nb] | children | forces ], null when the model has other mobilizers
+    const unsigned char* ltablesLevel;   // the same blob with level-order link flags (plan 5, sbk_ltree.cuh)
+    double* treeScratch;                 // plan 5: per-cluster partial error sums + flags
+    uint32_t llistsOff, llistStartOff; int nsub, cutLevel;    // plan 5: per-warp task lists (in the ltablesLevel blob)
     const unsigned char* ltables; uint32_t ltableBytes, lchildrenOff, lforcesOff, lstageInSmem, lfcoefOff, lpad_;
     int localMinB, jointMask;                  // localMinB: register budget variant of the body-frame integrator kernels (2, 3, 4 CTAs / SM)                      // bit JT_x set = mobilizer kind x present in the model
     long long cStride, cInstStride, cSpan;  // cache addressing: base_b + field*cStride + (inst>>cShift)*cSpan + (inst&cMask)*cInstStride
@@ -83,6 +86,10 @@ cudaError_t launchGlRkm(const KArgs& a, cudaStream_t stream);
 cudaError_t launchGl(KernelOp op, const KArgs& a, cudaStream_t stream);
 // Integrator::initialize's forced projection: normalise every quaternion of y, count one projection per instance.
 cudaError_t launchInitProject(const KArgs& a, cudaStream_t stream);
+// Plan 5 (cluster-level-parallel, sbk_ctree.cu): fixed-step integrator; CS = CTAs per cluster (one cluster per 32 instances).
+cudaError_t launchCtreeRkm(const KArgs& a, int CS, cudaStream_t stream);
+int ctreeMaxClusterSize();
+size_t ctreeScratchDoubles(int N, int CS);
 // Ground record (identity transform, zero velocity/acceleration) for every instance.
 cudaError_t launchInitGround(const KArgs& a, cudaStream_t stream);
 // dst[k*len + i] <-> src[i*N + k]

@@ -29,7 +29,7 @@
 
 namespace sbkd {
 
-// Per-body constants of the local path (batch-shared, 224 bytes; staged into shared memory).
+// Per-body constants of the local path (batch-shared, 240 bytes; staged into shared memory).
 struct LBody {
     double RT[9];           // R_T = R_MB(parent) * R_PF : rotation F(child's inboard frame) -> M(parent), row-major
     double pT[3];           // p_T = p_MB(parent) + R_MB(parent) * p_PF : origin of F in M(parent)
@@ -39,6 +39,7 @@ struct LBody {
     int joint, parent, q0, u0;
     int flags, nchild, childStart, nforce;
     int forceStart, rec, parentLink, pad_;  // rec: first row of this body's scratch record; parentLink: first of the parent's V | A rows
+    int childIA[4];         // first row of the P+ / z+ hand-over rows (IA) of the first four children (-1: none); further children through the tables
 };
 enum { BF_NO_RT = 32 };     // R_T is exactly the identity
 
@@ -610,8 +611,10 @@ SBK_BODY void lInwardBody(const Ctx& c, const LTables& T, const LBody& bc, const
     ABI P = labiRigid(bc); SV z = zeroSV();
     if (haveCarryChild) { ABI cP; SV cz; lcyLoadIA(cy, cP, cz); addInto(P, cP); z = z + cz; }
     for (int j = haveCarryChild ? 1 : 0; j < bc.nchild; ++j) {
-        const LBody& cb = T.bodies[T.children[bc.childStart + j]];
-        const CacheRefT<BLK> ch = lrecOf<BLK>(c, inst, cb.rec + lrIA(dofOfJoint(cb.joint)));
+        int row;
+        if (j < 4) row = bc.childIA[j];
+        else { const LBody& cb = T.bodies[T.children[bc.childStart + j]]; row = cb.rec + lrIA(dofOfJoint(cb.joint)); }
+        const CacheRefT<BLK> ch = lrecOf<BLK>(c, inst, row);
         addInto(P, ch.ldABI(0)); z = z + ch.ldSV(21);
     }
     const SV pA = lbias(bc, v);

@@ -264,6 +264,42 @@ SBK_HD double lqErrAcc(const Ctx& c, const LTables& T, const int inst, const LRk
     return qAcc;
 }
 
+// End of an attempt from the error sums of the last outward sweep: error norm, the projection rule of attemptDAEStep
+// (AbstractIntegratorRep.cpp:137-208), quaternion normalisation with the radial part of the error estimate removed
+// (RigidBodyNodeSpec_Ball.h:417-434) and the recomputed norm (takeOneStep, AbstractIntegratorRep.cpp:556).
+template <bool BLK>
+SBK_HD RkmStepResult lFinishAttempt(const Ctx& c, const LTables& T, const int inst, const LRkmWork& w, const double qAcc, const double uAcc, const double quatAcc) {
+    const int nq = c.nq, nu = c.nu;
+    RkmStepResult res; res.projected = 0;
+    const double uNorm = w.useInfNorm ? uAcc : (nu ? sqrt(uAcc/nu) : 0.0);
+    double qNorm = w.useInfNorm ? qAcc : (nq ? sqrt(qAcc/nq) : 0.0);
+    res.errNorm = normMax(uNorm, qNorm);
+    if (c.nquat > 0 && !(res.errNorm > 16.0*w.accuracy)) {          // project only if errNorm <= 2^4 * accuracy (:165-166)
+        const double quatNorm = w.useInfNorm ? quatAcc : sqrt(quatAcc/c.nquat);
+        if (quatNorm > projectionLimit(w.consTol)) res.errNorm = 1.0/0.0;      // convergence failure: too far off the manifold to project
+        else if (quatNorm > w.consTol || w.projectEveryStep) {
+            for (int b = 1; b < c.nb; ++b) {
+                const LBody& bc = T.bodies[b];
+                if (bc.joint != JT_BALL && bc.joint != JT_FREE) continue;
+                double q[4], e[4], n2 = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { q[i] = ldS<BLK>(c, inst, w.Ynext, bc.q0 + i); e[i] = ldS<BLK>(c, inst, w.W, bc.q0 + i); n2 += q[i]*q[i]; }
+                const double n = sqrt(n2);
+                double dt = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { q[i] = q[i]/n; dt += e[i]*q[i]; }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { stS<BLK>(c, inst, w.Ynext, bc.q0 + i, q[i]); stS<BLK>(c, inst, w.W, bc.q0 + i, e[i] - dt*q[i]); }
+            }
+            res.projected = 1;
+            const double qAcc2 = lqErrAcc<BLK>(c, T, inst, w);        // the u part does not change
+            qNorm = w.useInfNorm ? qAcc2 : (nq ? sqrt(qAcc2/nq) : 0.0);
+            res.errNorm = normMax(uNorm, qNorm);
+        }
+    }
+    return res;
+}
+
 // Per-instance state of the fused integrator that survives from one attempt to the next.
 struct LRkmState { int vb; bool velValid; };    // velocity buffer (row offset 0 / LR_VBUF) with the data of the state in Y; whether it is current
 
@@ -290,37 +326,8 @@ SBK_HD RkmStepResult lRkmAttempt(const Ctx& c, const LTables& T, const int inst,
         lFusedOutSweep<JMASK>(c, T, inst, cy, w, w.W, stage, h, vb, vb ^ LR_VBUF); vb ^= LR_VBUF;
     }
     st.vb = vb; st.velValid = true;
-    RkmStepResult res; res.projected = 0;
-    const double qAcc = cy[LF_QACC*SBK_CARRY_STRIDE], uAcc = cy[LF_UACC*SBK_CARRY_STRIDE];
-    const double uNorm = w.useInfNorm ? uAcc : (nu ? sqrt(uAcc/nu) : 0.0);
-    double qNorm = w.useInfNorm ? qAcc : (nq ? sqrt(qAcc/nq) : 0.0);
-    res.errNorm = normMax(uNorm, qNorm);
-    // attemptDAEStep: project only if errNorm <= 2^4 * accuracy (AbstractIntegratorRep.cpp:165-166)
-    if (c.nquat > 0 && !(res.errNorm > 16.0*w.accuracy)) {
-        const double acc = cy[LF_QUATACC*SBK_CARRY_STRIDE];
-        const double quatNorm = w.useInfNorm ? acc : sqrt(acc/c.nquat);
-        if (quatNorm > projectionLimit(w.consTol)) res.errNorm = 1.0/0.0;      // convergence failure: too far off the manifold to project
-        else if (quatNorm > w.consTol || w.projectEveryStep) {
-            for (int b = 1; b < c.nb; ++b) {
-                const LBody& bc = T.bodies[b];
-                if (bc.joint != JT_BALL && bc.joint != JT_FREE) continue;
-                double q[4], e[4], n2 = 0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { q[i] = ldS<BLK>(c, inst, w.Ynext, bc.q0 + i); e[i] = ldS<BLK>(c, inst, w.W, bc.q0 + i); n2 += q[i]*q[i]; }
-                const double n = sqrt(n2);
-                double dt = 0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { q[i] = q[i]/n; dt += e[i]*q[i]; }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { stS<BLK>(c, inst, w.Ynext, bc.q0 + i, q[i]); stS<BLK>(c, inst, w.W, bc.q0 + i, e[i] - dt*q[i]); }
-            }
-            res.projected = 1;
-            const double qAcc2 = lqErrAcc<BLK>(c, T, inst, w);        // the u part does not change (takeOneStep recomputes the norm, AbstractIntegratorRep.cpp:556)
-            qNorm = w.useInfNorm ? qAcc2 : (nq ? sqrt(qAcc2/nq) : 0.0);
-            res.errNorm = normMax(uNorm, qNorm);
-            st.velValid = false;                                       // the quaternions moved: velocity data must be redone
-        }
-    }
+    const RkmStepResult res = lFinishAttempt<BLK>(c, T, inst, w, cy[LF_QACC*SBK_CARRY_STRIDE], cy[LF_UACC*SBK_CARRY_STRIDE], cy[LF_QUATACC*SBK_CARRY_STRIDE]);
+    if (res.projected) st.velValid = false;                            // the quaternions moved: velocity data must be redone
     return res;
 }
 

@@ -146,8 +146,11 @@ enum { CY_A = 18, CY_SELF = 30, CY_PRE = 48, CY_GNU = 56, GNU_ROWS = SBK_GNU_ROW
 // row CY_LOOP: the body-loop counter of the sweep drivers (parked in shared memory across a body step instead of
 // a register that the compiler would spill to local memory: its reload showed up as long-scoreboard stalls)
 // rows 48..55: two coordinate preload slots; rows 56..83: two G / nu preload slots (acceleration sweep, dof <= 2)
+#ifndef SBK_CARRY_STRIDE_DEVICE_THREADS
+#define SBK_CARRY_STRIDE_DEVICE_THREADS 128      // threads per CTA of the kernels of this translation unit (sbk_ctree.cu: 256)
+#endif
 #if defined(__CUDA_ARCH__)
-#define SBK_CARRY_STRIDE 128
+#define SBK_CARRY_STRIDE SBK_CARRY_STRIDE_DEVICE_THREADS
 #else
 #define SBK_CARRY_STRIDE 1
 #endif

@@ -1,5 +1,6 @@
 // topology.cpp -- see topology.h
 #include "topology.h"
+#include "sbk_ltree.cuh"
 #include <algorithm>
 #include <cstring>
 
@@ -57,7 +58,22 @@ static void compileLocalTables(sbk_topology& t) {
         lb.rec = row; row += sbkd::lrSize(t.nuOf[b]);
     }
     for (int b = 1; b < nb; ++b) { const int p = t.lbodies[b].parent; t.lbodies[b].parentLink = t.lbodies[p].rec + sbkd::lrV(t.nuOf[p]); }
+    for (int b = 0; b < nb; ++b)
+        for (int j = 0; j < 4; ++j) {
+            const sbkd::LBody& lb = t.lbodies[b];
+            const int cidx = j < lb.nchild ? t.children[lb.childStart + j] : -1;
+            t.lbodies[b].childIA[j] = cidx < 0 ? -1 : t.lbodies[cidx].rec + sbkd::lrIA(t.nuOf[cidx]);
+        }
     t.lrows = row;
+    // level-order variant: no body finds its parent in a carry (every link through the records), every body keeps its own
+    // velocity for the inward sweep (BF_TIP), every body with children publishes v / a (BF_STORE_LINK)
+    t.lbodiesLevel = t.lbodies;
+    for (int b = 0; b < nb; ++b) {
+        int f = t.lbodiesLevel[b].flags & sbkd::BF_NO_RT;
+        if (b >= 1) f |= sbkd::BF_TIP;
+        if (t.lbodiesLevel[b].nchild > 0) f |= sbkd::BF_STORE_LINK;
+        t.lbodiesLevel[b].flags = f;
+    }
     t.lfcoef.assign((size_t)3*std::max(1, t.nu), 0.0);
     for (int b = 1; b < nb; ++b) {
         const sbkd::BodyConst& bc = t.bodies[b];
@@ -69,6 +85,62 @@ static void compileLocalTables(sbk_topology& t) {
             else c[2] -= fc.a;
         }
     }
+}
+
+TreeCut cutTreeForWarps(const sbk_topology& t, int nwarps, int topWarps) {
+    TreeCut r; r.bodies = t.lbodiesLevel; r.cutLevel = t.nlevels; r.subStart.assign(1, 0);
+    for (int l = 1; l < t.nlevels; ++l) if (t.levelStart[l + 1] - t.levelStart[l] >= nwarps) { r.cutLevel = l; break; }
+    for (int i = t.levelStart[std::min(r.cutLevel, t.nlevels - 1)]; r.cutLevel < t.nlevels && i < t.levelStart[r.cutLevel + 1]; ++i) {
+        // depth-first walk, children in list order (the first child directly follows its parent)
+        std::vector<int> stack(1, t.levelOrder[i]);
+        while (!stack.empty()) {
+            const int b = stack.back(); stack.pop_back();
+            r.subOrder.push_back(b);
+            const sbkd::LBody& lb = t.lbodies[b];
+            for (int j = lb.nchild - 1; j >= 0; --j) stack.push_back(t.children[lb.childStart + j]);
+        }
+        r.subStart.push_back((int)r.subOrder.size());
+    }
+    const int nsub = (int)r.subStart.size() - 1;
+    // link flags of the walk: parent previous / next is my first child / some child is not next
+    for (int s = 0; s < nsub; ++s)
+        for (int k = r.subStart[s]; k < r.subStart[s + 1]; ++k) {
+            const int b = r.subOrder[k]; sbkd::LBody& lb = r.bodies[b];
+            const int prev = k > r.subStart[s] ? r.subOrder[k - 1] : -1, next = k + 1 < r.subStart[s + 1] ? r.subOrder[k + 1] : -1;
+            int f = lb.flags & sbkd::BF_NO_RT;
+            if (prev >= 0 && lb.parent == prev) f |= sbkd::BF_PARENT_PREV;
+            const bool nextIsChild = next >= 0 && lb.nchild > 0 && t.children[lb.childStart] == next;
+            if (!nextIsChild) f |= sbkd::BF_TIP;
+            if (lb.nchild > (nextIsChild ? 1 : 0)) f |= sbkd::BF_STORE_LINK;
+            lb.flags = f;
+        }
+    // task lists (sbk_ltree.cuh): per warp, inward then outward
+    topWarps = std::max(1, std::min(topWarps, nwarps));
+    r.listStart.assign(2*(size_t)nwarps, 0);
+    const bool haveTop = r.cutLevel > 1, haveSub = nsub > 0;
+    for (int dir = 0; dir < 2; ++dir)
+        for (int w = 0; w < nwarps; ++w) {
+            r.listStart[(size_t)dir*nwarps + w] = (int)r.lists.size();
+            std::vector<int> sub, top;
+            for (int s = w; s < nsub; s += nwarps) {
+                if (dir) for (int k = r.subStart[s]; k < r.subStart[s + 1]; ++k) sub.push_back(r.subOrder[k]);
+                else     for (int k = r.subStart[s + 1] - 1; k >= r.subStart[s]; --k) sub.push_back(r.subOrder[k]);
+            }
+            if (w < topWarps && haveTop)
+                for (int l = dir ? 1 : r.cutLevel - 1; dir ? l < r.cutLevel : l >= 1; l += dir ? 1 : -1) {
+                    const size_t before = top.size();
+                    for (int i = t.levelStart[l] + w; i < t.levelStart[l + 1]; i += topWarps) top.push_back(t.levelOrder[i]);
+                    if (top.size() == before) top.push_back(0);            // no body of this level for this warp: barrier only
+                    top.back() |= sbkd::LT_TSYNC;
+                }
+            // the group barrier separates the two parts: inward subtrees | top, outward top | subtrees
+            auto& first = dir ? top : sub; auto& second = dir ? sub : top;
+            if (haveTop && haveSub) { if (first.empty()) first.push_back(0); first.back() |= sbkd::LT_GSYNC; }
+            r.lists.insert(r.lists.end(), first.begin(), first.end());
+            r.lists.insert(r.lists.end(), second.begin(), second.end());
+            r.lists.push_back(sbkd::LT_END); r.lists.push_back(sbkd::LT_END); r.lists.push_back(sbkd::LT_END);
+        }
+    return r;
 }
 
 void compileTopology(const ModelSpec& spec, sbk_topology& t) {

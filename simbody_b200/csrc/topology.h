@@ -25,6 +25,7 @@ struct sbk_topology {
     std::vector<int>              children;   // concatenated child lists
     std::vector<sbkd::ForceConst> forces;     // concatenated per-body mobility force lists
     std::vector<sbkd::LBody>      lbodies;    // body-frame integrator path (sbk_local.cuh); empty unless localOk
+    std::vector<sbkd::LBody>      lbodiesLevel; // the same with level-order link flags (sbk_ltree.cuh): every link through the records
     std::vector<double>           lfcoef;     // [nu][3]: tau_j = A + B*q_j + C*u_j of the lowered mobility forces (sbk_local.cuh)
     int                           lrows = 0;  // scratch rows per instance of the body-frame path
     bool                          localOk = false;   // every mobilizer is Pin / Slider / Universal / Ball / Free (quaternion mode)
@@ -38,4 +39,11 @@ struct sbk_topology {
 namespace sbk {
 // Throws std::runtime_error with a message on invalid input.
 void compileTopology(const ModelSpec& spec, sbk_topology& out);
+// Plan 5 (sbk_ltree.cuh): cut the tree at the first level at least `nwarps` bodies wide (levels above it run level-parallel, every
+// body at it roots a subtree that one warp walks depth-first).  Fills the walk order of the subtrees, their start offsets, the cut
+// level (== nlevels if the tree is never that wide: no subtrees) and the body table with the link flags of that schedule.
+// lists / listStart: the per-warp task lists of sbk_ltree.cuh (listStart[dir*nwarps + w], dir 0 inward, 1 outward); the first
+// topWarps warps also run the levels above the cut.
+struct TreeCut { int cutLevel = 0; std::vector<int> subOrder, subStart, lists, listStart; std::vector<sbkd::LBody> bodies; };
+TreeCut cutTreeForWarps(const sbk_topology& t, int nwarps, int topWarps);
 }

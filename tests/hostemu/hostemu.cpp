@@ -12,6 +12,7 @@
 #include "../../simbody_b200/csrc/topology.h"
 #include "../../simbody_b200/csrc/sbk_fused.cuh"
 #include "../../simbody_b200/csrc/sbk_lrkm.cuh"
+#include "../../simbody_b200/csrc/sbk_ltree.cuh"
 
 using namespace sbkd;
 
@@ -166,6 +167,100 @@ int emu_step(const char* text, int N, const double* in, double* out, double h, i
             return 0;
         }
         if (lean >= 3 && !t.localOk) return 5;
+        if (lean == 5) {        // the same integrator in level order (sbk_ltree.cuh), one emulated warp group: wc = 0, nw = 1 (or 3: round robin)
+            LTables LT; LT.bodies = t.lbodiesLevel.data(); LT.children = t.children.data(); LT.forces = t.forces.data(); LT.fcoef = t.lfcoef.data();
+            struct { const int* order; const int* start; int nlevels; } LV; LV.order = t.levelOrder.data(); LV.start = t.levelStart.data(); LV.nlevels = t.nlevels;
+            for (int k = 0; k < N; ++k) {
+                Ctx c = makeCtx(e, k); c.qdotdot = nullptr; c.qerr = nullptr;
+                LRkmWork lw; lw.Y = e.y.data(); lw.W = e.ys.data(); lw.F0 = e.f0.data(); lw.F2 = e.fa.data(); lw.F3 = e.fb.data(); lw.Ynext = e.y.data();
+                lw.accuracy = accuracy; lw.consTol = consTol; lw.useInfNorm = useInfNorm; lw.projectEveryStep = projectEveryStep;
+                // three emulated warps take the bodies of a level round robin, one after the other (a level's bodies are independent)
+                const int NW = 3;
+                double cyw[NW][CARRY_ROWS + LFCARRY_ROWS]; int par[NW] = {0, 0, 0};
+                lLevelGround(c, LT, k);
+                int vb = 0; bool velValid = false; RkmStepResult r; r.errNorm = 0; r.projected = 0; int nproj = 0;
+                auto nosync = []() {};
+                for (int s = 0; s < nsteps; ++s) {
+                    // run the sweeps warp by warp inside each level: emulate by calling the per-level pieces in lockstep
+                    auto sweepAll = [&](bool out, const double* S, const LStage& sg, int vr, int vw) {
+                        for (int l = out ? 1 : LV.nlevels - 1; out ? l < LV.nlevels : l >= 1; l += out ? 1 : -1) {
+                            for (int wcn = 0; wcn < NW; ++wcn) {
+                                for (int i = wcn; i < LV.start[l + 1] - LV.start[l]; i += NW) {
+                                    const LBody& bc = LT.bodies[LV.order[LV.start[l] + i]];
+                                    Ctx cc = c; cc.q = S; cc.u = S + (size_t)cc.nq*cc.sStride;
+                                    double* cy = cyw[wcn]; double* pf = cy + LF_PF;
+                                    if (out) { lPrefetchOut<JM_MOBILE5, false>(cc, bc, k, pf, lw, S, sg);
+                                               SBK_DISPATCH_LOCAL(JM_MOBILE5, bc.joint, (lFusedOutBody<JT>(cc, bc, k, cy, lw, S, sg, vr, vw, pf))); }
+                                    else { lPrefetchIn<JM_MOBILE5, false>(cc, bc, k, pf, S, vr);
+                                           SBK_DISPATCH_LOCAL(JM_MOBILE5, bc.joint, (lInwardBody<JT>(cc, LT, bc, k, cy, vr, pf))); }
+                                }
+                            }
+                        }
+                    };
+                    if (!velValid) sweepAll(true, lw.Y, lstageOf(-1, 0.0, lw), vb, vb);
+                    for (int stage = 0; stage < 5; ++stage) {
+                        const double* S = stage == 0 ? lw.Y : lw.W;
+                        if (stage == 4) for (int wcn = 0; wcn < NW; ++wcn) { cyw[wcn][LF_QACC] = 0; cyw[wcn][LF_UACC] = 0; cyw[wcn][LF_QUATACC] = 0; }
+                        sweepAll(false, S, lstageOf(stage, h, lw), vb, vb);
+                        sweepAll(true, S, lstageOf(stage, h, lw), vb, vb ^ LR_VBUF);
+                        vb ^= LR_VBUF;
+                    }
+                    double qa = 0, ua = 0, qt = 0;
+                    for (int wcn = 0; wcn < NW; ++wcn) {
+                        if (useInfNorm) { qa = normMax(qa, cyw[wcn][LF_QACC]); ua = normMax(ua, cyw[wcn][LF_UACC]); qt = normMax(qt, cyw[wcn][LF_QUATACC]); }
+                        else { qa += cyw[wcn][LF_QACC]; ua += cyw[wcn][LF_UACC]; qt += cyw[wcn][LF_QUATACC]; }
+                    }
+                    r = lFinishAttempt<false>(c, LT, k, lw, qa, ua, qt);
+                    velValid = !r.projected; nproj += r.projected;
+                }
+                (void)nosync; (void)par;
+                double* o = out + (size_t)k*(ny+2);
+                for (int i = 0; i < ny; ++i) o[i] = e.y[(size_t)i*N + k];
+                o[ny] = r.errNorm; o[ny+1] = nproj;
+            }
+            return 0;
+        }
+        if (lean == 6) {        // lListStep itself with one emulated warp: its task lists hold the subtree walks below the cut, then the top levels
+            const sbk::TreeCut cut = sbk::cutTreeForWarps(t, 1, 1);
+            const sbk::TreeCut cut4 = sbk::cutTreeForWarps(t, 4, 1);     // flags / walks of a cut at the first level >= 4 wide, still one warp
+            // one warp executing the schedule of a 4-warp cut: concatenate the four warps' subtree lists, then the top
+            std::vector<int> lin, lout;
+            { const sbk::TreeCut& q = cut4; const int nw = 4;
+              auto seg = [&](int dir, int w) { std::vector<int> v; for (int k = q.listStart[(size_t)dir*nw + w]; !(q.lists[k] & LT_END); ++k) v.push_back(q.lists[k]); return v; };
+              // inward: all subtree parts (entries before the GSYNC flag, inclusive) of every warp, then the top part of warp 0
+              std::vector<int> top_in, top_out;
+              for (int w = 0; w < nw; ++w) { std::vector<int> v = seg(0, w); size_t i = 0; bool split = false;
+                  for (; i < v.size(); ++i) { const bool gs = (v[i] & LT_GSYNC) != 0; lin.push_back(v[i] & ~(LT_GSYNC | LT_TSYNC)); if (gs) { split = true; ++i; break; } }
+                  if (w == 0) for (; i < v.size(); ++i) top_in.push_back(v[i] & ~(LT_GSYNC | LT_TSYNC));
+                  (void)split; }
+              lin.insert(lin.end(), top_in.begin(), top_in.end());
+              for (int w = 0; w < nw; ++w) { std::vector<int> v = seg(1, w); size_t i = 0;
+                  if (w == 0) { for (; i < v.size(); ++i) { const bool gs = (v[i] & LT_GSYNC) != 0; top_out.push_back(v[i] & ~(LT_GSYNC | LT_TSYNC)); if (gs) { ++i; break; } } }
+                  else { for (; i < v.size(); ++i) if (v[i] & LT_GSYNC) { ++i; break; } } 
+                  std::vector<int> rest(v.begin() + i, v.end());
+                  if (w == 0) lout.insert(lout.begin(), top_out.begin(), top_out.end());
+                  for (int x : rest) lout.push_back(x & ~(LT_GSYNC | LT_TSYNC)); }
+              for (int k = 0; k < 3; ++k) { lin.push_back(LT_END); lout.push_back(LT_END); } }
+            (void)cut;
+            LTables LT; LT.bodies = cut4.bodies.data(); LT.children = t.children.data(); LT.forces = t.forces.data(); LT.fcoef = t.lfcoef.data();
+            for (int k = 0; k < N; ++k) {
+                Ctx c = makeCtx(e, k); c.qdotdot = nullptr; c.qerr = nullptr;
+                LRkmWork lw; lw.Y = e.y.data(); lw.W = e.ys.data(); lw.F0 = e.f0.data(); lw.F2 = e.fa.data(); lw.F3 = e.fb.data(); lw.Ynext = e.y.data();
+                lw.accuracy = accuracy; lw.consTol = consTol; lw.useInfNorm = useInfNorm; lw.projectEveryStep = projectEveryStep;
+                double cy[CARRY_ROWS + LFCARRY_ROWS]; int par = 0, vb = 0; bool velValid = false; int nproj = 0;
+                LBody slots[LT_BODY_SLOTS]; LBodySlots BS; BS.slot = slots;
+                lLevelGround(c, LT, k);
+                RkmStepResult r; r.errNorm = 0; r.projected = 0;
+                for (int s = 0; s < nsteps; ++s) {
+                    r = lListStep<JM_MOBILE5>(c, LT, lin.data(), lout.data(), BS, k, true, 0, cy, lw, h, vb, velValid, 0, par, []() {}, []() {}, [](double&, double&, double&) {});
+                    velValid = !r.projected; nproj += r.projected;
+                }
+                double* o = out + (size_t)k*(ny+2);
+                for (int i = 0; i < ny; ++i) o[i] = e.y[(size_t)i*N + k];
+                o[ny] = r.errNorm; o[ny+1] = nproj;
+            }
+            return 0;
+        }
         if (lean == 4) {        // fused two-sweep integrator on the body-frame cores (sbk_lrkm.cuh); Ynext == Y (fixed step)
             LTables LT; LT.bodies = t.lbodies.data(); LT.children = t.children.data(); LT.forces = t.forces.data(); LT.fcoef = t.lfcoef.data();
             for (int k = 0; k < N; ++k) {

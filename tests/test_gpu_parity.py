@@ -235,7 +235,7 @@ def test_grid_level_parallel_plan_matches_golden(name):
 
 def test_auto_plan_selection():
     for name, n, batch, plan in [("double_pendulum", 0, 1024, 2), ("pin_chain", 50, 1024, 1), ("humanoid30", 0, 1024, 1),
-                                 ("branched_tree", 1000, 64, 4), ("branched_tree", 1000, 65536 // 64 * 16, 1)]:
+                                 ("branched_tree", 1000, 64, 5), ("branched_tree", 1000, 65536 // 64 * 16, 1)]:
         topo = sb.Topology(text=sb.model_text(name, n))
         if name == "branched_tree" and batch > 64:
             batch = 16384       # large batches of wide trees go thread-per-instance
@@ -417,7 +417,7 @@ def _with_env(**kw):
     return cm()
 
 
-@pytest.mark.parametrize("plan", [1, 3, 4])
+@pytest.mark.parametrize("plan", [1, 3, 4, 5])
 def test_branched_tree_1000_matches_golden(plan):
     """BASELINE config 5 at its benched size (1000 bodies, 11 levels, width 489; tables too large to stage): every operator
     and a fixed-step RKM run against the reference's recorded outputs, through every plan that can run it."""
@@ -463,7 +463,7 @@ def test_full_size_batches_match_live_reference(name, n, batch, h, nsteps, qs):
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
-@pytest.mark.parametrize("variant", ["local", "ground", "plan3", "plan4"])
+@pytest.mark.parametrize("variant", ["local", "ground", "plan3", "plan4", "plan5"])
 def test_projection_options_match_live_reference(variant):
     """In-step quaternion projection in a regime where it FIRES (AbstractIntegratorRep.cpp:137-208): state and the number of
     projections (initialize()'s forced one included, Integrator.cpp:367-377) against the real Simbody, for the consTol rule,
@@ -473,7 +473,7 @@ def test_projection_options_match_live_reference(variant):
     q, u = info.random_states(nI, 5, q_scale=0.7)
     y0 = np.concatenate([q, u], axis=1)
     env = dict(SBK_NOLOCAL=1) if variant == "ground" else {}
-    plan = {"plan3": 3, "plan4": 4}.get(variant, 1)
+    plan = {"plan3": 3, "plan4": 4, "plan5": 5}.get(variant, 1)
     fired = 0
     cases = [(dict(), {}, 2e-2, 20), (dict(cons_tol=1e-12), dict(constraint_tol=1e-12), 2e-2, 20),
              (dict(project_every=1), dict(project_every_step=True), 1e-2, 20),
@@ -537,7 +537,7 @@ def test_adaptive_runs_in_the_auto_plan_of_wide_trees():
     info = ModelInfo(sb.model_text("branched_tree", 200))
     nI = 8
     q, u = info.random_states(nI, 3, q_scale=0.4)
-    topo = sb.Topology(text=info.text); bm = sb.BatchedMatter(topo, nI); assert bm.getPlan() == 4
+    topo = sb.Topology(text=info.text); bm = sb.BatchedMatter(topo, nI); assert bm.getPlan() == 5
     bm.setState(soa(q), soa(u), t=0.0)
     steps, att, last = bm.stepTo(0.02)
     qa, ua, t = bm.getState()
@@ -551,14 +551,14 @@ def test_adaptive_runs_in_the_auto_plan_of_wide_trees():
     bm.close(); topo.close()
 
 
-@pytest.mark.parametrize("variant", ["local", "ground", "plan3", "plan4", "fused2"])
+@pytest.mark.parametrize("variant", ["local", "ground", "plan3", "plan4", "plan5", "fused2"])
 def test_status_word_flags_bad_instances_only(variant):
     """Per-instance status word: bit 0 = non-finite error norm (a NaN state, RMS and Inf norm), bit 1 = singular joint-space
     inertia D; healthy instances of the same batch stay 0 and finite; a new state clears the word."""
     if variant == "fused2":
         info = ModelInfo(sb.model_text("double_pendulum")); plan = 2
     else:
-        info = ModelInfo(sb.model_text("mixed7")); plan = {"plan3": 3, "plan4": 4}.get(variant, 1)
+        info = ModelInfo(sb.model_text("mixed7")); plan = {"plan3": 3, "plan4": 4, "plan5": 5}.get(variant, 1)
     nI = 200
     q, u = info.random_states(nI, 9, q_scale=0.3)
     bad = [3, 131, 199]
@@ -578,7 +578,7 @@ def test_status_word_flags_bad_instances_only(variant):
             bm.stepBy(1e-3, 1)
             st, nbad = bm.status(); assert nbad == 0
             bm.close(); topo.close()
-    if variant in ("local", "ground", "plan3", "plan4"):
+    if variant in ("local", "ground", "plan3", "plan4", "plan5"):
         # a leaf Pin body with no inertia about its own axis: D = ~H P H = 0 (RigidBodyNodeSpec.cpp:293 inverts it)
         text = sb.model_text("double_pendulum").splitlines()
         tok = text[5].split(); assert tok[0] == "body" and tok[1] == "2"
@@ -591,3 +591,38 @@ def test_status_word_flags_bad_instances_only(variant):
             st, nbad = bm.status()
             assert nbad == 40 and np.all(st & 2), (variant, st[:4])
             bm.close(); topo.close()
+
+
+@pytest.mark.parametrize("name", ["mixed7", "humanoid30", "branched_tree"])
+def test_cluster_level_parallel_plan_matches_golden(name):
+    """Plan 5 (a thread-block cluster per 32 instances, warps over the bodies of a level, cluster barriers between levels):
+    fixed-step RKM against the reference's recorded run, the API operations (grid-level sweeps on the shared records), and
+    agreement with plan 1 on a batch that is not a multiple of the warp size (several clusters, a partial last one)."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    info = ModelInfo(str(g["text"]))
+    ref = info.split_eval_out(g["eval_out"])
+    got = run_eval(info, g["eval_in"], plan=5)
+    for k in ref:
+        assert rel_err(got[k], ref[k]) < TOL, (name, k, rel_err(got[k], ref[k]))
+    y0, yref = g["step_in"], g["step_out"]
+    n, ny = y0.shape[0], info.nq + info.nu
+    topo = sb.Topology(text=info.text); bm = sb.BatchedMatter(topo, n); bm.setPlan(5); assert bm.getPlan() == 5
+    bm.setState(soa(y0[:, :info.nq]), soa(y0[:, info.nq:]), t=0.0)
+    err = bm.stepBy(float(g["h"]), int(g["nsteps"]), want_err_norm=True)
+    q, u, t = bm.getState()
+    assert np.all(np.isfinite(err)) and np.allclose(t, float(g["h"]) * int(g["nsteps"]))
+    assert rel_err(np.concatenate([q.T, u.T], axis=1), yref[:, :ny]) < 1e-10
+    bm.close()
+    nb = 300
+    qq, uu = info.random_states(nb, 31, q_scale=0.5)
+    out = {}
+    for plan in (1, 5):
+        bm = sb.BatchedMatter(topo, nb); bm.setPlan(plan)
+        bm.setState(soa(qq), soa(uu), t=0.0)
+        e = bm.stepBy(1e-3, 3, want_err_norm=True)
+        a, b, _ = bm.getState()
+        out[plan] = (a, b, e)
+        bm.close()
+    assert rel_err(out[5][0], out[1][0]) < 1e-10 and rel_err(out[5][1], out[1][1]) < 1e-10
+    assert np.allclose(out[5][2], out[1][2], rtol=1e-3, atol=1e-14)
+    topo.close()
