@@ -72,7 +72,11 @@ enum {
     SBK_FORCE_DAMPER  = 3,  /* Force::MobilityLinearDamper: body, coord, a = c           */
     SBK_FORCE_UNIFORM_GRAVITY = 4, /* Force::UniformGravity (Force.cpp:1034-1057): dir = the gravity VECTOR g in Ground, zero height 0 */
     SBK_FORCE_GLOBAL_DAMPER   = 5, /* Force::GlobalDamper (Force.cpp:996-998): f -= a*u on every mobility          */
-    SBK_FORCE_MOBILITY_CONSTANT = 6 /* Force::MobilityConstantForce (Force_MobilityConstantForce.h:45): body, coord, a = f */
+    SBK_FORCE_MOBILITY_CONSTANT = 6, /* Force::MobilityConstantForce (Force_MobilityConstantForce.h:45): body, coord, a = f */
+    SBK_FORCE_TWO_POINT_SPRING = 7, /* Force::TwoPointLinearSpring (Force.cpp:103-140): body = body1, coord = body2, a = k, b = x0,
+                                       dir = station1 (in B1), station2 (in B2); body 0 is Ground */
+    SBK_FORCE_TWO_POINT_DAMPER = 8  /* Force::TwoPointLinearDamper (Force.cpp:179-221): body = body1, coord = body2, a = damping,
+                                       dir = station1, station2 */
 };
 
 /* One mobilized body, in MobilizedBodyIndex order; entry 0 must be Ground.
@@ -96,7 +100,8 @@ typedef struct sbk_force_desc {
     int32_t pad_;
     double  a;                    /* gravity g | spring k | damper c | global damper c    */
     double  b;                    /* spring q0                                            */
-    double  dir[3];               /* gravity: unit down direction | uniform gravity: vector g */
+    double  dir[3];               /* gravity: unit down direction | uniform gravity: vector g | two-point: station on body1 */
+    double  station2[3];          /* two-point elements: station on body2 (in B2)           */
 } sbk_force_desc;
 
 /* Integrator options; mirrors Integrator::setAccuracy / setConstraintTolerance /

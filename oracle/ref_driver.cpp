@@ -95,6 +95,12 @@ struct RefSystem {
                 Force::GlobalDamper(forces, matter, f.a);
             else if (f.kind == SBK_FORCE_MOBILITY_CONSTANT)
                 Force::MobilityConstantForce(forces, matter.getMobilizedBody(MobilizedBodyIndex(f.body)), MobilizerUIndex(f.coord), f.a);
+            else if (f.kind == SBK_FORCE_TWO_POINT_SPRING)
+                Force::TwoPointLinearSpring(forces, matter.getMobilizedBody(MobilizedBodyIndex(f.body)), Vec3(f.dir[0],f.dir[1],f.dir[2]),
+                                            matter.getMobilizedBody(MobilizedBodyIndex(f.coord)), Vec3(f.station2[0],f.station2[1],f.station2[2]), f.a, f.b);
+            else if (f.kind == SBK_FORCE_TWO_POINT_DAMPER)
+                Force::TwoPointLinearDamper(forces, matter.getMobilizedBody(MobilizedBodyIndex(f.body)), Vec3(f.dir[0],f.dir[1],f.dir[2]),
+                                            matter.getMobilizedBody(MobilizedBodyIndex(f.coord)), Vec3(f.station2[0],f.station2[1],f.station2[2]), f.a);
         }
         defaultState = system.realizeTopology();
         if (spec.useEulerAngles) matter.setUseEulerAngles(defaultState, true);

@@ -36,14 +36,15 @@
 
 enum { PIN = 1, SLIDER = 2, UNIVERSAL = 3, BALL = 4, FREE = 5, WELD = 6, TRANSLATION = 7, CYLINDER = 8, PLANAR = 9, GIMBAL = 10,
        BALL_EULER = 11, FREE_EULER = 12 };   /* Ball / Free under setUseEulerAngles: x-y-z angles, last q slot unused */
-enum { F_GRAVITY = 1, F_SPRING = 2, F_DAMPER = 3, F_UNIFORM_GRAVITY = 4, F_GLOBAL_DAMPER = 5, F_MOBILITY_CONSTANT = 6 };
+enum { F_GRAVITY = 1, F_SPRING = 2, F_DAMPER = 3, F_UNIFORM_GRAVITY = 4, F_GLOBAL_DAMPER = 5, F_MOBILITY_CONSTANT = 6,
+       F_TWO_POINT_SPRING = 7, F_TWO_POINT_DAMPER = 8 };
 #define MAXD 6
 
 typedef struct {
     int nb, nf;
     const int *parent, *joint;
     const double *mass, *com, *uinertia, *X_PF, *X_BM;   /* [nb], [nb*3], [nb*6], [nb*12], [nb*12] */
-    const int *fkind, *fbody, *fcoord; const double *fa, *fb, *fdir;   /* [nf], ..., [nf*3] */
+    const int *fkind, *fbody, *fcoord; const double *fa, *fb, *fdir;   /* [nf], ..., [nf*6]: dir (3) then station2 (3) per force */
 } Model;
 
 typedef struct {   /* per-body cache, dense */
@@ -278,13 +279,29 @@ static void systemForces(const Model* M, Body* B, const double* q, const double*
     for (int k = 0; k < M->nf; ++k) {
         if (M->fkind[k] == F_GRAVITY || M->fkind[k] == F_UNIFORM_GRAVITY) {   /* Force_Gravity.cpp:532 g*d; Force.cpp:1053 the vector itself */
             const int uni = M->fkind[k] == F_UNIFORM_GRAVITY;
-            const double g[3] = {uni ? M->fdir[3*k] : M->fa[k]*M->fdir[3*k], uni ? M->fdir[3*k+1] : M->fa[k]*M->fdir[3*k+1], uni ? M->fdir[3*k+2] : M->fa[k]*M->fdir[3*k+2]};
+            const double g[3] = {uni ? M->fdir[6*k] : M->fa[k]*M->fdir[6*k], uni ? M->fdir[6*k+1] : M->fa[k]*M->fdir[6*k+1], uni ? M->fdir[6*k+2] : M->fa[k]*M->fdir[6*k+2]};
             for (int b = 1; b < M->nb; ++b) { double F[3] = {B[b].m*g[0], B[b].m*g[1], B[b].m*g[2]}, t[3]; cross(B[b].c, F, t);
                 for (int i = 0; i < 3; ++i) { B[b].Fapp[i] += t[i]; B[b].Fapp[3+i] += F[i]; } }
         } else if (M->fkind[k] == F_SPRING) { const Body* me = &B[M->fbody[k]]; fmob[me->u0 + M->fcoord[k]] += -M->fa[k]*(q[me->q0 + M->fcoord[k]] - M->fb[k]); }
         else if (M->fkind[k] == F_MOBILITY_CONSTANT) { const Body* me = &B[M->fbody[k]]; fmob[me->u0 + M->fcoord[k]] += M->fa[k]; }
         else if (M->fkind[k] == F_GLOBAL_DAMPER) { for (int i = 0; i < nu; ++i) fmob[i] -= M->fa[k]*u[i]; }   /* Force.cpp:997 */
         else if (M->fkind[k] == F_DAMPER) { const Body* me = &B[M->fbody[k]]; fmob[me->u0 + M->fcoord[k]] += -M->fa[k]*u[me->u0 + M->fcoord[k]]; }
+        else if (M->fkind[k] == F_TWO_POINT_SPRING || M->fkind[k] == F_TWO_POINT_DAMPER) {   /* Force.cpp:103-140, 179-221 */
+            Body* b1 = &B[M->fbody[k]]; Body* b2 = &B[M->fcoord[k]];
+            double s1[3], s2[3], r[3], f1[3], t1[3], t2[3];
+            matvec3(b1->R, M->fdir + 6*k, s1); matvec3(b2->R, M->fdir + 6*k + 3, s2);
+            for (int i = 0; i < 3; ++i) r[i] = (b2->p[i] + s2[i]) - (b1->p[i] + s1[i]);
+            const double d = sqrt(r[0]*r[0] + r[1]*r[1] + r[2]*r[2]);
+            if (M->fkind[k] == F_TWO_POINT_SPRING) { const double frc = M->fa[k]*(d - M->fb[k]); for (int i = 0; i < 3; ++i) f1[i] = (frc/d)*r[i]; }
+            else {
+                double w1[3], w2[3], dir[3], vr = 0;
+                cross(b1->V, s1, w1); cross(b2->V, s2, w2);
+                for (int i = 0; i < 3; ++i) { dir[i] = r[i]/d; vr += ((b2->V[3+i] + w2[i]) - (b1->V[3+i] + w1[i]))*dir[i]; }
+                for (int i = 0; i < 3; ++i) f1[i] = M->fa[k]*vr*dir[i];
+            }
+            cross(s1, f1, t1); cross(s2, f1, t2);
+            for (int i = 0; i < 3; ++i) { b1->Fapp[i] += t1[i]; b1->Fapp[3+i] += f1[i]; b2->Fapp[i] -= t2[i]; b2->Fapp[3+i] -= f1[i]; }
+        }
     }
 }
 

@@ -24,7 +24,7 @@ class BodyDesc(ctypes.Structure):
 
 class ForceDesc(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int32), ("body", ctypes.c_int32), ("coord", ctypes.c_int32), ("pad_", ctypes.c_int32),
-                ("a", ctypes.c_double), ("b", ctypes.c_double), ("dir", ctypes.c_double * 3)]
+                ("a", ctypes.c_double), ("b", ctypes.c_double), ("dir", ctypes.c_double * 3), ("station2", ctypes.c_double * 3)]
 
 
 class RkmOpts(ctypes.Structure):

@@ -151,6 +151,7 @@ int sbk_model_text(const char* name, int n, char* buf, int cap) {
 
 // ---- batch --------------------------------------------------------------------------------
 static bool fusedOk(const sbk_batch* b) {
+    if (!b->topo->twoPoint.empty()) return false;
     std::vector<int> joints(b->topo->nb);
     for (int i = 0; i < b->topo->nb; ++i) joints[i] = b->topo->bodies[i].joint;
     return b->topo->isChain && fusedPlanSupports(b->topo->nb, joints.data());
@@ -200,7 +201,12 @@ static int configurePlan(sbk_batch* b, int plan) {
     const size_t forceBytes  = pad16(t->forces.size()*sizeof(ForceConst));
     const size_t orderBytes  = pad16(order.size()*sizeof(int));
     const size_t startBytes  = pad16(t->levelStart.size()*sizeof(int));
-    std::vector<unsigned char> blob(bodiesBytes + childBytes + forceBytes + orderBytes + startBytes, 0);
+    std::vector<TwoPointConst> tps = t->twoPoint;
+    for (TwoPointConst& tp : tps) { tp.cacheBase1 = bodies[tp.body1].cacheBase; tp.cacheBase2 = bodies[tp.body2].cacheBase; }
+    const size_t tpBytes = pad16(std::max<size_t>(tps.size(), 1)*sizeof(TwoPointConst));
+    std::vector<unsigned char> blob(bodiesBytes + childBytes + forceBytes + orderBytes + startBytes + tpBytes, 0);
+    if (!tps.empty()) std::memcpy(blob.data() + bodiesBytes + childBytes + forceBytes + orderBytes + startBytes, tps.data(), tps.size()*sizeof(TwoPointConst));
+    a.tpOff = (uint32_t)(bodiesBytes + childBytes + forceBytes + orderBytes + startBytes); a.ntp = (int)tps.size();
     std::memcpy(blob.data(), bodies.data(), bodies.size()*sizeof(BodyConst));
     std::memcpy(blob.data() + bodiesBytes, t->children.data(), t->children.size()*sizeof(int));
     std::memcpy(blob.data() + bodiesBytes + childBytes, t->forces.data(), t->forces.size()*sizeof(ForceConst));
@@ -312,6 +318,7 @@ sbk_batch* sbk_batch_create(const sbk_topology* t, int n, int device, void* stre
     dalloc(&a.yb, ny*Nb);
     dalloc(&a.y0, ny*Nb); dalloc(&a.f0, ny*Nb); dalloc(&a.fa, ny*Nb); dalloc(&a.fb, ny*Nb); dalloc(&a.ys, ny*Nb);
     dalloc(&a.tcur, N); dalloc(&a.errNorm, N);
+    if (!t->twoPoint.empty()) dalloc(&a.f2, (size_t)t->nb*6*N);
     dalloc(&b->dOpA, (size_t)t->nu*N); dalloc(&b->dOpB, (size_t)t->nu*N); dalloc(&b->dOpOut, (size_t)t->nu*N); dalloc(&b->dOpF, (size_t)t->nb*6*N);
     if (ok && cudaMalloc(&a.status, N*sizeof(int)) != cudaSuccess) ok = false;
     { const size_t nblk = (N + BLK_LANES - 1)/BLK_LANES;
@@ -341,7 +348,7 @@ void sbk_batch_destroy(sbk_batch* b) {
     KArgs& a = b->a;
     void* ptrs[] = {b->dTables, b->dLTables, b->dLTablesLevel, a.treeScratch, a.cache, a.y, a.yb, a.ydot, a.qdotdot, a.qerr, a.y0, a.f0, a.fa, a.fb, a.ys, a.tcur, a.errNorm,
                     b->dOpA, b->dOpB, b->dOpOut, b->dOpF, a.status, a.projCount, b->dScratch,
-                    a.hcur, a.lastStep, a.stepsTaken, a.attempts, a.taskCounter, a.lflags};
+                    a.hcur, a.lastStep, a.stepsTaken, a.attempts, a.taskCounter, a.lflags, a.f2};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (b->ev0) cudaEventDestroy(b->ev0); if (b->ev1) cudaEventDestroy(b->ev1);
     if (b->ownStream && b->stream) cudaStreamDestroy(b->stream);
@@ -495,6 +502,8 @@ int sbk_realize_acceleration(sbk_batch* b) {
     int rc = launch(b, OP_EVAL);
     b->a.fmobOut = nullptr; b->a.FbodyOut = nullptr;
     if (rc) return rc;
+    if (b->a.ntp)      // forces a two-point element applies to Ground are part of getRigidBodyForces()[0]
+        CUDA_TRY(cudaMemcpyAsync(b->dOpF, b->a.f2, (size_t)6*b->N*sizeof(double), cudaMemcpyDeviceToDevice, b->stream));
     b->stage = ST_ACCELERATION; b->abiValid = true; b->accelValid = true; b->realizations++;
     return SBK_OK;
 }
@@ -712,6 +721,7 @@ int sbk_rkm_adaptive(sbk_batch* b, double tFinal, const sbk_adaptive_opts* opts,
     if (!b) return fail(SBK_ERR_ARG, "null batch");
     if (int rc = useDevice(b)) return rc;
     if (b->plan == 3) return fail(SBK_ERR_ARG, "sbk_rkm_adaptive: not available in plan 3 (use sbk_batch_set_plan(b, 0 or 1))");
+    if (!b->topo->twoPoint.empty()) return fail(SBK_ERR_ARG, "sbk_rkm_adaptive: not available for models with two-point force elements (fixed steps only)");
     sbk_adaptive_opts o; sbk_adaptive_default_opts(&o);
     if (opts) {
         o = *opts;

@@ -30,6 +30,7 @@ __device__ __forceinline__ void fillCtxTree(Ctx& c, const KArgs& a) {
     c.qdot = nullptr; c.udot = nullptr; c.qdotdot = nullptr; c.qerr = nullptr;
     c.fmobIn = nullptr; c.FbodyIn = nullptr; c.fmobOut = nullptr; c.FbodyOut = nullptr; c.vecIn = nullptr; c.vecOut = nullptr;
     c.status = a.status;
+    c.tp = nullptr; c.ntp = 0; c.f2 = nullptr;
 }
 
 template <int JMASK>

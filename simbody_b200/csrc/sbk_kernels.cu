@@ -93,6 +93,7 @@ template <class F> __device__ __forceinline__ void lpInward(const LpLevels& L, F
 }
 __device__ __forceinline__ void lpEval(const Ctx& c, const int inst, const LpLevels& L, double* qdotDst, double* udotDst, double* qddDst) {
     lpOutward(L, [&](int b) { kinDispatch(c, b, inst, qdotDst); });
+    if (c.ntp) { if (threadIdx.x == 0) twoPointPass(c, inst); __syncthreads(); }       // element order, one thread: deterministic sums
     lpInward(L,  [&](int b) { inwardDispatch<IN_ABI | IN_Z | IN_BIAS | IN_FORCES>(c, b, inst); });
     lpOutward(L, [&](int b) { outwardDispatch<true>(c, b, inst, udotDst, qddDst); });
 }
@@ -307,6 +308,7 @@ __global__ void __launch_bounds__(GL_THREADS, SBK_GL_MINB) glRkmKernel(const KAr
             double* qd = fdst; double* ud = fdst + uoff;
 #pragma unroll 1
             for (int l = 1; l < L.nlevels; ++l) { glLevel(L, l, N, [&](int b, int i) { kinDispatch<true>(c, b, i, qd); }); gridBarrier(bar, gridDim.x, target); }
+            if (c.ntp) { for (long long i = tid; i < N; i += nth) twoPointPass<true>(c, (int)i); gridBarrier(bar, gridDim.x, target); }
 #pragma unroll 1
             for (int l = L.nlevels - 1; l >= 1; --l) { glLevel(L, l, N, [&](int b, int i) { inwardDispatch<IN_ABI | IN_Z | IN_BIAS | IN_FORCES, true>(c, b, i); }); gridBarrier(bar, gridDim.x, target); }
 #pragma unroll 1
@@ -382,6 +384,11 @@ __global__ void __launch_bounds__(GL_THREADS, SBK_GL_MINB) glOpKernel(const KArg
         inward([&](int b, int i) { inwardDispatch<IN_ABI, true>(c, b, i); });
     } else if constexpr (OP == OP_EVAL) {
         outward([&](int b, int i) { kinDispatch<true>(c, b, i, c.qdot); });
+        if (c.ntp) {
+            const long long tid = (long long)blockIdx.x*GL_THREADS + threadIdx.x, nth = (long long)gridDim.x*GL_THREADS;
+            for (long long i = tid; i < N; i += nth) twoPointPass<true>(c, (int)i);
+            gridBarrier(bar, gridDim.x, target);
+        }
         inward([&](int b, int i) { inwardDispatch<IN_ABI | IN_Z | IN_BIAS | IN_FORCES, true>(c, b, i); });
         outward([&](int b, int i) { outwardDispatch<true, true>(c, b, i, c.udot, c.qdotdot); });
     } else if constexpr (OP == OP_CALCACC) {
@@ -501,6 +508,15 @@ __global__ void energyKernel(const KArgs a, double* ke, double* pe) {
             pot += fc.a*(dq*dq)/2;
         }
     }
+    const TwoPointConst* tp = reinterpret_cast<const TwoPointConst*>(a.tables + a.tpOff);
+    for (int e = 0; e < a.ntp; ++e) {                      // TwoPointLinearSpringImpl::calcPotentialEnergy (Force.cpp:122-137)
+        if (tp[e].kind != TP_SPRING) continue;
+        CacheRef r1, r2; r1.p = a.cache + tp[e].cacheBase1 + instOffsetK(a, k); r1.stride = a.cStride; r2.p = a.cache + tp[e].cacheBase2 + instOffsetK(a, k); r2.stride = a.cStride;
+        const V3 p1 = r1.ld3(F_XGB + 9) + mul(r1.ldM3(F_XGB), mk(tp[e].s1[0], tp[e].s1[1], tp[e].s1[2]));
+        const V3 p2 = r2.ld3(F_XGB + 9) + mul(r2.ldM3(F_XGB), mk(tp[e].s2[0], tp[e].s2[1], tp[e].s2[2]));
+        const V3 r = p2 - p1; const double stretch = sqrt(dot(r, r)) - tp[e].b;
+        pot += tp[e].a*stretch*stretch/2;
+    }
     if (ke) ke[k] = kin;
     if (pe) pe[k] = pot;
 }
@@ -530,6 +546,9 @@ __global__ void reactionKernel(const KArgs a, double* out) {
         SV FM; FM.w = FB.w - cross(pBM, FB.v); FM.v = FB.v;
         put(b, FM);
         if (bc.parent == 0) z0 = z0 + phi(me.ld3(F_L), zP);
+    }
+    if (a.ntp) {        // a two-point element may act on Ground: z[0] = -F[0] + sum Phi zPlus (RigidBodyNode_Weld.cpp:213-222)
+        z0.w = z0.w - mk(a.f2[k], a.f2[(long long)a.N + k], a.f2[2LL*a.N + k]); z0.v = z0.v - mk(a.f2[3LL*a.N + k], a.f2[4LL*a.N + k], a.f2[5LL*a.N + k]);
     }
     put(0, z0);
 }
@@ -665,6 +684,9 @@ cudaError_t launchTpi(KernelOp op, const KArgs& a, cudaStream_t stream) {
         case OP_MULMINV: return launchOp<OP_MULMINV, SBK_HEAVY_MINB, JM_ALL>(a, stream);
         case OP_RESID:   return launchOp<OP_RESID, SBK_HEAVY_MINB, JM_ALL>(a, stream);
         case OP_RKM: case OP_RKM_ADAPT: {
+            // two-point force elements need every body's ground-frame transform between the sweeps: the FULL-record grid-level
+            // integrator (same record layout) steps such models; error-controlled stepping is not available for them
+            if (a.ntp > 0) return op == OP_RKM ? launchGlRkmImpl(a, stream) : cudaErrorNotSupported;
             // integrator kernels: instantiated per set of mobilizer kinds present in the model (one translation unit each)
             const int m = a.jointMask;
             if (a.ltables) {            // body-frame sweeps

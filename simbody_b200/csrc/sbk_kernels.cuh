@@ -13,6 +13,7 @@ struct KArgs {
     const unsigned char* tables;     // device blob
     uint32_t tableBytes, childrenOff, forcesOff, stageInSmem;
     uint32_t levelOrderOff, levelStartOff; int nlevels, plan;
+    uint32_t tpOff; int ntp; double* f2;     // two-point force elements (TwoPointConst[ntp] in the tables blob) and their body forces [nb*6][N]
     // body-frame integrator path (sbk_local.cuh): [ LBody[nb] | children | forces ], null when the model has other mobilizers
     const unsigned char* ltablesLevel;   // the same blob with level-order link flags (plan 5, sbk_ltree.cuh)
     double* treeScratch;                 // plan 5: per-cluster partial error sums + flags

@@ -101,6 +101,9 @@ struct BodyConst {
     int forceStart, level, flags, pad1;
 };
 struct ForceConst { int kind; int coord; double a; double b; };
+// Force::TwoPointLinearSpring / TwoPointLinearDamper (Force.cpp:103-221): a force along the line between a station on body1 and one on body2
+enum { TP_SPRING = 7, TP_DAMPER = 8 };
+struct TwoPointConst { int kind, body1, body2, pad_; double a, b; double s1[3], s2[3]; long long cacheBase1, cacheBase2; };
 
 // Context shared by every work item of a CTA (the device keeps ONE copy in shared memory, read
 // with LDS: nothing per-thread lives in local memory).  SoA arrays are addressed
@@ -122,6 +125,8 @@ struct Ctx {
     double* fmobOut; double* FbodyOut;              // force-subsystem results (getter)
     const double* vecIn; double* vecOut;            // generic nu-vectors for M, M^-1, residual
     int* status;                                    // per-instance status words [N]
+    // two-point force elements (FULL records only): their body forces accumulate in f2 [nb*6][N] between the kinematics and the inward sweep
+    const TwoPointConst* tp; int ntp; double* f2;
 };
 
 // The batch-shared tables as the integrator kernels see them: plain local pointers derived from
@@ -751,6 +756,36 @@ SBK_BODY void kinBody(const Ctx& c, const BodyConst& bc, const int bodyIndex, co
     if constexpr (JT == JT_BALL || JT == JT_FREE) { if (c.qerr) stS<false>(c, inst, c.qerr, bc.quat, qerr); }
 }
 
+// Force::TwoPointLinearSpringImpl::calcForce / TwoPointLinearDamperImpl::calcForce (Force.cpp:103-140,179-221) for one instance from the
+// realized position / velocity records: f2 (zeroed here) receives +(s1_G x f, f) on body1 and -(s2_G x f, f) on body2, in element order.
+template <bool CB = false>
+SBK_HD void twoPointPass(const Ctx& c, const int inst) {
+    if (c.ntp == 0) return;
+    for (int i = 0; i < 6*c.nb; ++i) stS<false>(c, inst, c.f2, i, 0.0);
+    for (int e = 0; e < c.ntp; ++e) {
+        const TwoPointConst& t = c.tp[e];
+        const CacheRefT<CB> r1 = cacheOf<CB>(c, inst, t.cacheBase1), r2 = cacheOf<CB>(c, inst, t.cacheBase2);
+        const V3 s1_G = mul(r1.ldM3(F_XGB), mk(t.s1[0], t.s1[1], t.s1[2])), s2_G = mul(r2.ldM3(F_XGB), mk(t.s2[0], t.s2[1], t.s2[2]));
+        const V3 p1_G = r1.ld3(F_XGB + 9) + s1_G, p2_G = r2.ld3(F_XGB + 9) + s2_G;
+        const V3 r_G = p2_G - p1_G;
+        const double d = sqrt(dot(r_G, r_G));
+        V3 f1;
+        if (t.kind == TP_SPRING) { const double frc = t.a*(d - t.b); f1 = (frc/d)*r_G; }
+        else {      // findStationVelocityInGround: v + w x s_G; UnitVec3(r) = r / |r|
+            const SV V1 = r1.ldSV(F_VGB), V2 = r2.ldSV(F_VGB);
+            const V3 vRel = (V2.v + cross(V2.w, s2_G)) - (V1.v + cross(V1.w, s1_G));
+            const V3 dir = (1.0/d)*r_G;
+            f1 = (t.a*dot(vRel, dir))*dir;
+        }
+        const V3 m1 = cross(s1_G, f1), m2 = cross(s2_G, f1);
+        const double add1[6] = {m1.x, m1.y, m1.z, f1.x, f1.y, f1.z}, add2[6] = {m2.x, m2.y, m2.z, f1.x, f1.y, f1.z};
+        for (int i = 0; i < 6; ++i) {
+            stS<false>(c, inst, c.f2, 6*t.body1 + i, ldS<false>(c, inst, c.f2, 6*t.body1 + i) + add1[i]);
+            stS<false>(c, inst, c.f2, 6*t.body2 + i, ldS<false>(c, inst, c.f2, 6*t.body2 + i) - add2[i]);
+        }
+    }
+}
+
 // Inward body step.  MODE bits:
 //   IN_ABI    articulated-body inertia: P, D, DI, G, PPlus (+ ZB = P*a + b)
 //   IN_Z      residual pass: z, eps, zPlus
@@ -811,6 +846,10 @@ SBK_BODY void inwardBody(const Ctx& c, const BodyConst& bc, const int bodyIndex,
                 for (int i = 0; i < d; ++i)  uF[i] = ldS<false>(c, inst, c.u, bc.u0 + i);
             }
             F = gravityForce(bc.mass, c_G, c.gx, c.gy, c.gz);
+            if (c.ntp) {
+                F.w = F.w + mk(ldS<false>(c, inst, c.f2, 6*bodyIndex+0), ldS<false>(c, inst, c.f2, 6*bodyIndex+1), ldS<false>(c, inst, c.f2, 6*bodyIndex+2));
+                F.v = F.v + mk(ldS<false>(c, inst, c.f2, 6*bodyIndex+3), ldS<false>(c, inst, c.f2, 6*bodyIndex+4), ldS<false>(c, inst, c.f2, 6*bodyIndex+5));
+            }
             mobilityForces<d>(bc, c.forces, qF, uF, f);
             if (c.fmobOut) {
 #pragma unroll
@@ -1235,6 +1274,7 @@ template <bool WITH_COR, bool CB = false> SBK_HD void tpiOutward(const Ctx& c, i
 template <bool LEAN, int JMASK = JM_ALL, bool CB = false> SBK_HD void tpiEvalDerivatives(const Ctx& c, const Tables& T, int inst, double* cy, double* qdotDst, double* udotDst, double* qddDst) {
     if constexpr (!LEAN) {
         tpiKinematics<CB>(c, inst, qdotDst);
+        twoPointPass<CB>(c, inst);
         tpiInward<IN_ABI | IN_Z | IN_BIAS | IN_FORCES, CB>(c, inst);
         tpiOutward<true, CB>(c, inst, udotDst, qddDst);
     } else {

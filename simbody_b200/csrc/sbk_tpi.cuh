@@ -62,6 +62,7 @@ __device__ __forceinline__ void fillCtx(Ctx& c, const KArgs& a, const unsigned c
     c.fmobIn = a.fmobIn; c.FbodyIn = a.FbodyIn; c.fmobOut = a.fmobOut; c.FbodyOut = a.FbodyOut;
     c.vecIn = a.vecIn; c.vecOut = a.vecOut;
     c.status = a.status;
+    c.tp = reinterpret_cast<const TwoPointConst*>(tables + a.tpOff); c.ntp = a.ntp; c.f2 = a.f2;
     if (integrator) { c.qdotdot = nullptr; c.qerr = nullptr; c.fmobOut = nullptr; c.FbodyOut = nullptr; }
 }
 // Thread-per-instance integrator kernels work on a CTA-blocked copy of the state ([block][slot][lane]).

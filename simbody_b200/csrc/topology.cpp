@@ -11,7 +11,7 @@ namespace sbk {
 // properties move from (Bo, B) to (Mo, M) once, here.
 static void compileLocalTables(sbk_topology& t) {
     const int nb = t.nb;
-    t.localOk = nb > 1; t.lbodies.clear(); t.lrows = 0;
+    t.localOk = nb > 1 && t.twoPoint.empty(); t.lbodies.clear(); t.lrows = 0;     // two-point elements need ground-frame positions
     for (int b = 1; b < nb; ++b) {
         const int jt = t.bodies[b].joint;
         if (jt != sbkd::JT_PIN && jt != sbkd::JT_SLIDER && jt != sbkd::JT_UNIVERSAL && jt != sbkd::JT_BALL && jt != sbkd::JT_FREE) t.localOk = false;
@@ -183,7 +183,7 @@ void compileTopology(const ModelSpec& spec, sbk_topology& t) {
     for (int l = 0; l < t.nlevels; ++l) t.maxLevelWidth = std::max(t.maxLevelWidth, t.levelStart[l+1] - t.levelStart[l]);
 
     // forces
-    int ngrav = 0;
+    int ngrav = 0; t.twoPoint.clear();
     std::vector<std::vector<sbkd::ForceConst>> perBody(nb);
     for (size_t i = 0; i < spec.forces.size(); ++i) {
         const sbk_force_desc& f = spec.forces[i];
@@ -210,6 +210,14 @@ void compileTopology(const ModelSpec& spec, sbk_topology& t) {
                 throw std::runtime_error("topology: MobilityLinearSpring on Ball/Free is not supported (reference Force.cpp:348 mixes q/u indices)");
             sbkd::ForceConst fc; fc.kind = f.kind; fc.coord = f.coord; fc.a = f.a; fc.b = f.b;
             perBody[f.body].push_back(fc);
+        } else if (f.kind == SBK_FORCE_TWO_POINT_SPRING || f.kind == SBK_FORCE_TWO_POINT_DAMPER) {
+            // body = body1, coord = body2 (Ground allowed: Force.cpp:103-140 takes any two mobilized bodies)
+            if (f.body < 0 || f.body >= nb || f.coord < 0 || f.coord >= nb || f.body == f.coord)
+                throw std::runtime_error("topology: force " + std::to_string(i) + " needs two different valid bodies");
+            sbkd::TwoPointConst tp; std::memset(&tp, 0, sizeof tp);
+            tp.kind = f.kind; tp.body1 = f.body; tp.body2 = f.coord; tp.a = f.a; tp.b = f.b;
+            for (int k = 0; k < 3; ++k) { tp.s1[k] = f.dir[k]; tp.s2[k] = f.station2[k]; }
+            t.twoPoint.push_back(tp);
         } else throw std::runtime_error("topology: unknown force kind");
     }
 

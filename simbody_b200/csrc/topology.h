@@ -29,6 +29,7 @@ struct sbk_topology {
     std::vector<double>           lfcoef;     // [nu][3]: tau_j = A + B*q_j + C*u_j of the lowered mobility forces (sbk_local.cuh)
     int                           lrows = 0;  // scratch rows per instance of the body-frame path
     bool                          localOk = false;   // every mobilizer is Pin / Slider / Universal / Ball / Free (quaternion mode)
+    std::vector<sbkd::TwoPointConst> twoPoint; // Force::TwoPointLinearSpring / Damper elements in force-index order (cacheBase filled per plan)
     std::vector<int>              levelOrder; // body indices sorted by level (stable)
     std::vector<int>              levelStart; // nlevels+1 offsets into levelOrder
     double grav[3] = {0, 0, 0};

@@ -79,6 +79,19 @@ public:
     void realizeArticulatedBodyInertias() { throwOnError(sbk_realize_articulated_body_inertias(h_)); }
     void realizeAcceleration()            { throwOnError(sbk_realize_acceleration(h_)); }   // System::realize(s, Stage::Acceleration)
     void getUDot(std::vector<double>& udot) { udot.resize((size_t)topo_.getNU()*n_); throwOnError(sbk_get_udot(h_, udot.data())); }
+    void getQDot(std::vector<double>& qdot) { qdot.resize((size_t)topo_.getNQ()*n_); throwOnError(sbk_get_qdot(h_, qdot.data())); }
+    void getQDotDot(std::vector<double>& qdd) { qdd.resize((size_t)topo_.getNQ()*n_); throwOnError(sbk_get_qdotdot(h_, qdd.data())); }
+    // MobilizedBody::getBodyTransform / getBodyVelocity / getBodyAcceleration for every body (MobilizedBody.h:560-620):
+    // X_GB [nb][12][N] (R row-major, p), V_GB / A_GB [nb][6][N] (angular, linear), expressed in Ground
+    void getBodyTransforms(std::vector<double>& X_GB)    { X_GB.resize((size_t)12*topo_.getNumBodies()*n_); throwOnError(sbk_get_body_transforms(h_, X_GB.data())); }
+    void getBodyVelocities(std::vector<double>& V_GB)    { V_GB.resize((size_t)6*topo_.getNumBodies()*n_); throwOnError(sbk_get_body_velocities(h_, V_GB.data())); }
+    void getBodyAccelerations(std::vector<double>& A_GB) { A_GB.resize((size_t)6*topo_.getNumBodies()*n_); throwOnError(sbk_get_body_accelerations(h_, A_GB.data())); }
+    // MultibodySystem::calcKineticEnergy / calcPotentialEnergy (MultibodySystem.h:143-168), one value per instance
+    void calcEnergy(std::vector<double>& kinetic, std::vector<double>& potential) {
+        kinetic.resize((size_t)n_); potential.resize((size_t)n_); throwOnError(sbk_calc_energy(h_, kinetic.data(), potential.data()));
+    }
+    // per-instance status words (include/sbk.h: bit 0 non-finite, bit 1 singular D, bit 2 attempt budget); returns the number of bad instances
+    long long getStatus(std::vector<int32_t>& status) { status.resize((size_t)n_); int64_t bad = 0; throwOnError(sbk_get_status(h_, status.data(), &bad)); return bad; }
 
     // Zero-length force vectors mean "all zero", as in the reference (SimbodyMatterSubsystemRep.cpp:5546-5564).
     void calcAcceleration(const std::vector<double>& appliedMobilityForces, const std::vector<double>& appliedBodyForces,
@@ -128,15 +141,32 @@ private:
     const Topology& topo_; int n_; sbk_batch* h_;
 };
 
-// RungeKuttaMersonIntegrator with a fixed step for the whole batch.
+// RungeKuttaMersonIntegrator for the whole batch: fixed steps (setFixedStepSize + stepBy) or error-controlled stepping to a
+// time (stepTo; every instance keeps its own step-size history, Integrator.h:226).
 class BatchedRungeKuttaMerson {
 public:
-    explicit BatchedRungeKuttaMerson(BatchedMatter& m) : m_(m) { sbk_rkm_default_opts(&o_); }
+    explicit BatchedRungeKuttaMerson(BatchedMatter& m) : m_(m) { sbk_rkm_default_opts(&o_); sbk_adaptive_default_opts(&ao_); }
     void setFixedStepSize(double h)        { h_ = h; }
-    void setAccuracy(double acc)           { o_.accuracy = acc; if (!userTol_) o_.constraint_tol = acc/10; }   // IntegratorRep.h:737-740
-    void setConstraintTolerance(double t)  { o_.constraint_tol = t; userTol_ = true; }
-    void setUseInfinityNorm(bool b)        { o_.use_infinity_norm = b; }
-    void setProjectEveryStep(bool b)       { o_.project_every_step = b; }
+    void setAccuracy(double acc)           { o_.accuracy = ao_.accuracy = acc; if (!userTol_) o_.constraint_tol = ao_.constraint_tol = acc/10; }   // IntegratorRep.h:737-740
+    void setConstraintTolerance(double t)  { o_.constraint_tol = ao_.constraint_tol = t; userTol_ = true; }
+    void setUseInfinityNorm(bool b)        { o_.use_infinity_norm = ao_.use_infinity_norm = b; }
+    void setProjectEveryStep(bool b)       { o_.project_every_step = ao_.project_every_step = b; }
+    void setInitialStepSize(double h)      { ao_.init_step = h; }                 // Integrator.h:322
+    void setMinimumStepSize(double h)      { ao_.min_step = h; }                  // :327
+    void setMaximumStepSize(double h)      { ao_.max_step = h; }                  // :332
+    void setAllowInterpolation(bool b)     { ao_.allow_interpolation = b; }       // :357 (default here false = TimeStepper semantics)
+    // Integrator::stepTo(reportTime) with error control (Integrator.h:226): every instance advances to tFinal with its own steps
+    void stepTo(double tFinal) {
+        const size_t n = (size_t)m_.getNumInstances();
+        steps_.resize(n); attempts_.resize(n); lastStep_.resize(n);
+        throwOnError(sbk_rkm_adaptive(m_.handle(), tFinal, &ao_, steps_.data(), attempts_.data(), lastStep_.data()));
+    }
+    // per-instance counters of the error-controlled run since the last setState (Integrator.h:286-290, :262)
+    const std::vector<int32_t>& getNumStepsTakenPerInstance() const     { return steps_; }
+    const std::vector<int32_t>& getNumStepsAttemptedPerInstance() const { return attempts_; }
+    const std::vector<double>&  getPreviousStepSizeTaken() const        { return lastStep_; }
+    long long getNumStepsAttempted() const { long long s = 0; for (int32_t a : attempts_) s += a; return s; }
+    std::vector<double> getTime() { std::vector<double> t((size_t)m_.getNumInstances()); throwOnError(sbk_get_state(m_.handle(), nullptr, nullptr, t.data())); return t; }
     // nsteps accepted steps of size h for every instance; the state stays on the GPU.
     void stepBy(int nsteps) {
         if (!(h_ > 0)) throw std::logic_error("BatchedRungeKuttaMerson: call setFixedStepSize() first");
@@ -147,7 +177,8 @@ public:
     long long getNumRealizations()  { int64_t s, r, p; throwOnError(sbk_rkm_stats(m_.handle(), &s, &r, &p)); return r; }
     long long getNumQProjections()  { int64_t s, r, p; throwOnError(sbk_rkm_stats(m_.handle(), &s, &r, &p)); return p; }
 private:
-    BatchedMatter& m_; sbk_rkm_opts o_; double h_ = -1; bool userTol_ = false;
+    BatchedMatter& m_; sbk_rkm_opts o_; sbk_adaptive_opts ao_; double h_ = -1; bool userTol_ = false;
+    std::vector<int32_t> steps_, attempts_; std::vector<double> lastStep_;
 };
 
 } // namespace sbk

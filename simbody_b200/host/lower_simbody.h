@@ -162,9 +162,74 @@ inline ModelSpec lowerSimbodySystem(const SimTK::MultibodySystem&        system,
                 if (mf.size() == 0) throw std::runtime_error("lowerSimbodySystem: GlobalDamper on a system without mobilities");
                 for (int i = 1; i < mf.size(); ++i) if (mf[i] != mf[0]) throw std::runtime_error("lowerSimbodySystem: unexpected GlobalDamper response");
                 spec.forces.push_back(globalDamperForce(-mf[0]));
+            } else if (Force::TwoPointLinearSpring::isInstanceOf(f) || Force::TwoPointLinearDamper::isInstanceOf(f)) {
+                // Neither class has a getter (Force.h:231-262): bodies, stations and constants are identified from
+                // Force::calcForceContribution at a few seeded states.  The element loads body1 with (s1_G x f, f) and body2 with
+                // -(s2_G x f, f), f along the line through the two stations -- so in each body's own frame every probe's line of
+                // action passes through that body's station: a 3x3 least-squares intersection per body, then a linear fit of
+                // the force magnitude against the stretch (spring) or the closing speed (damper).  Recovered values are snapped to 12
+                // significant digits (user-entered parameters come back exactly).
+                const bool isSpring = Force::TwoPointLinearSpring::isInstanceOf(f);
+                auto snap = [](double x) { if (std::fabs(x) < 1e-12) return 0.0; char buf[40]; std::snprintf(buf, sizeof buf, "%.12g", x); return std::strtod(buf, nullptr); };
+                XorShift64 rng(0x51ED27A1B0C3ull + (uint64_t)(int)fx);
+                const int K = 8;
+                int b1 = -1, b2 = -1;
+                Mat33 A[2] = {Mat33(0), Mat33(0)}; Vec3 rhs[2] = {Vec3(0), Vec3(0)};
+                std::vector<State> probes; std::vector<Vec3> f1s;
+                for (int i = 0; i < K; ++i) {
+                    State probe = system.getDefaultState();
+                    for (int j = 0; j < probe.getNQ(); ++j) probe.updQ()[j] += 0.7*rng.next();
+                    for (int j = 0; j < probe.getNU(); ++j) probe.updU()[j] = rng.next();
+                    for (MobilizedBodyIndex mbx(1); mbx < nb; ++mbx) {          // unit quaternions
+                        const int jt = spec.bodies[mbx].joint_type;
+                        if ((jt == SBK_JOINT_BALL || jt == SBK_JOINT_FREE) && !spec.useEulerAngles) {
+                            const int q0 = (int)matter.getMobilizedBody(mbx).getFirstQIndex(probe);
+                            Real n2 = 0; for (int j = 0; j < 4; ++j) n2 += probe.getQ()[q0 + j]*probe.getQ()[q0 + j];
+                            for (int j = 0; j < 4; ++j) probe.updQ()[q0 + j] /= std::sqrt(n2);
+                        }
+                    }
+                    system.realize(probe, Stage::Velocity);
+                    Vector_<SpatialVec> bf; Vector_<Vec3> pf; Vector mf;
+                    f.calcForceContribution(probe, bf, pf, mf);
+                    int hits[2], nh = 0;
+                    for (int b = 0; b < bf.size(); ++b) if (bf[b][1].norm() > 0) { if (nh < 2) hits[nh] = b; ++nh; }
+                    if (nh != 2) throw std::runtime_error("lowerSimbodySystem: a two-point force element must load exactly two bodies");
+                    if (b1 < 0) { b1 = hits[0]; b2 = hits[1]; }
+                    else if (b1 != hits[0] || b2 != hits[1]) throw std::runtime_error("lowerSimbodySystem: inconsistent two-point force element");
+                    for (int w = 0; w < 2; ++w) {
+                        const MobilizedBody& mb = matter.getMobilizedBody(MobilizedBodyIndex(w ? b2 : b1));
+                        const Rotation& R = mb.getBodyTransform(probe).R();
+                        const Vec3 fG = bf[w ? b2 : b1][1], mG = bf[w ? b2 : b1][0];
+                        const Vec3 aB = ~R*((fG % mG)/fG.normSqr()), dB = ~R*(fG/fG.norm());
+                        const Mat33 Pm = Mat33(1) - Mat33(dB*~dB);
+                        A[w] += Pm; rhs[w] += Pm*aB;
+                    }
+                    probes.push_back(probe); f1s.push_back(bf[b1][1]);
+                }
+                Vec3 st[2];
+                for (int w = 0; w < 2; ++w) { st[w] = A[w].invert()*rhs[w]; for (int j = 0; j < 3; ++j) st[w][j] = snap(st[w][j]); }
+                // magnitude law: f1 = frc * unit(p2 - p1), frc = k (d - x0)  |  c (vRel . unit)
+                Real sxx = 0, sx = 0, sy = 0, sxy = 0;
+                for (int i = 0; i < K; ++i) {
+                    system.realize(probes[i], Stage::Velocity);          // a copied State keeps its variables, not its realized cache
+                    const MobilizedBody& m1 = matter.getMobilizedBody(MobilizedBodyIndex(b1)); const MobilizedBody& m2 = matter.getMobilizedBody(MobilizedBodyIndex(b2));
+                    const Vec3 r = m2.findStationLocationInGround(probes[i], st[1]) - m1.findStationLocationInGround(probes[i], st[0]);
+                    const Real d = r.norm(), frc = dot(f1s[i], r/d);
+                    const Real x = isSpring ? d : dot(m2.findStationVelocityInGround(probes[i], st[1]) - m1.findStationVelocityInGround(probes[i], st[0]), r/d);
+                    sxx += x*x; sx += x; sy += frc; sxy += x*frc;
+                }
+                if (isSpring) {
+                    const Real k = (K*sxy - sx*sy)/(K*sxx - sx*sx), c0 = (sy - k*sx)/K;          // frc = k d + c0, x0 = -c0 / k
+                    const double s1[3] = {st[0][0], st[0][1], st[0][2]}, s2[3] = {st[1][0], st[1][1], st[1][2]};
+                    spec.forces.push_back(twoPointSpringForce(b1, s1, b2, s2, snap(k), snap(-c0/k)));
+                } else {
+                    const double s1[3] = {st[0][0], st[0][1], st[0][2]}, s2[3] = {st[1][0], st[1][1], st[1][2]};
+                    spec.forces.push_back(twoPointDamperForce(b1, s1, b2, s2, snap(sxy/sxx)));
+                }
             } else {
                 throw std::runtime_error("lowerSimbodySystem: force element " + std::to_string((int)fx) +
-                                         " is outside {Gravity, UniformGravity, MobilityLinearSpring, MobilityLinearDamper, MobilityConstantForce, GlobalDamper}");
+                                         " is outside {Gravity, UniformGravity, MobilityLinearSpring, MobilityLinearDamper, MobilityConstantForce, GlobalDamper, "
+                                         "TwoPointLinearSpring, TwoPointLinearDamper}");
             }
         }
     }

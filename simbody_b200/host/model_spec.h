@@ -122,6 +122,15 @@ inline sbk_force_desc mobilityConstantForce(int body, int coord, double f0) {
     sbk_force_desc f; std::memset(&f, 0, sizeof f);
     f.kind = SBK_FORCE_MOBILITY_CONSTANT; f.body = body; f.coord = coord; f.a = f0; return f;
 }
+inline sbk_force_desc twoPointSpringForce(int body1, const double s1[3], int body2, const double s2[3], double k, double x0) {
+    sbk_force_desc f; std::memset(&f, 0, sizeof f);
+    f.kind = SBK_FORCE_TWO_POINT_SPRING; f.body = body1; f.coord = body2; f.a = k; f.b = x0;
+    for (int i = 0; i < 3; ++i) { f.dir[i] = s1[i]; f.station2[i] = s2[i]; }
+    return f;
+}
+inline sbk_force_desc twoPointDamperForce(int body1, const double s1[3], int body2, const double s2[3], double c) {
+    sbk_force_desc f = twoPointSpringForce(body1, s1, body2, s2, c, 0); f.kind = SBK_FORCE_TWO_POINT_DAMPER; return f;
+}
 inline sbk_force_desc globalDamperForce(double c) {
     sbk_force_desc f; std::memset(&f, 0, sizeof f);
     f.kind = SBK_FORCE_GLOBAL_DAMPER; f.body = -1; f.a = c; return f;
@@ -310,6 +319,18 @@ inline ModelSpec makeCartesian8() {
     return m;
 }
 
+// mixed7 plus the two-point elements of Force.cpp:103-221: a spring between stations on the Universal body and the branch Pin body, a
+// spring from a Ground station to the Slider body, and a damper between the Ball body and the last Pin body (ExampleLongPendulum-style
+// models attach such elements between bodies and Ground).
+inline ModelSpec makeTwoPoint7() {
+    ModelSpec m = makeMixed7(); m.name = "twopoint7";
+    const double s1[3] = {0.1, -0.3, 0.05}, s2[3] = {-0.2, 0.15, 0.1}, g0[3] = {0.5, 1.5, -0.4}, s3[3] = {0.05, 0.1, -0.12}, s4[3] = {0.0, -0.2, 0.07};
+    m.forces.push_back(twoPointSpringForce(3, s1, 6, s2, 40.0, 0.35));
+    m.forces.push_back(twoPointSpringForce(0, g0, 5, s3, 15.0, 0.8));
+    m.forces.push_back(twoPointDamperForce(2, s4, 4, s1, 2.5));
+    return m;
+}
+
 inline ModelSpec makeNamedModel(const std::string& name, int n) {
     if (name == "double_pendulum") return makePinChain(2, "double_pendulum");
     if (name == "pin_chain")       return makePinChain(n > 0 ? n : 50);
@@ -318,6 +339,7 @@ inline ModelSpec makeNamedModel(const std::string& name, int n) {
     if (name == "ugdamp5")         return makeUgDamp5();
     if (name == "welded8")         return makeWelded8();
     if (name == "cartesian8")      return makeCartesian8();
+    if (name == "twopoint7")       return makeTwoPoint7();
     if (name == "humanoid30")      return makeHumanoid30();
     if (name == "branched_tree")   return makeBranchedTree(n > 0 ? n : 1000);
     throw std::runtime_error("unknown model '" + name + "'");
@@ -343,6 +365,11 @@ inline std::string toText(const ModelSpec& m) {
         else if (f.kind == SBK_FORCE_UNIFORM_GRAVITY) { out += "ugravity"; num(f.dir[0]); num(f.dir[1]); num(f.dir[2]); }
         else if (f.kind == SBK_FORCE_GLOBAL_DAMPER) { out += "gdamper"; num(f.a); }
         else if (f.kind == SBK_FORCE_MOBILITY_CONSTANT) { out += "mconst " + std::to_string(f.body) + " " + std::to_string(f.coord); num(f.a); }
+        else if (f.kind == SBK_FORCE_TWO_POINT_SPRING || f.kind == SBK_FORCE_TWO_POINT_DAMPER) {
+            out += (f.kind == SBK_FORCE_TWO_POINT_SPRING ? "tpspring " : "tpdamper ") + std::to_string(f.body) + " " + std::to_string(f.coord);
+            num(f.a); if (f.kind == SBK_FORCE_TWO_POINT_SPRING) num(f.b);
+            for (double v : f.dir) num(v); for (double v : f.station2) num(v);
+        }
         else throw std::runtime_error("bad force kind");
         out += "\n";
     }
@@ -378,6 +405,11 @@ inline ModelSpec fromText(const std::string& text) {
         else if (tok == "ugravity") { f.kind = SBK_FORCE_UNIFORM_GRAVITY; f.body = -1; f.a = 1; in >> f.dir[0] >> f.dir[1] >> f.dir[2]; }
         else if (tok == "gdamper") { f.kind = SBK_FORCE_GLOBAL_DAMPER; f.body = -1; in >> f.a; }
         else if (tok == "mconst") { f.kind = SBK_FORCE_MOBILITY_CONSTANT; in >> f.body >> f.coord >> f.a; }
+        else if (tok == "tpspring" || tok == "tpdamper") {
+            f.kind = tok == "tpspring" ? SBK_FORCE_TWO_POINT_SPRING : SBK_FORCE_TWO_POINT_DAMPER;
+            in >> f.body >> f.coord >> f.a; if (tok == "tpspring") in >> f.b;
+            for (double& v : f.dir) in >> v; for (double& v : f.station2) in >> v;
+        }
         else throw std::runtime_error("bad force token " + tok);
         if (!in) throw std::runtime_error("truncated force line");
         m.forces.push_back(f);

@@ -57,6 +57,16 @@ int main() {
         std::printf("facade_smoke: |Minv(M v)-v|=%.3e  |ID(FD)|=%.3e  steps=%lld realizations=%lld\n", e1, e2,
                     integ.getNumStepsTaken(), integ.getNumRealizations());
         if (!(e1 < 1e-9 && e2 < 1e-8 && integ.getNumStepsTaken() == 10LL*N && integ.getNumRealizations() - r0 == 50LL*N)) { std::printf("FAIL\n"); return 1; }
+        // getters, energies, status, error-controlled stepTo (Integrator.h:226,286-290): every instance lands on the report time
+        std::vector<double> X, V, ke, pe; std::vector<int32_t> st;
+        matter.realizeVelocityKinematics(); matter.getBodyTransforms(X); matter.getBodyVelocities(V); matter.calcEnergy(ke, pe);
+        if (X.size() != (size_t)12*nb*N || V.size() != (size_t)6*nb*N || !(ke[0] > 0) || matter.getStatus(st) != 0) { std::printf("FAIL: getters\n"); return 1; }
+        integ.setAccuracy(1e-4); integ.stepTo(0.05);
+        const std::vector<double> t = integ.getTime();
+        long long att = integ.getNumStepsAttempted(), stp = 0; for (int32_t a : integ.getNumStepsTakenPerInstance()) stp += a;
+        for (double tk : t) if (tk != 0.05) { std::printf("FAIL: stepTo ended at %.17g\n", tk); return 1; }
+        if (!(stp >= N && att >= stp)) { std::printf("FAIL: adaptive counters\n"); return 1; }
+        std::printf("facade_smoke: stepTo(0.05) steps=%lld attempts=%lld\n", stp, att);
         std::printf("OK\n");
         return 0;
     } catch (const std::exception& e) { std::printf("FAIL: %s\n", e.what()); return 1; }

@@ -24,6 +24,7 @@ CASES = [  # name, size param, n eval states, (h, nsteps), q_scale
     ("ugdamp5", 0, 6, (1e-3, 20), 0.7),          # Force::UniformGravity + Force::GlobalDamper
     ("welded8", 0, 6, (1e-3, 20), 0.7),          # MobilizedBody::Weld inside the chain and as a leaf
     ("cartesian8", 0, 6, (1e-3, 20), 0.7),       # MobilizedBody::Planar / Cylinder / Translation
+    ("twopoint7", 0, 6, (1e-3, 20), 0.7),        # Force::TwoPointLinearSpring / TwoPointLinearDamper between bodies and to Ground
     ("humanoid30", 0, 4, (1e-3, 10), 0.5),
     ("branched_tree", 100, 2, (5e-4, 4), 0.5),
     ("branched_tree", 1000, 2, (5e-4, 2), 0.5),  # BASELINE config 5 at full size (11 levels, width 489): file branched_tree1000.npz

@@ -25,6 +25,7 @@ struct Emu {
     std::vector<double> cache, y, ydot, qdd, qerr, fmob, Fbody, vin, vout, vin2, Fin;
     std::vector<double> y0, f0, fa, fb, ys;
     std::vector<int> status;
+    std::vector<TwoPointConst> tps; std::vector<double> f2;
 };
 void setup(Emu& e, const char* text, int N) {
     sbk::compileTopology(sbk::fromText(text), e.topo);
@@ -45,6 +46,9 @@ void setup(Emu& e, const char* text, int N) {
     e.vin.assign((size_t)t.nu*N, 0); e.vin2.assign((size_t)t.nu*N, 0); e.vout.assign((size_t)t.nu*N, 0); e.Fin.assign((size_t)t.nb*6*N, 0);
     e.y0.assign(ny*N, 0); e.f0.assign(ny*N, 0); e.fa.assign(ny*N, 0); e.fb.assign(ny*N, 0); e.ys.assign(ny*N, 0);
     e.status.assign(N, 0);
+    e.tps = t.twoPoint;
+    for (TwoPointConst& tp : e.tps) { tp.cacheBase1 = e.bodies[tp.body1].cacheBase; tp.cacheBase2 = e.bodies[tp.body2].cacheBase; }
+    e.f2.assign((size_t)t.nb*6*N, 0.0);
 }
 Ctx makeCtx(Emu& e, int inst) {
     const sbk_topology& t = e.topo; const int N = e.N;
@@ -58,6 +62,7 @@ Ctx makeCtx(Emu& e, int inst) {
     c.qdot = e.ydot.data(); c.udot = e.ydot.data() + (size_t)t.nq*N;
     c.qdotdot = e.qdd.data(); c.qerr = e.qerr.data();
     c.status = e.status.data();
+    c.tp = e.tps.data(); c.ntp = (int)e.tps.size(); c.f2 = e.f2.data();
     return c;
 }
 } // namespace
@@ -86,6 +91,7 @@ int emu_eval(const char* text, int N, const double* in, double* out) {
             double cy[CARRY_ROWS + LFCARRY_ROWS];
             c.fmobOut = e.fmob.data(); c.FbodyOut = e.Fbody.data();
             tpiEvalDerivatives<false>(c, tablesOf(c), k, cy, c.qdot, c.udot, c.qdotdot);
+            if (c.ntp) for (int i = 0; i < 6; ++i) e.Fbody[(size_t)i*N + k] = e.f2[(size_t)i*N + k];      // two-point forces on Ground
             for (int i = 0; i < nq; ++i) *o++ = e.ydot[(size_t)i*N + k];
             for (int i = 0; i < nu; ++i) *o++ = e.ydot[(size_t)(nq+i)*N + k];
             for (int i = 0; i < nq; ++i) *o++ = e.qdd[(size_t)i*N + k];
@@ -167,6 +173,7 @@ int emu_step(const char* text, int N, const double* in, double* out, double h, i
             return 0;
         }
         if (lean >= 3 && !t.localOk) return 5;
+        if (lean != 0 && !t.twoPoint.empty()) return 6;      // two-point force elements: FULL records only
         if (lean == 5) {        // the same integrator in level order (sbk_ltree.cuh), one emulated warp group: wc = 0, nw = 1 (or 3: round robin)
             LTables LT; LT.bodies = t.lbodiesLevel.data(); LT.children = t.children.data(); LT.forces = t.forces.data(); LT.fcoef = t.lfcoef.data();
             struct { const int* order; const int* start; int nlevels; } LV; LV.order = t.levelOrder.data(); LV.start = t.levelStart.data(); LV.nlevels = t.nlevels;

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(capi.BodyDesc) == 8 + 8 + 3 * 8 + 6 * 8 + 12 * 8 + 12 * 8
-    assert ctypes.sizeof(capi.ForceDesc) == 16 + 16 + 24
+    assert ctypes.sizeof(capi.ForceDesc) == 16 + 16 + 24 + 24
     assert ctypes.sizeof(capi.RkmOpts) == 24
 
 

@@ -20,7 +20,7 @@ from _harness import ModelInfo, RefDriver, check_sdfast2, have_ref, rel_err
 pytestmark = pytest.mark.gpu
 TOL = 1e-11
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-MODELS = ["double_pendulum", "pin_chain", "mixed7", "mixed7e", "ugdamp5", "welded8", "cartesian8", "humanoid30", "branched_tree"]
+MODELS = ["double_pendulum", "pin_chain", "mixed7", "mixed7e", "ugdamp5", "welded8", "cartesian8", "twopoint7", "humanoid30", "branched_tree"]
 
 
 def soa(a):

@@ -14,7 +14,7 @@ import pytest
 from _harness import COracle, HostEmu, ModelInfo, RefDriver, check_sdfast2, have_ref, rel_err, ROOT
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-MODELS = ["double_pendulum", "pin_chain", "mixed7", "mixed7e", "ugdamp5", "welded8", "cartesian8", "humanoid30", "branched_tree"]
+MODELS = ["double_pendulum", "pin_chain", "mixed7", "mixed7e", "ugdamp5", "welded8", "cartesian8", "twopoint7", "humanoid30", "branched_tree"]
 
 
 @pytest.fixture(scope="module")
@@ -47,7 +47,8 @@ def test_kernel_math_on_host_matches_reference_golden(built, name):
     for k in ref:
         assert rel_err(got[k], ref[k]) < 1e-11, (name, k, rel_err(got[k], ref[k]))
     ny = info.nq + info.nu
-    ys = HostEmu().step(info, g["step_in"], float(g["h"]), int(g["nsteps"]))
+    # two-point force elements need every body's ground-frame transform: FULL records (lean=0) is the only integrator form for them
+    ys = HostEmu().step(info, g["step_in"], float(g["h"]), int(g["nsteps"]), lean=0 if name == "twopoint7" else 1)
     assert rel_err(ys[:, :ny], g["step_out"][:, :ny]) < 1e-10
 
 
@@ -129,7 +130,7 @@ def test_quaternion_projection_rule(built):
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
 @pytest.mark.parametrize("name,n", [("double_pendulum", 0), ("pin_chain", 12), ("mixed7", 0), ("mixed7e", 0), ("ugdamp5", 0), ("welded8", 0),
-                                    ("cartesian8", 0), ("humanoid30", 0), ("branched_tree", 33)])
+                                    ("cartesian8", 0), ("twopoint7", 0), ("humanoid30", 0), ("branched_tree", 33)])
 def test_live_reference_differential(built, name, n):
     emu, ref, co = HostEmu(), RefDriver(), COracle()
     text = emu.model_text(name, n)
@@ -290,3 +291,12 @@ def test_non_finite_error_norm_survives_the_infinity_norm(built):
         for inf in (0, 1):
             o = emu.step(info, y, 1e-3, 2, inf_norm=inf, lean=lean)
             assert not np.isfinite(o[0, ny]) and np.isfinite(o[1, ny]), (lean, inf, o[:, ny])
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
+def test_two_point_elements_lower_by_probing(built):
+    """Force::TwoPointLinearSpring / TwoPointLinearDamper have no getters: lower_simbody.h identifies bodies, stations and
+    constants from Force::calcForceContribution at seeded states; user-entered parameters come back exactly."""
+    text = HostEmu().model_text("twopoint7")
+    assert RefDriver().lower(text) == text
+    assert sum(line.startswith("tp") for line in text.splitlines()) == 3
