@@ -178,7 +178,7 @@ def test_fused_plan_matches_generic_plan():
     bm.close(); topo.close()
 
 
-@pytest.mark.parametrize("name", ["mixed7", "mixed7e", "welded8", "cartesian8", "humanoid30", "branched_tree"])
+@pytest.mark.parametrize("name", ["mixed7", "mixed7e", "welded8", "cartesian8", "twopoint7", "humanoid30", "branched_tree"])
 def test_level_parallel_plan_matches_golden(name):
     """Plan 3 (CTA per instance, threads over the bodies of a level) against the reference."""
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
@@ -198,7 +198,7 @@ def test_level_parallel_plan_matches_golden(name):
     bm.close(); topo.close()
 
 
-@pytest.mark.parametrize("name", ["mixed7", "mixed7e", "welded8", "cartesian8", "humanoid30", "branched_tree"])
+@pytest.mark.parametrize("name", ["mixed7", "mixed7e", "welded8", "cartesian8", "twopoint7", "humanoid30", "branched_tree"])
 def test_grid_level_parallel_plan_matches_golden(name):
     """Plan 4 (persistent grid, work items = body of a level x warp of instances, grid barriers between
     levels) against the reference: fixed-step RKM, plus agreement with plan 1 on a batch that is not a
