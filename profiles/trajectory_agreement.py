@@ -15,7 +15,8 @@ from _harness import ModelInfo, RefDriver
 out = {}
 for name, n, h, horizons, qs in [("double_pendulum", 0, 1e-3, [0.1, 0.5, 1, 2, 5, 10, 20], 2.0),
                                  ("pin_chain", 50, 1e-3, [0.05, 0.2, 0.5], 1.0),
-                                 ("humanoid30", 0, 1e-3, [0.05, 0.2, 0.5, 1.0], 0.4)]:
+                                 ("humanoid30", 0, 1e-3, [0.05, 0.2, 0.5, 1.0], 0.4),
+                                 ("branched_tree", 1000, 5e-4, [0.005, 0.02, 0.05], 0.4)]:
     info = ModelInfo(sb.model_text(name, n))
     N = 32
     q, u = info.random_states(N, 777, q_scale=qs)
