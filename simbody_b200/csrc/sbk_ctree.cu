@@ -3,8 +3,8 @@
 // One thread-block CLUSTER owns 32 instances (lanes of every warp = those instances).  The tree is cut at the first level with at
 // least one body per warp of the cluster: every body of that level roots a subtree that ONE warp walks depth-first with no barrier
 // at all (links in the warp's carry, like the thread-per-instance plan); the few levels above the cut run level-parallel on the
-// eight warps of the cluster's first CTA with __syncthreads between levels.  The two parts meet at the cluster's hardware barrier
-// (barrier.cluster) twice per derivative evaluation -- no grid-wide barrier, clusters never wait for each other.  Body steps, prefetch and the step logic are those of the fused body-frame integrator
+// cluster's warps with the cluster's hardware barrier (barrier.cluster) between levels (or, selectable, on the first CTA's eight
+// warps with __syncthreads) -- no grid-wide barrier, clusters never wait for each other.  Body steps, prefetch and the step logic are those of the fused body-frame integrator
 // (sbk_local.cuh, sbk_lrkm.cuh) in level order (sbk_ltree.cuh).  Replaces the grid-level plan's 141 grid barriers per step
 // (ncu, round 1: 46% of the stall samples) by 100 cluster barriers over a 2.5x shorter instruction stream per body.
 #define SBK_CARRY_STRIDE_DEVICE_THREADS 256

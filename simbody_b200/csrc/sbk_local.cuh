@@ -517,41 +517,36 @@ template <int JT> struct LPfOut {
            Y = QU + NS, F0 = Y + NS, F23 = F0 + NS,
            HAS_F0 = (JT != JT_BALL && JT != JT_FREE) ? 1 : 0, HAS_F23 = (JT == JT_PIN || JT == JT_SLIDER) ? 1 : 0 };
 };
-// Row counts of a mobilizer kind at run time (the producer works on the NEXT body, whose kind is not a template parameter:
-// one compact loop per row group instead of an unrolled copy sequence per kind keeps the prefetch out of the instruction cache's way).
-struct LPfDims { int g, d, nsc, nq; };
-SBK_HD LPfDims lpfDims(const int joint) {
-    LPfDims r;
-    r.g   = joint == JT_BALL ? 9 : joint == JT_FREE ? 0 : joint == JT_UNIVERSAL ? 12 : 6;
-    r.d   = joint == JT_BALL ? 3 : joint == JT_FREE ? 6 : joint == JT_UNIVERSAL ? 2 : 1;
-    r.nsc = joint == JT_PIN ? 2 : joint == JT_UNIVERSAL ? 4 : 0;
-    r.nq  = joint == JT_BALL ? 4 : joint == JT_FREE ? 7 : joint == JT_UNIVERSAL ? 2 : 1;
-    return r;
-}
-// A kernel built for ONE mobilizer kind (the Pin-only variant) knows the counts at compile time: straight-line copies.
-template <int JMASK> SBK_HD LPfDims lpfDimsM(const int joint) {
-    if constexpr ((JMASK & JM_ALL) == JM_PIN) return lpfDims(JT_PIN);
-    else return lpfDims(joint);
-}
-template <int JMASK>
-SBK_HD void lpfRows(double* dst, const double* src, const long long srcStride, const int n) {
-    if constexpr ((JMASK & JM_ALL) == JM_PIN) {
-#pragma unroll
-        for (int i = 0; i < 6; ++i) if (i < n) lpfCopy(dst + i*SBK_CARRY_STRIDE, src + i*srcStride);
-    } else {
-#pragma unroll 1
-        for (int i = 0; i < n; ++i) lpfCopy(dst + i*SBK_CARRY_STRIDE, src + i*srcStride);
+#define SBK_DISPATCH_LOCAL(JMASK, jt, CALL)                                                                         \
+    switch (jt) {                                                                                                   \
+        case JT_PIN:       if constexpr (((JMASK) & JM_PIN) != 0)       { constexpr int JT = JT_PIN;       CALL; } break; \
+        case JT_SLIDER:    if constexpr (((JMASK) & JM_SLIDER) != 0)    { constexpr int JT = JT_SLIDER;    CALL; } break; \
+        case JT_UNIVERSAL: if constexpr (((JMASK) & JM_UNIVERSAL) != 0) { constexpr int JT = JT_UNIVERSAL; CALL; } break; \
+        case JT_BALL:      if constexpr (((JMASK) & JM_BALL) != 0)      { constexpr int JT = JT_BALL;      CALL; } break; \
+        case JT_FREE:      if constexpr (((JMASK) & JM_FREE) != 0)      { constexpr int JT = JT_FREE;      CALL; } break; \
+        default: break;                                                                                             \
     }
+
+// The producer works on the NEXT body, whose kind is a run-time value: it dispatches once on the kind into straight-line copies
+// with the group base addresses hoisted (one LDGSTS per row; a run-time row loop cost 19% of all executed instructions: ncu).
+template <int N>
+SBK_HD void lpfRowsN(double* dst, const double* src, const long long srcStride) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) lpfCopy(dst + i*SBK_CARRY_STRIDE, src + i*srcStride);
+}
+template <int JT, bool BLK>
+SBK_HD void lPrefetchInT(const Ctx& c, const LBody& bc, const int inst, double* pf, const double* S, const int vb) {
+    constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
+    const CacheRefT<BLK> me = lrecOf<BLK>(c, inst, bc.rec);
+    const long long rs = BLK ? BLK_LANES : me.stride, ss = BLK ? BLK_LANES : c.sStride;
+    lpfRowsN<lscCount<JT>()>(pf + LPfIn<JT>::SC*SBK_CARRY_STRIDE, me.p + LR_SC*rs, rs);
+    lpfRowsN<NQ>(pf + LPfIn<JT>::QU*SBK_CARRY_STRIDE, S + stateIndex<BLK>(c, inst, bc.q0), ss);
+    lpfRowsN<d>(pf + (LPfIn<JT>::QU + NQ)*SBK_CARRY_STRIDE, S + stateIndex<BLK>(c, inst, c.nq + bc.u0), ss);
+    if (bc.flags & BF_TIP) lpfRowsN<6>(pf + LPfIn<JT>::V*SBK_CARRY_STRIDE, me.p + (lrV(d) + vb)*rs, rs);
 }
 template <int JMASK, bool BLK>
 SBK_HD void lPrefetchIn(const Ctx& c, const LBody& bc, const int inst, double* pf, const double* S, const int vb) {
-    const LPfDims n = lpfDimsM<JMASK>(bc.joint);
-    const CacheRefT<BLK> me = lrecOf<BLK>(c, inst, bc.rec);
-    const long long rs = BLK ? BLK_LANES : me.stride, ss = BLK ? BLK_LANES : c.sStride;
-    lpfRows<JMASK>(pf, me.p + LR_SC*rs, rs, n.nsc);                                                        // LPfIn::SC = 0
-    lpfRows<JMASK>(pf + n.nsc*SBK_CARRY_STRIDE, S + stateIndex<BLK>(c, inst, bc.q0), ss, n.nq);             // LPfIn::QU
-    lpfRows<JMASK>(pf + (n.nsc + n.nq)*SBK_CARRY_STRIDE, S + stateIndex<BLK>(c, inst, c.nq + bc.u0), ss, n.d);
-    if (bc.flags & BF_TIP) lpfRows<JMASK>(pf + (n.nsc + n.nq + n.d)*SBK_CARRY_STRIDE, me.p + (lrV(n.d) + vb)*rs, rs, 6);   // LPfIn::V
+    SBK_DISPATCH_LOCAL(JMASK, bc.joint, (lPrefetchInT<JT, BLK>(c, bc, inst, pf, S, vb)));
 }
 
 //==============================================================================================
@@ -722,16 +717,6 @@ SBK_BODY void lOutwardBody(const Ctx& c, const LBody& bc, const int inst, double
         for (int i = 0; i < d; ++i) stS<BLK>(c, inst, udotDst, bc.u0 + i, udot[i]);
     }
 }
-
-#define SBK_DISPATCH_LOCAL(JMASK, jt, CALL)                                                                         \
-    switch (jt) {                                                                                                   \
-        case JT_PIN:       if constexpr (((JMASK) & JM_PIN) != 0)       { constexpr int JT = JT_PIN;       CALL; } break; \
-        case JT_SLIDER:    if constexpr (((JMASK) & JM_SLIDER) != 0)    { constexpr int JT = JT_SLIDER;    CALL; } break; \
-        case JT_UNIVERSAL: if constexpr (((JMASK) & JM_UNIVERSAL) != 0) { constexpr int JT = JT_UNIVERSAL; CALL; } break; \
-        case JT_BALL:      if constexpr (((JMASK) & JM_BALL) != 0)      { constexpr int JT = JT_BALL;      CALL; } break; \
-        case JT_FREE:      if constexpr (((JMASK) & JM_FREE) != 0)      { constexpr int JT = JT_FREE;      CALL; } break; \
-        default: break;                                                                                             \
-    }
 
 // Ground's "record" (rows lrV(0).., written once per sweep by the sweep drivers): v = 0, a = -g.
 SBK_HD void lGroundLinks(const Ctx& c, const LTables& T, const int inst, double* cy, bool withA) {

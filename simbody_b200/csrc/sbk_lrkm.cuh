@@ -41,32 +41,38 @@ SBK_HD LStage lstageOf(const int stage, const double h, const LRkmWork& w) {
 }
 
 // Request the rows the fused outward step of body bc will read (layout LPfOut<kind of bc>).
-template <int JMASK, bool BLK>
-SBK_HD void lPrefetchOut(const Ctx& c, const LBody& bc, const int inst, double* pf, const LRkmWork& w, const double* S, const LStage& sg) {
-    const LPfDims n = lpfDimsM<JMASK>(bc.joint);
-    const int ns = n.nq + n.d, oQU = n.g + n.d + n.nsc;
+template <int JT, bool BLK>
+SBK_HD void lPrefetchOutT(const Ctx& c, const LBody& bc, const int inst, double* pf, const LRkmWork& w, const double* S, const LStage& sg) {
+    constexpr int NQ = JointDims<JT>::nq, d = JointDims<JT>::nu;
+    typedef LPfOut<JT> L;
     const CacheRefT<BLK> me = lrecOf<BLK>(c, inst, bc.rec);
     const long long rs = BLK ? BLK_LANES : me.stride, ss = BLK ? BLK_LANES : c.sStride;
     const long long offQ = stateIndex<BLK>(c, inst, bc.q0), offU = stateIndex<BLK>(c, inst, c.nq + bc.u0);
-    lpfRows<JMASK>(pf + oQU*SBK_CARRY_STRIDE, S + offQ, ss, n.nq);
-    lpfRows<JMASK>(pf + (oQU + n.nq)*SBK_CARRY_STRIDE, S + offU, ss, n.d);
+    lpfRowsN<NQ>(pf + L::QU*SBK_CARRY_STRIDE, S + offQ, ss);
+    lpfRowsN<d>(pf + (L::QU + NQ)*SBK_CARRY_STRIDE, S + offU, ss);
     if (sg.stage < 0) return;
-    lpfRows<JMASK>(pf, me.p + LR_G*rs, rs, n.g);
-    lpfRows<JMASK>(pf + n.g*SBK_CARRY_STRIDE, me.p + lrNU(n.d)*rs, rs, n.d);
-    lpfRows<JMASK>(pf + (n.g + n.d)*SBK_CARRY_STRIDE, me.p + LR_SC*rs, rs, n.nsc);
+    lpfRowsN<lgCount<JT>()>(pf + L::G*SBK_CARRY_STRIDE, me.p + LR_G*rs, rs);
+    lpfRowsN<d>(pf + L::NU*SBK_CARRY_STRIDE, me.p + lrNU(d)*rs, rs);
+    lpfRowsN<lscCount<JT>()>(pf + L::SC*SBK_CARRY_STRIDE, me.p + LR_SC*rs, rs);
     if (sg.stage > 0) {
-        lpfRows<JMASK>(pf + (oQU + ns)*SBK_CARRY_STRIDE, w.Y + offQ, ss, n.nq);
-        lpfRows<JMASK>(pf + (oQU + ns + n.nq)*SBK_CARRY_STRIDE, w.Y + offU, ss, n.d);
-        if (bc.joint != JT_BALL && bc.joint != JT_FREE) {                  // LPfOut::HAS_F0
-            lpfRows<JMASK>(pf + (oQU + 2*ns)*SBK_CARRY_STRIDE, w.F0 + offQ, ss, n.nq);
-            lpfRows<JMASK>(pf + (oQU + 2*ns + n.nq)*SBK_CARRY_STRIDE, w.F0 + offU, ss, n.d);
+        lpfRowsN<NQ>(pf + L::Y*SBK_CARRY_STRIDE, w.Y + offQ, ss);
+        lpfRowsN<d>(pf + (L::Y + NQ)*SBK_CARRY_STRIDE, w.Y + offU, ss);
+        if constexpr (L::HAS_F0 != 0) {
+            lpfRowsN<NQ>(pf + L::F0*SBK_CARRY_STRIDE, w.F0 + offQ, ss);
+            lpfRowsN<d>(pf + (L::F0 + NQ)*SBK_CARRY_STRIDE, w.F0 + offU, ss);
         }
-        const double* f23 = sg.m2 != 0 ? w.F2 : sg.m3 != 0 ? w.F3 : nullptr;
-        if (f23 && (bc.joint == JT_PIN || bc.joint == JT_SLIDER)) {        // LPfOut::HAS_F23
-            lpfRows<JMASK>(pf + (oQU + 3*ns)*SBK_CARRY_STRIDE, f23 + offQ, ss, n.nq);
-            lpfRows<JMASK>(pf + (oQU + 3*ns + n.nq)*SBK_CARRY_STRIDE, f23 + offU, ss, n.d);
+        if constexpr (L::HAS_F23 != 0) {
+            const double* f23 = sg.m2 != 0 ? w.F2 : sg.m3 != 0 ? w.F3 : nullptr;
+            if (f23) {
+                lpfRowsN<NQ>(pf + L::F23*SBK_CARRY_STRIDE, f23 + offQ, ss);
+                lpfRowsN<d>(pf + (L::F23 + NQ)*SBK_CARRY_STRIDE, f23 + offU, ss);
+            }
         }
     }
+}
+template <int JMASK, bool BLK>
+SBK_HD void lPrefetchOut(const Ctx& c, const LBody& bc, const int inst, double* pf, const LRkmWork& w, const double* S, const LStage& sg) {
+    SBK_DISPATCH_LOCAL(JMASK, bc.joint, (lPrefetchOutT<JT, BLK>(c, bc, inst, pf, w, S, sg)));
 }
 
 // One body of the fused outward sweep.  Phase 0 (stage >= 0): acceleration of the evaluation at state S (S = Y for
