@@ -217,7 +217,6 @@ static int configurePlan(sbk_batch* b, int plan) {
     a.nlevels = t->nlevels; a.plan = plan;
     a.jointMask = 0;
     for (int i = 1; i < t->nb; ++i) a.jointMask |= 1 << t->bodies[i].joint;
-    { const char* e = getenv("SBK_JMASK"); if (e) a.jointMask |= atoi(e); }           // tuning override: force a wider kernel variant
     a.stageInSmem = (plan != 3 && blob.size() <= 28*1024) ? 1u : 0u;
     { const char* e = getenv("SBK_NOSTAGE"); if (e && atoi(e)) a.stageInSmem = 0; }   // tuning override: read the tables through L1/L2   // two resident CTAs: 2 x (tables + 84 KB carry) <= 227 KB
     CUDA_TRY(cudaStreamSynchronize(b->stream));
@@ -241,7 +240,6 @@ static int configurePlan(sbk_batch* b, int plan) {
         std::memcpy(lblob.data() + lb + childBytes + forceBytes, t->lfcoef.data(), t->lfcoef.size()*sizeof(double));
         a.lfcoefOff = (uint32_t)(lb + childBytes + forceBytes);
         a.localMinB = 2;
-        { const char* e3 = getenv("SBK_LOCAL_MINB"); if (e3) a.localMinB = atoi(e3); }     // tuning override
         std::memcpy(lblob.data(), t->lbodies.data(), t->lbodies.size()*sizeof(LBody));
         std::memcpy(lblob.data() + lb, t->children.data(), t->children.size()*sizeof(int));
         std::memcpy(lblob.data() + lb + childBytes, t->forces.data(), t->forces.size()*sizeof(ForceConst));
@@ -818,8 +816,8 @@ int sbk_integrator_kernel_name(const sbk_batch* b, char* buf, int cap) {
     else {
         const KArgs& a = b->a; const int m = a.jointMask;
         int jm, minb = 2, stage;
-        if (a.ltables) { jm = (((m & ~JM_PIN) == 0) ? JM_PIN : JM_MOBILE5) | JM_LOCAL; minb = (a.localMinB == 3 || a.localMinB == 4) ? a.localMinB : 2; stage = a.lstageInSmem ? 1 : 0; }
-        else { jm = (m & ~JM_PIN) == 0 ? JM_PIN : (m & ~JM_LIGHT) == 0 ? JM_LIGHT : (m & ~JM_MOBILE5) == 0 ? JM_MOBILE5 : JM_ALL; stage = a.stageInSmem ? 1 : 0; }
+        if (a.ltables) { jm = (((m & ~JM_PIN) == 0) ? JM_PIN : JM_MOBILE5) | JM_LOCAL; stage = a.lstageInSmem ? 1 : 0; }
+        else { jm = JM_ALL; stage = a.stageInSmem ? 1 : 0; }
         s = "tpiKernel<7, " + std::to_string(stage) + ", " + std::to_string(minb) + ", " + std::to_string(jm) + ">";
     }
     std::snprintf(buf, (size_t)cap, "%s", s.c_str());

@@ -689,17 +689,10 @@ cudaError_t launchTpi(KernelOp op, const KArgs& a, cudaStream_t stream) {
             if (a.ntp > 0) return op == OP_RKM ? launchGlRkmImpl(a, stream) : cudaErrorNotSupported;
             // integrator kernels: instantiated per set of mobilizer kinds present in the model (one translation unit each)
             const int m = a.jointMask;
-            if (a.ltables) {            // body-frame sweeps
-                const bool pin = (m & ~JM_PIN) == 0;
-                switch (a.localMinB) {
-                    case 4:  return pin ? launchTpiRkmLocalPin_m4(op, a, stream) : launchTpiRkmLocal_m4(op, a, stream);
-                    case 3:  return pin ? launchTpiRkmLocalPin_m3(op, a, stream) : launchTpiRkmLocal_m3(op, a, stream);
-                    default: return pin ? launchTpiRkmLocalPin_m2(op, a, stream) : launchTpiRkmLocal_m2(op, a, stream);
-                }
-            }
-            if ((m & ~JM_PIN) == 0)     return launchTpiRkmPin(op, a, stream);
-            if ((m & ~JM_LIGHT) == 0)   return launchTpiRkmLight(op, a, stream);
-            if ((m & ~JM_MOBILE5) == 0) return launchTpiRkmMobile5(op, a, stream);
+            if (a.ltables)              // body-frame sweeps: Pin-only models get the kernel without the other mobilizers' code
+                return (m & ~JM_PIN) == 0 ? launchTpiRkmLocalPin_m2(op, a, stream) : launchTpiRkmLocal_m2(op, a, stream);
+            // every other model (Weld, Translation, Cylinder, Planar, Gimbal, Euler-angle mode, or SBK_NOLOCAL=1): round 1's
+            // ground-frame integrator with reversible kinematics, one build for all mobilizer kinds
             return launchTpiRkmAll(op, a, stream);
         }
     }

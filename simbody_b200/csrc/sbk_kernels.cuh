@@ -66,14 +66,10 @@ enum KernelOp {
 // Launch one operation for the thread-per-instance plan on `stream`.
 cudaError_t launchTpi(KernelOp op, const KArgs& a, cudaStream_t stream);
 // Integrator kernels of the thread-per-instance plan, one family per set of mobilizer kinds (op = OP_RKM / OP_RKM_ADAPT).
-cudaError_t launchTpiRkmPin(KernelOp op, const KArgs& a, cudaStream_t stream);      // Pin only
-cudaError_t launchTpiRkmLight(KernelOp op, const KArgs& a, cudaStream_t stream);    // Pin / Slider / Universal / Weld
-cudaError_t launchTpiRkmMobile5(KernelOp op, const KArgs& a, cudaStream_t stream);  // Pin / Slider / Universal / Ball / Free
-cudaError_t launchTpiRkmAll(KernelOp op, const KArgs& a, cudaStream_t stream);      // every supported mobilizer
-// body-frame sweeps (Pin / Slider / Universal / Ball / Free, and Pin only), built for 2 / 3 / 4 resident CTAs per SM
+cudaError_t launchTpiRkmAll(KernelOp op, const KArgs& a, cudaStream_t stream);      // ground-frame integrator, every supported mobilizer
+// body-frame sweeps (Pin / Slider / Universal / Ball / Free, and Pin only), built for 2 resident CTAs per SM (255 registers; the
+// 3- and 4-CTA builds of sbk_rkm_local.inc measured no gain: shared memory, not registers, limits the occupancy)
 cudaError_t launchTpiRkmLocal_m2(KernelOp op, const KArgs& a, cudaStream_t stream); cudaError_t launchTpiRkmLocalPin_m2(KernelOp op, const KArgs& a, cudaStream_t stream);
-cudaError_t launchTpiRkmLocal_m3(KernelOp op, const KArgs& a, cudaStream_t stream); cudaError_t launchTpiRkmLocalPin_m3(KernelOp op, const KArgs& a, cudaStream_t stream);
-cudaError_t launchTpiRkmLocal_m4(KernelOp op, const KArgs& a, cudaStream_t stream); cudaError_t launchTpiRkmLocalPin_m4(KernelOp op, const KArgs& a, cudaStream_t stream);
 // Register-resident fused plan (serial chains of 1-2 Pin/Slider[/Universal] mobilizers).
 bool fusedPlanSupports(int nb, const int* joints /*[nb]*/);
 cudaError_t launchFusedRkm(const KArgs& a, const int* joints, bool adaptive, cudaStream_t stream);
