@@ -37,8 +37,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 WORKLOADS = {
     "double_pendulum_1M": dict(model="double_pendulum", n=0, batch=1048576, h=1e-3, q_scale=3.0, spl=200),
     # 65536 instances = 512 blocks of 128; 37 steps per launch make 512*37 = 64*296 block-steps: whole rounds of the persistent
-    # task queue on 148 SMs x 2 CTAs (no partial last round)
-    "pin_chain50_64k":    dict(model="pin_chain", n=50, batch=65536, h=1e-3, q_scale=1.0, spl=37),
+    # task queue on 148 SMs x 2 CTAs (no partial last round); the Pin-only kernel runs 3 work groups per SM: 512*111 = 128*444
+    "pin_chain50_64k":    dict(model="pin_chain", n=50, batch=65536, h=1e-3, q_scale=1.0, spl=111),
     "humanoid30_64k":     dict(model="humanoid30", n=0, batch=65536, h=1e-3, q_scale=0.5, spl=37),
     "branched_tree1000_256": dict(model="branched_tree", n=1000, batch=256, h=5e-4, q_scale=0.5, spl=2),
 }

@@ -815,10 +815,14 @@ int sbk_integrator_kernel_name(const sbk_batch* b, char* buf, int cap) {
     else if (b->plan == 5) s = "ctreeRkmKernel";
     else {
         const KArgs& a = b->a; const int m = a.jointMask;
-        int jm, minb = 2, stage;
-        if (a.ltables) { jm = (((m & ~JM_PIN) == 0) ? JM_PIN : JM_MOBILE5) | JM_LOCAL; stage = a.lstageInSmem ? 1 : 0; }
+        int jm, minb = 2, stage, vc = 1;
+        if (a.ltables) {
+            jm = (((m & ~JM_PIN) == 0) ? JM_PIN : JM_MOBILE5) | JM_LOCAL; stage = a.lstageInSmem ? 1 : 0;
+            // (same rule as launchTpi) Pin-only models: three work groups per CTA over one staged copy of the tables
+            if ((m & ~JM_PIN) == 0 && stage && a.ltableBytes + launchTpiRkmLocalPin_m3_workBytes() + 2048 <= (size_t)227*1024) { minb = 1; vc = 3; }
+        }
         else { jm = JM_ALL; stage = a.stageInSmem ? 1 : 0; }
-        s = "tpiKernel<7, " + std::to_string(stage) + ", " + std::to_string(minb) + ", " + std::to_string(jm) + ">";
+        s = "tpiKernel<7, " + std::to_string(stage) + ", " + std::to_string(minb) + ", " + std::to_string(jm) + ", " + std::to_string(vc) + ">";
     }
     std::snprintf(buf, (size_t)cap, "%s", s.c_str());
     return SBK_OK;

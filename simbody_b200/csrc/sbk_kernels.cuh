@@ -70,6 +70,7 @@ cudaError_t launchTpiRkmAll(KernelOp op, const KArgs& a, cudaStream_t stream);  
 // body-frame sweeps (Pin / Slider / Universal / Ball / Free, and Pin only), built for 2 resident CTAs per SM (255 registers; the
 // 3- and 4-CTA builds of sbk_rkm_local.inc measured no gain: shared memory, not registers, limits the occupancy)
 cudaError_t launchTpiRkmLocal_m2(KernelOp op, const KArgs& a, cudaStream_t stream); cudaError_t launchTpiRkmLocalPin_m2(KernelOp op, const KArgs& a, cudaStream_t stream);
+cudaError_t launchTpiRkmLocalPin_m3(KernelOp op, const KArgs& a, cudaStream_t stream); size_t launchTpiRkmLocalPin_m3_workBytes();
 // Register-resident fused plan (serial chains of 1-2 Pin/Slider[/Universal] mobilizers).
 bool fusedPlanSupports(int nb, const int* joints /*[nb]*/);
 cudaError_t launchFusedRkm(const KArgs& a, const int* joints, bool adaptive, cudaStream_t stream);

@@ -485,7 +485,10 @@ SBK_HD void lInUniversal(const ABI& P, const SV zsum, const SV pA, const SV cc, 
 // (cp.async, SASS LDGSTS) into one of two slots of the work item's shared-memory column, consumed with LDS.
 // Layouts are compile-time per mobilizer kind (same functions on the producer and the consumer side).
 //==============================================================================================
-enum { LPF_ROWS = 32 };                     // rows per prefetch slot (two slots per work item)
+#ifndef SBK_LPF_ROWS
+#define SBK_LPF_ROWS 32                     // a translation unit whose mobilizer kinds need fewer rows may shrink the slots
+#endif
+enum { LPF_ROWS = SBK_LPF_ROWS };           // rows per prefetch slot (two slots per work item)
 SBK_HD void lpfCopy(double* dst, const double* src) {
 #if defined(__CUDA_ARCH__)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");

@@ -97,8 +97,11 @@ template <> __device__ __forceinline__ LTables makeTables<LTables>(const unsigne
 // MINB = resident CTAs per SM the register allocation is sized for: 4 (128 registers) suits
 // models made of 1-2 dof mobilizers, 2 (255 registers) models with Ball/Free bodies, whose 3x3 /
 // 6x6 articulated-inertia algebra would otherwise spill (measured: +46% on the humanoid).
-template <int OP, bool STAGE, int MINB, int JMASK = JM_ALL>
-__global__ void __launch_bounds__(TPI_THREADS, MINB) tpiKernel(const KArgs a) {
+// VC > 1 (fixed-step integrator only): one CTA of VC*128 threads runs VC independent 128-thread work groups ("virtual CTAs":
+// own task slot, own named barrier, own work columns) over ONE staged copy of the tables -- more resident warps per SM than
+// VC separate CTAs would fit once every CTA carries its own copy.
+template <int OP, bool STAGE, int MINB, int JMASK = JM_ALL, int VC = 1>
+__global__ void __launch_bounds__(TPI_THREADS*VC, MINB) tpiKernel(const KArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ Ctx sctx;                      // ONE context per CTA, read with LDS by every body step
@@ -117,18 +120,22 @@ __global__ void __launch_bounds__(TPI_THREADS, MINB) tpiKernel(const KArgs a) {
         // slots) then costs nsteps*512/296 rounds instead of nsteps*2.  Steps of one block are
         // ordered through blockDone[block] (release after the step, acquire before the next one);
         // tasks are claimed in order, so the task a CTA waits for is always held by a running CTA.
-        __shared__ long long sTask;          // 64-bit: blocks x steps can exceed 2^31
+        __shared__ long long sTaskV[VC];     // 64-bit: blocks x steps can exceed 2^31
+        const int vc = VC > 1 ? (int)threadIdx.x/TPI_THREADS : 0, tid = VC > 1 ? (int)threadIdx.x - vc*TPI_THREADS : (int)threadIdx.x;
+        long long& sTask = sTaskV[vc];
+        auto groupSync = [&]() { if constexpr (VC > 1) asm volatile("bar.sync %0, %1;" :: "r"(vc + 1), "n"(TPI_THREADS) : "memory"); else __syncthreads(); };
         Ctx lctx; fillCtx(lctx, a, tables, true); useBlockedState(lctx, a);
         const Ctx& c = lctx;
         const TBL T = makeTables<TBL>(tables, a);
-        double* cy = reinterpret_cast<double*>(smem + (STAGE ? tableBytes : 0)) + threadIdx.x;
+        constexpr int rowsPerGroup = LOCAL ? (int)LFCARRY_ROWS : (int)CARRY_ROWS;
+        double* cy = reinterpret_cast<double*>(smem + (STAGE ? tableBytes : 0)) + (size_t)vc*rowsPerGroup*TPI_THREADS + tid;
         RkmWork w;
         w.y = a.yb; w.y0 = a.y0; w.f0 = a.f0; w.fa = a.fa; w.fb = a.fb; w.ys = a.ys;
         w.accuracy = a.accuracy; w.consTol = a.consTol; w.useInfNorm = a.useInfNorm; w.projectEveryStep = a.projectEveryStep;
         const int nblk = (a.N + TPI_THREADS - 1)/TPI_THREADS; const long long total = (long long)nblk*a.nsteps;
 #pragma unroll 1
         for (;;) {
-            if (threadIdx.x == 0) {
+            if (tid == 0) {
                 const long long t = (long long)atomicAdd(reinterpret_cast<unsigned long long*>(a.taskCounter), 1ULL);
                 if (t < total) {
                     const int blk = (int)(t % nblk), step = (int)(t / nblk); int done;
@@ -136,11 +143,11 @@ __global__ void __launch_bounds__(TPI_THREADS, MINB) tpiKernel(const KArgs a) {
                 }
                 sTask = t;
             }
-            __syncthreads();
+            groupSync();
             const long long t = sTask;
             if (t >= total) break;
             const int blk = (int)(t % nblk), step = (int)(t / nblk);
-            const int inst = blk*TPI_THREADS + threadIdx.x;
+            const int inst = blk*TPI_THREADS + tid;
             if (inst < a.N) {
                 if (step == 0) stateToBlocked(c, a, inst);
                 RkmStepResult r;
@@ -161,8 +168,8 @@ __global__ void __launch_bounds__(TPI_THREADS, MINB) tpiKernel(const KArgs a) {
                 if (a.status && !finiteNorm(r.errNorm)) atomicOr(a.status + inst, 1);   // non-finite error norm
             }
             __threadfence();
-            __syncthreads();
-            if (threadIdx.x == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(a.blockDone + blk), "r"(step + 1) : "memory");
+            groupSync();
+            if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(a.blockDone + blk), "r"(step + 1) : "memory");
         }
         return;
     }
@@ -222,14 +229,17 @@ __global__ void __launch_bounds__(TPI_THREADS, MINB) tpiKernel(const KArgs a) {
 }
 
 // Launch one thread-per-instance operation.  JMASK only matters for the integrator kernels.
-template <int OP, int MINB, int JMASK>
+template <int OP, int MINB, int JMASK, int VC = 1>
 cudaError_t launchOp(const KArgs& a, cudaStream_t stream) {
+    static_assert(VC == 1 || OP == OP_RKM, "virtual CTAs exist for the persistent fixed-step kernel only");
     static_assert(TPI_THREADS == SBK_CARRY_STRIDE_DEVICE, "carry columns are laid out for 128-thread CTAs");
     const int grid = (a.N + TPI_THREADS - 1)/TPI_THREADS;
     constexpr bool LOCAL = (OP == OP_RKM || OP == OP_RKM_ADAPT) && (JMASK & JM_LOCAL) != 0;
     const size_t carryBytes = (OP == OP_RKM || OP == OP_RKM_ADAPT) ? (size_t)(LOCAL ? (int)LFCARRY_ROWS : (int)CARRY_ROWS)*TPI_THREADS*sizeof(double) : 0;
-    const bool stage = LOCAL ? a.lstageInSmem != 0 : a.stageInSmem != 0;
-    const size_t smemBytes = (stage ? (LOCAL ? a.ltableBytes : a.tableBytes) : 0) + carryBytes;
+    bool stage = LOCAL ? a.lstageInSmem != 0 : a.stageInSmem != 0;
+    // builds for more than two resident CTAs stage the tables only if that many copies fit next to the work columns
+    if (MINB*VC > 2 && (size_t)MINB*((LOCAL ? a.ltableBytes : a.tableBytes) + VC*carryBytes + 2048) > (size_t)227*1024) stage = false;
+    const size_t smemBytes = (stage ? (LOCAL ? a.ltableBytes : a.tableBytes) : 0) + VC*carryBytes;
     auto go = [&](auto kernel) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
         if (e != cudaSuccess) return e;
@@ -237,19 +247,27 @@ cudaError_t launchOp(const KArgs& a, cudaStream_t stream) {
         if constexpr (OP == OP_RKM) {             // persistent: as many CTAs as are resident at once
             int dev = 0, sms = 0, perSm = 0;
             cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, TPI_THREADS, smemBytes);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, TPI_THREADS*VC, smemBytes);
             if (e != cudaSuccess) return e;
             if (perSm < 1) return cudaErrorLaunchOutOfResources;
-            g = std::min(grid, sms*perSm);
+            g = std::min((grid + VC - 1)/VC, sms*perSm);
             e = cudaMemsetAsync(a.taskCounter, 0, sizeof(int)*(size_t)(2 + grid), stream);   // 64-bit counter + blockDone[grid]
             if (e != cudaSuccess) return e;
         }
-        kernel<<<g, TPI_THREADS, smemBytes, stream>>>(a);
+        kernel<<<g, TPI_THREADS*VC, smemBytes, stream>>>(a);
         return cudaGetLastError();
     };
-    return stage ? go(tpiKernel<OP, true, MINB, JMASK>) : go(tpiKernel<OP, false, MINB, JMASK>);
+    return stage ? go(tpiKernel<OP, true, MINB, JMASK, VC>) : go(tpiKernel<OP, false, MINB, JMASK, VC>);
 }
 // Body of one integrator translation unit (sbk_rkm_<variant>.cu)
+// the fixed-step kernel as ONE CTA of VC work groups per SM (there is no error-controlled build of this form)
+#define SBK_DEFINE_RKM_VARIANT_VC(NAME, VC, JMASK)                                                  \
+    namespace sbkd {                                                                                \
+    cudaError_t NAME(KernelOp op, const KArgs& a, cudaStream_t stream) {                            \
+        if (op == OP_RKM)       return launchOp<OP_RKM, 1, JMASK, VC>(a, stream);                   \
+        return cudaErrorInvalidValue;                                                               \
+    }                                                                                               \
+    size_t NAME##_workBytes() { return (size_t)VC*LFCARRY_ROWS*TPI_THREADS*sizeof(double); } }
 #define SBK_DEFINE_RKM_VARIANT(NAME, MINB, JMASK)                                                   \
     namespace sbkd {                                                                                \
     cudaError_t NAME(KernelOp op, const KArgs& a, cudaStream_t stream) {                            \
