@@ -35,11 +35,11 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 # workload name -> model, size param, per-GPU batch, h, q scale, RKM steps per launch
 WORKLOADS = {
-    "double_pendulum_1M": dict(model="double_pendulum", n=0, batch=1048576, h=1e-3, q_scale=3.0, spl=200),
+    "double_pendulum_1M": dict(model="double_pendulum", n=0, batch=1048576, h=1e-3, q_scale=3.0, spl=200, t_adapt=0.5),
     # 65536 instances = 512 blocks of 128; 37 steps per launch make 512*37 = 64*296 block-steps: whole rounds of the persistent
     # task queue on 148 SMs x 2 CTAs (no partial last round); the Pin-only kernel runs 3 work groups per SM: 512*111 = 128*444
-    "pin_chain50_64k":    dict(model="pin_chain", n=50, batch=65536, h=1e-3, q_scale=1.0, spl=111),
-    "humanoid30_64k":     dict(model="humanoid30", n=0, batch=65536, h=1e-3, q_scale=0.5, spl=37),
+    "pin_chain50_64k":    dict(model="pin_chain", n=50, batch=65536, h=1e-3, q_scale=1.0, spl=111, t_adapt=0.05),
+    "humanoid30_64k":     dict(model="humanoid30", n=0, batch=65536, h=1e-3, q_scale=0.5, spl=37, t_adapt=0.05),
     "branched_tree1000_256": dict(model="branched_tree", n=1000, batch=256, h=5e-4, q_scale=0.5, spl=2),
 }
 F_EVAL = {"PIN": 1180.0, "SLIDER": 1130.0, "UNIVERSAL": 1710.0, "BALL": 2060.0, "FREE": 3800.0, "WELD": 700.0,
@@ -368,7 +368,21 @@ def main():
             lib.sbk_state_touched(bm.handle); sb.capi.check(lib, lib.sbk_realize_acceleration(bm.handle))
         ev1.record(stream); barrier()
         realize_per_s = ntot * nrep / (ev0.elapsed_time(ev1) * 1e-3)
+        # error-controlled form of the same path (Integrator::stepTo, accuracy 1e-3, every instance with its own step size):
+        # accepted and attempted steps per second of this GPU over a short horizon from the same initial states
+        adaptive = None
+        if wl.get("t_adapt"):
+            bm.setState(np.ascontiguousarray(q.T), np.ascontiguousarray(u.T), t=0.0)
+            st_w, at_w, _ = bm.stepTo(0.1 * wl["t_adapt"], accuracy=1e-3, init_step=wl["h"])      # warm-up
+            bm.setState(np.ascontiguousarray(q.T), np.ascontiguousarray(u.T), t=0.0)
+            st_a, at_a, _ = bm.stepTo(wl["t_adapt"], accuracy=1e-3, init_step=wl["h"])
+            del st_w, at_w                  # sbk_set_state re-initialises the integrator: the counters restart from zero
+            ms_a = bm.lastKernelMs()
+            adaptive = {"t_final": wl["t_adapt"], "accuracy": 1e-3, "accepted_steps_per_s": float(st_a.sum()) / (ms_a * 1e-3),
+                        "attempted_steps_per_s": float(at_a.sum()) / (ms_a * 1e-3), "mean_steps": float(st_a.mean()),
+                        "min_steps": int(st_a.min()), "max_steps": int(st_a.max()), "kernel_ms": ms_a, "scope": "this GPU"}
         res = {"name": name, "info": info, "N": N, "ntot": ntot, "spl": spl, "ms_per_step": ms_max / steps, "plan": plan, "kernel": kname,
+               "adaptive": adaptive,
                "value": ntot * spl * steps / (ms_max * 1e-3),
                "e2e": ntot * spl * e2e_steps / (e2e_ms_max * 1e-3),
                "h2d": 8 * ny * N, "d2h": 8 * ny * N, "launches": launches, "kernel_ms_last": kern_ms,
@@ -399,7 +413,8 @@ def main():
             "e2e": {"value": r["e2e"], "unit": "instance-steps/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
             "gpu_launches": r["launches"], "clocks": r["clocks"], "roofline": roofline_of(r),
             "dfma_probe": {"tflops": fp64_peak_tflops, "ms": best, "clocks": clocks_summary(samples0)},
-            "realize_acceleration_per_s": r["realize_per_s"], "non_finite_instances": r["nbad"], "max_err_norm_last_step": r["max_err_norm"]}
+            "realize_acceleration_per_s": r["realize_per_s"], "non_finite_instances": r["nbad"], "max_err_norm_last_step": r["max_err_norm"],
+            "adaptive": r["adaptive"]}
     if r["gathered"]:
         line["final_states_all_gather"] = r["gathered"]
 
@@ -428,7 +443,7 @@ def main():
             roof = roofline_of(rr)
             extra[name] = {"value": rr["value"], "e2e": rr["e2e"], "ms_per_step": rr["ms_per_step"], "fp64_frac": roof["frac"],
                            "achieved_tflops": roof["achieved"], "rkm_steps_per_bench_step": rr["spl"], "instances_per_gpu": rr["N"],
-                           "realize_acceleration_per_s": rr["realize_per_s"], "plan": rr["plan"], "roofline": roof}
+                           "realize_acceleration_per_s": rr["realize_per_s"], "plan": rr["plan"], "roofline": roof, "adaptive": rr["adaptive"]}
         line["workloads"] = extra
 
     if rank == 0:
