@@ -125,26 +125,27 @@ template <class E>
 SBK_HD void fusedRkmAdaptive(const E& e, double* y, const StepLimits& lim, const double tFinal, const int allowInterpolation,
                              const int maxAttempts, const int useInfNorm, AdaptiveState& st, double& lastErr) {
     constexpr int NY = E::NY;
-    int budget = maxAttempts;
-    while (st.t < tFinal && budget > 0) {
-        double y0[NY], f0[NY];
-        bool ok = false, fresh = true; double t1 = st.t;
-        do {
-            bool limited = false;
+    int budget = maxAttempts; bool fresh = true;
+    double y0[NY], f0[NY];
+    const WarpVote vote;
+    for (;;) {                                   // one attempt per trip; see WarpVote (sbk_rkm.cuh)
+        const bool mine = st.t < tFinal && budget > 0;
+        if (!vote(mine)) break;
+        if (mine) {
+            bool limited = false; double t1;
             if (allowInterpolation) t1 = st.t + st.h;
             else if (tFinal < st.t + 0.95*st.h)  { limited = true; t1 = tFinal; }
             else if (tFinal > st.t + 1.001*st.h) t1 = st.t + st.h;
             else t1 = tFinal;
             lastErr = fusedRkmAttempt(e, y0, f0, y, t1 - st.t, useInfNorm, fresh);
-            fresh = false; ++st.attempts; --budget;
-            ok = adjustStepSize(lastErr, lim, limited, st.h);
-        } while (!ok && budget > 0);
-        if (!ok) {
-#pragma unroll
-            for (int i = 0; i < NY; ++i) y[i] = y0[i];
-            break;
+            ++st.attempts; --budget;
+            fresh = adjustStepSize(lastErr, lim, limited, st.h);
+            if (fresh) { st.lastStep = t1 - st.t; st.t = t1; ++st.steps; }
         }
-        st.lastStep = t1 - st.t; st.t = t1; ++st.steps;
+    }
+    if (!fresh) {
+#pragma unroll
+        for (int i = 0; i < NY; ++i) y[i] = y0[i];
     }
 }
 

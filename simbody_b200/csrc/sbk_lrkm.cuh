@@ -209,42 +209,50 @@ SBK_BODY void lFusedOutBody(const Ctx& c, const LBody& bc, const int inst, doubl
 
 // Velocity / inward body steps with an explicit state pointer and velocity buffer (the drivers of sbk_local.cuh use
 // Ctx::q/u and buffer 0).
-template <int JMASK>
-SBK_HD void lInwardSweep(const Ctx& c0, const LTables& T, const int inst, double* cy, const double* S, const int vb) {
+// LOCK (error-controlled kernel): the CTA's threads meet at every body, threads without work (on = false) just keep pace --
+// the warps then share their instruction fetches instead of each streaming the kernel from L2 on its own.
+template <int JMASK, bool LOCK = false>
+SBK_HD void lInwardSweep(const Ctx& c0, const LTables& T, const int inst, double* cy, const double* S, const int vb, const bool on = true) {
     constexpr bool BLK = SBK_DEV_BLK;
     Ctx c = c0; c.q = S; c.u = S + (BLK ? (long long)c.nq*BLK_LANES : (long long)c.nq*c.sStride);
     #define SBK_PFSLOT(par) (cy + (LF_PF + LPF_ROWS*((par) & 1))*SBK_CARRY_STRIDE)
 #pragma unroll 1
     for (int b = c.nb; b >= 1; --b) {          // trip b = nb only requests the first body's rows
+        if constexpr (LOCK) ctaBarrier();
+        if (!on) continue;
         if (b > 1) lPrefetchIn<JMASK, BLK>(c, T.bodies[b - 1], inst, SBK_PFSLOT(b - 1), S, vb);
         lpfCommit(); lpfWait();
         if (b < c.nb) { const LBody& bc = T.bodies[b]; SBK_DISPATCH_LOCAL(JMASK, bc.joint, (lInwardBody<JT>(c, T, bc, inst, cy, vb, SBK_PFSLOT(b)))); }
     }
 }
 // stage 0..4: acceleration sweep of the evaluation at S + next stage state + its velocity data; stage < 0: velocity data of S only
-template <int JMASK>
+template <int JMASK, bool LOCK = false>
 SBK_HD void lFusedOutSweep(const Ctx& c, const LTables& T, const int inst, double* cy, const LRkmWork& w, const double* S,
-                           const int stage, const double h, const int vr, const int vw) {
+                           const int stage, const double h, const int vr, const int vw, const bool on = true) {
     constexpr bool BLK = SBK_DEV_BLK;
     const LStage sg = lstageOf(stage, h, w);
-    SV a0 = zeroSV(); a0.v = mk(-c.gx, -c.gy, -c.gz);
-    lcyStoreSV(cy + LF_V*SBK_CARRY_STRIDE, zeroSV()); lcyStoreSV(cy + LF_A*SBK_CARRY_STRIDE, a0); lcyStoreSV(cy + LF_V2*SBK_CARRY_STRIDE, zeroSV());
-    if (T.bodies[0].flags & BF_STORE_LINK) {     // Ground's links: v = 0 in both buffers, a = -g (gravity as a base acceleration)
-        const CacheRefT<BLK> g = lrecOf<BLK>(c, inst, T.bodies[0].rec);
-        g.stSV(lrV(0) + 6, a0); g.stSV(lrV(0) + vw, zeroSV()); g.stSV(lrV(0) + vr, zeroSV());
+    if (on) {
+        SV a0 = zeroSV(); a0.v = mk(-c.gx, -c.gy, -c.gz);
+        lcyStoreSV(cy + LF_V*SBK_CARRY_STRIDE, zeroSV()); lcyStoreSV(cy + LF_A*SBK_CARRY_STRIDE, a0); lcyStoreSV(cy + LF_V2*SBK_CARRY_STRIDE, zeroSV());
+        if (T.bodies[0].flags & BF_STORE_LINK) {     // Ground's links: v = 0 in both buffers, a = -g (gravity as a base acceleration)
+            const CacheRefT<BLK> g = lrecOf<BLK>(c, inst, T.bodies[0].rec);
+            g.stSV(lrV(0) + 6, a0); g.stSV(lrV(0) + vw, zeroSV()); g.stSV(lrV(0) + vr, zeroSV());
+        }
+        if (stage == 4) { cy[LF_QACC*SBK_CARRY_STRIDE] = 0; cy[LF_UACC*SBK_CARRY_STRIDE] = 0; cy[LF_QUATACC*SBK_CARRY_STRIDE] = 0; }
     }
-    if (stage == 4) { cy[LF_QACC*SBK_CARRY_STRIDE] = 0; cy[LF_UACC*SBK_CARRY_STRIDE] = 0; cy[LF_QUATACC*SBK_CARRY_STRIDE] = 0; }
 #pragma unroll 1
     for (int b = 0; b < c.nb; ++b) {           // trip b = 0 only requests the first body's rows
+        if constexpr (LOCK) ctaBarrier();
+        if (!on) continue;
         if (b + 1 < c.nb) lPrefetchOut<JMASK, BLK>(c, T.bodies[b + 1], inst, SBK_PFSLOT(b + 1), w, S, sg);
         lpfCommit(); lpfWait();
         if (b >= 1) { const LBody& bc = T.bodies[b]; SBK_DISPATCH_LOCAL(JMASK, bc.joint, (lFusedOutBody<JT>(c, bc, inst, cy, w, S, sg, vr, vw, SBK_PFSLOT(b)))); }
     }
     #undef SBK_PFSLOT
 }
-template <int JMASK>
-SBK_HD void lVelSweep(const Ctx& c, const LTables& T, const int inst, double* cy, const LRkmWork& w, const double* S, const int vb) {
-    lFusedOutSweep<JMASK>(c, T, inst, cy, w, S, -1, 0.0, vb, vb);
+template <int JMASK, bool LOCK = false>
+SBK_HD void lVelSweep(const Ctx& c, const LTables& T, const int inst, double* cy, const LRkmWork& w, const double* S, const int vb, const bool on = true) {
+    lFusedOutSweep<JMASK, LOCK>(c, T, inst, cy, w, S, -1, 0.0, vb, vb, on);
 }
 
 // q part of the error norm from the stored estimate (W) and the new state (after a projection changed both)
@@ -337,29 +345,70 @@ SBK_HD RkmStepResult lRkmAttempt(const Ctx& c, const LTables& T, const int inst,
     return res;
 }
 
+// The same attempt for a CTA that votes as a whole (error-controlled kernel): every thread walks every sweep some thread of the
+// CTA needs (the first-evaluation sweeps of threads starting a step, the restart sweep of threads retrying one), threads
+// without work in a sweep (or without work at all: mine = false) keep pace at the per-body barriers.
+template <int JMASK, class VOTE>
+SBK_HD RkmStepResult lRkmAttemptLockstep(const Ctx& c, const LTables& T, const int inst, const LRkmWork& w, const double h, double* cy,
+                                         LRkmState& st, const bool fresh, const bool mine, const VOTE& vote) {
+    constexpr bool BLK = SBK_DEV_BLK;
+    const int ny = c.nq + c.nu;
+    int vb = st.vb;
+    const bool doFresh = mine && fresh, doRetry = mine && !fresh, needVel = doFresh && !st.velValid;
+    if (vote(needVel)) lVelSweep<JMASK, true>(c, T, inst, cy, w, w.Y, vb, needVel);
+    if (vote(doFresh)) {
+        lInwardSweep<JMASK, true>(c, T, inst, cy, w.Y, vb, doFresh);
+        lFusedOutSweep<JMASK, true>(c, T, inst, cy, w, w.Y, 0, h, vb, vb ^ LR_VBUF, doFresh);
+    }
+    if (doFresh) vb ^= LR_VBUF;
+    if (vote(doRetry)) {
+        if (doRetry) for (int i = 0; i < ny; ++i) stS<BLK>(c, inst, w.W, i, ldS<BLK>(c, inst, w.Y, i) + (h/3)*ldS<BLK>(c, inst, w.F0, i));
+        lVelSweep<JMASK, true>(c, T, inst, cy, w, w.W, vb, doRetry);
+    }
+#pragma unroll 1
+    for (int stage = 1; stage < 5; ++stage) {
+        lInwardSweep<JMASK, true>(c, T, inst, cy, w.W, vb, mine);
+        lFusedOutSweep<JMASK, true>(c, T, inst, cy, w, w.W, stage, h, vb, vb ^ LR_VBUF, mine); vb ^= LR_VBUF;
+    }
+    RkmStepResult res; res.errNorm = 0; res.projected = 0;
+    if (mine) {
+        st.vb = vb; st.velValid = true;
+        res = lFinishAttempt<BLK>(c, T, inst, w, cy[LF_QACC*SBK_CARRY_STRIDE], cy[LF_UACC*SBK_CARRY_STRIDE], cy[LF_QUATACC*SBK_CARRY_STRIDE]);
+        if (res.projected) st.velValid = false;
+    }
+    return res;
+}
+
 // Error-controlled stepping with the fused attempt (cf. tpiRkmAdaptive): y1 goes to a second state buffer and the two
 // swap roles when a step is accepted.  On return w.Y points at the buffer holding the advanced state.
-template <int JMASK>
+template <int JMASK, class VOTE = WarpVote>
 SBK_HD void lRkmAdaptive(const Ctx& c, const LTables& T, const int inst, LRkmWork& w, const StepLimits& lim, const double tFinal,
                          const int allowInterpolation, const int maxAttempts, AdaptiveState& ast, double* cy, LRkmState& st,
-                         double& lastErr, int& nproj) {
-    int budget = maxAttempts;
-    while (ast.t < tFinal && budget > 0) {
-        bool fresh = true, ok = false; double t1 = ast.t;
-        do {
-            bool limited = false;
+                         double& lastErr, int& nproj, const bool live = true, const VOTE vote = VOTE()) {
+    int budget = maxAttempts; bool fresh = true;
+    for (;;) {                                   // one attempt per trip; see WarpVote (sbk_rkm.cuh)
+        const bool mine = live && ast.t < tFinal && budget > 0;
+        if (!vote(mine)) break;
+        bool limited = false; double t1 = ast.t;
+        if (mine) {
             if (allowInterpolation) t1 = ast.t + ast.h;
             else if (tFinal < ast.t + 0.95*ast.h)  { limited = true; t1 = tFinal; }
             else if (tFinal > ast.t + 1.001*ast.h) t1 = ast.t + ast.h;
             else t1 = tFinal;
-            const RkmStepResult r = lRkmAttempt<JMASK>(c, T, inst, w, t1 - ast.t, cy, st, fresh);
-            fresh = false; ++ast.attempts; --budget; nproj += r.projected; lastErr = r.errNorm;
-            ok = adjustStepSize(r.errNorm, lim, limited, ast.h);
-        } while (!ok && budget > 0);
-        if (!ok) { st.velValid = false; break; }        // out of budget inside a failing step: Y still holds y0
-        double* t = w.Y; w.Y = w.Ynext; w.Ynext = t;   // accept: y1 becomes the state
-        ast.lastStep = t1 - ast.t; ast.t = t1; ++ast.steps;
+        }
+        RkmStepResult r; r.errNorm = 0; r.projected = 0;
+        if constexpr (VOTE::CTA) r = lRkmAttemptLockstep<JMASK>(c, T, inst, w, t1 - ast.t, cy, st, fresh, mine, vote);
+        else if (mine) r = lRkmAttempt<JMASK>(c, T, inst, w, t1 - ast.t, cy, st, fresh);
+        if (mine) {
+            ++ast.attempts; --budget; nproj += r.projected; lastErr = r.errNorm;
+            fresh = adjustStepSize(r.errNorm, lim, limited, ast.h);
+            if (fresh) {                                  // accept: y1 becomes the state
+                double* t = w.Y; w.Y = w.Ynext; w.Ynext = t;
+                ast.lastStep = t1 - ast.t; ast.t = t1; ++ast.steps;
+            }
+        }
     }
+    if (!fresh) st.velValid = false;             // out of budget inside a failing step: Y still holds y0
 }
 
 } // namespace sbkd

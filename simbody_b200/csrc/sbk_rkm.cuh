@@ -206,31 +206,69 @@ SBK_HD RkmStepResult tpiRkmStep(const Ctx& c, const TBL& T, const int inst, cons
 // reference's default) steps are never shortened to hit tFinal, so the advanced state ends at
 // t >= tFinal; without it the last step lands on tFinal (hWasArtificiallyLimited logic).
 struct AdaptiveState { double t, h, lastStep; int steps, attempts; };
-template <bool LEAN, int JMASK = JM_ALL, class TBL = Tables>
+// The error-controlled loops make ONE attempt per trip and every lane of the warp keeps tripping (predicated off once its
+// instance is done) until no lane has work left: the lanes reconverge at each attempt (WarpVote below).  With the reference's nested
+// `while (t < tFinal) do attempt while (!ok)` form a lane that had rejected a step never rejoined the others before the end of
+// the outer loop -- the warp then ran its lanes' attempts one group after the other (measured: 25x slower on the humanoid).
+// vote(mine) -> "some thread of the group still has work": the group is the warp (WarpVote) or the whole CTA (CtaVote, every
+// thread of the CTA must call it).  The CTA form also keeps the CTA's warps in the same region of a 300 KB instruction stream:
+// with the warps of an SM spread over it, 80% of the stall samples of the humanoid's kernel were instruction-fetch misses (ncu).
+SBK_HD void ctaBarrier() {
+#ifdef __CUDA_ARCH__
+    __syncthreads();
+#endif
+}
+struct WarpVote {
+    static constexpr bool CTA = false;
+    unsigned lanes;
+    SBK_HD WarpVote() : lanes(1u) {
+#ifdef __CUDA_ARCH__
+        lanes = __activemask();
+#endif
+    }
+    SBK_HD bool operator()(const bool mine) const {
+#ifdef __CUDA_ARCH__
+        return __any_sync(lanes, mine) != 0;
+#else
+        return mine;
+#endif
+    }
+};
+struct CtaVote {
+    static constexpr bool CTA = true;
+    SBK_HD bool operator()(const bool mine) const {
+#ifdef __CUDA_ARCH__
+        return __syncthreads_or(mine ? 1 : 0) != 0;
+#else
+        return mine;
+#endif
+    }
+};
+template <bool LEAN, int JMASK = JM_ALL, class TBL = Tables, class VOTE = WarpVote>
 SBK_HD void tpiRkmAdaptive(const Ctx& c, const TBL& T, const int inst, const RkmWork& w, const StepLimits& lim, const double tFinal,
                            const int allowInterpolation, const int maxAttempts, AdaptiveState& st, double* cy,
-                           double& lastErr, int& nproj) {
+                           double& lastErr, int& nproj, const bool live = true, const VOTE vote = VOTE()) {
     constexpr bool BLK = LEAN && SBK_DEV_BLK;
-    int budget = maxAttempts;
-    while (st.t < tFinal && budget > 0) {
-        bool fresh = true, ok = false; double t1 = st.t;
-        do {
-            bool limited = false;
+    int budget = maxAttempts; bool fresh = true;
+    for (;;) {                                   // one attempt per trip; see WarpVote
+        const bool mine = live && st.t < tFinal && budget > 0;
+        if (!vote(mine)) break;
+        if (mine) {
+            bool limited = false; double t1;
             if (allowInterpolation) t1 = st.t + st.h;
             else if (tFinal < st.t + 0.95*st.h)  { limited = true; t1 = tFinal; }
             else if (tFinal > st.t + 1.001*st.h) t1 = st.t + st.h;
             else t1 = tFinal;
             const double hTry = t1 - st.t;
             const RkmStepResult r = tpiRkmStep<LEAN, JMASK>(c, T, inst, w, hTry, cy, fresh);
-            fresh = false; ++st.attempts; --budget; nproj += r.projected; lastErr = r.errNorm;
-            ok = adjustStepSize(r.errNorm, lim, limited, st.h);
-        } while (!ok && budget > 0);
-        if (!ok) {   // out of budget inside a failing step: put y0 back, report through the status word
-#pragma unroll 8
-            for (int i = 0; i < c.nq + c.nu; ++i) stS<BLK>(c, inst, w.y, i, ldS<BLK>(c, inst, w.y0, i));
-            break;
+            ++st.attempts; --budget; nproj += r.projected; lastErr = r.errNorm;
+            fresh = adjustStepSize(r.errNorm, lim, limited, st.h);
+            if (fresh) { st.lastStep = t1 - st.t; st.t = t1; ++st.steps; }
         }
-        st.lastStep = t1 - st.t; st.t = t1; ++st.steps;
+    }
+    if (!fresh) {    // out of budget inside a failing step: put y0 back, report through the status word
+#pragma unroll 8
+        for (int i = 0; i < c.nq + c.nu; ++i) stS<BLK>(c, inst, w.y, i, ldS<BLK>(c, inst, w.y0, i));
     }
 }
 

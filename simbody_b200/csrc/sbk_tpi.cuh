@@ -173,8 +173,10 @@ __global__ void __launch_bounds__(TPI_THREADS*VC, MINB) tpiKernel(const KArgs a)
         }
         return;
     }
-    const int inst = blockIdx.x*blockDim.x + threadIdx.x;
-    if (inst >= a.N) return;
+    const int inst0 = blockIdx.x*blockDim.x + threadIdx.x;
+    const bool live = inst0 < a.N;              // the error-controlled kernel votes CTA-wide: its surplus threads stay, predicated off
+    if (!live && OP != OP_RKM_ADAPT) return;
+    const int inst = live ? inst0 : a.N - 1;
     // API kernels read the context from shared memory; the integrator kernels keep it as a local whose
     // members are kernel parameters (constant bank operands) or one add away from them -- reading
     // it from shared memory cost a generic load plus descriptor moves per access (ncu).
@@ -208,19 +210,20 @@ __global__ void __launch_bounds__(TPI_THREADS*VC, MINB) tpiKernel(const KArgs a)
         RkmWork w;
         w.y = a.yb; w.y0 = a.y0; w.f0 = a.f0; w.fa = a.fa; w.fb = a.fb; w.ys = a.ys;
         w.accuracy = a.accuracy; w.consTol = a.consTol; w.useInfNorm = a.useInfNorm; w.projectEveryStep = a.projectEveryStep;
-        stateToBlocked(c, a, inst);
+        if (live) stateToBlocked(c, a, inst);
         StepLimits lim; lim.accuracy = a.accuracy; lim.minStep = a.minStep; lim.maxStep = a.maxStep;
         AdaptiveState st; st.t = a.tcur[inst]; st.h = a.hcur[inst]; st.lastStep = a.lastStep[inst]; st.steps = 0; st.attempts = 0;
         double lastErr = a.errNorm[inst]; int nproj = 0;
         if constexpr (LOCAL) {
             LRkmWork lw = fusedWork(a); lw.Ynext = a.y0;             // y1 goes to the second state buffer; the two swap on acceptance
             LRkmState ls; ls.vb = 0; ls.velValid = false;
-            lRkmAdaptive<JMASK>(c, T, inst, lw, lim, a.tFinal, a.allowInterp, a.maxAttempts, st, cy, ls, lastErr, nproj);
-            stateFromBlocked(c, a, inst, lw.Y);
+            lRkmAdaptive<JMASK, CtaVote>(c, T, inst, lw, lim, a.tFinal, a.allowInterp, a.maxAttempts, st, cy, ls, lastErr, nproj, live);
+            if (live) stateFromBlocked(c, a, inst, lw.Y);
         } else {
-            tpiRkmAdaptive<true, JMASK>(c, T, inst, w, lim, a.tFinal, a.allowInterp, a.maxAttempts, st, cy, lastErr, nproj);
-            stateFromBlocked(c, a, inst);
+            tpiRkmAdaptive<true, JMASK, TBL, CtaVote>(c, T, inst, w, lim, a.tFinal, a.allowInterp, a.maxAttempts, st, cy, lastErr, nproj, live);
+            if (live) stateFromBlocked(c, a, inst);
         }
+        if (!live) return;
         a.tcur[inst] = st.t; a.hcur[inst] = st.h; a.lastStep[inst] = st.lastStep;
         a.stepsTaken[inst] += st.steps; a.attempts[inst] += st.attempts;
         a.errNorm[inst] = lastErr; a.projCount[inst] += nproj;
