@@ -35,6 +35,7 @@ struct sbk_batch {
     KArgs a;                      // device pointers + constants
     unsigned char* dTables = nullptr; unsigned char* dLTables = nullptr; unsigned char* dLTablesLevel = nullptr;
     int clusterSize = 0;          // plan 5: CTAs per cluster
+    int clustersPerGroup = 1;     // plan 5: clusters that share one group of 32 instances
     double *dOpA = nullptr, *dOpB = nullptr, *dOpF = nullptr, *dOpOut = nullptr, *dScratch = nullptr;
     size_t scratchDoubles = 0;
     int stage = ST_EMPTY; bool abiValid = false, accelValid = false;
@@ -253,13 +254,28 @@ static int configurePlan(sbk_batch* b, int plan) {
             b->clusterSize = ctreeMaxClusterSize();
             { const char* e4 = getenv("SBK_CLUSTER"); if (e4 && atoi(e4) > 0) b->clusterSize = std::min(b->clusterSize, atoi(e4)); }   // tuning override
             if (b->clusterSize < 1) return fail(SBK_ERR_CUDA, "plan 5: the device cannot host a thread-block cluster of the integrator kernel");
-            const int nwarps = b->clusterSize*8;
+            // Two clusters per group of 32 instances when the device holds all of them at once (they wait for each other at
+            // a barrier in global memory): the subtrees below the cut are half as deep.  C5: 8 groups x 2 clusters x 8 CTAs.
+            b->clustersPerGroup = 1;
+            { const int groups = (n + 31)/32; int resident = ctreeMaxActiveClusters(b->clusterSize);
+              if (b->clusterSize == 8 && !getenv("SBK_CLUSTER")) {
+                  // 128 warps per group: 2 clusters of 8 CTAs, else 4 clusters of 4 (a B200 holds 15 clusters of 8 but 36 of 4)
+                  if (2*groups <= resident) b->clustersPerGroup = 2;
+                  else if (4*groups <= ctreeMaxActiveClusters(4)) { b->clusterSize = 4; b->clustersPerGroup = 4; resident = ctreeMaxActiveClusters(4); }
+              }
+              const char* e7 = getenv("SBK_CLUSTERS_PER_GROUP");                     // tuning override (never beyond what is resident)
+              if (e7 && atoi(e7) > 0) {
+                  if (b->clustersPerGroup > 1 && atoi(e7) == 1) { b->clusterSize = 8; resident = ctreeMaxActiveClusters(8); }
+                  if (atoi(e7)*groups <= resident) b->clustersPerGroup = atoi(e7);
+              }
+              if (getenv("SBK_VERBOSE")) std::fprintf(stderr, "sbk plan 5: %d groups, cluster of %d CTAs, %d clusters resident at once, %d per group\n", groups, b->clusterSize, resident, b->clustersPerGroup); }
+            const int nwarps = b->clusterSize*8*b->clustersPerGroup;
             // the levels above the cut run on ALL warps of the cluster with barrier.cluster between levels (measured +19% over running
             // them on the first CTA's eight warps with __syncthreads: 6 rounds instead of 10 on the C5 tree)
-            int topWarps = nwarps, cutWarps = nwarps;
+            int topWarps = nwarps/b->clustersPerGroup, cutWarps = nwarps;
             { const char* e5 = getenv("SBK_TOPWARPS"); if (e5 && atoi(e5) > 0) topWarps = atoi(e5); }      // tuning overrides
             { const char* e6 = getenv("SBK_CUTWARPS"); if (e6 && atoi(e6) > 0) cutWarps = atoi(e6); }
-            const sbk::TreeCut cut = sbk::cutTreeForWarps(*t, nwarps, topWarps, cutWarps);
+            const sbk::TreeCut cut = sbk::cutTreeForWarps(*t, nwarps, topWarps, cutWarps, b->clustersPerGroup);
             const size_t soBytes = pad16(cut.lists.size()*sizeof(int)), ssBytes = pad16(cut.listStart.size()*sizeof(int));
             std::vector<unsigned char> lv(lblob.size() + soBytes + ssBytes, 0);
             std::memcpy(lv.data(), lblob.data(), lblob.size());
@@ -274,7 +290,7 @@ static int configurePlan(sbk_batch* b, int plan) {
             a.ltablesLevel = b->dLTablesLevel;
             if (a.treeScratch) cudaFree(a.treeScratch);
             a.treeScratch = nullptr;
-            CUDA_TRY(cudaMalloc(&a.treeScratch, ctreeScratchDoubles(n, 16)*sizeof(double)));
+            CUDA_TRY(cudaMalloc(&a.treeScratch, ctreeScratchDoubles(n, b->clusterSize*b->clustersPerGroup)*sizeof(double)));
         }
       } }
     if (plan == 5 && !a.ltablesLevel) return fail(SBK_ERR_ARG, "plan 5 needs a model made of Pin / Slider / Universal / Ball / Free mobilizers (quaternion mode)");
@@ -703,7 +719,7 @@ int sbk_rkm_step(sbk_batch* b, double h, int nsteps, const sbk_rkm_opts* opts, d
         } else if (b->plan == 4) {
             CUDA_TRY(launchGlRkm(a, b->stream)); b->launches++;
         } else if (b->plan == 5) {
-            CUDA_TRY(launchCtreeRkm(a, b->clusterSize, b->stream)); b->launches++;
+            CUDA_TRY(launchCtreeRkm(a, b->clusterSize, b->clustersPerGroup, b->stream)); b->launches++;
         } else if (int rc = launch(b, OP_RKM)) return rc;
         CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
         invalidate(b);

@@ -34,12 +34,14 @@ __device__ __forceinline__ void fillCtxTree(Ctx& c, const KArgs& a) {
 }
 
 template <int JMASK>
-__global__ void __launch_bounds__(CT_THREADS, 1) ctreeRkmKernel(const KArgs a, const int CS) {
+__global__ void __launch_bounds__(CT_THREADS, 1) ctreeRkmKernel(const KArgs a, const int CS, const int K) {
     extern __shared__ __align__(16) unsigned char smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = (int)cluster.block_rank();
-    const int iw = blockIdx.x / CS;                                  // instance warp owned by this cluster
-    const int lane = threadIdx.x & 31, wc = crank*(CT_THREADS/32) + (threadIdx.x >> 5), nw = CS*(CT_THREADS/32);
+    // K clusters share one group of 32 instances (K > 1 only when all the grid's clusters are resident at once: they wait for
+    // each other): cluster kc of the group holds warps kc*CS*8 .. of the group's K*CS*8
+    const int cid = blockIdx.x / CS, iw = cid / K, kc = cid - iw*K;
+    const int lane = threadIdx.x & 31, wc = (kc*CS + crank)*(CT_THREADS/32) + (threadIdx.x >> 5), nw = K*CS*(CT_THREADS/32);
     const int inst = iw*32 + lane; const bool active = inst < a.N;
     Ctx c; fillCtxTree(c, a);
     LTables T; T.bodies = reinterpret_cast<const LBody*>(a.ltablesLevel); T.children = reinterpret_cast<const int*>(a.ltablesLevel + a.lchildrenOff);
@@ -56,14 +58,31 @@ __global__ void __launch_bounds__(CT_THREADS, 1) ctreeRkmKernel(const KArgs a, c
     const int ny = a.nq + a.nu;
     // barrier.cluster.arrive (release) / wait (acquire) order the global-memory hand-over rows between the warps of the cluster;
     // every such row is written with st.cg and read with ld.cg (L2), never through a possibly stale L1 line
-    auto groupSync = [&]() { cluster.sync(); };
-    auto topSync = [&]() { __syncthreads(); };
-    // per-cluster scratch in global memory: partial error sums [nw][3][32] and the group-uniform "some instance projected" flag
+    // per-group scratch in global memory: partial error sums [nw][3][32], the group-uniform "some instance projected" flag and the
+    // arrival counter of the barrier between the group's clusters (zeroed by the launcher)
     double* part = a.treeScratch + (size_t)iw*((size_t)nw*3*32 + 32);
     int* flag = reinterpret_cast<int*>(part + (size_t)nw*3*32);
+    unsigned* xcount = reinterpret_cast<unsigned*>(flag) + 4;
+    unsigned xphase = 0;
+    // barrier of the group's K clusters: every thread publishes its global writes (membar.gl), the cluster meets, one thread per
+    // cluster arrives on the counter (release) and waits for the K arrivals of this phase (acquire), the cluster meets again
+    auto crossSync = [&]() {
+        __threadfence();
+        cluster.sync();
+        ++xphase;
+        if (crank == 0 && threadIdx.x == 0) {
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(xcount) : "memory");
+            unsigned seen;
+            do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(xcount) : "memory"); } while (seen < xphase*(unsigned)K);
+        }
+        cluster.sync();
+    };
+    auto groupSync = [&](const bool cross) { if (cross && K > 1) crossSync(); else cluster.sync(); };
+    auto allSync = [&]() { if (K > 1) crossSync(); else { __threadfence(); cluster.sync(); } };
+    auto topSync = [&]() { __syncthreads(); };
     auto reduce = [&](double& q, double& u, double& qt) {
-        part[((size_t)wc*3 + 0)*32 + lane] = q; part[((size_t)wc*3 + 1)*32 + lane] = u; part[((size_t)wc*3 + 2)*32 + lane] = qt;
-        __threadfence(); cluster.sync();
+        __stcg(part + ((size_t)wc*3 + 0)*32 + lane, q); __stcg(part + ((size_t)wc*3 + 1)*32 + lane, u); __stcg(part + ((size_t)wc*3 + 2)*32 + lane, qt);
+        allSync();
         if (wc == 0) {                              // fixed summation order: deterministic
             double s0 = 0, s1 = 0, s2 = 0;
             for (int k = 0; k < nw; ++k) {
@@ -76,7 +95,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) ctreeRkmKernel(const KArgs a, c
     // state into the blocked layout, Ground's link rows
     if (active) for (int i = wc; i < ny; i += nw) a.yb[stateIndex<true>(c, inst, i)] = __ldcg(a.y + (long long)i*a.N + inst);
     if (active && wc == 0) lLevelGround(c, T, inst);
-    __threadfence(); cluster.sync();
+    allSync();
     int vb = 0, par = 0; bool velValid = false;
     double err = 0; int nproj = 0;
 #pragma unroll 1
@@ -84,10 +103,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) ctreeRkmKernel(const KArgs a, c
         const RkmStepResult r = lListStep<JMASK>(c, T, lstIn, lstOut, B, inst, active, lane, cy, w, a.h, vb, velValid, wc, par, topSync, groupSync, reduce);
         if (wc == 0) {
             const unsigned any = __ballot_sync(0xffffffffu, active && r.projected);
-            if (lane == 0) *flag = any != 0;
+            if (lane == 0) __stcg(flag, any != 0 ? 1 : 0);
             if (active) { err = r.errNorm; nproj += r.projected; if (a.status && !finiteNorm(r.errNorm)) atomicOr(a.status + inst, 1); }
         }
-        __threadfence(); cluster.sync();
+        allSync();
         velValid = __ldcg(flag) == 0;
     }
     lpfWaitAll();
@@ -100,18 +119,39 @@ __global__ void __launch_bounds__(CT_THREADS, 1) ctreeRkmKernel(const KArgs a, c
 // scratch doubles per instance warp for a cluster of CS CTAs
 size_t ctreeScratchDoubles(int N, int CS) { return (size_t)((N + 31)/32)*((size_t)CS*(CT_THREADS/32)*3*32 + 32); }
 
-cudaError_t launchCtreeRkm(const KArgs& a, int CS, cudaStream_t stream) {
+static cudaError_t ctreeConfig(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int nclusters, int CS, cudaStream_t stream, bool cooperative = false) {
     auto kernel = ctreeRkmKernel<JM_MOBILE5 | JM_LOCAL>;
     const size_t smemBytes = (size_t)LFCARRY_ROWS*CT_THREADS*sizeof(double) + (size_t)(CT_THREADS/32)*LT_BODY_SLOTS*sizeof(LBody);
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
     if (e != cudaSuccess) return e;
     if (CS > 8) { e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); if (e != cudaSuccess) return e; }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(((a.N + 31)/32)*CS)); cfg.blockDim = dim3(CT_THREADS); cfg.dynamicSmemBytes = smemBytes; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cfg = cudaLaunchConfig_t();
+    cfg.gridDim = dim3((unsigned)(nclusters*CS)); cfg.blockDim = dim3(CT_THREADS); cfg.dynamicSmemBytes = smemBytes; cfg.stream = stream;
     attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = (unsigned)CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, a, CS);
+    // clusters that wait for each other: a cooperative launch starts only when the whole grid is resident
+    if (cooperative) { attr[1].id = cudaLaunchAttributeCooperative; attr[1].val.cooperative = 1; cfg.numAttrs = 2; }
+    return cudaSuccess;
+}
+// How many clusters of CS CTAs of the integrator kernel the device holds at once (0 on error).
+int ctreeMaxActiveClusters(int CS) {
+    cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[2];
+    if (ctreeConfig(cfg, attr, 1, CS, 0) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, ctreeRkmKernel<JM_MOBILE5 | JM_LOCAL>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// K clusters per group of 32 instances (the task lists in a.ltablesLevel are cut for K*CS*8 warps).  K > 1 needs every cluster
+// of the grid resident at once (ctreeMaxActiveClusters): the caller checks.
+cudaError_t launchCtreeRkm(const KArgs& a, int CS, int K, cudaStream_t stream) {
+    const int groups = (a.N + 31)/32;
+    cudaError_t e = cudaMemsetAsync(a.treeScratch, 0, ctreeScratchDoubles(a.N, CS*K)*sizeof(double), stream);   // barrier counters
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[2];
+    e = ctreeConfig(cfg, attr, groups*K, CS, stream, K > 1);
+    if (e != cudaSuccess) return e;
+    return cudaLaunchKernelEx(&cfg, ctreeRkmKernel<JM_MOBILE5 | JM_LOCAL>, a, CS, K);
 }
 // Largest portable cluster size (8, 4, 2, 1) of which at least one cluster can be resident on this device.
 int ctreeMaxClusterSize() {

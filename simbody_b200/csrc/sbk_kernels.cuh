@@ -85,7 +85,8 @@ cudaError_t launchGl(KernelOp op, const KArgs& a, cudaStream_t stream);
 // Integrator::initialize's forced projection: normalise every quaternion of y, count one projection per instance.
 cudaError_t launchInitProject(const KArgs& a, cudaStream_t stream);
 // Plan 5 (cluster-level-parallel, sbk_ctree.cu): fixed-step integrator; CS = CTAs per cluster (one cluster per 32 instances).
-cudaError_t launchCtreeRkm(const KArgs& a, int CS, cudaStream_t stream);
+cudaError_t launchCtreeRkm(const KArgs& a, int CS, int K, cudaStream_t stream);
+int ctreeMaxActiveClusters(int CS);
 int ctreeMaxClusterSize();
 size_t ctreeScratchDoubles(int N, int CS);
 // Ground record (identity transform, zero velocity/acceleration) for every instance.

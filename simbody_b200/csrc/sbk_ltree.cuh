@@ -19,7 +19,9 @@
 namespace sbkd {
 
 // list entry: body index (0 = no body, only the barriers) | flags
-enum { LT_BODY_MASK = 0x00ffffff, LT_TSYNC = 1 << 28, LT_GSYNC = 1 << 29, LT_END = 1 << 30 };
+// LT_TSYNC: barrier of the warp's CTA; LT_GSYNC: barrier of the warp's cluster; LT_XSYNC: barrier of ALL the clusters that share the
+// group of instances (a group may be spread over several clusters: sbk_ctree.cu)
+enum { LT_BODY_MASK = 0x00ffffff, LT_XSYNC = 1 << 27, LT_TSYNC = 1 << 28, LT_GSYNC = 1 << 29, LT_END = 1 << 30 };
 struct LTaskLists { const int* entries; const int* start; };      // start[dir*nw + w] .. : entries of warp w, dir 0 = inward, 1 = outward; LT_END terminated
 
 enum { LT_BODY_SLOTS = 3 };
@@ -76,7 +78,7 @@ SBK_HD void lListSweep(const Ctx& c0, const LTables& T, const int* lst, const LB
             else { SBK_DISPATCH_LOCAL(JMASK, bc.joint, (lInwardBody<JT>(c, T, bc, inst, cy, vr, SBK_LT_PFSLOT(par)))); }
         }
         if (e0 & LT_TSYNC) topSync();
-        if (e0 & LT_GSYNC) groupSync();
+        if (e0 & (LT_GSYNC | LT_XSYNC)) groupSync((e0 & LT_XSYNC) != 0);
         ++par; ++k;
         e0 = e1; e1 = e2; e2 = (e1 & LT_END) ? e1 : lst[k + 2];
         lwarpSync();                                               // every lane is done with slot k-1 before it is refilled

@@ -87,7 +87,9 @@ static void compileLocalTables(sbk_topology& t) {
     }
 }
 
-TreeCut cutTreeForWarps(const sbk_topology& t, int nwarps, int topWarps, int cutWidth) {
+// nclusters > 1: the nwarps warps belong to that many clusters (consecutive ranges); the levels above the cut run on the FIRST
+// cluster's warps (cluster barrier between levels) and the two parts of a sweep meet at a barrier of all the clusters (LT_XSYNC).
+TreeCut cutTreeForWarps(const sbk_topology& t, int nwarps, int topWarps, int cutWidth, int nclusters) {
     if (cutWidth <= 0) cutWidth = nwarps;
     TreeCut r; r.bodies = t.lbodiesLevel; r.cutLevel = t.nlevels; r.subStart.assign(1, 0);
     for (int l = 1; l < t.nlevels; ++l) if (t.levelStart[l + 1] - t.levelStart[l] >= cutWidth) { r.cutLevel = l; break; }
@@ -116,8 +118,9 @@ TreeCut cutTreeForWarps(const sbk_topology& t, int nwarps, int topWarps, int cut
             lb.flags = f;
         }
     // task lists (sbk_ltree.cuh): per warp, inward then outward
-    topWarps = std::max(1, std::min(topWarps, nwarps));
-    const int levelSync = topWarps > 8 ? sbkd::LT_GSYNC : sbkd::LT_TSYNC;      // more than one CTA's warps on the top levels: group barrier between levels
+    const int perCluster = nwarps/std::max(1, nclusters);
+    topWarps = std::max(1, std::min(topWarps, nclusters > 1 ? perCluster : nwarps));
+    const int levelSync = (topWarps > 8 || nclusters > 1) ? sbkd::LT_GSYNC : sbkd::LT_TSYNC;      // more than one CTA's warps on the top levels: group barrier between levels
     r.listStart.assign(2*(size_t)nwarps, 0);
     const bool haveTop = r.cutLevel > 1, haveSub = nsub > 0;
     for (int dir = 0; dir < 2; ++dir)
@@ -128,17 +131,21 @@ TreeCut cutTreeForWarps(const sbk_topology& t, int nwarps, int topWarps, int cut
                 if (dir) for (int k = r.subStart[s]; k < r.subStart[s + 1]; ++k) sub.push_back(r.subOrder[k]);
                 else     for (int k = r.subStart[s + 1] - 1; k >= r.subStart[s]; --k) sub.push_back(r.subOrder[k]);
             }
-            if ((w < topWarps || levelSync == sbkd::LT_GSYNC) && haveTop)
+            const bool inTopCluster = nclusters <= 1 || w < perCluster;
+            if ((w < topWarps || levelSync == sbkd::LT_GSYNC) && haveTop && inTopCluster)
                 for (int l = dir ? 1 : r.cutLevel - 1; dir ? l < r.cutLevel : l >= 1; l += dir ? 1 : -1) {
                     const size_t before = top.size();
                     if (w < topWarps) for (int i = t.levelStart[l] + w; i < t.levelStart[l + 1]; i += topWarps) top.push_back(t.levelOrder[i]);
                     if (top.size() == before) top.push_back(0);            // no body of this level for this warp: barrier only
                     top.back() |= levelSync;
                 }
-            // the group barrier separates the two parts: inward subtrees | top, outward top | subtrees
+            // a barrier separates the two parts: inward subtrees | top, outward top | subtrees
             auto& first = dir ? top : sub; auto& second = dir ? sub : top;
-            // (with group barriers between the top levels the last / first of them already separates the parts)
-            if (haveTop && haveSub && !(levelSync == sbkd::LT_GSYNC && dir == 1)) { if (first.empty()) first.push_back(0); first.back() |= sbkd::LT_GSYNC; }
+            if (nclusters > 1) {
+                if (haveTop && haveSub) { if (first.empty()) first.push_back(0); first.back() = (first.back() & ~sbkd::LT_GSYNC) | sbkd::LT_XSYNC; }
+            }
+            // (one cluster with group barriers between the top levels: the last / first of them already separates the parts)
+            else if (haveTop && haveSub && !(levelSync == sbkd::LT_GSYNC && dir == 1)) { if (first.empty()) first.push_back(0); first.back() |= sbkd::LT_GSYNC; }
             r.lists.insert(r.lists.end(), first.begin(), first.end());
             r.lists.insert(r.lists.end(), second.begin(), second.end());
             r.lists.push_back(sbkd::LT_END); r.lists.push_back(sbkd::LT_END); r.lists.push_back(sbkd::LT_END);

@@ -46,5 +46,5 @@ void compileTopology(const ModelSpec& spec, sbk_topology& out);
 // lists / listStart: the per-warp task lists of sbk_ltree.cuh (listStart[dir*nwarps + w], dir 0 inward, 1 outward); the first
 // topWarps warps also run the levels above the cut.
 struct TreeCut { int cutLevel = 0; std::vector<int> subOrder, subStart, lists, listStart; std::vector<sbkd::LBody> bodies; };
-TreeCut cutTreeForWarps(const sbk_topology& t, int nwarps, int topWarps, int cutWidth = 0);   // cutWidth: minimum width of the cut level (default nwarps)
+TreeCut cutTreeForWarps(const sbk_topology& t, int nwarps, int topWarps, int cutWidth = 0, int nclusters = 1);   // cutWidth: minimum width of the cut level (default nwarps)
 }

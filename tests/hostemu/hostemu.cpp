@@ -259,7 +259,7 @@ int emu_step(const char* text, int N, const double* in, double* out, double h, i
                 lLevelGround(c, LT, k);
                 RkmStepResult r; r.errNorm = 0; r.projected = 0;
                 for (int s = 0; s < nsteps; ++s) {
-                    r = lListStep<JM_MOBILE5>(c, LT, lin.data(), lout.data(), BS, k, true, 0, cy, lw, h, vb, velValid, 0, par, []() {}, []() {}, [](double&, double&, double&) {});
+                    r = lListStep<JM_MOBILE5>(c, LT, lin.data(), lout.data(), BS, k, true, 0, cy, lw, h, vb, velValid, 0, par, []() {}, [](bool) {}, [](double&, double&, double&) {});
                     velValid = !r.projected; nproj += r.projected;
                 }
                 double* o = out + (size_t)k*(ny+2);
