@@ -48,6 +48,7 @@ struct KArgs {
     double* lastStep;   // [N] size of the last accepted step
     int* stepsTaken;    // [N] accumulated
     int* attempts;      // [N] accumulated
+    int roundSync;      // fixed-step integrator: the CTAs take their tasks round-robin and meet at a grid barrier before every round (set by launchOp)
     int* taskCounter;   // fixed-step integrator task queue: a 64-bit next-task counter (also plan 4's barrier counter); blockDone = taskCounter + 2
     int* blockDone;     // steps completed per block of 128 instances (this launch)
     int* lflags;        // [N] fused body-frame integrator: 1 = the velocity data left by the previous step are current

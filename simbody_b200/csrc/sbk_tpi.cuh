@@ -114,12 +114,17 @@ __global__ void __launch_bounds__(TPI_THREADS*VC, MINB) tpiKernel(const KArgs a)
     if (!INTEG && threadIdx.x == 0) fillCtx(sctx, a, tables, false);
     __syncthreads();
     if constexpr (OP == OP_RKM) {
-        // Fixed-step integrator: PERSISTENT CTAs (the grid is what fits the machine at once) pull
-        // (block of 128 instances, step) tasks from a global counter, step-major.  A batch whose
-        // CTA count is not a multiple of the resident slots (65536 instances = 512 CTAs on 296
-        // slots) then costs nsteps*512/296 rounds instead of nsteps*2.  Steps of one block are
-        // ordered through blockDone[block] (release after the step, acquire before the next one);
-        // tasks are claimed in order, so the task a CTA waits for is always held by a running CTA.
+        // Fixed-step integrator: PERSISTENT CTAs (the grid is what fits the machine at once) work through
+        // the (block of 128 instances, step) tasks step-major.  A batch whose CTA count is not a multiple of
+        // the resident slots (65536 instances = 512 CTAs on 296 slots) then costs nsteps*512/296 rounds
+        // instead of nsteps*2.  Steps of one block are ordered through blockDone[block] (release after
+        // the step, acquire before the next one); tasks are taken in order, so the task a CTA waits for
+        // is always held by a running CTA.  Two ways of taking them: a global counter (work groups of
+        // the Pin-only kernel), or -- roundSync, 128-thread CTAs -- round-robin with a grid barrier before
+        // every round: the CTAs then stay in the same phase of the step, which is what the memory system
+        // likes (humanoid: every launch 49.7 ms; with the counter 49.2 or 53.8 ms depending on how the CTAs
+        // happened to drift apart, and a deliberate start offset made every launch slow).  The grid is
+        // launched cooperatively, so all its CTAs are resident.
         __shared__ long long sTaskV[VC];     // 64-bit: blocks x steps can exceed 2^31
         const int vc = VC > 1 ? (int)threadIdx.x/TPI_THREADS : 0, tid = VC > 1 ? (int)threadIdx.x - vc*TPI_THREADS : (int)threadIdx.x;
         long long& sTask = sTaskV[vc];
@@ -133,11 +138,26 @@ __global__ void __launch_bounds__(TPI_THREADS*VC, MINB) tpiKernel(const KArgs a)
         w.y = a.yb; w.y0 = a.y0; w.f0 = a.f0; w.fa = a.fa; w.fb = a.fb; w.ys = a.ys;
         w.accuracy = a.accuracy; w.consTol = a.consTol; w.useInfNorm = a.useInfNorm; w.projectEveryStep = a.projectEveryStep;
         const int nblk = (a.N + TPI_THREADS - 1)/TPI_THREADS; const long long total = (long long)nblk*a.nsteps;
+        long long myRound = 0;
 #pragma unroll 1
         for (;;) {
             if (tid == 0) {
-                const long long t = (long long)atomicAdd(reinterpret_cast<unsigned long long*>(a.taskCounter), 1ULL);
-                if (t < total) {
+                long long t;
+                if (VC == 1 && a.roundSync) {
+                    // arrive on the 64-bit counter, wait for the whole grid
+                    unsigned long long* bar = reinterpret_cast<unsigned long long*>(a.taskCounter);
+                    if (myRound > 0) {
+                        __threadfence();
+                        atomicAdd(bar, 1ULL);
+                        const unsigned long long target = (unsigned long long)myRound*gridDim.x;
+                        unsigned long long seen;
+                        do { asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(bar) : "memory"); } while (seen < target);
+                    }
+                    t = myRound*gridDim.x + blockIdx.x; ++myRound;
+                    if ((myRound - 1)*(long long)gridDim.x >= total) t = total; else if (t >= total) t = -1;   // -1: idle this round, keep the barrier
+                } else
+                t = (long long)atomicAdd(reinterpret_cast<unsigned long long*>(a.taskCounter), 1ULL);
+                if (t >= 0 && t < total) {
                     const int blk = (int)(t % nblk), step = (int)(t / nblk); int done;
                     do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(a.blockDone + blk) : "memory"); if (done < step) __nanosleep(200); } while (done < step);
                 }
@@ -146,6 +166,7 @@ __global__ void __launch_bounds__(TPI_THREADS*VC, MINB) tpiKernel(const KArgs a)
             groupSync();
             const long long t = sTask;
             if (t >= total) break;
+            if (t < 0) continue;
             const int blk = (int)(t % nblk), step = (int)(t / nblk);
             const int inst = blk*TPI_THREADS + tid;
             if (inst < a.N) {
@@ -257,8 +278,18 @@ cudaError_t launchOp(const KArgs& a, cudaStream_t stream) {
             e = cudaMemsetAsync(a.taskCounter, 0, sizeof(int)*(size_t)(2 + grid), stream);   // 64-bit counter + blockDone[grid]
             if (e != cudaSuccess) return e;
         }
-        kernel<<<g, TPI_THREADS*VC, smemBytes, stream>>>(a);
-        return cudaGetLastError();
+        if constexpr (OP == OP_RKM && VC == 1) {
+            KArgs k = a; k.roundSync = g < grid ? 1 : 0;      // every CTA owns its block when the whole batch is resident: nothing to meet for
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)g); cfg.blockDim = dim3(TPI_THREADS); cfg.dynamicSmemBytes = smemBytes; cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
+            cfg.attrs = attr; cfg.numAttrs = k.roundSync ? 1 : 0;
+            return cudaLaunchKernelEx(&cfg, kernel, k);
+        } else {
+            kernel<<<g, TPI_THREADS*VC, smemBytes, stream>>>(a);
+            return cudaGetLastError();
+        }
     };
     return stage ? go(tpiKernel<OP, true, MINB, JMASK, VC>) : go(tpiKernel<OP, false, MINB, JMASK, VC>);
 }

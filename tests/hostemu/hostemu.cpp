@@ -373,4 +373,66 @@ int emu_model_text(const char* name, int n, char* buf, int cap) {
     } catch (const std::exception& ex) { std::fprintf(stderr, "emu: %s\n", ex.what()); return -1; }
 }
 
+// Schedule check of the plan-5 task lists (topology.cpp: cutTreeForWarps) by simulation: warps run their lists, a barrier entry
+// holds a warp until every warp of its scope (CTA of 8 warps / cluster / all clusters) waits at a barrier of the same kind.
+// Returns 0 if every body is processed exactly once per direction, a child always strictly before (inward) / after (outward)
+// its parent with a barrier or the same warp in between, and no warp is left waiting; else a positive error code.
+int emu_cut_check(const char* text, int nwarps, int topWarps, int cutWidth, int nclusters) {
+    try {
+        sbk_topology t; sbk::compileTopology(sbk::fromText(text), t);
+        const sbk::TreeCut cut = sbk::cutTreeForWarps(t, nwarps, topWarps, cutWidth, nclusters);
+        const int perCluster = nwarps/std::max(1, nclusters);
+        for (int dir = 0; dir < 2; ++dir) {
+            std::vector<int> pos(nwarps), doneRound(t.nb, -1), doneWarp(t.nb, -1), waiting(nwarps, 0);
+            for (int w = 0; w < nwarps; ++w) pos[w] = cut.listStart[(size_t)dir*nwarps + w];
+            std::vector<char> finished(nwarps, 0);
+            doneRound[0] = -2; doneWarp[0] = -2;       // Ground: always available
+            for (int round = 0; ; ++round) {
+                bool progress = false;
+                for (int w = 0; w < nwarps; ++w) {
+                    if (finished[w] || waiting[w]) continue;
+                    for (;;) {
+                        const int e = cut.lists[pos[w]];
+                        if (e & sbkd::LT_END) { finished[w] = 1; progress = true; break; }
+                        ++pos[w]; progress = true;
+                        const int b = e & sbkd::LT_BODY_MASK;
+                        if (b) {
+                            if (b >= t.nb || doneRound[b] != -1) return 2;                    // unknown body / processed twice
+                            const sbkd::LBody& lb = t.lbodies[b];
+                            if (dir == 0) {
+                                for (int j = 0; j < lb.nchild; ++j) {
+                                    const int ch = t.children[lb.childStart + j];
+                                    if (doneRound[ch] == -1) return 3;                        // child not done yet
+                                    if (doneRound[ch] == round && doneWarp[ch] != w) return 4; // concurrent with another warp's child
+                                }
+                            } else {
+                                const int pa = lb.parent;
+                                if (doneRound[pa] == -1) return 3;
+                                if (doneRound[pa] == round && doneWarp[pa] != w) return 4;
+                            }
+                            doneRound[b] = round; doneWarp[b] = w;
+                        }
+                        const int f = e & (sbkd::LT_TSYNC | sbkd::LT_GSYNC | sbkd::LT_XSYNC);
+                        if (f) { waiting[w] = (f & sbkd::LT_XSYNC) ? 3 : (f & sbkd::LT_GSYNC) ? 2 : 1; break; }
+                    }
+                }
+                // release the barriers whose whole scope has arrived
+                auto release = [&](int lo, int hi, int kind) {
+                    for (int w = lo; w < hi; ++w) if (waiting[w] != kind) return;
+                    for (int w = lo; w < hi; ++w) waiting[w] = 0;
+                    progress = true;
+                };
+                for (int w0 = 0; w0 < nwarps; w0 += 8) release(w0, std::min(nwarps, w0 + 8), 1);
+                for (int w0 = 0; w0 < nwarps; w0 += perCluster) release(w0, std::min(nwarps, w0 + perCluster), 2);
+                release(0, nwarps, 3);
+                bool all = true; for (int w = 0; w < nwarps; ++w) all = all && finished[w];
+                if (all) break;
+                if (!progress) return 5;                                                       // a warp waits for ever
+            }
+            for (int b = 1; b < t.nb; ++b) if (doneRound[b] == -1) return 6;                   // body never processed
+        }
+        return 0;
+    } catch (const std::exception& ex) { std::fprintf(stderr, "emu: %s\n", ex.what()); return 1; }
+}
+
 } // extern "C"

@@ -300,3 +300,16 @@ def test_two_point_elements_lower_by_probing(built):
     text = HostEmu().model_text("twopoint7")
     assert RefDriver().lower(text) == text
     assert sum(line.startswith("tp") for line in text.splitlines()) == 3
+
+
+@pytest.mark.parametrize("model,n", [("branched_tree", 1000), ("branched_tree", 200), ("branched_tree", 37), ("humanoid30", 0),
+                                     ("pin_chain", 12), ("mixed7", 0)])
+@pytest.mark.parametrize("sched", [(64, 64, 0, 1), (64, 8, 0, 1), (128, 64, 0, 2), (128, 32, 0, 4), (16, 8, 0, 2), (8, 8, 4, 1)])
+def test_cluster_task_lists_are_complete_ordered_and_deadlock_free(model, n, sched):
+    """Plan 5's schedule is data (topology.cpp: cutTreeForWarps): simulate the warps and their CTA / cluster / cross-cluster
+    barriers and check that every body runs once per sweep, after its children (inward) / its parent (outward) with a barrier
+    or the same warp in between, and that no warp is left waiting -- for one, two and four clusters per group of instances."""
+    emu = HostEmu()
+    info = ModelInfo(emu.model_text(model, n))
+    nwarps, top, cutw, k = sched
+    assert emu.cut_check(info, nwarps, top, cutw, k) == 0
