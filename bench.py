@@ -40,7 +40,7 @@ WORKLOADS = {
     # task queue on 148 SMs x 2 CTAs (no partial last round); the Pin-only kernel runs 3 work groups per SM: 512*111 = 128*444
     "pin_chain50_64k":    dict(model="pin_chain", n=50, batch=65536, h=1e-3, q_scale=1.0, spl=111, t_adapt=0.05),
     "humanoid30_64k":     dict(model="humanoid30", n=0, batch=65536, h=1e-3, q_scale=0.5, spl=37, t_adapt=0.05),
-    "branched_tree1000_256": dict(model="branched_tree", n=1000, batch=256, h=5e-4, q_scale=0.5, spl=2),
+    "branched_tree1000_256": dict(model="branched_tree", n=1000, batch=256, h=5e-4, q_scale=0.5, spl=8),
 }
 F_EVAL = {"PIN": 1180.0, "SLIDER": 1130.0, "UNIVERSAL": 1710.0, "BALL": 2060.0, "FREE": 3800.0, "WELD": 700.0,
           "TRANSLATION": 1800.0, "CYLINDER": 1650.0, "PLANAR": 1950.0, "GIMBAL": 2300.0}

@@ -292,7 +292,7 @@ int sbk_get_status(sbk_batch*, int32_t* status /*[N]*/, int64_t* n_bad);
 /* Number of kernels launched by this batch since creation (for bench accounting).       */
 int64_t sbk_launch_count(const sbk_batch*);
 /* Name of the fixed-step integrator kernel the batch's plan launches, spelled like a profiler's demangled name
- * (e.g. "tpiKernel<7, 1, 2, 1073741886>"): lets a bench line be matched with a committed ncu capture. */
+ * (e.g. "tpiKernel<7, 1, 2, 1073741886, 1>"): lets a bench line be matched with a committed ncu capture. */
 int sbk_integrator_kernel_name(const sbk_batch*, char* buf, int cap);
 /* Device time in ms of the kernels launched by the last sbk_rkm_step call, measured with
  * CUDA events on the batch's stream (0 if events disabled).                              */

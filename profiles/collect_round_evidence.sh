@@ -13,7 +13,7 @@ done
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${R}_launches_bench_default.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra-workloads > gpurun_out/launch_bench.log 2>&1
 for wl in double_pendulum_1M pin_chain50_64k humanoid30_64k branched_tree1000_256; do
   # steps per launch as in bench.py for the persistent-queue kernels (whole rounds: no tail), so per-step durations are comparable
-  spl=37; N=65536; [ $wl = pin_chain50_64k ] && spl=111; [ $wl = double_pendulum_1M ] && spl=20 && N=1048576; [ $wl = branched_tree1000_256 ] && spl=2 && N=256
+  spl=37; N=65536; [ $wl = pin_chain50_64k ] && spl=111; [ $wl = double_pendulum_1M ] && spl=20 && N=1048576; [ $wl = branched_tree1000_256 ] && spl=8 && N=256
   SBK_SPL=$spl timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'tpiKernel|fusedRkmKernel|glRkmKernel|ctreeRkmKernel' -s 1 -c 1 -o /tmp/prof_$wl python tools/quick_perf.py $wl > gpurun_out/prof_$wl.log 2>&1
   { echo "# capture: workload=$wl N=$N rkm_steps_per_launch=$spl command=tools/quick_perf.py (ncu --set full --clock-control none, second launch)"; python profiles/summarize_ncu.py /tmp/prof_$wl.ncu-rep; } > gpurun_out/${R}_prof_$wl.txt
   python profiles/ncu_sass.py /tmp/prof_$wl.ncu-rep 25 > gpurun_out/${R}_prof_${wl}_sass.txt

@@ -440,8 +440,8 @@ def test_branched_tree_1000_matches_golden(plan):
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
-@pytest.mark.parametrize("name,n,batch,h,nsteps,qs", [("double_pendulum", 0, 1048576, 1e-3, 200, 3.0), ("pin_chain", 50, 65536, 1e-3, 10, 1.0),
-                                                      ("humanoid30", 0, 65536, 1e-3, 10, 0.5), ("branched_tree", 1000, 256, 5e-4, 2, 0.5)])
+@pytest.mark.parametrize("name,n,batch,h,nsteps,qs", [("double_pendulum", 0, 1048576, 1e-3, 200, 3.0), ("pin_chain", 50, 65536, 1e-3, 111, 1.0),
+                                                      ("humanoid30", 0, 65536, 1e-3, 37, 0.5), ("branched_tree", 1000, 256, 5e-4, 8, 0.5)])
 def test_full_size_batches_match_live_reference(name, n, batch, h, nsteps, qs):
     """The four BASELINE batches at the size and the steps-per-launch bench.py runs (several rounds of the persistent
     task queue / the whole cooperative grid): a strided sample of 64+ instances -- first, last, spread over every

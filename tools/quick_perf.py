@@ -31,5 +31,5 @@ def run(name, spl, reps=3, plan=None, batch=None):
 if __name__ == "__main__":
     names = sys.argv[1:] or ["pin_chain50_64k", "humanoid30_64k"]
     for n in names:
-        spl = int(os.environ.get("SBK_SPL", 0)) or {"double_pendulum_1M": 100, "pin_chain50_64k": 8, "humanoid30_64k": 8, "branched_tree1000_256": 2}[n]
+        spl = int(os.environ.get("SBK_SPL", 0)) or {"double_pendulum_1M": 100, "pin_chain50_64k": 8, "humanoid30_64k": 8, "branched_tree1000_256": 8}[n]
         run(n, spl)
