@@ -145,20 +145,47 @@ def ncu_fields(workload, live_kernel, live_ms_per_launch, N, spl, plan):
     return out
 
 
-def sample_clocks(stop, out):
-    """nvidia-smi clocks line of the profiling recipe, sampled during the timed region."""
+def sample_clocks(stop, out, devices=None):
+    """Clocks and throttle reasons of the job's GPUs (the profiling recipe's clocks line), sampled during the timed region.
+    In-process through NVML (one light query per GPU every 0.2 s, rank 0 only): eight ranks each spawning nvidia-smi five times a
+    second kept the driver busy enough to delay the other ranks' kernel launches by milliseconds."""
+    if devices is not None and len(devices) == 0:
+        return
+    devices = devices or [int(os.environ.get("LOCAL_RANK", "0"))]
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hs = [pynvml.nvmlDeviceGetHandleByIndex(i) for i in devices]
+        R = pynvml
+        bits = [getattr(R, "nvmlClocksEventReasonHwSlowdown", getattr(R, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+                getattr(R, "nvmlClocksEventReasonHwThermalSlowdown", getattr(R, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+                getattr(R, "nvmlClocksEventReasonSwThermalSlowdown", getattr(R, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+                getattr(R, "nvmlClocksEventReasonSwPowerCap", getattr(R, "nvmlClocksThrottleReasonSwPowerCap", 0x4))]
+        reasons_of = getattr(R, "nvmlDeviceGetCurrentClocksEventReasons", None) or R.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not stop.is_set():
+            for h in hs:
+                try:
+                    sm = R.nvmlDeviceGetClockInfo(h, R.NVML_CLOCK_SM); mx = R.nvmlDeviceGetMaxClockInfo(h, R.NVML_CLOCK_SM)
+                    m = reasons_of(h)
+                    out.append([str(float(sm)), str(float(mx))] + ["Active" if (m & b) else "Not Active" for b in bits])
+                except Exception:
+                    pass
+            stop.wait(0.2)
+        return
+    except Exception:
+        pass
     q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-    dev = os.environ.get("LOCAL_RANK", "0")
     while not stop.is_set():
         try:
-            r = subprocess.run(["nvidia-smi", "-i", dev, "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+            r = subprocess.run(["nvidia-smi", "-i", ",".join(str(d) for d in devices), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
                                capture_output=True, text=True, timeout=5)
             if r.returncode == 0 and r.stdout.strip():
-                out.append([x.strip() for x in r.stdout.strip().splitlines()[0].split(",")])
+                for line in r.stdout.strip().splitlines():
+                    out.append([x.strip() for x in line.split(",")])
         except Exception:
             pass
-        stop.wait(0.2)
+        stop.wait(0.5)
 
 
 def clocks_summary(samples):
@@ -269,7 +296,7 @@ def main():
     lib = sb.load_library()
     # FP64 roofline denominator: measured DFMA throughput on this GPU (MEASURED_PEAKS.json has none), with the SM clock under it
     stop0, samples0 = threading.Event(), []
-    th0 = threading.Thread(target=sample_clocks, args=(stop0, samples0)); th0.start()
+    th0 = threading.Thread(target=sample_clocks, args=(stop0, samples0) if rank == 0 else (stop0, samples0, [])); th0.start()
     msd = ctypes.c_double(); iters = 20000; best = 1e30
     for _ in range(8):
         sb.capi.check(lib, lib.sbk_dfma_probe(local, 148 * 8, 256, iters, ctypes.byref(msd))); best = min(best, msd.value)
@@ -301,6 +328,10 @@ def main():
         sb.capi.check(lib, lib.sbk_set_state(bm.handle, dp(qh), dp(uh), None))
 
         def barrier():
+            # drain this rank's streams BEFORE the collective: the NCCL barrier kernel otherwise slips in between two queued
+            # launches of the persistent integrator kernel (which fills every SM) and holds the next one back until the slowest
+            # rank has reached ITS next kernel boundary -- seen at 8 GPUs as one extra kernel time on some ranks
+            torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
@@ -311,7 +342,8 @@ def main():
         barrier()
         launches0 = bm.launchCount()
         stop, samples = threading.Event(), []
-        th = threading.Thread(target=sample_clocks, args=(stop, samples)); th.start()
+        # rank 0 samples every GPU of the job (one node: local ranks = device indices); the other ranks run no sampler
+        th = threading.Thread(target=sample_clocks, args=(stop, samples, list(range(world)) if rank == 0 else [])); th.start()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(steps):
@@ -341,7 +373,12 @@ def main():
         e2e_s = time.perf_counter() - t0
 
         tmax = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+        per_rank = None
         if world > 1:
+            mine = torch.tensor([ms / steps, kern_ms], dtype=torch.float64, device="cuda")
+            allr = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            per_rank = {"ms_per_step": [round(float(x[0]), 3) for x in allr], "kernel_ms_last_launch": [round(float(x[1]), 3) for x in allr]}
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         ms_max, e2e_ms_max = float(tmax[0]), float(tmax[1])
         # end-of-run statistics and (once) the final states: the only data-plane collectives of the job (NCCL)
@@ -387,7 +424,7 @@ def main():
                "e2e": ntot * spl * e2e_steps / (e2e_ms_max * 1e-3),
                "h2d": 8 * ny * N, "d2h": 8 * ny * N, "launches": launches, "kernel_ms_last": kern_ms,
                "flop_per_inst_step": flop, "bytes_per_inst_step": byts, "realize_per_s": realize_per_s, "clocks": clocks_summary(samples),
-               "nbad": int(nbad), "max_err_norm": max_err, "gathered": gathered}
+               "nbad": int(nbad), "max_err_norm": max_err, "gathered": gathered, "per_rank": per_rank}
         bm.close(); topo.close()
         return res
 
@@ -417,6 +454,8 @@ def main():
             "adaptive": r["adaptive"]}
     if r["gathered"]:
         line["final_states_all_gather"] = r["gathered"]
+    if r["per_rank"]:
+        line["per_rank"] = r["per_rank"]
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from _harness import have_ref

@@ -284,7 +284,8 @@ cudaError_t launchOp(const KArgs& a, cudaStream_t stream) {
             cfg.gridDim = dim3((unsigned)g); cfg.blockDim = dim3(TPI_THREADS); cfg.dynamicSmemBytes = smemBytes; cfg.stream = stream;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
-            cfg.attrs = attr; cfg.numAttrs = k.roundSync ? 1 : 0;
+            static const bool noCoop = []() { const char* e = getenv("SBK_NOCOOP"); return e && atoi(e); }();   // diagnostics: plain launch
+            cfg.attrs = attr; cfg.numAttrs = (k.roundSync && !noCoop) ? 1 : 0;
             return cudaLaunchKernelEx(&cfg, kernel, k);
         } else {
             kernel<<<g, TPI_THREADS*VC, smemBytes, stream>>>(a);

@@ -10,7 +10,7 @@ python - <<PY
 import json
 for f in ("gpurun_out/r2_scale_weak_n$N.json", "gpurun_out/r2_scale_strong_c2_n$N.json", "gpurun_out/r2_scale_weak_humanoid_n$N.json"):
     try:
-        d = json.load(open(f))
+        d = json.loads([l for l in open(f).read().splitlines() if l.startswith('{')][-1])
         print(f, "n_gpus", d["n_gpus"], "scaling", d["scaling"], "value %.4g e2e %.4g" % (d["value"], d["e2e"]["value"]), "inst/gpu", d["config"]["instances_per_gpu"], "gather", d.get("final_states_all_gather"))
         for k, v in d.get("workloads", {}).items(): print("   ", k, "value %.4g e2e %.4g frac %.3f" % (v["value"], v["e2e"], v["fp64_frac"]))
     except Exception as e:
