@@ -286,7 +286,15 @@ cudaError_t launchOp(const KArgs& a, cudaStream_t stream) {
             attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
             static const bool noCoop = []() { const char* e = getenv("SBK_NOCOOP"); return e && atoi(e); }();   // diagnostics: plain launch
             cfg.attrs = attr; cfg.numAttrs = (k.roundSync && !noCoop) ? 1 : 0;
-            return cudaLaunchKernelEx(&cfg, kernel, k);
+            cudaError_t le = cudaLaunchKernelEx(&cfg, kernel, k);
+            if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorNotSupported) {
+                // the whole grid cannot be resident right now (shared GPU, MPS limits): fall back to the task counter, which needs no
+                // co-residency
+                cudaGetLastError();
+                k.roundSync = 0; cfg.numAttrs = 0;
+                le = cudaLaunchKernelEx(&cfg, kernel, k);
+            }
+            return le;
         } else {
             kernel<<<g, TPI_THREADS*VC, smemBytes, stream>>>(a);
             return cudaGetLastError();
