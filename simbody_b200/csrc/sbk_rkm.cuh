@@ -116,15 +116,19 @@ SBK_HD void rkmCombine(const Ctx& c, const int inst, const int ny, const double*
 // The caller's Ctx must have q = w.y, u = w.y + nq*sStride and null qerr / fmobOut / FbodyOut.
 // The derivative evaluation behind a table type: Tables = ground-frame sweeps (FULL records or LEAN reversible
 // kinematics), LTables = body-frame sweeps (sbk_local.cuh).
-template <bool LEAN, int JMASK> SBK_HD void rkmEval(const Ctx& c, const Tables& T, const int inst, double* cy, double* qd, double* ud) {
-    tpiEvalDerivatives<LEAN, JMASK>(c, T, inst, cy, qd, ud, nullptr);
+template <bool LEAN, int JMASK, bool LOCK = false> SBK_HD void rkmEval(const Ctx& c, const Tables& T, const int inst, double* cy, double* qd, double* ud, const bool on = true) {
+    tpiEvalDerivatives<LEAN, JMASK, false, LOCK>(c, T, inst, cy, qd, ud, nullptr, on);
 }
-template <bool LEAN, int JMASK> SBK_HD void rkmEval(const Ctx& c, const LTables& T, const int inst, double* cy, double* qd, double* ud) {
-    lEvalDerivatives<JMASK>(c, T, inst, cy, qd, ud);
+template <bool LEAN, int JMASK, bool LOCK = false> SBK_HD void rkmEval(const Ctx& c, const LTables& T, const int inst, double* cy, double* qd, double* ud, const bool on = true) {
+    static_assert(!LOCK, "the body-frame integrator has its own lockstep attempt (sbk_lrkm.cuh)");
+    if (on) lEvalDerivatives<JMASK>(c, T, inst, cy, qd, ud);
 }
 
-template <bool LEAN, int JMASK = JM_ALL, class TBL = Tables>
-SBK_HD RkmStepResult tpiRkmStep(const Ctx& c, const TBL& T, const int inst, const RkmWork& w, const double h, double* cy, const bool fresh = true) {
+// LOCK (CTA-voting error-controlled kernel): every thread of the CTA walks every evaluation some thread needs -- `anyFresh` = some
+// thread starts a step and needs f0 -- and meets the others at every body; mine = false: nothing to do but keep pace.
+template <bool LEAN, int JMASK = JM_ALL, class TBL = Tables, bool LOCK = false>
+SBK_HD RkmStepResult tpiRkmStep(const Ctx& c, const TBL& T, const int inst, const RkmWork& w, const double h, double* cy, const bool fresh = true,
+                                const bool mine = true, const bool anyFresh = true) {
     constexpr bool BLK = LEAN && SBK_DEV_BLK;
     const int nq = c.nq, ny = c.nq + c.nu;
     const long long uoff = BLK ? (long long)nq*BLK_LANES : (long long)nq*c.sStride;   // u rows follow the q rows
@@ -139,7 +143,9 @@ SBK_HD RkmStepResult tpiRkmStep(const Ctx& c, const TBL& T, const int inst, cons
         double* fdst = stage == 0 ? w.f0 : (stage == 3 ? w.fb : w.fa);
         // stage 0: f0 = f(y0), AbstractIntegratorRep.cpp:393 realizeStateDerivatives at the start of a step;
         // a retry after a failed attempt keeps the saved y0 / f0
-        if (stage > 0 || fresh) rkmEval<LEAN, JMASK>(c, T, inst, cy, fdst, fdst + uoff);
+        if constexpr (LOCK) { if (stage > 0 || anyFresh) rkmEval<LEAN, JMASK, true>(c, T, inst, cy, fdst, fdst + uoff, mine && (stage > 0 || fresh)); }
+        else if (stage > 0 || fresh) rkmEval<LEAN, JMASK>(c, T, inst, cy, fdst, fdst + uoff);
+        if (!mine) continue;
         if (stage == 0) {
             if (fresh) rkmCombine<BLK, 2>(c, inst, ny, w.y, w.f0, nullptr, nullptr, nullptr, [&](int i, const double* v) {
                            stS<BLK>(c, inst, w.y0, i, v[0]);
@@ -164,7 +170,8 @@ SBK_HD RkmStepResult tpiRkmStep(const Ctx& c, const TBL& T, const int inst, cons
         }
     }
 
-    RkmStepResult res; res.projected = 0;
+    RkmStepResult res; res.projected = 0; res.errNorm = 0;
+    if (!mine) return res;
     res.errNorm = rkmErrorNorm<BLK>(c, T, inst, w);
     // attemptDAEStep: project only if errNorm <= 2^4 * accuracy (AbstractIntegratorRep.cpp:165-166)
     if (c.nquat > 0 && !(res.errNorm > 16.0*w.accuracy)) {
@@ -253,14 +260,18 @@ SBK_HD void tpiRkmAdaptive(const Ctx& c, const TBL& T, const int inst, const Rkm
     for (;;) {                                   // one attempt per trip; see WarpVote
         const bool mine = live && st.t < tFinal && budget > 0;
         if (!vote(mine)) break;
+        bool limited = false; double t1 = st.t;
         if (mine) {
-            bool limited = false; double t1;
             if (allowInterpolation) t1 = st.t + st.h;
             else if (tFinal < st.t + 0.95*st.h)  { limited = true; t1 = tFinal; }
             else if (tFinal > st.t + 1.001*st.h) t1 = st.t + st.h;
             else t1 = tFinal;
-            const double hTry = t1 - st.t;
-            const RkmStepResult r = tpiRkmStep<LEAN, JMASK>(c, T, inst, w, hTry, cy, fresh);
+        }
+        const double hTry = t1 - st.t;
+        RkmStepResult r; r.errNorm = 0; r.projected = 0;
+        if constexpr (VOTE::CTA) { const bool anyFresh = vote(mine && fresh); r = tpiRkmStep<LEAN, JMASK, TBL, true>(c, T, inst, w, hTry, cy, fresh, mine, anyFresh); }
+        else if (mine) r = tpiRkmStep<LEAN, JMASK>(c, T, inst, w, hTry, cy, fresh);
+        if (mine) {
             ++st.attempts; --budget; nproj += r.projected; lastErr = r.errNorm;
             fresh = adjustStepSize(r.errNorm, lim, limited, st.h);
             if (fresh) { st.lastStep = t1 - st.t; st.t = t1; ++st.steps; }

@@ -1271,7 +1271,13 @@ template <bool WITH_COR, bool CB = false> SBK_HD void tpiOutward(const Ctx& c, i
 // One full derivative evaluation = System::realize(Acceleration) for the lowered system.
 //   LEAN = false: FULL records (every cache entry a getter may ask for); cy unused
 //   LEAN = true : integrator path, reversible kinematics (see above); cy = the work item's carry column
-template <bool LEAN, int JMASK = JM_ALL, bool CB = false> SBK_HD void tpiEvalDerivatives(const Ctx& c, const Tables& T, int inst, double* cy, double* qdotDst, double* udotDst, double* qddDst) {
+// LOCK (error-controlled kernel, LEAN only): the CTA's threads meet at every body; a thread with on = false just keeps pace.
+SBK_HD void sweepBarrier() {
+#ifdef __CUDA_ARCH__
+    __syncthreads();
+#endif
+}
+template <bool LEAN, int JMASK = JM_ALL, bool CB = false, bool LOCK = false> SBK_HD void tpiEvalDerivatives(const Ctx& c, const Tables& T, int inst, double* cy, double* qdotDst, double* udotDst, double* qddDst, const bool on = true) {
     if constexpr (!LEAN) {
         tpiKinematics<CB>(c, inst, qdotDst);
         twoPointPass<CB>(c, inst);
@@ -1287,10 +1293,12 @@ template <bool LEAN, int JMASK = JM_ALL, bool CB = false> SBK_HD void tpiEvalDer
         volatile int* bslot = reinterpret_cast<volatile int*>(cy + CY_LOOP*SBK_CARRY_STRIDE);
         #define SBK_PARK(b)   (*bslot = (b))
         #define SBK_UNPARK(b) ((b) = *bslot)
-        cyStoreOut(cy, identity3(), zero3(), z0);                                 // Ground's link for body 1
-        preloadCoords<JMASK>(c, inst, T.bodies[1], SBK_PRE(0));
+        if (on) { cyStoreOut(cy, identity3(), zero3(), z0);                       // Ground's link for body 1
+                  preloadCoords<JMASK>(c, inst, T.bodies[1], SBK_PRE(0)); }
 #pragma unroll 1
         for (int b = 1; b < c.nb; ++b) {
+            if constexpr (LOCK) sweepBarrier();
+            if (!on) continue;
             const BodyConst& bc = T.bodies[b];
             preloadCoords<JMASK>(c, inst, T.bodies[b + 1 < c.nb ? b + 1 : c.nb - 1], SBK_PRE(b));       // after the last body: the first of the inward sweep
             preloadWait();
@@ -1300,6 +1308,8 @@ template <bool LEAN, int JMASK = JM_ALL, bool CB = false> SBK_HD void tpiEvalDer
         }
 #pragma unroll 1
         for (int b = c.nb - 1; b >= 1; --b) {
+            if constexpr (LOCK) sweepBarrier();
+            if (!on) continue;
             const BodyConst& bc = T.bodies[b];
             preloadCoords<JMASK>(c, inst, T.bodies[b > 1 ? b - 1 : 1], SBK_PRE(b - 1));                  // after body 1: the first of the outward sweep
             preloadWait();
@@ -1307,9 +1317,11 @@ template <bool LEAN, int JMASK = JM_ALL, bool CB = false> SBK_HD void tpiEvalDer
             SBK_DISPATCH_JOINT_M(JMASK, bc.joint, (leanInwardBody<JT>(c, T, bc, b, inst, cy, SBK_PRE(b))));
             SBK_UNPARK(b);
         }
-        cyStoreOut(cy, identity3(), zero3(), z0); cyStoreA(cy + CY_A*SBK_CARRY_STRIDE, z0);
+        if (on) { cyStoreOut(cy, identity3(), zero3(), z0); cyStoreA(cy + CY_A*SBK_CARRY_STRIDE, z0); }
 #pragma unroll 1
         for (int b = 1; b < c.nb; ++b) {
+            if constexpr (LOCK) sweepBarrier();
+            if (!on) continue;
             const BodyConst& bc = T.bodies[b];
             if (b + 1 < c.nb) preloadGNu(c, inst, T.bodies[b + 1], SBK_GNU(b));
             preloadCoords<JMASK>(c, inst, T.bodies[b + 1 < c.nb ? b + 1 : b], SBK_PRE(b));
