@@ -89,22 +89,61 @@ static void compileLocalTables(sbk_topology& t) {
 
 // nclusters > 1: the nwarps warps belong to that many clusters (consecutive ranges); the levels above the cut run on the FIRST
 // cluster's warps (cluster barrier between levels) and the two parts of a sweep meet at a barrier of all the clusters (LT_XSYNC).
+// CTA-local levels: with one subtree per warp, a body above the cut whose descendants' subtrees all belong to the eight warps of
+// ONE CTA is processed by the warp of its first child, right after / before that warp's subtree, with the CTA's barrier
+// (LT_TSYNC, every warp of every CTA one entry per such level) -- for a binary tree the three levels above the cut leave the
+// cluster-barrier part of the sweep.
 TreeCut cutTreeForWarps(const sbk_topology& t, int nwarps, int topWarps, int cutWidth, int nclusters) {
     if (cutWidth <= 0) cutWidth = nwarps;
     TreeCut r; r.bodies = t.lbodiesLevel; r.cutLevel = t.nlevels; r.subStart.assign(1, 0);
     for (int l = 1; l < t.nlevels; ++l) if (t.levelStart[l + 1] - t.levelStart[l] >= cutWidth) { r.cutLevel = l; break; }
-    for (int i = t.levelStart[std::min(r.cutLevel, t.nlevels - 1)]; r.cutLevel < t.nlevels && i < t.levelStart[r.cutLevel + 1]; ++i) {
+    const int L = r.cutLevel;
+    std::vector<std::vector<int>> dfs;
+    for (int i = t.levelStart[std::min(L, t.nlevels - 1)]; L < t.nlevels && i < t.levelStart[L + 1]; ++i) {
         // depth-first walk, children in list order (the first child directly follows its parent)
+        dfs.emplace_back();
         std::vector<int> stack(1, t.levelOrder[i]);
         while (!stack.empty()) {
             const int b = stack.back(); stack.pop_back();
-            r.subOrder.push_back(b);
+            dfs.back().push_back(b);
             const sbkd::LBody& lb = t.lbodies[b];
             for (int j = lb.nchild - 1; j >= 0; --j) stack.push_back(t.children[lb.childStart + j]);
         }
+    }
+    const int nsub = (int)dfs.size();
+    const int perCluster = nwarps/std::max(1, nclusters);
+    topWarps = std::max(1, std::min(topWarps, nclusters > 1 ? perCluster : nwarps));
+    const int levelSync = (topWarps > 8 || nclusters > 1) ? sbkd::LT_GSYNC : sbkd::LT_TSYNC;      // more than one CTA's warps on the top levels: group barrier between levels
+    // CTA-local levels l0 .. L-1 (l0 = L: none) and the chain of such bodies each subtree's warp owns (top-down)
+    int l0 = L;
+    std::vector<std::vector<int>> chain(nsub);
+    if (nsub > 0 && nsub <= nwarps && levelSync == sbkd::LT_GSYNC) {
+        std::vector<int> owner(t.nb, -1);
+        for (int s = 0; s < nsub; ++s) owner[dfs[s][0]] = s;
+        for (int l = L - 1; l >= 1; --l) {
+            std::vector<std::pair<int, int>> got;
+            bool all = true;
+            for (int i = t.levelStart[l]; all && i < t.levelStart[l + 1]; ++i) {
+                const int p = t.levelOrder[i]; const sbkd::LBody& lb = t.lbodies[p];
+                if (lb.nchild == 0) { all = false; break; }
+                int lo = nwarps, hi = -1;
+                for (int j = 0; j < lb.nchild; ++j) { const int o = owner[t.children[lb.childStart + j]]; if (o < 0) all = false; lo = std::min(lo, o); hi = std::max(hi, o); }
+                if (!all || lo/8 != hi/8) { all = false; break; }
+                got.push_back({p, owner[t.children[lb.childStart]]});
+            }
+            if (!all) break;
+            for (const auto& g : got) owner[g.first] = g.second;
+            l0 = l;
+        }
+        for (int l = l0; l < L; ++l)
+            for (int i = t.levelStart[l]; i < t.levelStart[l + 1]; ++i) chain[owner[t.levelOrder[i]]].push_back(t.levelOrder[i]);
+    }
+    // a warp's walk: its chain (a parent -> first child sequence ending right above the subtree's root), then the subtree
+    for (int s = 0; s < nsub; ++s) {
+        r.subOrder.insert(r.subOrder.end(), chain[s].begin(), chain[s].end());
+        r.subOrder.insert(r.subOrder.end(), dfs[s].begin(), dfs[s].end());
         r.subStart.push_back((int)r.subOrder.size());
     }
-    const int nsub = (int)r.subStart.size() - 1;
     // link flags of the walk: parent previous / next is my first child / some child is not next
     for (int s = 0; s < nsub; ++s)
         for (int k = r.subStart[s]; k < r.subStart[s + 1]; ++k) {
@@ -118,22 +157,32 @@ TreeCut cutTreeForWarps(const sbk_topology& t, int nwarps, int topWarps, int cut
             lb.flags = f;
         }
     // task lists (sbk_ltree.cuh): per warp, inward then outward
-    const int perCluster = nwarps/std::max(1, nclusters);
-    topWarps = std::max(1, std::min(topWarps, nclusters > 1 ? perCluster : nwarps));
-    const int levelSync = (topWarps > 8 || nclusters > 1) ? sbkd::LT_GSYNC : sbkd::LT_TSYNC;      // more than one CTA's warps on the top levels: group barrier between levels
     r.listStart.assign(2*(size_t)nwarps, 0);
-    const bool haveTop = r.cutLevel > 1, haveSub = nsub > 0;
+    const bool haveTop = l0 > 1, haveSub = nsub > 0;
     for (int dir = 0; dir < 2; ++dir)
         for (int w = 0; w < nwarps; ++w) {
             r.listStart[(size_t)dir*nwarps + w] = (int)r.lists.size();
             std::vector<int> sub, top;
-            for (int s = w; s < nsub; s += nwarps) {
-                if (dir) for (int k = r.subStart[s]; k < r.subStart[s + 1]; ++k) sub.push_back(r.subOrder[k]);
-                else     for (int k = r.subStart[s + 1] - 1; k >= r.subStart[s]; --k) sub.push_back(r.subOrder[k]);
-            }
+            if (l0 < L) {        // one subtree per warp, CTA-local levels between it and the top
+                const int s = w < nsub ? w : -1, nch = s >= 0 ? (int)chain[s].size() : 0;
+                auto levelBody = [&](int l) { return (s >= 0 && l >= L - nch) ? chain[s][l - (L - nch)] : 0; };
+                if (dir) {
+                    for (int l = l0; l < L; ++l) sub.push_back(levelBody(l) | sbkd::LT_TSYNC);
+                    if (s >= 0) sub.insert(sub.end(), dfs[s].begin(), dfs[s].end());
+                } else {
+                    if (s >= 0) sub.insert(sub.end(), dfs[s].rbegin(), dfs[s].rend());
+                    if (sub.empty()) sub.push_back(0);
+                    sub.back() |= sbkd::LT_TSYNC;
+                    for (int l = L - 1; l >= l0; --l) sub.push_back(levelBody(l) | (l > l0 ? sbkd::LT_TSYNC : 0));
+                }
+            } else
+                for (int s = w; s < nsub; s += nwarps) {
+                    if (dir) sub.insert(sub.end(), dfs[s].begin(), dfs[s].end());
+                    else     sub.insert(sub.end(), dfs[s].rbegin(), dfs[s].rend());
+                }
             const bool inTopCluster = nclusters <= 1 || w < perCluster;
             if ((w < topWarps || levelSync == sbkd::LT_GSYNC) && haveTop && inTopCluster)
-                for (int l = dir ? 1 : r.cutLevel - 1; dir ? l < r.cutLevel : l >= 1; l += dir ? 1 : -1) {
+                for (int l = dir ? 1 : l0 - 1; dir ? l < l0 : l >= 1; l += dir ? 1 : -1) {
                     const size_t before = top.size();
                     if (w < topWarps) for (int i = t.levelStart[l] + w; i < t.levelStart[l + 1]; i += topWarps) top.push_back(t.levelOrder[i]);
                     if (top.size() == before) top.push_back(0);            // no body of this level for this warp: barrier only

@@ -435,4 +435,21 @@ int emu_cut_check(const char* text, int nwarps, int topWarps, int cutWidth, int 
     } catch (const std::exception& ex) { std::fprintf(stderr, "emu: %s\n", ex.what()); return 1; }
 }
 
+// Shape of a plan-5 schedule: out = {cut level, entries / TSYNC / GSYNC / XSYNC counts of the longest inward list}.
+int emu_cut_info(const char* text, int nwarps, int topWarps, int cutWidth, int nclusters, int* out) {
+    try {
+        sbk_topology t; sbk::compileTopology(sbk::fromText(text), t);
+        const sbk::TreeCut cut = sbk::cutTreeForWarps(t, nwarps, topWarps, cutWidth, nclusters);
+        out[0] = cut.cutLevel; out[1] = out[2] = out[3] = out[4] = 0;
+        for (int w = 0; w < nwarps; ++w) {
+            int n = 0, ts = 0, gs = 0, xs = 0;
+            for (int k = cut.listStart[w]; !(cut.lists[k] & sbkd::LT_END); ++k) {
+                ++n; ts += (cut.lists[k] & sbkd::LT_TSYNC) != 0; gs += (cut.lists[k] & sbkd::LT_GSYNC) != 0; xs += (cut.lists[k] & sbkd::LT_XSYNC) != 0;
+            }
+            if (n > out[1]) { out[1] = n; out[2] = ts; out[3] = gs; out[4] = xs; }
+        }
+        return 0;
+    } catch (const std::exception& ex) { std::fprintf(stderr, "emu: %s\n", ex.what()); return 1; }
+}
+
 } // extern "C"
