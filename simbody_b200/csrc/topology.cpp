@@ -113,11 +113,11 @@ TreeCut cutTreeForWarps(const sbk_topology& t, int nwarps, int topWarps, int cut
     const int nsub = (int)dfs.size();
     const int perCluster = nwarps/std::max(1, nclusters);
     topWarps = std::max(1, std::min(topWarps, nclusters > 1 ? perCluster : nwarps));
-    const int levelSync = (topWarps > 8 || nclusters > 1) ? sbkd::LT_GSYNC : sbkd::LT_TSYNC;      // more than one CTA's warps on the top levels: group barrier between levels
+    const bool multiCta = topWarps > 8 || nclusters > 1;
     // CTA-local levels l0 .. L-1 (l0 = L: none) and the chain of such bodies each subtree's warp owns (top-down)
     int l0 = L;
     std::vector<std::vector<int>> chain(nsub);
-    if (nsub > 0 && nsub <= nwarps && levelSync == sbkd::LT_GSYNC) {
+    if (nsub > 0 && nsub <= nwarps && multiCta) {
         std::vector<int> owner(t.nb, -1);
         for (int s = 0; s < nsub; ++s) owner[dfs[s][0]] = s;
         for (int l = L - 1; l >= 1; --l) {
@@ -138,6 +138,12 @@ TreeCut cutTreeForWarps(const sbk_topology& t, int nwarps, int topWarps, int cut
         for (int l = l0; l < L; ++l)
             for (int i = t.levelStart[l]; i < t.levelStart[l + 1]; ++i) chain[owner[t.levelOrder[i]]].push_back(t.levelOrder[i]);
     }
+    // the levels that remain on top: on the first CTA's eight warps with __syncthreads when none of them is wider than that,
+    // else on topWarps warps of the first cluster with the cluster barrier
+    int topWidth = 0;
+    for (int l = 1; l < l0; ++l) topWidth = std::max(topWidth, t.levelStart[l + 1] - t.levelStart[l]);
+    if (multiCta && l0 < L && topWidth <= 8) topWarps = std::min(topWarps, 8);
+    const int levelSync = (topWarps > 8 || (nclusters > 1 && !(l0 < L && topWidth <= 8))) ? sbkd::LT_GSYNC : sbkd::LT_TSYNC;
     // a warp's walk: its chain (a parent -> first child sequence ending right above the subtree's root), then the subtree
     for (int s = 0; s < nsub; ++s) {
         r.subOrder.insert(r.subOrder.end(), chain[s].begin(), chain[s].end());

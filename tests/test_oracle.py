@@ -317,9 +317,9 @@ def test_cluster_task_lists_are_complete_ordered_and_deadlock_free(model, n, sch
 
 def test_cluster_schedule_shape_of_the_c5_tree():
     """The 1000-body binary tree on 128 warps (4 clusters of 4 CTAs): cut at level 8 (128 subtrees of 7 bodies), the three levels
-    above it stay inside the CTAs (__syncthreads), the four top levels run on the first cluster: 14 tasks per sweep on the
-    longest list, one cross-cluster barrier."""
+    above it stay inside the CTAs (__syncthreads), the four top levels (at most 8 bodies wide) run on the first CTA: 14 tasks per
+    sweep on the longest list, seven CTA barriers, no cluster barrier, one cross-cluster barrier."""
     emu = HostEmu()
     info = ModelInfo(emu.model_text("branched_tree", 1000))
-    assert emu.cut_info(info, 128, 32, 0, 4) == (8, 14, 3, 4, 1)
-    assert emu.cut_info(info, 64, 64, 0, 1)[:3] == (7, 21, 3)
+    assert emu.cut_info(info, 128, 32, 0, 4) == (8, 14, 7, 0, 1)
+    assert emu.cut_info(info, 64, 64, 0, 1) == (7, 21, 6, 1, 0)
