@@ -47,7 +47,7 @@ run("double_pendulum", 0, 1000, 2, 5)
 run("mixed7", 0, 40, 3, 2)
 run("branched_tree", 60, 64, 4, 1, h=5e-4)
 run("twopoint7", 0, 96, 4, 1)
-run("branched_tree", 200, 64, 5, 1, h=5e-4)
+run("branched_tree", 600, 64, 5, 1, h=5e-4)      # two clusters per group, CTA-local levels, cross-cluster barrier
 run("mixed7", 0, 100, 1, 0, ops=True)
 run("branched_tree", 60, 40, 4, 0, ops=True)
 print("SANITIZE_SUBSET_DONE")
