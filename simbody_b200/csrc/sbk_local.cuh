@@ -410,13 +410,13 @@ SBK_HD bool solveSym6(const ABI& P, const double* b, double* x) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) A[3+i][j] = P.F.a[3*j+i];          // lower-left block = ~F
     A[3][3] = P.M.xx; A[4][3] = P.M.xy; A[4][4] = P.M.yy; A[5][3] = P.M.xz; A[5][4] = P.M.yz; A[5][5] = P.M.zz;
-    double L[6][6], W[6][6], dd[6], od[6]; bool ok = true;            // W = L * diag(dd)
+    double L[6][6], W[6][6], od[6]; bool ok = true;                   // W = L * diag(d), od = 1/d
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
         double s = A[j][j];
 #pragma unroll
         for (int k = 0; k < 6; ++k) if (k < j) s -= L[j][k]*W[j][k];
-        dd[j] = s; ok = ok && (s > 0.0); od[j] = 1.0/s;
+        ok = ok && (s > 0.0); od[j] = 1.0/s;
 #pragma unroll
         for (int i = 0; i < 6; ++i) if (i > j) {
             double t = A[i][j];
