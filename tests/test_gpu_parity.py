@@ -626,3 +626,35 @@ def test_cluster_level_parallel_plan_matches_golden(name):
     assert rel_err(out[5][0], out[1][0]) < 1e-10 and rel_err(out[5][1], out[1][1]) < 1e-10
     assert np.allclose(out[5][2], out[1][2], rtol=1e-3, atol=1e-14)
     topo.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cluster,per_group", [(8, 1), (8, 2), (4, 4), (4, 2), (2, 1), (1, 1)])
+def test_cluster_plan_schedules_agree_with_thread_per_instance(cluster, per_group):
+    """Plan 5 under every shape of its schedule (cluster size, clusters per group of 32 instances: with and without the
+    cross-cluster barrier, CTA-local levels, top on one CTA or on a cluster) steps a 600-body tree to the same state as the
+    thread-per-instance plan; the batch has a partial last group."""
+    info = ModelInfo(sb.model_text("branched_tree", 600))
+    n = 72
+    q, u = info.random_states(n, 77, q_scale=0.5)
+    topo = sb.Topology(text=info.text)
+    out = {}
+    for plan in (1, 5):
+        old = {k: os.environ.get(k) for k in ("SBK_CLUSTER", "SBK_CLUSTERS_PER_GROUP")}
+        if plan == 5:
+            os.environ["SBK_CLUSTER"] = str(cluster); os.environ["SBK_CLUSTERS_PER_GROUP"] = str(per_group)
+        try:
+            bm = sb.BatchedMatter(topo, n); bm.setPlan(plan); assert bm.getPlan() == plan
+            bm.setState(soa(q), soa(u), t=0.0)
+            e = bm.stepBy(5e-4, 3, want_err_norm=True)
+            a, b, _ = bm.getState()
+            st, nbad = bm.status(); assert nbad == 0
+            out[plan] = (a, b, e)
+            bm.close()
+        finally:
+            for k, v in old.items():
+                if v is None: os.environ.pop(k, None)
+                else: os.environ[k] = v
+    assert rel_err(out[5][0], out[1][0]) < 1e-10 and rel_err(out[5][1], out[1][1]) < 1e-10
+    assert np.allclose(out[5][2], out[1][2], rtol=1e-3, atol=1e-14)
+    topo.close()
