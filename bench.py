@@ -437,6 +437,10 @@ def main():
                 "flop_per_instance_step": r["flop_per_inst_step"], "bytes_per_instance_step": r["bytes_per_inst_step"],
                 "hbm_algorithmic_GBs": per_gpu_rate * r["bytes_per_inst_step"] / 1e9, "hbm_peak_GBs": peaks.get("hbm_gbs"),
                 "kernel": r["kernel"], "plan": PLAN_NAMES.get(r["plan"], str(r["plan"])), "kernel_ms_last_launch": r["kernel_ms_last"], "traffic": None}
+        if r["plan"] == 2:
+            roof["frac_note"] = ("algorithmic = the reference's operation count (SURVEY.md 8d); the register-resident kernel skips the "
+                                 "multiplications by structural 0 / 1 that count includes and pays less than its 50 flop per sincos, so frac can "
+                                 "reach 1.0 while the FP64 pipe (fp64_pipe_active_ncu) is the hardware-side utilisation")
         roof.update(ncu_fields(r["name"], r["kernel"], r["kernel_ms_last"], r["N"], r["spl"], r["plan"]))
         if roof.get("dram_bytes_per_instance_step_ncu") and peaks.get("hbm_gbs"):
             roof["hbm_traffic_frac_ncu"] = roof["dram_bytes_per_instance_step_ncu"] * per_gpu_rate / 1e9 / peaks["hbm_gbs"]

@@ -20,7 +20,12 @@ namespace {
 
 // Register-resident fused plan: the whole multi-step RKM loop of one instance in one thread.
 template <class E, bool ADAPT>
-__global__ void __launch_bounds__(128) fusedRkmKernel(const KArgs a) {
+// three resident CTAs per SM (168 registers, 176 bytes of spill code per thread): 12 warps per SM cover the FP64 latency better than
+// 8 at 244 registers -- C2 3.26e9 -> 3.42e9 instance-steps/s; four CTAs at 128 registers: 3.32e9
+#ifndef SBK_FUSED_MINB
+#define SBK_FUSED_MINB 3
+#endif
+__global__ void __launch_bounds__(128, SBK_FUSED_MINB) fusedRkmKernel(const KArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t mbar;
     tmaStage(smem, a.tables, a.tableBytes, &mbar);
