@@ -343,7 +343,7 @@ int emu_adaptive(const char* text, int N, const double* in, double* out, double 
                 ch.gx = t.grav[0]; ch.gy = t.grav[1]; ch.gz = t.grav[2];
                 fusedRkmAdaptive(ch, y, lim, tFinal, allowInterpolation, 1000000, 0, st, lastErr);
                 for (int i = 0; i < ny; ++i) o[i] = y[i];
-            } else if (fused == 2) {   // fused two-sweep integrator on the body-frame cores
+            } else if (fused == 2 || fused == 3) {   // fused two-sweep integrator on the body-frame cores; 3: the CTA-voting lockstep form
                 if (!t.localOk) return 5;
                 LTables LT; LT.bodies = t.lbodies.data(); LT.children = t.children.data(); LT.forces = t.forces.data(); LT.fcoef = t.lfcoef.data();
                 Ctx c = makeCtx(e, k); c.qdotdot = nullptr; c.qerr = nullptr;
@@ -351,12 +351,14 @@ int emu_adaptive(const char* text, int N, const double* in, double* out, double 
                 LRkmWork lw; lw.Y = e.y.data(); lw.W = e.ys.data(); lw.F0 = e.f0.data(); lw.F2 = e.fa.data(); lw.F3 = e.fb.data(); lw.Ynext = e.y0.data();
                 lw.accuracy = accuracy; lw.consTol = accuracy/10; lw.useInfNorm = 0; lw.projectEveryStep = 0;
                 LRkmState ls; ls.vb = 0; ls.velValid = false;
-                lRkmAdaptive<JM_MOBILE5>(c, LT, k, lw, lim, tFinal, allowInterpolation, 1000000, st, cy, ls, lastErr, nproj);
+                if (fused == 3) lRkmAdaptive<JM_MOBILE5, CtaVote>(c, LT, k, lw, lim, tFinal, allowInterpolation, 1000000, st, cy, ls, lastErr, nproj, true);
+                else lRkmAdaptive<JM_MOBILE5>(c, LT, k, lw, lim, tFinal, allowInterpolation, 1000000, st, cy, ls, lastErr, nproj);
                 for (int i = 0; i < ny; ++i) o[i] = lw.Y[(size_t)i*N + k];
             } else {
                 Ctx c = makeCtx(e, k); c.qdotdot = nullptr; c.qerr = nullptr;
                 double cy[CARRY_ROWS + LFCARRY_ROWS];
-                tpiRkmAdaptive<true>(c, tablesOf(c), k, w, lim, tFinal, allowInterpolation, 1000000, st, cy, lastErr, nproj);
+                if (fused == 4) tpiRkmAdaptive<true, JM_ALL, Tables, CtaVote>(c, tablesOf(c), k, w, lim, tFinal, allowInterpolation, 1000000, st, cy, lastErr, nproj, true);
+                else tpiRkmAdaptive<true>(c, tablesOf(c), k, w, lim, tFinal, allowInterpolation, 1000000, st, cy, lastErr, nproj);
                 for (int i = 0; i < ny; ++i) o[i] = e.y[(size_t)i*N + k];
             }
             o[ny] = st.steps; o[ny+1] = st.attempts; o[ny+2] = st.steps + 4.0*st.attempts; o[ny+3] = st.lastStep; o[ny+4] = st.t;

@@ -323,3 +323,19 @@ def test_cluster_schedule_shape_of_the_c5_tree():
     info = ModelInfo(emu.model_text("branched_tree", 1000))
     assert emu.cut_info(info, 128, 32, 0, 4) == (8, 14, 7, 0, 1)
     assert emu.cut_info(info, 64, 64, 0, 1) == (7, 21, 6, 1, 0)
+
+
+@pytest.mark.parametrize("model,tf", [("mixed7", 0.3), ("humanoid30", 0.05), ("ugdamp5", 0.3)])
+def test_lockstep_adaptive_forms_match_the_plain_ones_on_the_host(model, tf):
+    """The error-controlled kernels run a CTA-voting, per-body-lockstep form of the attempt (lRkmAttemptLockstep; the ground-frame
+    step with its `mine` / `anyFresh` predicates).  On the host (one thread, the vote is the thread's own flag) both must
+    reproduce the plain forms bit for bit: same states, same step and attempt counts."""
+    emu = HostEmu()
+    info = ModelInfo(emu.model_text(model))
+    q, u = info.random_states(6, 11, q_scale=0.6)
+    y = np.concatenate([q, u], axis=1)
+    for plain, lock in ((2, 3), (0, 4)):
+        a = emu.adaptive(info, y, tf, allow_interpolation=False, fused=plain)
+        b = emu.adaptive(info, y, tf, allow_interpolation=False, fused=lock)
+        assert np.array_equal(a, b), (model, plain, lock, np.abs(a - b).max())
+        assert a[:, info.nq + info.nu].min() >= 2                      # several steps were taken
