@@ -739,7 +739,14 @@ void sbk_adaptive_default_opts(sbk_adaptive_opts* o) {
 int sbk_rkm_adaptive(sbk_batch* b, double tFinal, const sbk_adaptive_opts* opts, int32_t* steps, int32_t* attempts, double* lastStep) {
     if (!b) return fail(SBK_ERR_ARG, "null batch");
     if (int rc = useDevice(b)) return rc;
-    if (b->plan == 3) return fail(SBK_ERR_ARG, "sbk_rkm_adaptive: not available in plan 3 (use sbk_batch_set_plan(b, 0 or 1))");
+    if (b->plan == 3) {
+        // the CTA-per-instance plan keeps its records instance-major: error-controlled stepping (one step-size history per
+        // instance) borrows the thread-per-instance plan's layout and kernel for the call; the state arrays are shared
+        if (int rc = configurePlan(b, 1)) return rc;
+        const int rc = sbk_rkm_adaptive(b, tFinal, opts, steps, attempts, lastStep);
+        const int rc2 = configurePlan(b, 3);
+        return rc ? rc : rc2;
+    }
     if (!b->topo->twoPoint.empty()) return fail(SBK_ERR_ARG, "sbk_rkm_adaptive: not available for models with two-point force elements (fixed steps only)");
     sbk_adaptive_opts o; sbk_adaptive_default_opts(&o);
     if (opts) {

@@ -548,6 +548,15 @@ def test_adaptive_runs_in_the_auto_plan_of_wide_trees():
     s1, a1, _ = bm.stepTo(0.02)
     q1, u1, _ = bm.getState()
     assert np.array_equal(s1, steps) and np.array_equal(a1, att) and rel_err(qa, q1) < 1e-12
+    bm.close()
+    # the CTA-per-instance plan borrows the thread-per-instance layout for the call and keeps working afterwards
+    bm = sb.BatchedMatter(topo, nI); bm.setPlan(3)
+    bm.setState(soa(q), soa(u), t=0.0)
+    s3, a3, _ = bm.stepTo(0.02)
+    q3, u3, _ = bm.getState()
+    assert bm.getPlan() == 3 and np.array_equal(s3, steps) and np.array_equal(a3, att) and rel_err(q3, q1) < 1e-12
+    bm.stepBy(5e-4, 2); bm.realizeAcceleration()
+    assert np.all(np.isfinite(bm.getUDot()))
     bm.close(); topo.close()
 
 
