@@ -339,3 +339,32 @@ def test_lockstep_adaptive_forms_match_the_plain_ones_on_the_host(model, tf):
         b = emu.adaptive(info, y, tf, allow_interpolation=False, fused=lock)
         assert np.array_equal(a, b), (model, plain, lock, np.abs(a - b).max())
         assert a[:, info.nq + info.nu].min() >= 2                      # several steps were taken
+
+
+def _random_tree_text(rng, nb, max_children):
+    """A random tree of Pin / Universal / Ball bodies in the model text format (mass properties copied from a template body)."""
+    emu = HostEmu()
+    lines = emu.model_text("branched_tree", 4).splitlines()
+    ground = next(l for l in lines if l.startswith("body 0 "))
+    tmpl = next(l for l in lines if l.startswith("body 1 ")).split()
+    nchild = [0] * (nb + 1)
+    out = ["sbkmodel 1", "name random_tree", "nb %d" % (nb + 1), ground]
+    for b in range(1, nb + 1):
+        cands = [p for p in range(max(0, b - 12), b) if nchild[p] < max_children] or [b - 1]
+        p = int(rng.choice(cands)); nchild[p] += 1
+        out.append(" ".join(["body", str(b), str(p), str(rng.choice(["PIN", "UNIVERSAL", "BALL"]))] + tmpl[4:]))
+    out += [l for l in lines if l.startswith("nf ") or l.startswith("gravity")]
+    return "\n".join(out) + "\n"
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_cluster_task_lists_on_random_trees(seed):
+    """The schedule builder on irregular trees (leaves above the cut, sibling groups that straddle a CTA's eight warps, several
+    subtrees per warp): the simulated run must still process every body once per sweep in dependency order, with no warp left
+    waiting, for one, two and four clusters per group."""
+    rng = np.random.default_rng(1000 + seed)
+    nb = int(rng.integers(20, 700)); max_children = int(rng.integers(1, 5))
+    emu = HostEmu()
+    info = ModelInfo(_random_tree_text(rng, nb, max_children))
+    for sched in [(64, 64, 0, 1), (64, 8, 0, 1), (128, 64, 0, 2), (128, 32, 0, 4), (32, 16, 0, 2), (16, 16, 8, 1), (8, 8, 0, 1)]:
+        assert emu.cut_check(info, *sched) == 0, (seed, nb, max_children, sched)
