@@ -9,6 +9,10 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <memory>
 #include "../../simbody_b200/csrc/topology.h"
 #include "../../simbody_b200/csrc/sbk_fused.cuh"
 #include "../../simbody_b200/csrc/sbk_lrkm.cuh"
@@ -449,6 +453,73 @@ int emu_cut_info(const char* text, int nwarps, int topWarps, int cutWidth, int n
                 ++n; ts += (cut.lists[k] & sbkd::LT_TSYNC) != 0; gs += (cut.lists[k] & sbkd::LT_GSYNC) != 0; xs += (cut.lists[k] & sbkd::LT_XSYNC) != 0;
             }
             if (n > out[1]) { out[1] = n; out[2] = ts; out[3] = gs; out[4] = xs; }
+        }
+        return 0;
+    } catch (const std::exception& ex) { std::fprintf(stderr, "emu: %s\n", ex.what()); return 1; }
+}
+
+// Plan 5 with its real schedule on the host: one std::thread per warp of the group runs lListStep (sbk_ltree.cuh) over the
+// task lists of cutTreeForWarps, with cyclic barriers standing in for __syncthreads (8 warps), barrier.cluster and the
+// cross-cluster barrier, and the fixed-order reduction of the error sums -- what ctreeRkmKernel does for one lane.
+namespace {
+struct CyclicBarrier {
+    std::mutex m; std::condition_variable cv; int n, waiting = 0; long gen = 0;
+    explicit CyclicBarrier(int n_) : n(n_) {}
+    void wait() {
+        std::unique_lock<std::mutex> lk(m);
+        const long g = gen;
+        if (++waiting == n) { waiting = 0; ++gen; cv.notify_all(); }
+        else cv.wait(lk, [&] { return gen != g; });
+    }
+};
+}
+int emu_cluster_step(const char* text, int N, const double* in, double* out, double h, int nsteps, double accuracy,
+                     int nwarps, int topWarps, int cutWidth, int nclusters) {
+    try {
+        Emu e; setup(e, text, N);
+        const sbk_topology& t = e.topo; const int ny = t.nq + t.nu;
+        if (!t.localOk) return 5;
+        for (int k = 0; k < N; ++k) for (int i = 0; i < ny; ++i) e.y[(size_t)i*N + k] = in[(size_t)k*ny + i];
+        const sbk::TreeCut cut = sbk::cutTreeForWarps(t, nwarps, topWarps, cutWidth, nclusters);
+        LTables LT; LT.bodies = cut.bodies.data(); LT.children = t.children.data(); LT.forces = t.forces.data(); LT.fcoef = t.lfcoef.data();
+        const int perCluster = nwarps/std::max(1, nclusters);
+        for (int k = 0; k < N; ++k) {
+            std::vector<std::unique_ptr<CyclicBarrier>> ctaBar, clusterBar;
+            for (int w0 = 0; w0 < nwarps; w0 += 8) ctaBar.emplace_back(new CyclicBarrier(std::min(8, nwarps - w0)));
+            for (int w0 = 0; w0 < nwarps; w0 += perCluster) clusterBar.emplace_back(new CyclicBarrier(std::min(perCluster, nwarps - w0)));
+            CyclicBarrier allBar(nwarps);
+            std::vector<double> part((size_t)nwarps*3, 0.0);
+            int projectedFlag = 0; RkmStepResult last; last.errNorm = 0; last.projected = 0; int nprojTotal = 0;
+            { Ctx c0 = makeCtx(e, k); lLevelGround(c0, LT, k); }
+            auto warp = [&](const int wc) {
+                Ctx c = makeCtx(e, k); c.qdotdot = nullptr; c.qerr = nullptr;
+                LRkmWork lw; lw.Y = e.y.data(); lw.W = e.ys.data(); lw.F0 = e.f0.data(); lw.F2 = e.fa.data(); lw.F3 = e.fb.data(); lw.Ynext = e.y.data();
+                lw.accuracy = accuracy; lw.consTol = accuracy/10; lw.useInfNorm = 0; lw.projectEveryStep = 0;
+                std::vector<double> cyv(CARRY_ROWS + LFCARRY_ROWS, 0.0); double* cy = cyv.data();
+                LBody slots[LT_BODY_SLOTS]; LBodySlots BS; BS.slot = slots;
+                const int* lstIn = cut.lists.data() + cut.listStart[wc]; const int* lstOut = cut.lists.data() + cut.listStart[(size_t)nwarps + wc];
+                int par = 0, vb = 0; bool velValid = false;
+                auto topSync = [&]() { ctaBar[wc/8]->wait(); };
+                auto groupSync = [&](const bool cross) { if (cross && nclusters > 1) allBar.wait(); else clusterBar[wc/perCluster]->wait(); };
+                auto reduce = [&](double& q, double& u, double& qt) {
+                    part[(size_t)wc*3] = q; part[(size_t)wc*3 + 1] = u; part[(size_t)wc*3 + 2] = qt;
+                    allBar.wait();
+                    if (wc == 0) { double s0 = 0, s1 = 0, s2 = 0; for (int w = 0; w < nwarps; ++w) { s0 += part[(size_t)w*3]; s1 += part[(size_t)w*3 + 1]; s2 += part[(size_t)w*3 + 2]; } q = s0; u = s1; qt = s2; }
+                };
+                for (int s = 0; s < nsteps; ++s) {
+                    const RkmStepResult r = lListStep<JM_MOBILE5>(c, LT, lstIn, lstOut, BS, k, true, 0, cy, lw, h, vb, velValid, wc, par, topSync, groupSync, reduce);
+                    if (wc == 0) { projectedFlag = r.projected; last = r; nprojTotal += r.projected; }
+                    allBar.wait();
+                    velValid = projectedFlag == 0;
+                    allBar.wait();          // nobody overwrites the flag before everyone has read it
+                }
+            };
+            std::vector<std::thread> th;
+            for (int w = 0; w < nwarps; ++w) th.emplace_back(warp, w);
+            for (auto& x : th) x.join();
+            double* o = out + (size_t)k*(ny+2);
+            for (int i = 0; i < ny; ++i) o[i] = e.y[(size_t)i*N + k];
+            o[ny] = last.errNorm; o[ny+1] = nprojTotal;
         }
         return 0;
     } catch (const std::exception& ex) { std::fprintf(stderr, "emu: %s\n", ex.what()); return 1; }

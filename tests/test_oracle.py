@@ -368,3 +368,28 @@ def test_cluster_task_lists_on_random_trees(seed):
     info = ModelInfo(_random_tree_text(rng, nb, max_children))
     for sched in [(64, 64, 0, 1), (64, 8, 0, 1), (128, 64, 0, 2), (128, 32, 0, 4), (32, 16, 0, 2), (16, 16, 8, 1), (8, 8, 0, 1)]:
         assert emu.cut_check(info, *sched) == 0, (seed, nb, max_children, sched)
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("case", ["tree600", "tree150", "humanoid30", "random0", "random1", "random2"])
+def test_cluster_plan_on_the_host_matches_the_thread_per_instance_integrator(case):
+    """Plan 5 end to end without a GPU: one host thread per warp runs lListStep over the real task lists, with cyclic barriers
+    for __syncthreads / barrier.cluster / the cross-cluster barrier.  Every schedule shape must reproduce the plain fused
+    integrator (the link flags of subtree walks, CTA-local chains and top levels decide which data ride in a warp's carry)."""
+    emu = HostEmu()
+    if case.startswith("tree"):
+        info = ModelInfo(emu.model_text("branched_tree", int(case[4:])))
+    elif case.startswith("random"):
+        rng = np.random.default_rng(50 + int(case[6:]))
+        info = ModelInfo(_random_tree_text(rng, int(rng.integers(60, 400)), int(rng.integers(2, 4))))
+    else:
+        info = ModelInfo(emu.model_text(case))
+    q, u = info.random_states(2, 21, q_scale=0.4)
+    y = np.concatenate([q, u], axis=1)
+    ny = info.nq + info.nu
+    ref = emu.step(info, y, 5e-4, 2, lean=4)
+    for sched in [(64, 64, 0, 1), (128, 32, 0, 4), (128, 64, 0, 2), (32, 16, 0, 2), (16, 16, 0, 1), (8, 8, 0, 1)]:
+        got = emu.cluster_step(info, y, 5e-4, 2, *sched)
+        assert rel_err(got[:, :ny], ref[:, :ny]) < 1e-13, (case, sched, rel_err(got[:, :ny], ref[:, :ny]))
+        assert np.allclose(got[:, ny], ref[:, ny], rtol=1e-9, atol=1e-16), (case, sched)        # error norm: another summation order
+        assert np.array_equal(got[:, ny + 1], ref[:, ny + 1])
