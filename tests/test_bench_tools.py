@@ -37,3 +37,27 @@ def test_algorithmic_work_matches_survey_counts():
     info = ModelInfo(HostEmu().model_text("double_pendulum"))
     flop, byts = bench.algorithmic_work(info)
     assert flop == pytest.approx(10170.0) and byts == 64.0                # C2
+
+
+def test_reference_arm_contract():
+    """`bench.py --impl reference`: the real reference on the host cores, one JSON line with the GPU arm's metric / unit / config
+    keys, `impl`, a `cpu_baseline` describing the run and a zero-copy `e2e`; ranks other than 0 print nothing and exit 0."""
+    import json, subprocess
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _harness import have_ref
+    if not have_ref():
+        pytest.skip("oracle/_ref not present")
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "pin_chain50_64k", "--steps", "1", "--warmup", "0"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "instance_steps_per_s" and d["unit"] == "instance-steps/s" and d["higher_is_better"]
+    wl = bench.WORKLOADS["pin_chain50_64k"]
+    assert d["config"] == bench.workload_config("pin_chain50_64k", wl, wl["batch"], wl["spl"], "weak")
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r1 = subprocess.run(cmd + ["--gpus", "2"], capture_output=True, text=True, timeout=60, cwd=ROOT, env=env)
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
