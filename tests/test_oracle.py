@@ -393,3 +393,27 @@ def test_cluster_plan_on_the_host_matches_the_thread_per_instance_integrator(cas
         assert rel_err(got[:, :ny], ref[:, :ny]) < 1e-13, (case, sched, rel_err(got[:, :ny], ref[:, :ny]))
         assert np.allclose(got[:, ny], ref[:, ny], rtol=1e-9, atol=1e-16), (case, sched)        # error norm: another summation order
         assert np.array_equal(got[:, ny + 1], ref[:, ny + 1])
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("seed", range(6))
+def test_random_trees_match_live_reference(built, seed):
+    """Differential test on irregular random trees of Pin / Universal / Ball bodies (1-4 children per body) against the real
+    Simbody: accelerations of the body-frame and ground-frame sweeps and of the C restatement, then a few RKM steps of the fused
+    body-frame integrator and of the ground-frame one."""
+    rng = np.random.default_rng(7000 + seed)
+    emu, ref, co = HostEmu(), RefDriver(), COracle()
+    info = ModelInfo(_random_tree_text(rng, int(rng.integers(5, 70)), int(rng.integers(1, 5))))
+    inp = info.random_eval_input(4, 100 + seed, q_scale=0.6)
+    r = info.split_eval_out(ref.eval(info, inp))
+    y = inp[:, :info.nq + info.nu]
+    for local in (1, 0):
+        d = emu.deriv(info, y, local=local)
+        assert rel_err(d[:, info.nq:], r["udot"]) < 1e-10 and rel_err(d[:, :info.nq], r["qdot"]) < 1e-13, (seed, local)
+    c = info.split_eval_out(co.eval(info, inp))
+    assert rel_err(c["udot"], r["udot"]) < 1e-10 and rel_err(c["X_GB"], r["X_GB"]) < 1e-12
+    ny = info.nq + info.nu
+    yr = ref.step(info, y, 1e-3, 5)[:, :ny]
+    for lean in (4, 1):
+        ys = emu.step(info, y, 1e-3, 5, lean=lean)[:, :ny]
+        assert rel_err(ys, yr) < 1e-10, (seed, lean, rel_err(ys, yr))
