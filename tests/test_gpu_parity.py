@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 
 import simbody_b200 as sb
-from _harness import ModelInfo, RefDriver, check_sdfast2, have_ref, rel_err
+from _harness import ModelInfo, RefDriver, check_sdfast2, have_ref, random_tree_text, rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-11
@@ -667,3 +667,27 @@ def test_cluster_plan_schedules_agree_with_thread_per_instance(cluster, per_grou
     assert rel_err(out[5][0], out[1][0]) < 1e-10 and rel_err(out[5][1], out[1][1]) < 1e-10
     assert np.allclose(out[5][2], out[1][2], rtol=1e-3, atol=1e-14)
     topo.close()
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("seed,plan", [(0, 1), (1, 1), (2, 1), (3, 5), (4, 5), (5, 4), (6, 3)])
+def test_random_trees_match_live_reference(seed, plan):
+    """Irregular random trees of Pin / Universal / Ball bodies (1-4 children per body) through the C ABI against the real Simbody:
+    every operator of `run_eval`, then five RKM steps -- thread-per-instance, cluster, grid-level and CTA-per-instance plans."""
+    rng = np.random.default_rng(9000 + seed)
+    nb = int(rng.integers(150, 500)) if plan == 5 else int(rng.integers(5, 70))
+    info = ModelInfo(random_tree_text(rng, nb, int(rng.integers(1, 5)))); ny = info.nq + info.nu
+    ein = info.random_eval_input(5, 300 + seed, q_scale=0.6)
+    ref = info.split_eval_out(RefDriver().eval(info, ein))
+    got = run_eval(info, ein, plan=plan)
+    for k in ref:
+        assert rel_err(got[k], ref[k]) < 1e-10, (seed, plan, k, rel_err(got[k], ref[k]))
+    y = ein[:, :ny]
+    yref = RefDriver().step(info, y, 5e-4, 5)[:, :ny]
+    topo = sb.Topology(text=info.text); bm = sb.BatchedMatter(topo, y.shape[0]); bm.setPlan(plan); assert bm.getPlan() == plan
+    bm.setState(soa(y[:, :info.nq]), soa(y[:, info.nq:]), t=0.0)
+    bm.stepBy(5e-4, 5)
+    q, u, _ = bm.getState()
+    st, nbad = bm.status(); assert nbad == 0
+    assert rel_err(np.concatenate([q.T, u.T], axis=1), yref) < 1e-10, (seed, plan)
+    bm.close(); topo.close()

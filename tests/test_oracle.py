@@ -11,7 +11,7 @@ import os
 import numpy as np
 import pytest
 
-from _harness import COracle, HostEmu, ModelInfo, RefDriver, check_sdfast2, have_ref, rel_err, ROOT
+from _harness import COracle, HostEmu, ModelInfo, RefDriver, check_sdfast2, have_ref, rel_err, ROOT, random_tree_text as _random_tree_text
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 MODELS = ["double_pendulum", "pin_chain", "mixed7", "mixed7e", "ugdamp5", "welded8", "cartesian8", "twopoint7", "humanoid30", "branched_tree"]
@@ -339,22 +339,6 @@ def test_lockstep_adaptive_forms_match_the_plain_ones_on_the_host(model, tf):
         b = emu.adaptive(info, y, tf, allow_interpolation=False, fused=lock)
         assert np.array_equal(a, b), (model, plain, lock, np.abs(a - b).max())
         assert a[:, info.nq + info.nu].min() >= 2                      # several steps were taken
-
-
-def _random_tree_text(rng, nb, max_children):
-    """A random tree of Pin / Universal / Ball bodies in the model text format (mass properties copied from a template body)."""
-    emu = HostEmu()
-    lines = emu.model_text("branched_tree", 4).splitlines()
-    ground = next(l for l in lines if l.startswith("body 0 "))
-    tmpl = next(l for l in lines if l.startswith("body 1 ")).split()
-    nchild = [0] * (nb + 1)
-    out = ["sbkmodel 1", "name random_tree", "nb %d" % (nb + 1), ground]
-    for b in range(1, nb + 1):
-        cands = [p for p in range(max(0, b - 12), b) if nchild[p] < max_children] or [b - 1]
-        p = int(rng.choice(cands)); nchild[p] += 1
-        out.append(" ".join(["body", str(b), str(p), str(rng.choice(["PIN", "UNIVERSAL", "BALL"]))] + tmpl[4:]))
-    out += [l for l in lines if l.startswith("nf ") or l.startswith("gravity")]
-    return "\n".join(out) + "\n"
 
 
 @pytest.mark.parametrize("seed", range(12))
